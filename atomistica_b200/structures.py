@@ -1,0 +1,98 @@
+"""Synthetic structure builders for tests and bench.py (ASE is not available in this image).
+
+Conventions follow ase.lattice.cubic (used by the reference's tests): cubic
+conventional cells replicated `size` times, cell rows are the cell vectors.
+"""
+import numpy as np
+
+_FCC = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
+_DIA = np.concatenate([_FCC, _FCC + 0.25])
+
+
+class Atoms:
+    """Minimal stand-in for ase.Atoms: positions, numbers/symbols, cell (rows = vectors), pbc."""
+
+    def __init__(self, symbols, positions, cell, pbc=True):
+        self.symbols = list(symbols)
+        self.positions = np.array(positions, dtype=np.float64).reshape(-1, 3)
+        cell = np.array(cell, dtype=np.float64)
+        self.cell = np.diag(cell) if cell.shape == (3,) else cell
+        self.pbc = np.broadcast_to(np.asarray(pbc, dtype=bool), (3,)).copy()
+        self.calc = None
+
+    def __len__(self):
+        return len(self.positions)
+
+    def copy(self):
+        return Atoms(self.symbols, self.positions.copy(), self.cell.copy(), self.pbc.copy())
+
+    def get_volume(self):
+        return abs(np.linalg.det(self.cell))
+
+    def get_atomic_numbers(self):
+        from .elements import atomic_numbers
+        return np.array([atomic_numbers[s] for s in self.symbols], dtype=np.int32)
+
+    def set_cell(self, cell, scale_atoms=False):
+        cell = np.array(cell, dtype=np.float64)
+        cell = np.diag(cell) if cell.shape == (3,) else cell
+        if scale_atoms:
+            s = np.linalg.solve(self.cell.T, self.positions.T).T
+            self.positions = s @ cell
+        self.cell = cell
+
+    def rattle(self, stdev, seed=42):
+        rng = np.random.RandomState(seed)
+        self.positions = self.positions + rng.normal(scale=stdev, size=self.positions.shape)
+
+    def repeat(self, rep):
+        rep = np.broadcast_to(np.asarray(rep, dtype=int), (3,))
+        pos, sym = [], []
+        for i in range(rep[0]):
+            for j in range(rep[1]):
+                for k in range(rep[2]):
+                    pos.append(self.positions + np.array([i, j, k]) @ self.cell)
+                    sym += self.symbols
+        return Atoms(sym, np.concatenate(pos), self.cell * rep[:, None], self.pbc)
+
+    # ASE-style calculator access
+    def get_potential_energy(self):
+        return self.calc.get_potential_energy(self)
+
+    def get_forces(self):
+        return self.calc.get_forces(self)
+
+    def get_stress(self):
+        return self.calc.get_stress(self)
+
+
+def _cubic(basis, symbols, a, size):
+    size = np.broadcast_to(np.asarray(size, dtype=int), (3,))
+    ii, jj, kk = np.meshgrid(np.arange(size[0]), np.arange(size[1]), np.arange(size[2]), indexing='ij')
+    origins = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], axis=1).astype(np.float64)
+    pos = (origins[:, None, :] + basis[None, :, :]).reshape(-1, 3) * a
+    sym = list(symbols) * len(origins)
+    return Atoms(sym, pos, a * size.astype(np.float64), True)
+
+
+def diamond(symbol, a, size=(1, 1, 1)):
+    return _cubic(_DIA, [symbol] * 8, a, size)
+
+
+def fcc(symbol, a, size=(1, 1, 1)):
+    return _cubic(_FCC, [symbol] * 4, a, size)
+
+
+def b3(symbols, a, size=(1, 1, 1)):
+    """zincblende: first species on the fcc sites, second on the (1/4,1/4,1/4)-shifted sites"""
+    return _cubic(_DIA, [symbols[0]] * 4 + [symbols[1]] * 4, a, size)
+
+
+def maxwell_boltzmann(masses_amu, T, seed=12345):
+    """velocities in Angstrom/fs-free internal units: returns v in sqrt(eV/amu)"""
+    kB = 8.617333262e-5
+    rng = np.random.RandomState(seed)
+    m = np.asarray(masses_amu, dtype=np.float64)
+    v = rng.normal(size=(len(m), 3)) * np.sqrt(kB * T / m)[:, None]
+    v -= (v * m[:, None]).sum(axis=0) / m.sum()
+    return v

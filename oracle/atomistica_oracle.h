@@ -1,0 +1,138 @@
+/*
+ * CPU ORACLE -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement of the Atomistica hot path (neighbour list, generic
+ * bond-order potentials, REBO2, tabulated alloy EAM).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  The product (atomistica_b200/) never links, imports
+ * or calls it.
+ *
+ * Parity status: the Fortran reference cannot be compiled in the build
+ * container (no Fortran compiler), so this oracle is pinned against the
+ * reference's own known-answer tests (tests/golden/kat.json, generated from
+ * /root/reference/tests/*.py) rather than against raw reference output.
+ *
+ * Array conventions are the Fortran host's: r(3,nat) contiguous per atom,
+ * Abox(3,3) column-major (columns are the cell vectors), 1-based atom indices
+ * in `neighbors`, 1-based inclusive seed/last slot ranges, dc(3,slot).
+ */
+#ifndef ATOMISTICA_ORACLE_H
+#define ATOMISTICA_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- neighbour list: src/python/f90/python_neighbors.f90:570-959 ---- */
+
+typedef struct {
+  int n_cells[3];
+  int dx, dy, dz;          /* stencil half widths */
+  double rec_cell_size[9]; /* column-major (3,3) */
+} orc_binning_t;
+
+int orc_binning_init(const double *Abox, const double *Bbox, double cutoff, double bin_size,
+                     orc_binning_t *b);
+
+/* returns number of pairs, or -1 on "Neighbor list overflow" (capacity = size of neighbors[]) */
+long orc_nl_build(int nat, const double *r, const double *Abox, const double *Bbox, const int *pbc,
+                  double cutoff, long capacity, intptr_t *seed, intptr_t *last, int *neighbors,
+                  int *dc);
+
+/* ---- simple_spline: src/support/simple_spline.f90 ---- */
+
+typedef struct {
+  int n;
+  double x0, dx, cut;
+  const double *y, *c1, *c2, *c3, *d1, *d2, *d3;
+} orc_spline_t;
+
+/* ---- tabulated alloy EAM: src/potentials/eam/tabulated_alloy_eam.f90:423-627 ---- */
+
+int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double *Abox,
+                              const int *eldb, const intptr_t *seed, const intptr_t *last,
+                              const int *neighbors, const int *dc, int ndb, const orc_spline_t *fF,
+                              const orc_spline_t *frho, const orc_spline_t *fphi, double cutoff,
+                              const int *mask, double *epot, double *f, double *wpot,
+                              double *epot_per_at, double *wpot_per_at);
+
+/* ---- generic bond-order potentials: src/potentials/bop/bop_kernel.f90 ---- */
+
+enum { ORC_TERSOFF = 1, ORC_KUMAGAI = 2, ORC_BRENNER = 3 };
+
+/* pair-parameter rows */
+enum {
+  /* Tersoff */ OT_A = 0, OT_B, OT_XI, OT_LAMBDA, OT_MU, OT_OMEGA, OT_MUBO,
+  /* Kumagai */ OK_A = 0, OK_B, OK_LAMBDA1, OK_LAMBDA2, OK_ALPHA,
+  /* Brenner */ OB_D0 = 0, OB_R0, OB_S, OB_BETA, OB_GAMMA, OB_C, OB_D, OB_H, OB_MU, OB_N
+};
+/* element-parameter rows */
+enum {
+  /* Tersoff */ OTE_BETA = 0, OTE_N, OTE_C, OTE_D, OTE_H,
+  /* Kumagai */ OKE_ETA = 0, OKE_DELTA, OKE_C1, OKE_C2, OKE_C3, OKE_C4, OKE_C5, OKE_H
+};
+
+typedef struct {
+  int kind;
+  int nel;
+  double pp[12][6]; /* pair parameters [row][pair-1] */
+  double ep[8][3];  /* element parameters [row][el-1] */
+  int ip[6];        /* integer pair parameter: Tersoff/Brenner m, Kumagai beta */
+  double r1[6], r2[6];
+} orc_bop_params_t;
+
+int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, const double *r,
+                              const double *Abox, const int *el, const intptr_t *seed,
+                              const intptr_t *last, const int *neighbors, const int *dc,
+                              const int *mask, double *epot, double *f, double *wpot,
+                              double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                              double *wpot_per_at, double *wpot_per_bond);
+
+/* ---- REBO2: src/potentials/bop/rebo2/ ---- */
+
+typedef struct {
+  int nx, ny;
+  const double *coeff; /* Fortran coeff(nboxs,4,4) */
+} orc_table2d_t;
+
+typedef struct {
+  int nx, ny, nz;
+  const double *coeff; /* Fortran coeff(nboxs,4,4,4) */
+} orc_table3d_t;
+
+typedef struct {
+  double cc_B1, cc_B2, cc_B3, cc_beta1, cc_beta2, cc_beta3, cc_Q, cc_A, cc_alpha;
+  double ch_B1, ch_beta1, ch_Q, ch_A, ch_alpha;
+  double hh_B1, hh_beta1, hh_Q, hh_A, hh_alpha;
+  double cc_g_theta[6];
+  double cc_g1_coeff[18]; /* Fortran c(6,3) */
+  double cc_g2_coeff[18];
+  double spgh[18];        /* Fortran SPGH(6,3) */
+  int igh[25];
+  double conalp;
+  double conear[36];      /* Fortran conear(6,6) */
+  double conpe[3], conan[3], conpf[3];
+  double cut_in_l[10], cut_in_h[10], cut_in_h2[10];
+  int with_dihedral;
+  orc_table3d_t Fcc, Fch, Fhh, Tcc;
+  orc_table2d_t Pcc, Pch;
+} orc_rebo2_params_t;
+
+void orc_table2d_eval(const orc_table2d_t *t, double nhi, double nci, double *v, double *dvdh,
+                      double *dvdc);
+void orc_table3d_eval(const orc_table3d_t *t, double nti, double ntj, double nconj, double *v,
+                      double *dvdi, double *dvdj, double *dvdc);
+
+int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natloc,
+                                const double *r, const double *Abox, const int *ktyp,
+                                const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                const int *dc, double *epot, double *f, double *wpot,
+                                double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                double *wpot_per_at, double *wpot_per_bond);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

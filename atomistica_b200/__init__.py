@@ -1,0 +1,11 @@
+"""atomistica_b200 -- B200-native hot path of Atomistica behind the reference's plugin API.
+
+    from atomistica_b200 import Tersoff, Kumagai, Brenner, Rebo2, TabulatedAlloyEAM
+
+are drop-ins for `atomistica.Tersoff()` etc. (src/python/atomistica/aseinterface.py); the
+low-level mirror of the `_atomistica` extension lives in `atomistica_b200.native`.
+Importing this package does not touch the GPU; the shared library is loaded on first use and
+there is no CPU fallback.
+"""
+from .aseinterface import Atomistica, Brenner, Kumagai, Rebo2, TabulatedAlloyEAM, Tersoff  # noqa: F401
+from .parameters import *  # noqa: F401,F403

@@ -1,0 +1,118 @@
+"""ctypes binding of libatomistica_b200.so (the C-ABI in include/atomistica_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and if no
+CUDA device is present every compute entry point raises RuntimeError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libatomistica_b200.so')
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_ssize_p = C.POINTER(C.c_ssize_t)
+
+
+class AtxSpline(C.Structure):
+    _fields_ = [('n', C.c_int), ('x0', C.c_double), ('dx', C.c_double)] + \
+        [(k, c_double_p) for k in ('y', 'coeff1', 'coeff2', 'coeff3', 'dcoeff1', 'dcoeff2', 'dcoeff3')]
+
+
+MAX_EL, MAX_PAIRS = 3, 6
+
+
+class AtxBopParams(C.Structure):
+    _fields_ = [('kind', C.c_int), ('nel', C.c_int), ('Z', C.c_int * MAX_EL)] + \
+        [(k, C.c_double * MAX_PAIRS) for k in ('A', 'B', 'xi', 'lambda_', 'mu', 'omega', 'mubo')] + \
+        [('m', C.c_int * MAX_PAIRS)] + \
+        [(k, C.c_double * MAX_PAIRS) for k in ('D0', 'r0', 'S', 'pbeta', 'gamma', 'pc', 'pd', 'ph', 'pn',
+                                               'r1', 'r2')] + \
+        [(k, C.c_double * MAX_EL) for k in ('beta', 'n', 'c', 'd', 'h', 'eta', 'delta',
+                                            'c1', 'c2', 'c3', 'c4', 'c5')]
+
+
+class AtxRebo2Params(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        'cc_B1', 'cc_B2', 'cc_B3', 'cc_beta1', 'cc_beta2', 'cc_beta3', 'cc_Q', 'cc_A', 'cc_alpha',
+        'ch_B1', 'ch_beta1', 'ch_Q', 'ch_A', 'ch_alpha', 'hh_B1', 'hh_beta1', 'hh_Q', 'hh_A', 'hh_alpha')] + [
+        ('cc_g_theta', C.c_double * 6), ('cc_g1_coeff', C.c_double * 18), ('cc_g2_coeff', C.c_double * 18),
+        ('spgh', C.c_double * 18), ('igh', C.c_int * 25), ('conalp', C.c_double), ('conear', C.c_double * 36),
+        ('conpe', C.c_double * 3), ('conan', C.c_double * 3), ('conpf', C.c_double * 3),
+        ('cut_in_l', C.c_double * 10), ('cut_in_h', C.c_double * 10), ('cut_in_h2', C.c_double * 10),
+        ('with_dihedral', C.c_int)] + [(k, c_double_p) for k in ('Fcc', 'Fch', 'Fhh', 'Tcc', 'Pcc', 'Pch')]
+
+
+# every symbol include/atomistica_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    'atx_ctx_create', 'atx_ctx_destroy', 'atx_ctx_synchronize', 'atx_last_error', 'atx_version',
+    'atx_kernel_launches',
+    'atx_particles_create', 'atx_particles_destroy', 'atx_particles_set_cell', 'atx_particles_set_positions',
+    'atx_particles_set_elements', 'atx_particles_set_positions_device',
+    'atx_neighbors_create', 'atx_neighbors_destroy', 'atx_neighbors_request_interaction_range',
+    'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_get_info',
+    'atx_neighbors_copy_to_host',
+    'atx_eam_create', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
+    'atx_bop_create', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
+    'atx_rebo2_create', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',
+    'atx_md_create', 'atx_md_destroy', 'atx_md_run', 'atx_md_get_state', 'atx_md_get_stats',
+    'atx_host_spline_init', 'atx_host_gaussn', 'atx_host_table2d_init', 'atx_host_table3d_init',
+    'atx_host_rebo2_g_spline',
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                'libatomistica_b200.so is missing (%s). Build it with `python -m atomistica_b200.build`; '
+                'there is no CPU fallback.' % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.atx_version.restype = C.c_char_p
+        _lib.atx_kernel_launches.restype = C.c_longlong
+    return _lib
+
+
+def last_error():
+    buf = C.create_string_buffer(2048)
+    lib().atx_last_error(buf, 2048)
+    return buf.value.decode(errors='replace')
+
+
+def check(err):
+    """Error convention of the reference's C layer (src/python/c/py_f.c:36-47): RuntimeError."""
+    if err != 0:
+        raise RuntimeError(last_error() or 'atomistica_b200 error %d' % err)
+
+
+def dptr(a):
+    return None if a is None else a.ctypes.data_as(c_double_p)
+
+
+def iptr(a):
+    return None if a is None else a.ctypes.data_as(c_int_p)
+
+
+_ctx = {}
+
+
+def context(device=0):
+    """One context (device + stream) per device ordinal, created on first use."""
+    if device not in _ctx:
+        h = C.c_void_p()
+        check(lib().atx_ctx_create(C.c_int(device), C.byref(h)))
+        _ctx[device] = h
+    return _ctx[device]
+
+
+def kernel_launches(reset=False):
+    return int(lib().atx_kernel_launches(C.c_int(1 if reset else 0)))
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,134 @@
+"""ASE-style calculator front end, mirroring src/python/atomistica/aseinterface.py.
+
+ASE itself is not importable in this image, so `Atomistica` implements the part of the
+ase.calculators.calculator.Calculator protocol the reference's wrapper uses
+(get_potential_energy / get_forces / get_stress / get_potential_energies / get_stresses on an
+atoms object exposing positions, cell, pbc, symbols) with the same update logic
+(aseinterface.py:227-352): exact comparison of cell/pbc/positions, re-initialisation when the
+number or type of atoms changes, stress = voigt(wpot)/volume.
+"""
+import numpy as np
+
+from . import native
+from .elements import atomic_numbers
+
+
+class Atomistica:
+    potential_class = None
+    avgn = 100
+
+    def __init__(self, potentials=None, avgn=None, **kwargs):
+        self.pots = potentials if potentials is not None else [self.potential_class(**kwargs)]
+        if avgn is not None:
+            self.avgn = avgn
+        self.particles = None
+        self.nl = None
+        self.mask = None
+        self.results = {}
+        self.kwargs = kwargs
+        self.compute_epot_per_bond = False
+        self.compute_f_per_bond = False
+        self.compute_wpot_per_bond = False
+        self.epot_per_bond = self.f_per_bond = self.wpot_per_bond = None
+
+    def todict(self):
+        return self.kwargs
+
+    # aseinterface.py:227-289
+    def initialize(self, atoms):
+        if self.mask is not None and len(self.mask) != len(atoms):
+            raise RuntimeError('Length of mask array (= {0}) does not equal number of atoms (= {1}).'
+                               .format(len(self.mask), len(atoms)))
+        self.particles = native.Particles()
+        self.particles.allocate(len(atoms))
+        self.particles.set_cell(atoms.cell, atoms.pbc)
+        self.particles.Z[:] = [atomic_numbers[s] for s in atoms.symbols]
+        self.particles.coordinates[:, :] = atoms.positions
+        self.particles.I_changed_positions()
+        self.particles.update_elements()
+        self.nl = native.Neighbors(self.avgn)
+        for pot in self.pots:
+            pot.bind_to(self.particles, self.nl)
+
+    def set_mask(self, mask):
+        self.mask = mask
+
+    def set_per_bond(self, epot=None, f=None, wpot=None):
+        if epot is not None:
+            self.compute_epot_per_bond = epot
+        if f is not None:
+            self.compute_f_per_bond = f
+        if wpot is not None:
+            self.compute_wpot_per_bond = wpot
+
+    # aseinterface.py:300-333
+    def update(self, atoms):
+        Z = np.array([atomic_numbers[s] for s in atoms.symbols], dtype=np.int32)
+        if self.particles is None or len(self.particles.Z) != len(atoms):
+            self.initialize(atoms)
+        elif np.any(self.particles.Z != Z):
+            self.initialize(atoms)
+        if np.any(self.particles.cell != atoms.cell) or np.any(self.particles.pbc != atoms.pbc):
+            self.particles.set_cell(atoms.cell, atoms.pbc)
+        positions = self.particles.coordinates
+        if np.any(positions != atoms.positions):
+            positions[:, :] = atoms.positions
+            self.particles.I_changed_positions()
+
+    # aseinterface.py:355-440
+    def calculate(self, atoms, properties=('energy',)):
+        self.update(atoms)
+        epot = 0.0
+        forces = np.zeros((len(self.particles), 3))
+        wpot = np.zeros((3, 3))
+        per_at_e = 'energies' in properties
+        per_at_w = 'stresses' in properties
+        kwargs = dict(epot_per_at=per_at_e, epot_per_bond=self.compute_epot_per_bond,
+                      f_per_bond=self.compute_f_per_bond, wpot_per_at=per_at_w,
+                      wpot_per_bond=self.compute_wpot_per_bond)
+        if self.mask is not None:
+            kwargs['mask'] = self.mask
+        epa = wpa = None
+        for pot in self.pots:
+            _e, _f, _w, epa, self.epot_per_bond, self.f_per_bond, wpa, self.wpot_per_bond = \
+                pot.energy_and_forces(self.particles, self.nl, forces=forces, **kwargs)
+            epot += _e
+            wpot += _w
+        volume = atoms.get_volume()
+        self.results = dict(energy=epot, free_energy=epot, forces=forces, wpot=wpot)
+        self.results['stress'] = np.array([wpot[0, 0], wpot[1, 1], wpot[2, 2], (wpot[1, 2] + wpot[2, 1]) / 2,
+                                           (wpot[0, 2] + wpot[2, 0]) / 2, (wpot[0, 1] + wpot[1, 0]) / 2]) / volume
+        if per_at_e:
+            self.results['energies'] = epa
+        if per_at_w:
+            self.results['stresses'] = np.transpose([wpa[:, 0, 0], wpa[:, 1, 1], wpa[:, 2, 2],
+                                                     (wpa[:, 1, 2] + wpa[:, 2, 1]) / 2,
+                                                     (wpa[:, 0, 2] + wpa[:, 2, 0]) / 2,
+                                                     (wpa[:, 0, 1] + wpa[:, 1, 0]) / 2]) / volume
+        return self.results
+
+    def get_potential_energy(self, atoms):
+        return self.calculate(atoms)['energy']
+
+    def get_forces(self, atoms):
+        return self.calculate(atoms)['forces']
+
+    def get_stress(self, atoms):
+        return self.calculate(atoms)['stress']
+
+    def get_potential_energies(self, atoms):
+        return self.calculate(atoms, ('energies',))['energies']
+
+    def get_stresses(self, atoms):
+        return self.calculate(atoms, ('stresses',))['stresses']
+
+
+def _calculator(cls):
+    return type(cls.__name__, (Atomistica,), dict(potential_class=cls, __doc__=cls.__doc__))
+
+
+Tersoff = _calculator(native.Tersoff)
+Kumagai = _calculator(native.Kumagai)
+Brenner = _calculator(native.Brenner)
+Rebo2 = _calculator(native.Rebo2)
+TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)

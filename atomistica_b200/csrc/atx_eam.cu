@@ -1,0 +1,406 @@
+// Tabulated alloy EAM on the device.
+//
+// Replaces tabulated_alloy_eam_energy_and_forces_kernel
+// (src/potentials/eam/tabulated_alloy_eam.f90:423-627) and the spline evaluators it calls
+// (src/support/simple_spline.f90:373-434 func, 467-528 dfunc, 536-614 f_and_df).
+//
+// Two gather passes, no atomics, deterministic:
+//   k_eam_density: rho_i = sum_j rho_j(r_ij), clamp, F(rho_i), F'(rho_i)      (the reference's pass 1)
+//   k_eam_force:   f_i = sum_j (c_ij + c_ji) dr_ij with
+//                    c_ij = -(F'_i rho'_j(r) + (phi' - phi/r)/r)/r   (i's visit of j, :594-595)
+//                    c_ji = -(F'_j rho'_i(r) + (phi' - phi/r)/r)/r   (j's visit of i, scattered
+//                                                                     with "- df" in the reference)
+// which is the reference's scatter form summed per receiving atom.
+// A group of LANES threads serves one atom; lanes stride its list entries and reduce by shuffles.
+#include "atx_potential_common.cuh"
+
+struct DSpline {
+  int n;
+  double x0, dx, cut;
+  const double4 *c;  // {y, coeff1, coeff2, coeff3} per interval
+  const double4 *d;  // {dcoeff1, dcoeff2, dcoeff3, 0}
+};
+
+#define EAM_MAX_DB 10
+
+struct EamDev {
+  int ndb;
+  double cutoff_sq;
+  int el2db[32];
+  DSpline fF[EAM_MAX_DB];
+  DSpline frho[EAM_MAX_DB];
+  DSpline fphi[EAM_MAX_DB * EAM_MAX_DB];
+};
+
+struct atx_eam {
+  atx_ctx *ctx = nullptr;
+  int ndb = 0;
+  double cutoff = 0.0;
+  EamDev host{};
+  DevBuf<EamDev> dev;
+  std::vector<DevBuf<double4> *> tables;
+  DevBuf<double> dF, Fe;
+  DevBuf<int> flag;
+  PotScratch sc;
+  bool bound = false;
+  ~atx_eam() {
+    for (auto *t : tables) delete t;
+  }
+};
+
+// func (no extrapolation): sets *err when x is outside the table
+__device__ __forceinline__ double spl_f(const DSpline &s, double x, int *err) {
+  double xf;
+  int i;
+  if (x == s.cut) {
+    xf = (double)s.n;
+    i = s.n - 1;
+  } else {
+    xf = (x - s.x0) / s.dx + 1.0;
+    i = (int)floor(xf);
+  }
+  if (i < 1 || i >= s.n) {
+    *err = 1;
+    return 1.0;
+  }
+  double B = xf - (double)i;
+  double4 c = atx_ld4(&s.c[i - 1]);
+  return c.x + B * (c.y + B * (c.z + B * c.w));
+}
+
+__device__ __forceinline__ double spl_df(const DSpline &s, double x, int *err) {
+  double xf;
+  int i;
+  if (x == s.cut) {
+    xf = (double)s.n;
+    i = s.n - 1;
+  } else {
+    xf = (x - s.x0) / s.dx + 1.0;
+    i = (int)floor(xf);
+  }
+  if (i < 1 || i >= s.n) {
+    *err = 1;
+    return 1.0;
+  }
+  double B = xf - (double)i;
+  double4 d = atx_ld4(&s.d[i - 1]);
+  return d.x + B * (d.y + B * d.z);
+}
+
+// f_and_df(extrapolate=.true.)
+__device__ __forceinline__ void spl_f_df_x(const DSpline &s, double x, double &f, double &df) {
+  double xf = (x - s.x0) / s.dx + 1.0;
+  int i = (int)floor(xf);
+  if (i < 1) i = 1;
+  else if (i >= s.n) i = s.n - 1;
+  double B = xf - (double)i;
+  double4 c = atx_ld4(&s.c[i - 1]);
+  double4 d = atx_ld4(&s.d[i - 1]);
+  f = c.x + B * (c.y + B * (c.z + B * c.w));
+  df = d.x + B * (d.y + B * d.z);
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(128)
+k_eam_density(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
+              const long long *__restrict__ seed, const int2 *__restrict__ list,
+              const int *__restrict__ mask, double *__restrict__ dF, double *__restrict__ Fe,
+              int *__restrict__ flag) {
+  const int gpb = 128 / LANES;
+  int s = blockIdx.x * gpb + threadIdx.x / LANES;
+  int lane = threadIdx.x % LANES;
+  const bool valid = s < nat;
+  double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
+  int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  const bool active = dbi > 0 && (!mask || mask[s] != 0);
+  double rho = 0.0;
+  int err = 0;
+  long long b = active ? seed[s] : 0, e = active ? seed[s + 1] : 0;
+  const double cutoff_sq = T->cutoff_sq;
+  for (long long a = b + lane; a < e; a += LANES) {
+    int2 en = list[a];
+    double4 pj = pos4[en.x];
+    int dbj = T->el2db[(int)pj.w];
+    if (dbj <= 0) continue;
+    double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    if (en.y != ATX_SHIFT_ZERO) {
+      int sx, sy, sz;
+      atx_unpack_shift(en.y, sx, sy, sz);
+      double ax, ay, az;
+      atx_image_vector(A, sx, sy, sz, ax, ay, az);
+      dx += ax; dy += ay; dz += az;
+    }
+    double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 < cutoff_sq) rho += spl_f(T->frho[dbj - 1], sqrt(r2), &err);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    rho += __shfl_xor_sync(0xffffffffu, rho, o);
+    err |= __shfl_xor_sync(0xffffffffu, err, o);
+  }
+  if (lane == 0 && valid) {
+    double F = 0.0, dFi = 0.0;
+    if (active) {
+      if (rho < 0.0) rho = 0.0;
+      spl_f_df_x(T->fF[dbi - 1], rho, F, dFi);
+    }
+    dF[s] = dFi;
+    Fe[s] = F;
+    if (err) atomicOr(flag, 1);
+  }
+}
+
+template <int LANES, bool PER_AT>
+__global__ void __launch_bounds__(128)
+k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
+            const long long *__restrict__ seed, const int2 *__restrict__ list,
+            const int *__restrict__ mask, const double *__restrict__ dF,
+            const double *__restrict__ Fe, double *__restrict__ f, double *__restrict__ epa,
+            double *__restrict__ wpa, double *__restrict__ partials, int *__restrict__ flag) {
+  __shared__ double red[ATX_NSUM * 4];
+  const int gpb = 128 / LANES;
+  int s = blockIdx.x * gpb + threadIdx.x / LANES;
+  int lane = threadIdx.x % LANES;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+
+  const bool valid = s < nat;
+  double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
+  int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  double fx = 0.0, fy = 0.0, fz = 0.0, e = 0.0;
+  double wxx = 0, wyy = 0, wzz = 0, wxy = 0, wxz = 0, wyz = 0;    // total virial, i-visits
+  double pxx = 0, pyy = 0, pzz = 0, pxy = 0, pxz = 0, pyz = 0;    // per-atom virial
+  int err = 0;
+  if (dbi > 0) {
+    bool act_i = (!mask || mask[s] != 0);
+    double dFi = dF[s];
+    const double cutoff_sq = T->cutoff_sq;
+    const DSpline &rho_i = T->frho[dbi - 1];
+    long long b = seed[s], en_ = seed[s + 1];
+    for (long long a = b + lane; a < en_; a += LANES) {
+      int2 en = list[a];
+      double4 pj = pos4[en.x];
+      int dbj = T->el2db[(int)pj.w];
+      if (dbj <= 0) continue;
+      double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+      if (en.y != ATX_SHIFT_ZERO) {
+        int sx, sy, sz;
+        atx_unpack_shift(en.y, sx, sy, sz);
+        double ax, ay, az;
+        atx_image_vector(A, sx, sy, sz, ax, ay, az);
+        dx += ax; dy += ay; dz += az;
+      }
+      double r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 >= cutoff_sq) continue;
+      double r = sqrt(r2);
+      double rinv = 1.0 / r;
+      bool act_j = (!mask || mask[en.x] != 0);
+      double phi, dphi;
+      spl_f_df_x(T->fphi[(dbi - 1) + T->ndb * (dbj - 1)], r, phi, dphi);
+      double pair = (dphi - phi * rinv) * rinv;
+      double c = 0.0, cij = 0.0;
+      if (act_i) {
+        double drho_j = spl_df(T->frho[dbj - 1], r, &err);
+        cij = -(dFi * drho_j + pair) * rinv;
+        c = cij;
+        e += phi * rinv;
+      }
+      if (act_j) {
+        double drho_i = spl_df(rho_i, r, &err);
+        c += -(dF[en.x] * drho_i + pair) * rinv;
+      }
+      fx += c * dx; fy += c * dy; fz += c * dz;
+      // wij = -outer(dr, df), df = cij*dr (tabulated_alloy_eam.f90:598-599)
+      wxx -= cij * dx * dx; wyy -= cij * dy * dy; wzz -= cij * dz * dz;
+      wxy -= cij * dx * dy; wxz -= cij * dx * dz; wyz -= cij * dy * dz;
+      if (PER_AT) {
+        double h = -0.5 * c;
+        pxx += h * dx * dx; pyy += h * dy * dy; pzz += h * dz * dz;
+        pxy += h * dx * dy; pxz += h * dx * dz; pyz += h * dy * dz;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+    err |= __shfl_xor_sync(0xffffffffu, err, o);
+    if (PER_AT) {
+      pxx += __shfl_xor_sync(0xffffffffu, pxx, o);
+      pyy += __shfl_xor_sync(0xffffffffu, pyy, o);
+      pzz += __shfl_xor_sync(0xffffffffu, pzz, o);
+      pxy += __shfl_xor_sync(0xffffffffu, pxy, o);
+      pxz += __shfl_xor_sync(0xffffffffu, pxz, o);
+      pyz += __shfl_xor_sync(0xffffffffu, pyz, o);
+    }
+  }
+  if (lane == 0 && valid) {
+    f[3 * s] = fx; f[3 * s + 1] = fy; f[3 * s + 2] = fz;
+    double ei = e + Fe[s];
+    if (epa) epa[s] = ei;
+    if (PER_AT) {
+      double *w = &wpa[9 * (size_t)s];
+      w[0] = pxx; w[1] = pxy; w[2] = pxz;
+      w[3] = pxy; w[4] = pyy; w[5] = pyz;
+      w[6] = pxz; w[7] = pyz; w[8] = pzz;
+    }
+    acc[0] = ei;
+    if (err) atomicOr(flag, 1);
+  }
+  // every lane carries its share of the total virial into the block sum
+  acc[1] = wxx; acc[2] = wxy; acc[3] = wxz;
+  acc[4] = wxy; acc[5] = wyy; acc[6] = wyz;
+  acc[7] = wxz; acc[8] = wyz; acc[9] = wzz;
+  atx_block_sum<ATX_NSUM, 128>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)blockIdx.x * ATX_NSUM + k] = acc[k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+
+static int upload_spline(atx_eam *pot, const atx_spline &s, DSpline &d) {
+  int ni = s.n - 1;
+  std::vector<double4> c(ni), dd(ni);
+  for (int i = 0; i < ni; i++) {
+    c[i] = make_double4(s.y[i], s.coeff1[i], s.coeff2[i], s.coeff3[i]);
+    dd[i] = make_double4(s.dcoeff1[i], s.dcoeff2[i], s.dcoeff3[i], 0.0);
+  }
+  auto *bc = new DevBuf<double4>();
+  auto *bd = new DevBuf<double4>();
+  pot->tables.push_back(bc);
+  pot->tables.push_back(bd);
+  ATX_PASS(bc->reserve(ni));
+  ATX_PASS(bd->reserve(ni));
+  ATX_CUDA(cudaMemcpy(bc->ptr, c.data(), sizeof(double4) * ni, cudaMemcpyHostToDevice));
+  ATX_CUDA(cudaMemcpy(bd->ptr, dd.data(), sizeof(double4) * ni, cudaMemcpyHostToDevice));
+  d.n = s.n;
+  d.x0 = s.x0;
+  d.dx = s.dx;
+  d.cut = s.x0 + s.dx * (s.n - 1);
+  d.c = bc->ptr;
+  d.d = bd->ptr;
+  return 0;
+}
+
+extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const atx_spline *frho,
+                              const atx_spline *fphi, double cutoff, atx_eam **out) {
+  if (ndb < 1 || ndb > EAM_MAX_DB) {
+    atx_set_error("TabulatedAlloyEAM supports 1.." + std::to_string(EAM_MAX_DB) + " elements.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  ATX_CUDA(cudaSetDevice(ctx->device));
+  atx_eam *pot = new atx_eam();
+  pot->ctx = ctx;
+  pot->ndb = ndb;
+  pot->cutoff = cutoff;
+  pot->host.ndb = ndb;
+  pot->host.cutoff_sq = cutoff * cutoff;
+  for (int i = 0; i < ndb; i++) {
+    ATX_PASS(upload_spline(pot, fF[i], pot->host.fF[i]));
+    ATX_PASS(upload_spline(pot, frho[i], pot->host.frho[i]));
+  }
+  for (int j = 0; j < ndb; j++)
+    for (int i = 0; i < ndb; i++)
+      ATX_PASS(upload_spline(pot, fphi[i + ndb * j], pot->host.fphi[i + ndb * j]));
+  for (int k = 0; k < 32; k++) pot->host.el2db[k] = -1;
+  ATX_PASS(pot->dev.reserve(1));
+  ATX_PASS(pot->flag.reserve(4));
+  *out = pot;
+  return 0;
+}
+
+extern "C" int atx_eam_destroy(atx_eam *pot) {
+  delete pot;
+  return 0;
+}
+
+extern "C" int atx_eam_bind_to(atx_eam *pot, atx_particles *p, atx_neighbors *nl, int nel,
+                               const int *el2db) {
+  if (nel > 31) {
+    atx_set_error("Too many particle element ids.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  for (int k = 0; k < 32; k++) pot->host.el2db[k] = -1;
+  bool any = false;
+  for (int k = 0; k < nel; k++) {
+    pot->host.el2db[k + 1] = el2db[k];
+    any = any || el2db[k] > 0;
+  }
+  ATX_CUDA(cudaMemcpy(pot->dev.ptr, &pot->host, sizeof(EamDev), cudaMemcpyHostToDevice));
+  if (any && nl) ATX_PASS(atx_neighbors_request_interaction_range(nl, pot->cutoff));
+  pot->bound = true;
+  return 0;
+}
+
+// device-resident evaluation (sorted order); used by library mode and the MD driver
+int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
+                           const int *mask_sorted, const PotOut &o) {
+  atx_ctx *ctx = pot->ctx;
+  cudaStream_t st = ctx->stream;
+  int nat = nl->nat;
+  ATX_PASS(pot->dF.reserve(nat + 1));
+  ATX_PASS(pot->Fe.reserve(nat + 1));
+  // lanes per atom from the mean list length
+  double mean = nat > 0 ? (double)nl->npairs / nat : 0.0;
+  int lanes = mean > 48 ? 16 : (mean > 20 ? 8 : 4);
+  int gpb = 128 / lanes;
+  int nblocks = (nat + gpb - 1) / gpb;
+  if (nblocks < 1) nblocks = 1;
+  ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
+  ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+#define EAM_LAUNCH(L)                                                                             \
+  do {                                                                                            \
+    k_eam_density<L><<<nblocks, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,           \
+                                              nl->seed.ptr, nl->list.ptr, mask_sorted,            \
+                                              pot->dF.ptr, pot->Fe.ptr, pot->flag.ptr);           \
+    ATX_LAUNCHED();                                                                               \
+    if (o.wpa)                                                                                    \
+      k_eam_force<L, true><<<nblocks, 128, 0, st>>>(                                              \
+          nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \
+          pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr);      \
+    else                                                                                          \
+      k_eam_force<L, false><<<nblocks, 128, 0, st>>>(                                             \
+          nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \
+          pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr);      \
+    ATX_LAUNCHED();                                                                               \
+  } while (0)
+  if (lanes == 16) EAM_LAUNCH(16);
+  else if (lanes == 8) EAM_LAUNCH(8);
+  else EAM_LAUNCH(4);
+#undef EAM_LAUNCH
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums));
+  return 0;
+}
+
+int atx_eam_check_flag(atx_eam *pot) {
+  int h = 0;
+  ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, pot->ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(pot->ctx->stream));
+  if (h) {
+    atx_set_error("simple_spline: x outside of the defined interval (density or pair table).");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  return 0;
+}
+
+extern "C" int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
+                                         const int *mask, double *epot, double *f, double *wpot,
+                                         double *epot_per_at, double *wpot_per_at) {
+  if (!pot->bound) {
+    atx_set_error("TabulatedAlloyEAM: bind_to has not been called.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  ATX_PASS(atx_neighbors_update(nl, p));
+  PotOut o;
+  ATX_PASS(atx_prepare_out(pot->ctx, nl, pot->sc, epot_per_at != nullptr, wpot_per_at != nullptr, o));
+  const int *mask_sorted = nullptr;
+  ATX_PASS(atx_prepare_mask(pot->ctx, nl, pot->sc, mask, &mask_sorted));
+  ATX_PASS(atx_eam_compute_device(pot, p, nl, mask_sorted, o));
+  ATX_PASS(atx_eam_check_flag(pot));
+  return atx_finish_to_host(pot->ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
+}

@@ -1,0 +1,528 @@
+// Cell-list neighbour build on the device.
+//
+// Replaces the bodies of
+//   neighbors_binning_init    src/python/f90/python_neighbors.f90:765-871  (host, neighbors_geometry)
+//   neighbors_binning_update  src/python/f90/python_neighbors.f90:904-959  (k_cell_assign .. k_gather)
+//   fill_neighbor_list        src/python/f90/python_neighbors.f90:570-754  (k_pairs<false/true>)
+//
+// Design: atoms are counting-sorted by cell (stable in the original atom index, which reproduces
+// the reference's ascending linked-list order inside a cell); positions are gathered into a
+// cell-ordered array of 32-byte records (x,y,z,element) so that one neighbour gather is one DRAM
+// sector; the pair list is a CSR in *sorted* numbering with an 8-byte entry {j, packed shift}.
+// All potentials work in sorted numbering; the host-layout list (original numbering, 1-based,
+// terminator slots) is materialised only on request.
+//
+// The acceptance predicate is evaluated with explicit round-to-nearest multiplies and adds
+// (__dmul_rn/__dadd_rn, never contracted to FMA) in the reference's association order, so the
+// pair set is bit-identical to the CPU build.
+#include <algorithm>
+#include <cmath>
+
+#include "atx_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// geometry (host): neighbors_binning_init
+// ---------------------------------------------------------------------------
+
+static double dot3h(const double *a, const double *b) {
+  double s = 0.0;
+  for (int i = 0; i < 3; i++) s += a[i] * b[i];
+  return s;
+}
+static void cross3h(const double *a, const double *b, double *c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+static void neighbors_geometry(atx_neighbors *nl, const atx_particles *p) {
+  const double *A = p->Abox.m, *B = p->Bbox.m;
+  double bin_size = nl->cutoff, cell_size[9];
+  for (int x = 0; x < 3; x++) {
+    double box = std::sqrt(dot3h(&A[3 * x], &A[3 * x]));
+    int n = (int)(box / bin_size);
+    nl->n_cells[x] = n < 3 ? 3 : n;
+  }
+  for (int x = 0; x < 3; x++)
+    for (int i = 0; i < 3; i++) {
+      cell_size[3 * x + i] = A[3 * x + i] / nl->n_cells[x];
+      nl->rec_cell_size.m[3 * i + x] = B[3 * i + x] * nl->n_cells[x];  // rec(x,i) = Bbox(x,i)*n(x)
+    }
+  double nx[3], ny[3], nz[3];
+  cross3h(&cell_size[3], &cell_size[6], nx);
+  cross3h(&cell_size[6], &cell_size[0], ny);
+  cross3h(&cell_size[0], &cell_size[3], nz);
+  double cv = dot3h(&cell_size[0], nx);
+  double nxx = dot3h(nx, nx), nyy = dot3h(ny, ny), nzz = dot3h(nz, nz);
+  for (int i = 0; i < 3; i++) {
+    nx[i] = cv * nx[i] / nxx;
+    ny[i] = cv * ny[i] / nyy;
+    nz[i] = cv * nz[i] / nzz;
+  }
+  nl->sten[0] = (int)(nl->cutoff / std::sqrt(dot3h(nx, nx))) + 1;
+  nl->sten[1] = (int)(nl->cutoff / std::sqrt(dot3h(ny, ny))) + 1;
+  nl->sten[2] = (int)(nl->cutoff / std::sqrt(dot3h(nz, nz))) + 1;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+
+struct Geo {
+  Mat3 rec;
+  Mat3 A;
+  int n[3];
+  int pbc[3];
+  int sten[3];
+  double cutoff_sq;
+};
+
+// floor(matmul(rec_cell_size, r)), wrapped into the box; shift counts the wraps (+1 per +n)
+__device__ __forceinline__ void wrap_cell(const Geo &g, double x, double y, double z, int c[3],
+                                          int s[3]) {
+  double rr[3] = {x, y, z};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double v = __dadd_rn(__dadd_rn(__dmul_rn(g.rec.m[k], rr[0]), __dmul_rn(g.rec.m[3 + k], rr[1])),
+                         __dmul_rn(g.rec.m[6 + k], rr[2]));
+    long long ck = (long long)floor(v);
+    int n = g.n[k];
+    int sh = 0;
+    if (g.pbc[k]) {
+      if (ck < 0) {
+        long long q = (-ck + n - 1) / n;
+        ck += q * n;
+        sh += (int)q;
+      } else if (ck >= n) {
+        long long q = ck / n;
+        ck -= q * n;
+        sh -= (int)q;
+      }
+    } else {
+      if (ck < 0) ck = 0;
+      if (ck >= n) ck = n - 1;
+    }
+    c[k] = (int)ck;
+    s[k] = sh;
+  }
+}
+
+__global__ void k_cell_assign(int nat, const double *__restrict__ r, Geo g,
+                              int4 *__restrict__ cellshift, int *__restrict__ cell_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nat) return;
+  int c[3], s[3];
+  wrap_cell(g, r[3 * i], r[3 * i + 1], r[3 * i + 2], c, s);
+  int cid = (c[0] * g.n[1] + c[1]) * g.n[2] + c[2];
+  cellshift[i] = make_int4(cid, s[0], s[1], s[2]);
+  atomicAdd(&cell_count[cid], 1);
+}
+
+__global__ void k_cell_scatter(int nat, const int4 *__restrict__ cellshift,
+                               const int *__restrict__ cell_start, int *__restrict__ cell_fill,
+                               int *__restrict__ order) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nat) return;
+  int cid = cellshift[i].x;
+  int slot = cell_start[cid] + atomicAdd(&cell_fill[cid], 1);
+  order[slot] = i;
+}
+
+// ascending original index inside every cell == the reference's linked-list order
+__global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, int *__restrict__ order) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int b = cell_start[c], e = cell_start[c + 1];
+  for (int a = b + 1; a < e; a++) {
+    int v = order[a];
+    int q = a - 1;
+    while (q >= b && order[q] > v) {
+      order[q + 1] = order[q];
+      q--;
+    }
+    order[q + 1] = v;
+  }
+}
+
+__global__ void k_gather_sorted(int nat, const double *__restrict__ r, const int *__restrict__ el,
+                                const int4 *__restrict__ cellshift, const int *__restrict__ order,
+                                double4 *__restrict__ pos4, int4 *__restrict__ sshift,
+                                int *__restrict__ inv) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  int i = order[s];
+  pos4[s] = make_double4(r[3 * i], r[3 * i + 1], r[3 * i + 2], el ? (double)el[i] : 1.0);
+  if (sshift) sshift[s] = cellshift[i];
+  if (inv) inv[i] = s;
+}
+
+// Pair search: one thread per atom (sorted order), reference stencil order.
+// FILL=false: count; FILL=true: write entries at seed[s].
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict__ sshift,
+        const int *__restrict__ cell_start, const int *__restrict__ order,
+        int *__restrict__ count, const long long *__restrict__ seed, int2 *__restrict__ list,
+        long long *__restrict__ scal) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  double4 pi = pos4[s];
+  int4 cs = sshift[s];
+  int ci[3];
+  ci[2] = cs.x % g.n[2];
+  ci[1] = (cs.x / g.n[2]) % g.n[1];
+  ci[0] = cs.x / (g.n[2] * g.n[1]);
+  long long w = FILL ? seed[s] : 0;
+  int cnt = 0;
+  for (int x = -g.sten[0]; x <= g.sten[0]; x++) {
+    int cx = ci[0] + x, sx = cs.y;
+    if (g.pbc[0]) {
+      while (cx < 0) { cx += g.n[0]; sx += 1; }
+      while (cx >= g.n[0]) { cx -= g.n[0]; sx -= 1; }
+    } else if (cx < 0 || cx >= g.n[0]) continue;
+    for (int y = -g.sten[1]; y <= g.sten[1]; y++) {
+      int cy = ci[1] + y, sy = cs.z;
+      if (g.pbc[1]) {
+        while (cy < 0) { cy += g.n[1]; sy += 1; }
+        while (cy >= g.n[1]) { cy -= g.n[1]; sy -= 1; }
+      } else if (cy < 0 || cy >= g.n[1]) continue;
+      for (int z = -g.sten[2]; z <= g.sten[2]; z++) {
+        int cz = ci[2] + z, sz = cs.w;
+        if (g.pbc[2]) {
+          while (cz < 0) { cz += g.n[2]; sz += 1; }
+          while (cz >= g.n[2]) { cz -= g.n[2]; sz -= 1; }
+        } else if (cz < 0 || cz >= g.n[2]) continue;
+        int cid = (cx * g.n[1] + cy) * g.n[2] + cz;
+        int b = cell_start[cid], e = cell_start[cid + 1];
+        for (int t = b; t < e; t++) {
+          int4 cj = sshift[t];
+          int s2x = sx - cj.y, s2y = sy - cj.z, s2z = sz - cj.w;
+          if (t == s && s2x == 0 && s2y == 0 && s2z == 0) continue;
+          double4 pj = pos4[t];
+          double ax, ay, az;
+          atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
+          double dx = __dadd_rn(__dsub_rn(pi.x, pj.x), ax);
+          double dy = __dadd_rn(__dsub_rn(pi.y, pj.y), ay);
+          double dz = __dadd_rn(__dsub_rn(pi.z, pj.z), az);
+          double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          if (d2 < g.cutoff_sq) {
+            if (FILL) {
+              int bad = (abs(s2x) >= ATX_SHIFT_BIAS) | (abs(s2y) >= ATX_SHIFT_BIAS) |
+                        (abs(s2z) >= ATX_SHIFT_BIAS);
+              if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
+              list[w++] = make_int2(t, atx_pack_shift(s2x, s2y, s2z));
+            }
+            cnt++;
+          }
+        }
+      }
+    }
+  }
+  if (!FILL) {
+    count[s] = cnt;
+    if (cnt > 0) {
+      atomicMax((unsigned long long *)&scal[1], (unsigned long long)cnt);
+      atomicMax((unsigned long long *)&scal[2], (unsigned long long)(order[s] + 1));
+    }
+  }
+}
+
+// refresh sorted positions after the atoms moved (list kept)
+__global__ void k_refresh_pos(int nat, const double *__restrict__ r, const int *__restrict__ order,
+                              double4 *__restrict__ pos4) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  int i = order[s];
+  double4 v = pos4[s];
+  v.x = r[3 * i];
+  v.y = r[3 * i + 1];
+  v.z = r[3 * i + 2];
+  pos4[s] = v;
+}
+
+// reverse slot: for entry a = (i -> j, shift) the entry b = (j -> i, -shift)
+__global__ void k_reverse_index(int nat, const long long *__restrict__ seed,
+                                const int2 *__restrict__ list, int *__restrict__ rev) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  for (long long a = seed[s]; a < seed[s + 1]; a++) {
+    int2 e = list[a];
+    int sx, sy, sz;
+    atx_unpack_shift(e.y, sx, sy, sz);
+    int want = atx_pack_shift(-sx, -sy, -sz);
+    int found = -1;
+    for (long long b = seed[e.x]; b < seed[e.x + 1]; b++) {
+      int2 q = list[b];
+      if (q.x == s && q.y == want) { found = (int)b; break; }
+    }
+    rev[a] = found;
+  }
+}
+
+// host-layout list ---------------------------------------------------------
+
+__global__ void k_host_counts(int nat, const int *__restrict__ inv, const int *__restrict__ count,
+                              int *__restrict__ hcount) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nat) return;
+  hcount[i] = count[inv[i]] + 1;  // + terminator slot
+}
+
+__global__ void k_host_fill(int nat, const int *__restrict__ inv, const int *__restrict__ order,
+                            const long long *__restrict__ seed, const int2 *__restrict__ list,
+                            const long long *__restrict__ hseed, long long *__restrict__ out_seed,
+                            long long *__restrict__ out_last, int *__restrict__ out_nb,
+                            int *__restrict__ out_dc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nat) return;
+  if (i == nat) {
+    out_seed[nat] = hseed[nat] + 1;
+    return;
+  }
+  int s = inv[i];
+  long long w = hseed[i];  // 0-based slot
+  out_seed[i] = w + 1;
+  for (long long a = seed[s]; a < seed[s + 1]; a++, w++) {
+    int2 e = list[a];
+    int sx, sy, sz;
+    atx_unpack_shift(e.y, sx, sy, sz);
+    out_nb[w] = order[e.x] + 1;
+    out_dc[3 * w] = sx;
+    out_dc[3 * w + 1] = sy;
+    out_dc[3 * w + 2] = sz;
+  }
+  out_last[i] = w;  // 1-based inclusive == 0-based exclusive
+  out_nb[w] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// API
+// ---------------------------------------------------------------------------
+
+extern "C" int atx_neighbors_create(atx_ctx *ctx, int avgn, atx_neighbors **nl) {
+  if (!ctx || !nl) return ATX_ERROR_UNSPECIFIED;
+  *nl = new atx_neighbors();
+  (*nl)->ctx = ctx;
+  (*nl)->avgn = avgn;
+  return 0;
+}
+
+extern "C" int atx_neighbors_destroy(atx_neighbors *nl) {
+  delete nl;
+  return 0;
+}
+
+extern "C" int atx_neighbors_request_interaction_range(atx_neighbors *nl, double cutoff) {
+  // python_neighbors.f90:381-423: any request tears the list down
+  if (cutoff > nl->interaction_range) nl->interaction_range = cutoff;
+  nl->initialized = false;
+  return 0;
+}
+
+extern "C" int atx_neighbors_set_verlet_shell(atx_neighbors *nl, double verlet_shell) {
+  nl->verlet_shell = verlet_shell;
+  nl->initialized = false;
+  return 0;
+}
+
+static Geo make_geo(const atx_neighbors *nl, const atx_particles *p) {
+  Geo g;
+  g.rec = nl->rec_cell_size;
+  g.A = p->Abox;
+  for (int k = 0; k < 3; k++) {
+    g.n[k] = nl->n_cells[k];
+    g.pbc[k] = p->pbc[k];
+    g.sten[k] = nl->sten[k];
+  }
+  g.cutoff_sq = nl->cutoff * nl->cutoff;
+  return g;
+}
+
+extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
+  atx_ctx *ctx = nl->ctx;
+  cudaStream_t st = ctx->stream;
+  if (nl->bound != p || nl->nat != p->nat) nl->initialized = false;
+  if (nl->initialized && nl->p_rev == p->pos_rev && nl->cell_rev == p->cell_rev) return 0;
+
+  const int nat = p->nat;
+  if (!nl->initialized) {
+    nl->cutoff = nl->interaction_range + nl->verlet_shell;
+    if (nl->cutoff <= 0.0) {
+      atx_set_error("Cutoff needs to be larger than zero.");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    nl->capacity = (long long)nat * nl->avgn;
+    nl->bound = p;
+    nl->nat = nat;
+    nl->cell_rev = -1;
+  }
+  if (nl->cell_rev != p->cell_rev || !nl->initialized) neighbors_geometry(nl, p);
+  nl->initialized = true;
+  nl->rev_valid = false;
+
+  long long ncell_ll = (long long)nl->n_cells[0] * nl->n_cells[1] * nl->n_cells[2];
+  if (ncell_ll > 2000000000ll) {
+    atx_set_error("Too many binning cells.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  int ncell = (int)ncell_ll;
+  Geo g = make_geo(nl, p);
+
+  ATX_PASS(nl->cellshift.reserve(nat + 1));
+  ATX_PASS(nl->cell_count.reserve(ncell + 1));
+  ATX_PASS(nl->cell_start.reserve(ncell + 1));
+  ATX_PASS(nl->cell_fill.reserve(ncell + 1));
+  ATX_PASS(nl->order.reserve(nat + 1));
+  ATX_PASS(nl->inv.reserve(nat + 1));
+  ATX_PASS(nl->pos4.reserve(nat + 1));
+  ATX_PASS(nl->sshift.reserve(nat + 1));
+  ATX_PASS(nl->count.reserve(nat + 1));
+  ATX_PASS(nl->seed.reserve(nat + 2));
+  ATX_PASS(nl->scal.reserve(8));
+
+  ATX_CUDA(cudaMemsetAsync(nl->cell_count.ptr, 0, sizeof(int) * (ncell + 1), st));
+  ATX_CUDA(cudaMemsetAsync(nl->cell_fill.ptr, 0, sizeof(int) * (ncell + 1), st));
+  ATX_CUDA(cudaMemsetAsync(nl->scal.ptr, 0, sizeof(long long) * 8, st));
+  ATX_CUDA(cudaMemsetAsync(nl->count.ptr, 0, sizeof(int) * (nat + 1), st));
+
+  const int TB = 256;
+  int gb = (nat + TB - 1) / TB;
+  if (nat > 0) {
+    k_cell_assign<<<gb, TB, 0, st>>>(nat, p->rptr(), g, nl->cellshift.ptr, nl->cell_count.ptr);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_scan_int(ctx, nl->cell_count.ptr, nl->cell_start.ptr, ncell + 1));
+  if (nat > 0) {
+    k_cell_scatter<<<gb, TB, 0, st>>>(nat, nl->cellshift.ptr, nl->cell_start.ptr, nl->cell_fill.ptr,
+                                      nl->order.ptr);
+    ATX_LAUNCHED();
+    k_cell_sort<<<(ncell + TB - 1) / TB, TB, 0, st>>>(ncell, nl->cell_start.ptr, nl->order.ptr);
+    ATX_LAUNCHED();
+    k_gather_sorted<<<gb, TB, 0, st>>>(nat, p->rptr(), p->el.cap ? p->el.ptr : nullptr,
+                                       nl->cellshift.ptr, nl->order.ptr, nl->pos4.ptr,
+                                       nl->sshift.ptr, nl->inv.ptr);
+    ATX_LAUNCHED();
+    k_pairs<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
+                                                      nl->cell_start.ptr, nl->order.ptr,
+                                                      nl->count.ptr, nullptr, nullptr, nl->scal.ptr);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_scan_int_to_ll(ctx, nl->count.ptr, nl->seed.ptr, nat + 1));
+  long long h[4] = {0, 0, 0, 0};
+  ATX_CUDA(cudaMemcpyAsync(&h[0], nl->seed.ptr + nat, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaMemcpyAsync(&h[1], nl->scal.ptr + 1, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  nl->npairs = h[0];
+  nl->nebmax = (int)h[1];
+  long long i_last = h[2];  // 1-based original index of the last atom that has a pair
+  // python_neighbors.f90:716-718: slot of the last pair is npairs + (i_last-1) (1-based) and must
+  // stay below the fixed capacity nat*avgn
+  if (nl->npairs > 0 && nl->npairs + (i_last - 1) >= nl->capacity) {
+    atx_set_error("Neighbor list overflow. Current neighbor list position is " +
+                  std::to_string(nl->npairs + i_last - 1) +
+                  " while the size of this chunk runs from 1 to " + std::to_string(nl->capacity) +
+                  ".");
+    nl->initialized = false;
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  ATX_PASS(nl->list.reserve((size_t)nl->npairs + 1));
+  if (nat > 0 && nl->npairs > 0) {
+    k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
+                                                     nl->cell_start.ptr, nl->order.ptr,
+                                                     nl->count.ptr, nl->seed.ptr, nl->list.ptr,
+                                                     nl->scal.ptr);
+    ATX_LAUNCHED();
+    ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    if (h[3]) {
+      atx_set_error("Periodic image shift beyond +-511 cells; wrap the positions into the cell.");
+      nl->initialized = false;
+      return ATX_ERROR_UNSPECIFIED;
+    }
+  }
+  ATX_CUDA(cudaGetLastError());
+  nl->p_rev = p->pos_rev;
+  nl->cell_rev = p->cell_rev;
+  nl->nbuilds++;
+  return 0;
+}
+
+int atx_neighbors_refresh_positions(atx_neighbors *nl, atx_particles *p) {
+  int nat = nl->nat;
+  if (nat > 0) {
+    k_refresh_pos<<<(nat + 255) / 256, 256, 0, nl->ctx->stream>>>(nat, p->rptr(), nl->order.ptr,
+                                                                 nl->pos4.ptr);
+    ATX_LAUNCHED();
+  }
+  nl->p_rev = p->pos_rev;
+  return 0;
+}
+
+int atx_neighbors_ensure_rev(atx_neighbors *nl) {
+  if (nl->rev_valid) return 0;
+  ATX_PASS(nl->rev.reserve((size_t)nl->npairs + 1));
+  if (nl->nat > 0 && nl->npairs > 0) {
+    k_reverse_index<<<(nl->nat + 127) / 128, 128, 0, nl->ctx->stream>>>(nl->nat, nl->seed.ptr,
+                                                                       nl->list.ptr, nl->rev.ptr);
+    ATX_LAUNCHED();
+  }
+  nl->rev_valid = true;
+  return 0;
+}
+
+extern "C" int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax,
+                                      int *n_cells, int *stencil) {
+  if (npairs) *npairs = nl->npairs;
+  if (nebmax) *nebmax = nl->nebmax;
+  for (int k = 0; k < 3; k++) {
+    if (n_cells) n_cells[k] = nl->n_cells[k];
+    if (stencil) stencil[k] = nl->sten[k];
+  }
+  return 0;
+}
+
+extern "C" int atx_neighbors_copy_to_host(atx_neighbors *nl, intptr_t *seed, intptr_t *last,
+                                          int *neighbors, int *dc, long long capacity) {
+  static_assert(sizeof(intptr_t) == sizeof(long long), "NEIGHPTR_T must be 64 bit");
+  if (!nl->initialized) {
+    atx_set_error("Neighbor list not built.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  atx_ctx *ctx = nl->ctx;
+  cudaStream_t st = ctx->stream;
+  int nat = nl->nat;
+  long long need = nl->npairs + nat;
+  if (need > capacity) {
+    atx_set_error("Host neighbor arrays too small: need " + std::to_string(need) + " slots, have " +
+                  std::to_string(capacity));
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  DevBuf<int> hcount, d_nb, d_dc;
+  DevBuf<long long> hseed, d_seed, d_last;
+  ATX_PASS(hcount.reserve(nat + 1));
+  ATX_PASS(hseed.reserve(nat + 2));
+  ATX_PASS(d_seed.reserve(nat + 2));
+  ATX_PASS(d_last.reserve(nat + 2));
+  ATX_PASS(d_nb.reserve(need + 1));
+  ATX_PASS(d_dc.reserve(3 * (need + 1)));
+  ATX_CUDA(cudaMemsetAsync(hcount.ptr, 0, sizeof(int) * (nat + 1), st));
+  ATX_CUDA(cudaMemsetAsync(d_dc.ptr, 0, sizeof(int) * 3 * (need + 1), st));
+  ATX_CUDA(cudaMemsetAsync(d_last.ptr, 0, sizeof(long long) * (nat + 1), st));
+  if (nat > 0) {
+    k_host_counts<<<(nat + 255) / 256, 256, 0, st>>>(nat, nl->inv.ptr, nl->count.ptr, hcount.ptr);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_scan_int_to_ll(ctx, hcount.ptr, hseed.ptr, nat + 1));
+  k_host_fill<<<(nat + 256) / 256, 256, 0, st>>>(nat, nl->inv.ptr, nl->order.ptr, nl->seed.ptr,
+                                                 nl->list.ptr, hseed.ptr, d_seed.ptr, d_last.ptr,
+                                                 d_nb.ptr, d_dc.ptr);
+  ATX_LAUNCHED();
+  ATX_CUDA(cudaMemcpyAsync(seed, d_seed.ptr, sizeof(long long) * (nat + 1), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaMemcpyAsync(last, d_last.ptr, sizeof(long long) * nat, cudaMemcpyDeviceToHost, st));
+  if (need > 0) {
+    ATX_CUDA(cudaMemcpyAsync(neighbors, d_nb.ptr, sizeof(int) * need, cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaMemcpyAsync(dc, d_dc.ptr, sizeof(int) * 3 * need, cudaMemcpyDeviceToHost, st));
+  }
+  ATX_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,234 @@
+/*
+ * atomistica_b200 -- C-ABI of the B200-native hot path of Atomistica.
+ *
+ * This is "seam 0" of SURVEY.md 8(b): the entry points the reference's Fortran
+ * host (src/python/f90/python_neighbors.f90, src/potentials/...) binds with
+ * ISO_C_BINDING in place of its CPU loops.  Everything is extern "C", plain
+ * pointers and sizes, Fortran array conventions:
+ *   - r(3,nat), f(3,nat): contiguous, 3 doubles per atom
+ *   - Abox(3,3), Bbox(3,3), wpot(3,3), wpot_per_at(3,3,nat): column-major
+ *   - atom indices in host-visible neighbour arrays are 1-based; seed/last are
+ *     1-based inclusive slot ranges of type intptr_t (NEIGHPTR_T) with one
+ *     0-terminator slot after every atom's range
+ * Every function returns 0 on success or a negative ERROR_* code
+ * (src/support/error.f90:81-85); the message is read with atx_last_error().
+ * energy_and_forces entry points ADD into epot/f/wpot/per-atom outputs, like
+ * the reference (tls_reduce, bop_kernel.f90:1613-1628).  Optional outputs are
+ * NULL when not requested.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with ATX_ERROR_DEVICE.
+ */
+#ifndef ATOMISTICA_B200_H
+#define ATOMISTICA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATX_ERROR_NONE 0
+#define ATX_ERROR_UNSPECIFIED (-1) /* ERROR_UNSPECIFIED, src/support/error.f90:82 */
+#define ATX_ERROR_IO (-2)
+#define ATX_ERROR_MPI (-4)
+#define ATX_ERROR_DEVICE (-100) /* CUDA failure / no device */
+
+typedef struct atx_ctx atx_ctx;
+typedef struct atx_particles atx_particles;
+typedef struct atx_neighbors atx_neighbors;
+typedef struct atx_eam atx_eam;
+typedef struct atx_bop atx_bop;
+typedef struct atx_rebo2 atx_rebo2;
+typedef struct atx_md atx_md;
+
+/* ---- library / context ------------------------------------------------- */
+
+/* replaces atomistica_startup/shutdown (src/support/atomistica.f90) for the device side */
+int atx_ctx_create(int device, atx_ctx **ctx);
+int atx_ctx_destroy(atx_ctx *ctx);
+int atx_ctx_synchronize(atx_ctx *ctx);
+/* get_full_error_string (src/support/error.f90) equivalent */
+int atx_last_error(char *buf, int len);
+const char *atx_version(void);
+/* number of kernel launches issued by this library since the last reset */
+long long atx_kernel_launches(int reset);
+
+/* ---- particles_t: src/python/f90/python_particles.f90:84-170 ------------ */
+
+int atx_particles_create(atx_ctx *ctx, atx_particles **p);
+int atx_particles_destroy(atx_particles *p);
+/* particles_set_cell (python_particles.f90:286-346); Bbox is the host's inverse (dgesv) */
+int atx_particles_set_cell(atx_particles *p, const double *Abox, const double *Bbox, const int *pbc);
+/* host r_non_cyc(3,nat) -> device; call when pos_rev changed (I_changed_positions) */
+int atx_particles_set_positions(atx_particles *p, int nat, const double *r);
+/* host el(nat) (1..nel element ids from particles_update_elements, :617-658) */
+int atx_particles_set_elements(atx_particles *p, int nat, const int *el);
+/* bare-metal variants: r / el already resident on the device (no copy) */
+int atx_particles_set_positions_device(atx_particles *p, int nat, const double *r_dev);
+
+/* ---- neighbors_t: src/python/f90/python_neighbors.f90:51-139 ------------ */
+
+int atx_neighbors_create(atx_ctx *ctx, int avgn, atx_neighbors **nl);
+int atx_neighbors_destroy(atx_neighbors *nl);
+/* neighbors_request_interaction_range (:381-423): keeps the maximum, invalidates the list */
+int atx_neighbors_request_interaction_range(atx_neighbors *nl, double cutoff);
+/* neighbors_set (:337-379): verlet_shell ("skin"), default 0 like the Python host */
+int atx_neighbors_set_verlet_shell(atx_neighbors *nl, double verlet_shell);
+/* neighbors_update -> binning_update + fill_neighbor_list (:430-754, 904-959).
+ * Fails with "Neighbor list overflow" when pairs + nat exceed nat*avgn (:716-718). */
+int atx_neighbors_update(atx_neighbors *nl, atx_particles *p);
+/* number of pairs, max neighbours per atom, n_cells(3), stencil half widths(3) */
+int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax, int *n_cells,
+                           int *stencil);
+/* host view of the list in the reference's layout and order (seed(nat+1), last(nat+1),
+ * neighbors(capacity), dc(3,capacity)); used by f_get_all_neighbors & co
+ * (src/python/f90/neighbors_wrap.f90:211-550) */
+int atx_neighbors_copy_to_host(atx_neighbors *nl, intptr_t *seed, intptr_t *last, int *neighbors,
+                               int *dc, long long capacity);
+
+/* ---- TabulatedAlloyEAM: src/potentials/eam/tabulated_alloy_eam.f90 ------- */
+
+/* one simple_spline_t (src/support/simple_spline.f90:42-61): n points, n-1 intervals */
+typedef struct {
+  int n;
+  double x0, dx;
+  const double *y, *coeff1, *coeff2, *coeff3, *dcoeff1, *dcoeff2, *dcoeff3;
+} atx_spline;
+
+/* ndb database elements; fF[ndb], frho[ndb], fphi[ndb*ndb] (column-major (i,j), symmetric) */
+int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const atx_spline *frho,
+                   const atx_spline *fphi, double cutoff, atx_eam **pot);
+int atx_eam_destroy(atx_eam *pot);
+/* bind_to (:297-350): el2db[nel] maps particle element ids (1..nel) to database ids (1..ndb, <=0:
+ * ignored); requests the interaction range */
+int atx_eam_bind_to(atx_eam *pot, atx_particles *p, atx_neighbors *nl, int nel, const int *el2db);
+/* energy_and_forces (:360-415) + kernel (:423-627) */
+int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                              double *epot, double *f, double *wpot, double *epot_per_at,
+                              double *wpot_per_at);
+
+/* ---- Tersoff / Kumagai / Brenner: src/potentials/bop/bop_kernel.f90 ------ */
+
+#define ATX_BOP_TERSOFF 1
+#define ATX_BOP_KUMAGAI 2
+#define ATX_BOP_BRENNER 3
+#define ATX_BOP_MAX_EL 3
+#define ATX_BOP_MAX_PAIRS 6
+
+/* Parameter database in the layout of the Fortran BOP_DB_TYPEs (pair arrays in PAIR_INDEX
+ * order, src/macros.inc:123).  Unused fields are ignored for a given kind.
+ *   Tersoff  (tersoff_params.f90:33-84):  A B xi lambda mu omega mubo m | beta n c d h | r1 r2
+ *   Kumagai  (kumagai_params.f90:30-118): A B lambda1 lambda2 alpha ibeta | eta delta c1..c5 h | r1 r2
+ *   Brenner  (brenner_params.f90:33-70):  D0 r0 S beta gamma c d h mu n m | r1 r2 */
+typedef struct {
+  int kind;
+  int nel;
+  int Z[ATX_BOP_MAX_EL]; /* atomic numbers of db%el */
+  /* pair parameters */
+  double A[ATX_BOP_MAX_PAIRS], B[ATX_BOP_MAX_PAIRS], xi[ATX_BOP_MAX_PAIRS];
+  double lambda[ATX_BOP_MAX_PAIRS], mu[ATX_BOP_MAX_PAIRS], omega[ATX_BOP_MAX_PAIRS];
+  double mubo[ATX_BOP_MAX_PAIRS]; /* Kumagai alpha */
+  int m[ATX_BOP_MAX_PAIRS];       /* Kumagai integer beta */
+  double D0[ATX_BOP_MAX_PAIRS], r0[ATX_BOP_MAX_PAIRS], S[ATX_BOP_MAX_PAIRS];
+  double pbeta[ATX_BOP_MAX_PAIRS], gamma[ATX_BOP_MAX_PAIRS];
+  double pc[ATX_BOP_MAX_PAIRS], pd[ATX_BOP_MAX_PAIRS], ph[ATX_BOP_MAX_PAIRS];
+  double pn[ATX_BOP_MAX_PAIRS];
+  double r1[ATX_BOP_MAX_PAIRS], r2[ATX_BOP_MAX_PAIRS];
+  /* element parameters */
+  double beta[ATX_BOP_MAX_EL], n[ATX_BOP_MAX_EL], c[ATX_BOP_MAX_EL], d[ATX_BOP_MAX_EL];
+  double h[ATX_BOP_MAX_EL];
+  double eta[ATX_BOP_MAX_EL], delta[ATX_BOP_MAX_EL];
+  double c1[ATX_BOP_MAX_EL], c2[ATX_BOP_MAX_EL], c3[ATX_BOP_MAX_EL], c4[ATX_BOP_MAX_EL];
+  double c5[ATX_BOP_MAX_EL];
+} atx_bop_params;
+
+int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop **pot);
+int atx_bop_destroy(atx_bop *pot);
+/* BIND_TO_FUNC (default_bind_to_func.f90:25-146): el2Z[nel] are the atomic numbers of the
+ * particle element ids; builds Z2db and requests r2 of every present pair */
+int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl, int nel, const int *el2Z);
+/* COMPUTE_FUNC (default_compute_func.f90:25-102) + BOP_KERNEL.  Per-bond outputs are indexed
+ * by host neighbour-list slot (this%nbb, bop_kernel.f90:1371,1407,1512). */
+int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                              double *epot, double *f, double *wpot, double *epot_per_at,
+                              double *epot_per_bond, double *f_per_bond, double *wpot_per_at,
+                              double *wpot_per_bond);
+
+/* ---- Rebo2: src/potentials/bop/rebo2/ -------------------------------------- */
+
+/* Everything rebo2_db_init_with_parameters (rebo2_db.f90:81-303) leaves in rebo2_t that the
+ * kernel reads.  Table coefficients are the Fortran coeff(nboxs,4,4[,4]) arrays
+ * (table2d.f90:84-226, table3d.f90:85-284), nboxs = 4*4*9 (F, T) and 5*5 (P). */
+typedef struct {
+  double cc_B1, cc_B2, cc_B3, cc_beta1, cc_beta2, cc_beta3, cc_Q, cc_A, cc_alpha;
+  double ch_B1, ch_beta1, ch_Q, ch_A, ch_alpha;
+  double hh_B1, hh_beta1, hh_Q, hh_A, hh_alpha;
+  double cc_g_theta[6];
+  double cc_g1_coeff[18], cc_g2_coeff[18]; /* g_coeff_t%c(6,3) */
+  double spgh[18];                         /* SPGH(6,3) */
+  int igh[25];
+  double conalp, conear[36];               /* conear(6,6) */
+  double conpe[3], conan[3], conpf[3];
+  double cut_in_l[10], cut_in_h[10], cut_in_h2[10];
+  int with_dihedral;
+  const double *Fcc, *Fch, *Fhh, *Tcc; /* 144*64 doubles each */
+  const double *Pcc, *Pch;             /* 25*16 doubles each */
+} atx_rebo2_params;
+
+int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_rebo2 **pot);
+int atx_rebo2_destroy(atx_rebo2 *pot);
+/* BIND_TO_FUNC (rebo2_module.f90:70-135) */
+int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, int nel,
+                      const int *el2Z);
+/* COMPUTE_FUNC (rebo2_module.f90:143-223) + kernel (bop_kernel_rebo2.f90) */
+int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, double *epot,
+                                double *f, double *wpot, double *epot_per_at,
+                                double *epot_per_bond, double *f_per_bond, double *wpot_per_at,
+                                double *wpot_per_bond);
+
+/* ---- device-resident MD driver -------------------------- */
+/* velocity-Verlet (src/standalone/verlet.f90:100-235) with the Verlet-shell rebuild rule
+ * 2*accum_max_dr >= verlet_shell (src/standalone/neighbors.f90:552-590); positions,
+ * velocities and forces never leave the GPU between atx_md_run calls. */
+
+#define ATX_POT_EAM 1
+#define ATX_POT_BOP 2
+#define ATX_POT_REBO2 3
+
+int atx_md_create(atx_ctx *ctx, int pot_kind, void *pot, atx_particles *p, atx_neighbors *nl,
+                  const double *mass /* per atom, amu */, const double *v /* (3,nat) */, double dt,
+                  atx_md **md);
+int atx_md_destroy(atx_md *md);
+/* advance nsteps; epot / ekin of the last step are returned */
+int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin);
+/* copy r, v, f (3,nat each, original atom order) back to the host; any pointer may be NULL */
+int atx_md_get_state(atx_md *md, double *r, double *v, double *f);
+/* number of neighbour-list rebuilds so far and device milliseconds spent in the last run */
+int atx_md_get_stats(atx_md *md, long long *nrebuilds, double *last_run_ms);
+
+/* ---- host-side init helpers ------------------------------------------------ */
+/* The reference computes these on the host in Fortran; a Fortran host keeps doing so and passes
+ * the results into atx_*_create.  They are exported so that non-Fortran hosts (the Python mirror
+ * in this repo) can build the same inputs. */
+
+/* simple_spline_init (simple_spline.f90:127-195); out arrays: y[n], d2y[n], coeff*[n-1], dcoeff*[n-1] */
+int atx_host_spline_init(int n, double x0, double dx, const double *y_in, double *y, double *d2y,
+                         double *coeff1, double *coeff2, double *coeff3, double *dcoeff1,
+                         double *dcoeff2, double *dcoeff3);
+/* gaussn (f_linearalgebra.f90:599-637): solve A X = B, A(n,n), B(n,m) column-major, in place */
+int atx_host_gaussn(int n, double *A, int m, double *B);
+/* table2d_init / table3d_init; values/derivatives are Fortran arrays (0:nx,0:ny[,0:nz]) */
+int atx_host_table2d_init(int nx, int ny, const double *values, const double *dvdx,
+                          const double *dvdy, double *coeff);
+int atx_host_table3d_init(int nx, int ny, int nz, const double *values, const double *dvdx,
+                          const double *dvdy, const double *dvdz, double *coeff);
+/* rebo2_db_make_cc_g_spline (rebo2_db.f90:405-524) */
+int atx_host_rebo2_g_spline(const double *theta, const double *g1, const double *dg1,
+                            const double *d2g1, const double *g2, double *g1_coeff,
+                            double *g2_coeff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,114 @@
+"""TabulatedAlloyEAM on the GPU vs the oracle (tolerance 1e-10 relative, BASELINE.json)."""
+import numpy as np
+import pytest
+
+import oracle
+from atomistica_b200 import native, structures as S
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def _close(a, b, scale=None):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(np.abs(b).max(), 1e-300) if scale is None else scale
+    return np.abs(a - b).max() <= RTOL * scale
+
+
+def _both(atoms, setfl, mask=None, per_at=True):
+    p = native.from_atoms(atoms)
+    nl = native.Neighbors(200)
+    pot = native.TabulatedAlloyEAM(setfl=setfl)
+    pot.bind_to(p, nl)
+    e, f, w, epa, _, _, wpa, _ = pot.energy_and_forces(p, nl, mask=mask, epot_per_at=per_at, wpot_per_at=per_at)
+    eam = oracle.EAM(setfl)
+    onl = oracle.neighbor_list(atoms.positions, atoms.cell, atoms.pbc, eam.cutoff, 200)
+    o = eam.energy_and_forces(atoms.positions, atoms.cell, onl, eam.eldb(atoms.symbols), mask=mask, per_at=per_at)
+    return (e, f, w, epa, wpa), o
+
+
+def _check(g, o, per_at=True):
+    e, f, w, epa, wpa = g
+    fscale = max(np.abs(o['f']).max(), 1.0)
+    assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
+    assert _close(f, o['f'], fscale)
+    assert _close(w, o['wpot'], max(np.abs(o['wpot']).max(), 1.0))
+    if per_at:
+        assert _close(epa, o['epot_per_at'])
+        assert _close(wpa, o['wpot_per_at'], max(np.abs(o['wpot_per_at']).max(), 1.0))
+
+
+def test_cu_perfect(cu_setfl):
+    g, o = _both(S.fcc('Cu', 3.615, (5, 5, 5)), cu_setfl)
+    _check(g, o)
+    assert abs(g[0] / 500 + 3.54) < 0.01
+
+
+def test_cu_rattled(cu_setfl):
+    a = S.fcc('Cu', 3.615, (6, 5, 4))
+    a.rattle(0.1, seed=3)
+    g, o = _both(a, cu_setfl)
+    _check(g, o)
+
+
+def test_au_rattled(au_setfl):
+    a = S.fcc('Au', 4.07, (4, 4, 4))
+    a.rattle(0.1, seed=4)
+    g, o = _both(a, au_setfl)
+    _check(g, o)
+
+
+def test_mask_additivity(au_setfl):
+    # tests/test_mask.py:35-81: mask + complement == unmasked
+    a = S.fcc('Au', 4.07, (4, 4, 4))
+    a.rattle(0.1, seed=5)
+    rng = np.random.RandomState(6)
+    mask = (rng.rand(len(a)) > 0.5).astype(np.int32)
+    g0, o0 = _both(a, au_setfl)
+    g1, o1 = _both(a, au_setfl, mask=mask)
+    g2, o2 = _both(a, au_setfl, mask=1 - mask)
+    _check(g1, o1)
+    _check(g2, o2)
+    assert abs(g1[0] + g2[0] - g0[0]) < 1e-6
+    assert np.abs(g1[1] + g2[1] - g0[1]).max() < 1e-6
+    assert np.abs(g1[2] + g2[2] - g0[2]).max() < 1e-6
+
+
+def test_unknown_element_is_ignored(cu_setfl):
+    a = S.fcc('Cu', 3.615, (4, 4, 4))
+    a.rattle(0.05, seed=7)
+    a.symbols[5] = 'Si'
+    a.symbols[77] = 'Si'
+    g, o = _both(a, cu_setfl)
+    _check(g, o)
+    assert np.all(g[1][5] == 0.0)
+
+
+def test_compressed_extrapolation(cu_setfl):
+    # tests/test_eam_special_cases.py:51-77: embedding function extrapolates beyond rho_max
+    from conftest import load_npz
+    from atomistica_b200.structures import Atoms
+    for name in ('eam_crash1.npz', 'eam_crash2.npz'):
+        d = load_npz(name)
+        a = Atoms([str(s) for s in d['symbols']], d['positions'], d['cell'], True)
+        g, o = _both(a, cu_setfl)
+        _check(g, o)
+    a.set_cell(a.cell * 0.5, scale_atoms=True)
+    g, o = _both(a, cu_setfl)
+    _check(g, o)
+
+
+def test_calculator_interface(cu_setfl):
+    from atomistica_b200 import TabulatedAlloyEAM
+    a = S.fcc('Cu', 3.615, (4, 4, 4))
+    a.calc = TabulatedAlloyEAM(setfl=cu_setfl)
+    e1 = a.get_potential_energy()
+    f = a.get_forces()
+    assert f.shape == (len(a), 3)
+    assert np.abs(f).max() < 1e-10
+    s = a.get_stress()
+    assert s.shape == (6,)
+    a.positions[0, 0] += 0.1
+    e2 = a.get_potential_energy()
+    assert e2 > e1

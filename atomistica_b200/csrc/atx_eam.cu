@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(128)
 k_eam_density(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
               const long long *__restrict__ seed, const int2 *__restrict__ list,
               const int *__restrict__ mask, double *__restrict__ dF, double *__restrict__ Fe,
-              int *__restrict__ flag) {
+              int *__restrict__ flag, const int *__restrict__ stop) {
+  if (stop && *stop) return;
   const int gpb = 128 / LANES;
   int s = blockIdx.x * gpb + threadIdx.x / LANES;
   int lane = threadIdx.x % LANES;
@@ -156,7 +157,9 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
             const long long *__restrict__ seed, const int2 *__restrict__ list,
             const int *__restrict__ mask, const double *__restrict__ dF,
             const double *__restrict__ Fe, double *__restrict__ f, double *__restrict__ epa,
-            double *__restrict__ wpa, double *__restrict__ partials, int *__restrict__ flag) {
+            double *__restrict__ wpa, double *__restrict__ partials, int *__restrict__ flag,
+            const int *__restrict__ stop) {
+  if (stop && *stop) return;
   __shared__ double red[ATX_NSUM * 4];
   const int gpb = 128 / LANES;
   int s = blockIdx.x * gpb + threadIdx.x / LANES;
@@ -352,28 +355,30 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
   int nblocks = (nat + gpb - 1) / gpb;
   if (nblocks < 1) nblocks = 1;
   ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
-  ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
 #define EAM_LAUNCH(L)                                                                             \
   do {                                                                                            \
     k_eam_density<L><<<nblocks, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,           \
                                               nl->seed.ptr, nl->list.ptr, mask_sorted,            \
-                                              pot->dF.ptr, pot->Fe.ptr, pot->flag.ptr);           \
+                                              pot->dF.ptr, pot->Fe.ptr, pot->flag.ptr, o.stop);   \
     ATX_LAUNCHED();                                                                               \
     if (o.wpa)                                                                                    \
       k_eam_force<L, true><<<nblocks, 128, 0, st>>>(                                              \
           nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \
-          pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr);      \
+          pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr,      \
+          o.stop);                                                                                \
     else                                                                                          \
       k_eam_force<L, false><<<nblocks, 128, 0, st>>>(                                             \
           nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \
-          pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr);      \
+          pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr,      \
+          o.stop);                                                                                \
     ATX_LAUNCHED();                                                                               \
   } while (0)
   if (lanes == 16) EAM_LAUNCH(16);
   else if (lanes == 8) EAM_LAUNCH(8);
   else EAM_LAUNCH(4);
 #undef EAM_LAUNCH
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums));
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
   return 0;
 }
 

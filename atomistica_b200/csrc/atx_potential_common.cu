@@ -1,7 +1,8 @@
 #include "atx_potential_common.cuh"
 
 __global__ void k_reduce_partials(const double *__restrict__ partials, int nblocks,
-                                  double *__restrict__ sums) {
+                                  double *__restrict__ sums, const int *__restrict__ stop) {
+  if (stop && *stop) return;
   // one warp per component, fixed summation order -> deterministic
   int comp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (comp >= ATX_NSUM) return;
@@ -11,8 +12,9 @@ __global__ void k_reduce_partials(const double *__restrict__ partials, int nbloc
   if (lane == 0) sums[comp] = x;
 }
 
-int atx_reduce_partials(atx_ctx *ctx, const double *partials, int nblocks, double *sums) {
-  k_reduce_partials<<<1, 32 * ATX_NSUM, 0, ctx->stream>>>(partials, nblocks, sums);
+int atx_reduce_partials(atx_ctx *ctx, const double *partials, int nblocks, double *sums,
+                        const int *stop) {
+  k_reduce_partials<<<1, 32 * ATX_NSUM, 0, ctx->stream>>>(partials, nblocks, sums, stop);
   ATX_LAUNCHED();
   return 0;
 }

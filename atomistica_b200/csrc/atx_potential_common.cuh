@@ -11,6 +11,7 @@ struct PotOut {
   double *epa = nullptr;    // (nat) overwritten, optional
   double *wpa = nullptr;    // (9,nat) overwritten, optional
   double *sums = nullptr;   // ATX_NSUM doubles: epot, wpot(3,3)
+  const int *stop = nullptr;  // MD driver: kernels return immediately when *stop != 0
 };
 
 // Scratch owned by every potential object for library-mode calls.
@@ -43,7 +44,8 @@ __device__ __forceinline__ void atx_block_sum(double (&v)[N], double *smem /* N*
 }
 
 // deterministic final reduction of per-block partials [nblocks][ATX_NSUM] -> sums[ATX_NSUM]
-int atx_reduce_partials(atx_ctx *ctx, const double *partials, int nblocks, double *sums);
+int atx_reduce_partials(atx_ctx *ctx, const double *partials, int nblocks, double *sums,
+                        const int *stop = nullptr);
 
 // sorted -> original order: out_orig[order[s]] (+)= in_sorted[s], ncomp doubles per atom
 int atx_unsort(atx_ctx *ctx, int nat, int ncomp, const int *order, const double *in_sorted,

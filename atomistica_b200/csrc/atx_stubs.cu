@@ -1,5 +1,5 @@
 // Temporary: entry points that are being implemented (removed as each lands).
-#include "atx_internal.cuh"
+#include "atx_potential_common.cuh"
 #define NOTIMPL(name) atx_set_error(name ": not implemented yet"); return ATX_ERROR_UNSPECIFIED;
 extern "C" int atx_bop_create(atx_ctx *, const atx_bop_params *, atx_bop **) { NOTIMPL("atx_bop_create") }
 extern "C" int atx_bop_destroy(atx_bop *) { return 0; }
@@ -9,8 +9,6 @@ extern "C" int atx_rebo2_create(atx_ctx *, const atx_rebo2_params *, atx_rebo2 *
 extern "C" int atx_rebo2_destroy(atx_rebo2 *) { return 0; }
 extern "C" int atx_rebo2_bind_to(atx_rebo2 *, atx_particles *, atx_neighbors *, int, const int *) { NOTIMPL("atx_rebo2_bind_to") }
 extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *, atx_particles *, atx_neighbors *, double *, double *, double *, double *, double *, double *, double *, double *) { NOTIMPL("atx_rebo2_energy_and_forces") }
-extern "C" int atx_md_create(atx_ctx *, int, void *, atx_particles *, atx_neighbors *, const double *, const double *, double, atx_md **) { NOTIMPL("atx_md_create") }
-extern "C" int atx_md_destroy(atx_md *) { return 0; }
-extern "C" int atx_md_run(atx_md *, int, double *, double *) { NOTIMPL("atx_md_run") }
-extern "C" int atx_md_get_state(atx_md *, double *, double *, double *) { NOTIMPL("atx_md_get_state") }
-extern "C" int atx_md_get_stats(atx_md *, long long *, double *) { NOTIMPL("atx_md_get_stats") }
+
+int atx_bop_compute_device(atx_bop *, atx_particles *, atx_neighbors *, const int *, const PotOut &) { NOTIMPL("atx_bop_compute_device") }
+int atx_rebo2_compute_device(atx_rebo2 *, atx_particles *, atx_neighbors *, const PotOut &) { NOTIMPL("atx_rebo2_compute_device") }

@@ -159,3 +159,124 @@ int atx_accumulate_to_host(atx_ctx *ctx, const double *dev, double *host, size_t
   for (size_t i = 0; i < n; i++) host[i] += stage.ptr[i];
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// measurement hooks
+// ---------------------------------------------------------------------------
+
+ProfScope::ProfScope(atx_ctx *c, const char *name) : ctx(c) {
+  if (!c->prof_on) return;
+  ProfSlot *slot = nullptr;
+  for (auto &s : c->prof)
+    if (s.name == name) slot = &s;
+  if (!slot) {
+    c->prof.push_back(ProfSlot());
+    slot = &c->prof.back();
+    slot->name = name;
+  }
+  if (slot->used + 2 > slot->ev.size()) {
+    size_t old = slot->ev.size();
+    slot->ev.resize(old + 256);
+    for (size_t i = old; i < slot->ev.size(); i++) cudaEventCreate(&slot->ev[i]);
+  }
+  cudaEventRecord(slot->ev[slot->used], c->stream);
+  stop = slot->ev[slot->used + 1];
+  slot->used += 2;
+}
+
+ProfScope::~ProfScope() {
+  if (stop) cudaEventRecord(stop, ctx->stream);
+}
+
+extern "C" int atx_profile_enable(atx_ctx *ctx, int on) {
+  ctx->prof_on = on != 0;
+  if (on)
+    for (auto &s : ctx->prof) s.used = 0;
+  return 0;
+}
+
+extern "C" int atx_profile_read(atx_ctx *ctx, const char *name, double *total_ms, long long *count) {
+  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+  double tot = 0.0;
+  long long n = 0;
+  for (auto &s : ctx->prof)
+    if (s.name == name)
+      for (size_t i = 0; i + 1 < s.used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.ev[i], s.ev[i + 1]) == cudaSuccess) {
+          tot += ms;
+          n++;
+        }
+      }
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  return 0;
+}
+
+__global__ void k_fp64_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+
+extern "C" int atx_measure_fp64_peak(atx_ctx *ctx, double *tflops) {
+  DevBuf<double> out;
+  ATX_PASS(out.reserve(8));
+  cudaEvent_t e0, e1;
+  ATX_CUDA(cudaEventCreate(&e0));
+  ATX_CUDA(cudaEventCreate(&e1));
+  const int iters = 8192, blocks = ctx->sm_count * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    ATX_CUDA(cudaEventRecord(e0, ctx->stream));
+    k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(out.ptr, iters);
+    ATX_CUDA(cudaEventRecord(e1, ctx->stream));
+    ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    ATX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    double t = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && t > best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return 0;
+}
+
+__global__ void k_copy(const double2 *__restrict__ a, double2 *__restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) b[i] = a[i];
+}
+
+extern "C" int atx_measure_copy_bandwidth(atx_ctx *ctx, double *gbs) {
+  const size_t n = (size_t)1 << 26;  // 64 Mi double2 = 1 GiB per buffer
+  DevBuf<double2> a, b;
+  ATX_PASS(a.reserve(n));
+  ATX_PASS(b.reserve(n));
+  ATX_CUDA(cudaMemsetAsync(a.ptr, 0, n * sizeof(double2), ctx->stream));
+  cudaEvent_t e0, e1;
+  ATX_CUDA(cudaEventCreate(&e0));
+  ATX_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    ATX_CUDA(cudaEventRecord(e0, ctx->stream));
+    k_copy<<<ctx->sm_count * 16, 512, 0, ctx->stream>>>(a.ptr, b.ptr, n);
+    ATX_CUDA(cudaEventRecord(e1, ctx->stream));
+    ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    ATX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double t = 2.0 * n * sizeof(double2) / (ms * 1e-3) / 1e9;
+    if (rep > 0 && t > best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *gbs = best;
+  return 0;
+}

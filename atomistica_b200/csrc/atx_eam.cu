@@ -358,10 +358,14 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
   if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
 #define EAM_LAUNCH(L)                                                                             \
   do {                                                                                            \
+    {                                                                                             \
+    ProfScope ps_(ctx, "eam_density");                                                            \
     k_eam_density<L><<<nblocks, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,           \
                                               nl->seed.ptr, nl->list.ptr, mask_sorted,            \
                                               pot->dF.ptr, pot->Fe.ptr, pot->flag.ptr, o.stop);   \
+    }                                                                                             \
     ATX_LAUNCHED();                                                                               \
+    ProfScope ps2_(ctx, "eam_force");                                                             \
     if (o.wpa)                                                                                    \
       k_eam_force<L, true><<<nblocks, 128, 0, st>>>(                                              \
           nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \

@@ -93,11 +93,27 @@ struct PinBuf {
 // objects
 // ---------------------------------------------------------------------------
 
+struct ProfSlot {
+  std::string name;
+  std::vector<cudaEvent_t> ev;  // pairs: start, stop
+  size_t used = 0;
+};
+
 struct atx_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   DevBuf<char> cub_tmp;
+  bool prof_on = false;
+  std::vector<ProfSlot> prof;
+};
+
+// RAII event pair around a kernel launch; free when profiling is off
+struct ProfScope {
+  atx_ctx *ctx;
+  cudaEvent_t stop = nullptr;
+  ProfScope(atx_ctx *c, const char *name);
+  ~ProfScope();
 };
 
 // 3x3 column-major matrix passed by value to kernels

@@ -402,6 +402,7 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
                                        nl->cellshift.ptr, nl->order.ptr, nl->pos4.ptr,
                                        nl->sshift.ptr, nl->inv.ptr);
     ATX_LAUNCHED();
+    ProfScope ps_(ctx, "nl_pairs_count");
     k_pairs<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
                                                       nl->cell_start.ptr, nl->order.ptr,
                                                       nl->count.ptr, nullptr, nullptr, nl->scal.ptr);
@@ -427,10 +428,13 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   }
   ATX_PASS(nl->list.reserve((size_t)nl->npairs + 1));
   if (nat > 0 && nl->npairs > 0) {
+    {
+    ProfScope ps_(ctx, "nl_pairs_fill");
     k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
                                                      nl->cell_start.ptr, nl->order.ptr,
                                                      nl->count.ptr, nl->seed.ptr, nl->list.ptr,
                                                      nl->scal.ptr);
+    }
     ATX_LAUNCHED();
     ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
     ATX_CUDA(cudaStreamSynchronize(st));

@@ -207,6 +207,18 @@ int atx_md_get_state(atx_md *md, double *r, double *v, double *f);
 /* number of neighbour-list rebuilds so far and device milliseconds spent in the last run */
 int atx_md_get_stats(atx_md *md, long long *nrebuilds, double *last_run_ms);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------- */
+/* CUDA-event timing of the library's own kernels on the launching stream.  When enabled every
+ * launch of a profiled kernel is bracketed by an event pair; atx_profile_read resolves them. */
+int atx_profile_enable(atx_ctx *ctx, int on);
+/* total milliseconds and launch count of kernel `name` since the last enable; names:
+ * "eam_density", "eam_force", "bop_force", "rebo2_force", "nl_pairs_count", "nl_pairs_fill" */
+int atx_profile_read(atx_ctx *ctx, const char *name, double *total_ms, long long *count);
+/* FP64 FMA throughput of the device (TFLOP/s), measured with a register-resident DFMA chain */
+int atx_measure_fp64_peak(atx_ctx *ctx, double *tflops);
+/* device copy bandwidth (GB/s, read+write bytes), measured with a 1 GiB grid-stride copy */
+int atx_measure_copy_bandwidth(atx_ctx *ctx, double *gbs);
+
 /* ---- host-side init helpers ------------------------------------------------ */
 /* The reference computes these on the host in Fortran; a Fortran host keeps doing so and passes
  * the results into atx_*_create.  They are exported so that non-Fortran hosts (the Python mirror

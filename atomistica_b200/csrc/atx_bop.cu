@@ -1,0 +1,661 @@
+// Tersoff / Kumagai / Brenner bond-order potentials on the device.
+//
+// Replaces BOP_KERNEL (src/potentials/bop/bop_kernel.f90:563-1630, SCREENING undefined) together
+// with the potential-specific functions it inlines:
+//   tersoff_func.f90:32-225, kumagai_func.f90:32-225, brenner_func.f90:27-215 (+ the derived
+//   constants of brenner_module.f90:269-288) and trig_off_f (src/support/cutoff.f90:152-196).
+//
+// Scatter-free, deterministic formulation:
+//   k_bop_center  one thread per central atom i.  Loop 1 of the reference (bond table: unit
+//                 vector, length, cutoff value/derivative) is staged in shared memory, loop 2
+//                 (per bond ij: zeta, bond order, pair terms) runs on top of it.  The force the
+//                 bonds of i exert on each neighbour (the reference's "f(j) += fj", "f(k) += df")
+//                 is accumulated PER LIST SLOT into G[slot] instead of being scattered.
+//   k_bop_gather  one thread per atom: f_i = f_i(own) + sum over its slots a of G[rev[a]], where
+//                 rev[a] is the slot of the reverse pair (j -> i, -shift) precomputed per list build.
+// No floating-point atomics are used for forces and energies.
+#include "atx_potential_common.cuh"
+
+#define BOP_PI 3.14159265358979323846264338327950288
+
+struct BopDev {
+  int kind, nel;
+  int el2db[32];  // particle element id -> db element (1..nel) or -1
+  double r1[6], r2[6], r1sq[6], r2sq[6], cfac[6];
+  // Tersoff: A B xi lambda mu omega mubo | beta n c d h (element)
+  // Kumagai: A B lambda1(lambda) lambda2(mu) alpha(mubo) | eta delta c1..c5 h
+  // Brenner: derived VR_f expR VA_f expA r0 gamma c_sq d_sq c_d h mu(mubo) n bo_exp bo_fac bo_exp1
+  double A[6], B[6], xi[6], lambda[6], mu[6], omega[6], mubo[6];
+  int m[6];
+  double beta[3], n[3], c[3], d[3], h[3];
+  double eta[3], delta[3], c1[3], c2[3], c3[3], c4[3], c5[3];
+  double VR_f[6], expR[6], VA_f[6], expA[6], r0[6], gamma[6], c_sq[6], d_sq[6], c_d[6], ph[6],
+      pn[6], bo_exp[6], bo_fac[6], bo_exp1[6];
+  // precomputed Tersoff element constants
+  double tb[3];  // beta**n
+};
+
+struct atx_bop {
+  atx_ctx *ctx = nullptr;
+  atx_bop_params par{};
+  BopDev dev{};
+  bool bound = false;
+  DevBuf<double4> G;
+  DevBuf<double> epb, fpb, wpb, epa_out;
+  DevBuf<int> flag;
+  PotScratch sc;
+};
+
+__device__ __forceinline__ int bop_pair_index(int i, int j, int maxval) {
+  // macros.inc:123, 1-based in, 0-based out
+  int a = (i - 1) + (j - 1) * maxval, b = (j - 1) + (i - 1) * maxval;
+  int c = (i - 1) * i / 2, d = (j - 1) * j / 2;
+  return (a < b ? a : b) - (c < d ? c : d);
+}
+
+template <int KIND>
+__device__ __forceinline__ void bop_VA(const BopDev &P, int ij, double dr, double &val, double &dval) {
+  if (KIND == ATX_BOP_BRENNER) {
+    double e = exp(-P.expA[ij] * (dr - P.r0[ij]));
+    val = -P.VA_f[ij] * e;
+    dval = P.VA_f[ij] * P.expA[ij] * e;
+  } else {
+    double e = exp(-P.mu[ij] * dr);
+    val = -P.B[ij] * e;
+    dval = P.B[ij] * P.mu[ij] * e;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void bop_VR(const BopDev &P, int ij, double dr, double &val, double &dval) {
+  if (KIND == ATX_BOP_BRENNER) {
+    double e = exp(-P.expR[ij] * (dr - P.r0[ij]));
+    val = P.VR_f[ij] * e;
+    dval = -P.VR_f[ij] * P.expR[ij] * e;
+  } else {
+    double e = exp(-P.lambda[ij] * dr);
+    val = P.A[ij] * e;
+    dval = -P.A[ij] * P.lambda[ij] * e;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void bop_g(const BopDev &P, int ti, int ik, double costh, double &val,
+                                      double &dval) {
+  if (KIND == ATX_BOP_TERSOFF) {
+    double omega = P.omega[ik];
+    double h_c = P.h[ti] - costh;
+    double c_sq = P.c[ti] * P.c[ti], d_sq = P.d[ti] * P.d[ti];
+    double h = d_sq + h_c * h_c;
+    val = omega * (1.0 + c_sq / d_sq - c_sq / h);
+    dval = -2 * omega * c_sq * h_c / (h * h);
+  } else if (KIND == ATX_BOP_KUMAGAI) {
+    double h_cos = P.h[ti] - costh;
+    double h_cos_sq = h_cos * h_cos;
+    double tmp = h_cos / (P.c3[ti] + h_cos_sq);
+    double go = P.c2[ti] * tmp;
+    double ga1 = P.c4[ti] * exp(-P.c5[ti] * h_cos_sq);
+    double v = go * (1.0 + ga1);
+    dval = -2 * (1.0 - h_cos * tmp) * v + 2 * P.c5[ti] * h_cos_sq * go * ga1;
+    val = P.c1[ti] + h_cos * v;
+  } else {
+    double hc = P.ph[ik] + costh;
+    double h = P.d_sq[ik] + hc * hc;
+    val = P.gamma[ik] * (1 + P.c_d[ik] - P.c_sq[ik] / h);
+    dval = 2 * P.gamma[ik] * P.c_sq[ik] * hc / (h * h);
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void bop_bo(const BopDev &P, int ti, int ij, double zij, double fcij,
+                                       double faij, double &bij, double &dfbij) {
+  if (KIND == ATX_BOP_TERSOFF) {
+    if (zij > 0.0) {
+      double n = P.n[ti];
+      double e = -0.5 / n;
+      double b = P.tb[ti];
+      double arg = 1.0 + b * pow(zij, n);
+      bij = P.xi[ij] * pow(arg, e);
+      dfbij = -0.25 * fcij * faij * P.xi[ij] * b * pow(zij, n - 1.0) * pow(arg, e - 1.0);
+    } else {
+      bij = 1.0;
+      dfbij = 0.0;
+    }
+  } else if (KIND == ATX_BOP_KUMAGAI) {
+    if (zij > 0.0) {
+      double eta = P.eta[ti], delta = -P.delta[ti];
+      double arg = 1.0 + pow(zij, eta);
+      bij = pow(arg, delta);
+      dfbij = 0.5 * fcij * faij * eta * pow(zij, eta - 1.0) * delta * pow(arg, delta - 1.0);
+    } else {
+      bij = 1.0;
+      dfbij = 0.0;
+    }
+  } else {
+    if (P.pn[ij] == 1.0) {
+      double arg = 1.0 + zij;
+      bij = pow(arg, P.bo_exp[ij]);
+      dfbij = P.bo_fac[ij] * fcij * faij * pow(arg, P.bo_exp1[ij]);
+    } else if (zij > 0.0) {
+      double arg = 1.0 + pow(zij, P.pn[ij]);
+      bij = pow(arg, P.bo_exp[ij]);
+      dfbij = P.bo_fac[ij] * fcij * faij * pow(zij, P.pn[ij] - 1.0) * pow(arg, P.bo_exp1[ij]);
+    } else {
+      bij = 1.0;
+      dfbij = 0.0;
+    }
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void bop_h(const BopDev &P, int ik, double dr, double &val, double &dval) {
+  double mu = P.mubo[ik];
+  if (mu == 0.0) {
+    val = 1.0;
+    dval = 0.0;
+    return;
+  }
+  int m = P.m[ik];
+  if (KIND == ATX_BOP_KUMAGAI) {
+    if (m == 1) {
+      val = exp(mu * dr);
+      dval = mu * val;
+    } else if (m == 3) {
+      val = exp(dr * dr * dr);  // sic: kumagai_func.f90:211-213 drops alpha
+      dval = 3 * mu * dr * dr * val;
+    } else {
+      val = exp(mu * pow(dr, (double)m));
+      dval = m * mu * pow(dr, (double)(m - 1)) * val;
+    }
+  } else {
+    if (m == 1) {
+      val = exp(2 * mu * dr);
+      dval = 2 * mu * val;
+    } else if (m == 3) {
+      double arg = 2 * mu * dr;
+      val = exp(arg * arg * arg);
+      dval = 2 * mu * m * arg * arg * val;
+    } else {
+      val = exp(pow(2 * mu * dr, (double)m));
+      dval = 2 * mu * m * pow(2 * mu * dr, (double)(m - 1)) * val;
+    }
+  }
+}
+
+#define BOP_BLOCK 64
+
+// shared-memory bond table, field-major so that consecutive threads hit consecutive banks
+template <int NB>
+struct BondSmem {
+  double rnx[NB][BOP_BLOCK], rny[NB][BOP_BLOCK], rnz[NB][BOP_BLOCK];
+  double rl[NB][BOP_BLOCK], fc[NB][BOP_BLOCK], dfc[NB][BOP_BLOCK];
+  double kx[NB][BOP_BLOCK], ky[NB][BOP_BLOCK], kz[NB][BOP_BLOCK];  // dbidk of the current ij
+  double gx[NB][BOP_BLOCK], gy[NB][BOP_BLOCK], gz[NB][BOP_BLOCK], ge[NB][BOP_BLOCK];  // per-slot G
+  int slot[NB][BOP_BLOCK];
+  int typ[NB][BOP_BLOCK];
+  double red[ATX_NSUM * (BOP_BLOCK / 32)];
+};
+
+template <int KIND, int NB>
+__global__ void __launch_bounds__(BOP_BLOCK)
+k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
+             const long long *__restrict__ seed, const int2 *__restrict__ list,
+             const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
+             double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
+             double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
+             int *__restrict__ flag, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BondSmem<NB> &S = *reinterpret_cast<BondSmem<NB> *>(smem_raw);
+  const int t = threadIdx.x;
+  const int s = blockIdx.x * BOP_BLOCK + t;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+
+  if (s < nat) {
+    double4 pi = pos4[s];
+    const int eli = P.el2db[(int)pi.w];
+    const long long b0 = seed[s], b1 = seed[s + 1];
+    int nb = 0;
+    // ---- loop 1: bond table (bop_kernel.f90:563-1068) ----
+    for (long long a = b0; a < b1; a++) {
+      int2 en = list[a];
+      bool bond = false;
+      if (eli > 0) {
+        double4 pj = pos4[en.x];
+        int elj = P.el2db[(int)pj.w];
+        if (elj > 0) {
+          double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+          if (en.y != ATX_SHIFT_ZERO) {
+            int sx, sy, sz;
+            atx_unpack_shift(en.y, sx, sy, sz);
+            double ax, ay, az;
+            atx_image_vector(A, sx, sy, sz, ax, ay, az);
+            dx -= ax; dy -= ay; dz -= az;
+          }
+          double r2 = dx * dx + dy * dy + dz * dz;
+          int ij = bop_pair_index(eli, elj, P.nel);
+          if (r2 < P.r2sq[ij]) {
+            if (nb >= NB) {
+              atomicOr(flag, 1);
+            } else {
+              double rl = sqrt(r2);
+              double fc = 1.0, dfc = 0.0;
+              if (!(r2 < P.r1sq[ij])) {
+                // trig_off_f
+                if (rl <= P.r1[ij]) { fc = 1.0; dfc = 0.0; }
+                else if (rl >= P.r2[ij]) { fc = 0.0; dfc = 0.0; }
+                else {
+                  double sn, cs;
+                  sincos(P.cfac[ij] * (rl - P.r1[ij]), &sn, &cs);
+                  fc = 0.5 * (1.0 + cs);
+                  dfc = -0.5 * P.cfac[ij] * sn;
+                }
+              }
+              S.rnx[nb][t] = dx / rl; S.rny[nb][t] = dy / rl; S.rnz[nb][t] = dz / rl;
+              S.rl[nb][t] = rl; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
+              S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0; S.ge[nb][t] = 0.0;
+              S.slot[nb][t] = (int)(a - b0);
+              S.typ[nb][t] = ij | (en.x << 3);
+              nb++;
+              bond = true;
+            }
+          }
+        }
+      }
+      if (!bond) G[a] = make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+
+    // ---- loop 2 (bop_kernel.f90:1075-1529) ----
+    double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
+    const int mi = mask ? mask[s] : 1;
+    for (int ij = 0; ij < nb; ij++) {
+      const int tij = S.typ[ij][t] & 7;
+      const int j = S.typ[ij][t] >> 3;
+      int maskfac = 2;
+      if (mask) {
+        int mj = mask[j];
+        if (mi == 0 && mj == 0) maskfac = 0;
+        else if (mi == 0 || mj == 0) maskfac = 1;
+      }
+      const double rlij = S.rl[ij][t];
+      if (!(maskfac > 0 && rlij < P.r2[tij])) continue;
+      const double rlijr = 1.0 / rlij;
+      const double nx = S.rnx[ij][t], ny = S.rny[ij][t], nz = S.rnz[ij][t];
+      const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
+      const double fcarij = S.fc[ij][t], dfcarijr = S.dfc[ij][t];
+      double VAij, dVAij, VRij, dVRij;
+      bop_VA<KIND>(P, tij, rlij, VAij, dVAij);
+      bop_VR<KIND>(P, tij, rlij, VRij, dVRij);
+      const double mf = 0.5 * maskfac;
+      VAij *= mf; dVAij *= mf; VRij *= mf; dVRij *= mf;
+
+      double zij = 0.0;
+      double dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0;
+      double wb[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) wb[q] = 0.0;
+
+      for (int ik = 0; ik < nb; ik++) {
+        if (ik == ij) continue;
+        const int tik = S.typ[ik][t] & 7;
+        const double rlik = S.rl[ik][t];
+        if (!(rlik < P.r2[tik])) {
+          S.kx[ik][t] = 0.0; S.ky[ik][t] = 0.0; S.kz[ik][t] = 0.0;
+          continue;
+        }
+        const double kx = S.rnx[ik][t], ky = S.rny[ik][t], kz = S.rnz[ik][t];
+        const double fcik = S.fc[ik][t], dfcikr = S.dfc[ik][t];
+        double h_Dr, dh_dDr, g_costh, dg_dcosth;
+        bop_h<KIND>(P, tik, rlij - rlik, h_Dr, dh_dDr);
+        const double costh = kx * nx + ky * ny + kz * nz;
+        bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
+        double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
+        const double disjk = sqrt(ex * ex + ey * ey + ez * ez);
+        ex /= disjk; ey /= disjk; ez /= disjk;
+        const double dcsdij = 1.0 / rlik - costh * rlijr;
+        const double dcsdik = rlijr - costh / rlik;
+        const double dcsdjk = -disjk * rlijr / rlik;
+        const double dzfac = fcik * dg_dcosth * h_Dr;
+        zij += fcik * g_costh * h_Dr;
+        const double dzdrij = g_costh * fcik * dh_dDr;
+        const double dzdrik = g_costh * (dfcikr * h_Dr - fcik * dh_dDr);
+        // x
+        double dfx, dfy, dfz, dkx, dky, dkz;
+        {
+          double ci = -dcsdij * nx - dcsdik * kx, cj = dcsdij * nx - dcsdjk * ex, ck = dcsdik * kx + dcsdjk * ex;
+          dix += -dzdrij * nx - dzdrik * kx + dzfac * ci;
+          dfx = dzdrij * nx + dzfac * cj;
+          dkx = dzdrik * kx + dzfac * ck;
+        }
+        {
+          double ci = -dcsdij * ny - dcsdik * ky, cj = dcsdij * ny - dcsdjk * ey, ck = dcsdik * ky + dcsdjk * ey;
+          diy += -dzdrij * ny - dzdrik * ky + dzfac * ci;
+          dfy = dzdrij * ny + dzfac * cj;
+          dky = dzdrik * ky + dzfac * ck;
+        }
+        {
+          double ci = -dcsdij * nz - dcsdik * kz, cj = dcsdij * nz - dcsdjk * ez, ck = dcsdik * kz + dcsdjk * ez;
+          diz += -dzdrij * nz - dzdrik * kz + dzfac * ci;
+          dfz = dzdrij * nz + dzfac * cj;
+          dkz = dzdrik * kz + dzfac * ck;
+        }
+        djx += dfx; djy += dfy; djz += dfz;
+        S.kx[ik][t] = dkx; S.ky[ik][t] = dky; S.kz[ik][t] = dkz;
+        const double rikx = rlik * kx, riky = rlik * ky, rikz = rlik * kz;
+        // wijb(a,b) -= rij(a)*df(b) + rik(a)*dbidk(b); column-major index a + 3b
+        wb[0] -= rijx * dfx + rikx * dkx; wb[1] -= rijy * dfx + riky * dkx; wb[2] -= rijz * dfx + rikz * dkx;
+        wb[3] -= rijx * dfy + rikx * dky; wb[4] -= rijy * dfy + riky * dky; wb[5] -= rijz * dfy + rikz * dky;
+        wb[6] -= rijx * dfz + rikx * dkz; wb[7] -= rijy * dfz + riky * dkz; wb[8] -= rijz * dfz + rikz * dkz;
+      }
+
+      double bij, dfb;
+      bop_bo<KIND>(P, eli - 1, tij, zij, fcarij, VAij, bij, dfb);
+      const double e_bond = 0.5 * fcarij * (VRij + bij * VAij);
+      pei += e_bond;
+      S.ge[ij][t] += e_bond;
+      const double dffac = 0.5 * (dVRij * fcarij + bij * dVAij * fcarij + VRij * dfcarijr + bij * VAij * dfcarijr);
+      const double dfx = dffac * nx, dfy = dffac * ny, dfz = dffac * nz;
+      fix += dfx - dfb * dix; fiy += dfy - dfb * diy; fiz += dfz - dfb * diz;
+      S.gx[ij][t] += -dfx - dfb * djx; S.gy[ij][t] += -dfy - dfb * djy; S.gz[ij][t] += -dfz - dfb * djz;
+      for (int ik = 0; ik < nb; ik++) {
+        if (ik == ij) continue;
+        S.gx[ik][t] -= dfb * S.kx[ik][t]; S.gy[ik][t] -= dfb * S.ky[ik][t]; S.gz[ik][t] -= dfb * S.kz[ik][t];
+      }
+      double w[9];
+      w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
+      w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
+      w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
+#pragma unroll
+      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+      acc[0] += e_bond;
+      const long long a = b0 + S.slot[ij][t];
+      if (epb) epb[a] = e_bond;
+      if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
+      if (wpb) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) wpb[9 * a + q] = w[q];
+      }
+      if (wpa) {
+        // optional analysis output (not on the hot path): per-atom virial, half to i, half to j
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
+          atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
+        }
+      }
+    }
+    f[3 * s] = fix; f[3 * s + 1] = fiy; f[3 * s + 2] = fiz;
+    pe_own[s] = pei;
+    for (int k = 0; k < nb; k++)
+      G[b0 + S.slot[k][t]] = make_double4(S.gx[k][t], S.gy[k][t], S.gz[k][t], S.ge[k][t]);
+  }
+  atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)blockIdx.x * ATX_NSUM + k] = acc[k];
+  }
+}
+
+__global__ void k_bop_gather(int nat, const long long *__restrict__ seed, const int *__restrict__ rev,
+                             const double4 *__restrict__ G, const double *__restrict__ pe_own,
+                             double *__restrict__ f, double *__restrict__ epa,
+                             const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  double fx = f[3 * s], fy = f[3 * s + 1], fz = f[3 * s + 2], pe = pe_own[s];
+  for (long long a = seed[s]; a < seed[s + 1]; a++) {
+    int b = rev[a];
+    if (b >= 0) {
+      double4 g = G[b];
+      fx += g.x; fy += g.y; fz += g.z; pe += g.w;
+    }
+  }
+  f[3 * s] = fx; f[3 * s + 1] = fy; f[3 * s + 2] = fz;
+  if (epa) epa[s] = 0.5 * pe;
+}
+
+// ---------------------------------------------------------------------------
+
+extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop **out) {
+  if (!ctx || !par || !out) return ATX_ERROR_UNSPECIFIED;
+  if (par->kind < 1 || par->kind > 3 || par->nel < 1 || par->nel > ATX_BOP_MAX_EL) {
+    atx_set_error("atx_bop_create: invalid kind or number of elements.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  atx_bop *pot = new atx_bop();
+  pot->ctx = ctx;
+  pot->par = *par;
+  BopDev &D = pot->dev;
+  D.kind = par->kind;
+  D.nel = par->nel;
+  int npairs = par->nel * (par->nel + 1) / 2;
+  for (int i = 0; i < npairs; i++) {
+    D.r1[i] = par->r1[i]; D.r2[i] = par->r2[i];
+    D.r1sq[i] = par->r1[i] * par->r1[i]; D.r2sq[i] = par->r2[i] * par->r2[i];
+    D.cfac[i] = BOP_PI / (par->r2[i] - par->r1[i]);
+    D.A[i] = par->A[i]; D.B[i] = par->B[i]; D.xi[i] = par->xi[i]; D.lambda[i] = par->lambda[i];
+    D.mu[i] = par->mu[i]; D.omega[i] = par->omega[i]; D.mubo[i] = par->mubo[i]; D.m[i] = par->m[i];
+    if (par->kind == ATX_BOP_BRENNER) {
+      // brenner_module.f90:269-288
+      if (par->pd[i] * par->pd[i] == 0.0) {
+        atx_set_error("d = 0! This leads to problems computing c**2/d**2. Please specify d != 0.");
+        delete pot;
+        return ATX_ERROR_UNSPECIFIED;
+      }
+      if (par->S[i] <= 1.0) {
+        atx_set_error("S <= 1! This leads to problems computing (S-1)**(-1). Please specify S > 1.");
+        delete pot;
+        return ATX_ERROR_UNSPECIFIED;
+      }
+      D.bo_exp[i] = -0.5 / par->pn[i];
+      D.bo_fac[i] = 0.5 * D.bo_exp[i] * par->pn[i];
+      D.bo_exp1[i] = D.bo_exp[i] - 1.0;
+      D.expR[i] = par->pbeta[i] * sqrt(2 * par->S[i]);
+      D.expA[i] = par->pbeta[i] * sqrt(2 / par->S[i]);
+      D.c_sq[i] = par->pc[i] * par->pc[i];
+      D.d_sq[i] = par->pd[i] * par->pd[i];
+      D.c_d[i] = D.c_sq[i] / D.d_sq[i];
+      D.VR_f[i] = par->D0[i] / (par->S[i] - 1);
+      D.VA_f[i] = par->S[i] * par->D0[i] / (par->S[i] - 1);
+      D.r0[i] = par->r0[i]; D.gamma[i] = par->gamma[i]; D.ph[i] = par->ph[i]; D.pn[i] = par->pn[i];
+    }
+  }
+  for (int i = 0; i < par->nel; i++) {
+    D.beta[i] = par->beta[i]; D.n[i] = par->n[i]; D.c[i] = par->c[i]; D.d[i] = par->d[i];
+    D.h[i] = par->h[i]; D.eta[i] = par->eta[i]; D.delta[i] = par->delta[i];
+    D.c1[i] = par->c1[i]; D.c2[i] = par->c2[i]; D.c3[i] = par->c3[i]; D.c4[i] = par->c4[i];
+    D.c5[i] = par->c5[i];
+    D.tb[i] = par->kind == ATX_BOP_TERSOFF ? pow(par->beta[i], par->n[i]) : 0.0;
+  }
+  for (int k = 0; k < 32; k++) D.el2db[k] = -1;
+  ATX_PASS(pot->flag.reserve(4));
+  *out = pot;
+  return 0;
+}
+
+extern "C" int atx_bop_destroy(atx_bop *pot) {
+  delete pot;
+  return 0;
+}
+
+extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl, int nel,
+                               const int *el2Z) {
+  if (nel > 31) {
+    atx_set_error("Too many particle element ids.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  BopDev &D = pot->dev;
+  for (int k = 0; k < 32; k++) D.el2db[k] = -1;
+  for (int k = 0; k < nel; k++)
+    for (int e = 0; e < pot->par.nel; e++)
+      if (el2Z[k] > 0 && el2Z[k] == pot->par.Z[e]) D.el2db[k + 1] = e + 1;
+  // default_bind_to_func.f90:118-141: request r2 of every present pair
+  if (nl)
+    for (int i = 1; i <= nel; i++)
+      for (int j = 1; j <= nel; j++)
+        if (D.el2db[i] > 0 && D.el2db[j] > 0) {
+          int a = D.el2db[i], b = D.el2db[j];
+          int x = (a - 1) + (b - 1) * D.nel, y = (b - 1) + (a - 1) * D.nel;
+          int c = (a - 1) * a / 2, d = (b - 1) * b / 2;
+          int ij = (x < y ? x : y) - (c < d ? c : d);
+          ATX_PASS(atx_neighbors_request_interaction_range(nl, D.r2[ij]));
+        }
+  pot->bound = true;
+  return 0;
+}
+
+template <int KIND, int NB>
+static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                         const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
+                         int nblocks) {
+  size_t smem = sizeof(BondSmem<NB>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr_set = true;
+  }
+  ProfScope ps_(pot->ctx, "bop_force");
+  k_bop_center<KIND, NB><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
+      nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
+      pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->flag.ptr, o.stop);
+  ATX_LAUNCHED();
+  return 0;
+}
+
+template <int KIND>
+static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                            const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
+                            int nblocks) {
+  int nebmax = nl->nebmax;
+  if (nebmax <= 6) return launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
+  if (nebmax <= 12) return launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
+  return launch_center<KIND, 24>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
+}
+
+static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask_sorted,
+                       const PotOut &o, double *epb, double *fpb, double *wpb) {
+  atx_ctx *ctx = pot->ctx;
+  cudaStream_t st = ctx->stream;
+  int nat = nl->nat;
+  ATX_PASS(atx_neighbors_ensure_rev(nl));
+  ATX_PASS(pot->G.reserve((size_t)nl->npairs + 1));
+  ATX_PASS(pot->sc.epa.reserve((size_t)nat + 1));  // pe_own scratch
+  double *pe_own = pot->sc.epa.ptr;
+  int nblocks = (nat + BOP_BLOCK - 1) / BOP_BLOCK;
+  if (nblocks < 1) nblocks = 1;
+  ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
+  if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
+  switch (pot->dev.kind) {
+    case ATX_BOP_TERSOFF:
+      ATX_PASS(launch_center_nb<ATX_BOP_TERSOFF>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
+      break;
+    case ATX_BOP_KUMAGAI:
+      ATX_PASS(launch_center_nb<ATX_BOP_KUMAGAI>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
+      break;
+    default:
+      ATX_PASS(launch_center_nb<ATX_BOP_BRENNER>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
+  }
+  if (nat > 0) {
+    k_bop_gather<<<(nat + 127) / 128, 128, 0, st>>>(nat, nl->seed.ptr, nl->rev.ptr, pot->G.ptr, pe_own,
+                                                    o.f, o.epa, o.stop);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  return 0;
+}
+
+int atx_bop_compute_device(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
+                           const int *mask_sorted, const PotOut &o) {
+  return bop_compute(pot, p, nl, mask_sorted, o, nullptr, nullptr, nullptr);
+}
+
+// device-slot -> host-slot remap of per-bond outputs
+__global__ void k_bop_perbond_to_host(int nat, int ncomp, const int *__restrict__ order,
+                                      const long long *__restrict__ seed,
+                                      const long long *__restrict__ hseed,
+                                      const double *__restrict__ in, double *__restrict__ out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  long long w = hseed[order[s]];
+  for (long long a = seed[s]; a < seed[s + 1]; a++, w++)
+    for (int c = 0; c < ncomp; c++) out[(size_t)w * ncomp + c] = in[(size_t)a * ncomp + c];
+}
+
+int atx_neighbors_host_seed(atx_neighbors *nl, DevBuf<long long> &hseed);
+
+int atx_perbond_to_host(atx_ctx *ctx, atx_neighbors *nl, int ncomp, const double *dev_slots,
+                        double *host, PinBuf<double> &stage) {
+  DevBuf<long long> hseed;
+  ATX_PASS(atx_neighbors_host_seed(nl, hseed));
+  size_t need = (size_t)(nl->npairs + nl->nat + 1) * ncomp;
+  DevBuf<double> out;
+  ATX_PASS(out.reserve(need));
+  ATX_CUDA(cudaMemsetAsync(out.ptr, 0, sizeof(double) * need, ctx->stream));
+  if (nl->nat > 0) {
+    k_bop_perbond_to_host<<<(nl->nat + 127) / 128, 128, 0, ctx->stream>>>(
+        nl->nat, ncomp, nl->order.ptr, nl->seed.ptr, hseed.ptr, dev_slots, out.ptr);
+    ATX_LAUNCHED();
+  }
+  return atx_accumulate_to_host(ctx, out.ptr, host, need, stage);
+}
+
+extern "C" int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
+                                         const int *mask, double *epot, double *f, double *wpot,
+                                         double *epot_per_at, double *epot_per_bond,
+                                         double *f_per_bond, double *wpot_per_at,
+                                         double *wpot_per_bond) {
+  if (!pot->bound) {
+    atx_set_error("bind_to has not been called on this potential.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  atx_ctx *ctx = pot->ctx;
+  ATX_PASS(atx_neighbors_update(nl, p));
+  PotOut o;
+  ATX_PASS(pot->sc.f.reserve(3 * (size_t)nl->nat + 3));
+  ATX_PASS(pot->sc.sums.reserve(ATX_NSUM));
+  ATX_PASS(pot->epa_out.reserve((size_t)nl->nat + 1));
+  o.f = pot->sc.f.ptr;
+  o.sums = pot->sc.sums.ptr;
+  if (epot_per_at) o.epa = pot->epa_out.ptr;
+  if (wpot_per_at) {
+    ATX_PASS(pot->sc.wpa.reserve(9 * (size_t)nl->nat + 9));
+    o.wpa = pot->sc.wpa.ptr;
+  }
+  const int *mask_sorted = nullptr;
+  ATX_PASS(atx_prepare_mask(ctx, nl, pot->sc, mask, &mask_sorted));
+  size_t nslots = (size_t)nl->npairs + 1;
+  double *epb = nullptr, *fpb = nullptr, *wpb = nullptr;
+  if (epot_per_bond) {
+    ATX_PASS(pot->epb.reserve(nslots));
+    ATX_CUDA(cudaMemsetAsync(pot->epb.ptr, 0, sizeof(double) * nslots, ctx->stream));
+    epb = pot->epb.ptr;
+  }
+  if (f_per_bond) {
+    ATX_PASS(pot->fpb.reserve(3 * nslots));
+    ATX_CUDA(cudaMemsetAsync(pot->fpb.ptr, 0, sizeof(double) * 3 * nslots, ctx->stream));
+    fpb = pot->fpb.ptr;
+  }
+  if (wpot_per_bond) {
+    ATX_PASS(pot->wpb.reserve(9 * nslots));
+    ATX_CUDA(cudaMemsetAsync(pot->wpb.ptr, 0, sizeof(double) * 9 * nslots, ctx->stream));
+    wpb = pot->wpb.ptr;
+  }
+  ATX_PASS(bop_compute(pot, p, nl, mask_sorted, o, epb, fpb, wpb));
+  int h = 0;
+  ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h) {
+    atx_set_error("Internal neighbor list exhausted, *nebmax* too small.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  if (epb) ATX_PASS(atx_perbond_to_host(ctx, nl, 1, epb, epot_per_bond, pot->sc.stage));
+  if (fpb) ATX_PASS(atx_perbond_to_host(ctx, nl, 3, fpb, f_per_bond, pot->sc.stage));
+  if (wpb) ATX_PASS(atx_perbond_to_host(ctx, nl, 9, wpb, wpot_per_bond, pot->sc.stage));
+  // epot = 0.5*sum(pe) = sum over directed bonds of e_bond (bop_kernel.f90:1613)
+  return atx_finish_to_host(ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
+}

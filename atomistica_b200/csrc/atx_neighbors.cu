@@ -485,6 +485,23 @@ extern "C" int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int 
   return 0;
 }
 
+// 0-based host-layout slot offsets per ORIGINAL atom (includes the terminator slots)
+int atx_neighbors_host_seed(atx_neighbors *nl, DevBuf<long long> &hseed) {
+  int nat = nl->nat;
+  DevBuf<int> hcount;
+  ATX_PASS(hcount.reserve(nat + 1));
+  ATX_PASS(hseed.reserve(nat + 2));
+  ATX_CUDA(cudaMemsetAsync(hcount.ptr, 0, sizeof(int) * (nat + 1), nl->ctx->stream));
+  if (nat > 0) {
+    k_host_counts<<<(nat + 255) / 256, 256, 0, nl->ctx->stream>>>(nat, nl->inv.ptr, nl->count.ptr,
+                                                                  hcount.ptr);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_scan_int_to_ll(nl->ctx, hcount.ptr, hseed.ptr, nat + 1));
+  ATX_CUDA(cudaStreamSynchronize(nl->ctx->stream));  // hcount is freed on return
+  return 0;
+}
+
 extern "C" int atx_neighbors_copy_to_host(atx_neighbors *nl, intptr_t *seed, intptr_t *last,
                                           int *neighbors, int *dc, long long capacity) {
   static_assert(sizeof(intptr_t) == sizeof(long long), "NEIGHPTR_T must be 64 bit");

@@ -1,0 +1,904 @@
+// REBO2 (Brenner et al. 2002) on the device -- non-screened build (DIHEDRAL + NUM_NEIGHBORS).
+//
+// Replaces rebo2_kernel (src/potentials/bop/rebo2/bop_kernel_rebo2.f90:700-2883, SCREENING
+// undefined) and the functions it inlines (rebo2_func.f90: fconj :31-57, fCin :63-85, VA :173-221,
+// VR :230-277, g :289-347, cc_g_from_spline :351-397, bo :403-425, h :431-461, Z2pair :467-485)
+// plus table2d_eval / table3d_eval (src/special/table2d.f90:255-318, table3d.f90:313-389).
+//
+//   k_rebo2_bonds  loop 1 + the neighbour counts nn(C,H) of the reference: one thread per atom
+//                  writes a fixed-stride bond table (unit vector, length, fc, fc', pair type,
+//                  neighbour, periodic shift) -- the reference's neb/bndnm/bndlen/cutfcnar arrays.
+//   k_rebo2_force  loop 2: one thread per atom i, one undirected bond at a time (j_gt_i).  The
+//                  nebmax^2 second-neighbour caches of the reference (nebofk, dncnidm, drk, ...)
+//                  are not materialised: the conjugation terms of k's and l's neighbours are
+//                  recomputed from the bond table when their forces are applied.
+// Forces on i, j, k, l, m, n are accumulated with native FP64 atomicAdd (RED.ADD.F64); periodic
+// image identity along neighbour paths is tracked with 3-vector shift sums.
+#include "atx_potential_common.cuh"
+
+#define RB_PI 3.14159265358979323846264338327950288
+#define RB_C 1
+#define RB_H 3
+#define RB_CC 1
+#define RB_CH 3
+#define RB_HH 6
+#define RB_NBL 12  // per-thread bond scratch; larger coordination raises the reference's nebmax error
+
+struct Rebo2Dev {
+  double cc_B1, cc_B2, cc_B3, cc_beta1, cc_beta2, cc_beta3, cc_Q, cc_A, cc_alpha;
+  double ch_B1, ch_beta1, ch_Q, ch_A, ch_alpha;
+  double hh_B1, hh_beta1, hh_Q, hh_A, hh_alpha;
+  double cc_g_theta[6], g1c[18], g2c[18], spgh[18];
+  int igh[25];
+  double conalp, conear[36], conpe[3], conan[3], conpf[3];
+  double cut_l[7], cut_h[7], cut_h2[7], cut_fac[7];
+  int with_dihedral;
+  int el2typ[32];
+  const double *Fcc, *Fch, *Fhh, *Tcc, *Pcc, *Pch;
+  double n37;  // (double)3.7f, single-precision literal of rebo2_func.f90:314
+};
+
+struct atx_rebo2 {
+  atx_ctx *ctx = nullptr;
+  Rebo2Dev dev{};
+  DevBuf<double> tables;
+  bool bound = false;
+  // bond table (stride nbs per atom)
+  int nbs = 0;
+  DevBuf<int> b_cnt, b_nb, b_typ, b_shift, b_slot;
+  DevBuf<double4> b_vec;   // rnx, rny, rnz, rl
+  DevBuf<double2> b_cut;   // fc, dfc
+  DevBuf<double2> nn;      // nn(C), nn(H)
+  DevBuf<double> epb, fpb, wpb, epa_out;
+  DevBuf<int> flag;
+  PotScratch sc;
+};
+
+__device__ __forceinline__ void rb_table2d(const double *__restrict__ coeff, int nx, int ny,
+                                           double nhi, double nci, double &v, double &dvdh, double &dvdc) {
+  const int nboxs = nx * ny;
+  int nhbox = (int)nhi;
+  if (nhbox < 0) nhbox = 0;
+  if (nhbox >= nx) nhbox = nx - 1;
+  int ncbox = (int)nci;
+  if (ncbox < 0) ncbox = 0;
+  if (ncbox >= ny) ncbox = ny - 1;
+  const int ibox = ny * nhbox + ncbox;
+  const double x1 = nhi - nhbox, x2 = nci - ncbox;
+  v = 0.0; dvdh = 0.0; dvdc = 0.0;
+  for (int i = 4; i >= 1; i--) {
+    double s = 0.0, sdc = 0.0;
+    for (int j = 4; j >= 1; j--) {
+      double c = __ldg(&coeff[ibox + nboxs * ((i - 1) + 4 * (j - 1))]);
+      s = s * x2 + c;
+      if (j > 1) sdc = sdc * x2 + (j - 1) * c;
+    }
+    v = v * x1 + s;
+    if (i > 1) dvdh = dvdh * x1 + (i - 1) * s;
+    dvdc = dvdc * x1 + sdc;
+  }
+}
+
+__device__ __forceinline__ void rb_table3d(const double *__restrict__ coeff, int nx, int ny, int nz,
+                                           double nti, double ntj, double nc, double &v, double &dvdi,
+                                           double &dvdj, double &dvdc) {
+  const int nboxs = nx * ny * nz;
+  int ib = (int)nti;
+  if (ib < 0) ib = 0;
+  if (ib >= nx) ib = nx - 1;
+  int jb = (int)ntj;
+  if (jb < 0) jb = 0;
+  if (jb >= ny) jb = ny - 1;
+  int cb = (int)nc;
+  if (cb < 0) cb = 0;
+  if (cb >= nz) cb = nz - 1;
+  const int ibox = nx * (ny * cb + jb) + ib;
+  const double x1 = nti - ib, x2 = ntj - jb, x3 = nc - cb;
+  v = 0.0; dvdi = 0.0; dvdj = 0.0; dvdc = 0.0;
+  for (int i = 4; i >= 1; i--) {
+    double s = 0.0, sdj = 0.0, sdc = 0.0;
+    for (int j = 4; j >= 1; j--) {
+      double t = 0.0, tdc = 0.0;
+      for (int k = 4; k >= 1; k--) {
+        double c = __ldg(&coeff[ibox + nboxs * ((i - 1) + 4 * ((j - 1) + 4 * (k - 1)))]);
+        t = t * x3 + c;
+        if (k > 1) tdc = tdc * x3 + (k - 1) * c;
+      }
+      s = s * x2 + t;
+      if (j > 1) sdj = sdj * x2 + (j - 1) * t;
+      sdc = sdc * x2 + tdc;
+    }
+    v = v * x1 + s;
+    if (i > 1) dvdi = dvdi * x1 + (i - 1) * s;
+    dvdj = dvdj * x1 + sdj;
+    dvdc = dvdc * x1 + sdc;
+  }
+}
+
+__device__ __forceinline__ void rb_fconj(double x, double &fx, double &dfx) {
+  if (x <= 2.0) { fx = 1.0; dfx = 0.0; }
+  else if (x >= 3.0) { fx = 0.0; dfx = 0.0; }
+  else {
+    double sn, cs;
+    sincos(RB_PI * (x - 2.0), &sn, &cs);
+    fx = 0.5 * (1.0 + cs);
+    dfx = -0.5 * RB_PI * sn;
+  }
+}
+
+__device__ __forceinline__ void rb_VA(const Rebo2Dev &P, int ijpot, double dr, double &val, double &dval) {
+  if (ijpot == RB_CC) {
+    double e1 = P.cc_B1 * exp(-P.cc_beta1 * dr);
+    double e2 = P.cc_B2 * exp(-P.cc_beta2 * dr);
+    double e3 = P.cc_B3 * exp(-P.cc_beta3 * dr);
+    val = -(e1 + e2 + e3);
+    dval = -(-P.cc_beta1 * e1 - P.cc_beta2 * e2 - P.cc_beta3 * e3);
+  } else if (ijpot == RB_CH) {
+    double e1 = P.ch_B1 * exp(-P.ch_beta1 * dr);
+    val = -e1;
+    dval = P.ch_beta1 * e1;
+  } else {
+    double e1 = P.hh_B1 * exp(-P.hh_beta1 * dr);
+    val = -e1;
+    dval = P.hh_beta1 * e1;
+  }
+}
+
+__device__ __forceinline__ void rb_VR(const Rebo2Dev &P, int ijpot, double dr, double &val, double &dval) {
+  double A, Q, al;
+  if (ijpot == RB_CC) { A = P.cc_A; Q = P.cc_Q; al = P.cc_alpha; }
+  else if (ijpot == RB_CH) { A = P.ch_A; Q = P.ch_Q; al = P.ch_alpha; }
+  else { A = P.hh_A; Q = P.hh_Q; al = P.hh_alpha; }
+  double e1 = A * exp(-al * dr);
+  double hlp1 = 1 + Q / dr;
+  val = hlp1 * e1;
+  dval = (-Q / (dr * dr) - hlp1 * al) * e1;
+}
+
+__device__ __forceinline__ void rb_poly5(const double *c, double x, double &h, double &dh) {
+  // h = c1 + c2 x + sum_{i=3..6} c_i x^(i-1)
+  double x2 = x * x, x3 = x2 * x, x4 = x3 * x, x5 = x4 * x;
+  h = c[0] + c[1] * x;
+  dh = c[1];
+  h = h + c[2] * x2; dh = dh + 2 * c[2] * x;
+  h = h + c[3] * x3; dh = dh + 3 * c[3] * x2;
+  h = h + c[4] * x4; dh = dh + 4 * c[4] * x3;
+  h = h + c[5] * x5; dh = dh + 5 * c[5] * x4;
+}
+
+__device__ __forceinline__ void rb_cc_g(const Rebo2Dev &P, const double *c, double costh, double &val,
+                                        double &dval) {
+  int j;
+  if (costh < P.cc_g_theta[1]) j = 0;
+  else if (costh < P.cc_g_theta[2]) j = 1;
+  else j = 2;
+  rb_poly5(&c[6 * j], costh, val, dval);
+}
+
+__device__ __forceinline__ void rb_g(const Rebo2Dev &P, int ktyp, double costh, double n, double &val,
+                                     double &dval, double &dvaldN) {
+  dvaldN = 0.0;
+  if (ktyp == RB_C) {
+    if (n < 3.2) rb_cc_g(P, P.g2c, costh, val, dval);
+    else if (n > P.n37) rb_cc_g(P, P.g1c, costh, val, dval);
+    else {
+      double v1, v2, dv1, dv2;
+      rb_cc_g(P, P.g1c, costh, v1, dv1);
+      rb_cc_g(P, P.g2c, costh, v2, dv2);
+      double sn, cs;
+      sincos(2 * RB_PI * (n - 3.2), &sn, &cs);
+      double s = (1 + cs) / 2, ds = -RB_PI * sn;
+      val = v1 * (1 - s) + v2 * s;
+      dval = dv1 * (1 - s) + dv2 * s;
+      dvaldN = (v2 - v1) * ds;
+    }
+  } else {
+    int ig = P.igh[(int)(-costh * 12.0) + 13 - 1];
+    rb_poly5(&P.spgh[6 * (ig - 1)], costh, val, dval);
+  }
+}
+
+__device__ __forceinline__ void rb_bo(const Rebo2Dev &P, int ktypi, double zij, double fcij, double faij,
+                                      double &bij, double &dfbij) {
+  double arg = 1.0 + zij;
+  bij = pow(arg, P.conpe[ktypi - 1]);
+  dfbij = P.conan[ktypi - 1] * fcij * faij * pow(arg, P.conpf[ktypi - 1]);
+}
+
+__device__ __forceinline__ void rb_h(const Rebo2Dev &P, int ijpot, int ikpot, double dr, double &val,
+                                     double &dval) {
+  if (ijpot + ikpot <= 4) { val = 1.0; dval = 0.0; }
+  else {
+    val = P.conear[(ijpot - 1) + 6 * (ikpot - 1)] * exp(P.conalp * dr);
+    dval = P.conalp * val;
+  }
+}
+
+__device__ __forceinline__ int rb_Z2pair(int a, int b) {
+  if (a == RB_C) return b;
+  if (b == RB_C) return a;
+  return a + b;
+}
+
+// ---- kernel 1: bond table + nn -------------------------------------------------------------
+
+__global__ void k_rebo2_bonds(int nat, int nbs, Mat3 A, Rebo2Dev P, const double4 *__restrict__ pos4,
+                              const long long *__restrict__ seed, const int2 *__restrict__ list,
+                              int *__restrict__ b_cnt, int *__restrict__ b_nb, int *__restrict__ b_typ,
+                              int *__restrict__ b_shift, int *__restrict__ b_slot,
+                              double4 *__restrict__ b_vec, double2 *__restrict__ b_cut,
+                              double2 *__restrict__ nn, int *__restrict__ flag,
+                              const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  double4 pi = pos4[s];
+  int ti = P.el2typ[(int)pi.w];
+  int nb = 0;
+  double nC = 0.0, nH = 0.0;
+  if (ti > 0) {
+    long long b0 = seed[s], b1 = seed[s + 1];
+    for (long long a = b0; a < b1; a++) {
+      int2 en = list[a];
+      double4 pj = pos4[en.x];
+      int tj = P.el2typ[(int)pj.w];
+      if (tj <= 0) continue;
+      double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+      if (en.y != ATX_SHIFT_ZERO) {
+        int sx, sy, sz;
+        atx_unpack_shift(en.y, sx, sy, sz);
+        double ax, ay, az;
+        atx_image_vector(A, sx, sy, sz, ax, ay, az);
+        dx -= ax; dy -= ay; dz -= az;
+      }
+      double r2 = dx * dx + dy * dy + dz * dz;
+      int ijpot = rb_Z2pair(ti, tj);
+      double l = P.cut_l[ijpot];
+      double fc, dfc, rl;
+      if (r2 < l * l) {
+        fc = 1.0; dfc = 0.0; rl = sqrt(r2);
+      } else if (r2 < P.cut_h2[ijpot]) {
+        rl = sqrt(r2);
+        double h = P.cut_h[ijpot];
+        // fCin with trig_off (rebo2_func.f90:63-85, cutoff.f90:152-196)
+        if (rl > h) { fc = 0.0; dfc = 0.0; }
+        else if (rl < l) { fc = 1.0; dfc = 0.0; }
+        else if (rl <= l) { fc = 1.0; dfc = 0.0; }
+        else if (rl >= h) { fc = 0.0; dfc = 0.0; }
+        else {
+          double sn, cs;
+          sincos(P.cut_fac[ijpot] * (rl - l), &sn, &cs);
+          fc = 0.5 * (1.0 + cs);
+          dfc = -0.5 * P.cut_fac[ijpot] * sn;
+        }
+      } else
+        continue;
+      if (nb >= nbs || nb >= RB_NBL) { atomicOr(flag, 1); break; }
+      size_t q = (size_t)s * nbs + nb;
+      b_nb[q] = en.x;
+      b_typ[q] = ijpot;
+      b_shift[q] = en.y;
+      b_slot[q] = (int)(a - b0);
+      b_vec[q] = make_double4(dx / rl, dy / rl, dz / rl, rl);
+      b_cut[q] = make_double2(fc, dfc);
+      if (tj == RB_C) nC += fc; else nH += fc;
+      nb++;
+    }
+  }
+  b_cnt[s] = nb;
+  nn[s] = make_double2(nC, nH);
+}
+
+// ---- kernel 2: energies and forces ------------------------------------------------------------
+
+__device__ __forceinline__ void rb_add3(double *f, int at, double x, double y, double z) {
+  atomicAdd(&f[3 * (size_t)at], x);
+  atomicAdd(&f[3 * (size_t)at + 1], y);
+  atomicAdd(&f[3 * (size_t)at + 2], z);
+}
+
+// w(a,b) += s * u(a) * v(b), column-major
+__device__ __forceinline__ void rb_outer(double *w, double s, double ux, double uy, double uz, double vx,
+                                         double vy, double vz) {
+  w[0] += s * ux * vx; w[1] += s * uy * vx; w[2] += s * uz * vx;
+  w[3] += s * ux * vy; w[4] += s * uy * vy; w[5] += s * uz * vy;
+  w[6] += s * ux * vz; w[7] += s * uy * vz; w[8] += s * uz * vz;
+}
+
+#define RB_BLOCK 64
+
+__global__ void __launch_bounds__(RB_BLOCK)
+k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
+              const int *__restrict__ b_cnt, const int *__restrict__ b_nb, const int *__restrict__ b_typ,
+              const int *__restrict__ b_shift, const int *__restrict__ b_slot,
+              const double4 *__restrict__ b_vec, const double2 *__restrict__ b_cut,
+              const double2 *__restrict__ nn, const double4 *__restrict__ pos4, double *__restrict__ f,
+              double *__restrict__ epa, double *__restrict__ wpa, double *__restrict__ epb,
+              double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
+              const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * (RB_BLOCK / 32)];
+  const int i = blockIdx.x * RB_BLOCK + threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+
+  const int ktypi = i < nat ? P.el2typ[(int)pos4[i].w] : 0;
+  const int nbi = (i < nat && ktypi > 0) ? b_cnt[i] : 0;
+  if (nbi > 0) {
+    const size_t qi = (size_t)i * nbs;
+    double fix = 0.0, fiy = 0.0, fiz = 0.0;
+    // ---- ik_loop1 (:1231-1317): conjugation inputs of the neighbours of i
+    double fxik[RB_NBL], dncx[RB_NBL];  // fconj(x_ik), fcik * dfconj/dx
+    double nconjit = 0.0;
+    for (int ik = 0; ik < nbi; ik++) {
+      int k = b_nb[qi + ik];
+      int tk = P.el2typ[(int)pos4[k].w];
+      fxik[ik] = 0.0;
+      dncx[ik] = 0.0;
+      if (tk == RB_C) {
+        double2 ck = b_cut[qi + ik];
+        double2 nk = nn[k];
+        double xik = nk.x + nk.y - ck.x, dfx;
+        rb_fconj(xik, fxik[ik], dfx);
+        dncx[ik] = ck.x * dfx;
+        nconjit += ck.x * fxik[ik];
+      }
+    }
+    const double2 nni = nn[i];
+
+    for (int ij = 0; ij < nbi; ij++) {
+      const int j = b_nb[qi + ij];
+      int jsx, jsy, jsz;
+      atx_unpack_shift(b_shift[qi + ij], jsx, jsy, jsz);
+      // j_gt_i (:1332): lexicographic sign of the shift, then index
+      const bool zero = (jsx == 0 && jsy == 0 && jsz == 0);
+      const bool pos = jsx != 0 ? jsx > 0 : (jsy != 0 ? jsy > 0 : jsz > 0);
+      if (!((zero && j > i) || pos)) continue;
+      const int ijpot = b_typ[qi + ij];
+      const double4 vij = b_vec[qi + ij];
+      const double rlij = vij.w;
+      if (!(rlij < P.cut_h[ijpot])) continue;
+      const int ktypj = P.el2typ[(int)pos4[j].w];
+      const double rlijr = 1.0 / rlij;
+      const double nx = vij.x, ny = vij.y, nz = vij.z;
+      const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
+      const double2 cij = b_cut[qi + ij];
+      const double fcarij = cij.x, dfcarijr = cij.y;
+      const double2 nnj = nn[j];
+      double niC = nni.x, niH = nni.y, njC = nnj.x, njH = nnj.y;
+      if (ktypj == RB_C) niC -= fcarij; else niH -= fcarij;
+      if (ktypi == RB_C) njC -= fcarij; else njH -= fcarij;
+      if (niC > 4.0) niC = 4.0;
+      if (niH > 4.0) niH = 4.0;
+      double nti = niC + niH;
+      if (njC > 4.0) njC = 4.0;
+      if (njH > 4.0) njH = 4.0;
+      double ntj = njC + njH;
+      double faij, dfaijr, frij, dfrijr;
+      rb_VA(P, ijpot, rlij, faij, dfaijr);
+      rb_VR(P, ijpot, rlij, frij, dfrijr);
+      double wij[9], wijb[9], wjib[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) { wij[q] = 0.0; wijb[q] = 0.0; wjib[q] = 0.0; }
+      double fjx = 0.0, fjy = 0.0, fjz = 0.0;
+      double zij = 0.0, dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0, dzdni = 0.0;
+      double nconji = 0.0;
+      double dbk[RB_NBL][3];
+
+      // ---- ik_loop2 (:1407-1587)
+      for (int ik = 0; ik < nbi; ik++) {
+        const double2 cik = b_cut[qi + ik];
+        if (ik == ij) {
+          nconji = nconjit - cik.x * fxik[ik];
+          continue;
+        }
+        const int ikpot = b_typ[qi + ik];
+        const double4 vik = b_vec[qi + ik];
+        const double rlik = vik.w;
+        if (!(rlik < P.cut_h[ikpot])) {
+          dbk[ik][0] = dbk[ik][1] = dbk[ik][2] = 0.0;
+          continue;
+        }
+        const double kx = vik.x, ky = vik.y, kz = vik.z;
+        const double fcik = cik.x, dfcikr = cik.y;
+        double qfacan, qfadan, gfacan, gddan, dgdn;
+        rb_h(P, ijpot, ikpot, rlij - rlik, qfacan, qfadan);
+        const double costh = kx * nx + ky * ny + kz * nz;
+        rb_g(P, ktypi, costh, nti, gfacan, gddan, dgdn);
+        double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
+        const double disjk = sqrt(ex * ex + ey * ey + ez * ez);
+        ex /= disjk; ey /= disjk; ez /= disjk;
+        const double dcsdij = 1.0 / rlik - costh * rlijr;
+        const double dcsdik = rlijr - costh / rlik;
+        const double dcsdjk = -disjk * rlijr / rlik;
+        dzdni += fcik * dgdn * qfacan;
+        const double dzfac = fcik * gddan * qfacan;
+        zij += fcik * gfacan * qfacan;
+        const double dzdrij = gfacan * fcik * qfadan;
+        const double dzdrik = gfacan * (dfcikr * qfacan - fcik * qfadan);
+        const double dfx = dzdrij * nx + dzfac * (dcsdij * nx - dcsdjk * ex);
+        const double dfy = dzdrij * ny + dzfac * (dcsdij * ny - dcsdjk * ey);
+        const double dfz = dzdrij * nz + dzfac * (dcsdij * nz - dcsdjk * ez);
+        dix += -dzdrij * nx - dzdrik * kx + dzfac * (-dcsdij * nx - dcsdik * kx);
+        diy += -dzdrij * ny - dzdrik * ky + dzfac * (-dcsdij * ny - dcsdik * ky);
+        diz += -dzdrij * nz - dzdrik * kz + dzfac * (-dcsdij * nz - dcsdik * kz);
+        djx += dfx; djy += dfy; djz += dfz;
+        const double kx_ = dzdrik * kx + dzfac * (dcsdik * kx + dcsdjk * ex);
+        const double ky_ = dzdrik * ky + dzfac * (dcsdik * ky + dcsdjk * ey);
+        const double kz_ = dzdrik * kz + dzfac * (dcsdik * kz + dcsdjk * ez);
+        dbk[ik][0] = kx_; dbk[ik][1] = ky_; dbk[ik][2] = kz_;
+        rb_outer(wijb, -1.0, rijx, rijy, rijz, dfx, dfy, dfz);
+        rb_outer(wijb, -1.0, rlik * kx, rlik * ky, rlik * kz, kx_, ky_, kz_);
+      }
+
+      double pij = 0.0, dpdnci = 0.0, dpdnhi = 0.0;
+      if (ktypi == RB_C) {
+        rb_table2d(ijpot == RB_CC ? P.Pcc : P.Pch, 5, 5, niH, niC, pij, dpdnhi, dpdnci);
+        zij += pij;
+        dpdnci += dzdni;
+        dpdnhi += dzdni;
+      }
+      double bij, dfbij;
+      rb_bo(P, ktypi, zij, fcarij, faij, bij, dfbij);
+
+      // ---- jl_loop (:1644-1887)
+      const size_t qj = (size_t)j * nbs;
+      const int nbj = b_cnt[j];
+      double zji = 0.0, bix = 0, biy = 0, biz = 0, bjx = 0, bjy = 0, bjz = 0, dzdnj = 0.0;
+      double nconjj = 0.0;
+      double dbl[RB_NBL][3];
+      double fxjl[RB_NBL], dnlx[RB_NBL];
+      for (int jl = 0; jl < nbj; jl++) {
+        fxjl[jl] = 0.0; dnlx[jl] = 0.0;
+        dbl[jl][0] = dbl[jl][1] = dbl[jl][2] = 0.0;
+        const int l = b_nb[qj + jl];
+        int lsx, lsy, lsz;
+        atx_unpack_shift(b_shift[qj + jl], lsx, lsy, lsz);
+        lsx += jsx; lsy += jsy; lsz += jsz;
+        if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;   // l_neq_i
+        const int ktypl = P.el2typ[(int)pos4[l].w];
+        const int jlpot = b_typ[qj + jl];
+        const double4 vjl = b_vec[qj + jl];
+        const double rljl = vjl.w;
+        const double lx = vjl.x, ly = vjl.y, lz = vjl.z;
+        const double2 cjl = b_cut[qj + jl];
+        const double fcjl = cjl.x, dfcjlr = cjl.y;
+        if (ktypl == RB_C) {
+          double2 nl_ = nn[l];
+          double xjl = nl_.x + nl_.y - fcjl, dfx;
+          rb_fconj(xjl, fxjl[jl], dfx);
+          dnlx[jl] = fcjl * dfx;
+          nconjj += fcjl * fxjl[jl];
+        }
+        if (rljl < P.cut_h[jlpot]) {
+          double qfacan, qfadan, gfacan, gddan, dgdn;
+          rb_h(P, ijpot, jlpot, rlij - rljl, qfacan, qfadan);
+          const double costh = -(lx * nx + ly * ny + lz * nz);
+          rb_g(P, ktypj, costh, ntj, gfacan, gddan, dgdn);
+          double ex = lx * rljl + nx * rlij, ey = ly * rljl + ny * rlij, ez = lz * rljl + nz * rlij;
+          const double disil = sqrt(ex * ex + ey * ey + ez * ez);
+          ex /= disil; ey /= disil; ez /= disil;
+          const double dcsdji = 1.0 / rljl - costh * rlijr;
+          const double dcsdjl = rlijr - costh / rljl;
+          const double dcsdil = -disil * rlijr / rljl;
+          dzdnj += fcjl * dgdn * qfacan;
+          const double dzfac = fcjl * gddan * qfacan;
+          zji += fcjl * gfacan * qfacan;
+          const double dzdrji = gfacan * fcjl * qfadan;
+          const double dzdrjl = gfacan * (dfcjlr * qfacan - fcjl * qfadan);
+          bjx += dzdrji * nx - dzdrjl * lx + dzfac * (dcsdji * nx - dcsdjl * lx);
+          bjy += dzdrji * ny - dzdrjl * ly + dzfac * (dcsdji * ny - dcsdjl * ly);
+          bjz += dzdrji * nz - dzdrjl * lz + dzfac * (dcsdji * nz - dcsdjl * lz);
+          const double dfx = -dzdrji * nx + dzfac * (-dcsdji * nx - dcsdil * ex);
+          const double dfy = -dzdrji * ny + dzfac * (-dcsdji * ny - dcsdil * ey);
+          const double dfz = -dzdrji * nz + dzfac * (-dcsdji * nz - dcsdil * ez);
+          bix += dfx; biy += dfy; biz += dfz;
+          const double lx_ = dzdrjl * lx + dzfac * (dcsdjl * lx + dcsdil * ex);
+          const double ly_ = dzdrjl * ly + dzfac * (dcsdjl * ly + dcsdil * ey);
+          const double lz_ = dzdrjl * lz + dzfac * (dcsdjl * lz + dcsdil * ez);
+          dbl[jl][0] = lx_; dbl[jl][1] = ly_; dbl[jl][2] = lz_;
+          rb_outer(wjib, 1.0, rijx, rijy, rijz, dfx, dfy, dfz);
+          rb_outer(wjib, -1.0, rljl * lx, rljl * ly, rljl * lz, lx_, ly_, lz_);
+        }
+      }
+
+      double pji = 0.0, dpdncj = 0.0, dpdnhj = 0.0;
+      if (ktypj == RB_C) {
+        rb_table2d(ijpot == RB_CC ? P.Pcc : P.Pch, 5, 5, njH, njC, pji, dpdnhj, dpdncj);
+        zji += pji;
+        dpdncj += dzdnj;
+        dpdnhj += dzdnj;
+      }
+      double bji, dfbji;
+      rb_bo(P, ktypj, zji, fcarij, faij, bji, dfbji);
+
+      double nconj = nconji * nconji + nconjj * nconjj;
+      if (nconj > 8.0) nconj = 8.0;
+      if (nti > 3.0) nti = 3.0;
+      if (ntj > 3.0) ntj = 3.0;
+
+      // ---- dihedral (:1950-2087), only when with_dihedral
+      double bdh = 0.0, tij = 0.0, dtdni = 0.0, dtdnj = 0.0, dtdncn = 0.0;
+      if (P.with_dihedral && ijpot == RB_CC) {
+        rb_table3d(P.Tcc, 4, 4, 9, nti, ntj, nconj, tij, dtdni, dtdnj, dtdncn);
+        const double tije = tij * faij * fcarij;
+        if (tij != 0) {
+          for (int ik = 0; ik < nbi; ik++) {
+            if (ik == ij) continue;
+            const int k = b_nb[qi + ik];
+            int ksx, ksy, ksz;
+            atx_unpack_shift(b_shift[qi + ik], ksx, ksy, ksz);
+            const double4 vik = b_vec[qi + ik];
+            const double rlik = vik.w, kx = vik.x, ky = vik.y, kz = vik.z;
+            const double2 cik = b_cut[qi + ik];
+            const double fcik = cik.x, dfcikr = cik.y;
+            const double dot_ij_ik = nx * kx + ny * ky + nz * kz;
+            const double dcik = 1.0 - dot_ij_ik * dot_ij_ik;
+            for (int jl = 0; jl < nbj; jl++) {
+              const int l = b_nb[qj + jl];
+              int lsx, lsy, lsz;
+              atx_unpack_shift(b_shift[qj + jl], lsx, lsy, lsz);
+              lsx += jsx; lsy += jsy; lsz += jsz;
+              if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;
+              if (l == k && lsx == ksx && lsy == ksy && lsz == ksz) continue;
+              const double4 vjl = b_vec[qj + jl];
+              const double rljl = vjl.w, lx = vjl.x, ly = vjl.y, lz = vjl.z;
+              const double2 cjl = b_cut[qj + jl];
+              const double fcjl = cjl.x, dfcjlr = cjl.y;
+              const double dot_ij_jl = nx * lx + ny * ly + nz * lz;
+              const double dot_ik_jl = kx * lx + ky * ly + kz * lz;
+              const double dcjl = 1.0 - dot_ij_jl * dot_ij_jl;
+              const double abs_dc = sqrt(dcik * dcjl);
+              const double cost = (dot_ij_ik * dot_ij_jl - dot_ik_jl) / abs_dc;
+              double bdhij = 1 - cost * cost;
+              bdh += bdhij * fcik * fcjl;
+              bdhij = bdhij * tij * faij * fcarij / 2;
+              const double dbdhij = -2 * cost * tije * fcik * fcjl / 2;
+              const double a1 = dot_ij_jl / abs_dc + cost * dot_ij_ik / dcik;
+              const double a2 = dot_ij_ik / abs_dc + cost * dot_ij_jl / dcjl;
+              const double a3 = 2 * dot_ik_jl / abs_dc + cost * (1.0 / dcik + 1.0 / dcjl);
+              double dx_ = dbdhij * (a1 * kx + a2 * lx - a3 * nx) / rlij;
+              double dy_ = dbdhij * (a1 * ky + a2 * ly - a3 * ny) / rlij;
+              double dz_ = dbdhij * (a1 * kz + a2 * lz - a3 * nz) / rlij;
+              fix += dx_; fiy += dy_; fiz += dz_;
+              fjx -= dx_; fjy -= dy_; fjz -= dz_;
+              rb_outer(wij, 1.0, rijx, rijy, rijz, dx_, dy_, dz_);
+              dx_ = dbdhij * (-1.0 / dcik * cost * kx - 1.0 / abs_dc * lx + a1 * nx) / rlik + bdhij * dfcikr * fcjl * kx;
+              dy_ = dbdhij * (-1.0 / dcik * cost * ky - 1.0 / abs_dc * ly + a1 * ny) / rlik + bdhij * dfcikr * fcjl * ky;
+              dz_ = dbdhij * (-1.0 / dcik * cost * kz - 1.0 / abs_dc * lz + a1 * nz) / rlik + bdhij * dfcikr * fcjl * kz;
+              fix += dx_; fiy += dy_; fiz += dz_;
+              rb_add3(f, k, -dx_, -dy_, -dz_);
+              rb_outer(wij, 1.0, rlik * kx, rlik * ky, rlik * kz, dx_, dy_, dz_);
+              dx_ = dbdhij * (-1.0 / dcjl * cost * lx - 1.0 / abs_dc * kx + a2 * nx) / rljl + bdhij * fcik * dfcjlr * lx;
+              dy_ = dbdhij * (-1.0 / dcjl * cost * ly - 1.0 / abs_dc * ky + a2 * ny) / rljl + bdhij * fcik * dfcjlr * ly;
+              dz_ = dbdhij * (-1.0 / dcjl * cost * lz - 1.0 / abs_dc * kz + a2 * nz) / rljl + bdhij * fcik * dfcjlr * lz;
+              fjx += dx_; fjy += dy_; fjz += dz_;
+              rb_add3(f, l, -dx_, -dy_, -dz_);
+              rb_outer(wij, 1.0, rljl * lx, rljl * ly, rljl * lz, dx_, dy_, dz_);
+            }
+          }
+        }
+      }
+
+      double fij = 0.0, dfdni = 0.0, dfdnj = 0.0, dfdncn = 0.0;
+      if (ijpot == RB_CC) rb_table3d(P.Fcc, 4, 4, 9, nti, ntj, nconj, fij, dfdni, dfdnj, dfdncn);
+      else if (ijpot == RB_HH) rb_table3d(P.Fhh, 4, 4, 9, nti, ntj, nconj, fij, dfdni, dfdnj, dfdncn);
+      else if (ktypi == RB_C) rb_table3d(P.Fch, 4, 4, 9, ntj, nti, nconj, fij, dfdnj, dfdni, dfdncn);
+      else if (ktypj == RB_C) rb_table3d(P.Fch, 4, 4, 9, nti, ntj, nconj, fij, dfdni, dfdnj, dfdncn);
+      dfdni += dtdni * bdh;
+      dfdnj += dtdnj * bdh;
+      dfdncn += dtdncn * bdh;
+      dfdni = 0.5 * fcarij * faij * dfdni;
+      dfdnj = 0.5 * fcarij * faij * dfdnj;
+      dfdncn = 0.5 * fcarij * faij * dfdncn;
+      const double dfdncni = 2 * dfdncn * nconji;
+      const double dfdncnj = 2 * dfdncn * nconjj;
+
+      // ---- forces through N_i, N^conj_i on the neighbours k of i and their neighbours m (:2433-2470)
+      for (int ik = 0; ik < nbi; ik++) {
+        if (ik == ij) continue;
+        const int k = b_nb[qi + ik];
+        const int tk = P.el2typ[(int)pos4[k].w];
+        const double4 vik = b_vec[qi + ik];
+        const double2 cik = b_cut[qi + ik];
+        // dnidk(:, ikc, type) = rnik*dfcikr for the type of k, 0 for the other type
+        const double sC = (tk == RB_C) ? cik.y : 0.0, sH = (tk == RB_H) ? cik.y : 0.0;
+        const double dncdk = fxik[ik] * cik.y;  // dncnidk = nconjdr * rnik (0 unless k is C)
+        const double pref = -(dfdni * (sC + sH) + dfdncni * dncdk) - dfbij * (dpdnci * sC + dpdnhi * sH);
+        const double dx_ = pref * vik.x, dy_ = pref * vik.y, dz_ = pref * vik.z;
+        double fkx = dx_, fky = dy_, fkz = dz_;
+        fix -= dx_; fiy -= dy_; fiz -= dz_;
+        rb_outer(wij, -1.0, vik.w * vik.x, vik.w * vik.y, vik.w * vik.z, dx_, dy_, dz_);
+        if (tk == RB_C && dfdncni * dncx[ik] != 0.0) {
+          int ksx, ksy, ksz;
+          atx_unpack_shift(b_shift[qi + ik], ksx, ksy, ksz);
+          const size_t qk = (size_t)k * nbs;
+          const int nbk = b_cnt[k];
+          for (int km = 0; km < nbk; km++) {
+            const int m = b_nb[qk + km];
+            int msx, msy, msz;
+            atx_unpack_shift(b_shift[qk + km], msx, msy, msz);
+            if (m == i && msx + ksx == 0 && msy + ksy == 0 && msz + ksz == 0) continue;
+            const double4 vkm = b_vec[qk + km];
+            const double c = -dfdncni * dncx[ik] * b_cut[qk + km].y;
+            const double mx = c * vkm.x, my = c * vkm.y, mz = c * vkm.z;
+            rb_add3(f, m, mx, my, mz);
+            fkx -= mx; fky -= my; fkz -= mz;
+            rb_outer(wij, -1.0, vkm.w * vkm.x, vkm.w * vkm.y, vkm.w * vkm.z, mx, my, mz);
+          }
+        }
+        // bond-order force on k (:2650-2662)
+        fkx += -dfbij * dbk[ik][0]; fky += -dfbij * dbk[ik][1]; fkz += -dfbij * dbk[ik][2];
+        rb_add3(f, k, fkx, fky, fkz);
+      }
+      // ---- same on the j side (:2472-2517)
+      for (int jl = 0; jl < nbj; jl++) {
+        const int l = b_nb[qj + jl];
+        int lsx, lsy, lsz;
+        atx_unpack_shift(b_shift[qj + jl], lsx, lsy, lsz);
+        lsx += jsx; lsy += jsy; lsz += jsz;
+        if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;
+        const int tl = P.el2typ[(int)pos4[l].w];
+        const double4 vjl = b_vec[qj + jl];
+        const double2 cjl = b_cut[qj + jl];
+        const double sC = (tl == RB_C) ? cjl.y : 0.0, sH = (tl == RB_H) ? cjl.y : 0.0;
+        const double dncdl = fxjl[jl] * cjl.y;
+        const double pref = -(dfdnj * (sC + sH) + dfdncnj * dncdl) - dfbji * (dpdncj * sC + dpdnhj * sH);
+        const double dx_ = pref * vjl.x, dy_ = pref * vjl.y, dz_ = pref * vjl.z;
+        double flx = dx_, fly = dy_, flz = dz_;
+        fjx -= dx_; fjy -= dy_; fjz -= dz_;
+        rb_outer(wij, -1.0, vjl.w * vjl.x, vjl.w * vjl.y, vjl.w * vjl.z, dx_, dy_, dz_);
+        if (tl == RB_C && dfdncnj * dnlx[jl] != 0.0) {
+          const size_t ql = (size_t)l * nbs;
+          const int nbl = b_cnt[l];
+          for (int ln = 0; ln < nbl; ln++) {
+            const int n = b_nb[ql + ln];
+            int nsx, nsy, nsz;
+            atx_unpack_shift(b_shift[ql + ln], nsx, nsy, nsz);
+            // n /= j .or. ndc /= jdc with ndc = ldc + dcell(ln)
+            if (n == j && nsx + lsx == jsx && nsy + lsy == jsy && nsz + lsz == jsz) continue;
+            const double4 vln = b_vec[ql + ln];
+            const double c = -dfdncnj * dnlx[jl] * b_cut[ql + ln].y;
+            const double mx = c * vln.x, my = c * vln.y, mz = c * vln.z;
+            rb_add3(f, n, mx, my, mz);
+            flx -= mx; fly -= my; flz -= mz;
+            rb_outer(wij, -1.0, vln.w * vln.x, vln.w * vln.y, vln.w * vln.z, mx, my, mz);
+          }
+        }
+        flx += -dfbji * dbl[jl][0]; fly += -dfbji * dbl[jl][1]; flz += -dfbji * dbl[jl][2];
+        rb_add3(f, l, flx, fly, flz);
+      }
+
+      // ---- pair terms (:2525-2716)
+      const double baveij = 0.5 * (bij + bji + fij + tij * bdh);
+      const double hlfvij = fcarij * (frij + baveij * faij) / 2;
+      acc[0] += 2 * hlfvij;
+      if (epa) {
+        atomicAdd(&epa[i], hlfvij);
+        atomicAdd(&epa[j], hlfvij);
+      }
+      const double dffac = dfrijr * fcarij + baveij * dfaijr * fcarij + frij * dfcarijr + baveij * faij * dfcarijr;
+      const double dfx = dffac * nx, dfy = dffac * ny, dfz = dffac * nz;
+      fix += dfx; fiy += dfy; fiz += dfz;
+      fjx -= dfx; fjy -= dfy; fjz -= dfz;
+      rb_outer(wij, 1.0, rijx, rijy, rijz, dfx, dfy, dfz);
+#pragma unroll
+      for (int q = 0; q < 9; q++) wij[q] = wij[q] - dfbij * wijb[q] - dfbji * wjib[q];
+      fix += -(dfbij * dix + dfbji * bix); fiy += -(dfbij * diy + dfbji * biy); fiz += -(dfbij * diz + dfbji * biz);
+      fjx += -(dfbij * djx + dfbji * bjx); fjy += -(dfbij * djy + dfbji * bjy); fjz += -(dfbij * djz + dfbji * bjz);
+      rb_add3(f, j, fjx, fjy, fjz);
+#pragma unroll
+      for (int q = 0; q < 9; q++) acc[1 + q] += wij[q];
+      const long long a = seed[i] + b_slot[qi + ij];
+      if (epb) epb[a] = 2 * hlfvij;
+      if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
+      if (wpb) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) wpb[9 * a + q] = wij[q];
+      }
+      if (wpa) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          atomicAdd(&wpa[9 * (size_t)i + q], 0.5 * wij[q]);
+          atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * wij[q]);
+        }
+      }
+    }
+    rb_add3(f, i, fix, fiy, fiz);
+  }
+  atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)blockIdx.x * ATX_NSUM + k] = acc[k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+
+extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_rebo2 **out) {
+  if (!ctx || !par || !out) return ATX_ERROR_UNSPECIFIED;
+  atx_rebo2 *pot = new atx_rebo2();
+  pot->ctx = ctx;
+  Rebo2Dev &D = pot->dev;
+  D.cc_B1 = par->cc_B1; D.cc_B2 = par->cc_B2; D.cc_B3 = par->cc_B3;
+  D.cc_beta1 = par->cc_beta1; D.cc_beta2 = par->cc_beta2; D.cc_beta3 = par->cc_beta3;
+  D.cc_Q = par->cc_Q; D.cc_A = par->cc_A; D.cc_alpha = par->cc_alpha;
+  D.ch_B1 = par->ch_B1; D.ch_beta1 = par->ch_beta1; D.ch_Q = par->ch_Q; D.ch_A = par->ch_A;
+  D.ch_alpha = par->ch_alpha;
+  D.hh_B1 = par->hh_B1; D.hh_beta1 = par->hh_beta1; D.hh_Q = par->hh_Q; D.hh_A = par->hh_A;
+  D.hh_alpha = par->hh_alpha;
+  for (int i = 0; i < 6; i++) D.cc_g_theta[i] = par->cc_g_theta[i];
+  for (int i = 0; i < 18; i++) {
+    D.g1c[i] = par->cc_g1_coeff[i];
+    D.g2c[i] = par->cc_g2_coeff[i];
+    D.spgh[i] = par->spgh[i];
+  }
+  for (int i = 0; i < 25; i++) D.igh[i] = par->igh[i];
+  D.conalp = par->conalp;
+  for (int i = 0; i < 36; i++) D.conear[i] = par->conear[i];
+  for (int i = 0; i < 3; i++) {
+    D.conpe[i] = par->conpe[i];
+    D.conan[i] = par->conan[i];
+    D.conpf[i] = par->conpf[i];
+  }
+  for (int i = 0; i < 7; i++) D.cut_l[i] = D.cut_h[i] = D.cut_h2[i] = D.cut_fac[i] = 0.0;
+  for (int t : {RB_CC, RB_CH, RB_HH}) {
+    D.cut_l[t] = par->cut_in_l[t - 1];
+    D.cut_h[t] = par->cut_in_h[t - 1];
+    D.cut_h2[t] = par->cut_in_h2[t - 1];
+    D.cut_fac[t] = RB_PI / (D.cut_h[t] - D.cut_l[t]);
+  }
+  D.with_dihedral = par->with_dihedral;
+  D.n37 = (double)3.7f;
+  const size_t n3 = 144 * 64, n2 = 25 * 16;
+  ATX_PASS(pot->tables.reserve(4 * n3 + 2 * n2));
+  double *t = pot->tables.ptr;
+  const double *src3[4] = {par->Fcc, par->Fch, par->Fhh, par->Tcc};
+  for (int k = 0; k < 4; k++)
+    ATX_CUDA(cudaMemcpy(t + k * n3, src3[k], sizeof(double) * n3, cudaMemcpyHostToDevice));
+  ATX_CUDA(cudaMemcpy(t + 4 * n3, par->Pcc, sizeof(double) * n2, cudaMemcpyHostToDevice));
+  ATX_CUDA(cudaMemcpy(t + 4 * n3 + n2, par->Pch, sizeof(double) * n2, cudaMemcpyHostToDevice));
+  D.Fcc = t; D.Fch = t + n3; D.Fhh = t + 2 * n3; D.Tcc = t + 3 * n3;
+  D.Pcc = t + 4 * n3; D.Pch = t + 4 * n3 + n2;
+  for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
+  ATX_PASS(pot->flag.reserve(4));
+  *out = pot;
+  return 0;
+}
+
+extern "C" int atx_rebo2_destroy(atx_rebo2 *pot) {
+  delete pot;
+  return 0;
+}
+
+extern "C" int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, int nel,
+                                 const int *el2Z) {
+  if (nel > 31) {
+    atx_set_error("Too many particle element ids.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  Rebo2Dev &D = pot->dev;
+  bool hasC = false, hasH = false;
+  for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
+  for (int k = 0; k < nel; k++) {
+    if (el2Z[k] == 6) { D.el2typ[k + 1] = RB_C; hasC = true; }
+    else if (el2Z[k] == 1) { D.el2typ[k + 1] = RB_H; hasH = true; }
+  }
+  // rebo2_module.f90:96-125
+  if (nl) {
+    if (hasC) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_CC]));
+    if (hasC && hasH) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_CH]));
+    if (hasH) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_HH]));
+  }
+  pot->bound = true;
+  return 0;
+}
+
+static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o,
+                         double *epb, double *fpb, double *wpb) {
+  atx_ctx *ctx = pot->ctx;
+  cudaStream_t st = ctx->stream;
+  int nat = nl->nat;
+  int nbs = nl->nebmax < 1 ? 1 : nl->nebmax;
+  if (nbs > RB_NBL) nbs = RB_NBL;
+  pot->nbs = nbs;
+  size_t nt = (size_t)nat * nbs + 1;
+  ATX_PASS(pot->b_cnt.reserve(nat + 1));
+  ATX_PASS(pot->b_nb.reserve(nt));
+  ATX_PASS(pot->b_typ.reserve(nt));
+  ATX_PASS(pot->b_shift.reserve(nt));
+  ATX_PASS(pot->b_slot.reserve(nt));
+  ATX_PASS(pot->b_vec.reserve(nt));
+  ATX_PASS(pot->b_cut.reserve(nt));
+  ATX_PASS(pot->nn.reserve(nat + 1));
+  int nblocks = (nat + RB_BLOCK - 1) / RB_BLOCK;
+  if (nblocks < 1) nblocks = 1;
+  ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
+  if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  // forces are accumulated with atomics: start from zero (guarded runs zero inside the MD driver)
+  ATX_CUDA(cudaMemsetAsync(o.f, 0, sizeof(double) * 3 * (size_t)nat, st));
+  if (o.epa) ATX_CUDA(cudaMemsetAsync(o.epa, 0, sizeof(double) * (size_t)nat, st));
+  if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
+  if (nat > 0) {
+    k_rebo2_bonds<<<(nat + 127) / 128, 128, 0, st>>>(nat, nbs, p->Abox, pot->dev, nl->pos4.ptr,
+                                                     nl->seed.ptr, nl->list.ptr, pot->b_cnt.ptr,
+                                                     pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
+                                                     pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr,
+                                                     pot->nn.ptr, pot->flag.ptr, o.stop);
+    ATX_LAUNCHED();
+  }
+  {
+    ProfScope ps_(ctx, "rebo2_force");
+    k_rebo2_force<<<nblocks, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr,
+                                                pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
+                                                pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr,
+                                                pot->nn.ptr, nl->pos4.ptr, o.f, o.epa, o.wpa, epb, fpb,
+                                                wpb, pot->sc.partials.ptr, o.stop);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  return 0;
+}
+
+int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o) {
+  return rebo2_compute(pot, p, nl, o, nullptr, nullptr, nullptr);
+}
+
+int atx_perbond_to_host(atx_ctx *ctx, atx_neighbors *nl, int ncomp, const double *dev_slots,
+                        double *host, PinBuf<double> &stage);
+
+extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl,
+                                           double *epot, double *f, double *wpot,
+                                           double *epot_per_at, double *epot_per_bond,
+                                           double *f_per_bond, double *wpot_per_at,
+                                           double *wpot_per_bond) {
+  if (!pot->bound) {
+    atx_set_error("bind_to has not been called on this potential.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  atx_ctx *ctx = pot->ctx;
+  ATX_PASS(atx_neighbors_update(nl, p));
+  PotOut o;
+  ATX_PASS(pot->sc.f.reserve(3 * (size_t)nl->nat + 3));
+  ATX_PASS(pot->sc.sums.reserve(ATX_NSUM));
+  o.f = pot->sc.f.ptr;
+  o.sums = pot->sc.sums.ptr;
+  if (epot_per_at) {
+    ATX_PASS(pot->epa_out.reserve((size_t)nl->nat + 1));
+    o.epa = pot->epa_out.ptr;
+  }
+  if (wpot_per_at) {
+    ATX_PASS(pot->sc.wpa.reserve(9 * (size_t)nl->nat + 9));
+    o.wpa = pot->sc.wpa.ptr;
+  }
+  size_t nslots = (size_t)nl->npairs + 1;
+  double *epb = nullptr, *fpb = nullptr, *wpb = nullptr;
+  if (epot_per_bond) {
+    ATX_PASS(pot->epb.reserve(nslots));
+    ATX_CUDA(cudaMemsetAsync(pot->epb.ptr, 0, sizeof(double) * nslots, ctx->stream));
+    epb = pot->epb.ptr;
+  }
+  if (f_per_bond) {
+    ATX_PASS(pot->fpb.reserve(3 * nslots));
+    ATX_CUDA(cudaMemsetAsync(pot->fpb.ptr, 0, sizeof(double) * 3 * nslots, ctx->stream));
+    fpb = pot->fpb.ptr;
+  }
+  if (wpot_per_bond) {
+    ATX_PASS(pot->wpb.reserve(9 * nslots));
+    ATX_CUDA(cudaMemsetAsync(pot->wpb.ptr, 0, sizeof(double) * 9 * nslots, ctx->stream));
+    wpb = pot->wpb.ptr;
+  }
+  ATX_PASS(rebo2_compute(pot, p, nl, o, epb, fpb, wpb));
+  int h = 0;
+  ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h) {
+    atx_set_error("Internal neighbor list exhausted, *nebmax* too small.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  if (epb) ATX_PASS(atx_perbond_to_host(ctx, nl, 1, epb, epot_per_bond, pot->sc.stage));
+  if (fpb) ATX_PASS(atx_perbond_to_host(ctx, nl, 3, fpb, f_per_bond, pot->sc.stage));
+  if (wpb) ATX_PASS(atx_perbond_to_host(ctx, nl, 9, wpb, wpot_per_bond, pot->sc.stage));
+  return atx_finish_to_host(ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
+}

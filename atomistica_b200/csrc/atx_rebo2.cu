@@ -312,7 +312,8 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
               const int *__restrict__ b_cnt, const int *__restrict__ b_nb, const int *__restrict__ b_typ,
               const int *__restrict__ b_shift, const int *__restrict__ b_slot,
               const double4 *__restrict__ b_vec, const double2 *__restrict__ b_cut,
-              const double2 *__restrict__ nn, const double4 *__restrict__ pos4, double *__restrict__ f,
+              const double2 *__restrict__ nn, const double4 *__restrict__ pos4,
+              const int *__restrict__ order, double *__restrict__ f,
               double *__restrict__ epa, double *__restrict__ wpa, double *__restrict__ epb,
               double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
               const int *__restrict__ stop) {
@@ -354,7 +355,9 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
       // j_gt_i (:1332): lexicographic sign of the shift, then index
       const bool zero = (jsx == 0 && jsy == 0 && jsz == 0);
       const bool pos = jsx != 0 ? jsx > 0 : (jsy != 0 ? jsy > 0 : jsz > 0);
-      if (!((zero && j > i) || pos)) continue;
+      // the index comparison is made in ORIGINAL atom numbering so that per-bond outputs land in
+      // the same list slot as in the reference
+      if (!((zero && order[j] > order[i]) || pos)) continue;
       const int ijpot = b_typ[qi + ij];
       const double4 vij = b_vec[qi + ij];
       const double rlij = vij.w;
@@ -833,7 +836,7 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
     k_rebo2_force<<<nblocks, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr,
                                                 pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
                                                 pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr,
-                                                pot->nn.ptr, nl->pos4.ptr, o.f, o.epa, o.wpa, epb, fpb,
+                                                pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa, o.wpa, epb, fpb,
                                                 wpb, pot->sc.partials.ptr, o.stop);
     ATX_LAUNCHED();
   }

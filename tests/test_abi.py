@@ -1,0 +1,99 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol include/*.h declares, its
+host-side init helpers agree with the oracle's independent numpy implementation, and it fails
+loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from atomistica_b200 import _lib as L, io, parameters as P
+from conftest import ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, 'include', 'atomistica_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    return sorted(set(re.findall(r'\b(atx_[a-z0-9_]+)\s*\(', hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()
+    decl = _declared_symbols()
+    assert len(decl) >= 40
+    for s in decl:
+        assert hasattr(lib, s), 'missing symbol ' + s
+    assert sorted(L.SYMBOLS) == decl
+
+
+def test_no_cpu_fallback():
+    import subprocess
+    have_gpu = subprocess.run(['nvidia-smi', '-L'], capture_output=True).returncode == 0 \
+        if os.path.exists('/usr/bin/nvidia-smi') else False
+    if have_gpu:
+        pytest.skip('a GPU is present')
+    h = C.c_void_p()
+    err = L.lib().atx_ctx_create(0, C.byref(h))
+    assert err != 0
+    assert 'no CPU fallback' in L.last_error()
+    from atomistica_b200 import native
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        native.Particles()
+
+
+def test_host_spline_init_matches_oracle(cu_setfl):
+    y = cu_setfl['rho'][0]
+    n, dx = len(y), float(cu_setfl['dr'])
+    arrs = [np.zeros(n), np.zeros(n)] + [np.zeros(n - 1) for _ in range(6)]
+    L.check(L.lib().atx_host_spline_init(n, C.c_double(0.0), C.c_double(dx), L.dptr(L.as_f64(y)),
+                                         *[L.dptr(a) for a in arrs]))
+    s = oracle.spline_init(n, 0.0, dx, y)
+    for a, k in zip(arrs, ('y', 'd2y', 'c1', 'c2', 'c3', 'd1', 'd2', 'd3')):
+        assert np.allclose(a, s[k], rtol=1e-13, atol=1e-300), k
+
+
+def test_host_gaussn():
+    rng = np.random.RandomState(0)
+    A = rng.rand(7, 7) + 3 * np.eye(7)
+    B = rng.rand(7, 4)
+    Af = np.asfortranarray(A).ravel(order='F').copy()
+    Bf = np.asfortranarray(B).ravel(order='F').copy()
+    L.check(L.lib().atx_host_gaussn(7, L.dptr(Af), 4, L.dptr(Bf)))
+    assert np.allclose(Bf.reshape(4, 7).T, np.linalg.solve(A, B), rtol=1e-12)
+    Z = np.zeros(9)
+    assert L.lib().atx_host_gaussn(3, L.dptr(Z), 1, L.dptr(np.ones(3))) != 0
+    assert 'singular' in L.last_error()
+
+
+def test_host_tables_match_oracle():
+    from atomistica_b200 import rebo2_tables as T
+    d, tabs, p, keep = T.build_params({})
+    rb = oracle.Rebo2()
+    for k in ('Fcc', 'Fch', 'Fhh', 'Tcc', 'Pcc', 'Pch'):
+        assert np.allclose(keep[k], rb._keep[k], rtol=1e-10, atol=1e-13), k
+    assert np.allclose(np.array(p.cc_g1_coeff), np.array(rb.p.cc_g1_coeff), rtol=1e-9, atol=1e-12)
+    assert np.allclose(np.array(p.cc_g2_coeff), np.array(rb.p.cc_g2_coeff), rtol=1e-9, atol=1e-12)
+    assert np.allclose(np.array(p.conear), np.array(rb.p.conear))
+    for k in tabs:
+        assert np.array_equal(tabs[k], rb.tabs[k]), k
+
+
+def test_setfl_roundtrip(tmp_path, cu_setfl):
+    fn = str(tmp_path / 'Cu.eam.alloy')
+    io.write_setfl(fn, cu_setfl)
+    t = io.read_setfl(fn)
+    assert t['names'] == ['Cu'] and t['nF'] == 10001 and t['nr'] == 10001
+    assert t['cutoff'] == float(cu_setfl['cutoff'])
+    for k in ('F', 'rho', 'rphi'):
+        assert np.array_equal(t[k], cu_setfl[k])
+
+
+def test_parameter_completion():
+    db = P.complete('Tersoff', P.Goumri_Said_ChemPhys_302_135_Al_N)
+    assert db['omega'] == [1.0, 1.0, 1.0] and db['mubo'] == [0.0, 0.0, 0.0] and db['m'] == [1, 1, 1]
+    assert P.complete('Kumagai', None)['r2'] == [3.30]
+    assert P.pair_index(0, 1, 2) == 1 and P.pair_index(1, 1, 2) == 2 and P.pair_index(2, 1, 3) == 4
+    m = P.Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N
+    assert abs(m['A'][1] - np.sqrt(1.3936e3 * 1.1e4)) < 1e-9

@@ -394,7 +394,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)blockIdx.x * ATX_NSUM + k] = acc[k];
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
   }
 }
 

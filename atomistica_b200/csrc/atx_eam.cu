@@ -12,6 +12,8 @@
 //                                                                     with "- df" in the reference)
 // which is the reference's scatter form summed per receiving atom.
 // A group of LANES threads serves one atom; lanes stride its list entries and reduce by shuffles.
+#include <cstdlib>
+
 #include "atx_potential_common.cuh"
 
 struct DSpline {
@@ -26,6 +28,9 @@ struct DSpline {
 struct EamDev {
   int ndb;
   double cutoff_sq;
+  // common grid of all frho/fphi tables (setfl shares nr, dr); used by the fast kernels
+  int r_n;
+  double r_x0, r_inv_dx;
   int el2db[32];
   DSpline fF[EAM_MAX_DB];
   DSpline frho[EAM_MAX_DB];
@@ -43,6 +48,9 @@ struct atx_eam {
   DevBuf<int> flag;
   PotScratch sc;
   bool bound = false;
+  bool fast_ok = false;  // all r-tables share one grid that covers the cutoff
+  bool force_generic = false;
+  int fast_lanes = 8, fast_unroll = 2;
   ~atx_eam() {
     for (auto *t : tables) delete t;
   }
@@ -260,11 +268,195 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
   atx_block_sum<ATX_NSUM, 128>(acc, red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)blockIdx.x * ATX_NSUM + k] = acc[k];
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
   }
 }
 
 // ---------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------
+// Fast kernels (no mask, no per-atom virial): U list entries per lane are processed together so
+// that the position gathers and the spline-row loads of U pairs are in flight at the same time
+// (the v0 kernels were stalled on dependent loads, profiles/r01_ncu_eam_v0.csv), the three r-tables
+// share one interval index, and (r - x0)/dx is evaluated as (r - x0)*(1/dx) -- a <= 1 ulp change of
+// the interval coordinate that a C2 spline turns into a relative change far below 1e-10.
+// ---------------------------------------------------------------------------
+
+template <int LANES, int U>
+__global__ void __launch_bounds__(128)
+k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
+                   const long long *__restrict__ seed, const int2 *__restrict__ list,
+                   double *__restrict__ dF, double *__restrict__ Fe, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  const int gpb = 128 / LANES;
+  const int s = blockIdx.x * gpb + threadIdx.x / LANES;
+  const int lane = threadIdx.x % LANES;
+  const bool valid = s < nat;
+  const double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
+  const int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  const double cutoff_sq = T->cutoff_sq, x0 = T->r_x0, inv_dx = T->r_inv_dx;
+  const int nr = T->r_n;
+  double rho = 0.0;
+  const long long b = dbi > 0 ? seed[s] : 0, e = dbi > 0 ? seed[s + 1] : 0;
+  for (long long a0 = b + lane * U; a0 < e; a0 += LANES * U) {
+    int2 en[U];
+    double4 pj[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) en[u] = (a0 + u < e) ? list[a0 + u] : make_int2(s, ATX_SHIFT_ZERO);
+#pragma unroll
+    for (int u = 0; u < U; u++) pj[u] = pos4[en[u].x];
+    double B[U], w[U];
+    const double4 *row[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      double dx = pi.x - pj[u].x, dy = pi.y - pj[u].y, dz = pi.z - pj[u].z;
+      if (en[u].y != ATX_SHIFT_ZERO) {
+        int sx, sy, sz;
+        atx_unpack_shift(en[u].y, sx, sy, sz);
+        double ax, ay, az;
+        atx_image_vector(A, sx, sy, sz, ax, ay, az);
+        dx += ax; dy += ay; dz += az;
+      }
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      const int dbj = T->el2db[(int)pj[u].w];
+      const bool in = (a0 + u < e) && dbj > 0 && r2 < cutoff_sq;
+      const double r = sqrt(in ? r2 : 1.0);
+      const double xf = (r - x0) * inv_dx + 1.0;
+      int i = (int)floor(xf);
+      i = i < 1 ? 1 : (i >= nr ? nr - 1 : i);
+      B[u] = xf - (double)i;
+      w[u] = in ? 1.0 : 0.0;
+      row[u] = &T->frho[in ? dbj - 1 : 0].c[i - 1];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const double4 c = atx_ld4(row[u]);
+      rho += w[u] * (c.x + B[u] * (c.y + B[u] * (c.z + B[u] * c.w)));
+    }
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) rho += __shfl_xor_sync(0xffffffffu, rho, o);
+  if (lane == 0 && valid) {
+    double F = 0.0, dFi = 0.0;
+    if (dbi > 0) {
+      if (rho < 0.0) rho = 0.0;
+      spl_f_df_x(T->fF[dbi - 1], rho, F, dFi);
+    }
+    dF[s] = dFi;
+    Fe[s] = F;
+  }
+}
+
+template <int LANES, int U, bool VIRIAL>
+__global__ void __launch_bounds__(128)
+k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
+                 const long long *__restrict__ seed, const int2 *__restrict__ list,
+                 const double *__restrict__ dF, const double *__restrict__ Fe, double *__restrict__ f,
+                 double *__restrict__ epa, double *__restrict__ partials,
+                 const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * 4];
+  const int gpb = 128 / LANES;
+  const int s = blockIdx.x * gpb + threadIdx.x / LANES;
+  const int lane = threadIdx.x % LANES;
+  const bool valid = s < nat;
+  const double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
+  const int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  const double cutoff_sq = T->cutoff_sq, x0 = T->r_x0, inv_dx = T->r_inv_dx;
+  const int nr = T->r_n, ndb = T->ndb;
+  double fx = 0.0, fy = 0.0, fz = 0.0, en_ = 0.0;
+  double wxx = 0, wyy = 0, wzz = 0, wxy = 0, wxz = 0, wyz = 0;
+  const double dFi = dbi > 0 ? dF[s] : 0.0;
+  const long long b = dbi > 0 ? seed[s] : 0, e = dbi > 0 ? seed[s + 1] : 0;
+  const int di = dbi > 0 ? dbi - 1 : 0;
+  for (long long a0 = b + lane * U; a0 < e; a0 += LANES * U) {
+    int2 en[U];
+    double4 pj[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) en[u] = (a0 + u < e) ? list[a0 + u] : make_int2(s, ATX_SHIFT_ZERO);
+#pragma unroll
+    for (int u = 0; u < U; u++) pj[u] = pos4[en[u].x];
+    double B[U], w[U], dx[U], dy[U], dz[U], rinv[U], dFj[U];
+    int idx[U], dj[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      dx[u] = pi.x - pj[u].x; dy[u] = pi.y - pj[u].y; dz[u] = pi.z - pj[u].z;
+      if (en[u].y != ATX_SHIFT_ZERO) {
+        int sx, sy, sz;
+        atx_unpack_shift(en[u].y, sx, sy, sz);
+        double ax, ay, az;
+        atx_image_vector(A, sx, sy, sz, ax, ay, az);
+        dx[u] += ax; dy[u] += ay; dz[u] += az;
+      }
+      const double r2 = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+      const int dbj = T->el2db[(int)pj[u].w];
+      const bool in = (a0 + u < e) && dbj > 0 && r2 < cutoff_sq;
+      const double r = sqrt(in ? r2 : 1.0);
+      rinv[u] = 1.0 / r;
+      const double xf = (r - x0) * inv_dx + 1.0;
+      int i = (int)floor(xf);
+      i = i < 1 ? 1 : (i >= nr ? nr - 1 : i);
+      B[u] = xf - (double)i;
+      idx[u] = i - 1;
+      w[u] = in ? 1.0 : 0.0;
+      dj[u] = in ? dbj - 1 : 0;
+      dFj[u] = dF[en[u].x];
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const DSpline &ph = T->fphi[di + ndb * dj[u]];
+      const double4 c = atx_ld4(&ph.c[idx[u]]);
+      const double4 d = atx_ld4(&ph.d[idx[u]]);
+      const double4 rj = atx_ld4(&T->frho[dj[u]].d[idx[u]]);
+      const double Bu = B[u];
+      const double phi = c.x + Bu * (c.y + Bu * (c.z + Bu * c.w));
+      const double dphi = d.x + Bu * (d.y + Bu * d.z);
+      const double drho_j = rj.x + Bu * (rj.y + Bu * rj.z);
+      double drho_i = drho_j;
+      if (dj[u] != di) {
+        const double4 ri = atx_ld4(&T->frho[di].d[idx[u]]);
+        drho_i = ri.x + Bu * (ri.y + Bu * ri.z);
+      }
+      const double ri_ = rinv[u];
+      const double pair = (dphi - phi * ri_) * ri_;
+      const double cij = -(dFi * drho_j + pair) * ri_ * w[u];
+      const double cji = -(dFj[u] * drho_i + pair) * ri_ * w[u];
+      const double cc = cij + cji;
+      fx += cc * dx[u]; fy += cc * dy[u]; fz += cc * dz[u];
+      en_ += w[u] * phi * ri_;
+      if (VIRIAL) {
+        wxx -= cij * dx[u] * dx[u]; wyy -= cij * dy[u] * dy[u]; wzz -= cij * dz[u] * dz[u];
+        wxy -= cij * dx[u] * dy[u]; wxz -= cij * dx[u] * dz[u]; wyz -= cij * dy[u] * dz[u];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    fx += __shfl_xor_sync(0xffffffffu, fx, o);
+    fy += __shfl_xor_sync(0xffffffffu, fy, o);
+    fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    en_ += __shfl_xor_sync(0xffffffffu, en_, o);
+  }
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+  if (lane == 0 && valid) {
+    f[3 * s] = fx; f[3 * s + 1] = fy; f[3 * s + 2] = fz;
+    const double ei = en_ + Fe[s];
+    if (epa) epa[s] = ei;
+    acc[0] = ei;
+  }
+  if (VIRIAL) {
+    acc[1] = wxx; acc[2] = wxy; acc[3] = wxz;
+    acc[4] = wxy; acc[5] = wyy; acc[6] = wyz;
+    acc[7] = wxz; acc[8] = wyz; acc[9] = wzz;
+  }
+  atx_block_sum<ATX_NSUM, 128>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
+  }
+}
 
 static int upload_spline(atx_eam *pot, const atx_spline &s, DSpline &d) {
   int ni = s.n - 1;
@@ -311,6 +503,20 @@ extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const
     for (int i = 0; i < ndb; i++)
       ATX_PASS(upload_spline(pot, fphi[i + ndb * j], pot->host.fphi[i + ndb * j]));
   for (int k = 0; k < 32; k++) pot->host.el2db[k] = -1;
+  {
+    const atx_spline &g0 = frho[0];
+    bool same = true;
+    for (int i = 0; i < ndb; i++) same = same && frho[i].n == g0.n && frho[i].x0 == g0.x0 && frho[i].dx == g0.dx;
+    for (int i = 0; i < ndb * ndb; i++) same = same && fphi[i].n == g0.n && fphi[i].x0 == g0.x0 && fphi[i].dx == g0.dx;
+    pot->host.r_n = g0.n;
+    pot->host.r_x0 = g0.x0;
+    pot->host.r_inv_dx = 1.0 / g0.dx;
+    // func() without extrapolation must never leave the table: cutoff <= last knot
+    pot->fast_ok = same && g0.x0 <= 0.0 && cutoff <= g0.x0 + g0.dx * (g0.n - 1);
+  }
+  if (const char *v = getenv("ATX_EAM_GENERIC")) pot->force_generic = atoi(v) != 0;
+  if (const char *v = getenv("ATX_EAM_LANES")) pot->fast_lanes = atoi(v);
+  if (const char *v = getenv("ATX_EAM_UNROLL")) pot->fast_unroll = atoi(v);
   ATX_PASS(pot->dev.reserve(1));
   ATX_PASS(pot->flag.reserve(4));
   *out = pot;
@@ -356,6 +562,45 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
   if (nblocks < 1) nblocks = 1;
   ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
   if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  if (pot->fast_ok && !mask_sorted && !o.wpa && !pot->force_generic) {
+    const int L = pot->fast_lanes, gp = 128 / L;
+    const int nb = nat > 0 ? (nat + gp - 1) / gp : 1;
+    ATX_PASS(pot->sc.partials.reserve((size_t)nb * ATX_NSUM));
+    const bool vir = o.want_virial;
+#define EAM_FAST(LL, UU)                                                                          \
+  do {                                                                                            \
+    {                                                                                             \
+      ProfScope ps_(ctx, "eam_density");                                                          \
+      k_eam_density_fast<LL, UU><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,    \
+                                                     nl->seed.ptr, nl->list.ptr, pot->dF.ptr,     \
+                                                     pot->Fe.ptr, o.stop);                        \
+    }                                                                                             \
+    ATX_LAUNCHED();                                                                               \
+    ProfScope ps2_(ctx, "eam_force");                                                             \
+    if (vir)                                                                                      \
+      k_eam_force_fast<LL, UU, true><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, \
+          nl->seed.ptr, nl->list.ptr, pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr,  \
+          o.stop);                                                                                \
+    else                                                                                          \
+      k_eam_force_fast<LL, UU, false><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, \
+          nl->seed.ptr, nl->list.ptr, pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr,  \
+          o.stop);                                                                                \
+    ATX_LAUNCHED();                                                                               \
+  } while (0)
+    const int U = pot->fast_unroll;
+    if (L == 4 && U == 4) EAM_FAST(4, 4);
+    else if (L == 4 && U == 2) EAM_FAST(4, 2);
+    else if (L == 8 && U == 4) EAM_FAST(8, 4);
+    else if (L == 8 && U == 2) EAM_FAST(8, 2);
+    else if (L == 2 && U == 4) EAM_FAST(2, 4);
+    else if (L == 16 && U == 2) EAM_FAST(16, 2);
+    else if (L == 16 && U == 1) EAM_FAST(16, 1);
+    else if (L == 1 && U == 4) EAM_FAST(1, 4);
+    else EAM_FAST(8, 2);
+#undef EAM_FAST
+    ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nb, o.sums, o.stop));
+    return 0;
+  }
 #define EAM_LAUNCH(L)                                                                             \
   do {                                                                                            \
     {                                                                                             \

@@ -117,17 +117,30 @@ __global__ void k_md_kick(int nat, double dt, double *__restrict__ v, const doub
   for (int o = 16; o > 0; o >>= 1) ek += __shfl_xor_sync(0xffffffffu, ek, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ek;
   __syncthreads();
+  __shared__ bool is_last;
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
     kin_partials[blockIdx.x] = t;
     __threadfence();
     unsigned int done = atomicAdd(&ctrl->counter_kick, 1u);
-    if (done == gridDim.x - 1) {
-      __threadfence();
-      double tot = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; b++) tot += ((volatile double *)kin_partials)[b];
-      ctrl->ekin = tot;
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    // last block: deterministic tree sum of the per-block kinetic energies
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      tot += ((volatile double *)kin_partials)[b];
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+      ctrl->ekin = t;
       ctrl->epot = sums[0];
       ctrl->counter_kick = 0u;
       ctrl->steps_done += 1;
@@ -181,6 +194,7 @@ static int md_compute(atx_md *md, bool guarded) {
   o.f = md->f.ptr;
   o.sums = md->sums.ptr;
   o.stop = guarded ? &md->ctrl.ptr->stop : nullptr;
+  o.want_virial = false;
   switch (md->pot_kind) {
     case ATX_POT_EAM:
       return atx_eam_compute_device((atx_eam *)md->pot, &md->pint, md->nl, nullptr, o);

@@ -1,20 +1,29 @@
 #include "atx_potential_common.cuh"
 
-__global__ void k_reduce_partials(const double *__restrict__ partials, int nblocks,
-                                  double *__restrict__ sums, const int *__restrict__ stop) {
+// partials are stored component-major: partials[comp * nblocks + block].
+// One block per component, fixed summation tree -> deterministic.
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const double *__restrict__ partials, int nblocks, double *__restrict__ sums,
+                  const int *__restrict__ stop) {
   if (stop && *stop) return;
-  // one warp per component, fixed summation order -> deterministic
-  int comp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (comp >= ATX_NSUM) return;
+  __shared__ double red[8];
+  const int comp = blockIdx.x;
+  const double *src = partials + (size_t)comp * nblocks;
   double x = 0.0;
-  for (int b = lane; b < nblocks; b += 32) x += partials[(size_t)b * ATX_NSUM + comp];
+  for (int b = threadIdx.x; b < nblocks; b += 256) x += src[b];
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-  if (lane == 0) sums[comp] = x;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    sums[comp] = t;
+  }
 }
 
 int atx_reduce_partials(atx_ctx *ctx, const double *partials, int nblocks, double *sums,
                         const int *stop) {
-  k_reduce_partials<<<1, 32 * ATX_NSUM, 0, ctx->stream>>>(partials, nblocks, sums, stop);
+  k_reduce_partials<<<ATX_NSUM, 256, 0, ctx->stream>>>(partials, nblocks, sums, stop);
   ATX_LAUNCHED();
   return 0;
 }

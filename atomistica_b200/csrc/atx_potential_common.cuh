@@ -12,6 +12,7 @@ struct PotOut {
   double *wpa = nullptr;    // (9,nat) overwritten, optional
   double *sums = nullptr;   // ATX_NSUM doubles: epot, wpot(3,3)
   const int *stop = nullptr;  // MD driver: kernels return immediately when *stop != 0
+  bool want_virial = true;    // NVE stepping does not need wpot
 };
 
 // Scratch owned by every potential object for library-mode calls.

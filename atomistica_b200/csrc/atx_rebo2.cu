@@ -713,7 +713,7 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
   atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)blockIdx.x * ATX_NSUM + k] = acc[k];
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
   }
 }
 

@@ -227,7 +227,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
         int elj = P.el2db[(int)pj.w];
         if (elj > 0) {
           double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-          if (en.y != ATX_SHIFT_ZERO) {
+          if (ATX_NONZERO_SHIFT(en.y)) {
             int sx, sy, sz;
             atx_unpack_shift(en.y, sx, sy, sz);
             double ax, ay, az;

@@ -35,6 +35,7 @@ struct EamDev {
   DSpline fF[EAM_MAX_DB];
   DSpline frho[EAM_MAX_DB];
   DSpline fphi[EAM_MAX_DB * EAM_MAX_DB];
+  const double4 *pairrec[EAM_MAX_DB * EAM_MAX_DB];  // 64-byte records, see k_eam_force_fast
 };
 
 struct atx_eam {
@@ -45,12 +46,13 @@ struct atx_eam {
   DevBuf<EamDev> dev;
   std::vector<DevBuf<double4> *> tables;
   DevBuf<double> dF, Fe;
+  DevBuf<double4> pd4;
   DevBuf<int> flag;
   PotScratch sc;
   bool bound = false;
   bool fast_ok = false;  // all r-tables share one grid that covers the cutoff
   bool force_generic = false;
-  int fast_lanes = 8, fast_unroll = 2;
+  int fast_lanes = 4, fast_unroll = 2;
   ~atx_eam() {
     for (auto *t : tables) delete t;
   }
@@ -132,7 +134,7 @@ k_eam_density(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__re
     int dbj = T->el2db[(int)pj.w];
     if (dbj <= 0) continue;
     double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-    if (en.y != ATX_SHIFT_ZERO) {
+    if (ATX_NONZERO_SHIFT(en.y)) {
       int sx, sy, sz;
       atx_unpack_shift(en.y, sx, sy, sz);
       double ax, ay, az;
@@ -195,7 +197,7 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
       int dbj = T->el2db[(int)pj.w];
       if (dbj <= 0) continue;
       double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-      if (en.y != ATX_SHIFT_ZERO) {
+      if (ATX_NONZERO_SHIFT(en.y)) {
         int sx, sy, sz;
         atx_unpack_shift(en.y, sx, sy, sz);
         double ax, ay, az;
@@ -286,7 +288,8 @@ template <int LANES, int U>
 __global__ void __launch_bounds__(128)
 k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
                    const long long *__restrict__ seed, const int2 *__restrict__ list,
-                   double *__restrict__ dF, double *__restrict__ Fe, const int *__restrict__ stop) {
+                   double4 *__restrict__ pd4, double *__restrict__ Fe,
+                   const int *__restrict__ stop) {
   if (stop && *stop) return;
   const int gpb = 128 / LANES;
   const int s = blockIdx.x * gpb + threadIdx.x / LANES;
@@ -304,13 +307,13 @@ k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 
 #pragma unroll
     for (int u = 0; u < U; u++) en[u] = (a0 + u < e) ? list[a0 + u] : make_int2(s, ATX_SHIFT_ZERO);
 #pragma unroll
-    for (int u = 0; u < U; u++) pj[u] = pos4[en[u].x];
+    for (int u = 0; u < U; u++) pj[u] = atx_ld4(&pos4[en[u].x]);
     double B[U], w[U];
     const double4 *row[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       double dx = pi.x - pj[u].x, dy = pi.y - pj[u].y, dz = pi.z - pj[u].z;
-      if (en[u].y != ATX_SHIFT_ZERO) {
+      if (ATX_NONZERO_SHIFT(en[u].y)) {
         int sx, sy, sz;
         atx_unpack_shift(en[u].y, sx, sy, sz);
         double ax, ay, az;
@@ -318,7 +321,7 @@ k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 
         dx += ax; dy += ay; dz += az;
       }
       const double r2 = dx * dx + dy * dy + dz * dz;
-      const int dbj = T->el2db[(int)pj[u].w];
+      const int dbj = T->el2db[ATX_ENTRY_EL(en[u].y)];
       const bool in = (a0 + u < e) && dbj > 0 && r2 < cutoff_sq;
       const double r = sqrt(in ? r2 : 1.0);
       const double xf = (r - x0) * inv_dx + 1.0;
@@ -342,16 +345,18 @@ k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 
       if (rho < 0.0) rho = 0.0;
       spl_f_df_x(T->fF[dbi - 1], rho, F, dFi);
     }
-    dF[s] = dFi;
+    pd4[s] = make_double4(pi.x, pi.y, pi.z, dFi);  // position + F'(rho): one gather in the force pass
     Fe[s] = F;
   }
 }
 
+// Force pass.  Per pair it gathers ONE 32-byte record {x,y,z,F'_j} and ONE 64-byte table record
+// {phi: y c1 c2 c3 | rho_j: c1 c2 c3 | -}; derivative coefficients are formed as k*c_k/dx.
 template <int LANES, int U, bool VIRIAL>
 __global__ void __launch_bounds__(128)
-k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
-                 const long long *__restrict__ seed, const int2 *__restrict__ list,
-                 const double *__restrict__ dF, const double *__restrict__ Fe, double *__restrict__ f,
+k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pd4,
+                 const double4 *__restrict__ pos4, const long long *__restrict__ seed,
+                 const int2 *__restrict__ list, const double *__restrict__ Fe, double *__restrict__ f,
                  double *__restrict__ epa, double *__restrict__ partials,
                  const int *__restrict__ stop) {
   if (stop && *stop) return;
@@ -360,13 +365,13 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
   const int s = blockIdx.x * gpb + threadIdx.x / LANES;
   const int lane = threadIdx.x % LANES;
   const bool valid = s < nat;
-  const double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
-  const int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  const double4 pi = valid ? pd4[s] : make_double4(0, 0, 0, 0);
+  const int dbi = valid ? T->el2db[(int)pos4[s].w] : -1;
   const double cutoff_sq = T->cutoff_sq, x0 = T->r_x0, inv_dx = T->r_inv_dx;
   const int nr = T->r_n, ndb = T->ndb;
   double fx = 0.0, fy = 0.0, fz = 0.0, en_ = 0.0;
   double wxx = 0, wyy = 0, wzz = 0, wxy = 0, wxz = 0, wyz = 0;
-  const double dFi = dbi > 0 ? dF[s] : 0.0;
+  const double dFi = pi.w;
   const long long b = dbi > 0 ? seed[s] : 0, e = dbi > 0 ? seed[s + 1] : 0;
   const int di = dbi > 0 ? dbi - 1 : 0;
   for (long long a0 = b + lane * U; a0 < e; a0 += LANES * U) {
@@ -375,13 +380,13 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
 #pragma unroll
     for (int u = 0; u < U; u++) en[u] = (a0 + u < e) ? list[a0 + u] : make_int2(s, ATX_SHIFT_ZERO);
 #pragma unroll
-    for (int u = 0; u < U; u++) pj[u] = pos4[en[u].x];
-    double B[U], w[U], dx[U], dy[U], dz[U], rinv[U], dFj[U];
+    for (int u = 0; u < U; u++) pj[u] = atx_ld4(&pd4[en[u].x]);
+    double B[U], w[U], dx[U], dy[U], dz[U], rinv[U];
     int idx[U], dj[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       dx[u] = pi.x - pj[u].x; dy[u] = pi.y - pj[u].y; dz[u] = pi.z - pj[u].z;
-      if (en[u].y != ATX_SHIFT_ZERO) {
+      if (ATX_NONZERO_SHIFT(en[u].y)) {
         int sx, sy, sz;
         atx_unpack_shift(en[u].y, sx, sy, sz);
         double ax, ay, az;
@@ -389,7 +394,7 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
         dx[u] += ax; dy[u] += ay; dz[u] += az;
       }
       const double r2 = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
-      const int dbj = T->el2db[(int)pj[u].w];
+      const int dbj = T->el2db[ATX_ENTRY_EL(en[u].y)];
       const bool in = (a0 + u < e) && dbj > 0 && r2 < cutoff_sq;
       const double r = sqrt(in ? r2 : 1.0);
       rinv[u] = 1.0 / r;
@@ -400,27 +405,25 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
       idx[u] = i - 1;
       w[u] = in ? 1.0 : 0.0;
       dj[u] = in ? dbj - 1 : 0;
-      dFj[u] = dF[en[u].x];
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const DSpline &ph = T->fphi[di + ndb * dj[u]];
-      const double4 c = atx_ld4(&ph.c[idx[u]]);
-      const double4 d = atx_ld4(&ph.d[idx[u]]);
-      const double4 rj = atx_ld4(&T->frho[dj[u]].d[idx[u]]);
+      const double4 *rec = T->pairrec[di + ndb * dj[u]] + 2 * (size_t)idx[u];
+      const double4 c = atx_ld4(rec);       // phi: y c1 c2 c3
+      const double4 q = atx_ld4(rec + 1);   // rho_j: c1 c2 c3
       const double Bu = B[u];
       const double phi = c.x + Bu * (c.y + Bu * (c.z + Bu * c.w));
-      const double dphi = d.x + Bu * (d.y + Bu * d.z);
-      const double drho_j = rj.x + Bu * (rj.y + Bu * rj.z);
+      const double dphi = (c.y + Bu * (2.0 * c.z + Bu * (3.0 * c.w))) * inv_dx;
+      const double drho_j = (q.x + Bu * (2.0 * q.y + Bu * (3.0 * q.z))) * inv_dx;
       double drho_i = drho_j;
       if (dj[u] != di) {
-        const double4 ri = atx_ld4(&T->frho[di].d[idx[u]]);
-        drho_i = ri.x + Bu * (ri.y + Bu * ri.z);
+        const double4 ri = atx_ld4(&T->frho[di].c[idx[u]]);
+        drho_i = (ri.y + Bu * (2.0 * ri.z + Bu * (3.0 * ri.w))) * inv_dx;
       }
       const double ri_ = rinv[u];
       const double pair = (dphi - phi * ri_) * ri_;
       const double cij = -(dFi * drho_j + pair) * ri_ * w[u];
-      const double cji = -(dFj[u] * drho_i + pair) * ri_ * w[u];
+      const double cji = -(pj[u].w * drho_i + pair) * ri_ * w[u];
       const double cc = cij + cji;
       fx += cc * dx[u]; fy += cc * dy[u]; fz += cc * dz[u];
       en_ += w[u] * phi * ri_;
@@ -513,6 +516,24 @@ extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const
     pot->host.r_inv_dx = 1.0 / g0.dx;
     // func() without extrapolation must never leave the table: cutoff <= last knot
     pot->fast_ok = same && g0.x0 <= 0.0 && cutoff <= g0.x0 + g0.dx * (g0.n - 1);
+    if (pot->fast_ok) {
+      const int ni = g0.n - 1;
+      std::vector<double4> rec(2 * (size_t)ni);
+      for (int j = 0; j < ndb; j++)
+        for (int i = 0; i < ndb; i++) {
+          const atx_spline &ph = fphi[i + ndb * j];
+          const atx_spline &rj = frho[j];
+          for (int k = 0; k < ni; k++) {
+            rec[2 * k] = make_double4(ph.y[k], ph.coeff1[k], ph.coeff2[k], ph.coeff3[k]);
+            rec[2 * k + 1] = make_double4(rj.coeff1[k], rj.coeff2[k], rj.coeff3[k], 0.0);
+          }
+          auto *bb = new DevBuf<double4>();
+          pot->tables.push_back(bb);
+          ATX_PASS(bb->reserve(2 * (size_t)ni));
+          ATX_CUDA(cudaMemcpy(bb->ptr, rec.data(), sizeof(double4) * 2 * ni, cudaMemcpyHostToDevice));
+          pot->host.pairrec[i + ndb * j] = bb->ptr;
+        }
+    }
   }
   if (const char *v = getenv("ATX_EAM_GENERIC")) pot->force_generic = atoi(v) != 0;
   if (const char *v = getenv("ATX_EAM_LANES")) pot->fast_lanes = atoi(v);
@@ -554,6 +575,7 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
   int nat = nl->nat;
   ATX_PASS(pot->dF.reserve(nat + 1));
   ATX_PASS(pot->Fe.reserve(nat + 1));
+  ATX_PASS(pot->pd4.reserve(nat + 1));
   // lanes per atom from the mean list length
   double mean = nat > 0 ? (double)nl->npairs / nat : 0.0;
   int lanes = mean > 48 ? 16 : (mean > 20 ? 8 : 4);
@@ -572,18 +594,18 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
     {                                                                                             \
       ProfScope ps_(ctx, "eam_density");                                                          \
       k_eam_density_fast<LL, UU><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,    \
-                                                     nl->seed.ptr, nl->list.ptr, pot->dF.ptr,     \
+                                                     nl->seed.ptr, nl->list.ptr, pot->pd4.ptr,    \
                                                      pot->Fe.ptr, o.stop);                        \
     }                                                                                             \
     ATX_LAUNCHED();                                                                               \
     ProfScope ps2_(ctx, "eam_force");                                                             \
     if (vir)                                                                                      \
-      k_eam_force_fast<LL, UU, true><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, \
-          nl->seed.ptr, nl->list.ptr, pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr,  \
+      k_eam_force_fast<LL, UU, true><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
+          nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr, \
           o.stop);                                                                                \
     else                                                                                          \
-      k_eam_force_fast<LL, UU, false><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, \
-          nl->seed.ptr, nl->list.ptr, pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr,  \
+      k_eam_force_fast<LL, UU, false><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
+          nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr, \
           o.stop);                                                                                \
     ATX_LAUNCHED();                                                                               \
   } while (0)

@@ -134,9 +134,13 @@ struct atx_particles {
   const double *rptr() const { return r_ext ? r_ext : r.ptr; }
 };
 
-// packed periodic shift: 10 bits per component, bias 512
-#define ATX_SHIFT_BIAS 512
-#define ATX_SHIFT_ZERO (ATX_SHIFT_BIAS | (ATX_SHIFT_BIAS << 10) | (ATX_SHIFT_BIAS << 20))
+// list entry word .y: periodic shift, 8 bits per component (bias 128), in bits 0..23 and the
+// particle element id of the neighbour in bits 24..30
+#define ATX_SHIFT_BIAS 128
+#define ATX_SHIFT_ZERO (ATX_SHIFT_BIAS | (ATX_SHIFT_BIAS << 8) | (ATX_SHIFT_BIAS << 16))
+#define ATX_SHIFT_MASK 0xFFFFFF
+#define ATX_NONZERO_SHIFT(p) (((p) & ATX_SHIFT_MASK) != ATX_SHIFT_ZERO)
+#define ATX_ENTRY_EL(p) ((p) >> 24)
 
 struct atx_neighbors {
   atx_ctx *ctx = nullptr;
@@ -194,12 +198,12 @@ int atx_accumulate_to_host(atx_ctx *ctx, const double *dev, double *host, size_t
 // ---------------------------------------------------------------------------
 
 __device__ __forceinline__ int atx_pack_shift(int sx, int sy, int sz) {
-  return (sx + ATX_SHIFT_BIAS) | ((sy + ATX_SHIFT_BIAS) << 10) | ((sz + ATX_SHIFT_BIAS) << 20);
+  return (sx + ATX_SHIFT_BIAS) | ((sy + ATX_SHIFT_BIAS) << 8) | ((sz + ATX_SHIFT_BIAS) << 16);
 }
 __device__ __forceinline__ void atx_unpack_shift(int p, int &sx, int &sy, int &sz) {
-  sx = (p & 1023) - ATX_SHIFT_BIAS;
-  sy = ((p >> 10) & 1023) - ATX_SHIFT_BIAS;
-  sz = ((p >> 20) & 1023) - ATX_SHIFT_BIAS;
+  sx = (p & 255) - ATX_SHIFT_BIAS;
+  sy = ((p >> 8) & 255) - ATX_SHIFT_BIAS;
+  sz = ((p >> 16) & 255) - ATX_SHIFT_BIAS;
 }
 
 // matmul(Abox, shift) with the reference's association order and no FMA contraction
@@ -211,11 +215,23 @@ __device__ __forceinline__ void atx_image_vector(const Mat3 &A, int sx, int sy, 
   az = __dadd_rn(__dadd_rn(__dmul_rn(A.m[2], s0), __dmul_rn(A.m[5], s1)), __dmul_rn(A.m[8], s2));
 }
 
-// read-only 32-byte load (two 16-byte non-coherent loads)
+// read-only 32-byte load as ONE 256-bit instruction (LDG.E.ENL2.256.CONSTANT on sm_100a):
+// one L1 request per gathered record instead of two
 __device__ __forceinline__ double4 atx_ld4(const double4 *p) {
-  double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-  double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-  return make_double4(a.x, a.y, b.x, b.y);
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p));
+  return v;
+}
+// coherent variant for data written earlier in the same kernel sequence by other kernels is not
+// needed (kernel boundaries order the writes); this one is for arrays updated in place.
+__device__ __forceinline__ double4 atx_ld4_ca(const double4 *p) {
+  double4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+               : "l"(p));
+  return v;
 }
 
 template <typename T>

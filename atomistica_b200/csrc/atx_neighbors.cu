@@ -210,7 +210,7 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
               int bad = (abs(s2x) >= ATX_SHIFT_BIAS) | (abs(s2y) >= ATX_SHIFT_BIAS) |
                         (abs(s2z) >= ATX_SHIFT_BIAS);
               if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
-              list[w++] = make_int2(t, atx_pack_shift(s2x, s2y, s2z));
+              list[w++] = make_int2(t, atx_pack_shift(s2x, s2y, s2z) | ((int)pj.w << 24));
             }
             cnt++;
           }
@@ -253,7 +253,7 @@ __global__ void k_reverse_index(int nat, const long long *__restrict__ seed,
     int found = -1;
     for (long long b = seed[e.x]; b < seed[e.x + 1]; b++) {
       int2 q = list[b];
-      if (q.x == s && q.y == want) { found = (int)b; break; }
+      if (q.x == s && (q.y & ATX_SHIFT_MASK) == want) { found = (int)b; break; }
     }
     rev[a] = found;
   }
@@ -439,7 +439,7 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
     ATX_CUDA(cudaStreamSynchronize(st));
     if (h[3]) {
-      atx_set_error("Periodic image shift beyond +-511 cells; wrap the positions into the cell.");
+      atx_set_error("Periodic image shift beyond +-127 cells; wrap the positions into the cell.");
       nl->initialized = false;
       return ATX_ERROR_UNSPECIFIED;
     }

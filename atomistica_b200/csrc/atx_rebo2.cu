@@ -244,7 +244,7 @@ __global__ void k_rebo2_bonds(int nat, int nbs, Mat3 A, Rebo2Dev P, const double
       int tj = P.el2typ[(int)pj.w];
       if (tj <= 0) continue;
       double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-      if (en.y != ATX_SHIFT_ZERO) {
+      if (ATX_NONZERO_SHIFT(en.y)) {
         int sx, sy, sz;
         atx_unpack_shift(en.y, sx, sy, sz);
         double ax, ay, az;

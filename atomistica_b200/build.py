@@ -18,7 +18,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
-              '-I' + os.path.join(HERE, '..', 'include')]
+              '-I' + os.path.join(HERE, '..', 'include'), '-I/usr/include']
 VISIBLE = ['-Xcompiler', '-fvisibility=default']
 
 

@@ -1,0 +1,964 @@
+// Spatial domain decomposition over the GPUs of one node: slab decomposition, ghost-atom halo
+// exchange and global rebuild decision over NCCL (NVLink 5 / NVSwitch).
+//
+// Behavioural model: src/standalone/domain_decomposition.f90 (communicate_particles :494-640,
+// communicate_ghosts :699-826, global OR of the rebuild flag standalone/neighbors.f90:552-557).
+// Differences by design:
+//   * 1-D slabs along the first cell vector: on an NVSwitch box every peer is one hop away and the
+//     halo messages are sub-MB, so two large messages per step beat 26 small ones.
+//   * The halo is 2*(rc + skin) thick and every rank evaluates the density / bond-order terms of
+//     its inner ghosts itself; the reference's reverse force communication (communicate_forces
+//     :887-970) and the EAM embedding-derivative exchange disappear, one forward position exchange
+//     per step remains.
+//   * The rebuild flag is all-reduced on the device into the stop flag of the optimistic step
+//     batches (atx_md.cu), so there is no per-step host synchronisation either.
+// NCCL is loaded with dlopen("libnccl.so.2"): the library has no link-time dependency on it and
+// single-GPU users never touch it.
+#include <cub/device/device_select.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "atx_potential_common.cuh"
+
+#define ATX_ACCEL_CONV 9.648533212331e-3
+
+int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
+                           const int *mask_sorted, const PotOut &o);
+int atx_bop_compute_device(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
+                           const int *mask_sorted, const PotOut &o);
+int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o);
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen
+// ---------------------------------------------------------------------------
+
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    atx_set_error(std::string("Cannot load libnccl.so.2: ") + dlerror());
+    return ATX_ERROR_MPI;
+  }
+#define LOAD(field, name)                                            \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                        \
+  if (!g_nccl.field) {                                               \
+    atx_set_error(std::string("libnccl lacks symbol ") + name);     \
+    return ATX_ERROR_MPI;                                            \
+  }
+  LOAD(GetUniqueId, "ncclGetUniqueId")
+  LOAD(CommInitRank, "ncclCommInitRank")
+  LOAD(CommDestroy, "ncclCommDestroy")
+  LOAD(Send, "ncclSend")
+  LOAD(Recv, "ncclRecv")
+  LOAD(AllReduce, "ncclAllReduce")
+  LOAD(GroupStart, "ncclGroupStart")
+  LOAD(GroupEnd, "ncclGroupEnd")
+  LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+  g_nccl.h = h;
+  return 0;
+}
+
+#define ATX_NCCL(call)                                                                      \
+  do {                                                                                      \
+    ncclResult_t r_ = (call);                                                               \
+    if (r_ != ncclSuccess) {                                                                \
+      atx_set_error(std::string(#call) + ": " + g_nccl.GetErrorString(r_));                 \
+      return ATX_ERROR_MPI;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+struct atx_dd {
+  atx_ctx *ctx = nullptr;
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+};
+
+extern "C" int atx_dd_get_unique_id(char *id128) {
+  ATX_PASS(nccl_load());
+  ncclUniqueId id;
+  ATX_NCCL(g_nccl.GetUniqueId(&id));
+  std::memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+  return 0;
+}
+
+extern "C" int atx_dd_create(atx_ctx *ctx, int rank, int nranks, const char *id128, atx_dd **out) {
+  ATX_PASS(nccl_load());
+  ATX_CUDA(cudaSetDevice(ctx->device));
+  atx_dd *dd = new atx_dd();
+  dd->ctx = ctx;
+  dd->rank = rank;
+  dd->nranks = nranks;
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+  ATX_NCCL(g_nccl.CommInitRank(&dd->comm, nranks, id, rank));
+  *out = dd;
+  return 0;
+}
+
+extern "C" int atx_dd_destroy(atx_dd *dd) {
+  if (!dd) return 0;
+  if (dd->comm) g_nccl.CommDestroy(dd->comm);
+  delete dd;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// domain-decomposed MD
+// ---------------------------------------------------------------------------
+
+struct DdCtrl {
+  int stop;          // global (all-reduced) rebuild flag
+  int want;          // local rebuild wish of the current step
+  int steps_done;
+  unsigned int counter_drift;
+  unsigned int counter_kick;
+  unsigned long long stepmax_bits;
+  double accum_max_dr;
+  double verlet_shell;
+  double epot;       // local: sum of per-atom energies of owned atoms (last step)
+  double ekin;
+};
+
+#define DD_ROW 9  // migration record: id, el, r(3), v(3), minv
+
+struct atx_ddmd {
+  atx_dd *dd = nullptr;
+  atx_ctx *ctx = nullptr;
+  int pot_kind = 0;
+  void *pot = nullptr;
+  Mat3 A{}, B{};
+  int pbc[3] = {1, 1, 1};
+  double slo = 0, shi = 1, hfrac = 0;
+  double slo_own = 0, shi_own = 1;  // ownership interval (open ended at non-periodic faces)
+  double a1[3] = {0, 0, 0};
+  double torig[3] = {0, 0, 0};
+  int left = -1, right = -1;
+  double wrapL = 0.0, wrapR = 0.0;  // multiples of a1 added to positions sent left / right
+  double dt = 1.0, rc = 0.0, skin = 0.0;
+  int nown = 0, ngl = 0, ngr = 0, nsendL = 0, nsendR = 0;
+  DevBuf<double> r, v, f, minv, tmpd, bufL, bufR, epa, sums, kin_partials, mig_send, mig_recv;
+  DevBuf<double> idd;  // atom ids stored as doubles (exact up to 2^53)
+  DevBuf<int> el, sendL, sendR, flags, sel, tmpi, cnt;
+  DevBuf<DdCtrl> ctrl;
+  PinBuf<DdCtrl> hctrl;
+  PinBuf<double> stage;
+  PinBuf<int> hcnt;
+  atx_particles ploc;
+  atx_neighbors *nl = nullptr;
+  long long nrebuilds = 0;
+  double last_ms = 0.0;
+  int batch = 16;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+__global__ void k_dd_drift(int nown, double dt, double *__restrict__ r, double *__restrict__ v,
+                           const double *__restrict__ f, const double *__restrict__ minv,
+                           DdCtrl *__restrict__ ctrl) {
+  if (ctrl->stop) return;
+  __shared__ double red[8];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (i < nown) {
+    double a = 0.5 * minv[i] * ATX_ACCEL_CONV * dt;
+    double vx = v[3 * i] + a * f[3 * i], vy = v[3 * i + 1] + a * f[3 * i + 1], vz = v[3 * i + 2] + a * f[3 * i + 2];
+    v[3 * i] = vx; v[3 * i + 1] = vy; v[3 * i + 2] = vz;
+    double dx = vx * dt, dy = vy * dt, dz = vz * dt;
+    r[3 * i] += dx; r[3 * i + 1] += dy; r[3 * i + 2] += dz;
+    d2 = dx * dx + dy * dy + dz * dz;
+  }
+  for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, red[w]);
+    atomicMax(&ctrl->stepmax_bits, (unsigned long long)__double_as_longlong(m));
+    __threadfence();
+    unsigned int done = atomicAdd(&ctrl->counter_drift, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      double mx = __longlong_as_double((long long)atomicAdd(&ctrl->stepmax_bits, 0ull));
+      double acc = ctrl->accum_max_dr + sqrt(mx);
+      ctrl->accum_max_dr = acc;
+      ctrl->stepmax_bits = 0ull;
+      ctrl->counter_drift = 0u;
+      ctrl->want = (2.0 * acc >= ctrl->verlet_shell) ? 1 : 0;  // all-reduced into ctrl->stop
+    }
+  }
+}
+
+// ranks with no owned atoms still have to publish a wish
+__global__ void k_dd_nowish(DdCtrl *ctrl) {
+  if (!ctrl->stop) ctrl->want = 0;
+}
+
+__global__ void k_dd_pack(int n, const int *__restrict__ idx, const double *__restrict__ r,
+                          double sx, double sy, double sz, double *__restrict__ buf,
+                          const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = idx[t];
+  buf[3 * t] = r[3 * i] + sx;
+  buf[3 * t + 1] = r[3 * i + 1] + sy;
+  buf[3 * t + 2] = r[3 * i + 2] + sz;
+}
+
+__global__ void k_dd_refresh(int n, const double *__restrict__ r, const int *__restrict__ order,
+                             double4 *__restrict__ pos4, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int i = order[s];
+  double4 v = pos4[s];
+  v.x = r[3 * i]; v.y = r[3 * i + 1]; v.z = r[3 * i + 2];
+  pos4[s] = v;
+}
+
+// kick owned atoms with the forces of the sorted arrays; kinetic energy and owned potential energy
+__global__ void k_dd_kick(int nown, double dt, double *__restrict__ v, const double *__restrict__ fs,
+                          const double *__restrict__ epa_s, const int *__restrict__ inv,
+                          const double *__restrict__ minv, double *__restrict__ f_loc,
+                          double *__restrict__ partials, DdCtrl *__restrict__ ctrl) {
+  if (ctrl->stop) return;
+  __shared__ double red[16];
+  __shared__ bool is_last;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double ek = 0.0, ep = 0.0;
+  if (i < nown) {
+    int s = inv[i];
+    double mi = minv[i];
+    double a = 0.5 * mi * ATX_ACCEL_CONV * dt;
+    double fx = fs[3 * s], fy = fs[3 * s + 1], fz = fs[3 * s + 2];
+    f_loc[3 * i] = fx; f_loc[3 * i + 1] = fy; f_loc[3 * i + 2] = fz;
+    double vx = v[3 * i] + a * fx, vy = v[3 * i + 1] + a * fy, vz = v[3 * i + 2] + a * fz;
+    v[3 * i] = vx; v[3 * i + 1] = vy; v[3 * i + 2] = vz;
+    ek = 0.5 * (vx * vx + vy * vy + vz * vz) / (mi * ATX_ACCEL_CONV);
+    ep = epa_s[s];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ek += __shfl_xor_sync(0xffffffffu, ek, o);
+    ep += __shfl_xor_sync(0xffffffffu, ep, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = ek; red[8 + (threadIdx.x >> 5)] = ep; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0, u = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { t += red[w]; u += red[8 + w]; }
+    partials[2 * blockIdx.x] = t;
+    partials[2 * blockIdx.x + 1] = u;
+    __threadfence();
+    unsigned int done = atomicAdd(&ctrl->counter_kick, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    double t = 0.0, u = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+      t += ((volatile double *)partials)[2 * b];
+      u += ((volatile double *)partials)[2 * b + 1];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+      u += __shfl_xor_sync(0xffffffffu, u, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = t; red[8 + (threadIdx.x >> 5)] = u; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tt = 0.0, uu = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { tt += red[w]; uu += red[8 + w]; }
+      ctrl->ekin = tt;
+      ctrl->epot = uu;
+      ctrl->counter_kick = 0u;
+      ctrl->steps_done += 1;
+    }
+  }
+}
+
+__global__ void k_dd_empty_step(DdCtrl *ctrl) {
+  if (ctrl->stop) return;
+  ctrl->ekin = 0.0;
+  ctrl->epot = 0.0;
+  ctrl->steps_done += 1;
+}
+
+// flags for migration / ghost selection; s = Bbox(1,:) . (r + torig) is the fractional coordinate
+__global__ void k_dd_flags(int nown, const double *__restrict__ r, double b0, double b1, double b2,
+                           double t0, double t1, double t2, double lo, double hi, int mode,
+                           int *__restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nown) return;
+  double s = b0 * (r[3 * i] + t0) + b1 * (r[3 * i + 1] + t1) + b2 * (r[3 * i + 2] + t2);
+  int fl;
+  if (mode == 0) fl = (s >= lo && s < hi);  // stay
+  else if (mode == 1) fl = (s < lo);        // below
+  else fl = (s >= hi);                      // above or equal
+  flags[i] = fl;
+}
+
+__global__ void k_dd_iota(int n, int *a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+
+__global__ void k_dd_pack_rows(int n, const int *__restrict__ idx, const double *__restrict__ idd,
+                               const int *__restrict__ el, const double *__restrict__ r,
+                               const double *__restrict__ v, const double *__restrict__ minv,
+                               double sx, double sy, double sz, double *__restrict__ rows) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = idx[t];
+  double *o = rows + (size_t)DD_ROW * t;
+  o[0] = idd[i];
+  o[1] = (double)el[i];
+  o[2] = r[3 * i] + sx; o[3] = r[3 * i + 1] + sy; o[4] = r[3 * i + 2] + sz;
+  o[5] = v[3 * i]; o[6] = v[3 * i + 1]; o[7] = v[3 * i + 2];
+  o[8] = minv[i];
+}
+
+__global__ void k_dd_unpack_rows(int n, int at, const double *__restrict__ rows, double sx, double sy,
+                                 double sz, double *__restrict__ idd, int *__restrict__ el,
+                                 double *__restrict__ r, double *__restrict__ v,
+                                 double *__restrict__ minv) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = at + t;
+  const double *o = rows + (size_t)DD_ROW * t;
+  idd[i] = o[0];
+  el[i] = (int)o[1];
+  r[3 * i] = o[2] + sx; r[3 * i + 1] = o[3] + sy; r[3 * i + 2] = o[4] + sz;
+  v[3 * i] = o[5]; v[3 * i + 1] = o[6]; v[3 * i + 2] = o[7];
+  minv[i] = o[8];
+}
+
+// ghost record: el, r(3)
+__global__ void k_dd_pack_ghost(int n, const int *__restrict__ idx, const int *__restrict__ el,
+                                const double *__restrict__ r, double sx, double sy, double sz,
+                                double *__restrict__ rows) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = idx[t];
+  rows[4 * t] = (double)el[i];
+  rows[4 * t + 1] = r[3 * i] + sx; rows[4 * t + 2] = r[3 * i + 1] + sy; rows[4 * t + 3] = r[3 * i + 2] + sz;
+}
+
+__global__ void k_dd_unpack_ghost(int n, int at, const double *__restrict__ rows, int *__restrict__ el,
+                                  double *__restrict__ r) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = at + t;
+  el[i] = (int)rows[4 * t];
+  r[3 * i] = rows[4 * t + 1]; r[3 * i + 1] = rows[4 * t + 2]; r[3 * i + 2] = rows[4 * t + 3];
+}
+
+__global__ void k_dd_gather_owned(int n, const int *__restrict__ idx, const double *__restrict__ idd,
+                                  const int *__restrict__ el, const double *__restrict__ r,
+                                  const double *__restrict__ v, const double *__restrict__ minv,
+                                  double *__restrict__ idd2, int *__restrict__ el2,
+                                  double *__restrict__ r2, double *__restrict__ v2,
+                                  double *__restrict__ minv2) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = idx[t];
+  idd2[t] = idd[i];
+  el2[t] = el[i];
+  for (int c = 0; c < 3; c++) { r2[3 * t + c] = r[3 * i + c]; v2[3 * t + c] = v[3 * i + c]; }
+  minv2[t] = minv[i];
+}
+
+template <typename T>
+static void swapbuf(DevBuf<T> &a, DevBuf<T> &b) {
+  std::swap(a.ptr, b.ptr);
+  std::swap(a.cap, b.cap);
+}
+
+// stable selection of the indices i < n with flags[i] != 0 into out; count returned on the host
+static int dd_select(atx_ddmd *md, int n, const int *flags, int *out, int *count) {
+  atx_ctx *ctx = md->ctx;
+  ATX_PASS(md->tmpi.reserve(n + 1));
+  ATX_PASS(md->cnt.reserve(4));
+  if (n == 0) {
+    *count = 0;
+    return 0;
+  }
+  k_dd_iota<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, md->tmpi.ptr);
+  ATX_LAUNCHED();
+  size_t bytes = 0;
+  cub::DeviceSelect::Flagged(nullptr, bytes, md->tmpi.ptr, flags, out, md->cnt.ptr, n, ctx->stream);
+  ATX_PASS(ctx->cub_tmp.reserve(bytes));
+  ATX_CUDA(cub::DeviceSelect::Flagged(ctx->cub_tmp.ptr, bytes, md->tmpi.ptr, flags, out, md->cnt.ptr,
+                                      n, ctx->stream));
+  g_atx_launches += 2;
+  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr, md->cnt.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *count = md->hcnt.ptr[0];
+  return 0;
+}
+
+// exchange two integers with the slab neighbours: what I send left/right -> what I receive
+static int dd_exchange_counts(atx_ddmd *md, int sendL, int sendR, int *recvL, int *recvR) {
+  atx_dd *dd = md->dd;
+  cudaStream_t st = md->ctx->stream;
+  ATX_PASS(md->cnt.reserve(8));
+  int *d = md->cnt.ptr;
+  md->hcnt.ptr[0] = sendL;
+  md->hcnt.ptr[1] = sendR;
+  md->hcnt.ptr[2] = 0;
+  md->hcnt.ptr[3] = 0;
+  ATX_CUDA(cudaMemcpyAsync(d, md->hcnt.ptr, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+  ATX_NCCL(g_nccl.GroupStart());
+  if (md->left >= 0) ATX_NCCL(g_nccl.Send(d + 0, 1, ncclInt, md->left, dd->comm, st));
+  if (md->right >= 0) ATX_NCCL(g_nccl.Send(d + 1, 1, ncclInt, md->right, dd->comm, st));
+  if (md->left >= 0 && md->left == md->right) {
+    // two ranks, periodic: the peer's first message is what it sent to ITS left, i.e. my right
+    ATX_NCCL(g_nccl.Recv(d + 3, 1, ncclInt, md->right, dd->comm, st));
+    ATX_NCCL(g_nccl.Recv(d + 2, 1, ncclInt, md->left, dd->comm, st));
+  } else {
+    if (md->left >= 0) ATX_NCCL(g_nccl.Recv(d + 2, 1, ncclInt, md->left, dd->comm, st));
+    if (md->right >= 0) ATX_NCCL(g_nccl.Recv(d + 3, 1, ncclInt, md->right, dd->comm, st));
+  }
+  ATX_NCCL(g_nccl.GroupEnd());
+  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr + 4, d + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  *recvL = md->hcnt.ptr[4];
+  *recvR = md->hcnt.ptr[5];
+  return 0;
+}
+
+// Note on send/recv matching with two ranks and periodic x: left == right == the other rank.  My
+// "send left" is the peer's "receive from right"; NCCL matches operations to the same peer in issue
+// order, so sends are issued (left, right) and receives (right-of-peer == from left first...) --
+// to keep both sides consistent every exchange issues: send L, send R, recv from R, recv from L when
+// left == right, which pairs my L-send with the peer's R-recv.
+static int dd_sendrecv(atx_ddmd *md, const double *sL, size_t nL, const double *sR, size_t nR,
+                       double *rL, size_t mL, double *rR, size_t mR) {
+  atx_dd *dd = md->dd;
+  cudaStream_t st = md->ctx->stream;
+  ATX_NCCL(g_nccl.GroupStart());
+  if (md->left >= 0) ATX_NCCL(g_nccl.Send(sL, nL, ncclDouble, md->left, dd->comm, st));
+  if (md->right >= 0) ATX_NCCL(g_nccl.Send(sR, nR, ncclDouble, md->right, dd->comm, st));
+  if (md->left >= 0 && md->left == md->right) {
+    ATX_NCCL(g_nccl.Recv(rR, mR, ncclDouble, md->right, dd->comm, st));
+    ATX_NCCL(g_nccl.Recv(rL, mL, ncclDouble, md->left, dd->comm, st));
+  } else {
+    if (md->left >= 0) ATX_NCCL(g_nccl.Recv(rL, mL, ncclDouble, md->left, dd->comm, st));
+    if (md->right >= 0) ATX_NCCL(g_nccl.Recv(rR, mR, ncclDouble, md->right, dd->comm, st));
+  }
+  ATX_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+static int dd_reserve_local(atx_ddmd *md, size_t n) {
+  // grow all per-local-atom arrays, preserving the owned part
+  if (n + 1 <= md->r.cap / 3 && n + 1 <= md->el.cap) return 0;
+  size_t want = n + n / 4 + 1024;
+  cudaStream_t st = md->ctx->stream;
+  auto grow_d = [&](DevBuf<double> &b, size_t per, size_t keep) -> int {
+    DevBuf<double> nb;
+    ATX_PASS(nb.reserve(per * want));
+    if (keep && b.ptr) ATX_CUDA(cudaMemcpyAsync(nb.ptr, b.ptr, sizeof(double) * keep, cudaMemcpyDeviceToDevice, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    swapbuf(b, nb);
+    return 0;
+  };
+  size_t no = md->nown;
+  ATX_PASS(grow_d(md->r, 3, 3 * no));
+  ATX_PASS(grow_d(md->v, 3, 3 * no));
+  ATX_PASS(grow_d(md->f, 3, 0));
+  ATX_PASS(grow_d(md->minv, 1, no));
+  ATX_PASS(grow_d(md->idd, 1, no));
+  {
+    DevBuf<int> nb;
+    ATX_PASS(nb.reserve(want));
+    if (no && md->el.ptr) ATX_CUDA(cudaMemcpyAsync(nb.ptr, md->el.ptr, sizeof(int) * no, cudaMemcpyDeviceToDevice, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    swapbuf(md->el, nb);
+  }
+  ATX_PASS(md->flags.reserve(want));
+  ATX_PASS(md->sel.reserve(want));
+  ATX_PASS(md->sendL.reserve(want));
+  ATX_PASS(md->sendR.reserve(want));
+  return 0;
+}
+
+static int dd_compute(atx_ddmd *md, bool guarded) {
+  PotOut o;
+  int nloc = md->nown + md->ngl + md->ngr;
+  ATX_PASS(md->tmpd.reserve(3 * (size_t)nloc + 3));
+  ATX_PASS(md->epa.reserve((size_t)nloc + 1));
+  o.f = md->tmpd.ptr;  // sorted order
+  o.epa = md->epa.ptr;
+  o.sums = md->sums.ptr;
+  o.stop = guarded ? &md->ctrl.ptr->stop : nullptr;
+  o.want_virial = false;
+  switch (md->pot_kind) {
+    case ATX_POT_EAM:
+      return atx_eam_compute_device((atx_eam *)md->pot, &md->ploc, md->nl, nullptr, o);
+    case ATX_POT_BOP:
+      return atx_bop_compute_device((atx_bop *)md->pot, &md->ploc, md->nl, nullptr, o);
+    case ATX_POT_REBO2:
+      return atx_rebo2_compute_device((atx_rebo2 *)md->pot, &md->ploc, md->nl, o);
+  }
+  atx_set_error("atx_dd_md: unknown potential kind");
+  return ATX_ERROR_UNSPECIFIED;
+}
+
+// migration + ghost construction + local neighbour list
+static int dd_rebuild(atx_ddmd *md) {
+  atx_ctx *ctx = md->ctx;
+  cudaStream_t st = ctx->stream;
+  const double b0 = md->B.m[0], b1 = md->B.m[3], b2 = md->B.m[6];  // Bbox(1,:)
+  const double *t = md->torig;
+  int n = md->nown;
+  int gb = (n + 255) / 256;
+  ATX_PASS(dd_reserve_local(md, n));
+
+  // ---- migration: atoms outside [slo, shi) go to the neighbouring slab
+  int nstay = n, nL = 0, nR = 0;
+  if (md->dd->nranks > 1) {
+    if (n > 0) {
+      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 1, md->flags.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendL.ptr, &nL));
+    if (n > 0) {
+      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 2, md->flags.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendR.ptr, &nR));
+    if (n > 0) {
+      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 0, md->flags.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sel.ptr, &nstay));
+    if ((md->left < 0 && nL > 0) || (md->right < 0 && nR > 0)) {
+      atx_set_error("Particle outside simulation domain (left the non-periodic box along x).");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    int inL = 0, inR = 0;
+    ATX_PASS(dd_exchange_counts(md, nL, nR, &inL, &inR));
+    ATX_PASS(md->mig_send.reserve((size_t)DD_ROW * (nL + nR) + DD_ROW));
+    ATX_PASS(md->mig_recv.reserve((size_t)DD_ROW * (inL + inR) + DD_ROW));
+    // positions travel in the GLOBAL frame (+ periodic wrap), the receiver subtracts its origin
+    if (nL > 0) {
+      k_dd_pack_rows<<<(nL + 127) / 128, 128, 0, st>>>(nL, md->sendL.ptr, md->idd.ptr, md->el.ptr, md->r.ptr,
+                                                       md->v.ptr, md->minv.ptr, t[0] + md->wrapL * md->a1[0],
+                                                       t[1] + md->wrapL * md->a1[1], t[2] + md->wrapL * md->a1[2],
+                                                       md->mig_send.ptr);
+      ATX_LAUNCHED();
+    }
+    if (nR > 0) {
+      k_dd_pack_rows<<<(nR + 127) / 128, 128, 0, st>>>(nR, md->sendR.ptr, md->idd.ptr, md->el.ptr, md->r.ptr,
+                                                       md->v.ptr, md->minv.ptr, t[0] + md->wrapR * md->a1[0],
+                                                       t[1] + md->wrapR * md->a1[1], t[2] + md->wrapR * md->a1[2],
+                                                       md->mig_send.ptr + (size_t)DD_ROW * nL);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_sendrecv(md, md->mig_send.ptr, (size_t)DD_ROW * nL, md->mig_send.ptr + (size_t)DD_ROW * nL,
+                         (size_t)DD_ROW * nR, md->mig_recv.ptr, (size_t)DD_ROW * inL,
+                         md->mig_recv.ptr + (size_t)DD_ROW * inL, (size_t)DD_ROW * inR));
+    // compact the stayers into fresh arrays, append the arrivals
+    int nnew = nstay + inL + inR;
+    size_t want = (size_t)nnew + nnew / 4 + 1024;
+    DevBuf<double> r2, v2, minv2, idd2, f2;
+    DevBuf<int> el2;
+    ATX_PASS(r2.reserve(3 * want)); ATX_PASS(v2.reserve(3 * want)); ATX_PASS(f2.reserve(3 * want));
+    ATX_PASS(minv2.reserve(want)); ATX_PASS(idd2.reserve(want)); ATX_PASS(el2.reserve(want));
+    if (nstay > 0) {
+      k_dd_gather_owned<<<(nstay + 255) / 256, 256, 0, st>>>(nstay, md->sel.ptr, md->idd.ptr, md->el.ptr, md->r.ptr,
+                                                            md->v.ptr, md->minv.ptr, idd2.ptr, el2.ptr, r2.ptr,
+                                                            v2.ptr, minv2.ptr);
+      ATX_LAUNCHED();
+    }
+    if (inL > 0) {
+      k_dd_unpack_rows<<<(inL + 127) / 128, 128, 0, st>>>(inL, nstay, md->mig_recv.ptr, -t[0], -t[1], -t[2],
+                                                          idd2.ptr, el2.ptr, r2.ptr, v2.ptr, minv2.ptr);
+      ATX_LAUNCHED();
+    }
+    if (inR > 0) {
+      k_dd_unpack_rows<<<(inR + 127) / 128, 128, 0, st>>>(inR, nstay + inL, md->mig_recv.ptr + (size_t)DD_ROW * inL,
+                                                          -t[0], -t[1], -t[2], idd2.ptr, el2.ptr, r2.ptr, v2.ptr,
+                                                          minv2.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_CUDA(cudaStreamSynchronize(st));
+    swapbuf(md->r, r2); swapbuf(md->v, v2); swapbuf(md->f, f2); swapbuf(md->minv, minv2);
+    swapbuf(md->idd, idd2); swapbuf(md->el, el2);
+    md->nown = n = nnew;
+    gb = (n + 255) / 256;
+    ATX_PASS(md->flags.reserve(want)); ATX_PASS(md->sel.reserve(want));
+    ATX_PASS(md->sendL.reserve(want)); ATX_PASS(md->sendR.reserve(want));
+  }
+
+  // ---- ghosts: owned atoms within the halo of a face are sent to that neighbour
+  md->nsendL = md->nsendR = md->ngl = md->ngr = 0;
+  if (md->dd->nranks > 1) {
+    if (md->left >= 0) {
+      if (n > 0) {
+        k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo + md->hfrac, 2.0, 1,
+                                       md->flags.ptr);
+        ATX_LAUNCHED();
+      }
+      ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendL.ptr, &md->nsendL));
+    }
+    if (md->right >= 0) {
+      if (n > 0) {
+        k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], -1.0, md->shi - md->hfrac, 2,
+                                       md->flags.ptr);
+        ATX_LAUNCHED();
+      }
+      ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendR.ptr, &md->nsendR));
+    }
+    ATX_PASS(dd_exchange_counts(md, md->nsendL, md->nsendR, &md->ngl, &md->ngr));
+    int nloc = n + md->ngl + md->ngr;
+    ATX_PASS(dd_reserve_local(md, nloc));
+    ATX_PASS(md->bufL.reserve(4 * (size_t)md->nsendL + 4));
+    ATX_PASS(md->bufR.reserve(4 * (size_t)md->nsendR + 4));
+    ATX_PASS(md->mig_recv.reserve(4 * (size_t)(md->ngl + md->ngr) + 4));
+    // ghost positions travel in the receiver's... no: global frame + wrap; receiver subtracts origin
+    if (md->nsendL > 0) {
+      k_dd_pack_ghost<<<(md->nsendL + 127) / 128, 128, 0, st>>>(
+          md->nsendL, md->sendL.ptr, md->el.ptr, md->r.ptr, t[0] + md->wrapL * md->a1[0],
+          t[1] + md->wrapL * md->a1[1], t[2] + md->wrapL * md->a1[2], md->bufL.ptr);
+      ATX_LAUNCHED();
+    }
+    if (md->nsendR > 0) {
+      k_dd_pack_ghost<<<(md->nsendR + 127) / 128, 128, 0, st>>>(
+          md->nsendR, md->sendR.ptr, md->el.ptr, md->r.ptr, t[0] + md->wrapR * md->a1[0],
+          t[1] + md->wrapR * md->a1[1], t[2] + md->wrapR * md->a1[2], md->bufR.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_sendrecv(md, md->bufL.ptr, 4 * (size_t)md->nsendL, md->bufR.ptr, 4 * (size_t)md->nsendR,
+                         md->mig_recv.ptr, 4 * (size_t)md->ngl, md->mig_recv.ptr + 4 * (size_t)md->ngl,
+                         4 * (size_t)md->ngr));
+    if (md->ngl + md->ngr > 0) {
+      int ng = md->ngl + md->ngr;
+      k_dd_unpack_ghost<<<(ng + 127) / 128, 128, 0, st>>>(ng, n, md->mig_recv.ptr, md->el.ptr, md->r.ptr);
+      ATX_LAUNCHED();
+      // receiver frame: subtract the local origin (ghost rows hold global positions)
+    }
+  }
+  return 0;
+}
+
+__global__ void k_dd_shift(int n, int at, double *__restrict__ r, double sx, double sy, double sz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int i = at + t;
+  r[3 * i] += sx; r[3 * i + 1] += sy; r[3 * i + 2] += sz;
+}
+
+static int dd_build_list(atx_ddmd *md) {
+  atx_ctx *ctx = md->ctx;
+  cudaStream_t st = ctx->stream;
+  int n = md->nown, ng = md->ngl + md->ngr, nloc = n + ng;
+  const double *t = md->torig;
+  if (ng > 0) {
+    k_dd_shift<<<(ng + 127) / 128, 128, 0, st>>>(ng, n, md->r.ptr, -t[0], -t[1], -t[2]);
+    ATX_LAUNCHED();
+  }
+  // local particles: alias the arrays
+  md->ploc.nat = nloc;
+  md->ploc.r_ext = md->r.ptr;
+  std::swap(md->ploc.el.ptr, md->el.ptr);  // ploc.el aliases md->el while the list is built
+  std::swap(md->ploc.el.cap, md->el.cap);
+  md->ploc.pos_rev++;
+  int err = atx_neighbors_update(md->nl, &md->ploc);
+  std::swap(md->ploc.el.ptr, md->el.ptr);
+  std::swap(md->ploc.el.cap, md->el.cap);
+  if (err) return err;
+  md->nrebuilds++;
+  return 0;
+}
+
+static int dd_reset_ctrl(atx_ddmd *md) {
+  DdCtrl *h = md->hctrl.ptr;
+  h->stop = 0;
+  h->want = 0;
+  h->accum_max_dr = 1e-6;
+  h->stepmax_bits = 0;
+  h->counter_drift = 0;
+  h->counter_kick = 0;
+  ATX_CUDA(cudaMemcpyAsync(md->ctrl.ptr, h, sizeof(DdCtrl), cudaMemcpyHostToDevice, md->ctx->stream));
+  return 0;
+}
+
+static int dd_kick(atx_ddmd *md) {
+  cudaStream_t st = md->ctx->stream;
+  int n = md->nown;
+  if (n > 0) {
+    int gb = (n + 255) / 256;
+    ATX_PASS(md->kin_partials.reserve(2 * (size_t)gb + 2));
+    k_dd_kick<<<gb, 256, 0, st>>>(n, md->dt, md->v.ptr, md->tmpd.ptr, md->epa.ptr, md->nl->inv.ptr, md->minv.ptr,
+                                  md->f.ptr, md->kin_partials.ptr, md->ctrl.ptr);
+  } else {
+    k_dd_empty_step<<<1, 1, 0, st>>>(md->ctrl.ptr);
+  }
+  ATX_LAUNCHED();
+  return 0;
+}
+
+extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const double *Abox,
+                                const double *Bbox, const int *pbc, double rc, double skin, int avgn,
+                                int nown, const long long *id, const int *el, const double *r,
+                                const double *v, const double *mass, double dt, atx_ddmd **out) {
+  if (!dd || !pot || !out) return ATX_ERROR_UNSPECIFIED;
+  atx_ctx *ctx = dd->ctx;
+  cudaStream_t st = ctx->stream;
+  ATX_CUDA(cudaSetDevice(ctx->device));
+  atx_ddmd *md = new atx_ddmd();
+  md->dd = dd;
+  md->ctx = ctx;
+  md->pot_kind = pot_kind;
+  md->pot = pot;
+  for (int i = 0; i < 9; i++) { md->A.m[i] = Abox[i]; md->B.m[i] = Bbox[i]; }
+  for (int k = 0; k < 3; k++) { md->pbc[k] = pbc[k] != 0; md->a1[k] = Abox[k]; }
+  md->dt = dt; md->rc = rc; md->skin = skin;
+  const int P = dd->nranks, me = dd->rank;
+  md->slo = (double)me / P;
+  md->shi = (double)(me + 1) / P;
+  const double slo_own = (!md->pbc[0] && me == 0) ? -1e300 : md->slo;      // open ends own the rest
+  const double shi_own = (!md->pbc[0] && me == P - 1) ? 1e300 : md->shi;
+  // thickness of the whole cell between the faces spanned by a2, a3: 1/|Bbox(1,:)|
+  double bn = std::sqrt(Bbox[0] * Bbox[0] + Bbox[3] * Bbox[3] + Bbox[6] * Bbox[6]);
+  double halo = P > 1 ? 2.0 * (rc + skin) : 0.0;
+  md->hfrac = halo * bn;
+  if (P > 1 && md->hfrac > 1.0 / P) {
+    atx_set_error("Domain decomposition: slabs are thinner than the halo 2*(rc+skin); use fewer ranks.");
+    delete md;
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  if (P > 1) {
+    md->left = me > 0 ? me - 1 : (md->pbc[0] ? P - 1 : -1);
+    md->right = me < P - 1 ? me + 1 : (md->pbc[0] ? 0 : -1);
+    md->wrapL = me == 0 ? 1.0 : 0.0;       // leaving through the lower face of the global cell
+    md->wrapR = me == P - 1 ? -1.0 : 0.0;
+  }
+  md->slo_own = slo_own;
+  md->shi_own = shi_own;
+  for (int k = 0; k < 3; k++) md->torig[k] = (md->slo - md->hfrac) * md->a1[k];
+  // local cell: (ds + 2h) a1, a2, a3; non-periodic along a1 when decomposed
+  double alpha = P > 1 ? (1.0 / P + 2.0 * md->hfrac) : 1.0;
+  md->ploc.ctx = ctx;
+  md->ploc.Abox = md->A;
+  md->ploc.Bbox = md->B;
+  for (int k = 0; k < 3; k++) {
+    md->ploc.Abox.m[k] = md->A.m[k] * alpha;          // column 1
+    md->ploc.Bbox.m[3 * k] = md->B.m[3 * k] / alpha;  // row 1
+    md->ploc.pbc[k] = md->pbc[k];
+  }
+  if (P > 1) md->ploc.pbc[0] = 0;
+  md->ploc.cell_rev = 1;
+  ATX_PASS(atx_neighbors_create(ctx, avgn, &md->nl));
+  ATX_PASS(atx_neighbors_request_interaction_range(md->nl, rc));
+  ATX_PASS(atx_neighbors_set_verlet_shell(md->nl, skin));
+
+  md->nown = 0;
+  ATX_PASS(dd_reserve_local(md, (size_t)nown + nown / 2 + 1024));
+  ATX_PASS(md->sums.reserve(ATX_NSUM));
+  ATX_PASS(md->ctrl.reserve(1));
+  ATX_PASS(md->hctrl.reserve(1));
+  ATX_PASS(md->hcnt.reserve(16));
+  ATX_PASS(md->stage.reserve(11 * (size_t)nown + 64));
+  double *h = md->stage.ptr;
+  // local frame = global - torig
+  for (int i = 0; i < nown; i++) {
+    for (int c = 0; c < 3; c++) h[3 * i + c] = r[3 * i + c] - md->torig[c];
+    h[3 * (size_t)nown + i] = 1.0 / mass[i];
+    h[4 * (size_t)nown + i] = (double)id[i];
+    for (int c = 0; c < 3; c++) h[5 * (size_t)nown + 3 * i + c] = v ? v[3 * i + c] : 0.0;
+  }
+  if (nown > 0) {
+    ATX_CUDA(cudaMemcpyAsync(md->r.ptr, h, sizeof(double) * 3 * nown, cudaMemcpyHostToDevice, st));
+    ATX_CUDA(cudaMemcpyAsync(md->minv.ptr, h + 3 * (size_t)nown, sizeof(double) * nown, cudaMemcpyHostToDevice, st));
+    ATX_CUDA(cudaMemcpyAsync(md->idd.ptr, h + 4 * (size_t)nown, sizeof(double) * nown, cudaMemcpyHostToDevice, st));
+    ATX_CUDA(cudaMemcpyAsync(md->v.ptr, h + 5 * (size_t)nown, sizeof(double) * 3 * nown, cudaMemcpyHostToDevice, st));
+    ATX_CUDA(cudaMemcpyAsync(md->el.ptr, el, sizeof(int) * nown, cudaMemcpyHostToDevice, st));
+  }
+  ATX_CUDA(cudaStreamSynchronize(st));
+  md->nown = nown;
+  DdCtrl c{};
+  c.accum_max_dr = 1e-6;
+  c.verlet_shell = skin;
+  *md->hctrl.ptr = c;
+  ATX_CUDA(cudaMemcpyAsync(md->ctrl.ptr, md->hctrl.ptr, sizeof(DdCtrl), cudaMemcpyHostToDevice, st));
+  ATX_CUDA(cudaEventCreate(&md->ev0));
+  ATX_CUDA(cudaEventCreate(&md->ev1));
+  int err = dd_rebuild(md);
+  if (!err) err = dd_build_list(md);
+  if (!err) err = dd_compute(md, false);
+  if (!err) {
+    // forces of the owned atoms in local order for the first drift
+    int n = md->nown;
+    if (n > 0) err = atx_unsort(ctx, md->nown + md->ngl + md->ngr, 3, md->nl->order.ptr, md->tmpd.ptr, md->f.ptr);
+  }
+  if (err) {
+    delete md;
+    return err;
+  }
+  ATX_CUDA(cudaStreamSynchronize(st));
+  *out = md;
+  return 0;
+}
+
+extern "C" int atx_dd_md_destroy(atx_ddmd *md) {
+  if (!md) return 0;
+  if (md->ev0) cudaEventDestroy(md->ev0);
+  if (md->ev1) cudaEventDestroy(md->ev1);
+  md->ploc.r_ext = nullptr;
+  if (md->nl) atx_neighbors_destroy(md->nl);
+  delete md;
+  return 0;
+}
+
+static int dd_enqueue_step(atx_ddmd *md) {
+  atx_dd *dd = md->dd;
+  cudaStream_t st = md->ctx->stream;
+  const int n = md->nown, nloc = n + md->ngl + md->ngr;
+  const int *stop = &md->ctrl.ptr->stop;
+  if (n > 0) {
+    k_dd_drift<<<(n + 255) / 256, 256, 0, st>>>(n, md->dt, md->r.ptr, md->v.ptr, md->f.ptr, md->minv.ptr,
+                                                md->ctrl.ptr);
+  } else {
+    k_dd_nowish<<<1, 1, 0, st>>>(md->ctrl.ptr);
+  }
+  ATX_LAUNCHED();
+  if (dd->nranks > 1) {
+    // global OR of the rebuild wish, written straight into the stop flag (no host involvement)
+    ATX_NCCL(g_nccl.AllReduce(&md->ctrl.ptr->want, &md->ctrl.ptr->stop, 1, ncclInt, ncclMax, dd->comm, st));
+    // ghost positions: my frame -> global (+ periodic wrap) -> receiver frame.  The local origins
+    // of neighbouring slabs differ by a1/P once the wrap is included, so the whole frame change is
+    // a constant shift applied by the sender.
+    const double dL = 1.0 / dd->nranks;    // to the left slab
+    const double dR = -1.0 / dd->nranks;   // to the right slab
+    if (md->nsendL > 0) {
+      k_dd_pack<<<(md->nsendL + 127) / 128, 128, 0, st>>>(md->nsendL, md->sendL.ptr, md->r.ptr, dL * md->a1[0],
+                                                          dL * md->a1[1], dL * md->a1[2], md->bufL.ptr, stop);
+      ATX_LAUNCHED();
+    }
+    if (md->nsendR > 0) {
+      k_dd_pack<<<(md->nsendR + 127) / 128, 128, 0, st>>>(md->nsendR, md->sendR.ptr, md->r.ptr, dR * md->a1[0],
+                                                          dR * md->a1[1], dR * md->a1[2], md->bufR.ptr, stop);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_sendrecv(md, md->bufL.ptr, 3 * (size_t)md->nsendL, md->bufR.ptr, 3 * (size_t)md->nsendR,
+                         md->r.ptr + 3 * (size_t)n, 3 * (size_t)md->ngl,
+                         md->r.ptr + 3 * (size_t)(n + md->ngl), 3 * (size_t)md->ngr));
+  } else {
+    // single rank: want -> stop
+    ATX_CUDA(cudaMemcpyAsync(&md->ctrl.ptr->stop, &md->ctrl.ptr->want, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  if (nloc > 0) {
+    k_dd_refresh<<<(nloc + 255) / 256, 256, 0, st>>>(nloc, md->r.ptr, md->nl->order.ptr, md->nl->pos4.ptr, stop);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(dd_compute(md, true));
+  ATX_PASS(dd_kick(md));
+  return 0;
+}
+
+extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *ekin) {
+  atx_dd *dd = md->dd;
+  cudaStream_t st = md->ctx->stream;
+  ATX_CUDA(cudaEventRecord(md->ev0, st));
+  md->hctrl.ptr->steps_done = 0;
+  ATX_CUDA(cudaMemcpyAsync(&md->ctrl.ptr->steps_done, &md->hctrl.ptr->steps_done, sizeof(int),
+                           cudaMemcpyHostToDevice, st));
+  int remaining = nsteps, done_total = 0;
+  while (remaining > 0) {
+    int batch = remaining < md->batch ? remaining : md->batch;
+    for (int b = 0; b < batch; b++) ATX_PASS(dd_enqueue_step(md));
+    ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(DdCtrl), cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    ATX_CUDA(cudaGetLastError());
+    DdCtrl hc = *md->hctrl.ptr;
+    int done = hc.steps_done - done_total;
+    done_total = hc.steps_done;
+    remaining -= done;
+    if (hc.stop) {
+      // the stop flag is global: every rank arrives here after the same step
+      ATX_PASS(dd_rebuild(md));
+      ATX_PASS(dd_build_list(md));
+      ATX_PASS(dd_reset_ctrl(md));
+      ATX_PASS(dd_compute(md, false));
+      ATX_PASS(dd_kick(md));
+      done_total += 1;
+      remaining -= 1;
+    }
+  }
+  ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(DdCtrl), cudaMemcpyDeviceToHost, st));
+  // global energies
+  ATX_PASS(md->sums.reserve(ATX_NSUM));
+  if (dd->nranks > 1) {
+    ATX_NCCL(g_nccl.AllReduce(&md->ctrl.ptr->epot, md->sums.ptr, 2, ncclDouble, ncclSum, dd->comm, st));
+  } else {
+    ATX_CUDA(cudaMemcpyAsync(md->sums.ptr, &md->ctrl.ptr->epot, 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  }
+  ATX_CUDA(cudaMemcpyAsync(md->stage.ptr, md->sums.ptr, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaEventRecord(md->ev1, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  ATX_CUDA(cudaGetLastError());
+  float ms = 0.f;
+  ATX_CUDA(cudaEventElapsedTime(&ms, md->ev0, md->ev1));
+  md->last_ms = ms;
+  if (epot) *epot = md->stage.ptr[0];
+  if (ekin) *ekin = md->stage.ptr[1];
+  return 0;
+}
+
+extern "C" int atx_dd_md_get_count(atx_ddmd *md, int *nown, int *nghost) {
+  if (nown) *nown = md->nown;
+  if (nghost) *nghost = md->ngl + md->ngr;
+  return 0;
+}
+
+extern "C" int atx_dd_md_get_state(atx_ddmd *md, long long *id, double *r, double *v, double *f) {
+  cudaStream_t st = md->ctx->stream;
+  int n = md->nown;
+  ATX_PASS(md->stage.reserve(10 * (size_t)n + 16));
+  double *h = md->stage.ptr;
+  if (n > 0) {
+    ATX_CUDA(cudaMemcpyAsync(h, md->r.ptr, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaMemcpyAsync(h + 3 * (size_t)n, md->v.ptr, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaMemcpyAsync(h + 6 * (size_t)n, md->f.ptr, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaMemcpyAsync(h + 9 * (size_t)n, md->idd.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  }
+  ATX_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < n; i++) {
+    if (id) id[i] = (long long)h[9 * (size_t)n + i];
+    for (int c = 0; c < 3; c++) {
+      if (r) r[3 * i + c] = h[3 * i + c] + md->torig[c];
+      if (v) v[3 * i + c] = h[3 * (size_t)n + 3 * i + c];
+      if (f) f[3 * i + c] = h[6 * (size_t)n + 3 * i + c];
+    }
+  }
+  return 0;
+}
+
+extern "C" int atx_dd_md_get_stats(atx_ddmd *md, long long *nrebuilds, double *last_run_ms) {
+  if (nrebuilds) *nrebuilds = md->nrebuilds;
+  if (last_run_ms) *last_run_ms = md->last_ms;
+  return 0;
+}

@@ -207,6 +207,34 @@ int atx_md_get_state(atx_md *md, double *r, double *v, double *f);
 /* number of neighbour-list rebuilds so far and device milliseconds spent in the last run */
 int atx_md_get_stats(atx_md *md, long long *nrebuilds, double *last_run_ms);
 
+/* ---- spatial domain decomposition over the GPUs of one node -------------------- */
+/* One process per GPU.  Slab decomposition along the first cell vector, ghost-atom halo exchange of
+ * positions with the two slab neighbours and the global rebuild decision run over NCCL
+ * (src/standalone/domain_decomposition.f90:494-970 is the behavioural model; MPI_context.f90 the
+ * backend it replaces).  NCCL is loaded lazily with dlopen. */
+typedef struct atx_dd atx_dd;
+typedef struct atx_ddmd atx_ddmd;
+/* rank 0 creates the 128-byte NCCL unique id and hands it to the other ranks out of band */
+int atx_dd_get_unique_id(char *id128);
+int atx_dd_create(atx_ctx *ctx, int rank, int nranks, const char *id128, atx_dd **dd);
+int atx_dd_destroy(atx_dd *dd);
+/* Domain-decomposed NVE driver.  Abox/Bbox/pbc describe the GLOBAL cell; every rank passes the
+ * nown atoms it owns (fractional coordinate along the first cell vector in [rank/P, (rank+1)/P)):
+ * global ids, particle element ids, positions (global frame), velocities (A/fs), masses (amu).
+ * rc is the interaction range of the potential (which must already be bound to the element map with
+ * atx_<pot>_bind_to(pot, NULL, NULL, nel, ...)), skin the Verlet shell. */
+int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const double *Abox, const double *Bbox,
+                     const int *pbc, double rc, double skin, int avgn, int nown, const long long *id,
+                     const int *el, const double *r, const double *v, const double *mass, double dt,
+                     atx_ddmd **md);
+int atx_dd_md_destroy(atx_ddmd *md);
+/* advance nsteps on all ranks (collective); GLOBAL potential and kinetic energy of the last step */
+int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *ekin);
+int atx_dd_md_get_count(atx_ddmd *md, int *nown, int *nghost);
+/* owned atoms of this rank: global ids, positions (global frame), velocities, forces */
+int atx_dd_md_get_state(atx_ddmd *md, long long *id, double *r, double *v, double *f);
+int atx_dd_md_get_stats(atx_ddmd *md, long long *nrebuilds, double *last_run_ms);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------- */
 /* CUDA-event timing of the library's own kernels on the launching stream.  When enabled every
  * launch of a profiled kernel is bracketed by an event pair; atx_profile_read resolves them. */

@@ -17,8 +17,9 @@ class Atomistica:
     potential_class = None
     avgn = 100
 
-    def __init__(self, potentials=None, avgn=None, **kwargs):
-        self.pots = potentials if potentials is not None else [self.potential_class(**kwargs)]
+    def __init__(self, potentials=None, avgn=None, device=0, **kwargs):
+        self.device = device
+        self.pots = potentials if potentials is not None else [self.potential_class(device=device, **kwargs)]
         if avgn is not None:
             self.avgn = avgn
         self.particles = None
@@ -39,14 +40,14 @@ class Atomistica:
         if self.mask is not None and len(self.mask) != len(atoms):
             raise RuntimeError('Length of mask array (= {0}) does not equal number of atoms (= {1}).'
                                .format(len(self.mask), len(atoms)))
-        self.particles = native.Particles()
+        self.particles = native.Particles(self.device)
         self.particles.allocate(len(atoms))
         self.particles.set_cell(atoms.cell, atoms.pbc)
         self.particles.Z[:] = [atomic_numbers[s] for s in atoms.symbols]
         self.particles.coordinates[:, :] = atoms.positions
         self.particles.I_changed_positions()
         self.particles.update_elements()
-        self.nl = native.Neighbors(self.avgn)
+        self.nl = native.Neighbors(self.avgn, self.device)
         for pot in self.pots:
             pot.bind_to(self.particles, self.nl)
 

@@ -160,7 +160,7 @@ def run_reference(args):
 def config_dict(ngpu):
     return dict(workload='TabulatedAlloyEAM Cu_mishin1 fcc Cu 40x40x40 (256000 atoms) per GPU, NVE velocity-Verlet, '
                          'dt 1 fs, 300 K, Verlet shell %.2f A' % SKIN,
-                atoms_per_gpu=4 * NCELL ** 3, n_gpus=ngpu, parallelism='%d independent replicas (one process per GPU)' % ngpu
+                atoms_per_gpu=4 * NCELL ** 3, n_gpus=ngpu, parallelism='slab domain decomposition x%d along x, NCCL halo exchange' % ngpu
                 if ngpu > 1 else 'single GPU',
                 l2_policy='no flush between MD steps (each step consumes the previous one); per-step working set '
                           '(pair list 155 MB + positions/forces) exceeds the 126 MB L2')
@@ -188,10 +188,25 @@ def run_ours(args):
     a, m, v0 = build_system()
     nat = len(a)
 
-    p = native.from_atoms(a, device=local_rank)
-    nl = native.Neighbors(200, device=local_rank)
     pot = native.TabulatedAlloyEAM(setfl=setfl, device=local_rank)
-    drv = md.VelocityVerlet(pot, p, nl, m, v0, dt=DT, verlet_shell=SKIN)
+    if world == 1:
+        p = native.from_atoms(a, device=local_rank)
+        nl = native.Neighbors(200, device=local_rank)
+        drv = md.VelocityVerlet(pot, p, nl, m, v0, dt=DT, verlet_shell=SKIN)
+        list_info = nl.info
+    else:
+        # weak scaling: the global cell is (40*N) x 40 x 40 fcc cells, slab-decomposed along x; every
+        # rank generates only the atoms of its own slab (ids are global)
+        from atomistica_b200 import parallel
+        dd = parallel.DomainDecomposition(rank, world, parallel.torch_exchange_id, device=local_rank)
+        gcell = a.cell.copy()
+        gcell[0] *= world
+        pos = a.positions + rank * a.cell[0] + 1e-3      # keep lattice planes off the slab faces
+        vel = md.maxwell_boltzmann(m, TEMP, seed=12345 + rank)
+        ids = np.arange(nat, dtype=np.int64) + rank * nat
+        drv = parallel.DDVelocityVerlet(dd, pot, None, [29], gcell, True, ids, np.ones(nat, dtype=np.int32), pos, vel,
+                                        m, float(setfl['cutoff']), SKIN, dt=DT)
+        list_info = None
 
     steps, warm = args.steps, max(args.warmup, 3)
     drv.run(warm)
@@ -229,13 +244,16 @@ def run_ours(args):
         dist.barrier()
     clocks = sampler.finish()
 
-    info = nl.info()
-    z_list = info['npairs'] / nat
+    if list_info is not None:
+        z_list = list_info()['npairs'] / nat
+    else:
+        z_list = 78.0      # fcc Cu, cutoff 5.507 + 0.5 A: pairs per atom of the list (measured at N=1)
+    nown, nghost = (nat, 0) if world == 1 else drv.counts()
     value = world * nat * steps / (dev_ms * 1e-3)
 
     # ---- e2e: reference-facing calculator API, host buffers, copies inside the timed region
     from atomistica_b200 import TabulatedAlloyEAM
-    calc = TabulatedAlloyEAM(setfl=setfl)
+    calc = TabulatedAlloyEAM(setfl=setfl, device=local_rank)
     r = a.positions.copy()
     vel = v0.copy()
     a2 = a.copy()
@@ -253,6 +271,11 @@ def run_ours(args):
         vel += 0.5 * f / MASS_CU * md.ACCEL_CONV * DT
         if _ >= 3:
             t_api += dt_call
+    if dist is not None:
+        import torch
+        tt = torch.tensor([t_api], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_api = float(tt[0])
     e2e_value = world * nat * e2e_steps / t_api
 
     # ---- roofline of the dominant kernel
@@ -273,7 +296,7 @@ def run_ours(args):
         data='synthetic', config=config_dict(world),
         e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=nat * 24, d2h_bytes_per_step=nat * 24 + 80,
                  steps=e2e_steps, note='calculator API (host positions in, host forces out, list rebuilt every call '
-                                       'as in the reference Python host)'),
+                                       'as in the reference Python host); at N>1 one calculator instance per GPU'),
         gpu_launches=launches,
         clocks=clocks,
         roofline=dict(bound='hbm', kernel='k_eam_force', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
@@ -284,7 +307,7 @@ def run_ours(args):
                         total_device=dev_ms),
         fp64_peak_tflops_measured=fp64.value,
         md=dict(epot=epot, ekin=ekin, rebuilds=rebuilds, rebuild_interval=steps / max(rebuilds, 1),
-                wall_s=wall),
+                wall_s=wall, owned_atoms_rank0=nown, ghost_atoms_rank0=nghost),
     )
     if rank == 0:
         if world == 1 and not args.no_cpu:

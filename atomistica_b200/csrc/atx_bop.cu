@@ -203,7 +203,8 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
              const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
              double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
              double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
-             int *__restrict__ flag, const int *__restrict__ stop) {
+             int *__restrict__ flag, const unsigned char *__restrict__ role,
+             const int *__restrict__ stop) {
   if (stop && *stop) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BondSmem<NB> &S = *reinterpret_cast<BondSmem<NB> *>(smem_raw);
@@ -213,7 +214,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
 
-  if (s < nat) {
+  if (s < nat && (!role || role[s] >= 1)) {
     double4 pi = pos4[s];
     const int eli = P.el2db[(int)pi.w];
     const long long b0 = seed[s], b1 = seed[s + 1];
@@ -401,10 +402,15 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
 __global__ void k_bop_gather(int nat, const long long *__restrict__ seed, const int *__restrict__ rev,
                              const double4 *__restrict__ G, const double *__restrict__ pe_own,
                              double *__restrict__ f, double *__restrict__ epa,
-                             const int *__restrict__ stop) {
+                             const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nat) return;
+  if (role && role[s] < 2) {
+    if (role[s] < 1) { f[3 * s] = 0.0; f[3 * s + 1] = 0.0; f[3 * s + 2] = 0.0; }
+    if (epa) epa[s] = 0.0;
+    return;
+  }
   double fx = f[3 * s], fy = f[3 * s + 1], fz = f[3 * s + 2], pe = pe_own[s];
   for (long long a = seed[s]; a < seed[s + 1]; a++) {
     int b = rev[a];
@@ -521,7 +527,7 @@ static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, cons
   ProfScope ps_(pot->ctx, "bop_force");
   k_bop_center<KIND, NB><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
       nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
-      pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->flag.ptr, o.stop);
+      pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->flag.ptr, o.role, o.stop);
   ATX_LAUNCHED();
   return 0;
 }
@@ -562,7 +568,7 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
   }
   if (nat > 0) {
     k_bop_gather<<<(nat + 127) / 128, 128, 0, st>>>(nat, nl->seed.ptr, nl->rev.ptr, pot->G.ptr, pe_own,
-                                                    o.f, o.epa, o.stop);
+                                                    o.f, o.epa, o.role, o.stop);
     ATX_LAUNCHED();
   }
   ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));

@@ -158,7 +158,10 @@ struct atx_ddmd {
   int nown = 0, ngl = 0, ngr = 0, nsendL = 0, nsendR = 0;
   DevBuf<double> r, v, f, minv, tmpd, bufL, bufR, epa, sums, kin_partials, mig_send, mig_recv;
   DevBuf<double> idd;  // atom ids stored as doubles (exact up to 2^53)
-  DevBuf<int> el, sendL, sendR, flags, sel, tmpi, cnt;
+  DevBuf<int> el, sendL, sendR, flags, flags2, flags3, sel, tmpi, cnt;
+  DevBuf<double> r2, v2, f2, minv2, idd2;  // double buffers for the migration compaction
+  DevBuf<int> el2;
+  DevBuf<unsigned char> role, role_loc;      // 2 owned, 1 inner ghost, 0 outer ghost (sorted / local order)
   DevBuf<DdCtrl> ctrl;
   PinBuf<DdCtrl> hctrl;
   PinBuf<double> stage;
@@ -318,6 +321,21 @@ __global__ void k_dd_flags(int nown, const double *__restrict__ r, double b0, do
   flags[i] = fl;
 }
 
+// role per SORTED atom: 2 owned, 1 inner ghost (within rc+skin of the slab), 0 outer ghost
+__global__ void k_dd_roles(int nloc, int nown, const int *__restrict__ order, const double *__restrict__ r,
+                           double b0, double b1, double b2, double t0, double t1, double t2, double lo,
+                           double hi, unsigned char *__restrict__ role) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  int i = order[s];
+  unsigned char q = 2;
+  if (i >= nown) {
+    double x = b0 * (r[3 * i] + t0) + b1 * (r[3 * i + 1] + t1) + b2 * (r[3 * i + 2] + t2);
+    q = (x >= lo && x < hi) ? 1 : 0;
+  }
+  role[s] = q;
+}
+
 __global__ void k_dd_iota(int n, int *a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = i;
@@ -394,26 +412,32 @@ static void swapbuf(DevBuf<T> &a, DevBuf<T> &b) {
   std::swap(a.cap, b.cap);
 }
 
-// stable selection of the indices i < n with flags[i] != 0 into out; count returned on the host
-static int dd_select(atx_ddmd *md, int n, const int *flags, int *out, int *count) {
+// stable selection of the indices i < n with flags[i] != 0 into out; the count lands in
+// md->cnt[8 + slot] on the device (read back later with dd_read_counts, one sync for several)
+static int dd_select(atx_ddmd *md, int n, const int *flags, int *out, int slot) {
   atx_ctx *ctx = md->ctx;
   ATX_PASS(md->tmpi.reserve(n + 1));
-  ATX_PASS(md->cnt.reserve(4));
+  ATX_PASS(md->cnt.reserve(16));
   if (n == 0) {
-    *count = 0;
+    ATX_CUDA(cudaMemsetAsync(md->cnt.ptr + 8 + slot, 0, sizeof(int), ctx->stream));
     return 0;
   }
   k_dd_iota<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, md->tmpi.ptr);
   ATX_LAUNCHED();
   size_t bytes = 0;
-  cub::DeviceSelect::Flagged(nullptr, bytes, md->tmpi.ptr, flags, out, md->cnt.ptr, n, ctx->stream);
+  cub::DeviceSelect::Flagged(nullptr, bytes, md->tmpi.ptr, flags, out, md->cnt.ptr + 8 + slot, n, ctx->stream);
   ATX_PASS(ctx->cub_tmp.reserve(bytes));
-  ATX_CUDA(cub::DeviceSelect::Flagged(ctx->cub_tmp.ptr, bytes, md->tmpi.ptr, flags, out, md->cnt.ptr,
-                                      n, ctx->stream));
+  ATX_CUDA(cub::DeviceSelect::Flagged(ctx->cub_tmp.ptr, bytes, md->tmpi.ptr, flags, out,
+                                      md->cnt.ptr + 8 + slot, n, ctx->stream));
   g_atx_launches += 2;
-  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr, md->cnt.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
-  *count = md->hcnt.ptr[0];
+  return 0;
+}
+
+static int dd_read_counts(atx_ddmd *md, int nslots, int *out) {
+  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr + 8, md->cnt.ptr + 8, sizeof(int) * nslots, cudaMemcpyDeviceToHost,
+                           md->ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(md->ctx->stream));
+  for (int k = 0; k < nslots; k++) out[k] = md->hcnt.ptr[8 + k];
   return 0;
 }
 
@@ -421,7 +445,7 @@ static int dd_select(atx_ddmd *md, int n, const int *flags, int *out, int *count
 static int dd_exchange_counts(atx_ddmd *md, int sendL, int sendR, int *recvL, int *recvR) {
   atx_dd *dd = md->dd;
   cudaStream_t st = md->ctx->stream;
-  ATX_PASS(md->cnt.reserve(8));
+  ATX_PASS(md->cnt.reserve(16));
   int *d = md->cnt.ptr;
   md->hcnt.ptr[0] = sendL;
   md->hcnt.ptr[1] = sendR;
@@ -471,11 +495,12 @@ static int dd_sendrecv(atx_ddmd *md, const double *sL, size_t nL, const double *
 }
 
 static int dd_reserve_local(atx_ddmd *md, size_t n) {
-  // grow all per-local-atom arrays, preserving the owned part
-  if (n + 1 <= md->r.cap / 3 && n + 1 <= md->el.cap) return 0;
-  size_t want = n + n / 4 + 1024;
+  // grow all per-local-atom arrays (main and alternate set), preserving the owned part
+  if (n + 1 <= md->r.cap / 3 && n + 1 <= md->el.cap && n + 1 <= md->r2.cap / 3 && n + 1 <= md->el2.cap) return 0;
+  size_t want = n + n / 4 + 4096;
   cudaStream_t st = md->ctx->stream;
   auto grow_d = [&](DevBuf<double> &b, size_t per, size_t keep) -> int {
+    if (b.cap >= per * want) return 0;
     DevBuf<double> nb;
     ATX_PASS(nb.reserve(per * want));
     if (keep && b.ptr) ATX_CUDA(cudaMemcpyAsync(nb.ptr, b.ptr, sizeof(double) * keep, cudaMemcpyDeviceToDevice, st));
@@ -486,20 +511,30 @@ static int dd_reserve_local(atx_ddmd *md, size_t n) {
   size_t no = md->nown;
   ATX_PASS(grow_d(md->r, 3, 3 * no));
   ATX_PASS(grow_d(md->v, 3, 3 * no));
-  ATX_PASS(grow_d(md->f, 3, 0));
+  ATX_PASS(grow_d(md->f, 3, 3 * no));
   ATX_PASS(grow_d(md->minv, 1, no));
   ATX_PASS(grow_d(md->idd, 1, no));
-  {
+  ATX_PASS(grow_d(md->r2, 3, 0));
+  ATX_PASS(grow_d(md->v2, 3, 0));
+  ATX_PASS(grow_d(md->f2, 3, 0));
+  ATX_PASS(grow_d(md->minv2, 1, 0));
+  ATX_PASS(grow_d(md->idd2, 1, 0));
+  if (md->el.cap < want) {
     DevBuf<int> nb;
     ATX_PASS(nb.reserve(want));
     if (no && md->el.ptr) ATX_CUDA(cudaMemcpyAsync(nb.ptr, md->el.ptr, sizeof(int) * no, cudaMemcpyDeviceToDevice, st));
     ATX_CUDA(cudaStreamSynchronize(st));
     swapbuf(md->el, nb);
   }
+  ATX_PASS(md->el2.reserve(want));
   ATX_PASS(md->flags.reserve(want));
+  ATX_PASS(md->flags2.reserve(want));
+  ATX_PASS(md->flags3.reserve(want));
   ATX_PASS(md->sel.reserve(want));
   ATX_PASS(md->sendL.reserve(want));
   ATX_PASS(md->sendR.reserve(want));
+  ATX_PASS(md->role.reserve(want));
+  ATX_PASS(md->role_loc.reserve(want));
   return 0;
 }
 
@@ -513,6 +548,7 @@ static int dd_compute(atx_ddmd *md, bool guarded) {
   o.sums = md->sums.ptr;
   o.stop = guarded ? &md->ctrl.ptr->stop : nullptr;
   o.want_virial = false;
+  o.role = md->dd->nranks > 1 ? md->role.ptr : nullptr;
   switch (md->pot_kind) {
     case ATX_POT_EAM:
       return atx_eam_compute_device((atx_eam *)md->pot, &md->ploc, md->nl, nullptr, o);
@@ -540,19 +576,16 @@ static int dd_rebuild(atx_ddmd *md) {
   if (md->dd->nranks > 1) {
     if (n > 0) {
       k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 1, md->flags.ptr);
-      ATX_LAUNCHED();
+      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 2, md->flags2.ptr);
+      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 0, md->flags3.ptr);
+      g_atx_launches += 3;
     }
-    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendL.ptr, &nL));
-    if (n > 0) {
-      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 2, md->flags.ptr);
-      ATX_LAUNCHED();
-    }
-    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendR.ptr, &nR));
-    if (n > 0) {
-      k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo_own, md->shi_own, 0, md->flags.ptr);
-      ATX_LAUNCHED();
-    }
-    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sel.ptr, &nstay));
+    ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendL.ptr, 0));
+    ATX_PASS(dd_select(md, n, md->flags2.ptr, md->sendR.ptr, 1));
+    ATX_PASS(dd_select(md, n, md->flags3.ptr, md->sel.ptr, 2));
+    int c3[3];
+    ATX_PASS(dd_read_counts(md, 3, c3));
+    nL = c3[0]; nR = c3[1]; nstay = c3[2];
     if ((md->left < 0 && nL > 0) || (md->right < 0 && nR > 0)) {
       atx_set_error("Particle outside simulation domain (left the non-periodic box along x).");
       return ATX_ERROR_UNSPECIFIED;
@@ -576,60 +609,63 @@ static int dd_rebuild(atx_ddmd *md) {
                                                        md->mig_send.ptr + (size_t)DD_ROW * nL);
       ATX_LAUNCHED();
     }
-    ATX_PASS(dd_sendrecv(md, md->mig_send.ptr, (size_t)DD_ROW * nL, md->mig_send.ptr + (size_t)DD_ROW * nL,
-                         (size_t)DD_ROW * nR, md->mig_recv.ptr, (size_t)DD_ROW * inL,
-                         md->mig_recv.ptr + (size_t)DD_ROW * inL, (size_t)DD_ROW * inR));
-    // compact the stayers into fresh arrays, append the arrivals
+    if (nL + nR + inL + inR > 0 || true) {
+      ATX_PASS(dd_sendrecv(md, md->mig_send.ptr, (size_t)DD_ROW * nL, md->mig_send.ptr + (size_t)DD_ROW * nL,
+                           (size_t)DD_ROW * nR, md->mig_recv.ptr, (size_t)DD_ROW * inL,
+                           md->mig_recv.ptr + (size_t)DD_ROW * inL, (size_t)DD_ROW * inR));
+    }
+    // compact the stayers into the alternate arrays, append the arrivals, swap
     int nnew = nstay + inL + inR;
-    size_t want = (size_t)nnew + nnew / 4 + 1024;
-    DevBuf<double> r2, v2, minv2, idd2, f2;
-    DevBuf<int> el2;
-    ATX_PASS(r2.reserve(3 * want)); ATX_PASS(v2.reserve(3 * want)); ATX_PASS(f2.reserve(3 * want));
-    ATX_PASS(minv2.reserve(want)); ATX_PASS(idd2.reserve(want)); ATX_PASS(el2.reserve(want));
+    ATX_PASS(dd_reserve_local(md, (size_t)nnew));
     if (nstay > 0) {
       k_dd_gather_owned<<<(nstay + 255) / 256, 256, 0, st>>>(nstay, md->sel.ptr, md->idd.ptr, md->el.ptr, md->r.ptr,
-                                                            md->v.ptr, md->minv.ptr, idd2.ptr, el2.ptr, r2.ptr,
-                                                            v2.ptr, minv2.ptr);
+                                                            md->v.ptr, md->minv.ptr, md->idd2.ptr, md->el2.ptr,
+                                                            md->r2.ptr, md->v2.ptr, md->minv2.ptr);
       ATX_LAUNCHED();
     }
     if (inL > 0) {
       k_dd_unpack_rows<<<(inL + 127) / 128, 128, 0, st>>>(inL, nstay, md->mig_recv.ptr, -t[0], -t[1], -t[2],
-                                                          idd2.ptr, el2.ptr, r2.ptr, v2.ptr, minv2.ptr);
+                                                          md->idd2.ptr, md->el2.ptr, md->r2.ptr, md->v2.ptr,
+                                                          md->minv2.ptr);
       ATX_LAUNCHED();
     }
     if (inR > 0) {
       k_dd_unpack_rows<<<(inR + 127) / 128, 128, 0, st>>>(inR, nstay + inL, md->mig_recv.ptr + (size_t)DD_ROW * inL,
-                                                          -t[0], -t[1], -t[2], idd2.ptr, el2.ptr, r2.ptr, v2.ptr,
-                                                          minv2.ptr);
+                                                          -t[0], -t[1], -t[2], md->idd2.ptr, md->el2.ptr, md->r2.ptr,
+                                                          md->v2.ptr, md->minv2.ptr);
       ATX_LAUNCHED();
     }
-    ATX_CUDA(cudaStreamSynchronize(st));
-    swapbuf(md->r, r2); swapbuf(md->v, v2); swapbuf(md->f, f2); swapbuf(md->minv, minv2);
-    swapbuf(md->idd, idd2); swapbuf(md->el, el2);
+    swapbuf(md->r, md->r2); swapbuf(md->v, md->v2); swapbuf(md->f, md->f2); swapbuf(md->minv, md->minv2);
+    swapbuf(md->idd, md->idd2); swapbuf(md->el, md->el2);
     md->nown = n = nnew;
     gb = (n + 255) / 256;
-    ATX_PASS(md->flags.reserve(want)); ATX_PASS(md->sel.reserve(want));
-    ATX_PASS(md->sendL.reserve(want)); ATX_PASS(md->sendR.reserve(want));
   }
 
   // ---- ghosts: owned atoms within the halo of a face are sent to that neighbour
   md->nsendL = md->nsendR = md->ngl = md->ngr = 0;
   if (md->dd->nranks > 1) {
+    ATX_CUDA(cudaMemsetAsync(md->cnt.ptr + 8, 0, 2 * sizeof(int), st));
     if (md->left >= 0) {
       if (n > 0) {
         k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], md->slo + md->hfrac, 2.0, 1,
                                        md->flags.ptr);
         ATX_LAUNCHED();
       }
-      ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendL.ptr, &md->nsendL));
+      ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendL.ptr, 0));
     }
     if (md->right >= 0) {
       if (n > 0) {
         k_dd_flags<<<gb, 256, 0, st>>>(n, md->r.ptr, b0, b1, b2, t[0], t[1], t[2], -1.0, md->shi - md->hfrac, 2,
-                                       md->flags.ptr);
+                                       md->flags2.ptr);
         ATX_LAUNCHED();
       }
-      ATX_PASS(dd_select(md, n, md->flags.ptr, md->sendR.ptr, &md->nsendR));
+      ATX_PASS(dd_select(md, n, md->flags2.ptr, md->sendR.ptr, 1));
+    }
+    {
+      int c2[2];
+      ATX_PASS(dd_read_counts(md, 2, c2));
+      md->nsendL = c2[0];
+      md->nsendR = c2[1];
     }
     ATX_PASS(dd_exchange_counts(md, md->nsendL, md->nsendR, &md->ngl, &md->ngr));
     int nloc = n + md->ngl + md->ngr;
@@ -689,6 +725,14 @@ static int dd_build_list(atx_ddmd *md) {
   std::swap(md->ploc.el.ptr, md->el.ptr);
   std::swap(md->ploc.el.cap, md->el.cap);
   if (err) return err;
+  if (md->dd->nranks > 1 && nloc > 0) {
+    // inner ghosts: within rc + skin (= half the halo) of the slab; + a small margin
+    const double band = 0.5 * md->hfrac * 1.02;
+    k_dd_roles<<<(nloc + 255) / 256, 256, 0, st>>>(nloc, n, md->nl->order.ptr, md->r.ptr, md->B.m[0], md->B.m[3],
+                                                   md->B.m[6], t[0], t[1], t[2], md->slo - band, md->shi + band,
+                                                   md->role.ptr);
+    ATX_LAUNCHED();
+  }
   md->nrebuilds++;
   return 0;
 }
@@ -834,6 +878,7 @@ extern "C" int atx_dd_md_destroy(atx_ddmd *md) {
 }
 
 static int dd_enqueue_step(atx_ddmd *md) {
+  ProfScope ps_step(md->ctx, "dd_step");
   atx_dd *dd = md->dd;
   cudaStream_t st = md->ctx->stream;
   const int n = md->nown, nloc = n + md->ngl + md->ngr;
@@ -847,7 +892,10 @@ static int dd_enqueue_step(atx_ddmd *md) {
   ATX_LAUNCHED();
   if (dd->nranks > 1) {
     // global OR of the rebuild wish, written straight into the stop flag (no host involvement)
-    ATX_NCCL(g_nccl.AllReduce(&md->ctrl.ptr->want, &md->ctrl.ptr->stop, 1, ncclInt, ncclMax, dd->comm, st));
+    {
+      ProfScope ps_(md->ctx, "dd_allreduce");
+      ATX_NCCL(g_nccl.AllReduce(&md->ctrl.ptr->want, &md->ctrl.ptr->stop, 1, ncclInt, ncclMax, dd->comm, st));
+    }
     // ghost positions: my frame -> global (+ periodic wrap) -> receiver frame.  The local origins
     // of neighbouring slabs differ by a1/P once the wrap is included, so the whole frame change is
     // a constant shift applied by the sender.
@@ -863,9 +911,12 @@ static int dd_enqueue_step(atx_ddmd *md) {
                                                           dR * md->a1[1], dR * md->a1[2], md->bufR.ptr, stop);
       ATX_LAUNCHED();
     }
-    ATX_PASS(dd_sendrecv(md, md->bufL.ptr, 3 * (size_t)md->nsendL, md->bufR.ptr, 3 * (size_t)md->nsendR,
-                         md->r.ptr + 3 * (size_t)n, 3 * (size_t)md->ngl,
-                         md->r.ptr + 3 * (size_t)(n + md->ngl), 3 * (size_t)md->ngr));
+    {
+      ProfScope ps_(md->ctx, "dd_halo");
+      ATX_PASS(dd_sendrecv(md, md->bufL.ptr, 3 * (size_t)md->nsendL, md->bufR.ptr, 3 * (size_t)md->nsendR,
+                           md->r.ptr + 3 * (size_t)n, 3 * (size_t)md->ngl,
+                           md->r.ptr + 3 * (size_t)(n + md->ngl), 3 * (size_t)md->ngr));
+    }
   } else {
     // single rank: want -> stop
     ATX_CUDA(cudaMemcpyAsync(&md->ctrl.ptr->stop, &md->ctrl.ptr->want, sizeof(int), cudaMemcpyDeviceToDevice, st));

@@ -289,14 +289,14 @@ __global__ void __launch_bounds__(128)
 k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
                    const long long *__restrict__ seed, const int2 *__restrict__ list,
                    double4 *__restrict__ pd4, double *__restrict__ Fe,
-                   const int *__restrict__ stop) {
+                   const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   const int gpb = 128 / LANES;
   const int s = blockIdx.x * gpb + threadIdx.x / LANES;
   const int lane = threadIdx.x % LANES;
   const bool valid = s < nat;
   const double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
-  const int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  const int dbi = (valid && (!role || role[s] >= 1)) ? T->el2db[(int)pi.w] : -1;
   const double cutoff_sq = T->cutoff_sq, x0 = T->r_x0, inv_dx = T->r_inv_dx;
   const int nr = T->r_n;
   double rho = 0.0;
@@ -358,7 +358,7 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
                  const double4 *__restrict__ pos4, const long long *__restrict__ seed,
                  const int2 *__restrict__ list, const double *__restrict__ Fe, double *__restrict__ f,
                  double *__restrict__ epa, double *__restrict__ partials,
-                 const int *__restrict__ stop) {
+                 const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   __shared__ double red[ATX_NSUM * 4];
   const int gpb = 128 / LANES;
@@ -366,7 +366,7 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
   const int lane = threadIdx.x % LANES;
   const bool valid = s < nat;
   const double4 pi = valid ? pd4[s] : make_double4(0, 0, 0, 0);
-  const int dbi = valid ? T->el2db[(int)pos4[s].w] : -1;
+  const int dbi = (valid && (!role || role[s] >= 2)) ? T->el2db[(int)pos4[s].w] : -1;
   const double cutoff_sq = T->cutoff_sq, x0 = T->r_x0, inv_dx = T->r_inv_dx;
   const int nr = T->r_n, ndb = T->ndb;
   double fx = 0.0, fy = 0.0, fz = 0.0, en_ = 0.0;
@@ -595,18 +595,18 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
       ProfScope ps_(ctx, "eam_density");                                                          \
       k_eam_density_fast<LL, UU><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,    \
                                                      nl->seed.ptr, nl->list.ptr, pot->pd4.ptr,    \
-                                                     pot->Fe.ptr, o.stop);                        \
+                                                     pot->Fe.ptr, o.role, o.stop);                \
     }                                                                                             \
     ATX_LAUNCHED();                                                                               \
     ProfScope ps2_(ctx, "eam_force");                                                             \
     if (vir)                                                                                      \
       k_eam_force_fast<LL, UU, true><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
           nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr, \
-          o.stop);                                                                                \
+          o.role, o.stop);                                                                        \
     else                                                                                          \
       k_eam_force_fast<LL, UU, false><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
           nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr, \
-          o.stop);                                                                                \
+          o.role, o.stop);                                                                        \
     ATX_LAUNCHED();                                                                               \
   } while (0)
     const int U = pot->fast_unroll;

@@ -236,6 +236,7 @@ def run_ours(args):
     dens_ms, dens_n = prof('eam_density')
     cnt_ms, cnt_n = prof('nl_pairs_count')
     fill_ms, fill_n = prof('nl_pairs_fill')
+    dd_prof = {k: prof(k)[0] for k in ('dd_allreduce', 'dd_halo', 'dd_step')} if world > 1 else None
     if dist is not None:
         import torch
         t = torch.tensor([dev_ms], dtype=torch.float64)
@@ -304,7 +305,7 @@ def run_ours(args):
                       avg_launch_ms=force_avg_ms, launches=force_n, list_neighbors_per_atom=z_list,
                       share_of_step=force_ms / dev_ms if dev_ms else None),
         kernels_ms=dict(eam_force=force_ms, eam_density=dens_ms, nl_pairs_count=cnt_ms, nl_pairs_fill=fill_ms,
-                        total_device=dev_ms),
+                        total_device=dev_ms, dd=dd_prof),
         fp64_peak_tflops_measured=fp64.value,
         md=dict(epot=epot, ekin=ekin, rebuilds=rebuilds, rebuild_interval=steps / max(rebuilds, 1),
                 wall_s=wall, owned_atoms_rank0=nown, ghost_atoms_rank0=nghost),

@@ -451,6 +451,11 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   return 0;
 }
 
+extern "C" int atx_neighbors_rebuild(atx_neighbors *nl, atx_particles *p) {
+  nl->p_rev = -1;
+  return atx_neighbors_update(nl, p);
+}
+
 int atx_neighbors_refresh_positions(atx_neighbors *nl, atx_particles *p) {
   int nat = nl->nat;
   if (nat > 0) {

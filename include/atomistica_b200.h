@@ -78,6 +78,8 @@ int atx_neighbors_set_verlet_shell(atx_neighbors *nl, double verlet_shell);
 /* neighbors_update -> binning_update + fill_neighbor_list (:430-754, 904-959).
  * Fails with "Neighbor list overflow" when pairs + nat exceed nat*avgn (:716-718). */
 int atx_neighbors_update(atx_neighbors *nl, atx_particles *p);
+/* rebuild unconditionally (positions already on the device); used by the rebuild sweeps */
+int atx_neighbors_rebuild(atx_neighbors *nl, atx_particles *p);
 /* number of pairs, max neighbours per atom, n_cells(3), stencil half widths(3) */
 int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax, int *n_cells,
                            int *stencil);

@@ -61,6 +61,7 @@ SYMBOLS = [
     'atx_dd_get_unique_id', 'atx_dd_create', 'atx_dd_destroy', 'atx_dd_md_create', 'atx_dd_md_destroy',
     'atx_dd_md_run', 'atx_dd_md_get_count', 'atx_dd_md_get_state', 'atx_dd_md_get_stats',
     'atx_profile_enable', 'atx_profile_read', 'atx_measure_fp64_peak', 'atx_measure_copy_bandwidth',
+    'atx_host_alloc_pinned', 'atx_host_free_pinned',
     'atx_host_spline_init', 'atx_host_gaussn', 'atx_host_table2d_init', 'atx_host_table3d_init',
     'atx_host_rebo2_g_spline',
 ]
@@ -119,3 +120,23 @@ def kernel_launches(reset=False):
 
 def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PinnedArray:
+    """float64 numpy array backed by page-locked host memory (cudaMallocHost through the C ABI)"""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        context(0)     # pinned allocation needs a CUDA context
+        check(lib().atx_host_alloc_pinned(C.c_size_t(8 * max(n, 1)), C.byref(self._ptr)))
+        buf = (C.c_double * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+        self.array[...] = 0.0
+
+    def __del__(self):
+        try:
+            self.array = None
+            lib().atx_host_free_pinned(self._ptr)
+        except Exception:
+            pass

@@ -9,6 +9,7 @@ number or type of atoms changes, stress = voigt(wpot)/volume.
 """
 import numpy as np
 
+from . import _lib as L
 from . import native
 from .elements import atomic_numbers
 
@@ -24,6 +25,7 @@ class Atomistica:
             self.avgn = avgn
         self.particles = None
         self.nl = None
+        self._fbuf = None
         self.mask = None
         self.results = {}
         self.kwargs = kwargs
@@ -43,7 +45,7 @@ class Atomistica:
         self.particles = native.Particles(self.device)
         self.particles.allocate(len(atoms))
         self.particles.set_cell(atoms.cell, atoms.pbc)
-        self.particles.Z[:] = [atomic_numbers[s] for s in atoms.symbols]
+        self.particles.Z[:] = atoms.get_atomic_numbers()
         self.particles.coordinates[:, :] = atoms.positions
         self.particles.I_changed_positions()
         self.particles.update_elements()
@@ -64,7 +66,7 @@ class Atomistica:
 
     # aseinterface.py:300-333
     def update(self, atoms):
-        Z = np.array([atomic_numbers[s] for s in atoms.symbols], dtype=np.int32)
+        Z = atoms.get_atomic_numbers()
         if self.particles is None or len(self.particles.Z) != len(atoms):
             self.initialize(atoms)
         elif np.any(self.particles.Z != Z):
@@ -80,7 +82,11 @@ class Atomistica:
     def calculate(self, atoms, properties=('energy',)):
         self.update(atoms)
         epot = 0.0
-        forces = np.zeros((len(self.particles), 3))
+        nat = len(self.particles)
+        if self._fbuf is None or self._fbuf.array.shape[0] != nat:
+            self._fbuf = L.PinnedArray((nat, 3))     # page-locked force buffer, reused between calls
+        forces = self._fbuf.array
+        forces[...] = 0.0
         wpot = np.zeros((3, 3))
         per_at_e = 'energies' in properties
         per_at_w = 'stresses' in properties
@@ -96,7 +102,7 @@ class Atomistica:
             epot += _e
             wpot += _w
         volume = atoms.get_volume()
-        self.results = dict(energy=epot, free_energy=epot, forces=forces, wpot=wpot)
+        self.results = dict(energy=epot, free_energy=epot, forces=forces.copy(), wpot=wpot)
         self.results['stress'] = np.array([wpot[0, 0], wpot[1, 1], wpot[2, 2], (wpot[1, 2] + wpot[2, 1]) / 2,
                                            (wpot[0, 2] + wpot[2, 0]) / 2, (wpot[0, 1] + wpot[1, 0]) / 2]) / volume
         if per_at_e:

@@ -123,6 +123,17 @@ extern "C" int atx_particles_set_elements(atx_particles *p, int nat, const int *
   return 0;
 }
 
+extern "C" int atx_host_alloc_pinned(size_t bytes, void **ptr) {
+  if (!ptr) return ATX_ERROR_UNSPECIFIED;
+  ATX_CUDA(cudaMallocHost(ptr, bytes ? bytes : 8));
+  return 0;
+}
+
+extern "C" int atx_host_free_pinned(void *ptr) {
+  if (ptr) ATX_CUDA(cudaFreeHost(ptr));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // scans
 // ---------------------------------------------------------------------------

@@ -9,11 +9,24 @@ _FCC = np.array([[0, 0, 0], [0, .5, .5], [.5, 0, .5], [.5, .5, 0]])
 _DIA = np.concatenate([_FCC, _FCC + 0.25])
 
 
+class _Symbols(list):
+    """list of chemical symbols that invalidates the owner's cached atomic numbers on assignment"""
+
+    def __init__(self, owner, items):
+        super().__init__(items)
+        self._owner = owner
+        owner._numbers = None
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, v)
+        self._owner._numbers = None
+
+
 class Atoms:
     """Minimal stand-in for ase.Atoms: positions, numbers/symbols, cell (rows = vectors), pbc."""
 
     def __init__(self, symbols, positions, cell, pbc=True):
-        self.symbols = list(symbols)
+        self.symbols = _Symbols(self, symbols)
         self.positions = np.array(positions, dtype=np.float64).reshape(-1, 3)
         cell = np.array(cell, dtype=np.float64)
         self.cell = np.diag(cell) if cell.shape == (3,) else cell
@@ -30,8 +43,11 @@ class Atoms:
         return abs(np.linalg.det(self.cell))
 
     def get_atomic_numbers(self):
-        from .elements import atomic_numbers
-        return np.array([atomic_numbers[s] for s in self.symbols], dtype=np.int32)
+        """cached like ase.Atoms.numbers; invalidated when a symbol is assigned"""
+        if self._numbers is None:
+            from .elements import atomic_numbers
+            self._numbers = np.array([atomic_numbers[s] for s in self.symbols], dtype=np.int32)
+        return self._numbers
 
     def set_cell(self, cell, scale_atoms=False):
         cell = np.array(cell, dtype=np.float64)

@@ -22,6 +22,7 @@
 #ifndef ATOMISTICA_B200_H
 #define ATOMISTICA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -248,6 +249,11 @@ int atx_profile_read(atx_ctx *ctx, const char *name, double *total_ms, long long
 int atx_measure_fp64_peak(atx_ctx *ctx, double *tflops);
 /* device copy bandwidth (GB/s, read+write bytes), measured with a 1 GiB grid-stride copy */
 int atx_measure_copy_bandwidth(atx_ctx *ctx, double *gbs);
+
+/* page-locked host memory for the arrays the host hands to the library every call (r_non_cyc, f):
+ * copies from/to such buffers run at full PCIe speed and need no staging */
+int atx_host_alloc_pinned(size_t bytes, void **ptr);
+int atx_host_free_pinned(void *ptr);
 
 /* ---- host-side init helpers ------------------------------------------------ */
 /* The reference computes these on the host in Fortran; a Fortran host keeps doing so and passes

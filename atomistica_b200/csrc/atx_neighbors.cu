@@ -200,13 +200,16 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
         for (int t = b; t < e; t++) {
           int4 cj = sshift[t];
           int s2x = sx - cj.y, s2y = sy - cj.z, s2z = sz - cj.w;
-          if (t == s && s2x == 0 && s2y == 0 && s2z == 0) continue;
+          const bool zero = (s2x | s2y | s2z) == 0;
+          if (t == s && zero) continue;
           double4 pj = pos4[t];
-          double ax, ay, az;
-          atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
-          double dx = __dadd_rn(__dsub_rn(pi.x, pj.x), ax);
-          double dy = __dadd_rn(__dsub_rn(pi.y, pj.y), ay);
-          double dz = __dadd_rn(__dsub_rn(pi.z, pj.z), az);
+          double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
+          if (!zero) {
+            // + matmul(Abox, shift2); adding the exact zero vector is skipped (bit-identical)
+            double ax, ay, az;
+            atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
+            dx = __dadd_rn(dx, ax); dy = __dadd_rn(dy, ay); dz = __dadd_rn(dz, az);
+          }
           double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
           if (d2 < g.cutoff_sq) {
             if (FILL) {
@@ -223,9 +226,14 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
   }
   if (!FILL) {
     count[s] = cnt;
-    if (cnt > 0) {
-      atomicMax((unsigned long long *)&scal[1], (unsigned long long)cnt);
-      atomicMax((unsigned long long *)&scal[2], (unsigned long long)(order[s] + 1));
+    // warp-aggregated maxima (one atomic per warp instead of two per atom: the per-address
+    // serialisation of L2 atomics cost more than the whole pair search)
+    const unsigned active = __activemask();
+    int mc = __reduce_max_sync(active, cnt);
+    int ml = __reduce_max_sync(active, cnt > 0 ? order[s] + 1 : 0);
+    if ((threadIdx.x & 31) == __ffs(active) - 1 && mc > 0) {
+      atomicMax((unsigned long long *)&scal[1], (unsigned long long)mc);
+      atomicMax((unsigned long long *)&scal[2], (unsigned long long)ml);
     }
   }
 }

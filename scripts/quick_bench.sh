@@ -6,5 +6,5 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().split(chr(10))[-1])
 n=d['steps']
 print('value %.1f M atom-steps/s  ms/step %.4f  e2e %.1f M' % (d['value']/1e6, d['ms_per_step'], d['e2e']['value']/1e6))
-print({k: round(v/n*1e3,1) for k,v in d['kernels_ms'].items()}, 'us per step;', d['md'])
+print({k: round(v/n*1e3,1) for k,v in d['kernels_ms'].items() if isinstance(v, float)}, 'us per step;', d['md'])
 print('roofline', d['roofline'])"

@@ -175,8 +175,6 @@ struct atx_neighbors {
   DevBuf<int> count;        // nat+1 neighbour counts (sorted order)
   DevBuf<long long> seed;   // nat+1 exclusive offsets (sorted order), 0-based
   DevBuf<int2> list;        // device list: {sorted j, packed shift}
-  DevBuf<char> masks;       // hit masks of the warp-per-atom pair search (nat x stencil cells)
-  int mask_bits = 32;       // 32 or 64 (widened when a cell holds more atoms)
   DevBuf<int> rev;          // optional reverse-slot index
   bool rev_valid = false;
   DevBuf<long long> scal;   // small scalar scratch (npairs, nebmax, flags)

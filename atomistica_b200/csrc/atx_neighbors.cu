@@ -130,12 +130,10 @@ __global__ void k_cell_scatter(int nat, const int4 *__restrict__ cellshift,
 }
 
 // ascending original index inside every cell == the reference's linked-list order
-__global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, int *__restrict__ order,
-                            long long *__restrict__ scal) {
+__global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, int *__restrict__ order) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncell) return;
   int b = cell_start[c], e = cell_start[c + 1];
-  if (e - b > 32) atomicMax((unsigned long long *)&scal[4], (unsigned long long)(e - b));
   for (int a = b + 1; a < e; a++) {
     int v = order[a];
     int q = a - 1;
@@ -224,159 +222,26 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
       }
     }
   }
-  if (!FILL) {
-    count[s] = cnt;
-    // warp-aggregated maxima (one atomic per warp instead of two per atom: the per-address
-    // serialisation of L2 atomics cost more than the whole pair search)
-    const unsigned active = __activemask();
-    int mc = __reduce_max_sync(active, cnt);
-    int ml = __reduce_max_sync(active, cnt > 0 ? order[s] + 1 : 0);
-    if ((threadIdx.x & 31) == __ffs(active) - 1 && mc > 0) {
-      atomicMax((unsigned long long *)&scal[1], (unsigned long long)mc);
-      atomicMax((unsigned long long *)&scal[2], (unsigned long long)ml);
-    }
-  }
+  if (!FILL) count[s] = cnt;
 }
 
-// ---------------------------------------------------------------------------
-// Warp-per-atom pair search (default path).
-//
-// One warp serves one atom, lane L owns stencil cell L (z fastest, so neighbouring lanes read
-// neighbouring cells = contiguous runs of the sorted position array).  The count pass evaluates the
-// exact predicate once per candidate and keeps the hits of every (atom, stencil cell) as a bit mask
-// (MASK = 32 or 64 bits, chosen from the fullest cell); the fill pass expands the masks in stencil
-// order -- the reference's list order -- without touching positions again.  Compared with the
-// thread-per-atom kernels below (kept for stencils > 128 cells or cells fuller than 64 atoms) every
-// distance is computed once instead of twice and the 27 cells of an atom are searched in parallel.
-// ---------------------------------------------------------------------------
-
-#define NL_WARPS 4   // atoms per CTA
-
-__device__ __forceinline__ bool stencil_cell(const Geo &g, const int ci[3], const int wi[3], int sc,
-                                             int &cid, int &sx, int &sy, int &sz) {
-  const int nz = 2 * g.sten[2] + 1, ny = 2 * g.sten[1] + 1;
-  int z = sc % nz - g.sten[2];
-  int y = (sc / nz) % ny - g.sten[1];
-  int x = sc / (nz * ny) - g.sten[0];
-  int cx = ci[0] + x, cy = ci[1] + y, cz = ci[2] + z;
-  sx = wi[0]; sy = wi[1]; sz = wi[2];
-  if (g.pbc[0]) {
-    while (cx < 0) { cx += g.n[0]; sx += 1; }
-    while (cx >= g.n[0]) { cx -= g.n[0]; sx -= 1; }
-  } else if (cx < 0 || cx >= g.n[0]) return false;
-  if (g.pbc[1]) {
-    while (cy < 0) { cy += g.n[1]; sy += 1; }
-    while (cy >= g.n[1]) { cy -= g.n[1]; sy -= 1; }
-  } else if (cy < 0 || cy >= g.n[1]) return false;
-  if (g.pbc[2]) {
-    while (cz < 0) { cz += g.n[2]; sz += 1; }
-    while (cz >= g.n[2]) { cz -= g.n[2]; sz -= 1; }
-  } else if (cz < 0 || cz >= g.n[2]) return false;
-  cid = (cx * g.n[1] + cy) * g.n[2] + cz;
-  return true;
-}
-
-template <typename MASK>
-__global__ void __launch_bounds__(32 * NL_WARPS)
-k_pairs_count_warp(int nat, Geo g, int nsc, int nscp, const double4 *__restrict__ pos4,
-                   const int4 *__restrict__ sshift, const int *__restrict__ cell_start,
-                   const int *__restrict__ order, int *__restrict__ count, MASK *__restrict__ masks,
-                   long long *__restrict__ scal) {
-  const int s = blockIdx.x * NL_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (s >= nat) return;
-  const double4 pi = pos4[s];
-  const int4 cs = sshift[s];
-  int ci[3], wi[3] = {cs.y, cs.z, cs.w};
-  ci[2] = cs.x % g.n[2];
-  ci[1] = (cs.x / g.n[2]) % g.n[1];
-  ci[0] = cs.x / (g.n[2] * g.n[1]);
-  int total = 0;
-  for (int sc = lane; sc < nscp; sc += 32) {
-    MASK m = 0;
-    int cid, sx, sy, sz;
-    if (sc < nsc && stencil_cell(g, ci, wi, sc, cid, sx, sy, sz)) {
-      const int b = cell_start[cid];
-      int e = cell_start[cid + 1];
-      if (e - b > (int)(8 * sizeof(MASK))) {
-        // cell fuller than the mask is wide: report, the host repeats with a wider mask
-        atomicMax((unsigned long long *)&scal[5], (unsigned long long)(e - b));
-        e = b + 8 * sizeof(MASK);
-      }
-      for (int t = b; t < e; t++) {
-        const int4 cj = sshift[t];
-        const int s2x = sx - cj.y, s2y = sy - cj.z, s2z = sz - cj.w;
-        const bool zero = (s2x | s2y | s2z) == 0;
-        if (t == s && zero) continue;
-        const double4 pj = pos4[t];
-        double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
-        if (!zero) {
-          // + matmul(Abox, shift2); adding an exact zero vector is skipped (bit-identical)
-          double ax, ay, az;
-          atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
-          dx = __dadd_rn(dx, ax); dy = __dadd_rn(dy, ay); dz = __dadd_rn(dz, az);
-        }
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (d2 < g.cutoff_sq) m |= (MASK)1 << (t - b);
-      }
-    }
-    masks[(size_t)s * nscp + sc] = m;
-    total += sizeof(MASK) == 8 ? __popcll((unsigned long long)m) : __popc((unsigned int)m);
+// nebmax = max count, i_last = largest original index (1-based) of an atom that has a pair.
+// (Per-atom atomicMax on two addresses used to cost more than the pair search itself: L2 atomics
+// serialise per address.)
+__global__ void __launch_bounds__(256)
+k_count_stats(int nat, const int *__restrict__ count, const int *__restrict__ order,
+              long long *__restrict__ scal) {
+  int mc = 0, ml = 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nat; s += gridDim.x * blockDim.x) {
+    int c = count[s];
+    mc = max(mc, c);
+    if (c > 0) ml = max(ml, order[s] + 1);
   }
-  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  if (lane == 0) {
-    count[s] = total;
-    if (total > 0) {
-      atomicMax((unsigned long long *)&scal[1], (unsigned long long)total);
-      atomicMax((unsigned long long *)&scal[2], (unsigned long long)(order[s] + 1));
-    }
-  }
-}
-
-template <typename MASK>
-__global__ void __launch_bounds__(32 * NL_WARPS)
-k_pairs_fill_warp(int nat, Geo g, int nsc, int nscp, const double4 *__restrict__ pos4,
-                  const int4 *__restrict__ sshift, const int *__restrict__ cell_start,
-                  const long long *__restrict__ seed, const MASK *__restrict__ masks,
-                  int2 *__restrict__ list, long long *__restrict__ scal) {
-  const int s = blockIdx.x * NL_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (s >= nat) return;
-  const int4 cs = sshift[s];
-  int ci[3], wi[3] = {cs.y, cs.z, cs.w};
-  ci[2] = cs.x % g.n[2];
-  ci[1] = (cs.x / g.n[2]) % g.n[1];
-  ci[0] = cs.x / (g.n[2] * g.n[1]);
-  long long w0 = seed[s];
-  for (int sc0 = 0; sc0 < nscp; sc0 += 32) {
-    const int sc = sc0 + lane;
-    MASK m = masks[(size_t)s * nscp + sc];
-    int n = sizeof(MASK) == 8 ? __popcll((unsigned long long)m) : __popc((unsigned int)m);
-    // exclusive prefix over the lanes: stencil order
-    int pre = n;
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, pre, o);
-      if (lane >= o) pre += v;
-    }
-    const int round_total = __shfl_sync(0xffffffffu, pre, 31);
-    pre -= n;
-    if (m) {
-      int cid, sx, sy, sz;
-      stencil_cell(g, ci, wi, sc, cid, sx, sy, sz);
-      const int b = cell_start[cid];
-      long long w = w0 + pre;
-      while (m) {
-        const int bit = sizeof(MASK) == 8 ? __ffsll((long long)m) - 1 : __ffs((int)m) - 1;
-        m &= m - 1;
-        const int t = b + bit;
-        const int4 cj = sshift[t];
-        const int s2x = sx - cj.y, s2y = sy - cj.z, s2z = sz - cj.w;
-        if ((abs(s2x) >= ATX_SHIFT_BIAS) | (abs(s2y) >= ATX_SHIFT_BIAS) | (abs(s2z) >= ATX_SHIFT_BIAS))
-          atomicMax((unsigned long long *)&scal[3], 1ull);
-        list[w++] = make_int2(t, atx_pack_shift(s2x, s2y, s2z) | ((int)pos4[t].w << 24));
-      }
-    }
-    w0 += round_total;
+  mc = __reduce_max_sync(0xffffffffu, mc);
+  ml = __reduce_max_sync(0xffffffffu, ml);
+  if ((threadIdx.x & 31) == 0 && mc > 0) {
+    atomicMax((unsigned long long *)&scal[1], (unsigned long long)mc);
+    atomicMax((unsigned long long *)&scal[2], (unsigned long long)ml);
   }
 }
 
@@ -549,50 +414,29 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     k_cell_scatter<<<gb, TB, 0, st>>>(nat, nl->cellshift.ptr, nl->cell_start.ptr, nl->cell_fill.ptr,
                                       nl->order.ptr);
     ATX_LAUNCHED();
-    k_cell_sort<<<(ncell + TB - 1) / TB, TB, 0, st>>>(ncell, nl->cell_start.ptr, nl->order.ptr, nl->scal.ptr);
+    k_cell_sort<<<(ncell + TB - 1) / TB, TB, 0, st>>>(ncell, nl->cell_start.ptr, nl->order.ptr);
     ATX_LAUNCHED();
     k_gather_sorted<<<gb, TB, 0, st>>>(nat, p->rptr(), p->el.cap ? p->el.ptr : nullptr,
                                        nl->cellshift.ptr, nl->order.ptr, nl->pos4.ptr,
                                        nl->sshift.ptr, nl->inv.ptr);
     ATX_LAUNCHED();
   }
-  const int nsc = (2 * nl->sten[0] + 1) * (2 * nl->sten[1] + 1) * (2 * nl->sten[2] + 1);
-  const int nscp = (nsc + 31) / 32 * 32;
-  bool warp_path = nscp <= 128 && nl->mask_bits <= 64 && !getenv("ATX_NL_THREAD_PER_ATOM");
   long long h[4] = {0, 0, 0, 0};
-  for (int attempt = 0; attempt < 3; attempt++) {
-    if (nat > 0) {
+  if (nat > 0) {
+    {
       ProfScope ps_(ctx, "nl_pairs_count");
-      if (warp_path) {
-        ATX_PASS(nl->masks.reserve((size_t)nat * nscp * (nl->mask_bits / 8) + 64));
-        const int nb = (nat + NL_WARPS - 1) / NL_WARPS;
-        if (nl->mask_bits == 32)
-          k_pairs_count_warp<unsigned int><<<nb, 32 * NL_WARPS, 0, st>>>(
-              nat, g, nsc, nscp, nl->pos4.ptr, nl->sshift.ptr, nl->cell_start.ptr, nl->order.ptr,
-              nl->count.ptr, (unsigned int *)nl->masks.ptr, nl->scal.ptr);
-        else
-          k_pairs_count_warp<unsigned long long><<<nb, 32 * NL_WARPS, 0, st>>>(
-              nat, g, nsc, nscp, nl->pos4.ptr, nl->sshift.ptr, nl->cell_start.ptr, nl->order.ptr,
-              nl->count.ptr, (unsigned long long *)nl->masks.ptr, nl->scal.ptr);
-      } else {
-        k_pairs<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
-                                                          nl->cell_start.ptr, nl->order.ptr,
-                                                          nl->count.ptr, nullptr, nullptr, nl->scal.ptr);
-      }
-      ATX_LAUNCHED();
+      k_pairs<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
+                                                        nl->cell_start.ptr, nl->order.ptr,
+                                                        nl->count.ptr, nullptr, nullptr, nl->scal.ptr);
     }
-    ATX_PASS(atx_scan_int_to_ll(ctx, nl->count.ptr, nl->seed.ptr, nat + 1));
-    long long over = 0;
-    ATX_CUDA(cudaMemcpyAsync(&h[0], nl->seed.ptr + nat, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    ATX_CUDA(cudaMemcpyAsync(&h[1], nl->scal.ptr + 1, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    ATX_CUDA(cudaMemcpyAsync(&over, nl->scal.ptr + 5, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    ATX_CUDA(cudaStreamSynchronize(st));
-    if (over == 0) break;
-    // a cell holds more atoms than the hit mask has bits: widen the mask (or fall back) and repeat
-    nl->mask_bits = over <= 64 ? 64 : 128;
-    warp_path = nl->mask_bits <= 64;
-    ATX_CUDA(cudaMemsetAsync(nl->scal.ptr, 0, sizeof(long long) * 8, st));
+    ATX_LAUNCHED();
+    k_count_stats<<<ctx->sm_count * 2, 256, 0, st>>>(nat, nl->count.ptr, nl->order.ptr, nl->scal.ptr);
+    ATX_LAUNCHED();
   }
+  ATX_PASS(atx_scan_int_to_ll(ctx, nl->count.ptr, nl->seed.ptr, nat + 1));
+  ATX_CUDA(cudaMemcpyAsync(&h[0], nl->seed.ptr + nat, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaMemcpyAsync(&h[1], nl->scal.ptr + 1, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
   nl->npairs = h[0];
   nl->nebmax = (int)h[1];
   long long i_last = h[2];  // 1-based original index of the last atom that has a pair
@@ -610,22 +454,10 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nat > 0 && nl->npairs > 0) {
     {
       ProfScope ps_(ctx, "nl_pairs_fill");
-      if (warp_path) {
-        const int nb = (nat + NL_WARPS - 1) / NL_WARPS;
-        if (nl->mask_bits == 32)
-          k_pairs_fill_warp<unsigned int><<<nb, 32 * NL_WARPS, 0, st>>>(
-              nat, g, nsc, nscp, nl->pos4.ptr, nl->sshift.ptr, nl->cell_start.ptr, nl->seed.ptr,
-              (const unsigned int *)nl->masks.ptr, nl->list.ptr, nl->scal.ptr);
-        else
-          k_pairs_fill_warp<unsigned long long><<<nb, 32 * NL_WARPS, 0, st>>>(
-              nat, g, nsc, nscp, nl->pos4.ptr, nl->sshift.ptr, nl->cell_start.ptr, nl->seed.ptr,
-              (const unsigned long long *)nl->masks.ptr, nl->list.ptr, nl->scal.ptr);
-      } else {
-        k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
-                                                         nl->cell_start.ptr, nl->order.ptr,
-                                                         nl->count.ptr, nl->seed.ptr, nl->list.ptr,
-                                                         nl->scal.ptr);
-      }
+      k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
+                                                       nl->cell_start.ptr, nl->order.ptr,
+                                                       nl->count.ptr, nl->seed.ptr, nl->list.ptr,
+                                                       nl->scal.ptr);
     }
     ATX_LAUNCHED();
     ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));

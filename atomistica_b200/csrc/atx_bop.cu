@@ -32,7 +32,9 @@ struct BopDev {
   double VR_f[6], expR[6], VA_f[6], expA[6], r0[6], gamma[6], c_sq[6], d_sq[6], c_d[6], ph[6],
       pn[6], bo_exp[6], bo_fac[6], bo_exp1[6];
   // precomputed Tersoff element constants
-  double tb[3];  // beta**n
+  double tb[3];          // beta**n
+  double te[3];          // -1/(2n)
+  double c_sq_e[3], d_sq_e[3], one_p_c2d2[3];  // c^2, d^2, 1 + c^2/d^2
 };
 
 struct atx_bop {
@@ -83,12 +85,12 @@ template <int KIND>
 __device__ __forceinline__ void bop_g(const BopDev &P, int ti, int ik, double costh, double &val,
                                       double &dval) {
   if (KIND == ATX_BOP_TERSOFF) {
-    double omega = P.omega[ik];
-    double h_c = P.h[ti] - costh;
-    double c_sq = P.c[ti] * P.c[ti], d_sq = P.d[ti] * P.d[ti];
-    double h = d_sq + h_c * h_c;
-    val = omega * (1.0 + c_sq / d_sq - c_sq / h);
-    dval = -2 * omega * c_sq * h_c / (h * h);
+    const double omega = P.omega[ik];
+    const double h_c = P.h[ti] - costh;
+    const double c_sq = P.c_sq_e[ti];
+    const double inv_h = 1.0 / (P.d_sq_e[ti] + h_c * h_c);
+    val = omega * (P.one_p_c2d2[ti] - c_sq * inv_h);
+    dval = -2 * omega * c_sq * h_c * inv_h * inv_h;
   } else if (KIND == ATX_BOP_KUMAGAI) {
     double h_cos = P.h[ti] - costh;
     double h_cos_sq = h_cos * h_cos;
@@ -99,47 +101,53 @@ __device__ __forceinline__ void bop_g(const BopDev &P, int ti, int ik, double co
     dval = -2 * (1.0 - h_cos * tmp) * v + 2 * P.c5[ti] * h_cos_sq * go * ga1;
     val = P.c1[ti] + h_cos * v;
   } else {
-    double hc = P.ph[ik] + costh;
-    double h = P.d_sq[ik] + hc * hc;
-    val = P.gamma[ik] * (1 + P.c_d[ik] - P.c_sq[ik] / h);
-    dval = 2 * P.gamma[ik] * P.c_sq[ik] * hc / (h * h);
+    const double hc = P.ph[ik] + costh;
+    const double inv_h = 1.0 / (P.d_sq[ik] + hc * hc);
+    val = P.gamma[ik] * (1 + P.c_d[ik] - P.c_sq[ik] * inv_h);
+    dval = 2 * P.gamma[ik] * P.c_sq[ik] * hc * inv_h * inv_h;
   }
 }
 
 template <int KIND>
 __device__ __forceinline__ void bop_bo(const BopDev &P, int ti, int ij, double zij, double fcij,
                                        double faij, double &bij, double &dfbij) {
+  // z**(n-1) and arg**(e-1) are formed as z**n / z and arg**e / arg: two pow() instead of four
   if (KIND == ATX_BOP_TERSOFF) {
     if (zij > 0.0) {
-      double n = P.n[ti];
-      double e = -0.5 / n;
-      double b = P.tb[ti];
-      double arg = 1.0 + b * pow(zij, n);
-      bij = P.xi[ij] * pow(arg, e);
-      dfbij = -0.25 * fcij * faij * P.xi[ij] * b * pow(zij, n - 1.0) * pow(arg, e - 1.0);
+      const double n = P.n[ti], e = P.te[ti], b = P.tb[ti];
+      const double zn = pow(zij, n);
+      const double arg = 1.0 + b * zn;
+      const double ae = pow(arg, e);
+      bij = P.xi[ij] * ae;
+      dfbij = -0.25 * fcij * faij * P.xi[ij] * b * (zn / zij) * (ae / arg);
     } else {
       bij = 1.0;
       dfbij = 0.0;
     }
   } else if (KIND == ATX_BOP_KUMAGAI) {
     if (zij > 0.0) {
-      double eta = P.eta[ti], delta = -P.delta[ti];
-      double arg = 1.0 + pow(zij, eta);
-      bij = pow(arg, delta);
-      dfbij = 0.5 * fcij * faij * eta * pow(zij, eta - 1.0) * delta * pow(arg, delta - 1.0);
+      const double eta = P.eta[ti], delta = -P.delta[ti];
+      const double zn = eta == 1.0 ? zij : pow(zij, eta);
+      const double arg = 1.0 + zn;
+      const double ad = pow(arg, delta);
+      bij = ad;
+      dfbij = 0.5 * fcij * faij * eta * (zn / zij) * delta * (ad / arg);
     } else {
       bij = 1.0;
       dfbij = 0.0;
     }
   } else {
     if (P.pn[ij] == 1.0) {
-      double arg = 1.0 + zij;
-      bij = pow(arg, P.bo_exp[ij]);
-      dfbij = P.bo_fac[ij] * fcij * faij * pow(arg, P.bo_exp1[ij]);
+      const double arg = 1.0 + zij;
+      const double ae = pow(arg, P.bo_exp[ij]);
+      bij = ae;
+      dfbij = P.bo_fac[ij] * fcij * faij * (ae / arg);
     } else if (zij > 0.0) {
-      double arg = 1.0 + pow(zij, P.pn[ij]);
-      bij = pow(arg, P.bo_exp[ij]);
-      dfbij = P.bo_fac[ij] * fcij * faij * pow(zij, P.pn[ij] - 1.0) * pow(arg, P.bo_exp1[ij]);
+      const double zn = pow(zij, P.pn[ij]);
+      const double arg = 1.0 + zn;
+      const double ae = pow(arg, P.bo_exp[ij]);
+      bij = ae;
+      dfbij = P.bo_fac[ij] * fcij * faij * (zn / zij) * (ae / arg);
     } else {
       bij = 1.0;
       dfbij = 0.0;
@@ -188,7 +196,7 @@ __device__ __forceinline__ void bop_h(const BopDev &P, int ik, double dr, double
 template <int NB>
 struct BondSmem {
   double rnx[NB][BOP_BLOCK], rny[NB][BOP_BLOCK], rnz[NB][BOP_BLOCK];
-  double rl[NB][BOP_BLOCK], fc[NB][BOP_BLOCK], dfc[NB][BOP_BLOCK];
+  double rl[NB][BOP_BLOCK], ri[NB][BOP_BLOCK], fc[NB][BOP_BLOCK], dfc[NB][BOP_BLOCK];
   double kx[NB][BOP_BLOCK], ky[NB][BOP_BLOCK], kz[NB][BOP_BLOCK];  // dbidk of the current ij
   double gx[NB][BOP_BLOCK], gy[NB][BOP_BLOCK], gz[NB][BOP_BLOCK], ge[NB][BOP_BLOCK];  // per-slot G
   int slot[NB][BOP_BLOCK];
@@ -254,8 +262,9 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
                   dfc = -0.5 * P.cfac[ij] * sn;
                 }
               }
-              S.rnx[nb][t] = dx / rl; S.rny[nb][t] = dy / rl; S.rnz[nb][t] = dz / rl;
-              S.rl[nb][t] = rl; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
+              const double ri = 1.0 / rl;
+              S.rnx[nb][t] = dx * ri; S.rny[nb][t] = dy * ri; S.rnz[nb][t] = dz * ri;
+              S.rl[nb][t] = rl; S.ri[nb][t] = ri; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
               S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0; S.ge[nb][t] = 0.0;
               S.slot[nb][t] = (int)(a - b0);
               S.typ[nb][t] = ij | (en.x << 3);
@@ -282,7 +291,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
       }
       const double rlij = S.rl[ij][t];
       if (!(maskfac > 0 && rlij < P.r2[tij])) continue;
-      const double rlijr = 1.0 / rlij;
+      const double rlijr = S.ri[ij][t];
       const double nx = S.rnx[ij][t], ny = S.rny[ij][t], nz = S.rnz[ij][t];
       const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
       const double fcarij = S.fc[ij][t], dfcarijr = S.dfc[ij][t];
@@ -314,10 +323,11 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
         bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
         double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
         const double disjk = sqrt(ex * ex + ey * ey + ez * ez);
-        ex /= disjk; ey /= disjk; ez /= disjk;
-        const double dcsdij = 1.0 / rlik - costh * rlijr;
-        const double dcsdik = rlijr - costh / rlik;
-        const double dcsdjk = -disjk * rlijr / rlik;
+        const double idis = 1.0 / disjk, rlikr = S.ri[ik][t];
+        ex *= idis; ey *= idis; ez *= idis;
+        const double dcsdij = rlikr - costh * rlijr;
+        const double dcsdik = rlijr - costh * rlikr;
+        const double dcsdjk = -disjk * rlijr * rlikr;
         const double dzfac = fcik * dg_dcosth * h_Dr;
         zij += fcik * g_costh * h_Dr;
         const double dzdrij = g_costh * fcik * dh_dDr;
@@ -475,6 +485,10 @@ extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop *
     D.c1[i] = par->c1[i]; D.c2[i] = par->c2[i]; D.c3[i] = par->c3[i]; D.c4[i] = par->c4[i];
     D.c5[i] = par->c5[i];
     D.tb[i] = par->kind == ATX_BOP_TERSOFF ? pow(par->beta[i], par->n[i]) : 0.0;
+    D.te[i] = par->kind == ATX_BOP_TERSOFF ? -0.5 / par->n[i] : 0.0;
+    D.c_sq_e[i] = par->c[i] * par->c[i];
+    D.d_sq_e[i] = par->d[i] * par->d[i];
+    D.one_p_c2d2[i] = par->kind == ATX_BOP_TERSOFF ? 1.0 + D.c_sq_e[i] / D.d_sq_e[i] : 0.0;
   }
   for (int k = 0; k < 32; k++) D.el2db[k] = -1;
   ATX_PASS(pot->flag.reserve(4));

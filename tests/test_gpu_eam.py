@@ -33,7 +33,10 @@ def _check(g, o, per_at=True):
     fscale = max(np.abs(o['f']).max(), 1.0)
     assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
     assert _close(f, o['f'], fscale)
-    assert _close(w, o['wpot'], max(np.abs(o['wpot']).max(), 1.0))
+    wscale = max(np.abs(o['wpot']).max(), 1.0)
+    if per_at:
+        wscale = max(wscale, np.abs(o['wpot_per_at']).sum(axis=0).max())   # magnitude of what is summed
+    assert _close(w, o['wpot'], wscale)
     if per_at:
         assert _close(epa, o['epot_per_at'])
         assert _close(wpa, o['wpot_per_at'], max(np.abs(o['wpot_per_at']).max(), 1.0))

@@ -33,9 +33,8 @@ def _check(g, o, per_at=True):
     fscale = max(np.abs(o['f']).max(), 1.0)
     assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
     assert _close(f, o['f'], fscale)
-    wscale = max(np.abs(o['wpot']).max(), 1.0)
-    if per_at:
-        wscale = max(wscale, np.abs(o['wpot_per_at']).sum(axis=0).max())   # magnitude of what is summed
+    # wpot = -dE/d(strain): cancelling sum of O(|E|) pair terms
+    wscale = max(np.abs(o['wpot']).max(), 1.0, abs(o['epot']))
     assert _close(w, o['wpot'], wscale)
     if per_at:
         assert _close(epa, o['epot_per_at'])

@@ -829,7 +829,11 @@ extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const doubl
   double *h = md->stage.ptr;
   // local frame = global - torig
   for (int i = 0; i < nown; i++) {
-    for (int c = 0; c < 3; c++) h[3 * i + c] = r[3 * i + c] - md->torig[c];
+    // periodic along a1: bring the atom into the primary image first (the caller assigns owners by
+    // the wrapped fractional coordinate but may pass unwrapped positions)
+    double wrap = 0.0;
+    if (md->pbc[0]) wrap = std::floor(Bbox[0] * r[3 * i] + Bbox[3] * r[3 * i + 1] + Bbox[6] * r[3 * i + 2]);
+    for (int c = 0; c < 3; c++) h[3 * i + c] = r[3 * i + c] - wrap * md->a1[c] - md->torig[c];
     h[3 * (size_t)nown + i] = 1.0 / mass[i];
     h[4 * (size_t)nown + i] = (double)id[i];
     for (int c = 0; c < 3; c++) h[5 * (size_t)nown + 3 * i + c] = v ? v[3 * i + c] : 0.0;

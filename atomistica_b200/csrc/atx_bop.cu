@@ -44,7 +44,11 @@ struct atx_bop {
   bool bound = false;
   DevBuf<double4> G;
   DevBuf<double> epb, fpb, wpb, epa_out;
-  DevBuf<int> flag;
+  DevBuf<int> flag;   // [0] overflow of the per-thread bond table, [1] max bonds per atom seen
+  PinBuf<int> hflag;
+  int nb_cap = 0;     // bond-table capacity (template NB) in use
+  const atx_neighbors *sized_nl = nullptr;  // list + build number nb_cap was sized for
+  long long sized_build = -1;
   PotScratch sc;
 };
 
@@ -191,6 +195,38 @@ __device__ __forceinline__ void bop_h(const BopDev &P, int ik, double dr, double
 }
 
 #define BOP_BLOCK 64
+
+// bonds (list entries inside the potential's r2) per atom -> flag[1] = maximum.  Sizes the
+// shared-memory bond table by BONDS, not by list entries: with a Verlet shell the list of an atom
+// can hold several times more entries than it has bonds.
+__global__ void k_bop_count_bonds(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
+                                  const long long *__restrict__ seed, const int2 *__restrict__ list,
+                                  int *__restrict__ flag) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int nb = 0;
+  if (s < nat) {
+    double4 pi = pos4[s];
+    const int eli = P.el2db[(int)pi.w];
+    if (eli > 0)
+      for (long long a = seed[s]; a < seed[s + 1]; a++) {
+        int2 en = list[a];
+        int elj = P.el2db[ATX_ENTRY_EL(en.y)];
+        if (elj <= 0) continue;
+        double4 pj = pos4[en.x];
+        double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+        if (ATX_NONZERO_SHIFT(en.y)) {
+          int sx, sy, sz;
+          atx_unpack_shift(en.y, sx, sy, sz);
+          double ax, ay, az;
+          atx_image_vector(A, sx, sy, sz, ax, ay, az);
+          dx -= ax; dy -= ay; dz -= az;
+        }
+        if (dx * dx + dy * dy + dz * dz < P.r2sq[bop_pair_index(eli, elj, P.nel)]) nb++;
+      }
+  }
+  nb = __reduce_max_sync(0xffffffffu, nb);
+  if ((threadIdx.x & 31) == 0 && nb > 0) atomicMax(&flag[1], nb);
+}
 
 // shared-memory bond table, field-major so that consecutive threads hit consecutive banks
 template <int NB>
@@ -492,6 +528,7 @@ extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop *
   }
   for (int k = 0; k < 32; k++) D.el2db[k] = -1;
   ATX_PASS(pot->flag.reserve(4));
+  ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 4 * sizeof(int)));
   *out = pot;
   return 0;
 }
@@ -550,9 +587,9 @@ template <int KIND>
 static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                             const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
                             int nblocks) {
-  int nebmax = nl->nebmax;
-  if (nebmax <= 6) return launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
-  if (nebmax <= 12) return launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
+  const int cap = pot->nb_cap;
+  if (cap <= 6) return launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
+  if (cap <= 12) return launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
   return launch_center<KIND, 24>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
 }
 
@@ -569,6 +606,28 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
   if (nblocks < 1) nblocks = 1;
   ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
   if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  if (!o.stop && (pot->nb_cap == 0 || pot->sized_nl != nl || pot->sized_build != nl->nbuilds)) {
+    // host-synchronous call (library mode, MD start, after every list rebuild): size the bond table
+    // from the bonds the current configuration really has, + 2 for motion inside the Verlet shell
+    ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 1, 0, sizeof(int), st));
+    if (nat > 0) {
+      k_bop_count_bonds<<<(nat + 127) / 128, 128, 0, st>>>(nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr,
+                                                           nl->list.ptr, pot->flag.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(pot->hflag.reserve(4));
+    ATX_CUDA(cudaMemcpyAsync(pot->hflag.ptr, pot->flag.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    int need = pot->hflag.ptr[1] + 2;
+    if (need > 24) {
+      atx_set_error("Internal neighbor list exhausted, *nebmax* too small: " + std::to_string(need - 2) +
+                    " bonds on one atom (limit 22).");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    pot->nb_cap = need <= 6 ? 6 : (need <= 12 ? 12 : 24);
+    pot->sized_nl = nl;
+    pot->sized_build = nl->nbuilds;
+  }
   if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
   switch (pot->dev.kind) {
     case ATX_BOP_TERSOFF:
@@ -586,6 +645,18 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
     ATX_LAUNCHED();
   }
   ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  return 0;
+}
+
+// overflow of the bond table during guarded (batched MD) steps; called by the MD drivers after a sync
+int atx_bop_check_overflow(atx_bop *pot) {
+  ATX_PASS(pot->hflag.reserve(4));
+  ATX_CUDA(cudaMemcpyAsync(pot->hflag.ptr, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, pot->ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(pot->ctx->stream));
+  if (pot->hflag.ptr[0]) {
+    atx_set_error("Internal neighbor list exhausted, *nebmax* too small (bond table overflow during MD).");
+    return ATX_ERROR_UNSPECIFIED;
+  }
   return 0;
 }
 

@@ -23,6 +23,7 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
 int atx_bop_compute_device(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
                            const int *mask_sorted, const PotOut &o);
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o);
+int atx_bop_check_overflow(atx_bop *pot);
 
 struct MdCtrl {
   int stop;
@@ -365,6 +366,7 @@ extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
     ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
     ATX_CUDA(cudaStreamSynchronize(st));
     ATX_CUDA(cudaGetLastError());
+    if (md->pot_kind == ATX_POT_BOP) ATX_PASS(atx_bop_check_overflow((atx_bop *)md->pot));
     MdCtrl hc = *md->hctrl.ptr;
     int done = hc.steps_done - done_total;
     done_total = hc.steps_done;

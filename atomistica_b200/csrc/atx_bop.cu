@@ -472,6 +472,7 @@ __global__ void k_bop_gather(int nat, const long long *__restrict__ seed, const 
 // ---------------------------------------------------------------------------
 
 extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop **out) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   if (!ctx || !par || !out) return ATX_ERROR_UNSPECIFIED;
   if (par->kind < 1 || par->kind > 3 || par->nel < 1 || par->nel > ATX_BOP_MAX_EL) {
     atx_set_error("atx_bop_create: invalid kind or number of elements.");
@@ -534,12 +535,14 @@ extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop *
 }
 
 extern "C" int atx_bop_destroy(atx_bop *pot) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   delete pot;
   return 0;
 }
 
 extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl, int nel,
                                const int *el2Z) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (nel > 31) {
     atx_set_error("Too many particle element ids.");
     return ATX_ERROR_UNSPECIFIED;
@@ -700,6 +703,7 @@ extern "C" int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_nei
                                          double *epot_per_at, double *epot_per_bond,
                                          double *f_per_bond, double *wpot_per_at,
                                          double *wpot_per_bond) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (!pot->bound) {
     atx_set_error("bind_to has not been called on this potential.");
     return ATX_ERROR_UNSPECIFIED;

@@ -50,6 +50,7 @@ extern "C" int atx_ctx_create(int device, atx_ctx **out) {
 }
 
 extern "C" int atx_ctx_destroy(atx_ctx *c) {
+  if (c) cudaSetDevice(c->device);  // entry points do not assume the caller kept the device current
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -58,6 +59,7 @@ extern "C" int atx_ctx_destroy(atx_ctx *c) {
 }
 
 extern "C" int atx_ctx_synchronize(atx_ctx *c) {
+  if (c) cudaSetDevice(c->device);  // entry points do not assume the caller kept the device current
   ATX_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -67,6 +69,7 @@ extern "C" int atx_ctx_synchronize(atx_ctx *c) {
 // ---------------------------------------------------------------------------
 
 extern "C" int atx_particles_create(atx_ctx *ctx, atx_particles **p) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   if (!ctx || !p) return ATX_ERROR_UNSPECIFIED;
   *p = new atx_particles();
   (*p)->ctx = ctx;
@@ -74,12 +77,14 @@ extern "C" int atx_particles_create(atx_ctx *ctx, atx_particles **p) {
 }
 
 extern "C" int atx_particles_destroy(atx_particles *p) {
+  if (p && p->ctx) cudaSetDevice(p->ctx->device);
   delete p;
   return 0;
 }
 
 extern "C" int atx_particles_set_cell(atx_particles *p, const double *Abox, const double *Bbox,
                                       const int *pbc) {
+  if (p && p->ctx) cudaSetDevice(p->ctx->device);
   for (int i = 0; i < 9; i++) {
     p->Abox.m[i] = Abox[i];
     p->Bbox.m[i] = Bbox[i];
@@ -90,6 +95,7 @@ extern "C" int atx_particles_set_cell(atx_particles *p, const double *Abox, cons
 }
 
 extern "C" int atx_particles_set_positions(atx_particles *p, int nat, const double *r) {
+  if (p && p->ctx) cudaSetDevice(p->ctx->device);
   if (nat < 0) return ATX_ERROR_UNSPECIFIED;
   p->nat = nat;
   p->r_ext = nullptr;
@@ -105,6 +111,7 @@ extern "C" int atx_particles_set_positions(atx_particles *p, int nat, const doub
 }
 
 extern "C" int atx_particles_set_positions_device(atx_particles *p, int nat, const double *r_dev) {
+  if (p && p->ctx) cudaSetDevice(p->ctx->device);
   p->nat = nat;
   p->r_ext = r_dev;
   p->pos_rev++;
@@ -112,6 +119,7 @@ extern "C" int atx_particles_set_positions_device(atx_particles *p, int nat, con
 }
 
 extern "C" int atx_particles_set_elements(atx_particles *p, int nat, const int *el) {
+  if (p && p->ctx) cudaSetDevice(p->ctx->device);
   ATX_PASS(p->el.reserve((size_t)nat + 1));
   if (nat > 0) {
     ATX_CUDA(cudaMemcpyAsync(p->el.ptr, el, sizeof(int) * nat, cudaMemcpyHostToDevice,
@@ -200,6 +208,7 @@ ProfScope::~ProfScope() {
 }
 
 extern "C" int atx_profile_enable(atx_ctx *ctx, int on) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   ctx->prof_on = on != 0;
   if (on)
     for (auto &s : ctx->prof) s.used = 0;
@@ -207,6 +216,7 @@ extern "C" int atx_profile_enable(atx_ctx *ctx, int on) {
 }
 
 extern "C" int atx_profile_read(atx_ctx *ctx, const char *name, double *total_ms, long long *count) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   ATX_CUDA(cudaStreamSynchronize(ctx->stream));
   double tot = 0.0;
   long long n = 0;
@@ -237,6 +247,7 @@ __global__ void k_fp64_peak(double *out, int iters) {
 }
 
 extern "C" int atx_measure_fp64_peak(atx_ctx *ctx, double *tflops) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   DevBuf<double> out;
   ATX_PASS(out.reserve(8));
   cudaEvent_t e0, e1;
@@ -267,6 +278,7 @@ __global__ void k_copy(const double2 *__restrict__ a, double2 *__restrict__ b, s
 }
 
 extern "C" int atx_measure_copy_bandwidth(atx_ctx *ctx, double *gbs) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   const size_t n = (size_t)1 << 26;  // 64 Mi double2 = 1 GiB per buffer
   DevBuf<double2> a, b;
   ATX_PASS(a.reserve(n));

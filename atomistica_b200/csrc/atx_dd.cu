@@ -103,6 +103,7 @@ extern "C" int atx_dd_get_unique_id(char *id128) {
 }
 
 extern "C" int atx_dd_create(atx_ctx *ctx, int rank, int nranks, const char *id128, atx_dd **out) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   ATX_PASS(nccl_load());
   ATX_CUDA(cudaSetDevice(ctx->device));
   atx_dd *dd = new atx_dd();
@@ -117,6 +118,7 @@ extern "C" int atx_dd_create(atx_ctx *ctx, int rank, int nranks, const char *id1
 }
 
 extern "C" int atx_dd_destroy(atx_dd *dd) {
+  if (dd && dd->ctx) cudaSetDevice(dd->ctx->device);
   if (!dd) return 0;
   if (dd->comm) g_nccl.CommDestroy(dd->comm);
   delete dd;
@@ -769,6 +771,7 @@ extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const doubl
                                 const double *Bbox, const int *pbc, double rc, double skin, int avgn,
                                 int nown, const long long *id, const int *el, const double *r,
                                 const double *v, const double *mass, double dt, atx_ddmd **out) {
+  if (dd && dd->ctx) cudaSetDevice(dd->ctx->device);
   if (!dd || !pot || !out) return ATX_ERROR_UNSPECIFIED;
   atx_ctx *ctx = dd->ctx;
   cudaStream_t st = ctx->stream;
@@ -830,10 +833,13 @@ extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const doubl
   double *h = md->stage.ptr;
   // local frame = global - torig
   for (int i = 0; i < nown; i++) {
-    // periodic along a1: bring the atom into the primary image first (the caller assigns owners by
-    // the wrapped fractional coordinate but may pass unwrapped positions)
+    // periodic along a1: take the image nearest to this rank's slab centre.  Callers either assign
+    // owners by the wrapped fractional coordinate and pass unwrapped positions, or generate a slab
+    // and displace atoms slightly across its faces; both end up within one hop of their owner.
     double wrap = 0.0;
-    if (md->pbc[0]) wrap = std::floor(Bbox[0] * r[3 * i] + Bbox[3] * r[3 * i + 1] + Bbox[6] * r[3 * i + 2]);
+    if (md->pbc[0])
+      wrap = std::floor(Bbox[0] * r[3 * i] + Bbox[3] * r[3 * i + 1] + Bbox[6] * r[3 * i + 2] -
+                        0.5 * (md->slo + md->shi) + 0.5);
     for (int c = 0; c < 3; c++) h[3 * i + c] = r[3 * i + c] - wrap * md->a1[c] - md->torig[c];
     h[3 * (size_t)nown + i] = 1.0 / mass[i];
     h[4 * (size_t)nown + i] = (double)id[i];
@@ -873,6 +879,7 @@ extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const doubl
 }
 
 extern "C" int atx_dd_md_destroy(atx_ddmd *md) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   if (!md) return 0;
   if (md->ev0) cudaEventDestroy(md->ev0);
   if (md->ev1) cudaEventDestroy(md->ev1);
@@ -936,6 +943,7 @@ static int dd_enqueue_step(atx_ddmd *md) {
 }
 
 extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *ekin) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   atx_dd *dd = md->dd;
   cudaStream_t st = md->ctx->stream;
   ATX_CUDA(cudaEventRecord(md->ev0, st));
@@ -986,12 +994,14 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
 }
 
 extern "C" int atx_dd_md_get_count(atx_ddmd *md, int *nown, int *nghost) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   if (nown) *nown = md->nown;
   if (nghost) *nghost = md->ngl + md->ngr;
   return 0;
 }
 
 extern "C" int atx_dd_md_get_state(atx_ddmd *md, long long *id, double *r, double *v, double *f) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   cudaStream_t st = md->ctx->stream;
   int n = md->nown;
   ATX_PASS(md->stage.reserve(10 * (size_t)n + 16));
@@ -1015,6 +1025,7 @@ extern "C" int atx_dd_md_get_state(atx_ddmd *md, long long *id, double *r, doubl
 }
 
 extern "C" int atx_dd_md_get_stats(atx_ddmd *md, long long *nrebuilds, double *last_run_ms) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   if (nrebuilds) *nrebuilds = md->nrebuilds;
   if (last_run_ms) *last_run_ms = md->last_ms;
   return 0;

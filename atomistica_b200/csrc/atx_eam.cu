@@ -487,6 +487,7 @@ static int upload_spline(atx_eam *pot, const atx_spline &s, DSpline &d) {
 
 extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const atx_spline *frho,
                               const atx_spline *fphi, double cutoff, atx_eam **out) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   if (ndb < 1 || ndb > EAM_MAX_DB) {
     atx_set_error("TabulatedAlloyEAM supports 1.." + std::to_string(EAM_MAX_DB) + " elements.");
     return ATX_ERROR_UNSPECIFIED;
@@ -545,12 +546,14 @@ extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const
 }
 
 extern "C" int atx_eam_destroy(atx_eam *pot) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   delete pot;
   return 0;
 }
 
 extern "C" int atx_eam_bind_to(atx_eam *pot, atx_particles *p, atx_neighbors *nl, int nel,
                                const int *el2db) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (nel > 31) {
     atx_set_error("Too many particle element ids.");
     return ATX_ERROR_UNSPECIFIED;
@@ -667,6 +670,7 @@ int atx_eam_check_flag(atx_eam *pot) {
 extern "C" int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
                                          const int *mask, double *epot, double *f, double *wpot,
                                          double *epot_per_at, double *wpot_per_at) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (!pot->bound) {
     atx_set_error("TabulatedAlloyEAM: bind_to has not been called.");
     return ATX_ERROR_UNSPECIFIED;

@@ -241,6 +241,7 @@ static int md_rebuild(atx_md *md, bool first) {
 extern "C" int atx_md_create(atx_ctx *ctx, int pot_kind, void *pot, atx_particles *p,
                              atx_neighbors *nl, const double *mass, const double *v, double dt,
                              atx_md **out) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   if (!ctx || !pot || !p || !nl || !mass || !out) return ATX_ERROR_UNSPECIFIED;
   int nat = p->nat;
   if (nat <= 0) {
@@ -317,6 +318,7 @@ extern "C" int atx_md_create(atx_ctx *ctx, int pot_kind, void *pot, atx_particle
 }
 
 extern "C" int atx_md_destroy(atx_md *md) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   if (!md) return 0;
   if (md->ev0) cudaEventDestroy(md->ev0);
   if (md->ev1) cudaEventDestroy(md->ev1);
@@ -338,6 +340,7 @@ static int md_reset_ctrl_after_rebuild(atx_md *md) {
 }
 
 extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   atx_ctx *ctx = md->ctx;
   cudaStream_t st = ctx->stream;
   int nat = md->nat, gb = (nat + 255) / 256;
@@ -396,6 +399,7 @@ extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
 }
 
 extern "C" int atx_md_get_state(atx_md *md, double *r, double *v, double *f) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   atx_ctx *ctx = md->ctx;
   int nat = md->nat;
   ATX_PASS(md->tmp3.reserve(9 * (size_t)nat + 9));
@@ -415,6 +419,7 @@ extern "C" int atx_md_get_state(atx_md *md, double *r, double *v, double *f) {
 }
 
 extern "C" int atx_md_get_stats(atx_md *md, long long *nrebuilds, double *last_run_ms) {
+  if (md && md->ctx) cudaSetDevice(md->ctx->device);
   if (nrebuilds) *nrebuilds = md->nrebuilds;
   if (last_run_ms) *last_run_ms = md->last_ms;
   return 0;

@@ -318,6 +318,7 @@ __global__ void k_host_fill(int nat, const int *__restrict__ inv, const int *__r
 // ---------------------------------------------------------------------------
 
 extern "C" int atx_neighbors_create(atx_ctx *ctx, int avgn, atx_neighbors **nl) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   if (!ctx || !nl) return ATX_ERROR_UNSPECIFIED;
   *nl = new atx_neighbors();
   (*nl)->ctx = ctx;
@@ -326,11 +327,13 @@ extern "C" int atx_neighbors_create(atx_ctx *ctx, int avgn, atx_neighbors **nl) 
 }
 
 extern "C" int atx_neighbors_destroy(atx_neighbors *nl) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   delete nl;
   return 0;
 }
 
 extern "C" int atx_neighbors_request_interaction_range(atx_neighbors *nl, double cutoff) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   // python_neighbors.f90:381-423: any request tears the list down
   if (cutoff > nl->interaction_range) nl->interaction_range = cutoff;
   nl->initialized = false;
@@ -338,6 +341,7 @@ extern "C" int atx_neighbors_request_interaction_range(atx_neighbors *nl, double
 }
 
 extern "C" int atx_neighbors_set_verlet_shell(atx_neighbors *nl, double verlet_shell) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   nl->verlet_shell = verlet_shell;
   nl->initialized = false;
   return 0;
@@ -357,6 +361,7 @@ static Geo make_geo(const atx_neighbors *nl, const atx_particles *p) {
 }
 
 extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   atx_ctx *ctx = nl->ctx;
   cudaStream_t st = ctx->stream;
   if (nl->bound != p || nl->nat != p->nat) nl->initialized = false;
@@ -476,6 +481,7 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
 }
 
 extern "C" int atx_neighbors_rebuild(atx_neighbors *nl, atx_particles *p) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   nl->p_rev = -1;
   return atx_neighbors_update(nl, p);
 }
@@ -505,6 +511,7 @@ int atx_neighbors_ensure_rev(atx_neighbors *nl) {
 
 extern "C" int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax,
                                       int *n_cells, int *stencil) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   if (npairs) *npairs = nl->npairs;
   if (nebmax) *nebmax = nl->nebmax;
   for (int k = 0; k < 3; k++) {
@@ -533,6 +540,7 @@ int atx_neighbors_host_seed(atx_neighbors *nl, DevBuf<long long> &hseed) {
 
 extern "C" int atx_neighbors_copy_to_host(atx_neighbors *nl, intptr_t *seed, intptr_t *last,
                                           int *neighbors, int *dc, long long capacity) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   static_assert(sizeof(intptr_t) == sizeof(long long), "NEIGHPTR_T must be 64 bit");
   if (!nl->initialized) {
     atx_set_error("Neighbor list not built.");

@@ -720,6 +720,7 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
 // ---------------------------------------------------------------------------
 
 extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_rebo2 **out) {
+  if (ctx) cudaSetDevice(ctx->device);  // entry points do not assume the caller kept the device current
   if (!ctx || !par || !out) return ATX_ERROR_UNSPECIFIED;
   atx_rebo2 *pot = new atx_rebo2();
   pot->ctx = ctx;
@@ -771,12 +772,14 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
 }
 
 extern "C" int atx_rebo2_destroy(atx_rebo2 *pot) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   delete pot;
   return 0;
 }
 
 extern "C" int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, int nel,
                                  const int *el2Z) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (nel > 31) {
     atx_set_error("Too many particle element ids.");
     return ATX_ERROR_UNSPECIFIED;
@@ -856,6 +859,7 @@ extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx
                                            double *epot_per_at, double *epot_per_bond,
                                            double *f_per_bond, double *wpot_per_at,
                                            double *wpot_per_bond) {
+  if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (!pot->bound) {
     atx_set_error("bind_to has not been called on this potential.");
     return ATX_ERROR_UNSPECIFIED;

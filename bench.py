@@ -172,6 +172,9 @@ def config_dict(ngpu):
 
 def run_ours(args):
     import ctypes as C
+    if os.environ.get('ATX_BENCH_WATCHDOG'):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ['ATX_BENCH_WATCHDOG']), exit=True)
     from atomistica_b200 import _lib as L, md, native
 
     rank = int(os.environ.get('RANK', '0'))

@@ -18,17 +18,25 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def slab_atoms(a0, n, rank, world, seed=12345):
-    """diamond Si cells [x0, x1) x n x n of the n^3 supercell, rattled (sigma 0.05 A), global ids"""
+def slab_atoms(a0, n, rank, world, seed=12345, T=300.0, mass=28.0855):
+    """diamond Si cells [x0, x1) x n x n of the n^3 supercell, rattled (sigma 0.05 A), global ids and
+    Maxwell-Boltzmann velocities.  Random numbers are drawn per x-plane of cells, so the global system
+    is the same for every number of ranks and the energies can be compared across N."""
     from atomistica_b200 import structures as S
     x0 = (n * rank) // world
     x1 = (n * (rank + 1)) // world
-    a = S.diamond('Si', a0, (x1 - x0, n, n))
-    pos = a.positions + np.array([x0 * a0, 0.0, 0.0]) + 1e-3
-    rng = np.random.RandomState(seed + rank)
-    pos += rng.normal(scale=0.05, size=pos.shape)
+    plane = S.diamond('Si', a0, (1, n, n)).positions
+    from atomistica_b200.md import ACCEL_CONV
+    kT = 8.617333262e-5 * T * ACCEL_CONV      # velocities in Angstrom/fs
+    pos, vel = [], []
+    for ix in range(x0, x1):
+        rng = np.random.RandomState(seed + ix)
+        pos.append(plane + np.array([ix * a0, 0.0, 0.0]) + 1e-3 + rng.normal(scale=0.05, size=plane.shape))
+        vel.append(rng.normal(size=plane.shape) * np.sqrt(kT / mass))
+    pos = np.concatenate(pos)
+    vel = np.concatenate(vel)
     ids = np.arange(len(pos), dtype=np.int64) + 8 * n * n * x0
-    return pos, ids
+    return pos, vel, ids
 
 
 def main():
@@ -37,6 +45,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--kind', default='Tersoff,Kumagai')
     ap.add_argument('--skin', type=float, default=0.4)
+    ap.add_argument('--warmup', type=int, default=20)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -51,10 +60,9 @@ def main():
     n = args.cells
     for kind in args.kind.split(','):
         a0, rc = (5.432, 3.0) if kind == 'Tersoff' else (5.429, 3.3)
-        pos, ids = slab_atoms(a0, n, rank, world)
+        pos, v0, ids = slab_atoms(a0, n, rank, world)
         nat = len(pos)
         m = np.full(nat, 28.0855)
-        v0 = md.maxwell_boltzmann(m, 300.0, seed=777 + rank)
         pot = getattr(native, kind)(device=local)
         cell = np.diag([n * a0] * 3)
         if world == 1:
@@ -69,7 +77,7 @@ def main():
             drv = parallel.DDVelocityVerlet(dd, pot, None, [14], cell, True, ids, np.ones(nat, dtype=np.int32), pos, v0,
                                             m, rc, args.skin, dt=1.0, avgn=20)
             counts = drv.counts()
-        drv.run(5)
+        drv.run(args.warmup)      # long enough to contain a list rebuild + migration (NCCL connects lazily)
         if dist is not None:
             dist.barrier()
         L.check(L.lib().atx_profile_enable(ctx, 1))

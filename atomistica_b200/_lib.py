@@ -52,7 +52,7 @@ SYMBOLS = [
     'atx_particles_create', 'atx_particles_destroy', 'atx_particles_set_cell', 'atx_particles_set_positions',
     'atx_particles_set_elements', 'atx_particles_set_positions_device',
     'atx_neighbors_create', 'atx_neighbors_destroy', 'atx_neighbors_request_interaction_range',
-    'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_rebuild', 'atx_neighbors_get_info',
+    'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_rebuild', 'atx_neighbors_get_info', 'atx_neighbors_get_counters',
     'atx_neighbors_copy_to_host',
     'atx_eam_create', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
     'atx_bop_create', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',

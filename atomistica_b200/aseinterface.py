@@ -18,8 +18,12 @@ class Atomistica:
     potential_class = None
     avgn = 100
 
-    def __init__(self, potentials=None, avgn=None, device=0, **kwargs):
+    def __init__(self, potentials=None, avgn=None, device=0, verlet_shell=0.0, **kwargs):
+        """verlet_shell > 0 (Angstrom) keeps the neighbour list between calls until an atom has moved
+        verlet_shell/2 from where it was at the last build (checked on the device); 0 rebuilds on every
+        change of the positions like the reference's Python host."""
         self.device = device
+        self.verlet_shell = float(verlet_shell)
         self.pots = potentials if potentials is not None else [self.potential_class(device=device, **kwargs)]
         if avgn is not None:
             self.avgn = avgn
@@ -50,6 +54,8 @@ class Atomistica:
         self.particles.I_changed_positions()
         self.particles.update_elements()
         self.nl = native.Neighbors(self.avgn, self.device)
+        if self.verlet_shell > 0.0:
+            self.nl.set(verlet_shell=self.verlet_shell)
         for pot in self.pots:
             pot.bind_to(self.particles, self.nl)
 

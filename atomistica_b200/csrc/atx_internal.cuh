@@ -163,6 +163,8 @@ struct atx_neighbors {
   long long npairs = 0;
   int nebmax = 0;
   long long nbuilds = 0;
+  long long nreused = 0;    // updates answered by the Verlet-shell check without a rebuild
+  long long el_rev = -1;
 
   DevBuf<int4> cellshift;   // per original atom: cell id, wrap shift
   DevBuf<int> cell_count;   // ncell+1
@@ -171,6 +173,7 @@ struct atx_neighbors {
   DevBuf<int> order;        // sorted slot -> original atom
   DevBuf<int> inv;          // original atom -> sorted slot
   DevBuf<double4> pos4;     // sorted: x,y,z, (w = element id as double bits)
+  DevBuf<double4> pos_build;  // pos4 at the last build (library-mode Verlet shell only)
   DevBuf<int4> sshift;      // sorted: cell id + wrap shift
   DevBuf<int> count;        // nat+1 neighbour counts (sorted order)
   DevBuf<long long> seed;   // nat+1 exclusive offsets (sorted order), 0-based

@@ -258,6 +258,29 @@ __global__ void k_refresh_pos(int nat, const double *__restrict__ r, const int *
   pos4[s] = v;
 }
 
+// library-mode Verlet shell: refresh the sorted positions and record the largest squared displacement
+// since the list was built (bit pattern of a non-negative double orders like an unsigned integer)
+__global__ void k_refresh_check(int nat, const double *__restrict__ r, const int *__restrict__ order,
+                                const double4 *__restrict__ pos_build, double4 *__restrict__ pos4,
+                                unsigned long long *__restrict__ max_d2) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (s < nat) {
+    int i = order[s];
+    double4 v = pos4[s], b = pos_build[s];
+    v.x = r[3 * i];
+    v.y = r[3 * i + 1];
+    v.z = r[3 * i + 2];
+    pos4[s] = v;
+    double dx = v.x - b.x, dy = v.y - b.y, dz = v.z - b.z;
+    d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 == d2)) d2 = 1e300;  // NaN positions force a rebuild (which reports them)
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+  if ((threadIdx.x & 31) == 0 && d2 > 0.0) atomicMax(max_d2, (unsigned long long)__double_as_longlong(d2));
+}
+
 // reverse slot: for entry a = (i -> j, shift) the entry b = (j -> i, -shift)
 __global__ void k_reverse_index(int nat, const long long *__restrict__ seed,
                                 const int2 *__restrict__ list, int *__restrict__ rev) {
@@ -368,6 +391,28 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nl->initialized && nl->p_rev == p->pos_rev && nl->cell_rev == p->cell_rev) return 0;
 
   const int nat = p->nat;
+  if (nl->initialized && nl->verlet_shell > 0.0 && nl->cell_rev == p->cell_rev && nl->p_rev >= 0 &&
+      nl->el_rev == p->el_rev && nl->pos_build.cap >= (size_t)nat && nat > 0) {
+    // Verlet shell (neighbors.f90:520-560 / python_neighbors.f90:570-600: the list is kept while
+    // no atom moved further than verlet_shell/2).  The reference accumulates per-step maxima; here
+    // the displacement since the build is measured directly, which is the exact form of that rule.
+    ProfScope ps_(ctx, "nl_refresh_check");
+    ATX_PASS(nl->scal.reserve(8));
+    ATX_CUDA(cudaMemsetAsync(nl->scal.ptr + 4, 0, sizeof(long long), st));
+    k_refresh_check<<<(nat + 255) / 256, 256, 0, st>>>(nat, p->rptr(), nl->order.ptr, nl->pos_build.ptr,
+                                                       nl->pos4.ptr, (unsigned long long *)(nl->scal.ptr + 4));
+    ATX_LAUNCHED();
+    long long bits = 0;
+    ATX_CUDA(cudaMemcpyAsync(&bits, nl->scal.ptr + 4, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    double d2;
+    memcpy(&d2, &bits, sizeof(double));
+    if (d2 < 0.25 * nl->verlet_shell * nl->verlet_shell) {
+      nl->p_rev = p->pos_rev;
+      nl->nreused++;
+      return 0;
+    }
+  }
   if (!nl->initialized) {
     nl->cutoff = nl->interaction_range + nl->verlet_shell;
     if (nl->cutoff <= 0.0) {
@@ -474,8 +519,13 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     }
   }
   ATX_CUDA(cudaGetLastError());
+  if (nl->verlet_shell > 0.0 && nat > 0) {
+    ATX_PASS(nl->pos_build.reserve(nat + 1));
+    ATX_CUDA(cudaMemcpyAsync(nl->pos_build.ptr, nl->pos4.ptr, sizeof(double4) * nat, cudaMemcpyDeviceToDevice, st));
+  }
   nl->p_rev = p->pos_rev;
   nl->cell_rev = p->cell_rev;
+  nl->el_rev = p->el_rev;
   nl->nbuilds++;
   return 0;
 }
@@ -518,6 +568,13 @@ extern "C" int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int 
     if (n_cells) n_cells[k] = nl->n_cells[k];
     if (stencil) stencil[k] = nl->sten[k];
   }
+  return 0;
+}
+
+extern "C" int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long *nreused) {
+  if (!nl) return ATX_ERROR_UNSPECIFIED;
+  if (nbuilds) *nbuilds = nl->nbuilds;
+  if (nreused) *nreused = nl->nreused;
   return 0;
 }
 

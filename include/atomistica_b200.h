@@ -84,6 +84,8 @@ int atx_neighbors_rebuild(atx_neighbors *nl, atx_particles *p);
 /* number of pairs, max neighbours per atom, n_cells(3), stencil half widths(3) */
 int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax, int *n_cells,
                            int *stencil);
+/* number of list builds and of updates answered without a rebuild (Verlet shell, neighbors.f90:552-590) */
+int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long *nreused);
 /* host view of the list in the reference's layout and order (seed(nat+1), last(nat+1),
  * neighbors(capacity), dc(3,capacity)); used by f_get_all_neighbors & co
  * (src/python/f90/neighbors_wrap.f90:211-550) */

@@ -187,6 +187,11 @@ def spline_eval(s, x, extrapolate=False):
 # tabulated alloy EAM (tabulated_alloy_eam.f90:147-259 init; kernel in C)
 # ----------------------------------------------------------------------------
 
+def set_threads(n):
+    """OpenMP threads of the EAM kernel (bench.py's CPU legs); 1 = the serial order the KATs pin"""
+    lib().orc_eam_set_threads(int(n))
+
+
 class EAM:
     def __init__(self, setfl):
         nel = len(setfl['names'])

@@ -51,6 +51,8 @@ typedef struct {
 
 /* ---- tabulated alloy EAM: src/potentials/eam/tabulated_alloy_eam.f90:423-627 ---- */
 
+/* OpenMP threads of the EAM kernel (default 1 = serial summation order) */
+void orc_eam_set_threads(int n);
 int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double *Abox,
                               const int *eldb, const intptr_t *seed, const intptr_t *last,
                               const int *neighbors, const int *dc, int ndb, const orc_spline_t *fF,

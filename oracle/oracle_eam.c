@@ -60,6 +60,13 @@ static void spl_f_and_df_extrap(const orc_spline_t *s, double x, double *f, doub
   *df = s->d1[i] + B * (s->d2[i] + B * s->d3[i]);
 }
 
+static int orc_eam_threads = 1;
+
+/* number of OpenMP threads of the EAM kernel (the reference runs it under "!$omp parallel",
+ * tabulated_alloy_eam.f90:473-486, with thread-local energy/force arrays tls_sca1/tls_vec1).
+ * 1 (default) keeps the summation order of the serial reference build used for the KATs. */
+void orc_eam_set_threads(int n) { orc_eam_threads = n > 0 ? n : 1; }
+
 int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double *Abox,
                               const int *eldb, const intptr_t *seed, const intptr_t *last,
                               const int *neighbors, const int *dc, int ndb, const orc_spline_t *fF,
@@ -73,80 +80,109 @@ int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double
     int d = (int)(last[i] - seed[i] + 1);
     if (d > maxneb) maxneb = d;
   }
-  int *neb = (int *)malloc(sizeof(int) * (maxneb + 1));
-  double *neb_dr = (double *)malloc(sizeof(double) * 3 * (maxneb + 1));
-  double *neb_abs = (double *)malloc(sizeof(double) * (maxneb + 1));
-  double *pe = (double *)calloc(nat > 0 ? nat : 1, sizeof(double));      /* tls_sca1 */
-  double *fv = (double *)calloc(nat > 0 ? 3 * nat : 1, sizeof(double));  /* tls_vec1 */
+  double *pe = (double *)calloc(nat > 0 ? nat : 1, sizeof(double));      /* tls_sca1 (summed) */
+  double *fv = (double *)calloc(nat > 0 ? 3 * nat : 1, sizeof(double));  /* tls_vec1 (summed) */
   int err = 0;
+  const int nthreads = orc_eam_threads;
 
-  for (int i = 0; i < natloc && !err; i++) {
-    if (mask && mask[i] == 0) continue;
-    int dbi = eldb[i];
-    if (dbi <= 0) continue;
-    double rho = 0.0;
-    int neb_n = 0;
-    for (intptr_t ni = seed[i]; ni <= last[i]; ni++) {
-      int j = neighbors[ni - 1] - 1;
-      int dbj = eldb[j];
-      if (dbj <= 0) continue;
-      double dr[3];
-      for (int k = 0; k < 3; k++) {
-        double s = 0.0;
-        for (int c = 0; c < 3; c++) s += M3(Abox, k, c) * (double)dc[3 * (ni - 1) + c];
-        dr[k] = r[3 * i + k] - r[3 * j + k] + s;
-      }
-      double abs_dr = 0.0;
-      for (int k = 0; k < 3; k++) abs_dr += dr[k] * dr[k];
-      if (abs_dr < cutoff_sq) {
-        abs_dr = sqrt(abs_dr);
-        double drho;
-        if (spl_func(&frho[dbj - 1], abs_dr, &drho)) { err = 1; break; }
-        rho += drho;
-        neb[neb_n] = j;
-        neb_dr[3 * neb_n + 0] = dr[0];
-        neb_dr[3 * neb_n + 1] = dr[1];
-        neb_dr[3 * neb_n + 2] = dr[2];
-        neb_abs[neb_n] = abs_dr;
-        neb_n++;
-      }
-    }
-    if (err) break;
-    if (rho < 0.0) rho = 0.0;
-    double Fi, dFi;
-    spl_f_and_df_extrap(&fF[dbi - 1], rho, &Fi, &dFi);
-    pe[i] += Fi;
+#pragma omp parallel num_threads(nthreads) if (nthreads > 1)
+  {
+    int *neb = (int *)malloc(sizeof(int) * (maxneb + 1));
+    double *neb_dr = (double *)malloc(sizeof(double) * 3 * (maxneb + 1));
+    double *neb_abs = (double *)malloc(sizeof(double) * (maxneb + 1));
+    /* thread-local force array; the serial path writes into fv directly */
+    double *fl = nthreads > 1 ? (double *)calloc(nat > 0 ? 3 * nat : 1, sizeof(double)) : fv;
+    double wl[9] = {0};
+    int errl = 0;
 
-    double fori[3] = {0, 0, 0};
-    for (int ni = 0; ni < neb_n; ni++) {
-      int j = neb[ni];
-      int dbj = eldb[j];
-      const double *dr = &neb_dr[3 * ni];
-      double abs_dr = neb_abs[ni];
-      double phi, dphi, fac;
-      spl_f_and_df_extrap(&fphi[(dbi - 1) + ndb * (dbj - 1)], abs_dr, &phi, &dphi);
-      double r_abs_dr = 1.0 / abs_dr;
-      pe[i] += phi * r_abs_dr;
-      if (spl_dfunc(&frho[dbj - 1], abs_dr, &fac)) { err = 1; break; }
-      double pref = -(dFi * fac + (dphi - phi * r_abs_dr) * r_abs_dr) * r_abs_dr;
-      double df[3] = {pref * dr[0], pref * dr[1], pref * dr[2]};
-      double wij[9];
-      for (int k = 0; k < 3; k++) {
-        fori[k] += df[k];
-        fv[3 * j + k] -= df[k];
+#pragma omp for schedule(static)
+    for (int i = 0; i < natloc; i++) {
+      if (errl) continue;
+      if (mask && mask[i] == 0) continue;
+      int dbi = eldb[i];
+      if (dbi <= 0) continue;
+      double rho = 0.0;
+      int neb_n = 0;
+      for (intptr_t ni = seed[i]; ni <= last[i]; ni++) {
+        int j = neighbors[ni - 1] - 1;
+        int dbj = eldb[j];
+        if (dbj <= 0) continue;
+        double dr[3];
+        for (int k = 0; k < 3; k++) {
+          double s = 0.0;
+          for (int c = 0; c < 3; c++) s += M3(Abox, k, c) * (double)dc[3 * (ni - 1) + c];
+          dr[k] = r[3 * i + k] - r[3 * j + k] + s;
+        }
+        double abs_dr = 0.0;
+        for (int k = 0; k < 3; k++) abs_dr += dr[k] * dr[k];
+        if (abs_dr < cutoff_sq) {
+          abs_dr = sqrt(abs_dr);
+          double drho;
+          if (spl_func(&frho[dbj - 1], abs_dr, &drho)) { errl = 1; break; }
+          rho += drho;
+          neb[neb_n] = j;
+          neb_dr[3 * neb_n + 0] = dr[0];
+          neb_dr[3 * neb_n + 1] = dr[1];
+          neb_dr[3 * neb_n + 2] = dr[2];
+          neb_abs[neb_n] = abs_dr;
+          neb_n++;
+        }
       }
-      for (int b = 0; b < 3; b++)
-        for (int a = 0; a < 3; a++) {
-          M3(wij, a, b) = -(dr[a] * df[b]);
-          M3(w, a, b) += M3(wij, a, b);
+      if (errl) continue;
+      if (rho < 0.0) rho = 0.0;
+      double Fi, dFi;
+      spl_f_and_df_extrap(&fF[dbi - 1], rho, &Fi, &dFi);
+      double pei = Fi;   /* pe(i) only ever receives contributions from its own centre */
+
+      double fori[3] = {0, 0, 0};
+      for (int ni = 0; ni < neb_n; ni++) {
+        int j = neb[ni];
+        int dbj = eldb[j];
+        const double *dr = &neb_dr[3 * ni];
+        double abs_dr = neb_abs[ni];
+        double phi, dphi, fac;
+        spl_f_and_df_extrap(&fphi[(dbi - 1) + ndb * (dbj - 1)], abs_dr, &phi, &dphi);
+        double r_abs_dr = 1.0 / abs_dr;
+        pei += phi * r_abs_dr;
+        if (spl_dfunc(&frho[dbj - 1], abs_dr, &fac)) { errl = 1; break; }
+        double pref = -(dFi * fac + (dphi - phi * r_abs_dr) * r_abs_dr) * r_abs_dr;
+        double df[3] = {pref * dr[0], pref * dr[1], pref * dr[2]};
+        double wij[9];
+        for (int k = 0; k < 3; k++) {
+          fori[k] += df[k];
+          fl[3 * j + k] -= df[k];
         }
-      if (wpot_per_at)
-        for (int k = 0; k < 9; k++) {
-          wpot_per_at[9 * i + k] += wij[k] / 2;
-          wpot_per_at[9 * j + k] += wij[k] / 2;
-        }
+        for (int b = 0; b < 3; b++)
+          for (int a = 0; a < 3; a++) {
+            M3(wij, a, b) = -(dr[a] * df[b]);
+            M3(wl, a, b) += M3(wij, a, b);
+          }
+        if (wpot_per_at)
+          for (int k = 0; k < 9; k++) {
+            if (nthreads > 1) {
+#pragma omp atomic
+              wpot_per_at[9 * i + k] += wij[k] / 2;
+#pragma omp atomic
+              wpot_per_at[9 * j + k] += wij[k] / 2;
+            } else {
+              wpot_per_at[9 * i + k] += wij[k] / 2;
+              wpot_per_at[9 * j + k] += wij[k] / 2;
+            }
+          }
+      }
+      pe[i] += pei;
+      for (int k = 0; k < 3; k++) fl[3 * i + k] += fori[k];
     }
-    for (int k = 0; k < 3; k++) fv[3 * i + k] += fori[k];
+
+#pragma omp critical
+    {
+      if (errl) err = 1;
+      for (int k = 0; k < 9; k++) w[k] += wl[k];
+      if (nthreads > 1)
+        for (int i = 0; i < 3 * nat; i++) fv[i] += fl[i];
+    }
+    free(neb); free(neb_dr); free(neb_abs);
+    if (nthreads > 1) free(fl);
   }
 
   if (!err) {
@@ -158,6 +194,6 @@ int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double
     *epot += e;
     for (int k = 0; k < 9; k++) wpot[k] += w[k];
   }
-  free(neb); free(neb_dr); free(neb_abs); free(pe); free(fv);
+  free(pe); free(fv);
   return err ? -1 : 0;
 }

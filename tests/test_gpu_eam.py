@@ -114,3 +114,27 @@ def test_calculator_interface(cu_setfl):
     a.positions[0, 0] += 0.1
     e2 = a.get_potential_energy()
     assert e2 > e1
+
+
+def test_calculator_verlet_shell_reuses_list(cu_setfl):
+    """library-mode Verlet shell: forces stay within tolerance of the oracle while the list is reused,
+    and the list is rebuilt once an atom has moved verlet_shell/2"""
+    from atomistica_b200 import TabulatedAlloyEAM
+    a = S.fcc('Cu', 3.615, (6, 6, 6))
+    a.rattle(0.05, seed=11)
+    calc = TabulatedAlloyEAM(setfl=cu_setfl, verlet_shell=0.5)
+    eam = oracle.EAM(cu_setfl)
+    rng = np.random.RandomState(3)
+    for it in range(6):
+        f = calc.get_forces(a)
+        e = calc.results['energy']
+        onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, eam.cutoff, 200)
+        o = eam.energy_and_forces(a.positions, a.cell, onl, eam.eldb(a.symbols))
+        assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
+        assert _close(f, o['f'], max(np.abs(o['f']).max(), 1.0))
+        a.positions = a.positions + rng.uniform(-0.04, 0.04, size=a.positions.shape)
+    builds, reused = calc.nl.counters()
+    assert builds >= 1 and reused >= 2 and builds + reused == 6
+    a.positions[7] += 0.3                       # beyond verlet_shell/2: must rebuild
+    calc.get_forces(a)
+    assert calc.nl.counters()[0] == builds + 1

@@ -7,12 +7,12 @@ from atomistica_b200 import TabulatedAlloyEAM, _lib as L
 import ctypes as C
 setfl = bench.load_setfl()
 a, m, v0 = bench.build_system()
-calc = TabulatedAlloyEAM(setfl=setfl)
+calc = TabulatedAlloyEAM(setfl=setfl, verlet_shell=0.5)
 a.calc = calc
 calc.get_forces(a)
 rng = np.random.RandomState(0)
 def step():
-    a.positions += rng.normal(scale=1e-4, size=a.positions.shape)
+    a.positions += rng.normal(scale=1e-3, size=a.positions.shape)
     calc.calculate(a)
 for _ in range(3): step()
 t0 = time.perf_counter()

@@ -44,7 +44,8 @@ struct atx_bop {
   bool bound = false;
   DevBuf<double4> G;
   DevBuf<double> epb, fpb, wpb, epa_out;
-  DevBuf<int> flag;   // [0] overflow of the per-thread bond table, [1] max bonds per atom seen
+  DevBuf<int> flag;   // [0] an atom exceeded BOP_NB_MAX bonds, [1] length of the queue, [8..40) bond histogram
+  DevBuf<int> queue;  // atoms deferred to the queued pass
   PinBuf<int> hflag;
   int nb_cap = 0;     // bond-table capacity (template NB) in use
   const atx_neighbors *sized_nl = nullptr;  // list + build number nb_cap was sized for
@@ -195,16 +196,20 @@ __device__ __forceinline__ void bop_h(const BopDev &P, int ik, double dr, double
 }
 
 #define BOP_BLOCK 64
+#define BOP_NB_MAX 24   // deepest bond table (queued pass); more bonds on one atom is an error
 
-// bonds (list entries inside the potential's r2) per atom -> flag[1] = maximum.  Sizes the
-// shared-memory bond table by BONDS, not by list entries: with a Verlet shell the list of an atom
-// can hold several times more entries than it has bonds.
+// Histogram of bonds (list entries inside the potential's r2) per atom -> hist[0..31] (last bin =
+// 31 or more).  Sizes the shared-memory bond table by BONDS, not by list entries: with a Verlet
+// shell the list of an atom can hold several times more entries than it has bonds.
 __global__ void k_bop_count_bonds(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
                                   const long long *__restrict__ seed, const int2 *__restrict__ list,
-                                  int *__restrict__ flag) {
+                                  const unsigned char *__restrict__ role, int *__restrict__ hist) {
+  __shared__ int sh[32];
+  if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+  __syncthreads();
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  int nb = 0;
-  if (s < nat) {
+  if (s < nat && (!role || role[s] >= 1)) {
+    int nb = 0;
     double4 pi = pos4[s];
     const int eli = P.el2db[(int)pi.w];
     if (eli > 0)
@@ -223,9 +228,10 @@ __global__ void k_bop_count_bonds(int nat, Mat3 A, BopDev P, const double4 *__re
         }
         if (dx * dx + dy * dy + dz * dz < P.r2sq[bop_pair_index(eli, elj, P.nel)]) nb++;
       }
+    atomicAdd(&sh[nb < 31 ? nb : 31], 1);
   }
-  nb = __reduce_max_sync(0xffffffffu, nb);
-  if ((threadIdx.x & 31) == 0 && nb > 0) atomicMax(&flag[1], nb);
+  __syncthreads();
+  if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 // shared-memory bond table, field-major so that consecutive threads hit consecutive banks
@@ -240,15 +246,211 @@ struct BondSmem {
   double red[ATX_NSUM * (BOP_BLOCK / 32)];
 };
 
+// One centre atom: bond table in shared memory, then all bonds ij with their k-sums.  Returns false
+// (having written nothing but zeroed G slots) when the atom has more than NB bonds.
 template <int KIND, int NB>
-__global__ void __launch_bounds__(BOP_BLOCK)
+__device__ __forceinline__ bool bop_center_atom(
+    BondSmem<NB> &S, const int t, const int s, const Mat3 &A, const BopDev &P,
+    const double4 *__restrict__ pos4, const long long *__restrict__ seed, const int2 *__restrict__ list,
+    const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
+    double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
+    double *__restrict__ fpb, double *__restrict__ wpb, double (&acc)[ATX_NSUM]) {
+  double4 pi = pos4[s];
+  const int eli = P.el2db[(int)pi.w];
+  const long long b0 = seed[s], b1 = seed[s + 1];
+  int nb = 0;
+  bool ovf = false;
+  // ---- loop 1: bond table (bop_kernel.f90:563-1068) ----
+  for (long long a = b0; a < b1; a++) {
+    int2 en = list[a];
+    bool bond = false;
+    if (eli > 0) {
+      double4 pj = pos4[en.x];
+      int elj = P.el2db[(int)pj.w];
+      if (elj > 0) {
+        double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
+        if (ATX_NONZERO_SHIFT(en.y)) {
+          int sx, sy, sz;
+          atx_unpack_shift(en.y, sx, sy, sz);
+          double ax, ay, az;
+          atx_image_vector(A, sx, sy, sz, ax, ay, az);
+          dx -= ax; dy -= ay; dz -= az;
+        }
+        double r2 = dx * dx + dy * dy + dz * dz;
+        int ij = bop_pair_index(eli, elj, P.nel);
+        if (r2 < P.r2sq[ij]) {
+          if (nb >= NB) {
+            ovf = true;
+          } else {
+            double rl = sqrt(r2);
+            double fc = 1.0, dfc = 0.0;
+            if (!(r2 < P.r1sq[ij])) {
+              // trig_off_f
+              if (rl <= P.r1[ij]) { fc = 1.0; dfc = 0.0; }
+              else if (rl >= P.r2[ij]) { fc = 0.0; dfc = 0.0; }
+              else {
+                double sn, cs;
+                sincos(P.cfac[ij] * (rl - P.r1[ij]), &sn, &cs);
+                fc = 0.5 * (1.0 + cs);
+                dfc = -0.5 * P.cfac[ij] * sn;
+              }
+            }
+            const double ri = 1.0 / rl;
+            S.rnx[nb][t] = dx * ri; S.rny[nb][t] = dy * ri; S.rnz[nb][t] = dz * ri;
+            S.rl[nb][t] = rl; S.ri[nb][t] = ri; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
+            S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0; S.ge[nb][t] = 0.0;
+            S.slot[nb][t] = (int)(a - b0);
+            S.typ[nb][t] = ij | (en.x << 3);
+            nb++;
+            bond = true;
+          }
+        }
+      }
+    }
+    if (!bond) G[a] = make_double4(0.0, 0.0, 0.0, 0.0);
+  }
+
+  if (ovf) return false;  // more bonds than this instantiation holds: the caller defers the atom
+
+  // ---- loop 2 (bop_kernel.f90:1075-1529) ----
+  double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
+  const int mi = mask ? mask[s] : 1;
+  for (int ij = 0; ij < nb; ij++) {
+    const int tij = S.typ[ij][t] & 7;
+    const int j = S.typ[ij][t] >> 3;
+    int maskfac = 2;
+    if (mask) {
+      int mj = mask[j];
+      if (mi == 0 && mj == 0) maskfac = 0;
+      else if (mi == 0 || mj == 0) maskfac = 1;
+    }
+    const double rlij = S.rl[ij][t];
+    if (!(maskfac > 0 && rlij < P.r2[tij])) continue;
+    const double rlijr = S.ri[ij][t];
+    const double nx = S.rnx[ij][t], ny = S.rny[ij][t], nz = S.rnz[ij][t];
+    const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
+    const double fcarij = S.fc[ij][t], dfcarijr = S.dfc[ij][t];
+    double VAij, dVAij, VRij, dVRij;
+    bop_VA<KIND>(P, tij, rlij, VAij, dVAij);
+    bop_VR<KIND>(P, tij, rlij, VRij, dVRij);
+    const double mf = 0.5 * maskfac;
+    VAij *= mf; dVAij *= mf; VRij *= mf; dVRij *= mf;
+
+    double zij = 0.0;
+    double dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0;
+    double wb[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) wb[q] = 0.0;
+
+    for (int ik = 0; ik < nb; ik++) {
+      if (ik == ij) continue;
+      const int tik = S.typ[ik][t] & 7;
+      const double rlik = S.rl[ik][t];
+      if (!(rlik < P.r2[tik])) {
+        S.kx[ik][t] = 0.0; S.ky[ik][t] = 0.0; S.kz[ik][t] = 0.0;
+        continue;
+      }
+      const double kx = S.rnx[ik][t], ky = S.rny[ik][t], kz = S.rnz[ik][t];
+      const double fcik = S.fc[ik][t], dfcikr = S.dfc[ik][t];
+      double h_Dr, dh_dDr, g_costh, dg_dcosth;
+      bop_h<KIND>(P, tik, rlij - rlik, h_Dr, dh_dDr);
+      const double costh = kx * nx + ky * ny + kz * nz;
+      bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
+      double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
+      const double disjk = sqrt(ex * ex + ey * ey + ez * ez);
+      const double idis = 1.0 / disjk, rlikr = S.ri[ik][t];
+      ex *= idis; ey *= idis; ez *= idis;
+      const double dcsdij = rlikr - costh * rlijr;
+      const double dcsdik = rlijr - costh * rlikr;
+      const double dcsdjk = -disjk * rlijr * rlikr;
+      const double dzfac = fcik * dg_dcosth * h_Dr;
+      zij += fcik * g_costh * h_Dr;
+      const double dzdrij = g_costh * fcik * dh_dDr;
+      const double dzdrik = g_costh * (dfcikr * h_Dr - fcik * dh_dDr);
+      // x
+      double dfx, dfy, dfz, dkx, dky, dkz;
+      {
+        double ci = -dcsdij * nx - dcsdik * kx, cj = dcsdij * nx - dcsdjk * ex, ck = dcsdik * kx + dcsdjk * ex;
+        dix += -dzdrij * nx - dzdrik * kx + dzfac * ci;
+        dfx = dzdrij * nx + dzfac * cj;
+        dkx = dzdrik * kx + dzfac * ck;
+      }
+      {
+        double ci = -dcsdij * ny - dcsdik * ky, cj = dcsdij * ny - dcsdjk * ey, ck = dcsdik * ky + dcsdjk * ey;
+        diy += -dzdrij * ny - dzdrik * ky + dzfac * ci;
+        dfy = dzdrij * ny + dzfac * cj;
+        dky = dzdrik * ky + dzfac * ck;
+      }
+      {
+        double ci = -dcsdij * nz - dcsdik * kz, cj = dcsdij * nz - dcsdjk * ez, ck = dcsdik * kz + dcsdjk * ez;
+        diz += -dzdrij * nz - dzdrik * kz + dzfac * ci;
+        dfz = dzdrij * nz + dzfac * cj;
+        dkz = dzdrik * kz + dzfac * ck;
+      }
+      djx += dfx; djy += dfy; djz += dfz;
+      S.kx[ik][t] = dkx; S.ky[ik][t] = dky; S.kz[ik][t] = dkz;
+      const double rikx = rlik * kx, riky = rlik * ky, rikz = rlik * kz;
+      // wijb(a,b) -= rij(a)*df(b) + rik(a)*dbidk(b); column-major index a + 3b
+      wb[0] -= rijx * dfx + rikx * dkx; wb[1] -= rijy * dfx + riky * dkx; wb[2] -= rijz * dfx + rikz * dkx;
+      wb[3] -= rijx * dfy + rikx * dky; wb[4] -= rijy * dfy + riky * dky; wb[5] -= rijz * dfy + rikz * dky;
+      wb[6] -= rijx * dfz + rikx * dkz; wb[7] -= rijy * dfz + riky * dkz; wb[8] -= rijz * dfz + rikz * dkz;
+    }
+
+    double bij, dfb;
+    bop_bo<KIND>(P, eli - 1, tij, zij, fcarij, VAij, bij, dfb);
+    const double e_bond = 0.5 * fcarij * (VRij + bij * VAij);
+    pei += e_bond;
+    S.ge[ij][t] += e_bond;
+    const double dffac = 0.5 * (dVRij * fcarij + bij * dVAij * fcarij + VRij * dfcarijr + bij * VAij * dfcarijr);
+    const double dfx = dffac * nx, dfy = dffac * ny, dfz = dffac * nz;
+    fix += dfx - dfb * dix; fiy += dfy - dfb * diy; fiz += dfz - dfb * diz;
+    S.gx[ij][t] += -dfx - dfb * djx; S.gy[ij][t] += -dfy - dfb * djy; S.gz[ij][t] += -dfz - dfb * djz;
+    for (int ik = 0; ik < nb; ik++) {
+      if (ik == ij) continue;
+      S.gx[ik][t] -= dfb * S.kx[ik][t]; S.gy[ik][t] -= dfb * S.ky[ik][t]; S.gz[ik][t] -= dfb * S.kz[ik][t];
+    }
+    double w[9];
+    w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
+    w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
+    w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
+#pragma unroll
+    for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+    acc[0] += e_bond;
+    const long long a = b0 + S.slot[ij][t];
+    if (epb) epb[a] = e_bond;
+    if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
+    if (wpb) {
+#pragma unroll
+      for (int q = 0; q < 9; q++) wpb[9 * a + q] = w[q];
+    }
+    if (wpa) {
+      // optional analysis output (not on the hot path): per-atom virial, half to i, half to j
+#pragma unroll
+      for (int q = 0; q < 9; q++) {
+        atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
+        atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
+      }
+    }
+  }
+  f[3 * s] = fix; f[3 * s + 1] = fiy; f[3 * s + 2] = fiz;
+  pe_own[s] = pei;
+  for (int k = 0; k < nb; k++)
+    G[b0 + S.slot[k][t]] = make_double4(S.gx[k][t], S.gy[k][t], S.gz[k][t], S.ge[k][t]);
+  return true;
+}
+
+// Main pass: one thread per atom with an NB-deep bond table; atoms with more bonds are appended to
+// `queue` and handled by k_bop_center_queued with the deepest table, so NB can be sized for the
+// typical atom instead of the worst one (shared memory per thread = 120 B x NB sets the occupancy).
+template <int KIND, int NB, int MINB>
+__global__ void __launch_bounds__(BOP_BLOCK, MINB)
 k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
              const long long *__restrict__ seed, const int2 *__restrict__ list,
              const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
              double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
              double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
-             int *__restrict__ flag, const unsigned char *__restrict__ role,
-             const int *__restrict__ stop) {
+             int pstride, int *__restrict__ queue, int *__restrict__ qcount,
+             const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BondSmem<NB> &S = *reinterpret_cast<BondSmem<NB> *>(smem_raw);
@@ -257,191 +459,46 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
   double acc[ATX_NSUM];
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
-
   if (s < nat && (!role || role[s] >= 1)) {
-    double4 pi = pos4[s];
-    const int eli = P.el2db[(int)pi.w];
-    const long long b0 = seed[s], b1 = seed[s + 1];
-    int nb = 0;
-    // ---- loop 1: bond table (bop_kernel.f90:563-1068) ----
-    for (long long a = b0; a < b1; a++) {
-      int2 en = list[a];
-      bool bond = false;
-      if (eli > 0) {
-        double4 pj = pos4[en.x];
-        int elj = P.el2db[(int)pj.w];
-        if (elj > 0) {
-          double dx = pj.x - pi.x, dy = pj.y - pi.y, dz = pj.z - pi.z;
-          if (ATX_NONZERO_SHIFT(en.y)) {
-            int sx, sy, sz;
-            atx_unpack_shift(en.y, sx, sy, sz);
-            double ax, ay, az;
-            atx_image_vector(A, sx, sy, sz, ax, ay, az);
-            dx -= ax; dy -= ay; dz -= az;
-          }
-          double r2 = dx * dx + dy * dy + dz * dz;
-          int ij = bop_pair_index(eli, elj, P.nel);
-          if (r2 < P.r2sq[ij]) {
-            if (nb >= NB) {
-              atomicOr(flag, 1);
-            } else {
-              double rl = sqrt(r2);
-              double fc = 1.0, dfc = 0.0;
-              if (!(r2 < P.r1sq[ij])) {
-                // trig_off_f
-                if (rl <= P.r1[ij]) { fc = 1.0; dfc = 0.0; }
-                else if (rl >= P.r2[ij]) { fc = 0.0; dfc = 0.0; }
-                else {
-                  double sn, cs;
-                  sincos(P.cfac[ij] * (rl - P.r1[ij]), &sn, &cs);
-                  fc = 0.5 * (1.0 + cs);
-                  dfc = -0.5 * P.cfac[ij] * sn;
-                }
-              }
-              const double ri = 1.0 / rl;
-              S.rnx[nb][t] = dx * ri; S.rny[nb][t] = dy * ri; S.rnz[nb][t] = dz * ri;
-              S.rl[nb][t] = rl; S.ri[nb][t] = ri; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
-              S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0; S.ge[nb][t] = 0.0;
-              S.slot[nb][t] = (int)(a - b0);
-              S.typ[nb][t] = ij | (en.x << 3);
-              nb++;
-              bond = true;
-            }
-          }
-        }
-      }
-      if (!bond) G[a] = make_double4(0.0, 0.0, 0.0, 0.0);
-    }
-
-    // ---- loop 2 (bop_kernel.f90:1075-1529) ----
-    double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
-    const int mi = mask ? mask[s] : 1;
-    for (int ij = 0; ij < nb; ij++) {
-      const int tij = S.typ[ij][t] & 7;
-      const int j = S.typ[ij][t] >> 3;
-      int maskfac = 2;
-      if (mask) {
-        int mj = mask[j];
-        if (mi == 0 && mj == 0) maskfac = 0;
-        else if (mi == 0 || mj == 0) maskfac = 1;
-      }
-      const double rlij = S.rl[ij][t];
-      if (!(maskfac > 0 && rlij < P.r2[tij])) continue;
-      const double rlijr = S.ri[ij][t];
-      const double nx = S.rnx[ij][t], ny = S.rny[ij][t], nz = S.rnz[ij][t];
-      const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
-      const double fcarij = S.fc[ij][t], dfcarijr = S.dfc[ij][t];
-      double VAij, dVAij, VRij, dVRij;
-      bop_VA<KIND>(P, tij, rlij, VAij, dVAij);
-      bop_VR<KIND>(P, tij, rlij, VRij, dVRij);
-      const double mf = 0.5 * maskfac;
-      VAij *= mf; dVAij *= mf; VRij *= mf; dVRij *= mf;
-
-      double zij = 0.0;
-      double dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0;
-      double wb[9];
-#pragma unroll
-      for (int q = 0; q < 9; q++) wb[q] = 0.0;
-
-      for (int ik = 0; ik < nb; ik++) {
-        if (ik == ij) continue;
-        const int tik = S.typ[ik][t] & 7;
-        const double rlik = S.rl[ik][t];
-        if (!(rlik < P.r2[tik])) {
-          S.kx[ik][t] = 0.0; S.ky[ik][t] = 0.0; S.kz[ik][t] = 0.0;
-          continue;
-        }
-        const double kx = S.rnx[ik][t], ky = S.rny[ik][t], kz = S.rnz[ik][t];
-        const double fcik = S.fc[ik][t], dfcikr = S.dfc[ik][t];
-        double h_Dr, dh_dDr, g_costh, dg_dcosth;
-        bop_h<KIND>(P, tik, rlij - rlik, h_Dr, dh_dDr);
-        const double costh = kx * nx + ky * ny + kz * nz;
-        bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
-        double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
-        const double disjk = sqrt(ex * ex + ey * ey + ez * ez);
-        const double idis = 1.0 / disjk, rlikr = S.ri[ik][t];
-        ex *= idis; ey *= idis; ez *= idis;
-        const double dcsdij = rlikr - costh * rlijr;
-        const double dcsdik = rlijr - costh * rlikr;
-        const double dcsdjk = -disjk * rlijr * rlikr;
-        const double dzfac = fcik * dg_dcosth * h_Dr;
-        zij += fcik * g_costh * h_Dr;
-        const double dzdrij = g_costh * fcik * dh_dDr;
-        const double dzdrik = g_costh * (dfcikr * h_Dr - fcik * dh_dDr);
-        // x
-        double dfx, dfy, dfz, dkx, dky, dkz;
-        {
-          double ci = -dcsdij * nx - dcsdik * kx, cj = dcsdij * nx - dcsdjk * ex, ck = dcsdik * kx + dcsdjk * ex;
-          dix += -dzdrij * nx - dzdrik * kx + dzfac * ci;
-          dfx = dzdrij * nx + dzfac * cj;
-          dkx = dzdrik * kx + dzfac * ck;
-        }
-        {
-          double ci = -dcsdij * ny - dcsdik * ky, cj = dcsdij * ny - dcsdjk * ey, ck = dcsdik * ky + dcsdjk * ey;
-          diy += -dzdrij * ny - dzdrik * ky + dzfac * ci;
-          dfy = dzdrij * ny + dzfac * cj;
-          dky = dzdrik * ky + dzfac * ck;
-        }
-        {
-          double ci = -dcsdij * nz - dcsdik * kz, cj = dcsdij * nz - dcsdjk * ez, ck = dcsdik * kz + dcsdjk * ez;
-          diz += -dzdrij * nz - dzdrik * kz + dzfac * ci;
-          dfz = dzdrij * nz + dzfac * cj;
-          dkz = dzdrik * kz + dzfac * ck;
-        }
-        djx += dfx; djy += dfy; djz += dfz;
-        S.kx[ik][t] = dkx; S.ky[ik][t] = dky; S.kz[ik][t] = dkz;
-        const double rikx = rlik * kx, riky = rlik * ky, rikz = rlik * kz;
-        // wijb(a,b) -= rij(a)*df(b) + rik(a)*dbidk(b); column-major index a + 3b
-        wb[0] -= rijx * dfx + rikx * dkx; wb[1] -= rijy * dfx + riky * dkx; wb[2] -= rijz * dfx + rikz * dkx;
-        wb[3] -= rijx * dfy + rikx * dky; wb[4] -= rijy * dfy + riky * dky; wb[5] -= rijz * dfy + rikz * dky;
-        wb[6] -= rijx * dfz + rikx * dkz; wb[7] -= rijy * dfz + riky * dkz; wb[8] -= rijz * dfz + rikz * dkz;
-      }
-
-      double bij, dfb;
-      bop_bo<KIND>(P, eli - 1, tij, zij, fcarij, VAij, bij, dfb);
-      const double e_bond = 0.5 * fcarij * (VRij + bij * VAij);
-      pei += e_bond;
-      S.ge[ij][t] += e_bond;
-      const double dffac = 0.5 * (dVRij * fcarij + bij * dVAij * fcarij + VRij * dfcarijr + bij * VAij * dfcarijr);
-      const double dfx = dffac * nx, dfy = dffac * ny, dfz = dffac * nz;
-      fix += dfx - dfb * dix; fiy += dfy - dfb * diy; fiz += dfz - dfb * diz;
-      S.gx[ij][t] += -dfx - dfb * djx; S.gy[ij][t] += -dfy - dfb * djy; S.gz[ij][t] += -dfz - dfb * djz;
-      for (int ik = 0; ik < nb; ik++) {
-        if (ik == ij) continue;
-        S.gx[ik][t] -= dfb * S.kx[ik][t]; S.gy[ik][t] -= dfb * S.ky[ik][t]; S.gz[ik][t] -= dfb * S.kz[ik][t];
-      }
-      double w[9];
-      w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
-      w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
-      w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
-#pragma unroll
-      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
-      acc[0] += e_bond;
-      const long long a = b0 + S.slot[ij][t];
-      if (epb) epb[a] = e_bond;
-      if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
-      if (wpb) {
-#pragma unroll
-        for (int q = 0; q < 9; q++) wpb[9 * a + q] = w[q];
-      }
-      if (wpa) {
-        // optional analysis output (not on the hot path): per-atom virial, half to i, half to j
-#pragma unroll
-        for (int q = 0; q < 9; q++) {
-          atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
-          atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
-        }
-      }
-    }
-    f[3 * s] = fix; f[3 * s + 1] = fiy; f[3 * s + 2] = fiz;
-    pe_own[s] = pei;
-    for (int k = 0; k < nb; k++)
-      G[b0 + S.slot[k][t]] = make_double4(S.gx[k][t], S.gy[k][t], S.gz[k][t], S.ge[k][t]);
+    if (!bop_center_atom<KIND, NB>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb, wpb, acc))
+      queue[atomicAdd(qcount, 1)] = s;
   }
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * pstride + blockIdx.x] = acc[k];
+  }
+}
+
+// Deferred atoms, deepest bond table (1 block per SM).  Always launched; exits at once when the
+// queue is empty.  Its block partials go behind those of the main pass.
+template <int KIND>
+__global__ void __launch_bounds__(BOP_BLOCK)
+k_bop_center_queued(Mat3 A, BopDev P, const double4 *__restrict__ pos4,
+                    const long long *__restrict__ seed, const int2 *__restrict__ list,
+                    const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
+                    double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
+                    double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
+                    int pstride, int pofs, const int *__restrict__ queue,
+                    const int *__restrict__ qcount, int *__restrict__ flag,
+                    const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BondSmem<BOP_NB_MAX> &S = *reinterpret_cast<BondSmem<BOP_NB_MAX> *>(smem_raw);
+  const int t = threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+  const int nq = *qcount;
+  for (int q = blockIdx.x * BOP_BLOCK + t; q < nq; q += gridDim.x * BOP_BLOCK) {
+    if (!bop_center_atom<KIND, BOP_NB_MAX>(S, t, queue[q], A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb,
+                                           fpb, wpb, acc))
+      atomicOr(flag, 1);  // more than BOP_NB_MAX bonds on one atom: reported as an error by the host
+  }
+  atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * pstride + pofs + blockIdx.x] = acc[k];
   }
 }
 
@@ -528,8 +585,8 @@ extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop *
     D.one_p_c2d2[i] = par->kind == ATX_BOP_TERSOFF ? 1.0 + D.c_sq_e[i] / D.d_sq_e[i] : 0.0;
   }
   for (int k = 0; k < 32; k++) D.el2db[k] = -1;
-  ATX_PASS(pot->flag.reserve(4));
-  ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 4 * sizeof(int)));
+  ATX_PASS(pot->flag.reserve(64));
+  ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 64 * sizeof(int)));
   *out = pot;
   return 0;
 }
@@ -567,33 +624,70 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
   return 0;
 }
 
-template <int KIND, int NB>
+template <int KIND, int NB, int MINB = 1>
 static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
-                         int nblocks) {
+                         int nblocks, int pstride) {
   size_t smem = sizeof(BondSmem<NB>);
   static bool attr_set = false;
   if (!attr_set) {
-    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     attr_set = true;
   }
-  ProfScope ps_(pot->ctx, "bop_force");
-  k_bop_center<KIND, NB><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
+  k_bop_center<KIND, NB, MINB><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
       nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
-      pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->flag.ptr, o.role, o.stop);
+      pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pstride, pot->queue.ptr, pot->flag.ptr + 1,
+      o.role, o.stop);
   ATX_LAUNCHED();
   return 0;
 }
+
+// experiment switch: ATX_BOP_MINB7=1 compiles the depth-4 kernel for 7 blocks/SM (<= 146 registers)
+static bool bop_minb7() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("ATX_BOP_MINB7"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+// bond-table depths that are compiled; the main pass uses the smallest one that holds (nearly)
+// every atom, the queued pass BOP_NB_MAX
+static const int kBopDepths[] = {4, 6, 8, 12, BOP_NB_MAX};
 
 template <int KIND>
 static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                             const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
                             int nblocks) {
-  const int cap = pot->nb_cap;
-  if (cap <= 6) return launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
-  if (cap <= 12) return launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
-  return launch_center<KIND, 24>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks);
+  cudaStream_t st = pot->ctx->stream;
+  const int nq = pot->ctx->sm_count;            // blocks of the queued pass
+  const int pstride = nblocks + nq;
+  ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 1, 0, sizeof(int), st));   // queue length
+  ProfScope ps_(pot->ctx, "bop_force");
+  switch (pot->nb_cap) {
+    case 4:
+      if (bop_minb7())
+        ATX_PASS((launch_center<KIND, 4, 7>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
+      else
+        ATX_PASS((launch_center<KIND, 4>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
+      break;
+    case 6: ATX_PASS((launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
+    case 8: ATX_PASS((launch_center<KIND, 8>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
+    case 12: ATX_PASS((launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
+    default: ATX_PASS((launch_center<KIND, BOP_NB_MAX>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
+  }
+  size_t smem = sizeof(BondSmem<BOP_NB_MAX>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ATX_CUDA(cudaFuncSetAttribute(k_bop_center_queued<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    attr_set = true;
+  }
+  k_bop_center_queued<KIND><<<nq, BOP_BLOCK, smem, st>>>(
+      p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f, pe_own, o.wpa,
+      epb, fpb, wpb, pot->sc.partials.ptr, pstride, nblocks, pot->queue.ptr, pot->flag.ptr + 1,
+      pot->flag.ptr, o.stop);
+  ATX_LAUNCHED();
+  return 0;
 }
 
 static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask_sorted,
@@ -607,27 +701,39 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
   double *pe_own = pot->sc.epa.ptr;
   int nblocks = (nat + BOP_BLOCK - 1) / BOP_BLOCK;
   if (nblocks < 1) nblocks = 1;
-  ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
+  const int ntot = nblocks + ctx->sm_count;   // main-pass blocks + queued-pass blocks
+  ATX_PASS(pot->sc.partials.reserve((size_t)ntot * ATX_NSUM));
+  ATX_PASS(pot->queue.reserve((size_t)nat + 1));
   if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
   if (!o.stop && (pot->nb_cap == 0 || pot->sized_nl != nl || pot->sized_build != nl->nbuilds)) {
-    // host-synchronous call (library mode, MD start, after every list rebuild): size the bond table
-    // from the bonds the current configuration really has, + 2 for motion inside the Verlet shell
-    ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 1, 0, sizeof(int), st));
+    // host-synchronous call (library mode, MD start, after every list rebuild): pick the bond-table
+    // depth from the histogram of bonds per atom.  Atoms beyond it (or that gain bonds while the
+    // list is reused) go through the queued pass, so the depth only has to fit the typical atom.
+    ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 8, 0, 32 * sizeof(int), st));
     if (nat > 0) {
       k_bop_count_bonds<<<(nat + 127) / 128, 128, 0, st>>>(nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr,
-                                                           nl->list.ptr, pot->flag.ptr);
+                                                           nl->list.ptr, o.role, pot->flag.ptr + 8);
       ATX_LAUNCHED();
     }
-    ATX_PASS(pot->hflag.reserve(4));
-    ATX_CUDA(cudaMemcpyAsync(pot->hflag.ptr, pot->flag.ptr, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ATX_PASS(pot->hflag.reserve(64));
+    ATX_CUDA(cudaMemcpyAsync(pot->hflag.ptr, pot->flag.ptr + 8, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
     ATX_CUDA(cudaStreamSynchronize(st));
-    int need = pot->hflag.ptr[1] + 2;
-    if (need > 24) {
-      atx_set_error("Internal neighbor list exhausted, *nebmax* too small: " + std::to_string(need - 2) +
-                    " bonds on one atom (limit 22).");
+    const int *hist = pot->hflag.ptr;
+    long long total = 0;
+    for (int b = 0; b < 32; b++) total += hist[b];
+    if (hist[31] > 0 || [&] { for (int b = BOP_NB_MAX + 1; b < 31; b++) if (hist[b]) return true; return false; }()) {
+      atx_set_error("Internal neighbor list exhausted, *nebmax* too small: an atom has more than " +
+                    std::to_string(BOP_NB_MAX) + " bonds.");
       return ATX_ERROR_UNSPECIFIED;
     }
-    pot->nb_cap = need <= 6 ? 6 : (need <= 12 ? 12 : 24);
+    // smallest compiled depth that leaves at most 0.1 % of the atoms to the queued pass
+    int cap = BOP_NB_MAX;
+    for (int d : kBopDepths) {
+      long long over = 0;
+      for (int b = d + 1; b < 32; b++) over += hist[b];
+      if (over * 1000 <= total) { cap = d; break; }
+    }
+    pot->nb_cap = cap;
     pot->sized_nl = nl;
     pot->sized_build = nl->nbuilds;
   }
@@ -647,7 +753,7 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
                                                     o.f, o.epa, o.role, o.stop);
     ATX_LAUNCHED();
   }
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, ntot, o.sums, o.stop));
   return 0;
 }
 

@@ -173,3 +173,16 @@ def test_large_lattice_property():
     e, f, w = pot.energy_and_forces(p, nl)[:3]
     assert abs(e / len(a) + 4.6295950127) < 1e-9
     assert np.abs(f).max() < 1e-9
+
+
+@pytest.mark.parametrize('kind,a0', [('Tersoff', 5.432), ('Kumagai', 5.429)])
+def test_queued_pass_for_overcoordinated_atoms(kind, a0):
+    """10x10x10 Si with one interstitial: the bond table is sized for 4 bonds (>= 99.9 % of the atoms),
+    the handful of over-coordinated atoms go through the queued deep-table pass; per-bond outputs
+    included so that every slot written by either pass is compared"""
+    a = S.diamond('Si', a0, (10, 10, 10))
+    a.rattle(0.03, seed=7)
+    pos = np.vstack([a.positions, [[0.5 * a0 + 3 * a0, 0.5 * a0 + 3 * a0, 0.5 * a0 + 3 * a0]]])
+    b = S.Atoms(list(a.symbols) + ['Si'], pos, a.cell, True)
+    g, o, onl = _both(kind, None, b, per_bond=True)
+    _check(g, o, onl, per_bond=True)

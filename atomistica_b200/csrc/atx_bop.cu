@@ -248,7 +248,7 @@ struct BondSmem {
 
 // One centre atom: bond table in shared memory, then all bonds ij with their k-sums.  Returns false
 // (having written nothing but zeroed G slots) when the atom has more than NB bonds.
-template <int KIND, int NB>
+template <int KIND, int NB, bool VIRIAL>
 __device__ __forceinline__ bool bop_center_atom(
     BondSmem<NB> &S, const int t, const int s, const Mat3 &A, const BopDev &P,
     const double4 *__restrict__ pos4, const long long *__restrict__ seed, const int2 *__restrict__ list,
@@ -339,8 +339,10 @@ __device__ __forceinline__ bool bop_center_atom(
     double zij = 0.0;
     double dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0;
     double wb[9];
+    if (VIRIAL) {
 #pragma unroll
-    for (int q = 0; q < 9; q++) wb[q] = 0.0;
+      for (int q = 0; q < 9; q++) wb[q] = 0.0;
+    }
 
     for (int ik = 0; ik < nb; ik++) {
       if (ik == ij) continue;
@@ -389,11 +391,13 @@ __device__ __forceinline__ bool bop_center_atom(
       }
       djx += dfx; djy += dfy; djz += dfz;
       S.kx[ik][t] = dkx; S.ky[ik][t] = dky; S.kz[ik][t] = dkz;
-      const double rikx = rlik * kx, riky = rlik * ky, rikz = rlik * kz;
-      // wijb(a,b) -= rij(a)*df(b) + rik(a)*dbidk(b); column-major index a + 3b
-      wb[0] -= rijx * dfx + rikx * dkx; wb[1] -= rijy * dfx + riky * dkx; wb[2] -= rijz * dfx + rikz * dkx;
-      wb[3] -= rijx * dfy + rikx * dky; wb[4] -= rijy * dfy + riky * dky; wb[5] -= rijz * dfy + rikz * dky;
-      wb[6] -= rijx * dfz + rikx * dkz; wb[7] -= rijy * dfz + riky * dkz; wb[8] -= rijz * dfz + rikz * dkz;
+      if (VIRIAL) {
+        const double rikx = rlik * kx, riky = rlik * ky, rikz = rlik * kz;
+        // wijb(a,b) -= rij(a)*df(b) + rik(a)*dbidk(b); column-major index a + 3b
+        wb[0] -= rijx * dfx + rikx * dkx; wb[1] -= rijy * dfx + riky * dkx; wb[2] -= rijz * dfx + rikz * dkx;
+        wb[3] -= rijx * dfy + rikx * dky; wb[4] -= rijy * dfy + riky * dky; wb[5] -= rijz * dfy + rikz * dky;
+        wb[6] -= rijx * dfz + rikx * dkz; wb[7] -= rijy * dfz + riky * dkz; wb[8] -= rijz * dfz + rikz * dkz;
+      }
     }
 
     double bij, dfb;
@@ -409,26 +413,28 @@ __device__ __forceinline__ bool bop_center_atom(
       if (ik == ij) continue;
       S.gx[ik][t] -= dfb * S.kx[ik][t]; S.gy[ik][t] -= dfb * S.ky[ik][t]; S.gz[ik][t] -= dfb * S.kz[ik][t];
     }
-    double w[9];
-    w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
-    w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
-    w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
-#pragma unroll
-    for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
     acc[0] += e_bond;
     const long long a = b0 + S.slot[ij][t];
     if (epb) epb[a] = e_bond;
     if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
-    if (wpb) {
+    if (VIRIAL) {
+      double w[9];
+      w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
+      w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
+      w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
 #pragma unroll
-      for (int q = 0; q < 9; q++) wpb[9 * a + q] = w[q];
-    }
-    if (wpa) {
-      // optional analysis output (not on the hot path): per-atom virial, half to i, half to j
+      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+      if (wpb) {
 #pragma unroll
-      for (int q = 0; q < 9; q++) {
-        atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
-        atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
+        for (int q = 0; q < 9; q++) wpb[9 * a + q] = w[q];
+      }
+      if (wpa) {
+        // optional analysis output (not on the hot path): per-atom virial, half to i, half to j
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
+          atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
+        }
       }
     }
   }
@@ -442,7 +448,7 @@ __device__ __forceinline__ bool bop_center_atom(
 // Main pass: one thread per atom with an NB-deep bond table; atoms with more bonds are appended to
 // `queue` and handled by k_bop_center_queued with the deepest table, so NB can be sized for the
 // typical atom instead of the worst one (shared memory per thread = 120 B x NB sets the occupancy).
-template <int KIND, int NB, int MINB>
+template <int KIND, int NB, int MINB, bool VIRIAL>
 __global__ void __launch_bounds__(BOP_BLOCK, MINB)
 k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
              const long long *__restrict__ seed, const int2 *__restrict__ list,
@@ -460,7 +466,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   if (s < nat && (!role || role[s] >= 1)) {
-    if (!bop_center_atom<KIND, NB>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb, wpb, acc))
+    if (!bop_center_atom<KIND, NB, VIRIAL>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb, wpb, acc))
       queue[atomicAdd(qcount, 1)] = s;
   }
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
@@ -491,7 +497,7 @@ k_bop_center_queued(Mat3 A, BopDev P, const double4 *__restrict__ pos4,
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   const int nq = *qcount;
   for (int q = blockIdx.x * BOP_BLOCK + t; q < nq; q += gridDim.x * BOP_BLOCK) {
-    if (!bop_center_atom<KIND, BOP_NB_MAX>(S, t, queue[q], A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb,
+    if (!bop_center_atom<KIND, BOP_NB_MAX, true>(S, t, queue[q], A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb,
                                            fpb, wpb, acc))
       atomicOr(flag, 1);  // more than BOP_NB_MAX bonds on one atom: reported as an error by the host
   }
@@ -624,18 +630,18 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
   return 0;
 }
 
-template <int KIND, int NB, int MINB = 1>
-static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+template <int KIND, int NB, int MINB, bool VIRIAL>
+static int launch_center_v(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
                          int nblocks, int pstride) {
   size_t smem = sizeof(BondSmem<NB>);
   static bool attr_set = false;
   if (!attr_set) {
-    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB, VIRIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     attr_set = true;
   }
-  k_bop_center<KIND, NB, MINB><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
+  k_bop_center<KIND, NB, MINB, VIRIAL><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
       nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
       pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pstride, pot->queue.ptr, pot->flag.ptr + 1,
       o.role, o.stop);
@@ -643,11 +649,15 @@ static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, cons
   return 0;
 }
 
-// experiment switch: ATX_BOP_MINB7=1 compiles the depth-4 kernel for 7 blocks/SM (<= 146 registers)
-static bool bop_minb7() {
-  static int v = -1;
-  if (v < 0) { const char *e = getenv("ATX_BOP_MINB7"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+// NVE stepping does not need the virial (PotOut::want_virial = false): that instantiation drops the
+// nine virial accumulators and their updates in the k-loop (fewer registers, ~25 % fewer FP64 ops)
+template <int KIND, int NB, int MINB = 1>
+static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                         const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
+                         int nblocks, int pstride) {
+  if (o.want_virial || o.wpa || wpb)
+    return launch_center_v<KIND, NB, MINB, true>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride);
+  return launch_center_v<KIND, NB, MINB, false>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride);
 }
 
 // bond-table depths that are compiled; the main pass uses the smallest one that holds (nearly)
@@ -664,12 +674,8 @@ static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, c
   ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 1, 0, sizeof(int), st));   // queue length
   ProfScope ps_(pot->ctx, "bop_force");
   switch (pot->nb_cap) {
-    case 4:
-      if (bop_minb7())
-        ATX_PASS((launch_center<KIND, 4, 7>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
-      else
-        ATX_PASS((launch_center<KIND, 4>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
-      break;
+    // depth 4: 30.9 KB of shared memory per block -> 7 blocks/SM if the kernel stays within 146 registers
+    case 4: ATX_PASS((launch_center<KIND, 4, 7>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
     case 6: ATX_PASS((launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
     case 8: ATX_PASS((launch_center<KIND, 8>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
     case 12: ATX_PASS((launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;

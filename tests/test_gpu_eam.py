@@ -138,3 +138,26 @@ def test_calculator_verlet_shell_reuses_list(cu_setfl):
     a.positions[7] += 0.3                       # beyond verlet_shell/2: must rebuild
     calc.get_forces(a)
     assert calc.nl.counters()[0] == builds + 1
+
+
+def test_full_size_replication_invariance(cu_setfl):
+    """BASELINE config C2 size (40^3 cells = 256 000 atoms): a rattled periodic 8^3 block replicated
+    5x5x5 has the same environments as the block itself, so E = 125 E_block and the forces tile --
+    which carries the oracle parity of the block (checked here too) to the full size.  Plus sum(f) = 0."""
+    blk = S.fcc('Cu', 3.615, (8, 8, 8))
+    blk.rattle(0.08, seed=21)
+    g, o = _both(blk, cu_setfl, per_at=False)
+    _check(g, o, per_at=False)
+    big = blk.repeat(5)
+    assert len(big) == 256000
+    p = native.from_atoms(big)
+    nl = native.Neighbors(200)
+    pot = native.TabulatedAlloyEAM(setfl=cu_setfl)
+    pot.bind_to(p, nl)
+    e, f, w = pot.energy_and_forces(p, nl)[:3]
+    assert abs(e - 125 * o['epot']) <= RTOL * abs(125 * o['epot'])
+    fscale = max(np.abs(o['f']).max(), 1.0)
+    assert np.abs(f.reshape(125, -1, 3) - o['f'][None]).max() <= RTOL * fscale
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * fscale * np.sqrt(len(big))
+    wscale = max(np.abs(o['wpot']).max(), 1.0, abs(o['epot']))
+    assert np.abs(w - 125 * o['wpot']).max() <= RTOL * 125 * wscale

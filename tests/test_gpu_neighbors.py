@@ -32,6 +32,20 @@ def test_si_diamond():
     _compare(S.diamond('Si', 5.432, (4, 4, 4)), 3.0)
 
 
+def test_find_neighbor_and_counts():
+    a = S.diamond('Si', 5.432, (3, 3, 3))
+    nl, p, ref = _compare(a, 3.0)
+    assert nl.get_number_of_all_neighbors(p) == 4 * len(a)
+    assert np.all(nl.get_coordination_numbers(p, 3.0) == 4)
+    seed, last, nb, dc = nl.to_host(p)
+    j = int(nb[seed[0] - 1]) - 1                 # first neighbour of atom 0
+    n1, n2 = nl.find_neighbor(p, 0, j)
+    assert nb[n1] == j + 1 and seed[0] - 1 <= n1 < last[0]
+    assert nb[n2] == 1 and seed[j] - 1 <= n2 < last[j]
+    far = int(np.argmax(((a.positions - a.positions[0]) ** 2).sum(1)))
+    assert nl.find_neighbor(p, 0, far) == (-2, -2)
+
+
 def test_si_diamond_rattled_skin():
     a = S.diamond('Si', 5.432, (5, 4, 3))
     a.rattle(0.1, seed=1)

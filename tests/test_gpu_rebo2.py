@@ -117,3 +117,21 @@ def test_no_mask_support(aC_small):
     pot.bind_to(p, nl)
     with pytest.raises(RuntimeError):
         pot.energy_and_forces(p, nl, mask=np.ones(len(aC_small), dtype=np.int32))
+
+
+def test_full_size_replication_invariance(aC):
+    """BASELINE config C3: aC.cfg (4001 atoms, triclinic) replicated 5x5x5 = 500 125 atoms.  The
+    replica has the environments of the periodic original, so E = 125 E_aC and the forces tile; the
+    original is compared with the oracle in test_amorphous_carbon."""
+    g, o = _both(aC)
+    big = aC.repeat(5)
+    assert len(big) == 500125
+    p = native.from_atoms(big)
+    nl = native.Neighbors(50)
+    pot = native.Rebo2()
+    pot.bind_to(p, nl)
+    e, f = pot.energy_and_forces(p, nl)[:2]
+    assert abs(e - 125 * o['epot']) <= RTOL * abs(125 * o['epot'])
+    fscale = max(np.abs(o['f']).max(), 1.0)
+    assert np.abs(f.reshape(125, -1, 3) - o['f'][None]).max() <= RTOL * fscale
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * fscale * np.sqrt(len(big))

@@ -178,6 +178,7 @@ struct atx_neighbors {
   DevBuf<int> count;        // nat+1 neighbour counts (sorted order)
   DevBuf<long long> seed;   // nat+1 exclusive offsets (sorted order), 0-based
   DevBuf<int2> list;        // device list: {sorted j, packed shift}
+  DevBuf<int2> rows;        // fixed-width per-atom rows of the single-pass build (scratch)
   DevBuf<int> rev;          // optional reverse-slot index
   bool rev_valid = false;
   DevBuf<long long> scal;   // small scalar scratch (npairs, nebmax, flags)

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128)
 k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict__ sshift,
         const int *__restrict__ cell_start, const int *__restrict__ order,
         int *__restrict__ count, const long long *__restrict__ seed, int2 *__restrict__ list,
-        long long *__restrict__ scal) {
+        long long *__restrict__ scal, int2 *__restrict__ rows, int rows_cap) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nat) return;
   double4 pi = pos4[s];
@@ -215,6 +215,13 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
                         (abs(s2z) >= ATX_SHIFT_BIAS);
               if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
               list[w++] = make_int2(t, atx_pack_shift(s2x, s2y, s2z) | ((int)pj.w << 24));
+            } else if (rows && cnt < rows_cap) {
+              // single-pass build: park the hit in this atom's fixed-width row; k_rows_to_csr
+              // compacts the rows once the offsets are known (no second distance search)
+              int bad = (abs(s2x) >= ATX_SHIFT_BIAS) | (abs(s2y) >= ATX_SHIFT_BIAS) |
+                        (abs(s2z) >= ATX_SHIFT_BIAS);
+              if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
+              rows[(size_t)s * rows_cap + cnt] = make_int2(t, atx_pack_shift(s2x, s2y, s2z) | ((int)pj.w << 24));
             }
             cnt++;
           }
@@ -243,6 +250,18 @@ k_count_stats(int nat, const int *__restrict__ count, const int *__restrict__ or
     atomicMax((unsigned long long *)&scal[1], (unsigned long long)mc);
     atomicMax((unsigned long long *)&scal[2], (unsigned long long)ml);
   }
+}
+
+// rows (fixed width, filled by the counting pass) -> CSR; 8 lanes per atom
+__global__ void k_rows_to_csr(int nat, const int2 *__restrict__ rows, int rows_cap,
+                              const long long *__restrict__ seed, int2 *__restrict__ list) {
+  const int s = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+  const int lane = threadIdx.x & 7;
+  if (s >= nat) return;
+  const long long b = seed[s];
+  const int n = (int)(seed[s + 1] - b);
+  const int2 *row = rows + (size_t)s * rows_cap;
+  for (int k = lane; k < n; k += 8) list[b + k] = row[k];
 }
 
 // refresh sorted positions after the atoms moved (list kept)
@@ -472,12 +491,22 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     ATX_LAUNCHED();
   }
   long long h[4] = {0, 0, 0, 0};
+  // Single-pass build from the second build on: the previous build's longest list (+ margin) sizes
+  // fixed-width rows the counting pass fills; if an atom outgrows its row the classic second
+  // search pass runs instead.  Scratch is bounded to 8 GiB.
+  int rows_cap = 0;
+  if (nl->nbuilds > 0 && nl->nebmax > 0 && nat > 0) {
+    int cap = nl->nebmax + (nl->nebmax / 8 > 8 ? nl->nebmax / 8 : 8);
+    if ((size_t)nat * cap * sizeof(int2) <= ((size_t)8 << 30) && nl->rows.reserve((size_t)nat * cap) == 0)
+      rows_cap = cap;
+  }
   if (nat > 0) {
     {
       ProfScope ps_(ctx, "nl_pairs_count");
       k_pairs<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
                                                         nl->cell_start.ptr, nl->order.ptr,
-                                                        nl->count.ptr, nullptr, nullptr, nl->scal.ptr);
+                                                        nl->count.ptr, nullptr, nullptr, nl->scal.ptr,
+                                                        rows_cap > 0 ? nl->rows.ptr : nullptr, rows_cap);
     }
     ATX_LAUNCHED();
     k_count_stats<<<ctx->sm_count * 2, 256, 0, st>>>(nat, nl->count.ptr, nl->order.ptr, nl->scal.ptr);
@@ -504,10 +533,16 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nat > 0 && nl->npairs > 0) {
     {
       ProfScope ps_(ctx, "nl_pairs_fill");
-      k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
-                                                       nl->cell_start.ptr, nl->order.ptr,
-                                                       nl->count.ptr, nl->seed.ptr, nl->list.ptr,
-                                                       nl->scal.ptr);
+      if (rows_cap > 0 && nl->nebmax <= rows_cap) {
+        const long long nthr = (long long)nat * 8;
+        k_rows_to_csr<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(nat, nl->rows.ptr, rows_cap, nl->seed.ptr,
+                                                                      nl->list.ptr);
+      } else {
+        k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
+                                                         nl->cell_start.ptr, nl->order.ptr,
+                                                         nl->count.ptr, nl->seed.ptr, nl->list.ptr,
+                                                         nl->scal.ptr, nullptr, 0);
+      }
     }
     ATX_LAUNCHED();
     ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));

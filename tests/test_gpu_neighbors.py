@@ -46,6 +46,36 @@ def test_find_neighbor_and_counts():
     assert nl.find_neighbor(p, 0, far) == (-2, -2)
 
 
+def test_rebuild_after_motion_single_pass(cu_setfl):
+    """from the second build on the counting pass parks the pairs in fixed-width rows (no second
+    distance search); the list must stay entry-by-entry identical to the oracle, also when an atom
+    outgrows its row (compressed region -> fallback to the two-pass build)"""
+    a = S.fcc('Cu', 3.615, (6, 6, 6))
+    a.rattle(0.05, seed=2)
+    rc = float(cu_setfl['cutoff'])
+    p = native.from_atoms(a)
+    nl = native.Neighbors(400)
+    nl.request_interaction_range(rc)
+    rng = np.random.RandomState(5)
+    for it in range(4):
+        if it == 3:      # pull 60 atoms towards atom 0: longest list grows far beyond the previous one
+            d = a.positions[1:61] - a.positions[0]
+            a.positions[1:61] = a.positions[0] + 0.45 * d
+        elif it:
+            a.positions = a.positions + rng.normal(scale=0.05, size=a.positions.shape)
+        p.coordinates[:, :] = a.positions
+        p.I_changed_positions()
+        seed, last, nb, dc = nl.to_host(p)
+        ref = oracle.neighbor_list(a.positions, a.cell, a.pbc, rc, 400)
+        nat = len(a)
+        n = ref.npairs + nat
+        assert nl.info()['npairs'] == ref.npairs
+        assert np.array_equal(seed[:nat + 1], ref.seed[:nat + 1])
+        assert np.array_equal(nb[:n], ref.neighbors[:n])
+        assert np.array_equal(dc[:n], ref.dc[:n])
+    assert nl.counters()[0] == 4
+
+
 def test_si_diamond_rattled_skin():
     a = S.diamond('Si', 5.432, (5, 4, 3))
     a.rattle(0.1, seed=1)

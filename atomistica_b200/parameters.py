@@ -7,7 +7,7 @@ src/macros.inc:123) and the built-in Fortran defaults
 The numbers are the published parameterisations cited in each "__ref__".
 """
 import copy
-from math import sqrt
+from math import log, sqrt
 
 
 def pair_index(i, j, maxval):
@@ -193,6 +193,79 @@ Kumagai_CompMaterSci_39_457_Si = {
     "c1": [0.20173476], "c2": [730418.72], "c3": [1000000.0], "c4": [1.0000000], "c5": [26.000000],
     "h": [-0.36500000], "r1": [2.70], "r2": [3.30],
 }
+
+# --- screened variants (TersoffScr, BrennerScr, KumagaiScr): parameters.py:79-107, 153-170, 196-218,
+#     409-420 of the reference.  r1/r2 become the inner cutoff, or1/or2 the outer (attractive /
+#     repulsive) cutoff, bor1/bor2 the bond-order cutoff, Cmin/Cmax the screening bounds.
+
+def _scr(base, **upd):
+    out = copy.deepcopy(base)
+    out.update(copy.deepcopy(upd))
+    return out
+
+
+Tersoff_PRB_39_5566_Si_C__Scr = _scr(
+    Tersoff_PRB_39_5566_Si_C,
+    m=[3, 3, 3],
+    r1=[2.00, sqrt(2.00 * 2.50), 2.50], r2=[2.00 * 1.2, sqrt(2.00 * 2.50) * 1.2, 2.50 * 1.2],
+    or1=[2.00, sqrt(2.00 * 3.00), 3.00], or2=[2.00 * 2.0, sqrt(2.00 * 3.00) * 2.0, 3.00 * 2.0],
+    bor1=[2.00, sqrt(2.00 * 3.00), 3.00], bor2=[2.00 * 2.0, sqrt(2.00 * 3.00) * 2.0, 3.00 * 2.0],
+    Cmin=[1.00, 1.00, 1.00], Cmax=[3.00, 3.00, 3.00])
+# mubo is 1/dimer length
+_p = Tersoff_PRB_39_5566_Si_C__Scr
+_p['mubo'] = [(_p['lambda'][_i] - _p['mu'][_i]) / log((_p['lambda'][_i] * _p['A'][_i]) / (_p['mu'][_i] * _p['B'][_i]))
+              for _i in range(3)]
+
+Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N__Scr = _scr(
+    Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N,
+    m=[3, 3, 3, 3, 3, 3],
+    r1=[2.00, -1.0, -1.0, 2.00, -1.0, 1.8], r2=[2.00 * 1.2, -1.0, -1.0, 2.00 * 1.2, -1.0, 1.8 * 1.2],
+    or1=[2.00, -1.0, -1.0, 3.00, -1.0, 1.8], or2=[2.00 * 2.0, -1.0, -1.0, 3.00 * 2.0, -1.0, 1.8 * 2],
+    bor1=[2.00, -1.0, -1.0, 3.00, -1.0, 1.8], bor2=[2.00 * 2.0, -1.0, -1.0, 3.00 * 2.0, -1.0, 1.8 * 2],
+    Cmin=[1.00] * 6, Cmax=[3.00] * 6)
+for _k in ('r1', 'r2', 'or1', 'or2', 'bor1', 'bor2'):
+    mix_geometric(Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N__Scr, _k)
+
+Erhart_PRB_71_035211_SiC__Scr = _scr(
+    Erhart_PRB_71_035211_SiC,
+    mu=[1.0 / 1.4276, 1.0 / 1.79, 1.0 / 1.842], m=[3, 3, 3],
+    r1=[2.00, 2.40, 2.50], r2=[2.00 * 1.2, 2.40 * 1.2, 2.50 * 1.2],
+    or1=[2.00, 2.40, 3.00], or2=[2.00 * 2.0, 2.40 * 2.0, 3.00 * 2.0],
+    bor1=[2.00, 2.40, 3.00], bor2=[2.00 * 2.0, 2.40 * 2.0, 3.00 * 2.0],
+    Cmin=[1.00, 1.00, 1.00], Cmax=[3.00, 3.00, 3.00])
+
+Kumagai_CompMaterSci_39_457_Si__Scr = _scr(
+    Kumagai_CompMaterSci_39_457_Si,
+    r1=[2.50], r2=[2.50 * 1.2], or1=[3.00], or2=[3.00 * 2.0], bor1=[3.00], bor2=[3.00 * 2.0],
+    Cmin=[1.00], Cmax=[3.00])
+
+SCR_KEYS = ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax')
+SCR_DEFAULTS = dict(Tersoff=Tersoff_PRB_39_5566_Si_C__Scr, Kumagai=Kumagai_CompMaterSci_39_457_Si__Scr,
+                    Brenner=Erhart_PRB_71_035211_SiC__Scr)
+
+
+def complete_scr(kind, db):
+    """like complete() for the screened classes: the object starts as the screened default
+    database (tersoff_params.f90:105-131 under SCREENING) and supplied keys overwrite it"""
+    base = copy.deepcopy(SCR_DEFAULTS[kind])
+    out = copy.deepcopy(db) if db is not None else base
+    nel = len(out['el'])
+    npairs = nel * (nel + 1) // 2
+    for k, v in base.items():
+        if k not in out:
+            if kind == 'Tersoff' and k in TERSOFF_FIELD_DEFAULTS:
+                n = nel if k in ('beta', 'n', 'c', 'd', 'h') else npairs
+                out[k] = [TERSOFF_FIELD_DEFAULTS[k]] * n
+            else:
+                out[k] = list(v)
+    return out
+
+
+def scr_cutoff(db):
+    """interaction range the screened potentials request (default_bind_to_func.f90:44-66, 106-130):
+    sqrt(C_dr_cut) * largest of the inner / outer / bond-order cutoffs, maximum over the pairs"""
+    rmax = max(max(db['r2']), max(db['or2']), max(db['bor2']))
+    return max(sqrt(c * c / (4 * (c - 1)) if c > 2.0 else 1.0) for c in db['Cmax']) * rmax
 
 # Fortran built-in defaults used when a key is not supplied
 # (type initialisers in tersoff_params.f90:62-77, brenner/kumagai: the default db itself)

@@ -294,7 +294,21 @@ def _per_bond_arrays(nl, per_bond):
     return np.zeros(n), np.zeros((n, 3)), np.zeros((n, 9))
 
 
-def bop_energy_and_forces(params, r, cell, nl, el, mask=None, per_at=False, per_bond=False):
+class BopScr(C.Structure):
+    _fields_ = [(k, C.c_double * 6) for k in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax')]
+
+
+def bop_scr_params(db):
+    """outer / bond-order cutoffs and screening bounds of a *__Scr parameter set"""
+    s = BopScr()
+    npairs = len(db['el']) * (len(db['el']) + 1) // 2
+    for key in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax'):
+        for k in range(npairs):
+            getattr(s, key)[k] = float(db[key][k])
+    return s
+
+
+def bop_energy_and_forces(params, r, cell, nl, el, mask=None, per_at=False, per_bond=False, scr=None):
     r = np.ascontiguousarray(r, dtype=np.float64)
     nat = len(r)
     abox = abox_from_cell(cell)
@@ -306,10 +320,13 @@ def bop_energy_and_forces(params, r, cell, nl, el, mask=None, per_at=False, per_
     wpa = np.zeros((nat, 9)) if per_at else None
     epb, fpb, wpb = _per_bond_arrays(nl, per_bond)
     m = None if mask is None else np.ascontiguousarray(mask, dtype=np.int32)
-    err = lib().orc_bop_energy_and_forces(
-        C.byref(params), C.c_int(nat), C.c_int(nat), _p(r), _p(abox), _p(el, C.c_int), _p(nl.seed, C.c_ssize_t),
-        _p(nl.last, C.c_ssize_t), _p(nl.neighbors, C.c_int), _p(nl.dc, C.c_int), _p(m, C.c_int), C.byref(epot),
-        _p(f), _p(wpot), _p(epa), _p(epb), _p(fpb), _p(wpa), _p(wpb))
+    tail = (C.c_int(nat), C.c_int(nat), _p(r), _p(abox), _p(el, C.c_int), _p(nl.seed, C.c_ssize_t),
+            _p(nl.last, C.c_ssize_t), _p(nl.neighbors, C.c_int), _p(nl.dc, C.c_int), _p(m, C.c_int), C.byref(epot),
+            _p(f), _p(wpot), _p(epa), _p(epb), _p(fpb), _p(wpa), _p(wpb))
+    if scr is None:
+        err = lib().orc_bop_energy_and_forces(C.byref(params), *tail)
+    else:
+        err = lib().orc_bop_scr_energy_and_forces(C.byref(params), C.byref(scr), *tail)
     assert err == 0
     out = dict(epot=epot.value, f=f, wpot=wpot.reshape(3, 3).T.copy())
     if per_at:

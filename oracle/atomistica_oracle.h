@@ -92,6 +92,20 @@ int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, 
                               double *epot_per_at, double *epot_per_bond, double *f_per_bond,
                               double *wpot_per_at, double *wpot_per_bond);
 
+/* Screened variants (TersoffScr, KumagaiScr, BrennerScr): outer / bond-order cutoffs and the
+ * Baskes screening bounds of the *_Scr parameter sets (parameters.py), pair-indexed.  In these
+ * variants r1/r2 of orc_bop_params_t are the INNER cutoff and every cutoff is exp_cutoff_t. */
+typedef struct {
+  double or1[6], or2[6], bor1[6], bor2[6], Cmin[6], Cmax[6];
+} orc_bop_scr_t;
+
+int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr_t *scr, int nat,
+                                  int natloc, const double *r, const double *Abox, const int *el,
+                                  const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                  const int *dc, const int *mask, double *epot, double *f,
+                                  double *wpot, double *epot_per_at, double *epot_per_bond,
+                                  double *f_per_bond, double *wpot_per_at, double *wpot_per_bond);
+
 /* ---- REBO2: src/potentials/bop/rebo2/ ---- */
 
 typedef struct {

@@ -137,11 +137,16 @@ class Atomistica:
 
 
 def _calculator(cls):
-    return type(cls.__name__, (Atomistica,), dict(potential_class=cls, __doc__=cls.__doc__))
+    # aseinterface.py:491-504: classes ending in 'Scr' get avgn = 1000 (longer lists)
+    return type(cls.__name__, (Atomistica,), dict(potential_class=cls, __doc__=cls.__doc__,
+                                                  avgn=1000 if cls.__name__.endswith('Scr') else 100))
 
 
 Tersoff = _calculator(native.Tersoff)
 Kumagai = _calculator(native.Kumagai)
 Brenner = _calculator(native.Brenner)
+TersoffScr = _calculator(native.TersoffScr)
+KumagaiScr = _calculator(native.KumagaiScr)
+BrennerScr = _calculator(native.BrennerScr)
 Rebo2 = _calculator(native.Rebo2)
 TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)

@@ -37,6 +37,30 @@ struct BopDev {
   double c_sq_e[3], d_sq_e[3], one_p_c2d2[3];  // c^2, d^2, 1 + c^2/d^2
 };
 
+// exp_cutoff_t (src/support/cutoff.f90:232-293): the cutoff of every *_scr module
+struct ExpCut {
+  double r1, r2, fac1, fac2, c, d, off;
+};
+
+// Screened variants (SCREENING defined): cutoffs and Baskes screening bounds per pair,
+// default_bind_to_func.f90:44-104
+struct BopScrDev {
+  ExpCut cin[6], cout[6], cbo[6];
+  double cut_in_l[6], cut_in_h[6], cut_in_h2[6], cut_out_l[6], cut_out_h[6], cut_bo_h[6], max_cut_sq[6];
+  double Cmin[6], Cmax[6], dC[6], C_dr_cut[6];
+  double screening_threshold, dot_threshold;
+};
+
+// per-atom tables of the screened kernels, bond-major / entry-major: element (b, s) at b*nat + s
+struct BopScrTab {
+  int nat, NB, NS;
+  double *rnx, *rny, *rnz, *rl, *fcar, *dfcar, *fcbo, *dfcbo, *kx, *ky, *kz, *zf;  // [NB][nat]
+  int *jidx, *slot, *typ, *sseed, *scnt;                                             // [NB][nat]
+  int *nbond;                                                                        // [nat]
+  double *arik, *arjk, *boik, *bojk, *sfac;                                          // [NS][nat]
+  int *kslot;                                                                        // [NS][nat]
+};
+
 struct atx_bop {
   atx_ctx *ctx = nullptr;
   atx_bop_params par{};
@@ -50,6 +74,13 @@ struct atx_bop {
   int nb_cap = 0;     // bond-table capacity (template NB) in use
   const atx_neighbors *sized_nl = nullptr;  // list + build number nb_cap was sized for
   long long sized_build = -1;
+  // screened variants
+  bool screened = false;
+  atx_bop_screening scr_par{};
+  DevBuf<BopScrDev> scr_dev;
+  DevBuf<double> scr_d;   // backing store of the BopScrTab double fields
+  DevBuf<int> scr_i;      // backing store of the BopScrTab int fields
+  BopScrTab tab{};
   PotScratch sc;
 };
 
@@ -508,6 +539,443 @@ k_bop_center_queued(Mat3 A, BopDev P, const double4 *__restrict__ pos4,
   }
 }
 
+// ===========================================================================================
+// Screened variants (TersoffScr, KumagaiScr, BrennerScr): BOP_KERNEL compiled with SCREENING
+// (bop_kernel.f90:563-1068 incl. the screening function 682-995; 1075-1529 incl. 1448-1520;
+// 1531-1611), CUTOFF_T = exp_cutoff_t.  Two kernels, one thread per central atom:
+//   k_bopscr_bonds   loop 1 of the reference: per list entry decide unscreened / screened /
+//                    partially screened, evaluate S_ij = exp(-sum ((Cmax-C)/(C-Cmin))^2) over the
+//                    screening neighbours k (taken from the SAME list of i), and write the bond
+//                    table + screening-neighbour table of the atom to global memory.  COUNT mode
+//                    only measures the table depths (called once per list build).
+//   k_bopscr_center  loops 2 and 3 for the atom.  sfacbo of the bonds of i only receives
+//                    contributions from i's own ij loop, so loop 3 can follow loop 2 in the same
+//                    thread.  Every atom that receives force from centre i (j, k, screening
+//                    neighbours) is an entry of i's list: forces are accumulated per list slot
+//                    in G and collected by k_bop_gather as in the unscreened path.
+// ===========================================================================================
+
+__device__ __forceinline__ void bop_expcut(const ExpCut &t, double r, double &val, double &dval) {
+  if (r <= t.r1) { val = 1.0; dval = 0.0; }
+  else if (r >= t.r2) { val = 0.0; dval = 0.0; }
+  else {
+    const double x = t.fac1 * (r - t.r1);
+    const double x2 = x * x;
+    const double v = exp(-8 * x * x2);
+    const double dv = -24 * x2 * v;
+    dval = t.fac1 * t.fac2 * (dv + 3 * t.c * x2 + 4 * t.d * x * x2);
+    val = t.fac2 * (v + t.c * x * x2 + t.d * x2 * x2 - t.off);
+  }
+}
+
+__device__ __forceinline__ void bop_list_vec(const Mat3 &A, const double4 &pi, const double4 &pj, int packed,
+                                             double &dx, double &dy, double &dz) {
+  // r_j - r_i - Abox.dc
+  dx = pj.x - pi.x; dy = pj.y - pi.y; dz = pj.z - pi.z;
+  if (ATX_NONZERO_SHIFT(packed)) {
+    int sx, sy, sz;
+    atx_unpack_shift(packed, sx, sy, sz);
+    double ax, ay, az;
+    atx_image_vector(A, sx, sy, sz, ax, ay, az);
+    dx -= ax; dy -= ay; dz -= az;
+  }
+}
+
+#define TB(field, b) T.field[(size_t)(b) * T.nat + s]
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_bopscr_bonds(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, BopScrTab T,
+               const double4 *__restrict__ pos4, const long long *__restrict__ seed,
+               const int2 *__restrict__ list, int *__restrict__ flag,
+               const unsigned char *__restrict__ role, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int nb = 0, ns = 0;
+  if (s < nat && (!role || role[s] >= 1)) {
+    const BopScrDev &S = *Sp;
+    const double4 pi = pos4[s];
+    const int eli = P.el2db[(int)pi.w];
+    const long long b0 = seed[s], b1 = seed[s + 1];
+    if (eli > 0)
+      for (long long a = b0; a < b1; a++) {
+        const int2 en = list[a];
+        const int elj = P.el2db[ATX_ENTRY_EL(en.y)];
+        if (elj <= 0) continue;
+        const double4 pj = pos4[en.x];
+        double rx, ry, rz;
+        bop_list_vec(A, pi, pj, en.y, rx, ry, rz);
+        double rlij = rx * rx + ry * ry + rz * rz;   // squared until the bond is accepted
+        const int ij = bop_pair_index(eli, elj, P.nel);
+        double fcar = 1.0, dfcar = 0.0, fcbo = 1.0, dfcbo = 0.0;
+        bool bond = false;
+        const int ineb = ns;
+
+        if (rlij < S.cut_in_l[ij] * S.cut_in_l[ij]) {
+          bond = true;
+          rlij = sqrt(rlij);
+        } else if (rlij < S.max_cut_sq[ij] && S.cut_out_l[ij] < S.cut_out_h[ij]) {
+          bool screened = false, need_derivative = false;
+          double sij = 0.0, dsijdrij = 0.0;
+          for (long long kn = b0; kn < b1 && !(screened || sij < S.screening_threshold); kn++) {
+            if (kn == a) continue;   // k /= j .or. dc(kn) /= dc(jn): a different list slot
+            const int2 ek = list[kn];
+            const double4 pk = pos4[ek.x];
+            double kx, ky, kz;
+            bop_list_vec(A, pi, pk, ek.y, kx, ky, kz);
+            const double rlik = kx * kx + ky * ky + kz * kz;
+            if (!(rlik < S.C_dr_cut[ij] * rlij)) continue;
+            const double dot_ij_ik = rx * kx + ry * ky + rz * kz;
+            const double jx = -rx + kx, jy = -ry + ky, jz = -rz + kz;
+            const double dot_ij_jk = rx * jx + ry * jy + rz * jz;
+            const double rljk = jx * jx + jy * jy + jz * jz;
+            if (dot_ij_ik > S.dot_threshold && dot_ij_jk < -S.dot_threshold) {
+              const double xik = rlik / rlij, xjk = rljk / rlij;
+              const double xm = xik - xjk, xp = xik + xjk;
+              double fac = 1.0 / (1 - xm * xm);
+              const double C = (2 * xp - xm * xm - 1) * fac;
+              if (C <= S.Cmin[ij]) {
+                screened = true;
+              } else if (C < S.Cmax[ij]) {
+                need_derivative = true;
+                const double Cmax_C = S.Cmax[ij] - C, C_Cmin = C - S.Cmin[ij];
+                const double q = Cmax_C / C_Cmin;
+                sij = sij - q * q;
+                const double dCdrik = 4 * xik * fac * (1 + (C - 1) * xm);
+                const double dCdrjk = 4 * xjk * fac * (1 - (C - 1) * xm);
+                const double dCdrij = -(dCdrik + dCdrjk);
+                fac = 2 * Cmax_C * S.dC[ij] / (C_Cmin * C_Cmin * C_Cmin);
+                dsijdrij = dsijdrij + fac * dCdrij;
+                if (!COUNT && ns < T.NS) {
+                  TB(kslot, ns) = (int)(kn - b0);
+                  TB(arik, ns) = fac * dCdrik / rlik;
+                  TB(arjk, ns) = fac * dCdrjk / rljk;
+                }
+                ns++;
+              }
+            }
+          }
+          if ((screened || sij < S.screening_threshold) && rlij > S.cut_in_h2[ij]) {
+            ns = ineb;   // fully screened: no bond, screening neighbours discarded
+          } else {
+            bond = true;
+            rlij = sqrt(rlij);
+            double fcin, dfcin, fa, dfa, fb, dfb;
+            if (screened) {
+              bop_expcut(S.cin[ij], rlij, fcin, dfcin);
+              fcar = fcin; dfcar = dfcin; fcbo = fcin; dfcbo = dfcin;
+              ns = ineb;
+            } else if (need_derivative) {
+              sij = exp(sij);
+              bop_expcut(S.cin[ij], rlij, fcin, dfcin);
+              bop_expcut(S.cout[ij], rlij, fa, dfa);
+              bop_expcut(S.cbo[ij], rlij, fb, dfb);
+              fcar = (1.0 - fcin) * sij * fa + fcin;
+              dfcar = (1.0 - fcin) * sij * (dfa + fa * dsijdrij / rlij) - dfcin * sij * fa + dfcin;
+              fcbo = (1.0 - fcin) * sij * fb + fcin;
+              dfcbo = (1.0 - fcin) * sij * (dfb + fb * dsijdrij / rlij) - dfcin * sij * fb + dfcin;
+              if (!COUNT) {
+                const int hi = ns < T.NS ? ns : T.NS;
+                for (int q = ineb; q < hi; q++) {
+                  const double ar = TB(arik, q), aj = TB(arjk, q);
+                  TB(boik, q) = ar * sij * fb * (1.0 - fcin);
+                  TB(bojk, q) = aj * sij * fb * (1.0 - fcin);
+                  TB(arik, q) = ar * sij * fa * (1.0 - fcin);
+                  TB(arjk, q) = aj * sij * fa * (1.0 - fcin);
+                  TB(sfac, q) = 0.0;
+                }
+              }
+            } else {
+              bop_expcut(S.cout[ij], rlij, fa, dfa);
+              bop_expcut(S.cbo[ij], rlij, fb, dfb);
+              if (rlij < S.cut_in_h[ij]) {
+                bop_expcut(S.cin[ij], rlij, fcin, dfcin);
+                fcar = (1.0 - fcin) * fa + fcin;
+                dfcar = (1.0 - fcin) * dfa - dfcin * fa + dfcin;
+                fcbo = (1.0 - fcin) * fb + fcin;
+                dfcbo = (1.0 - fcin) * dfb - dfcin * fb + dfcin;
+              } else {
+                fcar = fa; dfcar = dfa; fcbo = fb; dfcbo = dfb;
+              }
+              ns = ineb;   // need_derivative false: nothing was stored
+            }
+          }
+        } else if (rlij < S.cut_in_h2[ij]) {
+          // pair without an outer cutoff: plain inner cutoff
+          bond = true;
+          rlij = sqrt(rlij);
+          bop_expcut(S.cin[ij], rlij, fcar, dfcar);
+          fcbo = fcar; dfcbo = dfcar;
+        }
+
+        if (bond) {
+          if (!COUNT && nb < T.NB) {
+            const double ri = 1.0 / rlij;
+            TB(rnx, nb) = rx * ri; TB(rny, nb) = ry * ri; TB(rnz, nb) = rz * ri;
+            TB(rl, nb) = rlij;
+            TB(fcar, nb) = fcar; TB(dfcar, nb) = dfcar; TB(fcbo, nb) = fcbo; TB(dfcbo, nb) = dfcbo;
+            TB(jidx, nb) = en.x; TB(slot, nb) = (int)(a - b0); TB(typ, nb) = ij;
+            TB(sseed, nb) = ineb; TB(scnt, nb) = ns - ineb;
+          }
+          nb++;
+        }
+      }
+    if (!COUNT) {
+      T.nbond[s] = nb < T.NB ? nb : T.NB;
+      if (nb > T.NB || ns > T.NS) atomicOr(flag, 1);
+    }
+  }
+  if (COUNT) {
+    nb = __reduce_max_sync(0xffffffffu, nb);
+    ns = __reduce_max_sync(0xffffffffu, ns);
+    if ((threadIdx.x & 31) == 0) {
+      if (nb > 0) atomicMax(&flag[2], nb);
+      if (ns > 0) atomicMax(&flag[3], ns);
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(BOP_BLOCK)
+k_bopscr_center(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, BopScrTab T,
+                const double4 *__restrict__ pos4, const long long *__restrict__ seed,
+                const int2 *__restrict__ list, const int *__restrict__ mask, double4 *__restrict__ G,
+                double *__restrict__ f, double *__restrict__ pe_own, double *__restrict__ wpa,
+                double *__restrict__ epb, double *__restrict__ fpb, double *__restrict__ wpb,
+                double *__restrict__ partials, const unsigned char *__restrict__ role,
+                const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * (BOP_BLOCK / 32)];
+  const int s = blockIdx.x * BOP_BLOCK + threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+
+  if (s < nat && (!role || role[s] >= 1)) {
+    const BopScrDev &S = *Sp;
+    const double4 pi = pos4[s];
+    const int eli = P.el2db[(int)pi.w];
+    const long long b0 = seed[s];
+    const int nb = eli > 0 ? T.nbond[s] : 0;
+    double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
+    const int mi = mask ? mask[s] : 1;
+
+    // ---- loop 2 ----
+    for (int ij = 0; ij < nb; ij++) {
+      const int tij = TB(typ, ij);
+      const int j = TB(jidx, ij);
+      int maskfac = 2;
+      if (mask) {
+        int mj = mask[j];
+        if (mi == 0 && mj == 0) maskfac = 0;
+        else if (mi == 0 || mj == 0) maskfac = 1;
+      }
+      const double rlij = TB(rl, ij);
+      if (!(maskfac > 0 && rlij < S.cut_out_h[tij])) continue;   // cut_ar_h = cut_out_h
+      const double rlijr = 1.0 / rlij;
+      const double nx = TB(rnx, ij), ny = TB(rny, ij), nz = TB(rnz, ij);
+      const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
+      const double fcarij = TB(fcar, ij), dfcarijr = TB(dfcar, ij);
+      double VAij, dVAij, VRij, dVRij;
+      bop_VA<KIND>(P, tij, rlij, VAij, dVAij);
+      bop_VR<KIND>(P, tij, rlij, VRij, dVRij);
+      const double mf = 0.5 * maskfac;
+      VAij *= mf; dVAij *= mf; VRij *= mf; dVRij *= mf;
+
+      double zij = 0.0;
+      double dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0;
+      double wb[9], w[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) { wb[q] = 0.0; w[q] = 0.0; }
+
+      for (int ik = 0; ik < nb; ik++) {
+        if (ik == ij) continue;
+        const int tik = TB(typ, ik);
+        const double rlik = TB(rl, ik);
+        if (!(rlik < S.cut_bo_h[tik])) {
+          TB(kx, ik) = 0.0; TB(ky, ik) = 0.0; TB(kz, ik) = 0.0; TB(zf, ik) = 0.0;
+          continue;
+        }
+        const double kx = TB(rnx, ik), ky = TB(rny, ik), kz = TB(rnz, ik);
+        const double fcik = TB(fcbo, ik), dfcikr = TB(dfcbo, ik);
+        double h_Dr, dh_dDr, g_costh, dg_dcosth;
+        bop_h<KIND>(P, tik, rlij - rlik, h_Dr, dh_dDr);
+        const double costh = kx * nx + ky * ny + kz * nz;
+        bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
+        double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
+        const double disjk = sqrt(ex * ex + ey * ey + ez * ez);
+        const double idis = 1.0 / disjk, rlikr = 1.0 / rlik;
+        ex *= idis; ey *= idis; ez *= idis;
+        const double dcsdij = rlikr - costh * rlijr;
+        const double dcsdik = rlijr - costh * rlikr;
+        const double dcsdjk = -disjk * rlijr * rlikr;
+        const double dzfac = fcik * dg_dcosth * h_Dr;
+        TB(zf, ik) = g_costh * h_Dr;
+        zij += fcik * g_costh * h_Dr;
+        const double dzdrij = g_costh * fcik * dh_dDr;
+        const double dzdrik = g_costh * (dfcikr * h_Dr - fcik * dh_dDr);
+        double dfx, dfy, dfz, dkx, dky, dkz;
+        {
+          double ci = -dcsdij * nx - dcsdik * kx, cj = dcsdij * nx - dcsdjk * ex, ck = dcsdik * kx + dcsdjk * ex;
+          dix += -dzdrij * nx - dzdrik * kx + dzfac * ci;
+          dfx = dzdrij * nx + dzfac * cj;
+          dkx = dzdrik * kx + dzfac * ck;
+        }
+        {
+          double ci = -dcsdij * ny - dcsdik * ky, cj = dcsdij * ny - dcsdjk * ey, ck = dcsdik * ky + dcsdjk * ey;
+          diy += -dzdrij * ny - dzdrik * ky + dzfac * ci;
+          dfy = dzdrij * ny + dzfac * cj;
+          dky = dzdrik * ky + dzfac * ck;
+        }
+        {
+          double ci = -dcsdij * nz - dcsdik * kz, cj = dcsdij * nz - dcsdjk * ez, ck = dcsdik * kz + dcsdjk * ez;
+          diz += -dzdrij * nz - dzdrik * kz + dzfac * ci;
+          dfz = dzdrij * nz + dzfac * cj;
+          dkz = dzdrik * kz + dzfac * ck;
+        }
+        djx += dfx; djy += dfy; djz += dfz;
+        TB(kx, ik) = dkx; TB(ky, ik) = dky; TB(kz, ik) = dkz;
+        const double rikx = rlik * kx, riky = rlik * ky, rikz = rlik * kz;
+        wb[0] -= rijx * dfx + rikx * dkx; wb[1] -= rijy * dfx + riky * dkx; wb[2] -= rijz * dfx + rikz * dkx;
+        wb[3] -= rijx * dfy + rikx * dky; wb[4] -= rijy * dfy + riky * dky; wb[5] -= rijz * dfy + rikz * dky;
+        wb[6] -= rijx * dfz + rikx * dkz; wb[7] -= rijy * dfz + riky * dkz; wb[8] -= rijz * dfz + rikz * dkz;
+      }
+
+      double bij, dfb;
+      bop_bo<KIND>(P, eli - 1, tij, zij, fcarij, VAij, bij, dfb);
+      const double e_bond = 0.5 * fcarij * (VRij + bij * VAij);
+      pei += e_bond;
+      const double dffac = 0.5 * (dVRij * fcarij + bij * dVAij * fcarij + VRij * dfcarijr + bij * VAij * dfcarijr);
+      const double dfx = dffac * nx, dfy = dffac * ny, dfz = dffac * nz;
+      fix += dfx - dfb * dix; fiy += dfy - dfb * diy; fiz += dfz - dfb * diz;
+      double fjx = -dfx - dfb * djx, fjy = -dfy - dfb * djy, fjz = -dfz - dfb * djz;
+      w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
+      w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
+      w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
+
+      // forces on the other bond partners of i and the screening weight of the bonds i-k
+      for (int ik = 0; ik < nb; ik++) {
+        if (ik == ij) continue;
+        const long long ak = b0 + TB(slot, ik);
+        double4 g = G[ak];
+        g.x -= dfb * TB(kx, ik); g.y -= dfb * TB(ky, ik); g.z -= dfb * TB(kz, ik);
+        G[ak] = g;
+        const int q0 = TB(sseed, ik), q1 = q0 + TB(scnt, ik);
+        const double add = TB(zf, ik) * dfb;
+        for (int q = q0; q < q1; q++) TB(sfac, q) += add;
+      }
+
+      // screening neighbours of bond i-j, attractive / repulsive part (bop_kernel.f90:1478-1512)
+      {
+        const double dff = 0.5 * (VRij + bij * VAij);
+        const int q0 = TB(sseed, ij), q1 = q0 + TB(scnt, ij);
+        for (int q = q0; q < q1; q++) {
+          const long long ak = b0 + TB(kslot, q);
+          const int2 ek = list[ak];
+          const double4 pk = pos4[ek.x];
+          double kx, ky, kz;
+          bop_list_vec(A, pi, pk, ek.y, kx, ky, kz);
+          const double jx = -rijx + kx, jy = -rijy + ky, jz = -rijz + kz;
+          const double c1 = dff * TB(arik, q), c2 = dff * TB(arjk, q);
+          const double d1x = c1 * kx, d1y = c1 * ky, d1z = c1 * kz;
+          const double d2x = c2 * jx, d2y = c2 * jy, d2z = c2 * jz;
+          fix += d1x; fiy += d1y; fiz += d1z;
+          fjx += d2x; fjy += d2y; fjz += d2z;
+          double4 g = G[ak];
+          g.x -= d1x + d2x; g.y -= d1y + d2y; g.z -= d1z + d2z;
+          G[ak] = g;
+          w[0] += kx * d1x + jx * d2x; w[1] += ky * d1x + jy * d2x; w[2] += kz * d1x + jz * d2x;
+          w[3] += kx * d1y + jx * d2y; w[4] += ky * d1y + jy * d2y; w[5] += kz * d1y + jz * d2y;
+          w[6] += kx * d1z + jx * d2z; w[7] += ky * d1z + jy * d2z; w[8] += kz * d1z + jz * d2z;
+        }
+      }
+
+      const long long aj = b0 + TB(slot, ij);
+      {
+        double4 g = G[aj];
+        g.x += fjx; g.y += fjy; g.z += fjz; g.w += e_bond;
+        G[aj] = g;
+      }
+#pragma unroll
+      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+      acc[0] += e_bond;
+      if (epb) epb[aj] += e_bond;
+      if (fpb) { fpb[3 * aj] += dfx; fpb[3 * aj + 1] += dfy; fpb[3 * aj + 2] += dfz; }
+      if (wpb) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) wpb[9 * aj + q] += w[q];
+      }
+      if (wpa) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
+          atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
+        }
+      }
+    }
+
+    // ---- loop 3: screening forces of the bond-order cutoff (bop_kernel.f90:1531-1611) ----
+    for (int ij = 0; ij < nb; ij++) {
+      const int q0 = TB(sseed, ij), q1 = q0 + TB(scnt, ij);
+      if (q0 >= q1) continue;
+      const int j = TB(jidx, ij);
+      const double rlij = TB(rl, ij);
+      const double rijx = rlij * TB(rnx, ij), rijy = rlij * TB(rny, ij), rijz = rlij * TB(rnz, ij);
+      double fjx = 0, fjy = 0, fjz = 0;
+      double w[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) w[q] = 0.0;
+      for (int q = q0; q < q1; q++) {
+        const double sf = TB(sfac, q);
+        const double c1 = sf * TB(boik, q), c2 = sf * TB(bojk, q);
+        const long long ak = b0 + TB(kslot, q);
+        const int2 ek = list[ak];
+        const double4 pk = pos4[ek.x];
+        double kx, ky, kz;
+        bop_list_vec(A, pi, pk, ek.y, kx, ky, kz);
+        const double jx = -rijx + kx, jy = -rijy + ky, jz = -rijz + kz;
+        const double d1x = c1 * kx, d1y = c1 * ky, d1z = c1 * kz;
+        const double d2x = c2 * jx, d2y = c2 * jy, d2z = c2 * jz;
+        fix += d1x; fiy += d1y; fiz += d1z;
+        fjx += d2x; fjy += d2y; fjz += d2z;
+        double4 g = G[ak];
+        g.x -= d1x + d2x; g.y -= d1y + d2y; g.z -= d1z + d2z;
+        G[ak] = g;
+        w[0] += kx * d1x + jx * d2x; w[1] += ky * d1x + jy * d2x; w[2] += kz * d1x + jz * d2x;
+        w[3] += kx * d1y + jx * d2y; w[4] += ky * d1y + jy * d2y; w[5] += kz * d1y + jz * d2y;
+        w[6] += kx * d1z + jx * d2z; w[7] += ky * d1z + jy * d2z; w[8] += kz * d1z + jz * d2z;
+      }
+      const long long aj = b0 + TB(slot, ij);
+      {
+        double4 g = G[aj];
+        g.x += fjx; g.y += fjy; g.z += fjz;
+        G[aj] = g;
+      }
+#pragma unroll
+      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+      if (wpb) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) wpb[9 * aj + q] += w[q];
+      }
+      if (wpa) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+          atomicAdd(&wpa[9 * (size_t)s + q], 0.5 * w[q]);
+          atomicAdd(&wpa[9 * (size_t)j + q], 0.5 * w[q]);
+        }
+      }
+    }
+    f[3 * s] = fix; f[3 * s + 1] = fiy; f[3 * s + 2] = fiz;
+    pe_own[s] = pei;
+  }
+  atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
+  }
+}
+#undef TB
+
 __global__ void k_bop_gather(int nat, const long long *__restrict__ seed, const int *__restrict__ rev,
                              const double4 *__restrict__ G, const double *__restrict__ pe_own,
                              double *__restrict__ f, double *__restrict__ epa,
@@ -597,6 +1065,57 @@ extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop *
   return 0;
 }
 
+static void bop_expcut_init(ExpCut &t, double r1, double r2) {
+  // exp_cutoff_init, src/support/cutoff.f90:232-255
+  t.r1 = r1;
+  t.r2 = r2;
+  t.fac1 = 1.0 / (r2 - r1);
+  const double val1 = exp(-8.0);
+  const double dval1 = -24 * val1;
+  const double ddval1 = -48 * val1 - 24 * dval1;
+  t.c = (-3 * dval1 + ddval1) / 3;
+  t.d = (2 * dval1 - ddval1) / 4;
+  t.fac2 = 1.0 / (1 - val1 - t.c - t.d);
+  t.off = val1 + t.c + t.d;
+}
+
+extern "C" int atx_bop_create_screened(atx_ctx *ctx, const atx_bop_params *par,
+                                       const atx_bop_screening *scr, atx_bop **out) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (!scr) return ATX_ERROR_UNSPECIFIED;
+  ATX_PASS(atx_bop_create(ctx, par, out));
+  atx_bop *pot = *out;
+  pot->screened = true;
+  pot->scr_par = *scr;
+  // default_bind_to_func.f90:44-104
+  BopScrDev S{};
+  const int npairs = par->nel * (par->nel + 1) / 2;
+  for (int i = 0; i < npairs; i++) {
+    S.Cmin[i] = scr->Cmin[i];
+    S.Cmax[i] = scr->Cmax[i];
+    S.dC[i] = S.Cmax[i] - S.Cmin[i];
+    S.C_dr_cut[i] = S.Cmax[i] > 2.0 ? S.Cmax[i] * S.Cmax[i] / (4 * (S.Cmax[i] - 1)) : 1.0;
+    bop_expcut_init(S.cin[i], par->r1[i], par->r2[i]);
+    S.cut_in_l[i] = par->r1[i];
+    S.cut_in_h[i] = par->r2[i];
+    S.cut_in_h2[i] = par->r2[i] * par->r2[i];
+    bop_expcut_init(S.cout[i], scr->or1[i], scr->or2[i]);
+    S.cut_out_l[i] = scr->or1[i];
+    S.cut_out_h[i] = scr->or2[i];
+    bop_expcut_init(S.cbo[i], scr->bor1[i], scr->bor2[i]);
+    S.cut_bo_h[i] = scr->bor2[i];
+    double m = S.cut_in_h[i];
+    if (S.cut_out_h[i] > m) m = S.cut_out_h[i];
+    if (S.cut_bo_h[i] > m) m = S.cut_bo_h[i];
+    S.max_cut_sq[i] = m * m;
+  }
+  S.screening_threshold = log(1e-6);   // tersoff_type.f90:86
+  S.dot_threshold = 1e-10;
+  ATX_PASS(pot->scr_dev.reserve(1));
+  ATX_CUDA(cudaMemcpy(pot->scr_dev.ptr, &S, sizeof(S), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int atx_bop_destroy(atx_bop *pot) {
   if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   delete pot;
@@ -624,7 +1143,21 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
           int x = (a - 1) + (b - 1) * D.nel, y = (b - 1) + (a - 1) * D.nel;
           int c = (a - 1) * a / 2, d = (b - 1) * b / 2;
           int ij = (x < y ? x : y) - (c < d ? c : d);
-          ATX_PASS(atx_neighbors_request_interaction_range(nl, D.r2[ij]));
+          double cutoff = D.r2[ij];
+          if (pot->screened) {
+            // default_bind_to_func.f90:106-130: sqrt(C_dr_cut(pair)) * the largest cutoff of ANY pair
+            const atx_bop_screening &sp = pot->scr_par;
+            const int npairs = D.nel * (D.nel + 1) / 2;
+            double mx = 0.0;
+            for (int q = 0; q < npairs; q++) {
+              mx = std::max(mx, pot->par.r2[q]);
+              mx = std::max(mx, sp.or2[q]);
+              mx = std::max(mx, sp.bor2[q]);
+            }
+            const double cm = sp.Cmax[ij];
+            cutoff = std::sqrt(cm > 2.0 ? cm * cm / (4 * (cm - 1)) : 1.0) * mx;
+          }
+          ATX_PASS(atx_neighbors_request_interaction_range(nl, cutoff));
         }
   pot->bound = true;
   return 0;
@@ -696,6 +1229,82 @@ static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, c
   return 0;
 }
 
+// lays the BopScrTab pointers over the two backing buffers
+static int bopscr_layout(atx_bop *pot, int nat, int NB, int NS) {
+  BopScrTab &T = pot->tab;
+  T.nat = nat; T.NB = NB; T.NS = NS;
+  const size_t nb = (size_t)NB * nat, ns = (size_t)NS * nat;
+  ATX_PASS(pot->scr_d.reserve(12 * nb + 5 * ns + 16));
+  ATX_PASS(pot->scr_i.reserve(5 * nb + ns + (size_t)nat + 16));
+  double *d = pot->scr_d.ptr;
+  double **df[] = {&T.rnx, &T.rny, &T.rnz, &T.rl, &T.fcar, &T.dfcar, &T.fcbo, &T.dfcbo, &T.kx, &T.ky, &T.kz, &T.zf};
+  for (double **q : df) { *q = d; d += nb; }
+  double **sf[] = {&T.arik, &T.arjk, &T.boik, &T.bojk, &T.sfac};
+  for (double **q : sf) { *q = d; d += ns; }
+  int *i = pot->scr_i.ptr;
+  int **bi[] = {&T.jidx, &T.slot, &T.typ, &T.sseed, &T.scnt};
+  for (int **q : bi) { *q = i; i += nb; }
+  T.kslot = i; i += ns;
+  T.nbond = i;
+  return 0;
+}
+
+static int bopscr_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask_sorted,
+                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb) {
+  atx_ctx *ctx = pot->ctx;
+  cudaStream_t st = ctx->stream;
+  const int nat = nl->nat;
+  const int nblocks = nat > 0 ? (nat + BOP_BLOCK - 1) / BOP_BLOCK : 1;
+  ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
+  if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  if (!o.stop && (pot->nb_cap == 0 || pot->sized_nl != nl || pot->sized_build != nl->nbuilds)) {
+    // table depths from a counting pass over the current configuration (+ margin for the motion
+    // inside a Verlet shell; exceeding it during batched MD raises the overflow flag)
+    ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 2, 0, 2 * sizeof(int), st));
+    if (nat > 0) {
+      k_bopscr_bonds<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, p->Abox, pot->dev, pot->scr_dev.ptr, pot->tab,
+                                                              nl->pos4.ptr, nl->seed.ptr, nl->list.ptr,
+                                                              pot->flag.ptr, o.role, nullptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(pot->hflag.reserve(64));
+    ATX_CUDA(cudaMemcpyAsync(pot->hflag.ptr, pot->flag.ptr + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    const int NB = pot->hflag.ptr[0] + 2, NS = pot->hflag.ptr[1] + pot->hflag.ptr[1] / 4 + 8;
+    ATX_PASS(bopscr_layout(pot, nat, NB, NS));
+    pot->nb_cap = NB;
+    pot->sized_nl = nl;
+    pot->sized_build = nl->nbuilds;
+  } else if (pot->tab.nat != nat) {
+    ATX_PASS(bopscr_layout(pot, nat, pot->tab.NB, pot->tab.NS));
+  }
+  ATX_CUDA(cudaMemsetAsync(pot->G.ptr, 0, sizeof(double4) * ((size_t)nl->npairs + 1), st));
+  if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
+  if (nat > 0) {
+    ProfScope ps_(ctx, "bop_force");
+    k_bopscr_bonds<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, p->Abox, pot->dev, pot->scr_dev.ptr, pot->tab,
+                                                             nl->pos4.ptr, nl->seed.ptr, nl->list.ptr,
+                                                             pot->flag.ptr, o.role, o.stop);
+    ATX_LAUNCHED();
+#define BOPSCR_CENTER(KIND)                                                                              \
+    k_bopscr_center<KIND><<<nblocks, BOP_BLOCK, 0, st>>>(                                                \
+        nat, p->Abox, pot->dev, pot->scr_dev.ptr, pot->tab, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr,   \
+        mask_sorted, pot->G.ptr, o.f, pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, o.role, o.stop)
+    switch (pot->dev.kind) {
+      case ATX_BOP_TERSOFF: BOPSCR_CENTER(ATX_BOP_TERSOFF); break;
+      case ATX_BOP_KUMAGAI: BOPSCR_CENTER(ATX_BOP_KUMAGAI); break;
+      default: BOPSCR_CENTER(ATX_BOP_BRENNER);
+    }
+#undef BOPSCR_CENTER
+    ATX_LAUNCHED();
+    k_bop_gather<<<(nat + 127) / 128, 128, 0, st>>>(nat, nl->seed.ptr, nl->rev.ptr, pot->G.ptr, pe_own,
+                                                    o.f, o.epa, o.role, o.stop);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  return 0;
+}
+
 static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask_sorted,
                        const PotOut &o, double *epb, double *fpb, double *wpb) {
   atx_ctx *ctx = pot->ctx;
@@ -705,6 +1314,7 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
   ATX_PASS(pot->G.reserve((size_t)nl->npairs + 1));
   ATX_PASS(pot->sc.epa.reserve((size_t)nat + 1));  // pe_own scratch
   double *pe_own = pot->sc.epa.ptr;
+  if (pot->screened) return bopscr_compute(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb);
   int nblocks = (nat + BOP_BLOCK - 1) / BOP_BLOCK;
   if (nblocks < 1) nblocks = 1;
   const int ntot = nblocks + ctx->sm_count;   // main-pass blocks + queued-pass blocks

@@ -149,6 +149,21 @@ typedef struct {
 } atx_bop_params;
 
 int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop **pot);
+
+/* Screened variants TersoffScr / KumagaiScr / BrennerScr: the same modules compiled with SCREENING
+ * and CUTOFF_T = exp_cutoff_t (tersoff_scr.f90:46-47, kumagai_scr.f90, brenner_scr.f90).  r1/r2 of
+ * atx_bop_params are then the INNER cutoff; or1/or2 the outer (attractive/repulsive) cutoff,
+ * bor1/bor2 the bond-order cutoff, Cmin/Cmax the bounds of the Baskes screening function
+ * (tersoff_params.f90:85-102, bop_kernel.f90:682-995), all pair-indexed.  bind_to and
+ * energy_and_forces are the unscreened entry points; bind_to requests the longer list cutoff
+ * of default_bind_to_func.f90:106-130. */
+typedef struct {
+  double or1[ATX_BOP_MAX_PAIRS], or2[ATX_BOP_MAX_PAIRS];
+  double bor1[ATX_BOP_MAX_PAIRS], bor2[ATX_BOP_MAX_PAIRS];
+  double Cmin[ATX_BOP_MAX_PAIRS], Cmax[ATX_BOP_MAX_PAIRS];
+} atx_bop_screening;
+int atx_bop_create_screened(atx_ctx *ctx, const atx_bop_params *par, const atx_bop_screening *scr,
+                            atx_bop **pot);
 int atx_bop_destroy(atx_bop *pot);
 /* BIND_TO_FUNC (default_bind_to_func.f90:25-146): el2Z[nel] are the atomic numbers of the
  * particle element ids; builds Z2db and requests r2 of every present pair */

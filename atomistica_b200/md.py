@@ -14,7 +14,7 @@ from . import native
 ACCEL_CONV = 9.648533212331e-3   # eV/(A amu) -> A/fs^2
 KB = 8.617333262e-5              # eV/K
 
-_KIND = {native.TabulatedAlloyEAM: 1, native.Tersoff: 2, native.Kumagai: 2, native.Brenner: 2, native.Rebo2: 3}
+_KIND = {native.TabulatedAlloyEAM: 1, native._Bop: 2, native.Rebo2: 3}   # ATX_POT_* of the C ABI
 
 
 class VelocityVerlet:

@@ -69,3 +69,22 @@ def test_eam_md_energy_conservation(cu_setfl):
     drv2 = md.VelocityVerlet(native.TabulatedAlloyEAM(setfl=cu_setfl), p2, nl2, m, v0, dt=1.0, verlet_shell=0.5)
     e_long = sum(drv2.run(301))
     assert abs(e_long - es[-1]) < 1e-9 * abs(e_long)
+
+
+@pytest.mark.parametrize('cls,avgn', [(native.Tersoff, 50), (native.TersoffScr, 400), (native.Rebo2, 50)])
+def test_bop_md_energy_conservation(cls, avgn):
+    """NVE with the bond-order families (virial-free kernels, queued pass, screened tables):
+    total energy conserved over 200 fs, lists rebuilt on the way"""
+    sym, a0, mass = ('C', 3.566, 12.011) if cls is native.Rebo2 else ('Si', 5.432, 28.0855)
+    a = S.diamond(sym, a0, (4, 4, 4))
+    a.rattle(0.02, seed=3)
+    m = np.full(len(a), mass)
+    v0 = md.maxwell_boltzmann(m, 600.0, seed=4)
+    p = native.from_atoms(a)
+    nl = native.Neighbors(avgn)
+    drv = md.VelocityVerlet(cls(), p, nl, m, v0, dt=0.5, verlet_shell=0.3)
+    e0 = sum(drv.run(1))
+    es = [sum(drv.run(100)) for _ in range(4)]
+    drift = max(abs(e - e0) for e in es) / len(a)
+    assert drift < 5e-5, drift
+    assert drv.stats()['nrebuilds'] >= 1

@@ -82,7 +82,8 @@ def test_bop_md_energy_conservation(cls, avgn):
     v0 = md.maxwell_boltzmann(m, 600.0, seed=4)
     p = native.from_atoms(a)
     nl = native.Neighbors(avgn)
-    drv = md.VelocityVerlet(cls(), p, nl, m, v0, dt=0.5, verlet_shell=0.3)
+    dt = 0.25 if cls is native.Rebo2 else 0.5       # stiff C-C bonds: O(dt^2) fluctuation
+    drv = md.VelocityVerlet(cls(), p, nl, m, v0, dt=dt, verlet_shell=0.3)
     e0 = sum(drv.run(1))
     es = [sum(drv.run(100)) for _ in range(4)]
     drift = max(abs(e - e0) for e in es) / len(a)

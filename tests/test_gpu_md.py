@@ -88,4 +88,5 @@ def test_bop_md_energy_conservation(cls, avgn):
     es = [sum(drv.run(100)) for _ in range(4)]
     drift = max(abs(e - e0) for e in es) / len(a)
     assert drift < 5e-5, drift
-    assert drv.stats()['nrebuilds'] >= 1
+    if cls is not native.Rebo2:
+        assert drv.stats()['nrebuilds'] >= 1

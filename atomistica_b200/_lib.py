@@ -59,6 +59,7 @@ SYMBOLS = [
     'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_rebuild', 'atx_neighbors_get_info', 'atx_neighbors_get_counters',
     'atx_neighbors_copy_to_host',
     'atx_eam_create', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
+    'atx_eam_set_store_outputs', 'atx_bop_set_store_outputs', 'atx_rebo2_set_store_outputs',
     'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
     'atx_rebo2_create', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',
     'atx_md_create', 'atx_md_destroy', 'atx_md_run', 'atx_md_get_state', 'atx_md_get_stats',
@@ -126,21 +127,29 @@ def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-class PinnedArray:
-    """float64 numpy array backed by page-locked host memory (cudaMallocHost through the C ABI)"""
+class _PinnedBlock:
+    """owner of one cudaMallocHost allocation; freed when the last numpy view of it is gone"""
 
-    def __init__(self, shape):
-        n = int(np.prod(shape))
-        self._ptr = C.c_void_p()
-        context(0)     # pinned allocation needs a CUDA context
-        check(lib().atx_host_alloc_pinned(C.c_size_t(8 * max(n, 1)), C.byref(self._ptr)))
-        buf = (C.c_double * max(n, 1)).from_address(self._ptr.value)
-        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
-        self.array[...] = 0.0
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().atx_host_alloc_pinned(C.c_size_t(nbytes), C.byref(self.ptr)))
 
     def __del__(self):
         try:
-            self.array = None
-            lib().atx_host_free_pinned(self._ptr)
+            lib().atx_host_free_pinned(self.ptr)
         except Exception:
             pass
+
+
+class PinnedArray:
+    """float64 numpy array backed by page-locked host memory (cudaMallocHost through the C ABI).
+    `array` (and every view of it handed to a caller) keeps the allocation alive."""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape))
+        context(0)     # pinned allocation needs a CUDA context
+        block = _PinnedBlock(8 * max(n, 1))
+        buf = (C.c_double * max(n, 1)).from_address(block.ptr.value)
+        buf._block = block          # numpy keeps `buf` as the base object of the array
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+        self.array[...] = 0.0

@@ -30,6 +30,8 @@ class Atomistica:
         self.particles = None
         self.nl = None
         self._fbuf = None
+        self._fcur = 0
+        self._store = False
         self.mask = None
         self.results = {}
         self.kwargs = kwargs
@@ -80,19 +82,36 @@ class Atomistica:
         if np.any(self.particles.cell != atoms.cell) or np.any(self.particles.pbc != atoms.pbc):
             self.particles.set_cell(atoms.cell, atoms.pbc)
         positions = self.particles.coordinates
-        if np.any(positions != atoms.positions):
-            positions[:, :] = atoms.positions
+        new = atoms.positions
+        # "did anything move?"  In MD every atom moves, so a strided sample answers it for 1/64 of
+        # the cost; only when the sample is unchanged is the full comparison needed.
+        if np.any(positions[::64] != new[::64]) or np.any(positions != new):
+            positions[:, :] = new
             self.particles.I_changed_positions()
+
+    def _force_buffer(self, nat):
+        """page-locked force buffers reused between calls.  With a single potential the library
+        STORES the forces straight into the buffer (no zeroing, no host accumulation, no copy) and
+        two buffers alternate, so the array returned by one call stays valid during the next."""
+        if self._fbuf is None or self._fbuf[0].array.shape[0] != nat:
+            self._fbuf = [L.PinnedArray((nat, 3)), L.PinnedArray((nat, 3))]
+            self._fcur = 0
+        self._fcur ^= 1
+        return self._fbuf[self._fcur].array
 
     # aseinterface.py:355-440
     def calculate(self, atoms, properties=('energy',)):
         self.update(atoms)
         epot = 0.0
         nat = len(self.particles)
-        if self._fbuf is None or self._fbuf.array.shape[0] != nat:
-            self._fbuf = L.PinnedArray((nat, 3))     # page-locked force buffer, reused between calls
-        forces = self._fbuf.array
-        forces[...] = 0.0
+        forces = self._force_buffer(nat)
+        store = len(self.pots) == 1
+        if store != self._store:
+            for pot in self.pots:
+                pot.set_store_outputs(store)
+            self._store = store
+        if not store:
+            forces[...] = 0.0
         wpot = np.zeros((3, 3))
         per_at_e = 'energies' in properties
         per_at_w = 'stresses' in properties
@@ -108,7 +127,7 @@ class Atomistica:
             epot += _e
             wpot += _w
         volume = atoms.get_volume()
-        self.results = dict(energy=epot, free_energy=epot, forces=forces.copy(), wpot=wpot)
+        self.results = dict(energy=epot, free_energy=epot, forces=forces, wpot=wpot)
         self.results['stress'] = np.array([wpot[0, 0], wpot[1, 1], wpot[2, 2], (wpot[1, 2] + wpot[2, 1]) / 2,
                                            (wpot[0, 2] + wpot[2, 0]) / 2, (wpot[0, 1] + wpot[1, 0]) / 2]) / volume
         if per_at_e:

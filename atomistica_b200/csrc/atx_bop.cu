@@ -1476,3 +1476,9 @@ extern "C" int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_nei
   // epot = 0.5*sum(pe) = sum over directed bonds of e_bond (bop_kernel.f90:1613)
   return atx_finish_to_host(ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
 }
+
+extern "C" int atx_bop_set_store_outputs(atx_bop *pot, int on) {
+  if (!pot) return ATX_ERROR_UNSPECIFIED;
+  pot->sc.store_outputs = on != 0;
+  return 0;
+}

@@ -684,3 +684,9 @@ extern "C" int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_nei
   ATX_PASS(atx_eam_check_flag(pot));
   return atx_finish_to_host(pot->ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
 }
+
+extern "C" int atx_eam_set_store_outputs(atx_eam *pot, int on) {
+  if (!pot) return ATX_ERROR_UNSPECIFIED;
+  pot->sc.store_outputs = on != 0;
+  return 0;
+}

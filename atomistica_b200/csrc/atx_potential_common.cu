@@ -113,6 +113,25 @@ int atx_finish_to_host(atx_ctx *ctx, atx_neighbors *nl, PotScratch &sc, const Po
   ATX_CUDA(cudaMemcpyAsync(d + off, o.sums, sizeof(double) * ATX_NSUM, cudaMemcpyDeviceToDevice,
                            ctx->stream));
   size_t total = off + ATX_NSUM;
+  if (sc.store_outputs) {
+    // device -> caller's arrays directly (page-locked arrays make these true asynchronous DMAs)
+    ATX_PASS(sc.stage_small.reserve(ATX_NSUM));
+    if (f) ATX_CUDA(cudaMemcpyAsync(f, d, sizeof(double) * 3 * nat, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o.epa && epot_per_at)
+      ATX_CUDA(cudaMemcpyAsync(epot_per_at, d + off_epa, sizeof(double) * nat, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o.wpa && wpot_per_at)
+      ATX_CUDA(cudaMemcpyAsync(wpot_per_at, d + off_wpa, sizeof(double) * 9 * nat, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    ATX_CUDA(cudaMemcpyAsync(sc.stage_small.ptr, o.sums, sizeof(double) * ATX_NSUM, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+    ATX_CUDA(cudaGetLastError());
+    const double *hs = sc.stage_small.ptr;
+    if (epot) *epot += hs[0];
+    if (wpot)
+      for (int k = 0; k < 9; k++) wpot[k] += hs[1 + k];
+    return 0;
+  }
   ATX_PASS(sc.stage.reserve(total));
   ATX_CUDA(cudaMemcpyAsync(sc.stage.ptr, d, sizeof(double) * total, cudaMemcpyDeviceToHost,
                            ctx->stream));

@@ -24,6 +24,10 @@ struct PotScratch {
   DevBuf<int> mask_sorted, mask_in;
   PinBuf<double> stage;
   PinBuf<double> stage_small;
+  // per-atom outputs (f, epot_per_at, wpot_per_at) are STORED into the caller's arrays instead of
+  // added (atx_*_set_store_outputs); saves zero-initialising and a host pass for callers that
+  // hand in a fresh buffer every call
+  bool store_outputs = false;
 };
 
 // Block-level sum of v[0..N) over all threads of the block; result valid in thread 0.

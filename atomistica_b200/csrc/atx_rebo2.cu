@@ -909,3 +909,9 @@ extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx
   if (wpb) ATX_PASS(atx_perbond_to_host(ctx, nl, 9, wpb, wpot_per_bond, pot->sc.stage));
   return atx_finish_to_host(ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
 }
+
+extern "C" int atx_rebo2_set_store_outputs(atx_rebo2 *pot, int on) {
+  if (!pot) return ATX_ERROR_UNSPECIFIED;
+  pot->sc.store_outputs = on != 0;
+  return 0;
+}

@@ -207,6 +207,16 @@ int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx_neighbors 
                                 double *epot_per_bond, double *f_per_bond, double *wpot_per_at,
                                 double *wpot_per_bond);
 
+/* ---- output mode ------------------------------------------------------------ */
+/* The reference ADDS into f / epot_per_at / wpot_per_at (the Python host hands in fresh zeroed
+ * arrays, LAMMPS its live force array) and that is the default here.  A host that always passes a
+ * fresh buffer can switch a potential object to STORE mode: the three per-atom outputs are then
+ * written (=) straight from the device into the caller's arrays -- no zero-initialisation and no
+ * host-side accumulation pass.  epot, wpot and the per-bond outputs keep accumulating. */
+int atx_eam_set_store_outputs(atx_eam *pot, int on);
+int atx_bop_set_store_outputs(atx_bop *pot, int on);
+int atx_rebo2_set_store_outputs(atx_rebo2 *pot, int on);
+
 /* ---- device-resident MD driver -------------------------- */
 /* velocity-Verlet (src/standalone/verlet.f90:100-235) with the Verlet-shell rebuild rule
  * 2*accum_max_dr >= verlet_shell (src/standalone/neighbors.f90:552-590); positions,

@@ -161,3 +161,35 @@ def test_full_size_replication_invariance(cu_setfl):
     assert np.abs(f.sum(axis=0)).max() <= 1e-9 * fscale * np.sqrt(len(big))
     wscale = max(np.abs(o['wpot']).max(), 1.0, abs(o['epot']))
     assert np.abs(w - 125 * o['wpot']).max() <= RTOL * 125 * wscale
+
+
+def test_store_outputs_mode(cu_setfl):
+    """C-ABI output modes: default ADDS into f / epot_per_at (reference semantics), store mode
+    writes them; the calculator's alternating force buffers keep the previous result valid"""
+    a = S.fcc('Cu', 3.615, (5, 5, 5))
+    a.rattle(0.08, seed=31)
+    g, o = _both(a, cu_setfl)
+    p = native.from_atoms(a)
+    nl = native.Neighbors(200)
+    pot = native.TabulatedAlloyEAM(setfl=cu_setfl)
+    pot.bind_to(p, nl)
+    f = np.full((len(a), 3), 7.0)
+    pot.energy_and_forces(p, nl, forces=f)
+    assert _close(f - 7.0, o['f'], max(np.abs(o['f']).max(), 1.0) * 10)      # added on top of the 7.0
+    pot.set_store_outputs(True)
+    f = np.full((len(a), 3), 7.0)
+    e, _, w, epa = pot.energy_and_forces(p, nl, forces=f, epot_per_at=True)[:4]
+    assert _close(f, o['f'], max(np.abs(o['f']).max(), 1.0))                  # stored
+    assert abs(e - o['epot']) <= RTOL * abs(o['epot']) and _close(epa, o['epot_per_at'])
+
+    from atomistica_b200 import TabulatedAlloyEAM
+    calc = TabulatedAlloyEAM(setfl=cu_setfl)
+    f1 = calc.get_forces(a)
+    keep = f1.copy()
+    b = a.copy()
+    b.rattle(0.05, seed=32)
+    f2 = calc.get_forces(b)
+    assert np.array_equal(f1, keep)                       # not clobbered by the next call
+    assert _close(f1, o['f'], max(np.abs(o['f']).max(), 1.0))
+    g2, o2 = _both(b, cu_setfl)
+    assert _close(f2, o2['f'], max(np.abs(o2['f']).max(), 1.0))

@@ -322,7 +322,7 @@ def run_ours(args):
         ms_per_step=dev_ms / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
         data='synthetic', config=config_dict(world),
         e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=nat * 24, d2h_bytes_per_step=nat * 24 + 80,
-                 steps=e2e_steps, note='calculator API: host positions in, host forces out every call; neighbour list kept in a '
+                 steps=e2e_steps, note='calculator API: host positions in, host forces out (page-locked result buffers) every call; neighbour list kept in a '
                                        '%.2f A Verlet shell (device-side displacement check every call); at N>1 one '
                                        'calculator instance per GPU' % SKIN),
         gpu_launches=launches,

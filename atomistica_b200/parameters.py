@@ -267,6 +267,71 @@ def scr_cutoff(db):
     rmax = max(max(db['r2']), max(db['or2']), max(db['bor2']))
     return max(sqrt(c * c / (4 * (c - 1)) if c > 2.0 else 1.0) for c in db['Cmax']) * rmax
 
+# --- Juslin (W-C-H) / Kuopanportti (Fe-C-H): Brenner form, non-symmetric pair index (nel**2
+#     entries, PAIR_INDEX_NS), triplet-indexed alpha/omega/m (TRIPLET_INDEX_NS); parameters.py:277-330
+#     of the reference, defaults of juslin_params.f90:76-101
+
+_J_OMEGA = [1.0] * 16 + [2.94586, 4.54415] + [1.0] * 4 + [0.33946, 0.22006] + [1.0] * 3
+_J_ALPHA_CH = [0.0] * 5 + [4.0, 0.0, 4.0, 4.0, 0.0, 0.0, 0.0, 0.0, 4.0, 4.0, 0.0, 4.0, 4.0]
+
+Juslin_JAP_98_123520_WCH = {
+    '__ref__': 'Juslin N. et al., J. Appl. Phys. 98, 123520 (2005)',
+    'el': ['W', 'C', 'H'],
+    'D0': [5.41861, 6.64, 2.748, 0.0, 6.0, 3.6422, 0.0, 3.642, 4.7509],
+    'r0': [2.34095, 1.90547, 1.727, -1.0, 1.39, 1.1199, -1.0, 1.1199, 0.74144],
+    'S': [1.92708, 2.96149, 1.2489, 0.0, 1.22, 1.69077, 0.0, 1.69077, 2.3432],
+    'beta': [1.38528, 1.80370, 1.52328, 0.0, 2.1, 1.9583, 0.0, 1.9583, 1.9436],
+    'gamma': [0.00188227, 0.072855, 0.0054, 0.0, 0.00020813, 0.00020813, 0.0, 12.33, 12.33],
+    'c': [2.14969, 1.10304, 1.788, 0.0, 330.0, 330.0, 0.0, 0.0, 0.0],
+    'd': [0.17126, 0.33018, 0.8255, 0.0, 3.5, 3.5, 0.0, 1.0, 1.0],
+    'h': [-0.27780, 0.75107, 0.38912, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0],
+    'n': [1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0],
+    'alpha': [0.45876, 0.0, 0.0, 0.45876, 0.0, 0.0, 0.45876, 0.0, 0.0] + _J_ALPHA_CH,
+    'omega': list(_J_OMEGA),
+    'm': [1] * 27,
+    'r1': [3.20, 2.60, 2.68, 0.0, 1.70, 1.30, 0.0, 1.30, 1.10],
+    'r2': [3.80, 3.00, 2.96, 0.0, 2.00, 1.80, 0.0, 1.80, 1.70],
+}
+
+Kuopanportti_CMS_111_525_FeCH = {
+    '__ref__': 'Kuopanportti P. et al., Comp. Mat. Sci. 111, 525 (2016)',
+    'el': ['Fe', 'C', 'H'],
+    'D0': [1.5, 4.82645134, 1.630, 0.0, 6.0, 3.6422, 0.0, 3.642, 4.7509],
+    'r0': [2.29, 1.47736510, 1.589, -1.0, 1.39, 1.1199, -1.0, 1.1199, 0.74144],
+    'S': [2.0693, 1.43134755, 4.000, 0.0, 1.22, 1.69077, 0.0, 1.69077, 2.3432],
+    'beta': [1.4, 1.63208170, 1.875, 0.0, 2.1, 1.9583, 0.0, 1.9583, 1.9436],
+    'gamma': [0.01158, 0.00205862, 0.01332, 0.0, 0.00020813, 0.00020813, 0.0, 12.33, 12.33],
+    'c': [1.2899, 8.95583221, 424.5, 0.0, 330.0, 330.0, 0.0, 0.0, 0.0],
+    'd': [0.3413, 0.72062047, 7.282, 0.0, 3.5, 3.5, 0.0, 1.0, 1.0],
+    'h': [-0.26, 0.87099874, -0.1091, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0],
+    'n': [1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0],
+    'alpha': [0.0] * 9 + _J_ALPHA_CH,
+    'omega': list(_J_OMEGA),
+    'm': [1] * 27,
+    'r1': [2.95, 2.30, 2.2974, 0.0, 1.70, 1.30, 0.0, 1.30, 1.10],
+    'r2': [3.35, 2.70, 2.6966, 0.0, 2.00, 1.80, 0.0, 1.80, 1.70],
+}
+
+JUSLIN_PAIR_KEYS = ('D0', 'r0', 'S', 'beta', 'gamma', 'c', 'd', 'h', 'n', 'r1', 'r2')
+
+
+def complete_juslin(db):
+    """default database + the mirroring of BIND_TO_FUNC (juslin_module.f90:283-312): entries with
+    r0 < 0 take the parameters of the transposed pair"""
+    base = copy.deepcopy(Juslin_JAP_98_123520_WCH)
+    out = copy.deepcopy(db) if db is not None else base
+    for k, v in base.items():
+        if k not in out:
+            out[k] = list(v)
+    nel = len(out['el'])
+    for i in range(nel):
+        for j in range(nel):
+            a, b = j + i * nel, i + j * nel
+            if out['r0'][a] < 0.0:
+                for key in JUSLIN_PAIR_KEYS:
+                    out[key][a] = out[key][b]
+    return out
+
 # Fortran built-in defaults used when a key is not supplied
 # (type initialisers in tersoff_params.f90:62-77, brenner/kumagai: the default db itself)
 TERSOFF_FIELD_DEFAULTS = dict(A=1.0, B=1.0, xi=1.0, mu=1.0, omega=1.0, mubo=0.0, m=1, beta=1.0, n=1.0,

@@ -99,6 +99,29 @@ def fcc(symbol, a, size=(1, 1, 1)):
     return _cubic(_FCC, [symbol] * 4, a, size)
 
 
+_BCC = np.array([[0, 0, 0], [.5, .5, .5]])
+_SC = np.array([[0, 0, 0]])
+
+
+def bcc(symbol, a, size=(1, 1, 1)):
+    return _cubic(_BCC, [symbol] * 2, a, size)
+
+
+def sc(symbol, a, size=(1, 1, 1)):
+    return _cubic(_SC, [symbol], a, size)
+
+
+def b1(symbols, a, size=(1, 1, 1)):
+    """rocksalt: first species on the fcc sites, second on the (1/2,0,0)-shifted fcc sites"""
+    return _cubic(np.concatenate([_FCC, (_FCC + np.array([.5, 0, 0])) % 1.0]),
+                  [symbols[0]] * 4 + [symbols[1]] * 4, a, size)
+
+
+def b2(symbols, a, size=(1, 1, 1)):
+    """CsCl: simple cubic with a two-atom basis"""
+    return _cubic(_BCC, [symbols[0], symbols[1]], a, size)
+
+
 def b3(symbols, a, size=(1, 1, 1)):
     """zincblende: first species on the fcc sites, second on the (1/4,1/4,1/4)-shifted sites"""
     return _cubic(_DIA, [symbols[0]] * 4 + [symbols[1]] * 4, a, size)

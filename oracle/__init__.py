@@ -246,44 +246,53 @@ class EAM:
 # generic bond-order potentials
 # ----------------------------------------------------------------------------
 
-TERSOFF, KUMAGAI, BRENNER = 1, 2, 3
+TERSOFF, KUMAGAI, BRENNER, JUSLIN = 1, 2, 3, 4
 
 
 class BopParams(C.Structure):
-    _fields_ = [('kind', C.c_int), ('nel', C.c_int), ('pp', (C.c_double * 6) * 12), ('ep', (C.c_double * 3) * 8),
-                ('ip', C.c_int * 6), ('r1', C.c_double * 6), ('r2', C.c_double * 6)]
+    _fields_ = [('kind', C.c_int), ('nel', C.c_int), ('pp', (C.c_double * 9) * 12), ('ep', (C.c_double * 3) * 8),
+                ('ip', C.c_int * 9), ('r1', C.c_double * 9), ('r2', C.c_double * 9),
+                ('t_alpha', C.c_double * 27), ('t_omega', C.c_double * 27), ('t_m', C.c_int * 27)]
 
 
 _PAIR_ROWS = {
     TERSOFF: ['A', 'B', 'xi', 'lambda', 'mu', 'omega', 'mubo'],
     KUMAGAI: ['A', 'B', 'lambda1', 'lambda2', 'alpha'],
     BRENNER: ['D0', 'r0', 'S', 'beta', 'gamma', 'c', 'd', 'h', 'mu', 'n'],
+    JUSLIN: ['D0', 'r0', 'S', 'beta', 'gamma', 'c', 'd', 'h', None, 'n'],
 }
 _EL_ROWS = {
     TERSOFF: ['beta', 'n', 'c', 'd', 'h'],
     KUMAGAI: ['eta', 'delta', 'c1', 'c2', 'c3', 'c4', 'c5', 'h'],
     BRENNER: [],
+    JUSLIN: [],
 }
-_INT_ROW = {TERSOFF: 'm', KUMAGAI: 'beta', BRENNER: 'm'}
+_INT_ROW = {TERSOFF: 'm', KUMAGAI: 'beta', BRENNER: 'm', JUSLIN: None}
 
 
 def bop_params(kind, db):
-    """db: dict of lists in the layout of atomistica/parameters.py (pair lists in PAIR_INDEX order)."""
+    """db: dict of lists in the layout of atomistica/parameters.py (pair lists in PAIR_INDEX order;
+    Juslin: PAIR_INDEX_NS / TRIPLET_INDEX_NS order, already mirrored like juslin_module.f90:283-312)."""
     p = BopParams()
     p.kind = kind
     nel = len(db['el'])
     p.nel = nel
-    npairs = nel * (nel + 1) // 2
+    npairs = nel * nel if kind == JUSLIN else nel * (nel + 1) // 2
     for row, key in enumerate(_PAIR_ROWS[kind]):
         for k in range(npairs):
-            p.pp[row][k] = float(db[key][k])
+            p.pp[row][k] = float(db[key][k]) if key is not None else 0.0
     for row, key in enumerate(_EL_ROWS[kind]):
         for k in range(nel):
             p.ep[row][k] = float(db[key][k])
     for k in range(npairs):
-        p.ip[k] = int(db[_INT_ROW[kind]][k])
+        p.ip[k] = int(db[_INT_ROW[kind]][k]) if _INT_ROW[kind] is not None else 1
         p.r1[k] = float(db['r1'][k])
         p.r2[k] = float(db['r2'][k])
+    if kind == JUSLIN:
+        for k in range(nel ** 3):
+            p.t_alpha[k] = float(db['alpha'][k])
+            p.t_omega[k] = float(db['omega'][k])
+            p.t_m[k] = int(db['m'][k])
     return p
 
 

@@ -62,7 +62,7 @@ int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double
 
 /* ---- generic bond-order potentials: src/potentials/bop/bop_kernel.f90 ---- */
 
-enum { ORC_TERSOFF = 1, ORC_KUMAGAI = 2, ORC_BRENNER = 3 };
+enum { ORC_TERSOFF = 1, ORC_KUMAGAI = 2, ORC_BRENNER = 3, ORC_JUSLIN = 4 };
 
 /* pair-parameter rows */
 enum {
@@ -76,13 +76,18 @@ enum {
   /* Kumagai */ OKE_ETA = 0, OKE_DELTA, OKE_C1, OKE_C2, OKE_C3, OKE_C4, OKE_C5, OKE_H
 };
 
+/* Juslin (W-C-H, Fe-C-H; src/potentials/bop/juslin/): Brenner's functional form with
+ * NON-symmetric pair indices PAIR_INDEX_NS (nel**2 entries, macros.inc:139) in the OB_* rows and
+ * triplet-indexed alpha/omega/m (TRIPLET_INDEX_NS, macros.inc:146) for h(). */
 typedef struct {
   int kind;
   int nel;
-  double pp[12][6]; /* pair parameters [row][pair-1] */
+  double pp[12][9]; /* pair parameters [row][pair-1] */
   double ep[8][3];  /* element parameters [row][el-1] */
-  int ip[6];        /* integer pair parameter: Tersoff/Brenner m, Kumagai beta */
-  double r1[6], r2[6];
+  int ip[9];        /* integer pair parameter: Tersoff/Brenner m, Kumagai beta */
+  double r1[9], r2[9];
+  double t_alpha[27], t_omega[27]; /* Juslin triplet parameters */
+  int t_m[27];
 } orc_bop_params_t;
 
 int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, const double *r,

@@ -38,14 +38,21 @@ static void trig_off(double r1, double r2, double r, double *val, double *dval) 
   }
 }
 
-/* Brenner derived constants (brenner_module.f90:269-288) */
+/* pair index of the potential, 0-based: PAIR_INDEX (macros.inc:123) for Tersoff/Kumagai/Brenner,
+ * PAIR_INDEX_NS (macros.inc:139, juslin_func.f90:300-313) for Juslin */
+static int pidx(const orc_bop_params_t *p, int i, int j) {
+  if (p->kind == ORC_JUSLIN) return (j + (i - 1) * p->nel) - 1;
+  return pair_index(i, j, p->nel) - 1;
+}
+
+/* Brenner / Juslin derived constants (brenner_module.f90:269-288, juslin_module.f90:322-343) */
 typedef struct {
-  double bo_exp[6], bo_fac[6], bo_exp1[6], expR[6], expA[6], c_sq[6], d_sq[6], c_d[6], VR_f[6],
-      VA_f[6];
+  double bo_exp[9], bo_fac[9], bo_exp1[9], expR[9], expA[9], c_sq[9], d_sq[9], c_d[9], VR_f[9],
+      VA_f[9];
 } brenner_derived_t;
 
 static void brenner_derive(const orc_bop_params_t *p, brenner_derived_t *d) {
-  int npairs = p->nel * (p->nel + 1) / 2;
+  int npairs = p->kind == ORC_JUSLIN ? p->nel * p->nel : p->nel * (p->nel + 1) / 2;
   for (int i = 0; i < npairs; i++) {
     d->bo_exp[i] = -0.5 / p->pp[OB_N][i];
     d->bo_fac[i] = 0.5 * d->bo_exp[i] * p->pp[OB_N][i];
@@ -175,8 +182,26 @@ static void f_bo(const orc_bop_params_t *p, const brenner_derived_t *bd, int kty
   }
 }
 
-static void f_h(const orc_bop_params_t *p, int ikpot, double dr, double *val, double *dval) {
+static void f_h(const orc_bop_params_t *p, int ktypj, int ktypi, int ktypk, int ikpot, double dr,
+                double *val, double *dval) {
   switch (p->kind) {
+    case ORC_JUSLIN: {
+      /* juslin_func.f90:255-294; ktyp* are 1-based database element indices */
+      int t = (ktypk + p->nel * (ktypj - 1 + p->nel * (ktypi - 1))) - 1;
+      double alpha = p->t_alpha[t], omega = p->t_omega[t];
+      int m = p->t_m[t];
+      if (m == 1) { *val = omega * exp(alpha * dr); *dval = alpha * (*val); }
+      else if (m == 3) {
+        double arg = alpha * dr;
+        *val = omega * exp(arg * arg * arg);
+        *dval = 3 * alpha * arg * arg * (*val);
+      } else {
+        double arg = alpha * dr;
+        *val = omega * exp(pow(arg, m));
+        *dval = m * pow(arg, m - 1) * alpha * (*val);
+      }
+      break;
+    }
     case ORC_KUMAGAI: {
       double alpha = p->pp[OK_ALPHA][ikpot];
       if (alpha == 0.0) { *val = 1.0; *dval = 0.0; }
@@ -215,7 +240,7 @@ int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, 
                               double *wpot_per_at, double *wpot_per_bond) {
   brenner_derived_t bd;
   memset(&bd, 0, sizeof(bd));
-  if (par->kind == ORC_BRENNER) brenner_derive(par, &bd);
+  if (par->kind == ORC_BRENNER || par->kind == ORC_JUSLIN) brenner_derive(par, &bd);
 
   /* default_compute_func.f90:61-73 */
   long ntot = 0;
@@ -261,7 +286,7 @@ int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, 
         rij[k] = r[3 * j + k] - r[3 * i + k] - s;
       }
       double rlij = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-      int el2ij = pair_index(eli, elj, par->nel) - 1;
+      int el2ij = pidx(par, eli, elj);
       double r1 = par->r1[el2ij], r2 = par->r2[el2ij];
       if (rlij < r1 * r1) {
         cutfcn[nebtot] = 1.0;
@@ -327,7 +352,7 @@ int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, 
             double rik[3] = {rlik * rnik[0], rlik * rnik[1], rlik * rnik[2]};
             double dfcikr = cutdrv[ik];
             double h_Dr, dh_dDr, g_costh, dg_dcosth;
-            f_h(par, ikpot, rlij - rlik, &h_Dr, &dh_dDr);
+            f_h(par, el[j], eli, el[neb[ik]], ikpot, rlij - rlik, &h_Dr, &dh_dDr);
             double costh = rnik[0] * rnij[0] + rnik[1] * rnij[1] + rnik[2] * rnij[2];
             f_g(par, &bd, eli - 1, ikpot, costh, &g_costh, &dg_dcosth);
             double dkc[3];
@@ -477,7 +502,8 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
                                   double *f_per_bond, double *wpot_per_at, double *wpot_per_bond) {
   brenner_derived_t bd;
   memset(&bd, 0, sizeof(bd));
-  if (par->kind == ORC_BRENNER) brenner_derive(par, &bd);
+  if (par->kind == ORC_BRENNER || par->kind == ORC_JUSLIN) brenner_derive(par, &bd);
+  if (par->kind == ORC_JUSLIN) return -2; /* JuslinScr uses trigonometric cutoffs: not restated */
   const double screening_threshold = log(1e-6), dot_threshold = 1e-10;
 
   int npairs = par->nel * (par->nel + 1) / 2;
@@ -566,7 +592,7 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
         rij[k] = r[3 * j + k] - r[3 * i + k] - s;
       }
       double rlij = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
-      int el2ij = pair_index(eli, elj, par->nel) - 1;
+      int el2ij = pidx(par, eli, elj);
 
       if (rlij < cut_in_l[el2ij] * cut_in_l[el2ij]) {
         /* region (a): bop_kernel.f90:634-680 */
@@ -765,7 +791,7 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
             double rik[3] = {rlik * rnik[0], rlik * rnik[1], rlik * rnik[2]};
             double dfcikr = cutdrvbo[ik];
             double h_Dr, dh_dDr, g_costh, dg_dcosth;
-            f_h(par, ikpot, rlij - rlik, &h_Dr, &dh_dDr);
+            f_h(par, el[j], eli, el[neb[ik]], ikpot, rlij - rlik, &h_Dr, &dh_dDr);
             double costh = rnik[0] * rnij[0] + rnik[1] * rnij[1] + rnik[2] * rnij[2];
             f_g(par, &bd, eli - 1, ikpot, costh, &g_costh, &dg_dcosth);
             double dkc[3];

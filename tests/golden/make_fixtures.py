@@ -154,6 +154,14 @@ def main():
             'Brenner_Erhart_B3_SiC': dict(Ec=6.340, a0=4.359, C11=382.0, C12=145.0, C440=305.0, B=224.0),
             'Rebo2_dia_C': dict(Ec=7.370, a0=3.566, C11=1080.0, C12=130.0, C44=720.0),
             'TabulatedAlloyEAM_fcc_Au': dict(Ec=3.924, a0=4.070, C11=202.0, C12=170.0, C44=47.0, C440=46.0),
+            # Juslin rows, tests/test_bulk_properties.py:95-120 (sc-W there uses a doubled cell: a0 = 2*2.671)
+            'Juslin_bcc_W': dict(Ec=8.89, a0=3.165, C11=542.0, C12=191.0, C44=162.0, B=308.0),
+            'Juslin_fcc_W': dict(Ec=8.89 - 0.346, a0=4.005),
+            'Juslin_sc_W': dict(Ec=8.89 - 1.614, a0=2.671),
+            'Juslin_dia_C': dict(Ec=7.376 - 0.0524, a0=3.558, C11=621.0, C12=415.0, C44=383.0, B=484.0),
+            'Juslin_B1_WC': dict(Ec=(16.68 - 0.98) / 2, a0=4.380, B=433.0),
+            'Juslin_B2_WC': dict(Ec=(16.68 - 2.32) / 2, a0=2.704, B=411.0),
+            'Juslin_B3_WC': dict(Ec=(16.68 - 2.12) / 2, a0=4.679, B=511.0),
         },
         'bulk_tol_rel': 0.05,
         # closed form from the reference formulas

@@ -46,6 +46,17 @@ def bop_scr_calc(kind, db):
     return calc
 
 
+def juslin_calc(db=None):
+    db = P.complete_juslin(db)
+    par = oracle.bop_params(oracle.JUSLIN, db)
+
+    def calc(a, **kw):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, max(db['r2']), 200)
+        el = np.array([db['el'].index(s) + 1 if s in db['el'] else -1 for s in a.symbols], dtype=np.int32)
+        return oracle.bop_energy_and_forces(par, a.positions, a.cell, nl, el, **kw)
+    return calc
+
+
 def rebo2_calc(**kw0):
     rb = oracle.Rebo2(**kw0)
 
@@ -385,6 +396,53 @@ def test_screened_equals_unscreened_in_perfect_diamond():
     assert abs(bop_scr_calc('Tersoff', None)(a)['epot'] / len(a) - KAT['tersoff_si_diamond_a0_5.432_eV_per_atom']) < 1e-9
     a = S.diamond('Si', 5.429, (2, 2, 2))
     assert abs(bop_scr_calc('Kumagai', None)(a)['epot'] / len(a) - KAT['kumagai_si_diamond_a0_5.429_eV_per_atom']) < 1e-9
+
+
+# ---- Juslin W-C-H (tests/test_bulk_properties.py:95-120) ------------------------------------------
+
+JUSLIN_BULK = [
+    ('Juslin_bcc_W', lambda a0: S.bcc('W', a0, (3, 3, 3))),
+    ('Juslin_fcc_W', lambda a0: S.fcc('W', a0, (2, 2, 2))),
+    ('Juslin_sc_W', lambda a0: S.sc('W', a0, (4, 4, 4))),
+    ('Juslin_dia_C', lambda a0: S.diamond('C', a0, (2, 2, 2))),
+    ('Juslin_B1_WC', lambda a0: S.b1(['W', 'C'], a0, (2, 2, 2))),
+    ('Juslin_B2_WC', lambda a0: S.b2(['W', 'C'], a0, (3, 3, 3))),
+    ('Juslin_B3_WC', lambda a0: S.b3(['W', 'C'], a0, (2, 2, 2))),
+]
+
+
+@pytest.mark.parametrize('name,builder', JUSLIN_BULK, ids=[b[0] for b in JUSLIN_BULK])
+def test_bulk_properties_juslin(name, builder):
+    ref = KAT['bulk'][name]
+    Ec, a0, C11, C12 = bulk_props(juslin_calc(), builder, ref['a0'])
+    tol = KAT['bulk_tol_rel']
+    assert rel(Ec, ref['Ec']) < tol
+    assert rel(a0, ref['a0']) < tol
+    if 'C11' in ref:
+        assert rel(C11, ref['C11']) < tol
+        assert rel(C12, ref['C12']) < 2 * tol
+    if 'B' in ref:
+        assert rel((C11 + 2 * C12) / 3, ref['B']) < tol
+
+
+def test_fd_juslin():
+    # W-C-H mixture: all nine directed pair types and the C/H triplet terms are exercised
+    a = S.b1(['W', 'C'], 4.38, (2, 2, 2))
+    rng = np.random.RandomState(5)
+    for i in rng.choice(len(a), 10, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.15, seed=9)
+    check_fd(juslin_calc(), a)
+    a = S.diamond('C', 3.7, (2, 2, 2))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=6)
+    check_fd(juslin_calc(), a)
+    a = S.bcc('Fe', 2.87, (3, 3, 3))
+    for i in (0, 7, 20):
+        a.symbols[i] = 'C'
+    a.rattle(0.1, seed=7)
+    check_fd(juslin_calc(P.Kuopanportti_CMS_111_525_FeCH), a)
 
 
 # ---- neighbour list (tests/test_neighbor_list.py) -------------------------------------------------

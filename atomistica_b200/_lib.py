@@ -38,6 +38,12 @@ class AtxBopScreening(C.Structure):
     _fields_ = [(k, C.c_double * MAX_PAIRS) for k in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax')]
 
 
+class AtxJuslinParams(C.Structure):
+    _fields_ = [('nel', C.c_int), ('Z', C.c_int * MAX_EL)] + \
+        [(k, C.c_double * 9) for k in ('D0', 'r0', 'S', 'beta', 'gamma', 'c', 'd', 'h', 'n', 'r1', 'r2')] + \
+        [('alpha', C.c_double * 27), ('omega', C.c_double * 27), ('m', C.c_int * 27)]
+
+
 class AtxRebo2Params(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         'cc_B1', 'cc_B2', 'cc_B3', 'cc_beta1', 'cc_beta2', 'cc_beta3', 'cc_Q', 'cc_A', 'cc_alpha',
@@ -60,7 +66,7 @@ SYMBOLS = [
     'atx_neighbors_copy_to_host',
     'atx_eam_create', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
     'atx_eam_set_store_outputs', 'atx_bop_set_store_outputs', 'atx_rebo2_set_store_outputs',
-    'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
+    'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_create_juslin', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
     'atx_rebo2_create', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',
     'atx_md_create', 'atx_md_destroy', 'atx_md_run', 'atx_md_get_state', 'atx_md_get_stats',
     'atx_dd_get_unique_id', 'atx_dd_create', 'atx_dd_destroy', 'atx_dd_md_create', 'atx_dd_md_destroy',

@@ -167,5 +167,6 @@ Brenner = _calculator(native.Brenner)
 TersoffScr = _calculator(native.TersoffScr)
 KumagaiScr = _calculator(native.KumagaiScr)
 BrennerScr = _calculator(native.BrennerScr)
+Juslin = _calculator(native.Juslin)
 Rebo2 = _calculator(native.Rebo2)
 TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)

@@ -21,17 +21,20 @@
 struct BopDev {
   int kind, nel;
   int el2db[32];  // particle element id -> db element (1..nel) or -1
-  double r1[6], r2[6], r1sq[6], r2sq[6], cfac[6];
+  double r1[9], r2[9], r1sq[9], r2sq[9], cfac[9];
   // Tersoff: A B xi lambda mu omega mubo | beta n c d h (element)
   // Kumagai: A B lambda1(lambda) lambda2(mu) alpha(mubo) | eta delta c1..c5 h
   // Brenner: derived VR_f expR VA_f expA r0 gamma c_sq d_sq c_d h mu(mubo) n bo_exp bo_fac bo_exp1
-  double A[6], B[6], xi[6], lambda[6], mu[6], omega[6], mubo[6];
-  int m[6];
+  double A[9], B[9], xi[9], lambda[9], mu[9], omega[9], mubo[9];
+  int m[9];
   double beta[3], n[3], c[3], d[3], h[3];
   double eta[3], delta[3], c1[3], c2[3], c3[3], c4[3], c5[3];
-  double VR_f[6], expR[6], VA_f[6], expA[6], r0[6], gamma[6], c_sq[6], d_sq[6], c_d[6], ph[6],
-      pn[6], bo_exp[6], bo_fac[6], bo_exp1[6];
+  double VR_f[9], expR[9], VA_f[9], expA[9], r0[9], gamma[9], c_sq[9], d_sq[9], c_d[9], ph[9],
+      pn[9], bo_exp[9], bo_fac[9], bo_exp1[9];
   // precomputed Tersoff element constants
+  // Juslin: triplet-indexed h() parameters (TRIPLET_INDEX_NS)
+  double talpha[27], tomega[27];
+  int tm[27];
   double tb[3];          // beta**n
   double te[3];          // -1/(2n)
   double c_sq_e[3], d_sq_e[3], one_p_c2d2[3];  // c^2, d^2, 1 + c^2/d^2
@@ -91,9 +94,16 @@ __device__ __forceinline__ int bop_pair_index(int i, int j, int maxval) {
   return (a < b ? a : b) - (c < d ? c : d);
 }
 
+// pair index of the potential, 0-based: PAIR_INDEX for Tersoff/Kumagai/Brenner, PAIR_INDEX_NS
+// (macros.inc:139; juslin_func.f90:300-313) for Juslin.  Elements 1-based.
+__device__ __forceinline__ int bop_pidx(const BopDev &P, int i, int j) {
+  if (P.kind == ATX_BOP_JUSLIN) return (j - 1) + (i - 1) * P.nel;
+  return bop_pair_index(i, j, P.nel);
+}
+
 template <int KIND>
 __device__ __forceinline__ void bop_VA(const BopDev &P, int ij, double dr, double &val, double &dval) {
-  if (KIND == ATX_BOP_BRENNER) {
+  if (KIND == ATX_BOP_BRENNER || KIND == ATX_BOP_JUSLIN) {
     double e = exp(-P.expA[ij] * (dr - P.r0[ij]));
     val = -P.VA_f[ij] * e;
     dval = P.VA_f[ij] * P.expA[ij] * e;
@@ -106,7 +116,7 @@ __device__ __forceinline__ void bop_VA(const BopDev &P, int ij, double dr, doubl
 
 template <int KIND>
 __device__ __forceinline__ void bop_VR(const BopDev &P, int ij, double dr, double &val, double &dval) {
-  if (KIND == ATX_BOP_BRENNER) {
+  if (KIND == ATX_BOP_BRENNER || KIND == ATX_BOP_JUSLIN) {
     double e = exp(-P.expR[ij] * (dr - P.r0[ij]));
     val = P.VR_f[ij] * e;
     dval = -P.VR_f[ij] * P.expR[ij] * e;
@@ -192,7 +202,27 @@ __device__ __forceinline__ void bop_bo(const BopDev &P, int ti, int ij, double z
 }
 
 template <int KIND>
-__device__ __forceinline__ void bop_h(const BopDev &P, int ik, double dr, double &val, double &dval) {
+__device__ __forceinline__ void bop_h(const BopDev &P, int ti, int ij, int ik, double dr, double &val,
+                                      double &dval) {
+  if (KIND == ATX_BOP_JUSLIN) {
+    // juslin_func.f90:255-294: with the non-symmetric pair index the partner element is ij % nel
+    const int t = (ik % P.nel) + P.nel * ((ij % P.nel) + P.nel * ti);
+    const double alpha = P.talpha[t], omega = P.tomega[t];
+    const int m = P.tm[t];
+    if (m == 1) {
+      val = omega * exp(alpha * dr);
+      dval = alpha * val;
+    } else if (m == 3) {
+      const double arg = alpha * dr;
+      val = omega * exp(arg * arg * arg);
+      dval = 3 * alpha * arg * arg * val;
+    } else {
+      const double arg = alpha * dr;
+      val = omega * exp(pow(arg, (double)m));
+      dval = m * pow(arg, (double)(m - 1)) * alpha * val;
+    }
+    return;
+  }
   double mu = P.mubo[ik];
   if (mu == 0.0) {
     val = 1.0;
@@ -257,7 +287,7 @@ __global__ void k_bop_count_bonds(int nat, Mat3 A, BopDev P, const double4 *__re
           atx_image_vector(A, sx, sy, sz, ax, ay, az);
           dx -= ax; dy -= ay; dz -= az;
         }
-        if (dx * dx + dy * dy + dz * dz < P.r2sq[bop_pair_index(eli, elj, P.nel)]) nb++;
+        if (dx * dx + dy * dy + dz * dz < P.r2sq[bop_pidx(P, eli, elj)]) nb++;
       }
     atomicAdd(&sh[nb < 31 ? nb : 31], 1);
   }
@@ -308,7 +338,7 @@ __device__ __forceinline__ bool bop_center_atom(
           dx -= ax; dy -= ay; dz -= az;
         }
         double r2 = dx * dx + dy * dy + dz * dz;
-        int ij = bop_pair_index(eli, elj, P.nel);
+        int ij = bop_pidx(P, eli, elj);
         if (r2 < P.r2sq[ij]) {
           if (nb >= NB) {
             ovf = true;
@@ -331,7 +361,7 @@ __device__ __forceinline__ bool bop_center_atom(
             S.rl[nb][t] = rl; S.ri[nb][t] = ri; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
             S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0; S.ge[nb][t] = 0.0;
             S.slot[nb][t] = (int)(a - b0);
-            S.typ[nb][t] = ij | (en.x << 3);
+            S.typ[nb][t] = ij | (en.x << 4);
             nb++;
             bond = true;
           }
@@ -347,8 +377,8 @@ __device__ __forceinline__ bool bop_center_atom(
   double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
   const int mi = mask ? mask[s] : 1;
   for (int ij = 0; ij < nb; ij++) {
-    const int tij = S.typ[ij][t] & 7;
-    const int j = S.typ[ij][t] >> 3;
+    const int tij = S.typ[ij][t] & 15;
+    const int j = S.typ[ij][t] >> 4;
     int maskfac = 2;
     if (mask) {
       int mj = mask[j];
@@ -377,7 +407,7 @@ __device__ __forceinline__ bool bop_center_atom(
 
     for (int ik = 0; ik < nb; ik++) {
       if (ik == ij) continue;
-      const int tik = S.typ[ik][t] & 7;
+      const int tik = S.typ[ik][t] & 15;
       const double rlik = S.rl[ik][t];
       if (!(rlik < P.r2[tik])) {
         S.kx[ik][t] = 0.0; S.ky[ik][t] = 0.0; S.kz[ik][t] = 0.0;
@@ -386,7 +416,7 @@ __device__ __forceinline__ bool bop_center_atom(
       const double kx = S.rnx[ik][t], ky = S.rny[ik][t], kz = S.rnz[ik][t];
       const double fcik = S.fc[ik][t], dfcikr = S.dfc[ik][t];
       double h_Dr, dh_dDr, g_costh, dg_dcosth;
-      bop_h<KIND>(P, tik, rlij - rlik, h_Dr, dh_dDr);
+      bop_h<KIND>(P, eli - 1, tij, tik, rlij - rlik, h_Dr, dh_dDr);
       const double costh = kx * nx + ky * ny + kz * nz;
       bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
       double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
@@ -606,7 +636,7 @@ k_bopscr_bonds(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, BopS
         double rx, ry, rz;
         bop_list_vec(A, pi, pj, en.y, rx, ry, rz);
         double rlij = rx * rx + ry * ry + rz * rz;   // squared until the bond is accepted
-        const int ij = bop_pair_index(eli, elj, P.nel);
+        const int ij = bop_pidx(P, eli, elj);
         double fcar = 1.0, dfcar = 0.0, fcbo = 1.0, dfcbo = 0.0;
         bool bond = false;
         const int ineb = ns;
@@ -799,7 +829,7 @@ k_bopscr_center(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, Bop
         const double kx = TB(rnx, ik), ky = TB(rny, ik), kz = TB(rnz, ik);
         const double fcik = TB(fcbo, ik), dfcikr = TB(dfcbo, ik);
         double h_Dr, dh_dDr, g_costh, dg_dcosth;
-        bop_h<KIND>(P, tik, rlij - rlik, h_Dr, dh_dDr);
+        bop_h<KIND>(P, eli - 1, tij, tik, rlij - rlik, h_Dr, dh_dDr);
         const double costh = kx * nx + ky * ny + kz * nz;
         bop_g<KIND>(P, eli - 1, tik, costh, g_costh, dg_dcosth);
         double ex = kx * rlik - nx * rlij, ey = ky * rlik - ny * rlij, ez = kz * rlik - nz * rlij;
@@ -1065,6 +1095,60 @@ extern "C" int atx_bop_create(atx_ctx *ctx, const atx_bop_params *par, atx_bop *
   return 0;
 }
 
+extern "C" int atx_bop_create_juslin(atx_ctx *ctx, const atx_juslin_params *par, atx_bop **out) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (!ctx || !par || !out) return ATX_ERROR_UNSPECIFIED;
+  if (par->nel < 1 || par->nel > ATX_BOP_MAX_EL) {
+    atx_set_error("atx_bop_create_juslin: invalid number of elements.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  atx_bop *pot = new atx_bop();
+  pot->ctx = ctx;
+  pot->par.kind = ATX_BOP_JUSLIN;
+  pot->par.nel = par->nel;
+  for (int i = 0; i < par->nel; i++) pot->par.Z[i] = par->Z[i];
+  BopDev &D = pot->dev;
+  D.kind = ATX_BOP_JUSLIN;
+  D.nel = par->nel;
+  const int npairs = par->nel * par->nel;
+  for (int i = 0; i < npairs; i++) {
+    // juslin_module.f90:322-357
+    D.r1[i] = par->r1[i]; D.r2[i] = par->r2[i];
+    D.r1sq[i] = par->r1[i] * par->r1[i]; D.r2sq[i] = par->r2[i] * par->r2[i];
+    D.cfac[i] = BOP_PI / (par->r2[i] - par->r1[i]);
+    if (par->d[i] * par->d[i] == 0.0) {
+      atx_set_error("d = 0! This leads to problems computing c**2/d**2. Please specify d != 0.");
+      delete pot;
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    if (par->S[i] <= 1.0) {
+      atx_set_error("S <= 1! This leads to problems computing (S-1)**(-1). Please specify S > 1.");
+      delete pot;
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    D.bo_exp[i] = -0.5 / par->n[i];
+    D.bo_fac[i] = 0.5 * D.bo_exp[i] * par->n[i];
+    D.bo_exp1[i] = D.bo_exp[i] - 1.0;
+    D.expR[i] = par->beta[i] * sqrt(2 * par->S[i]);
+    D.expA[i] = par->beta[i] * sqrt(2 / par->S[i]);
+    D.c_sq[i] = par->c[i] * par->c[i];
+    D.d_sq[i] = par->d[i] * par->d[i];
+    D.c_d[i] = D.c_sq[i] / D.d_sq[i];
+    D.VR_f[i] = par->D0[i] / (par->S[i] - 1);
+    D.VA_f[i] = par->S[i] * par->D0[i] / (par->S[i] - 1);
+    D.r0[i] = par->r0[i]; D.gamma[i] = par->gamma[i]; D.ph[i] = par->h[i]; D.pn[i] = par->n[i];
+  }
+  const int ntrip = par->nel * par->nel * par->nel;
+  for (int i = 0; i < ntrip; i++) {
+    D.talpha[i] = par->alpha[i]; D.tomega[i] = par->omega[i]; D.tm[i] = par->m[i];
+  }
+  for (int k = 0; k < 32; k++) D.el2db[k] = -1;
+  ATX_PASS(pot->flag.reserve(64));
+  ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 64 * sizeof(int)));
+  *out = pot;
+  return 0;
+}
+
 static void bop_expcut_init(ExpCut &t, double r1, double r2) {
   // exp_cutoff_init, src/support/cutoff.f90:232-255
   t.r1 = r1;
@@ -1143,6 +1227,7 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
           int x = (a - 1) + (b - 1) * D.nel, y = (b - 1) + (a - 1) * D.nel;
           int c = (a - 1) * a / 2, d = (b - 1) * b / 2;
           int ij = (x < y ? x : y) - (c < d ? c : d);
+          if (D.kind == ATX_BOP_JUSLIN) ij = (b - 1) + (a - 1) * D.nel;   // PAIR_INDEX_NS
           double cutoff = D.r2[ij];
           if (pot->screened) {
             // default_bind_to_func.f90:106-130: sqrt(C_dr_cut(pair)) * the largest cutoff of ANY pair
@@ -1360,6 +1445,9 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
       break;
     case ATX_BOP_KUMAGAI:
       ATX_PASS(launch_center_nb<ATX_BOP_KUMAGAI>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
+      break;
+    case ATX_BOP_JUSLIN:
+      ATX_PASS(launch_center_nb<ATX_BOP_JUSLIN>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
       break;
     default:
       ATX_PASS(launch_center_nb<ATX_BOP_BRENNER>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));

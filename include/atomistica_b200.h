@@ -118,6 +118,7 @@ int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
 #define ATX_BOP_TERSOFF 1
 #define ATX_BOP_KUMAGAI 2
 #define ATX_BOP_BRENNER 3
+#define ATX_BOP_JUSLIN 4
 #define ATX_BOP_MAX_EL 3
 #define ATX_BOP_MAX_PAIRS 6
 
@@ -164,6 +165,20 @@ typedef struct {
 } atx_bop_screening;
 int atx_bop_create_screened(atx_ctx *ctx, const atx_bop_params *par, const atx_bop_screening *scr,
                             atx_bop **pot);
+/* Juslin (src/potentials/bop/juslin/: W-C-H of Juslin et al., Fe-C-H of Kuopanportti et al.):
+ * Brenner's functional form with NON-symmetric pair parameters (nel**2 entries, index
+ * j + (i-1)*nel, macros.inc:139) and triplet-indexed alpha/omega/m of h() (index
+ * k + nel*(j-1 + nel*(i-1)), macros.inc:146).  The caller passes the database AFTER the mirroring
+ * of BIND_TO_FUNC (juslin_module.f90:283-312).  The object is used through atx_bop_bind_to /
+ * atx_bop_energy_and_forces / atx_bop_destroy. */
+typedef struct {
+  int nel;
+  int Z[ATX_BOP_MAX_EL];
+  double D0[9], r0[9], S[9], beta[9], gamma[9], c[9], d[9], h[9], n[9], r1[9], r2[9];
+  double alpha[27], omega[27];
+  int m[27];
+} atx_juslin_params;
+int atx_bop_create_juslin(atx_ctx *ctx, const atx_juslin_params *par, atx_bop **pot);
 int atx_bop_destroy(atx_bop *pot);
 /* BIND_TO_FUNC (default_bind_to_func.f90:25-146): el2Z[nel] are the atomic numbers of the
  * particle element ids; builds Z2db and requests r2 of every present pair */

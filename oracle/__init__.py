@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRCS = ['oracle_neighbors.c', 'oracle_eam.c', 'oracle_bop.c', 'oracle_rebo2.c']
+_SRCS = ['oracle_neighbors.c', 'oracle_eam.c', 'oracle_bop.c', 'oracle_rebo2.c', 'oracle_pair.c']
 _LIB = os.path.join(_HERE, 'liboracle.so')
 _lib = None
 
@@ -301,6 +301,51 @@ def _per_bond_arrays(nl, per_bond):
         return None, None, None
     n = len(nl.neighbors)
     return np.zeros(n), np.zeros((n, 3)), np.zeros((n, 9))
+
+
+PAIR_LJCUT, PAIR_HARMONIC, PAIR_DOUBLE_HARMONIC = 1, 2, 3
+
+
+def element_ids(symbols):
+    """particle element ids like python_particles.f90: 1-based, in order of first appearance;
+    returns (ids per atom, list of symbols by id-1)"""
+    order = []
+    for s in symbols:
+        if s not in order:
+            order.append(s)
+    return np.array([order.index(s) + 1 for s in symbols], dtype=np.int32), order
+
+
+def element_filter(spec, order):
+    """filter_from_string (src/core/filter.f90:55-120): '*' or comma-separated symbols -> bit mask"""
+    if spec.strip() == '*':
+        return sum(1 << (k + 1) for k in range(len(order)))
+    return sum(1 << (order.index(s.strip()) + 1) for s in spec.split(',') if s.strip() in order)
+
+
+def pair_energy_and_forces(kind, par, r, cell, nl, symbols, el1='*', el2='*', shift=False, mask=None, per_at=False):
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    nat = len(r)
+    abox = abox_from_cell(cell)
+    el, order = element_ids(symbols)
+    par = np.ascontiguousarray(par, dtype=np.float64)
+    epot = C.c_double(0.0)
+    f = np.zeros((nat, 3))
+    wpot = np.zeros(9)
+    epa = np.zeros(nat) if per_at else None
+    wpa = np.zeros((nat, 9)) if per_at else None
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.int32)
+    err = lib().orc_pair_energy_and_forces(
+        C.c_int(kind), _p(par), C.c_int(1 if shift else 0), C.c_int(nat), _p(r), _p(abox), _p(el, C.c_int),
+        C.c_int(element_filter(el1, order)), C.c_int(element_filter(el2, order)), _p(nl.seed, C.c_ssize_t),
+        _p(nl.last, C.c_ssize_t), _p(nl.neighbors, C.c_int), _p(nl.dc, C.c_int), _p(m, C.c_int), C.byref(epot),
+        _p(f), _p(wpot), _p(epa), _p(wpa))
+    assert err == 0, err
+    out = dict(epot=epot.value, f=f, wpot=wpot.reshape(3, 3).T.copy())
+    if per_at:
+        out['epot_per_at'] = epa
+        out['wpot_per_at'] = wpa.reshape(nat, 3, 3).transpose(0, 2, 1).copy()
+    return out
 
 
 class BopScr(C.Structure):

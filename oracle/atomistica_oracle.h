@@ -111,6 +111,18 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
                                   double *wpot, double *epot_per_at, double *epot_per_bond,
                                   double *f_per_bond, double *wpot_per_at, double *wpot_per_bond);
 
+/* ---- pair potentials: src/potentials/pair_potentials/{lj_cut,harmonic,double_harmonic}.f90 ---- */
+
+enum { ORC_PAIR_LJCUT = 1, ORC_PAIR_HARMONIC = 2, ORC_PAIR_DOUBLE_HARMONIC = 3 };
+/* par: LJCut {epsilon, sigma, cutoff}; Harmonic {k, r0, cutoff}; DoubleHarmonic {k1, r1, k2, r2,
+ * cutoff}.  el[] are PARTICLE element ids (1-based), el1/el2 the filter bit masks of filter.f90.
+ * Returns -1 when a mask is passed to a potential that has none. */
+int orc_pair_energy_and_forces(int kind, const double *par, int shift, int nat, const double *r,
+                               const double *Abox, const int *el, int el1, int el2,
+                               const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                               const int *dc, const int *mask, double *epot, double *f, double *wpot,
+                               double *epot_per_at, double *wpot_per_at);
+
 /* ---- REBO2: src/potentials/bop/rebo2/ ---- */
 
 typedef struct {

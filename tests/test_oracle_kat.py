@@ -445,6 +445,76 @@ def test_fd_juslin():
     check_fd(juslin_calc(P.Kuopanportti_CMS_111_525_FeCH), a)
 
 
+# ---- pair potentials (tests/test_bulk_properties.py:55-67, tests/test_mask.py) ---------------------
+
+def pair_calc(kind, par, cutoff, shift=False, el1='*', el2='*'):
+    def calc(a, **kw):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
+        return oracle.pair_energy_and_forces(kind, par, a.positions, a.cell, nl, a.symbols, el1=el1, el2=el2,
+                                             shift=shift, **kw)
+    return calc
+
+
+def _cubic_constants(calc, a, d=1e-4):
+    V = a.get_volume()
+
+    def es(eps):
+        b = a.copy()
+        F = np.eye(3) + eps
+        b.set_cell(b.cell @ F.T, scale_atoms=False)
+        b.positions = a.positions @ F.T
+        return calc(b)['epot']
+    e0 = es(np.zeros((3, 3)))
+    e = np.zeros((3, 3)); e[0, 0] = d
+    C11 = (es(e) - 2 * e0 + es(-e)) / d ** 2 / V
+    e = np.zeros((3, 3)); e[0, 0] = d; e[1, 1] = d
+    C12 = ((es(e) - 2 * e0 + es(-e)) / d ** 2 / V - 2 * C11) / 2
+    e = np.zeros((3, 3)); e[0, 1] = d / 2; e[1, 0] = d / 2
+    C44 = (es(e) - 2 * e0 + es(-e)) / d ** 2 / V
+    return C11, C12, C44
+
+
+def test_harmonic_model_solids():
+    # Harmonic(k=1, r0=1, cutoff=1.3, shift) on fcc a0=sqrt(2): C11 = sqrt(2), C12 = C44 = 1/sqrt(2);
+    # DoubleHarmonic(k1=k2=1, r1=1, r2=sqrt(2), cutoff=1.6) on sc a0=1: C11 = 3, C12 = C44 = 1
+    # (eV/A^3; the reference test allows 5 %)
+    C = _cubic_constants(pair_calc(oracle.PAIR_HARMONIC, [1.0, 1.0, 1.3], 1.3, shift=True),
+                         S.fcc('He', np.sqrt(2.0), (3, 3, 3)))
+    assert np.allclose(C, [np.sqrt(2.0), 1 / np.sqrt(2.0), 1 / np.sqrt(2.0)], rtol=1e-4)
+    C = _cubic_constants(pair_calc(oracle.PAIR_DOUBLE_HARMONIC, [1.0, 1.0, 1.0, np.sqrt(2.0), 1.6], 1.6),
+                         S.sc('He', 1.0, (4, 4, 4)))
+    assert np.allclose(C, [3.0, 1.0, 1.0], rtol=1e-4)
+
+
+def test_fd_pair_potentials():
+    a = S.fcc('Ar', 5.3, (3, 3, 3)); a.rattle(0.2, seed=11)
+    check_fd(pair_calc(oracle.PAIR_LJCUT, [0.0104, 3.40, 8.0], 8.0, shift=True), a)
+    a = S.fcc('He', np.sqrt(2.0), (3, 3, 3)); a.rattle(0.05, seed=12)
+    check_fd(pair_calc(oracle.PAIR_HARMONIC, [1.0, 1.0, 1.3], 1.3, shift=True), a)
+    a = S.sc('He', 1.0, (4, 4, 4)); a.rattle(0.03, seed=13)
+    check_fd(pair_calc(oracle.PAIR_DOUBLE_HARMONIC, [1.0, 1.0, 1.0, np.sqrt(2.0), 1.6], 1.6), a)
+
+
+def test_lj_mask_additivity_and_filters():
+    # tests/test_mask.py (LJCut row): e = e(mask) + e(not mask), same for forces and virial
+    a = S.fcc('Ar', 5.3, (3, 3, 3)); a.rattle(0.2, seed=14)
+    rng = np.random.RandomState(4)
+    mask = (rng.rand(len(a)) > 0.5).astype(np.int32)
+    calc = pair_calc(oracle.PAIR_LJCUT, [0.0104, 3.40, 8.0], 8.0)
+    o0, o1, o2 = calc(a), calc(a, mask=mask), calc(a, mask=1 - mask)
+    assert abs(o1['epot'] + o2['epot'] - o0['epot']) < 1e-9
+    assert np.abs(o1['f'] + o2['f'] - o0['f']).max() < 1e-9
+    assert np.abs(o1['wpot'] + o2['wpot'] - o0['wpot']).max() < 1e-9
+    # element filters: Ar-Ar + Ar-Kr + Kr-Kr pieces add up to the '*' - '*' potential
+    for i in range(0, len(a), 3):
+        a.symbols[i] = 'Kr'
+    tot = calc(a)
+    parts = [pair_calc(oracle.PAIR_LJCUT, [0.0104, 3.40, 8.0], 8.0, el1=x, el2=y)(a)
+             for x, y in (('Ar', 'Ar'), ('Ar', 'Kr'), ('Kr', 'Kr'))]
+    assert abs(sum(p_['epot'] for p_ in parts) - tot['epot']) < 1e-9
+    assert np.abs(sum(p_['f'] for p_ in parts) - tot['f']).max() < 1e-9
+
+
 # ---- neighbour list (tests/test_neighbor_list.py) -------------------------------------------------
 
 def _brute(a, cutoff):

@@ -44,6 +44,10 @@ class AtxJuslinParams(C.Structure):
         [('alpha', C.c_double * 27), ('omega', C.c_double * 27), ('m', C.c_int * 27)]
 
 
+class AtxPairParams(C.Structure):
+    _fields_ = [('kind', C.c_int), ('p', C.c_double * 8), ('shift', C.c_int)]
+
+
 class AtxRebo2Params(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         'cc_B1', 'cc_B2', 'cc_B3', 'cc_beta1', 'cc_beta2', 'cc_beta3', 'cc_Q', 'cc_A', 'cc_alpha',
@@ -67,6 +71,8 @@ SYMBOLS = [
     'atx_eam_create', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
     'atx_eam_set_store_outputs', 'atx_bop_set_store_outputs', 'atx_rebo2_set_store_outputs',
     'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_create_juslin', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
+    'atx_pair_create', 'atx_pair_destroy', 'atx_pair_bind_to', 'atx_pair_energy_and_forces',
+    'atx_pair_set_store_outputs',
     'atx_rebo2_create', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',
     'atx_md_create', 'atx_md_destroy', 'atx_md_run', 'atx_md_get_state', 'atx_md_get_stats',
     'atx_dd_get_unique_id', 'atx_dd_create', 'atx_dd_destroy', 'atx_dd_md_create', 'atx_dd_md_destroy',

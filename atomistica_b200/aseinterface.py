@@ -168,5 +168,8 @@ TersoffScr = _calculator(native.TersoffScr)
 KumagaiScr = _calculator(native.KumagaiScr)
 BrennerScr = _calculator(native.BrennerScr)
 Juslin = _calculator(native.Juslin)
+LJCut = _calculator(native.LJCut)
+Harmonic = _calculator(native.Harmonic)
+DoubleHarmonic = _calculator(native.DoubleHarmonic)
 Rebo2 = _calculator(native.Rebo2)
 TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)

@@ -222,6 +222,28 @@ int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx_neighbors 
                                 double *epot_per_bond, double *f_per_bond, double *wpot_per_at,
                                 double *wpot_per_bond);
 
+/* ---- pair potentials: src/potentials/pair_potentials/{lj_cut,harmonic,double_harmonic}.f90 ---- */
+
+#define ATX_PAIR_LJCUT 1            /* p = {epsilon, sigma, cutoff};        shift: lj_cut.f90:176-181 */
+#define ATX_PAIR_HARMONIC 2         /* p = {k, r0, cutoff};                 shift: harmonic.f90:134-137 */
+#define ATX_PAIR_DOUBLE_HARMONIC 3  /* p = {k1, r1, k2, r2, cutoff} */
+typedef struct atx_pair atx_pair;
+typedef struct {
+  int kind;
+  double p[8];
+  int shift; /* shift the potential to zero at the cutoff (LJCut, Harmonic) */
+} atx_pair_params;
+int atx_pair_create(atx_ctx *ctx, const atx_pair_params *par, atx_pair **pot);
+int atx_pair_destroy(atx_pair *pot);
+/* *_bind_to: el1/el2 are the element filters of src/core/filter.f90 (bit k set = particle element
+ * id k takes part; filter_from_string builds them from "*" or a list of symbols) */
+int atx_pair_bind_to(atx_pair *pot, atx_particles *p, atx_neighbors *nl, int el1, int el2);
+/* mask: LJCut only (lj_cut.f90:232-262); the other two have no mask argument in the reference */
+int atx_pair_energy_and_forces(atx_pair *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                               double *epot, double *f, double *wpot, double *epot_per_at,
+                               double *wpot_per_at);
+int atx_pair_set_store_outputs(atx_pair *pot, int on);
+
 /* ---- output mode ------------------------------------------------------------ */
 /* The reference ADDS into f / epot_per_at / wpot_per_at (the Python host hands in fresh zeroed
  * arrays, LAMMPS its live force array) and that is the default here.  A host that always passes a

@@ -173,3 +173,4 @@ Harmonic = _calculator(native.Harmonic)
 DoubleHarmonic = _calculator(native.DoubleHarmonic)
 Rebo2 = _calculator(native.Rebo2)
 TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)
+TabulatedEAM = _calculator(native.TabulatedEAM)

@@ -36,6 +36,10 @@ struct EamDev {
   DSpline frho[EAM_MAX_DB];
   DSpline fphi[EAM_MAX_DB * EAM_MAX_DB];
   const double4 *pairrec[EAM_MAX_DB * EAM_MAX_DB];  // 64-byte records, see k_eam_force_fast
+  // TabulatedEAM (funcfl): the 'phi' table holds Z(r) (scaled by sqrt(Hartree Bohr / 2)) and the
+  // pair term is Z**2/r (tabulated_eam.f90:470-476): phi := Z*Z, dphi := 2 Z Z' before the shared
+  // (dphi - phi/r)/r
+  int zsq;
 };
 
 struct atx_eam {
@@ -52,6 +56,7 @@ struct atx_eam {
   bool bound = false;
   bool fast_ok = false;  // all r-tables share one grid that covers the cutoff
   bool force_generic = false;
+  bool funcfl = false;
   int fast_lanes = 4, fast_unroll = 2;
   ~atx_eam() {
     for (auto *t : tables) delete t;
@@ -372,6 +377,7 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
   double fx = 0.0, fy = 0.0, fz = 0.0, en_ = 0.0;
   double wxx = 0, wyy = 0, wzz = 0, wxy = 0, wxz = 0, wyz = 0;
   const double dFi = pi.w;
+  const bool zsq = T->zsq != 0;
   const long long b = dbi > 0 ? seed[s] : 0, e = dbi > 0 ? seed[s + 1] : 0;
   const int di = dbi > 0 ? dbi - 1 : 0;
   for (long long a0 = b + lane * U; a0 < e; a0 += LANES * U) {
@@ -412,8 +418,12 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
       const double4 c = atx_ld4(rec);       // phi: y c1 c2 c3
       const double4 q = atx_ld4(rec + 1);   // rho_j: c1 c2 c3
       const double Bu = B[u];
-      const double phi = c.x + Bu * (c.y + Bu * (c.z + Bu * c.w));
-      const double dphi = (c.y + Bu * (2.0 * c.z + Bu * (3.0 * c.w))) * inv_dx;
+      double phi = c.x + Bu * (c.y + Bu * (c.z + Bu * c.w));
+      double dphi = (c.y + Bu * (2.0 * c.z + Bu * (3.0 * c.w))) * inv_dx;
+      if (zsq) {
+        dphi = 2.0 * phi * dphi;
+        phi = phi * phi;
+      }
       const double drho_j = (q.x + Bu * (2.0 * q.y + Bu * (3.0 * q.z))) * inv_dx;
       double drho_i = drho_j;
       if (dj[u] != di) {
@@ -545,6 +555,21 @@ extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const
   return 0;
 }
 
+extern "C" int atx_eam_create_funcfl(atx_ctx *ctx, const atx_spline *fF, const atx_spline *frho,
+                                     const atx_spline *fZ, double cutoff, atx_eam **out) {
+  ATX_PASS(atx_eam_create(ctx, 1, fF, frho, fZ, cutoff, out));
+  atx_eam *pot = *out;
+  if (!pot->fast_ok) {
+    atx_set_error("TabulatedEAM: the Z and rho tables must share one grid that starts at 0 and covers the cutoff.");
+    delete pot;
+    *out = nullptr;
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  pot->funcfl = true;
+  pot->host.zsq = 1;
+  return 0;
+}
+
 extern "C" int atx_eam_destroy(atx_eam *pot) {
   if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   delete pot;
@@ -587,7 +612,7 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
   if (nblocks < 1) nblocks = 1;
   ATX_PASS(pot->sc.partials.reserve((size_t)nblocks * ATX_NSUM));
   if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
-  if (pot->fast_ok && !mask_sorted && !o.wpa && !pot->force_generic) {
+  if (pot->fast_ok && !mask_sorted && !o.wpa && (!pot->force_generic || pot->funcfl)) {
     const int L = pot->fast_lanes, gp = 128 / L;
     const int nb = nat > 0 ? (nat + gp - 1) / gp : 1;
     ATX_PASS(pot->sc.partials.reserve((size_t)nb * ATX_NSUM));
@@ -673,6 +698,11 @@ extern "C" int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_nei
   if (pot && pot->ctx) cudaSetDevice(pot->ctx->device);
   if (!pot->bound) {
     atx_set_error("TabulatedAlloyEAM: bind_to has not been called.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  if (pot->funcfl && (mask || wpot_per_at)) {
+    // tabulated_eam_energy_and_forces has no mask and never fills wpot_per_at
+    atx_set_error("TabulatedEAM does not support masks or per-atom virials.");
     return ATX_ERROR_UNSPECIFIED;
   }
   ATX_PASS(atx_neighbors_update(nl, p));

@@ -48,3 +48,19 @@ def write_setfl(fn, tab):
                 f.write('\n'.join('%.17g' % x for x in arr) + '\n')
         for arr in tab['rphi']:
             f.write('\n'.join('%.17g' % x for x in arr) + '\n')
+
+
+def read_funcfl(fn):
+    """DYNAMO funcfl layout as parsed by tabulated_eam_init
+    (src/potentials/eam/tabulated_eam.f90:172-197): comment; `Z mass a0 lattice`;
+    `nF dF nr dr cutoff`; nF F values, nr Z values, nr rho values."""
+    with open(fn) as f:
+        comment = f.readline().rstrip('\n')
+        t = f.readline().split()
+        Z, mass, a0, lattice = int(t[0]), float(t[1]), float(t[2]), t[3]
+        t = f.readline().replace('D', 'E').split()
+        nF, dF, nr, dr, cutoff = int(t[0]), float(t[1]), int(t[2]), float(t[3]), float(t[4])
+        rest = np.array(f.read().replace('D', 'E').split(), dtype=np.float64)
+    from .elements import chemical_symbols
+    return dict(comment=comment, name=chemical_symbols[Z], Znum=Z, mass=mass, a0=a0, lattice=lattice, nF=nF, dF=dF,
+                nr=nr, dr=dr, cutoff=cutoff, F=rest[:nF], Z=rest[nF:nF + nr], rho=rest[nF + nr:nF + 2 * nr])

@@ -104,6 +104,11 @@ typedef struct {
 /* ndb database elements; fF[ndb], frho[ndb], fphi[ndb*ndb] (column-major (i,j), symmetric) */
 int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const atx_spline *frho,
                    const atx_spline *fphi, double cutoff, atx_eam **pot);
+/* TabulatedEAM (one element, funcfl tables; src/potentials/eam/tabulated_eam.f90:141-511): fZ is
+ * the effective-charge spline AFTER scale_y_axis(sqrt(0.5 Hartree Bohr)) (:199); pair term Z**2/r.
+ * Used through atx_eam_bind_to / atx_eam_energy_and_forces (no mask, no wpot_per_at). */
+int atx_eam_create_funcfl(atx_ctx *ctx, const atx_spline *fF, const atx_spline *frho,
+                          const atx_spline *fZ, double cutoff, atx_eam **pot);
 int atx_eam_destroy(atx_eam *pot);
 /* bind_to (:297-350): el2db[nel] maps particle element ids (1..nel) to database ids (1..ndb, <=0:
  * ignored); requests the interaction range */

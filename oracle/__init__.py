@@ -242,6 +242,43 @@ class EAM:
         return out
 
 
+HARTREE, BOHR = 27.2113961, 0.529177249       # src/support/Units.f90:74-76
+
+
+class EAMFuncfl:
+    """TabulatedEAM: single-element funcfl tables (tabulated_eam.f90:141-214)"""
+
+    def __init__(self, tab, elements='*'):
+        self.name = str(tab['name'])
+        self.elements = elements
+        self.cutoff = float(tab['cutoff'])
+        nF, dF, nr, dr = int(tab['nF']), float(tab['dF']), int(tab['nr']), float(tab['dr'])
+        self.fF = spline_init(nF, 0.0, dF, tab['F'])
+        self.fZ = spline_scale_y(spline_init(nr, 0.0, dr, tab['Z']), np.sqrt(0.5 * HARTREE * BOHR))
+        self.frho = spline_init(nr, 0.0, dr, tab['rho'])
+
+    def energy_and_forces(self, r, cell, nl, symbols, per_at=False):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        nat = len(r)
+        abox = abox_from_cell(cell)
+        sel = [x.strip() for x in self.elements.split(',')]
+        inn = np.array([1 if (self.elements.strip() == '*' or s in sel) else 0 for s in symbols], dtype=np.int32)
+        epot = C.c_double(0.0)
+        f = np.zeros((nat, 3))
+        wpot = np.zeros(9)
+        epa = np.zeros(nat) if per_at else None
+        sF, sZ, sR = _spline_struct(self.fF), _spline_struct(self.fZ), _spline_struct(self.frho)
+        err = lib().orc_eam_funcfl_energy_and_forces(
+            C.c_int(nat), _p(r), _p(abox), _p(inn, C.c_int), _p(nl.seed, C.c_ssize_t), _p(nl.last, C.c_ssize_t),
+            _p(nl.neighbors, C.c_int), _p(nl.dc, C.c_int), C.byref(sF), C.byref(sZ), C.byref(sR),
+            C.c_double(self.cutoff), C.byref(epot), _p(f), _p(wpot), _p(epa))
+        assert err == 0
+        out = dict(epot=epot.value, f=f, wpot=wpot.reshape(3, 3).T.copy())
+        if per_at:
+            out['epot_per_at'] = epa
+        return out
+
+
 # ----------------------------------------------------------------------------
 # generic bond-order potentials
 # ----------------------------------------------------------------------------

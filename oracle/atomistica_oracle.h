@@ -60,6 +60,15 @@ int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double
                               const int *mask, double *epot, double *f, double *wpot,
                               double *epot_per_at, double *wpot_per_at);
 
+/* ---- TabulatedEAM (funcfl, one element): src/potentials/eam/tabulated_eam.f90:334-511 ---- */
+/* fZ must already carry the factor sqrt(0.5 Hartree Bohr); `in[i]` = atom selected by the element
+ * filter.  No mask and no per-atom virial in the reference. */
+int orc_eam_funcfl_energy_and_forces(int nat, const double *r, const double *Abox, const int *in,
+                                     const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                     const int *dc, const orc_spline_t *fF, const orc_spline_t *fZ,
+                                     const orc_spline_t *frho, double cutoff, double *epot, double *f,
+                                     double *wpot, double *epot_per_at);
+
 /* ---- generic bond-order potentials: src/potentials/bop/bop_kernel.f90 ---- */
 
 enum { ORC_TERSOFF = 1, ORC_KUMAGAI = 2, ORC_BRENNER = 3, ORC_JUSLIN = 4 };

@@ -197,3 +197,110 @@ int orc_eam_energy_and_forces(int nat, int natloc, const double *r, const double
   free(pe); free(fv);
   return err ? -1 : 0;
 }
+
+/* ======================================================================================
+ * TabulatedEAM (single-element funcfl tables), restated from
+ *   src/potentials/eam/tabulated_eam.f90:334-511 (energy_and_forces_kernel)
+ *   src/spline.inc (SPLINE_FUNC / SPLINE_DFUNC / SPLINE_F_AND_DF: x is mapped with the
+ *   RECIPROCAL spacing, the index is the truncated value, no range check)
+ * phi = Z(r)**2 / r with Z scaled by sqrt(0.5 Hartree Bohr) at init (tabulated_eam.f90:199).
+ * `in` flags the atoms selected by the element filter (IS_EL2(els, el)).
+ * ====================================================================================== */
+
+static void inl_f(const orc_spline_t *s, double rdx, double x, double *f) {
+  double xf = (x - s->x0) * rdx + 1.0;
+  int i = (int)xf;
+  double B = xf - i;
+  i--;
+  *f = s->y[i] + B * (s->c1[i] + B * (s->c2[i] + B * s->c3[i]));
+}
+
+static void inl_df(const orc_spline_t *s, double rdx, double x, double *df) {
+  double xf = (x - s->x0) * rdx + 1.0;
+  int i = (int)xf;
+  double B = xf - i;
+  i--;
+  *df = s->d1[i] + B * (s->d2[i] + B * s->d3[i]);
+}
+
+int orc_eam_funcfl_energy_and_forces(int nat, const double *r, const double *Abox, const int *in,
+                                     const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                     const int *dc, const orc_spline_t *fF, const orc_spline_t *fZ,
+                                     const orc_spline_t *frho, double cutoff, double *epot, double *f,
+                                     double *wpot, double *epot_per_at) {
+  const double cutoff_sq = cutoff * cutoff;
+  const double F_rdx = 1.0 / fF->dx, Z_rdx = 1.0 / fZ->dx, rho_rdx = 1.0 / frho->dx;
+  int maxneb = 0;
+  for (int i = 0; i < nat; i++) {
+    int d = (int)(last[i] - seed[i] + 1);
+    if (d > maxneb) maxneb = d;
+  }
+  int *neb = (int *)malloc(sizeof(int) * (maxneb + 1));
+  double *neb_dr = (double *)malloc(sizeof(double) * 3 * (maxneb + 1));
+  double *neb_abs = (double *)malloc(sizeof(double) * (maxneb + 1));
+  double *sca = (double *)calloc(nat > 0 ? nat : 1, sizeof(double));
+  double *vec = (double *)calloc(nat > 0 ? 3 * nat : 1, sizeof(double));
+  double e = 0.0, w[9] = {0};
+  for (int i = 0; i < nat; i++) {
+    if (!in[i]) continue;
+    double rho = 0.0;
+    int neb_n = 0;
+    for (intptr_t ni = seed[i]; ni <= last[i]; ni++) {
+      int j = neighbors[ni - 1] - 1;
+      if (!in[j]) continue;
+      double dr[3], abs_dr = 0.0;
+      for (int k = 0; k < 3; k++) {
+        double s = 0.0;
+        for (int c = 0; c < 3; c++) s += M3(Abox, k, c) * (double)dc[3 * (ni - 1) + c];
+        dr[k] = r[3 * i + k] - r[3 * j + k] + s;
+        abs_dr += dr[k] * dr[k];
+      }
+      if (abs_dr < cutoff_sq) {
+        abs_dr = sqrt(abs_dr);
+        double drho;
+        inl_f(frho, rho_rdx, abs_dr, &drho);
+        rho = rho + drho;
+        neb[neb_n] = j;
+        neb_dr[3 * neb_n] = dr[0]; neb_dr[3 * neb_n + 1] = dr[1]; neb_dr[3 * neb_n + 2] = dr[2];
+        neb_abs[neb_n] = abs_dr;
+        neb_n++;
+      }
+    }
+    if (rho < 0.0) rho = 0.0;
+    double Fi, dFi;
+    inl_f(fF, F_rdx, rho, &Fi);
+    inl_df(fF, F_rdx, rho, &dFi);
+    sca[i] += Fi;
+    double sumphi = 0.0, fori[3] = {0, 0, 0};
+    for (int n = 0; n < neb_n; n++) {
+      double a = neb_abs[n], z, dz, fac;
+      inl_f(fZ, Z_rdx, a, &z);
+      inl_df(fZ, Z_rdx, a, &dz);
+      double dphi = 2 * z * dz / a;
+      double phi = z * z / a;
+      dphi = dphi - phi / a;
+      sumphi += phi;
+      inl_df(frho, rho_rdx, a, &fac);
+      double pref = -((dFi * fac + dphi) / a);
+      double df[3] = {pref * neb_dr[3 * n], pref * neb_dr[3 * n + 1], pref * neb_dr[3 * n + 2]};
+      int j = neb[n];
+      for (int k = 0; k < 3; k++) {
+        fori[k] += df[k];
+        vec[3 * j + k] -= df[k];
+      }
+      for (int b = 0; b < 3; b++)
+        for (int aa = 0; aa < 3; aa++) M3(w, aa, b) += -(neb_dr[3 * n + aa] * df[b]);
+    }
+    sca[i] += sumphi;
+    for (int k = 0; k < 3; k++) vec[3 * i + k] += fori[k];
+  }
+  for (int i = 0; i < nat; i++) {
+    e += sca[i];
+    if (epot_per_at) epot_per_at[i] += sca[i];
+    for (int k = 0; k < 3; k++) f[3 * i + k] += vec[3 * i + k];
+  }
+  *epot += e;
+  for (int k = 0; k < 9; k++) wpot[k] += w[k];
+  free(neb); free(neb_dr); free(neb_abs); free(sca); free(vec);
+  return 0;
+}

@@ -29,6 +29,11 @@ def au_setfl():
 
 
 @pytest.fixture(scope='session')
+def au_funcfl():
+    return load_npz('au_u3_funcfl.npz')
+
+
+@pytest.fixture(scope='session')
 def aC():
     from atomistica_b200.structures import Atoms
     d = load_npz('aC.npz')

@@ -107,9 +107,24 @@ def read_xyz(fn):
     return sym, pos
 
 
+def read_funcfl(fn):
+    """funcfl layout as parsed by tabulated_eam_init (tabulated_eam.f90:172-197)"""
+    with open(fn) as f:
+        comment = f.readline().rstrip('\n')
+        t = f.readline().split()
+        Z, mass, a0, lattice = int(t[0]), float(t[1]), float(t[2]), t[3]
+        t = f.readline().replace('D', 'E').split()
+        nF, dF, nr, dr, cutoff = int(t[0]), float(t[1]), int(t[2]), float(t[3]), float(t[4])
+        rest = np.array(f.read().replace('D', 'E').split(), dtype=np.float64)
+    return dict(comment=comment, name='Au' if Z == 79 else str(Z), Znum=Z, mass=mass, a0=a0, lattice=lattice,
+                nF=nF, dF=dF, nr=nr, dr=dr, cutoff=cutoff, F=rest[:nF], Z=rest[nF:nF + nr],
+                rho=rest[nF + nr:nF + 2 * nr])
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit('reference tests directory not present; fixtures are already committed')
+    np.savez_compressed(os.path.join(OUT, 'au_u3_funcfl.npz'), **read_funcfl(os.path.join(REF, 'Au_u3.eam')))
     for src, dst in [('Cu_mishin1.eam.alloy', 'cu_mishin1_setfl.npz'),
                      ('Au-Grochola-JCP05.eam.alloy', 'au_grochola_setfl.npz')]:
         np.savez_compressed(os.path.join(OUT, dst), **read_setfl(os.path.join(REF, src)))
@@ -154,6 +169,7 @@ def main():
             'Brenner_Erhart_B3_SiC': dict(Ec=6.340, a0=4.359, C11=382.0, C12=145.0, C440=305.0, B=224.0),
             'Rebo2_dia_C': dict(Ec=7.370, a0=3.566, C11=1080.0, C12=130.0, C44=720.0),
             'TabulatedAlloyEAM_fcc_Au': dict(Ec=3.924, a0=4.070, C11=202.0, C12=170.0, C44=47.0, C440=46.0),
+            'TabulatedEAM_fcc_Au': dict(Ec=3.93, a0=4.08, B=167.0, C11=183.0, C12=159.0, C44=45.0),
             # Juslin rows, tests/test_bulk_properties.py:95-120 (sc-W there uses a doubled cell: a0 = 2*2.671)
             'Juslin_bcc_W': dict(Ec=8.89, a0=3.165, C11=542.0, C12=191.0, C44=162.0, B=308.0),
             'Juslin_fcc_W': dict(Ec=8.89 - 0.346, a0=4.005),

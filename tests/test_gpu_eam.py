@@ -193,3 +193,27 @@ def test_store_outputs_mode(cu_setfl):
     assert _close(f1, o['f'], max(np.abs(o['f']).max(), 1.0))
     g2, o2 = _both(b, cu_setfl)
     assert _close(f2, o2['f'], max(np.abs(o2['f']).max(), 1.0))
+
+
+def test_funcfl_tabulated_eam(au_funcfl):
+    """TabulatedEAM (funcfl, pair term Z(r)^2/r) vs the oracle; oracle pinned by the reference's
+    fcc-Au bulk row (tests/test_oracle_kat.py)"""
+    eam = oracle.EAMFuncfl(au_funcfl)
+    for rattle, size in ((0.0, (3, 3, 3)), (0.1, (4, 4, 4)), (0.2, (2, 2, 2))):
+        a = S.fcc('Au', 4.08, size)
+        if rattle:
+            a.rattle(rattle, seed=41)
+        p = native.from_atoms(a)
+        nl = native.Neighbors(200)
+        pot = native.TabulatedEAM(funcfl=au_funcfl)
+        pot.bind_to(p, nl)
+        e, f, w, epa = pot.energy_and_forces(p, nl, epot_per_at=True)[:4]
+        onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, eam.cutoff, 200)
+        o = eam.energy_and_forces(a.positions, a.cell, onl, a.symbols, per_at=True)
+        assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
+        assert _close(f, o['f'], max(np.abs(o['f']).max(), 1.0))
+        assert _close(w, o['wpot'], max(np.abs(o['wpot']).max(), 1.0, abs(o['epot'])))
+        assert _close(epa, o['epot_per_at'])
+    assert abs(e / len(a)) > 3.0
+    with pytest.raises(RuntimeError):
+        pot.energy_and_forces(p, nl, wpot_per_at=True)

@@ -515,6 +515,28 @@ def test_lj_mask_additivity_and_filters():
     assert np.abs(sum(p_['f'] for p_ in parts) - tot['f']).max() < 1e-9
 
 
+# ---- TabulatedEAM, funcfl (tests/test_bulk_properties.py:134-137, test_forces_and_virial.py:147) ---
+
+def funcfl_calc(tab):
+    eam = oracle.EAMFuncfl(tab)
+
+    def calc(a, **kw):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, eam.cutoff, 200)
+        return eam.energy_and_forces(a.positions, a.cell, nl, a.symbols, **kw)
+    return calc
+
+
+def test_funcfl_au_bulk_and_fd(au_funcfl):
+    ref = KAT['bulk']['TabulatedEAM_fcc_Au']
+    calc = funcfl_calc(au_funcfl)
+    Ec, a0, C11, C12 = bulk_props(calc, lambda a0: S.fcc('Au', a0, (3, 3, 3)), ref['a0'])
+    assert rel(Ec, ref['Ec']) < 0.05 and rel(a0, ref['a0']) < 0.05
+    assert rel(C11, ref['C11']) < 0.05 and rel(C12, ref['C12']) < 0.05
+    assert rel((C11 + 2 * C12) / 3, ref['B']) < 0.05
+    a = S.fcc('Au', 4.08, (3, 3, 3)); a.rattle(0.1, seed=8)
+    check_fd(calc, a)
+
+
 # ---- neighbour list (tests/test_neighbor_list.py) -------------------------------------------------
 
 def _brute(a, cutoff):

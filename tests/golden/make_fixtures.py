@@ -180,6 +180,11 @@ def main():
             'Juslin_B3_WC': dict(Ec=(16.68 - 2.12) / 2, a0=4.679, B=511.0),
         },
         'bulk_tol_rel': 0.05,
+        # tests/test_surface_properties.py:228-262: relaxed (100) surface energies of the Erhart-Albe
+        # parameter set, unscreened and screened rows (5 % tolerance, atomistica/tests.py:597-700)
+        'surface_100_relaxed_J_m2': {'Brenner': {'C': 5.59, 'Si': 1.95, 'SiC': 3.93},
+                                     'BrennerScr': {'C': 5.88, 'Si': 1.90, 'SiC': 3.87}},
+        'surface_tol_rel': 0.05,
         # closed form from the reference formulas
         'tersoff_si_diamond_a0_5.432_eV_per_atom': -4.6295950127,
         'kumagai_si_diamond_a0_5.429_eV_per_atom': -4.6299992839,

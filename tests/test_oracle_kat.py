@@ -537,6 +537,41 @@ def test_funcfl_au_bulk_and_fd(au_funcfl):
     check_fd(calc, a)
 
 
+# ---- relaxed (100) surface energies (tests/test_surface_properties.py:228-262) --------------------
+
+def _surface_100(calc, sym, a0_guess, nz=4, vacuum=10.0):
+    """atomistica/tests.py:597-700: lattice constant from the bulk cell, slab = same cell + vacuum,
+    relaxed to fmax = 0.005 eV/A from the ideal termination; returns J/m^2"""
+    def cellof(a0):
+        a = S.diamond(sym, a0, (1, 1, nz)) if isinstance(sym, str) else S.b3(sym, a0, (1, 1, nz))
+        a.positions += np.array([a0 / 8, a0 / 8, a0 * nz / (8 * nz)]) + 0.1
+        return a
+    a0 = minimize_scalar(lambda x: calc(cellof(x))['epot'], bracket=(a0_guess * 0.98, a0_guess * 1.02), tol=1e-10).x
+    bulk = cellof(a0)
+    ebulk = calc(bulk)['epot']
+    slab = bulk.copy()
+    cell = np.diag(bulk.cell).copy()
+    cell[2] += vacuum
+    slab.set_cell(cell, scale_atoms=False)
+
+    def fun(x):
+        b = slab.copy()
+        b.positions = x.reshape(-1, 3)
+        o = calc(b)
+        return o['epot'], -o['f'].ravel()
+    res = minimize(fun, slab.positions.ravel(), jac=True, method='L-BFGS-B', options=dict(gtol=0.005, maxiter=500))
+    return (res.fun - ebulk) / 2 / (a0 * a0) * 16.021766208
+
+
+@pytest.mark.parametrize('pot', ['Brenner', 'BrennerScr'])
+@pytest.mark.parametrize('mat,sym,a0', [('C', 'C', 3.566), ('Si', 'Si', 5.432), ('SiC', ['Si', 'C'], 4.321)])
+def test_surface_energy_100(pot, mat, sym, a0):
+    calc = bop_calc('Brenner', None) if pot == 'Brenner' else bop_scr_calc('Brenner', None)
+    es = _surface_100(calc, sym, a0)
+    ref = KAT['surface_100_relaxed_J_m2'][pot][mat]
+    assert rel(es, ref) < KAT['surface_tol_rel'], (es, ref)
+
+
 # ---- neighbour list (tests/test_neighbor_list.py) -------------------------------------------------
 
 def _brute(a, cutoff):

@@ -570,6 +570,9 @@ def test_surface_energy_100(pot, mat, sym, a0):
     es = _surface_100(calc, sym, a0)
     ref = KAT['surface_100_relaxed_J_m2'][pot][mat]
     assert rel(es, ref) < KAT['surface_tol_rel'], (es, ref)
+    # the reference allows 5 %; the restated kernels reproduce its 3-digit table values (also where the
+    # screened and unscreened rows differ: C 5.59 vs 5.88, Si 1.95 vs 1.90, SiC 3.93 vs 3.87)
+    assert abs(es - ref) < 0.006, (es, ref)
 
 
 # ---- neighbour list (tests/test_neighbor_list.py) -------------------------------------------------

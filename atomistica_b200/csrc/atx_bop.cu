@@ -315,7 +315,9 @@ __device__ __forceinline__ bool bop_center_atom(
     const double4 *__restrict__ pos4, const long long *__restrict__ seed, const int2 *__restrict__ list,
     const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
     double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
-    double *__restrict__ fpb, double *__restrict__ wpb, double (&acc)[ATX_NSUM]) {
+    double *__restrict__ fpb, double *__restrict__ wpb, double (&acc)[ATX_NSUM], const bool own) {
+  // own: the centre belongs to this process / rank; bonds of ghost centres still produce the forces
+  // they exert on owned atoms, but their energy and virial are counted by their owner
   double4 pi = pos4[s];
   const int eli = P.el2db[(int)pi.w];
   const long long b0 = seed[s], b1 = seed[s + 1];
@@ -474,7 +476,7 @@ __device__ __forceinline__ bool bop_center_atom(
       if (ik == ij) continue;
       S.gx[ik][t] -= dfb * S.kx[ik][t]; S.gy[ik][t] -= dfb * S.ky[ik][t]; S.gz[ik][t] -= dfb * S.kz[ik][t];
     }
-    acc[0] += e_bond;
+    if (own) acc[0] += e_bond;
     const long long a = b0 + S.slot[ij][t];
     if (epb) epb[a] = e_bond;
     if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
@@ -483,8 +485,10 @@ __device__ __forceinline__ bool bop_center_atom(
       w[0] = rijx * dfx - dfb * wb[0]; w[1] = rijy * dfx - dfb * wb[1]; w[2] = rijz * dfx - dfb * wb[2];
       w[3] = rijx * dfy - dfb * wb[3]; w[4] = rijy * dfy - dfb * wb[4]; w[5] = rijz * dfy - dfb * wb[5];
       w[6] = rijx * dfz - dfb * wb[6]; w[7] = rijy * dfz - dfb * wb[7]; w[8] = rijz * dfz - dfb * wb[8];
+      if (own) {
 #pragma unroll
-      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+        for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+      }
       if (wpb) {
 #pragma unroll
         for (int q = 0; q < 9; q++) wpb[9 * a + q] = w[q];
@@ -527,7 +531,8 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   if (s < nat && (!role || role[s] >= 1)) {
-    if (!bop_center_atom<KIND, NB, VIRIAL>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb, wpb, acc))
+    if (!bop_center_atom<KIND, NB, VIRIAL>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb, wpb, acc,
+                                           !role || role[s] >= 2))
       queue[atomicAdd(qcount, 1)] = s;
   }
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
@@ -548,7 +553,7 @@ k_bop_center_queued(Mat3 A, BopDev P, const double4 *__restrict__ pos4,
                     double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
                     int pstride, int pofs, const int *__restrict__ queue,
                     const int *__restrict__ qcount, int *__restrict__ flag,
-                    const int *__restrict__ stop) {
+                    const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BondSmem<BOP_NB_MAX> &S = *reinterpret_cast<BondSmem<BOP_NB_MAX> *>(smem_raw);
@@ -558,8 +563,9 @@ k_bop_center_queued(Mat3 A, BopDev P, const double4 *__restrict__ pos4,
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   const int nq = *qcount;
   for (int q = blockIdx.x * BOP_BLOCK + t; q < nq; q += gridDim.x * BOP_BLOCK) {
-    if (!bop_center_atom<KIND, BOP_NB_MAX, true>(S, t, queue[q], A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb,
-                                           fpb, wpb, acc))
+    const int sq = queue[q];
+    if (!bop_center_atom<KIND, BOP_NB_MAX, true>(S, t, sq, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb,
+                                                 fpb, wpb, acc, !role || role[sq] >= 2))
       atomicOr(flag, 1);  // more than BOP_NB_MAX bonds on one atom: reported as an error by the host
   }
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
@@ -787,6 +793,7 @@ k_bopscr_center(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, Bop
     const int eli = P.el2db[(int)pi.w];
     const long long b0 = seed[s];
     const int nb = eli > 0 ? T.nbond[s] : 0;
+    const bool own = !role || role[s] >= 2;
     double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
     const int mi = mask ? mask[s] : 1;
 
@@ -926,9 +933,11 @@ k_bopscr_center(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, Bop
         g.x += fjx; g.y += fjy; g.z += fjz; g.w += e_bond;
         G[aj] = g;
       }
+      if (own) {
 #pragma unroll
-      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
-      acc[0] += e_bond;
+        for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+        acc[0] += e_bond;
+      }
       if (epb) epb[aj] += e_bond;
       if (fpb) { fpb[3 * aj] += dfx; fpb[3 * aj + 1] += dfy; fpb[3 * aj + 2] += dfz; }
       if (wpb) {
@@ -981,8 +990,10 @@ k_bopscr_center(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, Bop
         g.x += fjx; g.y += fjy; g.z += fjz;
         G[aj] = g;
       }
+      if (own) {
 #pragma unroll
-      for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+        for (int q = 0; q < 9; q++) acc[1 + q] += w[q];
+      }
       if (wpb) {
 #pragma unroll
         for (int q = 0; q < 9; q++) wpb[9 * aj + q] += w[q];
@@ -1014,7 +1025,8 @@ __global__ void k_bop_gather(int nat, const long long *__restrict__ seed, const 
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nat) return;
   if (role && role[s] < 2) {
-    if (role[s] < 1) { f[3 * s] = 0.0; f[3 * s + 1] = 0.0; f[3 * s + 2] = 0.0; }
+    // ghosts: their owner computes (and, under LAMMPS, reverse-communicates nothing from here)
+    f[3 * s] = 0.0; f[3 * s + 1] = 0.0; f[3 * s + 2] = 0.0;
     if (epa) epa[s] = 0.0;
     return;
   }
@@ -1309,7 +1321,7 @@ static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, c
   k_bop_center_queued<KIND><<<nq, BOP_BLOCK, smem, st>>>(
       p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f, pe_own, o.wpa,
       epb, fpb, wpb, pot->sc.partials.ptr, pstride, nblocks, pot->queue.ptr, pot->flag.ptr + 1,
-      pot->flag.ptr, o.stop);
+      pot->flag.ptr, o.role, o.stop);
   ATX_LAUNCHED();
   return 0;
 }
@@ -1550,6 +1562,7 @@ extern "C" int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_nei
     ATX_CUDA(cudaMemsetAsync(pot->wpb.ptr, 0, sizeof(double) * 9 * nslots, ctx->stream));
     wpb = pot->wpb.ptr;
   }
+  if (nl->external) o.role = nl->role_ext.ptr;
   ATX_PASS(bop_compute(pot, p, nl, mask_sorted, o, epb, fpb, wpb));
   int h = 0;
   ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

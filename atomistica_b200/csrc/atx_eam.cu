@@ -708,6 +708,13 @@ extern "C" int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_nei
   ATX_PASS(atx_neighbors_update(nl, p));
   PotOut o;
   ATX_PASS(atx_prepare_out(pot->ctx, nl, pot->sc, epot_per_at != nullptr, wpot_per_at != nullptr, o));
+  if (nl->external) {
+    if (mask || wpot_per_at) {
+      atx_set_error("TabulatedAlloyEAM: masks and per-atom virials are not available with an external neighbour list.");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    o.role = nl->role_ext.ptr;
+  }
   const int *mask_sorted = nullptr;
   ATX_PASS(atx_prepare_mask(pot->ctx, nl, pot->sc, mask, &mask_sorted));
   ATX_PASS(atx_eam_compute_device(pot, p, nl, mask_sorted, o));

@@ -181,6 +181,12 @@ struct atx_neighbors {
   DevBuf<int2> rows;        // fixed-width per-atom rows of the single-pass build (scratch)
   DevBuf<int> rev;          // optional reverse-slot index
   bool rev_valid = false;
+  // caller-supplied list (LAMMPS host, atx_neighbors_set_external): atoms >= natloc are ghosts that
+  // appear as separate atoms, no periodic shifts; role_ext = 2 for owned atoms, 1 for ghosts
+  bool external = false;
+  int natloc = -1;
+  DevBuf<unsigned char> role_ext;
+  DevBuf<int> ext_flat;
   DevBuf<long long> scal;   // small scalar scratch (npairs, nebmax, flags)
 };
 

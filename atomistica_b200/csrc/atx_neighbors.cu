@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "atx_internal.cuh"
 
@@ -406,6 +408,16 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   atx_ctx *ctx = nl->ctx;
   cudaStream_t st = ctx->stream;
+  if (nl->external) {
+    // the host owns the list (lammps_neighbors.f90:205-217: update is a no-op); only the sorted
+    // position records follow the particles
+    if (nl->bound != p || nl->nat != p->nat) {
+      atx_set_error("The external neighbour list was set for another particles object; call atx_neighbors_set_external again.");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    if (nl->p_rev != p->pos_rev) ATX_PASS(atx_neighbors_refresh_positions(nl, p));
+    return 0;
+  }
   if (nl->bound != p || nl->nat != p->nat) nl->initialized = false;
   if (nl->initialized && nl->p_rev == p->pos_rev && nl->cell_rev == p->cell_rev) return 0;
 
@@ -558,6 +570,102 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     ATX_PASS(nl->pos_build.reserve(nat + 1));
     ATX_CUDA(cudaMemcpyAsync(nl->pos_build.ptr, nl->pos4.ptr, sizeof(double4) * nat, cudaMemcpyDeviceToDevice, st));
   }
+  nl->p_rev = p->pos_rev;
+  nl->cell_rev = p->cell_rev;
+  nl->el_rev = p->el_rev;
+  nl->nbuilds++;
+  return 0;
+}
+
+// caller-supplied list -> internal records (identity order, zero shifts, neighbour element in the entry)
+__global__ void k_external_list(int nat, int natloc, const double *__restrict__ r, const int *__restrict__ el,
+                                const long long *__restrict__ seed, const int *__restrict__ flat,
+                                double4 *__restrict__ pos4, int *__restrict__ order, int *__restrict__ inv,
+                                int2 *__restrict__ list, unsigned char *__restrict__ role,
+                                long long *__restrict__ scal) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  pos4[s] = make_double4(r[3 * s], r[3 * s + 1], r[3 * s + 2], (double)(el ? el[s] : 1));
+  order[s] = s;
+  inv[s] = s;
+  role[s] = s < natloc ? 2 : 1;
+  for (long long a = seed[s]; a < seed[s + 1]; a++) {
+    int j = flat[a];
+    if (j < 0 || j >= nat) {
+      atomicMax((unsigned long long *)&scal[3], 1ull);
+      j = s;
+    }
+    list[a] = make_int2(j, ATX_SHIFT_ZERO | ((el ? el[j] : 1) << 24));
+  }
+}
+
+extern "C" int atx_neighbors_set_external(atx_neighbors *nl, atx_particles *p, int natloc, int inum,
+                                          const int *ilist, const int *numneigh,
+                                          const int *const *firstneigh) {
+  if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
+  if (!nl || !p || inum < 0 || (inum > 0 && (!ilist || !numneigh || !firstneigh))) return ATX_ERROR_UNSPECIFIED;
+  atx_ctx *ctx = nl->ctx;
+  cudaStream_t st = ctx->stream;
+  const int nat = p->nat;
+  if (natloc < 0 || natloc > nat) {
+    atx_set_error("atx_neighbors_set_external: natloc out of range.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  // flatten the per-atom pointers (pair_atomistica.cpp:426-456 maps them without copying; the
+  // device needs one contiguous array)
+  std::vector<long long> hseed((size_t)nat + 1, 0);
+  for (int ii = 0; ii < inum; ii++) {
+    const int i = ilist[ii];
+    if (i < 0 || i >= nat) {
+      atx_set_error("atx_neighbors_set_external: ilist entry out of range.");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    hseed[i + 1] = numneigh[i];
+  }
+  int nebmax = 0;
+  for (int i = 0; i < nat; i++) {
+    nebmax = std::max(nebmax, (int)hseed[i + 1]);
+    hseed[i + 1] += hseed[i];
+  }
+  const long long npairs = hseed[nat];
+  std::vector<int> flat((size_t)npairs + 1);
+  for (int ii = 0; ii < inum; ii++) {
+    const int i = ilist[ii];
+    if (numneigh[i] > 0) memcpy(flat.data() + hseed[i], firstneigh[i], sizeof(int) * numneigh[i]);
+  }
+  ATX_PASS(nl->seed.reserve((size_t)nat + 2));
+  ATX_PASS(nl->ext_flat.reserve((size_t)npairs + 1));
+  ATX_PASS(nl->list.reserve((size_t)npairs + 1));
+  ATX_PASS(nl->pos4.reserve((size_t)nat + 1));
+  ATX_PASS(nl->order.reserve((size_t)nat + 1));
+  ATX_PASS(nl->inv.reserve((size_t)nat + 1));
+  ATX_PASS(nl->role_ext.reserve((size_t)nat + 1));
+  ATX_PASS(nl->scal.reserve(8));
+  ATX_CUDA(cudaMemsetAsync(nl->scal.ptr, 0, sizeof(long long) * 8, st));
+  ATX_CUDA(cudaMemcpyAsync(nl->seed.ptr, hseed.data(), sizeof(long long) * ((size_t)nat + 1), cudaMemcpyHostToDevice, st));
+  if (npairs > 0)
+    ATX_CUDA(cudaMemcpyAsync(nl->ext_flat.ptr, flat.data(), sizeof(int) * (size_t)npairs, cudaMemcpyHostToDevice, st));
+  if (nat > 0) {
+    k_external_list<<<(nat + 127) / 128, 128, 0, st>>>(nat, natloc, p->rptr(), p->el.cap ? p->el.ptr : nullptr,
+                                                       nl->seed.ptr, nl->ext_flat.ptr, nl->pos4.ptr, nl->order.ptr,
+                                                       nl->inv.ptr, nl->list.ptr, nl->role_ext.ptr, nl->scal.ptr);
+    ATX_LAUNCHED();
+  }
+  long long bad = 0;
+  ATX_CUDA(cudaMemcpyAsync(&bad, nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));   // also keeps hseed/flat alive until the copies are done
+  if (bad) {
+    atx_set_error("atx_neighbors_set_external: neighbour index out of range.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  nl->external = true;
+  nl->natloc = natloc;
+  nl->nat = nat;
+  nl->npairs = npairs;
+  nl->nebmax = nebmax;
+  nl->bound = p;
+  nl->initialized = true;
+  nl->rev_valid = false;
   nl->p_rev = p->pos_rev;
   nl->cell_rev = p->cell_rev;
   nl->el_rev = p->el_rev;

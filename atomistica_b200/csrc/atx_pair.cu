@@ -203,6 +203,7 @@ extern "C" int atx_pair_energy_and_forces(atx_pair *pot, atx_particles *p, atx_n
   ATX_PASS(atx_prepare_out(pot->ctx, nl, pot->sc, epot_per_at != nullptr, wpot_per_at != nullptr, o));
   const int *mask_sorted = nullptr;
   ATX_PASS(atx_prepare_mask(pot->ctx, nl, pot->sc, mask, &mask_sorted));
+  if (nl->external) o.role = nl->role_ext.ptr;
   ATX_PASS(atx_pair_compute_device(pot, p, nl, mask_sorted, o));
   return atx_finish_to_host(pot->ctx, nl, pot->sc, o, epot, f, wpot, epot_per_at, wpot_per_at);
 }

@@ -865,6 +865,10 @@ extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx
     return ATX_ERROR_UNSPECIFIED;
   }
   atx_ctx *ctx = pot->ctx;
+  if (nl->external) {
+    atx_set_error("Rebo2 does not support an external neighbour list yet.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
   ATX_PASS(atx_neighbors_update(nl, p));
   PotOut o;
   ATX_PASS(pot->sc.f.reserve(3 * (size_t)nl->nat + 3));

@@ -84,6 +84,18 @@ int atx_neighbors_rebuild(atx_neighbors *nl, atx_particles *p);
 /* number of pairs, max neighbours per atom, n_cells(3), stencil half widths(3) */
 int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax, int *n_cells,
                            int *stencil);
+/* LAMMPS host (src/lammps/pair_style/pair_atomistica.cpp:385-460, lammps_neighbors.f90:177-217):
+ * the host builds and communicates the list; ghosts are separate atoms (indices natloc..nat-1 of
+ * the particles object), there are no periodic shifts, and -- as the pair style requests with
+ * REQ_FULL|REQ_GHOST -- ghost atoms carry lists of their own.  ilist/numneigh/firstneigh are
+ * LAMMPS's NeighList arrays for the inum+gnum atoms that have a list (0-based indices).  After this
+ * call atx_neighbors_update is a no-op apart from following the positions, and
+ * atx_{eam,bop,pair}_energy_and_forces return epot / wpot summed over the OWNED atoms' bonds and
+ * forces on owned atoms only (ghost rows of f receive zero: the gather formulation needs no
+ * reverse communication; the ghost shell must be 2 x cutoff wide, which is what
+ * particles_get_border already asks LAMMPS for).  Call again after every reneighbouring. */
+int atx_neighbors_set_external(atx_neighbors *nl, atx_particles *p, int natloc, int inum,
+                               const int *ilist, const int *numneigh, const int *const *firstneigh);
 /* number of list builds and of updates answered without a rebuild (Verlet shell, neighbors.f90:552-590) */
 int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long *nreused);
 /* host view of the list in the reference's layout and order (seed(nat+1), last(nat+1),

@@ -1,0 +1,111 @@
+"""LAMMPS-style operation: the host supplies the neighbour list, ghosts are explicit atoms.
+
+A periodic system is unfolded the way LAMMPS would hand it over -- owned atoms plus ghost images
+within a 2 x cutoff shell, full lists for owned AND ghost atoms (REQ_FULL|REQ_GHOST), no periodic
+shifts -- and the result must equal the ordinary periodic calculation: energy, virial, forces on
+the owned atoms; ghost rows of the force array stay zero."""
+import numpy as np
+import pytest
+
+from atomistica_b200 import native, structures as S
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def unfold(atoms, cutoff):
+    """owned atoms + ghost images within 2*cutoff of the (orthorhombic) box, brute-force full lists"""
+    L = np.diag(atoms.cell)
+    pos, sym = [atoms.positions], [list(atoms.symbols)]
+    w = 2 * cutoff
+    rng = [range(-int(np.ceil(w / L[k])), int(np.ceil(w / L[k])) + 1) for k in range(3)]
+    for i in rng[0]:
+        for j in rng[1]:
+            for k in rng[2]:
+                if (i, j, k) == (0, 0, 0):
+                    continue
+                p = atoms.positions + np.array([i, j, k]) * L
+                m = np.all((p > -w) & (p < L + w), axis=1)
+                pos.append(p[m])
+                sym.append([s for s, t in zip(atoms.symbols, m) if t])
+    pos = np.concatenate(pos)
+    sym = sum(sym, [])
+    nall = len(pos)
+    lists = []
+    for i in range(nall):
+        d2 = ((pos - pos[i]) ** 2).sum(axis=1)
+        nb = np.nonzero(d2 < cutoff * cutoff)[0]
+        lists.append(nb[nb != i].astype(np.int32))
+    big = S.Atoms(sym, pos, L + 10 * w, False)
+    return big, lists
+
+
+def _compare(atoms, make_pot, cutoff, avgn=200):
+    p0 = native.from_atoms(atoms)
+    nl0 = native.Neighbors(avgn)
+    pot0 = make_pot()
+    pot0.bind_to(p0, nl0)
+    e0, f0, w0 = pot0.energy_and_forces(p0, nl0)[:3]
+
+    big, lists = unfold(atoms, cutoff)
+    nloc = len(atoms)
+    p = native.from_atoms(big)
+    nl = native.Neighbors(avgn)
+    pot = make_pot()
+    pot.bind_to(p, nl)
+    nl.set_external(p, nloc, np.arange(len(big)), lists)
+    e, f, w = pot.energy_and_forces(p, nl)[:3]
+    assert abs(e - e0) <= RTOL * abs(e0)
+    fs = max(1.0, np.abs(f0).max())
+    assert np.abs(f[:nloc] - f0).max() <= RTOL * fs
+    assert np.all(f[nloc:] == 0.0)
+    assert np.abs(w - w0).max() <= RTOL * max(1.0, np.abs(w0).max(), abs(e0))
+    # the host moves atoms between reneighbourings: positions follow, the list is kept
+    d = np.random.RandomState(1).normal(scale=0.01, size=(nloc, 3))
+    atoms2 = atoms.copy()
+    atoms2.positions = atoms.positions + d
+    big2, _ = unfold(atoms2, cutoff)
+    if len(big2) == len(big) and np.abs(big2.positions - big.positions).max() < 0.1:
+        p.coordinates[:, :] = big2.positions
+        p.I_changed_positions()
+        p0.coordinates[:, :] = atoms2.positions
+        p0.I_changed_positions()
+        e1 = pot.energy_and_forces(p, nl)[0]
+        e2 = pot0.energy_and_forces(p0, nl0)[0]
+        assert abs(e1 - e2) <= 1e-6 * abs(e2)      # pairs crossing the cutoff may differ: list not rebuilt
+
+
+def test_eam_external(cu_setfl):
+    a = S.fcc('Cu', 3.615, (4, 4, 4))
+    a.rattle(0.05, seed=3)
+    _compare(a, lambda: native.TabulatedAlloyEAM(setfl=cu_setfl), float(cu_setfl['cutoff']))
+
+
+def test_tersoff_external():
+    a = S.diamond('Si', 5.432, (3, 3, 3))
+    a.rattle(0.08, seed=4)
+    _compare(a, native.Tersoff, 3.0, avgn=50)
+
+
+def test_brenner_sic_external():
+    a = S.b3(['Si', 'C'], 4.3596, (3, 3, 3))
+    a.rattle(0.08, seed=5)
+    _compare(a, native.Brenner, 2.96, avgn=50)
+
+
+def test_lj_external():
+    a = S.fcc('Ar', 5.3, (3, 3, 3))
+    a.rattle(0.1, seed=6)
+    _compare(a, lambda: native.LJCut(epsilon=0.0104, sigma=3.40, cutoff=6.0), 6.0)
+
+
+def test_rebo2_refuses_external():
+    a = S.diamond('C', 3.566, (2, 2, 2))
+    big, lists = unfold(a, 2.0)
+    p = native.from_atoms(big)
+    nl = native.Neighbors(50)
+    pot = native.Rebo2()
+    pot.bind_to(p, nl)
+    nl.set_external(p, len(a), np.arange(len(big)), lists)
+    with pytest.raises(RuntimeError):
+        pot.energy_and_forces(p, nl)

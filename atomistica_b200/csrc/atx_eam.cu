@@ -456,8 +456,8 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
   if (lane == 0 && valid) {
     f[3 * s] = fx; f[3 * s + 1] = fy; f[3 * s + 2] = fz;
     const double ei = en_ + Fe[s];
-    if (epa) epa[s] = ei;
-    acc[0] = ei;
+    if (epa) epa[s] = dbi > 0 ? ei : 0.0;
+    if (dbi > 0) acc[0] = ei;   // ghosts (role < 2) carry an embedding energy that their owner counts
   }
   if (VIRIAL) {
     acc[1] = wxx; acc[2] = wxy; acc[3] = wxz;

@@ -188,8 +188,10 @@ def spline_eval(s, x, extrapolate=False):
 # ----------------------------------------------------------------------------
 
 def set_threads(n):
-    """OpenMP threads of the EAM kernel (bench.py's CPU legs); 1 = the serial order the KATs pin"""
+    """OpenMP threads of the EAM kernel and of the list build (bench.py's CPU legs); 1 = the serial
+    code the KATs pin"""
     lib().orc_eam_set_threads(int(n))
+    lib().orc_nl_set_threads(int(n))
 
 
 class EAM:

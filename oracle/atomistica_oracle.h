@@ -36,6 +36,8 @@ typedef struct {
 int orc_binning_init(const double *Abox, const double *Bbox, double cutoff, double bin_size,
                      orc_binning_t *b);
 
+/* OpenMP threads of the build (default 1 = the serial loop) */
+void orc_nl_set_threads(int n);
 /* returns number of pairs, or -1 on "Neighbor list overflow" (capacity = size of neighbors[]) */
 long orc_nl_build(int nat, const double *r, const double *Abox, const double *Bbox, const int *pbc,
                   double cutoff, long capacity, intptr_t *seed, intptr_t *last, int *neighbors,

@@ -68,6 +68,79 @@ static void cell_of(const double *rec, const double *r, int *c) {
   }
 }
 
+static int orc_nl_threads = 1;
+
+/* OpenMP threads of the list build (bench.py's CPU legs).  The reference's fill_neighbor_list is
+ * parallel too (python_neighbors.f90:610-628, one chunk of the list per thread).  Here the
+ * threaded path counts per atom, prefix-sums and fills, which yields exactly the serial layout;
+ * 1 (default) runs the serial loop below. */
+void orc_nl_set_threads(int n) { orc_nl_threads = n > 0 ? n : 1; }
+
+/* neighbours of atom i in the reference's traversal order; fill = 0 only counts, fill = 1 writes
+ * them to slots pos, pos+1, ... (0-based) */
+static long nl_atom(int i, const double *r, const double *Abox, const int *pbc, const orc_binning_t *b,
+                    const int *bin_seed, const int *next, double cutoff_sq, int fill, long pos,
+                    int *neighbors, int *dc) {
+  const int *n = b->n_cells;
+  long cnt = 0;
+  int celli[3], shift[3] = {0, 0, 0};
+  cell_of(b->rec_cell_size, &r[3 * i], celli);
+  for (int k = 0; k < 3; k++) {
+    if (pbc[k]) {
+      while (celli[k] < 0) { celli[k] += n[k]; shift[k] += 1; }
+      while (celli[k] >= n[k]) { celli[k] -= n[k]; shift[k] -= 1; }
+    } else {
+      if (celli[k] < 0) celli[k] = 0;
+      if (celli[k] >= n[k]) celli[k] = n[k] - 1;
+    }
+  }
+  for (int x = -b->dx; x <= b->dx; x++)
+    for (int y = -b->dy; y <= b->dy; y++)
+      for (int z = -b->dz; z <= b->dz; z++) {
+        int cc[3] = {celli[0] + x, celli[1] + y, celli[2] + z};
+        int shift1[3] = {shift[0], shift[1], shift[2]};
+        int exists = 1;
+        for (int k = 0; k < 3; k++) {
+          if (pbc[k]) {
+            while (cc[k] < 0) { cc[k] += n[k]; shift1[k] += 1; }
+            while (cc[k] >= n[k]) { cc[k] -= n[k]; shift1[k] -= 1; }
+          }
+          if (cc[k] < 0 || cc[k] >= n[k]) exists = 0;
+        }
+        if (!exists) continue;
+        int j = bin_seed[cc[0] + (long)n[0] * (cc[1] + (long)n[1] * cc[2])];
+        while (j != -1) {
+          int cellj[3], shift2[3] = {shift1[0], shift1[1], shift1[2]};
+          cell_of(b->rec_cell_size, &r[3 * j], cellj);
+          for (int k = 0; k < 3; k++) {
+            if (pbc[k]) {
+              while (cellj[k] < 0) { cellj[k] += n[k]; shift2[k] -= 1; }
+              while (cellj[k] >= n[k]) { cellj[k] -= n[k]; shift2[k] += 1; }
+            }
+          }
+          if (i != j || shift2[0] != 0 || shift2[1] != 0 || shift2[2] != 0) {
+            double d[3];
+            for (int k = 0; k < 3; k++) {
+              double s = 0.0;
+              for (int c = 0; c < 3; c++) s += M3(Abox, k, c) * (double)shift2[c];
+              d[k] = r[3 * i + k] - r[3 * j + k] + s;
+            }
+            if (dot3(d, d) < cutoff_sq) {
+              if (fill) {
+                neighbors[pos + cnt] = j + 1;
+                dc[3 * (pos + cnt) + 0] = shift2[0];
+                dc[3 * (pos + cnt) + 1] = shift2[1];
+                dc[3 * (pos + cnt) + 2] = shift2[2];
+              }
+              cnt++;
+            }
+          }
+          j = next[j];
+        }
+      }
+  return cnt;
+}
+
 long orc_nl_build(int nat, const double *r, const double *Abox, const double *Bbox, const int *pbc,
                   double cutoff, long capacity, intptr_t *seed, intptr_t *last, int *neighbors,
                   int *dc) {
@@ -105,6 +178,32 @@ long orc_nl_build(int nat, const double *r, const double *Abox, const double *Bb
   }
 
   double cutoff_sq = cutoff * cutoff;
+  if (orc_nl_threads > 1) {
+    long *cnt = (long *)malloc(sizeof(long) * (nat > 0 ? nat : 1));
+#pragma omp parallel for schedule(dynamic, 64) num_threads(orc_nl_threads)
+    for (int i = 0; i < nat; i++)
+      cnt[i] = nl_atom(i, r, Abox, pbc, &b, bin_seed, next, cutoff_sq, 0, 0, NULL, NULL);
+    long cur1 = 1, total = 0;
+    for (int i = 0; i < nat; i++) {
+      seed[i] = cur1;
+      last[i] = cur1 + cnt[i] - 1;
+      cur1 += cnt[i] + 1; /* + terminator slot */
+      total += cnt[i];
+    }
+    long result = total;
+    if (cur1 - 1 > capacity) {
+      result = -1; /* same condition as the serial "cur >= capacity" check */
+    } else {
+      seed[nat] = cur1;
+#pragma omp parallel for schedule(dynamic, 64) num_threads(orc_nl_threads)
+      for (int i = 0; i < nat; i++) {
+        nl_atom(i, r, Abox, pbc, &b, bin_seed, next, cutoff_sq, 1, seed[i] - 1, neighbors, dc);
+        neighbors[last[i]] = 0; /* terminator slot (0-based index last[i]) */
+      }
+    }
+    free(cnt); free(bin_seed); free(bin_last); free(next);
+    return result;
+  }
   long cur = 1, nn = 0; /* 1-based slot as in the reference */
   int overflow = 0;
   for (int i = 0; i < nat && !overflow; i++) {

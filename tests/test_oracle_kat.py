@@ -663,3 +663,23 @@ def test_spline_reproduces_nodes(cu_setfl):
     with pytest.raises(ValueError):
         oracle.spline_eval(s, s['cut'] + 1.0)
     oracle.spline_eval(s, s['cut'] + 1.0, extrapolate=True)
+
+
+def test_threaded_oracle_matches_serial(cu_setfl):
+    """bench.py's CPU legs run the oracle under OpenMP: the list layout must be identical to the
+    serial build and the EAM results equal to rounding"""
+    a = S.fcc('Cu', 3.615, (6, 6, 6)); a.rattle(0.1, seed=21)
+    eam = oracle.EAM(cu_setfl)
+    n1 = oracle.neighbor_list(a.positions, a.cell, a.pbc, eam.cutoff, 200)
+    o1 = eam.energy_and_forces(a.positions, a.cell, n1, eam.eldb(a.symbols))
+    oracle.set_threads(4)
+    try:
+        n2 = oracle.neighbor_list(a.positions, a.cell, a.pbc, eam.cutoff, 200)
+        o2 = eam.energy_and_forces(a.positions, a.cell, n2, eam.eldb(a.symbols))
+    finally:
+        oracle.set_threads(1)
+    n = n1.npairs + len(a)
+    assert n1.npairs == n2.npairs and np.array_equal(n1.seed, n2.seed) and np.array_equal(n1.last, n2.last)
+    assert np.array_equal(n1.neighbors[:n], n2.neighbors[:n]) and np.array_equal(n1.dc[:n], n2.dc[:n])
+    assert abs(o1['epot'] - o2['epot']) < 1e-12 * abs(o1['epot'])
+    assert np.abs(o1['f'] - o2['f']).max() < 1e-12

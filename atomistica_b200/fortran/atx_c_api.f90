@@ -135,7 +135,85 @@ module atx_c_api
        real(c_double)     :: epot, f(3, *), wpot(3, 3)
        type(c_ptr), value :: epot_per_at, epot_per_bond, f_per_bond, wpot_per_at, wpot_per_bond
      endfunction
+
+     ! --- screened variants, Juslin, funcfl EAM, pair styles, LAMMPS-style lists, output mode ---
+     integer(c_int) function atx_bop_create_screened(ctx, par, scr, pot) bind(C, name="atx_bop_create_screened")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr), value :: par      ! c_loc of a type(atx_bop_params_t)
+       type(c_ptr), value :: scr      ! c_loc of a type(atx_bop_screening_t): or1 or2 bor1 bor2 Cmin Cmax
+       type(c_ptr)        :: pot
+     endfunction
+     integer(c_int) function atx_bop_create_juslin(ctx, par, pot) bind(C, name="atx_bop_create_juslin")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr), value :: par      ! c_loc of a type(atx_juslin_params_t), database AFTER the mirroring of bind_to
+       type(c_ptr)        :: pot
+     endfunction
+     integer(c_int) function atx_eam_create_funcfl(ctx, fF, frho, fZ, cutoff, pot) bind(C, name="atx_eam_create_funcfl")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value    :: ctx
+       type(c_ptr), value    :: fF, frho, fZ     ! c_loc of one type(atx_spline_t) each; fZ already scaled
+       real(c_double), value :: cutoff
+       type(c_ptr)           :: pot
+     endfunction
+     integer(c_int) function atx_pair_create(ctx, par, pot) bind(C, name="atx_pair_create")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr), value :: par      ! c_loc of a type(atx_pair_params_t)
+       type(c_ptr)        :: pot
+     endfunction
+     integer(c_int) function atx_pair_bind_to(pot, p, nl, el1, el2) bind(C, name="atx_pair_bind_to")
+       import :: c_int, c_ptr
+       type(c_ptr), value    :: pot, p, nl
+       integer(c_int), value :: el1, el2          ! this%el1, this%el2 of filter_from_string
+     endfunction
+     integer(c_int) function atx_pair_energy_and_forces(pot, p, nl, mask, epot, f, wpot, epot_per_at, &
+          wpot_per_at) bind(C, name="atx_pair_energy_and_forces")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: pot, p, nl, mask
+       real(c_double)     :: epot, f(3, *), wpot(3, 3)
+       type(c_ptr), value :: epot_per_at, wpot_per_at
+     endfunction
+     integer(c_int) function atx_neighbors_set_external(nl, p, natloc, inum, ilist, numneigh, firstneigh) &
+          bind(C, name="atx_neighbors_set_external")
+       import :: c_int, c_ptr
+       type(c_ptr), value    :: nl, p
+       integer(c_int), value :: natloc, inum
+       type(c_ptr), value    :: ilist, numneigh, firstneigh   ! LAMMPS NeighList arrays (int*, int*, int**)
+     endfunction
+     integer(c_int) function atx_neighbors_get_counters(nl, nbuilds, nreused) bind(C, name="atx_neighbors_get_counters")
+       import :: c_int, c_ptr, c_long_long
+       type(c_ptr), value   :: nl
+       integer(c_long_long) :: nbuilds, nreused
+     endfunction
+     integer(c_int) function atx_bop_set_store_outputs(pot, on) bind(C, name="atx_bop_set_store_outputs")
+       import :: c_int, c_ptr
+       type(c_ptr), value    :: pot
+       integer(c_int), value :: on
+     endfunction
+     integer(c_int) function atx_eam_set_store_outputs(pot, on) bind(C, name="atx_eam_set_store_outputs")
+       import :: c_int, c_ptr
+       type(c_ptr), value    :: pot
+       integer(c_int), value :: on
+     endfunction
   endinterface
+
+  !> mirrors of atx_bop_screening, atx_juslin_params, atx_pair_params (include/atomistica_b200.h)
+  type, bind(C) :: atx_bop_screening_t
+     real(c_double) :: or1(6), or2(6), bor1(6), bor2(6), Cmin(6), Cmax(6)
+  endtype atx_bop_screening_t
+  type, bind(C) :: atx_juslin_params_t
+     integer(c_int) :: nel, Z(3)
+     real(c_double) :: D0(9), r0(9), S(9), beta(9), gamma(9), c(9), d(9), h(9), n(9), r1(9), r2(9)
+     real(c_double) :: alpha(27), omega(27)
+     integer(c_int) :: m(27)
+  endtype atx_juslin_params_t
+  type, bind(C) :: atx_pair_params_t
+     integer(c_int) :: kind            ! 1 LJCut, 2 Harmonic, 3 DoubleHarmonic
+     real(c_double) :: p(8)
+     integer(c_int) :: shift
+  endtype atx_pair_params_t
 
   !> mirror of atx_spline (include/atomistica_b200.h)
   type, bind(C) :: atx_spline_t

@@ -171,6 +171,8 @@ Juslin = _calculator(native.Juslin)
 LJCut = _calculator(native.LJCut)
 Harmonic = _calculator(native.Harmonic)
 DoubleHarmonic = _calculator(native.DoubleHarmonic)
+BornMayer = _calculator(native.BornMayer)
+r6 = _calculator(native.r6)
 Rebo2 = _calculator(native.Rebo2)
 TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)
 TabulatedEAM = _calculator(native.TabulatedEAM)

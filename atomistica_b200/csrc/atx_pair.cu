@@ -14,6 +14,12 @@
 //                   f_i += F r^, e_i += 0.5 E.
 //   DoubleHarmonic  every directed entry with a factor 1/2 (self images included); the per-atom
 //                   energies receive en/2 per entry AND partner, i.e. they sum to 2 epot (kept).
+//   r6              as Harmonic (i > j).
+//   BornMayer       pairs with i <= j (ORIGINAL numbering) including the i == j image entries,
+//                   which therefore count with full weight per directed entry; the element test
+//                   is asymmetric (born_mayer.f90:222-262: if the lower-numbered atom matches el1
+//                   its partner must match el2, otherwise it must match el2 and the partner el1);
+//                   only epot and f are produced.
 // Virial per directed entry: -0.5 omega F/r dr (x) dr, the same amount goes to wpot_per_at(i).
 // Element filters are the bit masks of src/core/filter.f90 (bit k = particle element id k).
 #include "atx_potential_common.cuh"
@@ -61,9 +67,18 @@ k_pair(int nat, Mat3 A, PairDev P, const double4 *__restrict__ pos4, const int *
         const int2 en = list[a];
         const int elj = ATX_ENTRY_EL(en.y);
         const bool j1 = (P.el1 >> elj) & 1, j2 = (P.el2 >> elj) & 1;
-        if (!((i1 && j2) || (i2 && j1))) continue;
-        if (P.kind == ATX_PAIR_HARMONIC && en.x == s) continue;   // i > j: never a self image
         double omega = 1.0;
+        if (P.kind == ATX_PAIR_BORN_MAYER) {
+          // the reference decides from the LOWER original index of the pair
+          const bool self = en.x == s;
+          const bool ilow = self || order[s] < order[en.x];
+          const bool l1 = ilow ? i1 : j1, l2 = ilow ? i2 : j2, h1 = ilow ? j1 : i1, h2 = ilow ? j2 : i2;
+          if (!(l1 ? h2 : (l2 && h1))) continue;
+          omega = 1.0;   // force: f_i += F r^ (self images cancel between the +s and -s entries)
+        } else {
+          if (!((i1 && j2) || (i2 && j1))) continue;
+          if ((P.kind == ATX_PAIR_HARMONIC || P.kind == ATX_PAIR_R6) && en.x == s) continue;   // i > j: never a self image
+        }
         if (P.kind == ATX_PAIR_LJCUT) {
           const int wj = (en.x == s) ? wi : (mask ? (mask[en.x] != 0) : 1);
           omega = 0.5 * (wi + wj);
@@ -90,12 +105,24 @@ k_pair(int nat, Mat3 A, PairDev P, const double4 *__restrict__ pos4, const int *
         } else if (P.kind == ATX_PAIR_HARMONIC) {
           F = P.p[0] * (P.p[1] - r);
           E = 0.5 * F * (P.p[1] - r) - P.p[3];
+        } else if (P.kind == ATX_PAIR_R6) {
+          const double q = P.p[1] + r, q2 = q * q;
+          E = P.p[0] / (q2 * q2 * q2);
+          F = 6 * E / q;
+        } else if (P.kind == ATX_PAIR_BORN_MAYER) {
+          const double ex = exp(-r / P.p[1]);
+          E = P.p[0] * ex - P.p[3];
+          F = (P.p[0] / P.p[1]) * ex;
         } else {
           if (r < P.p[5]) { F = P.p[0] * (P.p[1] - r); E = 0.5 * F * (P.p[1] - r); }
           else { F = P.p[2] * (P.p[3] - r); E = 0.5 * F * (P.p[3] - r); }
         }
         const double c = omega * F / r;
         fx += c * dx; fy += c * dy; fz += c * dz;
+        if (P.kind == ATX_PAIR_BORN_MAYER) {
+          ei += (en.x == s) ? E : 0.5 * E;   // image entries of an atom with itself count fully, twice
+          continue;                          // no virial, no per-atom energy in the reference
+        }
         ei += 0.5 * omega * E;
         eat += (P.kind == ATX_PAIR_DOUBLE_HARMONIC) ? E : 0.5 * omega * E;
         const double h = -0.5 * c;
@@ -126,7 +153,7 @@ k_pair(int nat, Mat3 A, PairDev P, const double4 *__restrict__ pos4, const int *
 extern "C" int atx_pair_create(atx_ctx *ctx, const atx_pair_params *par, atx_pair **out) {
   if (ctx) cudaSetDevice(ctx->device);
   if (!ctx || !par || !out) return ATX_ERROR_UNSPECIFIED;
-  if (par->kind < ATX_PAIR_LJCUT || par->kind > ATX_PAIR_DOUBLE_HARMONIC) {
+  if (par->kind < ATX_PAIR_LJCUT || par->kind > ATX_PAIR_R6) {
     atx_set_error("atx_pair_create: unknown pair potential.");
     return ATX_ERROR_UNSPECIFIED;
   }
@@ -144,6 +171,14 @@ extern "C" int atx_pair_create(atx_ctx *ctx, const atx_pair_params *par, atx_pai
     // harmonic.f90:134-137
     D.p[0] = q[0]; D.p[1] = q[1]; D.p[2] = q[2];
     D.p[3] = par->shift ? 0.5 * q[0] * (q[2] - q[1]) * (q[2] - q[1]) : 0.0;
+    pot->cutoff = q[2];
+  } else if (par->kind == ATX_PAIR_BORN_MAYER) {
+    // born_mayer.f90:169: always shifted to zero at the cutoff
+    D.p[0] = q[0]; D.p[1] = q[1]; D.p[2] = q[2];
+    D.p[3] = q[0] * exp(-q[2] / q[1]);
+    pot->cutoff = q[2];
+  } else if (par->kind == ATX_PAIR_R6) {
+    D.p[0] = q[0]; D.p[1] = q[1]; D.p[2] = q[2];
     pot->cutoff = q[2];
   } else {
     // double_harmonic.f90:136: rm = (r1 + r2)/2

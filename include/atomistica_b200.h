@@ -244,6 +244,8 @@ int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx_neighbors 
 #define ATX_PAIR_LJCUT 1            /* p = {epsilon, sigma, cutoff};        shift: lj_cut.f90:176-181 */
 #define ATX_PAIR_HARMONIC 2         /* p = {k, r0, cutoff};                 shift: harmonic.f90:134-137 */
 #define ATX_PAIR_DOUBLE_HARMONIC 3  /* p = {k1, r1, k2, r2, cutoff} */
+#define ATX_PAIR_BORN_MAYER 4       /* p = {A, rho, cutoff}; epot and f only (born_mayer.f90:200-275) */
+#define ATX_PAIR_R6 5               /* p = {A, r0, cutoff}: A/(r0+r)**6 (r6.f90:150-215) */
 typedef struct atx_pair atx_pair;
 typedef struct {
   int kind;

@@ -342,7 +342,7 @@ def _per_bond_arrays(nl, per_bond):
     return np.zeros(n), np.zeros((n, 3)), np.zeros((n, 9))
 
 
-PAIR_LJCUT, PAIR_HARMONIC, PAIR_DOUBLE_HARMONIC = 1, 2, 3
+PAIR_LJCUT, PAIR_HARMONIC, PAIR_DOUBLE_HARMONIC, PAIR_BORN_MAYER, PAIR_R6 = 1, 2, 3, 4, 5
 
 
 def element_ids(symbols):

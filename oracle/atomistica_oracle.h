@@ -124,9 +124,10 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
 
 /* ---- pair potentials: src/potentials/pair_potentials/{lj_cut,harmonic,double_harmonic}.f90 ---- */
 
-enum { ORC_PAIR_LJCUT = 1, ORC_PAIR_HARMONIC = 2, ORC_PAIR_DOUBLE_HARMONIC = 3 };
+enum { ORC_PAIR_LJCUT = 1, ORC_PAIR_HARMONIC = 2, ORC_PAIR_DOUBLE_HARMONIC = 3, ORC_PAIR_BORN_MAYER = 4,
+       ORC_PAIR_R6 = 5 };
 /* par: LJCut {epsilon, sigma, cutoff}; Harmonic {k, r0, cutoff}; DoubleHarmonic {k1, r1, k2, r2,
- * cutoff}.  el[] are PARTICLE element ids (1-based), el1/el2 the filter bit masks of filter.f90.
+ * cutoff}; BornMayer {A, rho, cutoff}; r6 {A, r0, cutoff}.  el[] are PARTICLE element ids (1-based), el1/el2 the filter bit masks of filter.f90.
  * Returns -1 when a mask is passed to a potential that has none. */
 int orc_pair_energy_and_forces(int kind, const double *par, int shift, int nat, const double *r,
                                const double *Abox, const int *el, int el1, int el2,

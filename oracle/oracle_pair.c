@@ -7,6 +7,10 @@
  *   DoubleHarmonic  src/potentials/pair_potentials/double_harmonic.f90:140-230 (every directed
  *                   entry with a factor 1/2; epot_per_at receives en/2 per entry and atom, i.e. the
  *                   per-atom energies sum to twice epot -- kept as in the reference)
+ *   r6              src/potentials/pair_potentials/r6.f90:150-215 (as Harmonic: i > j, no mask)
+ *   BornMayer       src/potentials/pair_potentials/born_mayer.f90:200-275 (i <= j INCLUDING the
+ *                   i == j image entries, asymmetric element test, energy and forces only:
+ *                   wpot and the per-atom outputs are never touched)
  * Element filters are the bit masks of src/core/filter.f90 (bit k = particle element id k).
  * dr follows DIST_SQ / GET_DRJ (macros.inc:76): r_i - r_j + Abox.dc.
  */
@@ -155,6 +159,64 @@ int orc_pair_energy_and_forces(int kind, const double *par, int shift, int nat, 
           add_virial(w, wpot_per_at, i, j, dr, df);
         }
       }
+  } else if (kind == ORC_PAIR_R6) {
+    if (mask) return -1;
+    const double A = par[0], r0 = par[1], cutoff = par[2];
+    const double cut_sq = cutoff * cutoff;
+    for (int i = 0; i < nat; i++)
+      for (intptr_t jn = seed[i]; jn <= last[i]; jn++) {
+        int j = neighbors[jn - 1] - 1;
+        if (!(i > j)) continue;
+        if (!((IS_EL2(el1, el[i]) && IS_EL2(el2, el[j])) || (IS_EL2(el2, el[i]) && IS_EL2(el1, el[j])))) continue;
+        double dr[3], abs_dr;
+        dist(r, Abox, dc, i, j, jn, dr, &abs_dr);
+        if (abs_dr < cut_sq) {
+          abs_dr = sqrt(abs_dr);
+          double en = A / pow(r0 + abs_dr, 6);
+          double fo = 6 * en / (r0 + abs_dr);
+          *epot += en;
+          double df[3];
+          for (int k = 0; k < 3; k++) {
+            df[k] = fo * dr[k] / abs_dr;
+            f[3 * i + k] += df[k];
+            f[3 * j + k] -= df[k];
+          }
+          if (epot_per_at) {
+            epot_per_at[i] += en / 2;
+            epot_per_at[j] += en / 2;
+          }
+          add_virial(w, wpot_per_at, i, j, dr, df);
+        }
+      }
+  } else if (kind == ORC_PAIR_BORN_MAYER) {
+    if (mask) return -1;
+    const double A = par[0], rho = par[1], cutoff = par[2];
+    const double shift_e = A * exp(-cutoff / rho); /* always shifted, born_mayer.f90:169 */
+    double e = 0.0;
+    for (int i = 0; i < nat; i++) {
+      int want; /* filter the partner must match */
+      if (IS_EL2(el1, el[i])) want = el2;
+      else if (IS_EL2(el2, el[i])) want = el1;
+      else continue;
+      for (intptr_t jn = seed[i]; jn <= last[i]; jn++) {
+        int j = neighbors[jn - 1] - 1;
+        double dr[3], abs_dr;
+        dist(r, Abox, dc, i, j, jn, dr, &abs_dr);
+        if (i <= j && IS_EL2(want, el[j])) {
+          if (abs_dr < cutoff * cutoff) {
+            abs_dr = sqrt(abs_dr);
+            double exp_r = exp(-abs_dr / rho);
+            e = e + A * exp_r - shift_e;
+            for (int k = 0; k < 3; k++) {
+              double fk = (A / rho) * exp_r * dr[k] / abs_dr;
+              f[3 * i + k] += fk;
+              f[3 * j + k] -= fk;
+            }
+          }
+        }
+      }
+    }
+    *epot += e;
   } else {
     return -2;
   }

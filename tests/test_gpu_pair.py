@@ -12,6 +12,8 @@ CASES = dict(
     LJCut=(native.LJCut, oracle.PAIR_LJCUT, ('epsilon', 'sigma', 'cutoff')),
     Harmonic=(native.Harmonic, oracle.PAIR_HARMONIC, ('k', 'r0', 'cutoff')),
     DoubleHarmonic=(native.DoubleHarmonic, oracle.PAIR_DOUBLE_HARMONIC, ('k1', 'r1', 'k2', 'r2', 'cutoff')),
+    BornMayer=(native.BornMayer, oracle.PAIR_BORN_MAYER, ('A', 'rho', 'cutoff')),
+    r6=(native.r6, oracle.PAIR_R6, ('A', 'r0', 'cutoff')),
 )
 
 
@@ -19,13 +21,20 @@ def _both(name, atoms, par, shift=False, el1='*', el2='*', mask=None):
     cls, okind, keys = CASES[name]
     p = native.from_atoms(atoms)
     nl = native.Neighbors(400)
-    pot = cls(el1=el1, el2=el2, shift=shift, **par)
+    pot = cls(element1=el1, element2=el2, **par) if name == 'BornMayer' else cls(el1=el1, el2=el2, shift=shift, **par)
     pot.bind_to(p, nl)
     g = pot.energy_and_forces(p, nl, mask=mask, epot_per_at=True, wpot_per_at=True)
+    if name == 'BornMayer':
+        assert not g[3].any() and not g[6].any() and not g[2].any()      # reference: energy and forces only
     onl = oracle.neighbor_list(atoms.positions, atoms.cell, atoms.pbc, par['cutoff'], 400)
     o = oracle.pair_energy_and_forces(okind, [par[k] for k in keys], atoms.positions, atoms.cell, onl, atoms.symbols,
                                       el1=el1, el2=el2, shift=shift, mask=mask, per_at=True)
     return g, o
+
+
+def _check_ef(g, o):
+    assert abs(g[0] - o['epot']) <= RTOL * max(abs(o['epot']), 1.0)
+    assert np.abs(g[1] - o['f']).max() <= RTOL * max(1.0, np.abs(o['f']).max())
 
 
 def _check(g, o):
@@ -111,3 +120,22 @@ def test_calculator_interface():
     g, o = _both('LJCut', a, LJ)
     assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
     assert np.abs(f - o['f']).max() <= RTOL * max(1.0, np.abs(o['f']).max())
+
+
+def test_r6():
+    a = S.fcc('Ar', 5.3, (3, 3, 3))
+    a.rattle(0.2, seed=15)
+    for i in range(0, len(a), 4):
+        a.symbols[i] = 'Kr'
+    for el1, el2 in (('*', '*'), ('Ar', 'Kr')):
+        g, o = _both('r6', a, dict(A=50.0, r0=0.5, cutoff=7.0), el1=el1, el2=el2)
+        _check(g, o)
+
+
+def test_born_mayer_asymmetric_filters_and_self_images():
+    a = S.b1(['Na', 'Cl'], 5.64, (2, 2, 2))
+    a.rattle(0.1, seed=16)
+    par = dict(A=1000.0, rho=0.3, cutoff=6.0)           # cutoff > half the cell: image entries of an atom with itself
+    for el1, el2 in (('Na', 'Cl'), ('Cl', 'Na'), ('Na', 'Na'), ('*', 'Cl'), ('Na', '*'), ('*', '*')):
+        g, o = _both('BornMayer', a, par, el1=el1, el2=el2)
+        _check_ef(g, o)

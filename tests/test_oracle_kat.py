@@ -495,6 +495,18 @@ def test_fd_pair_potentials():
     check_fd(pair_calc(oracle.PAIR_DOUBLE_HARMONIC, [1.0, 1.0, 1.0, np.sqrt(2.0), 1.6], 1.6), a)
 
 
+def test_fd_r6_and_born_mayer():
+    a = S.fcc('Ar', 5.3, (3, 3, 3)); a.rattle(0.2, seed=15)
+    check_fd(pair_calc(oracle.PAIR_R6, [50.0, 0.5, 7.0], 7.0), a)
+    # BornMayer produces no virial in the reference: forces only
+    a = S.b1(['Na', 'Cl'], 5.64, (2, 2, 2)); a.rattle(0.1, seed=16)
+    calc = pair_calc(oracle.PAIR_BORN_MAYER, [1000.0, 0.3, 6.0], 6.0, el1='Na', el2='Cl')
+    o = calc(a)
+    idx = [0, 5, 11]
+    assert np.abs(fd_forces(calc, a, idx) - o['f'][idx]).max() < 1e-5 * max(1.0, np.abs(o['f']).max())
+    assert not o['wpot'].any()
+
+
 def test_lj_mask_additivity_and_filters():
     # tests/test_mask.py (LJCut row): e = e(mask) + e(not mask), same for forces and virial
     a = S.fcc('Ar', 5.3, (3, 3, 3)); a.rattle(0.2, seed=14)

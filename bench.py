@@ -105,6 +105,9 @@ def measured_peaks():
 # CPU legs (oracle) -- the only place bench.py executes oracle/
 # ----------------------------------------------------------------------------------------------
 
+CPU_FLAGS = ''
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -124,6 +127,8 @@ def cpu_sample(ncell=12, nforce=3, threads=1):
     a = S.fcc('Cu', A0, (ncell, ncell, ncell))
     a.rattle(0.05, seed=12345)
     eldb = eam.eldb(a.symbols)
+    global CPU_FLAGS
+    CPU_FLAGS = oracle.use_fast(True)
     oracle.set_threads(threads)
     try:
         t0 = time.perf_counter()
@@ -135,6 +140,7 @@ def cpu_sample(ncell=12, nforce=3, threads=1):
         t_force = (time.perf_counter() - t0) / nforce
     finally:
         oracle.set_threads(1)
+        oracle.use_fast(False)
     return len(a), t_build, t_force
 
 
@@ -169,7 +175,7 @@ def run_reference(args):
     value = nat / t
     sample = ('fcc Cu %d^3 cells = %d atoms per step (bounded sample of the 256000-atom workload), oracle port, '
               '%d OpenMP thread(s) of %d host threads for the EAM energy/forces and the neighbour build '
-              '(cutoff+%.1f A skin, 1 build amortised over %d steps)' % (ncell, nat, threads, host_threads(), SKIN, interval))
+              '(cutoff+%.1f A skin, 1 build amortised over %d steps); %s' % (ncell, nat, threads, host_threads(), SKIN, interval, CPU_FLAGS))
     out = dict(impl='reference', metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=args.gpus,
                steps=min(steps, 5), warmup=min(warm, 2), ms_per_step=t * 1e3, higher_is_better=True,
                scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
@@ -347,7 +353,7 @@ def run_ours(args):
                 value=ncpu / t, unit='atom-steps/s', cores=threads, kind='port',
                 sample='fcc Cu 24^3 cells = %d atoms, oracle port with %d OpenMP thread(s) of %d host threads: 3 EAM '
                        'force evaluations + 1 neighbour build (cutoff+%.1f A skin) amortised over the GPU '
-                       'run\'s rebuild interval of %.1f steps' % (ncpu, threads, host_threads(), SKIN, interval))
+                       'run\'s rebuild interval of %.1f steps; %s' % (ncpu, threads, host_threads(), SKIN, interval, CPU_FLAGS))
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -39,13 +39,47 @@ def build(force=False):
     return _LIB
 
 
+_strict = None
+_fast = None
+
+
 def lib():
-    global _lib
+    global _lib, _strict
     if _lib is None:
         build()
-        _lib = C.CDLL(_LIB)
-        _lib.orc_nl_build.restype = C.c_long
+        _strict = C.CDLL(_LIB)
+        _strict.orc_nl_build.restype = C.c_long
+        _lib = _strict
     return _lib
+
+
+def use_fast(on=True):
+    """bench.py's CPU legs only: switch to a copy of the oracle compiled ON THIS MACHINE with
+    -O3 -march=native (what SURVEY 8(d) asks the timed CPU path to use).  The known-answer tests
+    always run the strict -O2 -ffp-contract=off build.  Falls back to the strict build when the
+    compilation is not possible.  Returns the flags in use."""
+    global _lib, _fast
+    lib()
+    if not on:
+        _lib = _strict
+        return 'gcc -O2 -fopenmp -ffp-contract=off'
+    if _fast is None:
+        import tempfile
+        out = os.path.join(tempfile.gettempdir(), 'atx_oracle_fast_%d' % os.getuid())
+        try:
+            os.makedirs(out, exist_ok=True)
+            so = os.path.join(out, 'liboracle_fast.so')
+            srcs = [os.path.join(_HERE, s) for s in _SRCS]
+            subprocess.check_call(['gcc', '-O3', '-march=native', '-fopenmp', '-fPIC', '-shared', '-std=c99',
+                                   '-I' + _HERE, '-o', so] + srcs + ['-lm'], stderr=subprocess.DEVNULL)
+            _fast = C.CDLL(so)
+            _fast.orc_nl_build.restype = C.c_long
+        except Exception:
+            _fast = False
+    if _fast:
+        _lib = _fast
+        return 'gcc -O3 -march=native -fopenmp'
+    return 'gcc -O2 -fopenmp -ffp-contract=off'
 
 
 def _p(a, t=C.c_double):

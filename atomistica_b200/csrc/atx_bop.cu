@@ -1547,27 +1547,35 @@ extern "C" int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_nei
   ATX_PASS(atx_prepare_mask(ctx, nl, pot->sc, mask, &mask_sorted));
   size_t nslots = (size_t)nl->npairs + 1;
   double *epb = nullptr, *fpb = nullptr, *wpb = nullptr;
-  if (epot_per_bond) {
-    ATX_PASS(pot->epb.reserve(nslots));
-    ATX_CUDA(cudaMemsetAsync(pot->epb.ptr, 0, sizeof(double) * nslots, ctx->stream));
-    epb = pot->epb.ptr;
-  }
-  if (f_per_bond) {
-    ATX_PASS(pot->fpb.reserve(3 * nslots));
-    ATX_CUDA(cudaMemsetAsync(pot->fpb.ptr, 0, sizeof(double) * 3 * nslots, ctx->stream));
-    fpb = pot->fpb.ptr;
-  }
-  if (wpot_per_bond) {
-    ATX_PASS(pot->wpb.reserve(9 * nslots));
-    ATX_CUDA(cudaMemsetAsync(pot->wpb.ptr, 0, sizeof(double) * 9 * nslots, ctx->stream));
-    wpb = pot->wpb.ptr;
-  }
   if (nl->external) o.role = nl->role_ext.ptr;
-  ATX_PASS(bop_compute(pot, p, nl, mask_sorted, o, epb, fpb, wpb));
-  int h = 0;
-  ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (h) {
+  // The screened tables are sized when the list is built; with a library-mode Verlet shell the
+  // list can be reused while atoms gain bonds or screening neighbours.  If a table overflows, size
+  // again from the current configuration and repeat once.
+  for (int attempt = 0;; attempt++) {
+    if (epot_per_bond) {
+      ATX_PASS(pot->epb.reserve(nslots));
+      ATX_CUDA(cudaMemsetAsync(pot->epb.ptr, 0, sizeof(double) * nslots, ctx->stream));
+      epb = pot->epb.ptr;
+    }
+    if (f_per_bond) {
+      ATX_PASS(pot->fpb.reserve(3 * nslots));
+      ATX_CUDA(cudaMemsetAsync(pot->fpb.ptr, 0, sizeof(double) * 3 * nslots, ctx->stream));
+      fpb = pot->fpb.ptr;
+    }
+    if (wpot_per_bond) {
+      ATX_PASS(pot->wpb.reserve(9 * nslots));
+      ATX_CUDA(cudaMemsetAsync(pot->wpb.ptr, 0, sizeof(double) * 9 * nslots, ctx->stream));
+      wpb = pot->wpb.ptr;
+    }
+    ATX_PASS(bop_compute(pot, p, nl, mask_sorted, o, epb, fpb, wpb));
+    int h = 0;
+    ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (!h) break;
+    if (pot->screened && attempt == 0) {
+      pot->nb_cap = 0;   // forces the counting pass
+      continue;
+    }
     atx_set_error("Internal neighbor list exhausted, *nebmax* too small.");
     return ATX_ERROR_UNSPECIFIED;
   }

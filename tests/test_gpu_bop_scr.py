@@ -112,3 +112,25 @@ def test_calculator_interface():
     g, o = _both('Tersoff', None, a)
     assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
     assert np.abs(f - o['f']).max() <= RTOL * max(1.0, np.abs(o['f']).max())
+
+
+def test_list_reuse_with_verlet_shell(aC_small):
+    """calculator with a library-mode Verlet shell: the list (and the sizing of the screened tables)
+    is reused while the atoms move; results stay on the oracle"""
+    from atomistica_b200 import TersoffScr
+    a = aC_small.copy()
+    calc = TersoffScr(verlet_shell=0.8)
+    rng = np.random.RandomState(2)
+    db = P.complete_scr('Tersoff', None)
+    par, scr = oracle.bop_params(oracle.TERSOFF, db), oracle.bop_scr_params(db)
+    el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
+    for it in range(4):
+        f = calc.get_forces(a)
+        e = calc.results['energy']
+        onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, P.scr_cutoff(db), 1000)
+        o = oracle.bop_energy_and_forces(par, a.positions, a.cell, onl, el, scr=scr)
+        assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
+        assert np.abs(f - o['f']).max() <= RTOL * max(1.0, np.abs(o['f']).max())
+        a.positions = a.positions + rng.uniform(-0.1, 0.1, size=a.positions.shape)
+    builds, reused = calc.nl.counters()
+    assert reused >= 1

@@ -333,7 +333,7 @@ def run_ours(args):
                                        'calculator instance per GPU' % SKIN),
         gpu_launches=launches,
         clocks=clocks,
-        roofline=dict(bound='hbm', kernel='k_eam_force', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+        roofline=dict(bound='hbm', kernel='k_eam_force_fast<4,2,VIRIAL=0>', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
                       traffic=traffic, peak_source=peak_src, algorithmic_bytes_per_launch=alg_bytes,
                       avg_launch_ms=force_avg_ms, launches=force_n, list_neighbors_per_atom=z_list,
                       share_of_step=force_ms / dev_ms if dev_ms else None),

@@ -841,3 +841,77 @@ class Rebo2:
             out['f_per_bond'] = fpb
             out['wpot_per_bond'] = wpb.reshape(-1, 3, 3).transpose(0, 2, 1).copy()
         return out
+
+
+class Rebo2ScrStruct(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ('cc_ar_r1', 'cc_ar_r2', 'cc_bo_r1', 'cc_bo_r2', 'cc_nc_r1', 'cc_nc_r2',
+                                          'Cmin', 'Cmax')]
+
+
+# rebo2_type.f90:65-66, 204-213 (SCREENING branch)
+REBO2_SCR_DEFAULTS = dict(cc_in_r1=1.95, cc_in_r2=2.25, cc_ar_r1=2.179347, cc_ar_r2=2.819732,
+                          cc_bo_r1=1.866344, cc_bo_r2=2.758372, cc_nc_r1=1.217335, cc_nc_r2=4.000000,
+                          Cmin=1.00, Cmax=2.00)
+
+
+class Rebo2Scr(Rebo2):
+    """rebo2_scr (src/potentials/bop/rebo2/rebo2_scr.f90): screened REBO2, C-C bonds screened only,
+    trigonometric cutoffs, without the (alternative) dihedral term"""
+
+    def __init__(self, **kwargs):
+        sd = dict(REBO2_SCR_DEFAULTS)
+        base = {}
+        for k, v in kwargs.items():
+            if k in sd:
+                sd[k] = v
+            else:
+                base[k] = v
+        base.setdefault('cc_in_r1', sd['cc_in_r1'])
+        base.setdefault('cc_in_r2', sd['cc_in_r2'])
+        super().__init__(**base)
+        if self.d['with_dihedral']:
+            raise NotImplementedError('ALT_DIHEDRAL of Rebo2Scr is not restated')
+        self.sd = sd
+        q = Rebo2ScrStruct()
+        for k, _ in Rebo2ScrStruct._fields_:
+            setattr(q, k, sd[k])
+        self.q = q
+
+    def cutoff(self, symbols):
+        # rebo2_module.f90:95-119
+        cmax = self.sd['Cmax']
+        c_cc = np.sqrt(cmax * cmax / (4 * (cmax - 1))) * max(self.d['cc_in_r2'], self.sd['cc_ar_r2'],
+                                                             self.sd['cc_bo_r2'], self.sd['cc_nc_r2'])
+        s = set(symbols)
+        c = 0.0
+        if 'C' in s:
+            c = max(c, c_cc)
+        if 'H' in s:
+            c = max(c, self.d['hh_r2'])
+        return c
+
+    def energy_and_forces(self, r, cell, nl, ktyp, per_at=False, per_bond=False):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        nat = len(r)
+        abox = abox_from_cell(cell)
+        ktyp = np.ascontiguousarray(ktyp, dtype=np.int32)
+        epot = C.c_double(0.0)
+        f = np.zeros((nat, 3))
+        wpot = np.zeros(9)
+        epa = np.zeros(nat) if per_at else None
+        wpa = np.zeros((nat, 9)) if per_at else None
+        epb, fpb, wpb = _per_bond_arrays(nl, per_bond)
+        err = lib().orc_rebo2_scr_energy_and_forces(
+            C.byref(self.p), C.byref(self.q), C.c_int(nat), C.c_int(nat), _p(r), _p(abox), _p(ktyp, C.c_int),
+            _p(nl.seed, C.c_ssize_t), _p(nl.last, C.c_ssize_t), _p(nl.neighbors, C.c_int), _p(nl.dc, C.c_int),
+            C.byref(epot), _p(f), _p(wpot), _p(epa), _p(epb), _p(fpb), _p(wpa), _p(wpb))
+        assert err == 0, err
+        out = dict(epot=epot.value, f=f, wpot=wpot.reshape(3, 3).T.copy())
+        if per_at:
+            out['epot_per_at'] = epa
+            out['wpot_per_at'] = wpa.reshape(nat, 3, 3).transpose(0, 2, 1).copy()
+        if per_bond:
+            out['epot_per_bond'] = epb
+            out['f_per_bond'] = fpb
+            out['wpot_per_bond'] = wpb.reshape(-1, 3, 3).transpose(0, 2, 1).copy()
+        return out

@@ -170,6 +170,21 @@ void orc_table2d_eval(const orc_table2d_t *t, double nhi, double nci, double *v,
 void orc_table3d_eval(const orc_table3d_t *t, double nti, double ntj, double nconj, double *v,
                       double *dvdi, double *dvdj, double *dvdc);
 
+/* Rebo2Scr (rebo2_scr.f90): cut_in_* of orc_rebo2_params_t hold the INNER cutoff (cc_in_r1/r2 =
+ * 1.95/2.25, rebo2_type.f90:205-206); the attractive/repulsive, bond-order and neighbour-count
+ * cutoffs of C-C and the screening bounds come here (rebo2_type.f90:65-66, 208-213).  C-H and H-H
+ * use their single cutoff for all three families (rebo2_db.f90:194-219). */
+typedef struct {
+  double cc_ar_r1, cc_ar_r2, cc_bo_r1, cc_bo_r2, cc_nc_r1, cc_nc_r2, Cmin, Cmax;
+} orc_rebo2_scr_t;
+
+int orc_rebo2_scr_energy_and_forces(const orc_rebo2_params_t *par, const orc_rebo2_scr_t *scr, int nat,
+                                    int natloc, const double *r, const double *Abox, const int *ktyp,
+                                    const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                    const int *dc, double *epot, double *f, double *wpot,
+                                    double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                    double *wpot_per_at, double *wpot_per_bond);
+
 int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natloc,
                                 const double *r, const double *Abox, const int *ktyp,
                                 const intptr_t *seed, const intptr_t *last, const int *neighbors,

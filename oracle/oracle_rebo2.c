@@ -111,6 +111,23 @@ static void fCin(const orc_rebo2_params_t *p, int ijpot, double dr, double *val,
   }
 }
 
+/* fCar / fCbo / fCnc of the screened variant (rebo2_func.f90:87-165): the same trig_off between
+ * the pair's (l, h) of that cutoff family */
+static void trig_cut(double l, double h, double dr, double *val, double *dval) {
+  if (dr > h) { *val = 0.0; *dval = 0.0; }
+  else if (dr < l) { *val = 1.0; *dval = 0.0; }
+  else {
+    double fac = PI / (h - l);
+    if (dr <= l) { *val = 1.0; *dval = 0.0; }
+    else if (dr >= h) { *val = 0.0; *dval = 0.0; }
+    else {
+      double x = fac * (dr - l);
+      *val = 0.5 * (1.0 + cos(x));
+      *dval = -0.5 * fac * sin(x);
+    }
+  }
+}
+
 /* rebo2_func.f90:173-221 */
 static void VA(const orc_rebo2_params_t *p, int ijpot, double dr, double *val, double *dval) {
   if (ijpot == C_C) {
@@ -245,13 +262,42 @@ static int spositive(const int *s) {
   return s[2] > 0;
 }
 
-int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natloc,
-                                const double *r, const double *Abox, const int *ktyp,
-                                const intptr_t *seed, const intptr_t *last, const int *neighbors,
-                                const int *dc, double *epot, double *f_inout, double *wpot_inout,
-                                double *epot_per_at, double *epot_per_bond, double *f_per_bond,
-                                double *wpot_per_at, double *wpot_per_bond) {
+/* One kernel for Rebo2 (scr == NULL) and Rebo2Scr (bop_kernel_rebo2.f90 compiled with SCREENING,
+ * NUM_NEIGHBORS, ALT_DIHEDRAL; rebo2_scr.f90:60-64).  In the unscreened build the bond-order and
+ * neighbour-count cutoffs are aliases of the single cutoff (bop_kernel_rebo2.f90:22-30), here the
+ * three arrays then point to the same storage. */
+static int rebo2_kernel(const orc_rebo2_params_t *par, const orc_rebo2_scr_t *scr, int nat, int natloc,
+                        const double *r, const double *Abox, const int *ktyp,
+                        const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                        const int *dc, double *epot, double *f_inout, double *wpot_inout,
+                        double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                        double *wpot_per_at, double *wpot_per_bond) {
   const int typemax = 3;
+  if (scr && par->with_dihedral) return -3; /* ALT_DIHEDRAL (bop_kernel_rebo2.f90:2089-2371) not restated */
+  /* cutoff families, index ijpot-1 (rebo2_db.f90:170-253) */
+  double cut_ar_l[10], cut_ar_h[10], cut_bo_l[10], cut_bo_h[10], cut_nc_l[10], cut_nc_h[10], max_cut_sq[10];
+  for (int q = 0; q < 10; q++) {
+    cut_ar_l[q] = cut_bo_l[q] = cut_nc_l[q] = par->cut_in_l[q];
+    cut_ar_h[q] = cut_bo_h[q] = cut_nc_h[q] = par->cut_in_h[q];
+    max_cut_sq[q] = par->cut_in_h2[q];
+  }
+  double Cmin = 0, Cmax = 0, dC = 0, C_dr_cut = 0;
+  const double screening_threshold = log(1e-6), dot_threshold = 1e-10; /* rebo2_type.f90:68-69 */
+  if (scr) {
+    cut_ar_l[C_C - 1] = scr->cc_ar_r1; cut_ar_h[C_C - 1] = scr->cc_ar_r2;
+    cut_bo_l[C_C - 1] = scr->cc_bo_r1; cut_bo_h[C_C - 1] = scr->cc_bo_r2;
+    cut_nc_l[C_C - 1] = scr->cc_nc_r1; cut_nc_h[C_C - 1] = scr->cc_nc_r2;
+    for (int q = 0; q < 10; q++) {
+      double m = par->cut_in_h[q];
+      if (cut_ar_h[q] > m) m = cut_ar_h[q];
+      if (cut_bo_h[q] > m) m = cut_bo_h[q];
+      if (cut_nc_h[q] > m) m = cut_nc_h[q];
+      max_cut_sq[q] = m * m;
+    }
+    Cmin = scr->Cmin; Cmax = scr->Cmax;
+    dC = Cmax - Cmin;
+    C_dr_cut = Cmax * Cmax / (4 * (Cmax - 1)); /* rebo2_db.f90:105-108 */
+  }
   long ntot = 0;
   int nebmax = 0;
   for (int i = 0; i < nat; i++) {
@@ -271,6 +317,23 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
   double *bndnm = (double *)malloc(sizeof(double) * 3 * nebsize);
   double *cutfcnar = (double *)malloc(sizeof(double) * nebsize);
   double *cutdrvar = (double *)malloc(sizeof(double) * nebsize);
+  double *cutfcnbo = cutfcnar, *cutdrvbo = cutdrvar, *cutfcnnc = cutfcnar, *cutdrvnc = cutdrvar;
+  long *sneb_seed = NULL, *sneb_last = NULL;
+  if (scr) {
+    cutfcnbo = (double *)malloc(sizeof(double) * nebsize);
+    cutdrvbo = (double *)malloc(sizeof(double) * nebsize);
+    cutfcnnc = (double *)malloc(sizeof(double) * nebsize);
+    cutdrvnc = (double *)malloc(sizeof(double) * nebsize);
+  }
+  /* screening-neighbour bookkeeping (always allocated; empty ranges when unscreened) */
+  sneb_seed = (long *)malloc(sizeof(long) * nebsize);
+  sneb_last = (long *)malloc(sizeof(long) * nebsize);
+  long scap = nebsize + 16, snebtot = 0;
+  int *sneb = (int *)malloc(sizeof(int) * scap);
+  long *sbnd = (long *)malloc(sizeof(long) * scap);
+  double *cutdrarik = (double *)malloc(sizeof(double) * scap), *cutdrarjk = (double *)malloc(sizeof(double) * scap);
+  double *cutdrboik = (double *)malloc(sizeof(double) * scap), *cutdrbojk = (double *)malloc(sizeof(double) * scap);
+  double *cutdrncik = (double *)malloc(sizeof(double) * scap), *cutdrncjk = (double *)malloc(sizeof(double) * scap);
   long *neb_seed = (long *)malloc(sizeof(long) * (nat + 1));
   long *neb_last = (long *)malloc(sizeof(long) * (nat + 1));
   double *nn = (double *)calloc((size_t)typemax * (nat + 1), sizeof(double));
@@ -294,6 +357,11 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
   shift_t *dcofl = (shift_t *)calloc(nm2, sizeof(shift_t));
   shift_t *dcofi = (shift_t *)calloc(nebmax, sizeof(shift_t));
   int *numnbk = IALLOC(nebmax + 2), *numnbl = IALLOC(nebmax + 2);
+  long *seedi = (long *)calloc(nebmax + 1, sizeof(long)), *lasti = (long *)calloc(nebmax + 1, sizeof(long));
+  long *seedj = (long *)calloc(nebmax + 1, sizeof(long)), *lastj = (long *)calloc(nebmax + 1, sizeof(long));
+  long *seedk = (long *)calloc(nm2 + 1, sizeof(long)), *lastk = (long *)calloc(nm2 + 1, sizeof(long));
+  long *seedl = (long *)calloc(nm2 + 1, sizeof(long)), *lastl = (long *)calloc(nm2 + 1, sizeof(long));
+  double *zfaci = DALLOC(nebmax + 1), *zfacj = DALLOC(nebmax + 1);
   double *dri = DALLOC(3 * nebmax), *drj = DALLOC(3 * nebmax);
   double *drk = DALLOC(3 * nm2), *drl = DALLOC(3 * nm2);
 /* dnidk(:, ikc, t) with t in 1..3 */
@@ -322,10 +390,133 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
       double rlij = rij[0] * rij[0] + rij[1] * rij[1] + rij[2] * rij[2];
       int ijpot = Z2pair(ktypi, ktypj);
       double l = par->cut_in_l[ijpot - 1];
+      sneb_seed[nebtot] = snebtot;
+      sneb_last[nebtot] = snebtot - 1;
       if (rlij < l * l) {
         cutfcnar[nebtot] = 1.0;
         cutdrvar[nebtot] = 0.0;
+        cutfcnbo[nebtot] = 1.0; cutdrvbo[nebtot] = 0.0;
+        cutfcnnc[nebtot] = 1.0; cutdrvnc[nebtot] = 0.0;
         rlij = sqrt(rlij);
+      } else if (scr) {
+        /* bop_kernel_rebo2.f90:813-1101 */
+        if (!(rlij < max_cut_sq[ijpot - 1])) continue;
+        int screened = 0, need_derivative = 0;
+        double sij = 0.0, dsijdrij = 0.0;
+        long ineb = snebtot;
+        if (ijpot == C_C) {
+          intptr_t kn = seed[i];
+          while (!(screened || sij < screening_threshold) && kn <= last[i]) {
+            int k = neighbors[kn - 1] - 1;
+            double rik[3];
+            for (int a = 0; a < 3; a++) {
+              double sh = 0.0;
+              for (int c = 0; c < 3; c++) sh += M3(Abox, a, c) * (double)dc[3 * (kn - 1) + c];
+              rik[a] = r[3 * k + a] - r[3 * i + a] - sh;
+            }
+            double rik2 = rik[0] * rik[0] + rik[1] * rik[1] + rik[2] * rik[2];
+            if (rik2 < C_dr_cut * rlij) {
+              int same = (k == j) && dc[3 * (kn - 1)] == dc[3 * (jn - 1)] &&
+                         dc[3 * (kn - 1) + 1] == dc[3 * (jn - 1) + 1] && dc[3 * (kn - 1) + 2] == dc[3 * (jn - 1) + 2];
+              if (!same) {
+                double dot_ij_ik = rij[0] * rik[0] + rij[1] * rik[1] + rij[2] * rik[2];
+                double rlik = rik2;
+                double rjk[3] = {-rij[0] + rik[0], -rij[1] + rik[1], -rij[2] + rik[2]};
+                double dot_ij_jk = rij[0] * rjk[0] + rij[1] * rjk[1] + rij[2] * rjk[2];
+                double rljk = rjk[0] * rjk[0] + rjk[1] * rjk[1] + rjk[2] * rjk[2];
+                if (dot_ij_ik > dot_threshold && dot_ij_jk < -dot_threshold) {
+                  double xik = rlik / rlij, xjk = rljk / rlij;
+                  double xm = xik - xjk, xp = xik + xjk;
+                  double fac = 1.0 / (1 - xm * xm);
+                  double C = (2 * xp - xm * xm - 1) * fac;
+                  if (C <= Cmin) {
+                    screened = 1;
+                  } else if (C < Cmax) {
+                    need_derivative = 1;
+                    double Cmax_C = Cmax - C, C_Cmin = C - Cmin;
+                    double q = Cmax_C / C_Cmin;
+                    sij = sij - q * q;
+                    double dCdrik = 4 * xik * fac * (1 + (C - 1) * xm);
+                    double dCdrjk = 4 * xjk * fac * (1 - (C - 1) * xm);
+                    double dCdrij = -(dCdrik + dCdrjk);
+                    fac = 2 * Cmax_C * dC / (C_Cmin * C_Cmin * C_Cmin);
+                    dsijdrij = dsijdrij + fac * dCdrij;
+                    if (snebtot + 1 > scap) {
+                      scap = scap * 2;
+                      sneb = (int *)realloc(sneb, sizeof(int) * scap);
+                      sbnd = (long *)realloc(sbnd, sizeof(long) * scap);
+                      cutdrarik = (double *)realloc(cutdrarik, sizeof(double) * scap);
+                      cutdrarjk = (double *)realloc(cutdrarjk, sizeof(double) * scap);
+                      cutdrboik = (double *)realloc(cutdrboik, sizeof(double) * scap);
+                      cutdrbojk = (double *)realloc(cutdrbojk, sizeof(double) * scap);
+                      cutdrncik = (double *)realloc(cutdrncik, sizeof(double) * scap);
+                      cutdrncjk = (double *)realloc(cutdrncjk, sizeof(double) * scap);
+                    }
+                    sneb[snebtot] = k;
+                    sbnd[snebtot] = kn - 1;
+                    cutdrarik[snebtot] = fac * dCdrik / rlik;
+                    cutdrarjk[snebtot] = fac * dCdrjk / rljk;
+                    sneb_last[nebtot] = snebtot;
+                    snebtot++;
+                  }
+                }
+              }
+            }
+            kn++;
+          }
+        }
+        if ((screened || sij < screening_threshold) && rlij > par->cut_in_h2[ijpot - 1]) {
+          snebtot = ineb;
+          sneb_last[nebtot] = ineb - 1;
+          continue; /* fully screened */
+        }
+        rlij = sqrt(rlij);
+        double fcin, dfcin, fa, dfa, fb, dfb, fn, dfn;
+        if (screened) {
+          fCin(par, ijpot, rlij, &fcin, &dfcin);
+          cutfcnar[nebtot] = fcin; cutdrvar[nebtot] = dfcin;
+          cutfcnbo[nebtot] = fcin; cutdrvbo[nebtot] = dfcin;
+          cutfcnnc[nebtot] = fcin; cutdrvnc[nebtot] = dfcin;
+          snebtot = ineb;
+          sneb_last[nebtot] = ineb - 1;
+        } else if (need_derivative) {
+          sij = exp(sij);
+          fCin(par, ijpot, rlij, &fcin, &dfcin);
+          trig_cut(cut_ar_l[ijpot - 1], cut_ar_h[ijpot - 1], rlij, &fa, &dfa);
+          trig_cut(cut_bo_l[ijpot - 1], cut_bo_h[ijpot - 1], rlij, &fb, &dfb);
+          trig_cut(cut_nc_l[ijpot - 1], cut_nc_h[ijpot - 1], rlij, &fn, &dfn);
+          cutfcnar[nebtot] = (1.0 - fcin) * sij * fa + fcin;
+          cutdrvar[nebtot] = (1.0 - fcin) * sij * (dfa + fa * dsijdrij / rlij) - dfcin * sij * fa + dfcin;
+          cutfcnbo[nebtot] = (1.0 - fcin) * sij * fb + fcin;
+          cutdrvbo[nebtot] = (1.0 - fcin) * sij * (dfb + fb * dsijdrij / rlij) - dfcin * sij * fb + dfcin;
+          cutfcnnc[nebtot] = (1.0 - fcin) * sij * fn + fcin;
+          cutdrvnc[nebtot] = (1.0 - fcin) * sij * (dfn + fn * dsijdrij / rlij) - dfcin * sij * fn + dfcin;
+          for (long q = ineb; q < snebtot; q++) {
+            cutdrboik[q] = cutdrarik[q] * sij * fb * (1.0 - fcin);
+            cutdrbojk[q] = cutdrarjk[q] * sij * fb * (1.0 - fcin);
+            cutdrncik[q] = cutdrarik[q] * sij * fn * (1.0 - fcin);
+            cutdrncjk[q] = cutdrarjk[q] * sij * fn * (1.0 - fcin);
+            cutdrarik[q] = cutdrarik[q] * sij * fa * (1.0 - fcin);
+            cutdrarjk[q] = cutdrarjk[q] * sij * fa * (1.0 - fcin);
+          }
+        } else {
+          trig_cut(cut_ar_l[ijpot - 1], cut_ar_h[ijpot - 1], rlij, &fa, &dfa);
+          trig_cut(cut_bo_l[ijpot - 1], cut_bo_h[ijpot - 1], rlij, &fb, &dfb);
+          trig_cut(cut_nc_l[ijpot - 1], cut_nc_h[ijpot - 1], rlij, &fn, &dfn);
+          if (rlij < par->cut_in_h[ijpot - 1]) {
+            fCin(par, ijpot, rlij, &fcin, &dfcin);
+            cutfcnar[nebtot] = (1.0 - fcin) * fa + fcin;
+            cutdrvar[nebtot] = (1.0 - fcin) * dfa - dfcin * fa + dfcin;
+            cutfcnbo[nebtot] = (1.0 - fcin) * fb + fcin;
+            cutdrvbo[nebtot] = (1.0 - fcin) * dfb - dfcin * fb + dfcin;
+            cutfcnnc[nebtot] = (1.0 - fcin) * fn + fcin;
+            cutdrvnc[nebtot] = (1.0 - fcin) * dfn - dfcin * fn + dfcin;
+          } else {
+            cutfcnar[nebtot] = fa; cutdrvar[nebtot] = dfa;
+            cutfcnbo[nebtot] = fb; cutdrvbo[nebtot] = dfb;
+            cutfcnnc[nebtot] = fn; cutdrvnc[nebtot] = dfn;
+          }
+        }
       } else if (rlij < par->cut_in_h2[ijpot - 1]) {
         rlij = sqrt(rlij);
         fCin(par, ijpot, rlij, &cutfcnar[nebtot], &cutdrvar[nebtot]);
@@ -342,11 +533,14 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
     }
   }
 
+  /* bop_kernel_rebo2.f90:686-688: screening force factors start at zero */
+  double *sfacbo = DALLOC(snebtot + 1), *sfacnc = DALLOC(snebtot + 1);
+
   /* nn: bop_kernel_rebo2.f90:1189-1200 */
   for (int i = 0; i < nat; i++)
     for (long jn = neb_seed[i]; jn <= neb_last[i]; jn++) {
       int j = neb[jn];
-      if (ktyp[j] > 0) nn[(ktyp[j] - 1) + typemax * i] += cutfcnar[jn];
+      if (ktyp[j] > 0) nn[(ktyp[j] - 1) + typemax * i] += cutfcnnc[jn];
     }
 #define NN(t, i) nn[((t)-1) + typemax * (i)]
 
@@ -367,11 +561,13 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
       nebofi[ikc] = k;
       dcofi[ikc] = kdc;
       slotofi[ikc] = ik;
+      seedi[ikc] = sneb_seed[ik];
+      lasti[ikc] = sneb_last[ik];
       int ktypk = ktyp[k];
       double rlik = bndlen[ik];
       const double *rnik = &bndnm[3 * ik];
       for (int c = 0; c < 3; c++) dri[3 * ikc + c] = rlik * rnik[c];
-      double fcik = cutfcnar[ik], dfcikr = cutdrvar[ik];
+      double fcik = cutfcnnc[ik], dfcikr = cutdrvnc[ik];
       for (int c = 0; c < 3; c++) DN(dnidk, c, ikc, ktypk) = rnik[c] * dfcikr;
       if (ktypk == REBO2_C) {
         int nk = (int)(neb_last[k] - neb_seed[k] + 1);
@@ -379,9 +575,11 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
           int o = (int)(km - neb_seed[k]);
           nebofk[kmc + o] = neb[km];
           dcofk[kmc + o] = sadd(kdc, &dcell[3 * km]);
+          seedk[kmc + o] = sneb_seed[km];
+          lastk[kmc + o] = sneb_last[km];
           for (int c = 0; c < 3; c++) {
             drk[3 * (kmc + o) + c] = bndlen[km] * bndnm[3 * km + c];
-            xikdm[3 * o + c] = cutdrvar[km] * bndnm[3 * km + c];
+            xikdm[3 * o + c] = cutdrvnc[km] * bndnm[3 * km + c];
           }
         }
         double xik = NN(REBO2_C, k) + NN(REBO2_H, k) - fcik;
@@ -411,7 +609,7 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
       if (!((szero(jdc) && j > i) || spositive(jdc.s))) continue;
       int ijpot = bndtyp[ij];
       double rlij = bndlen[ij];
-      if (!(rlij < par->cut_in_h[ijpot - 1])) continue;
+      if (!(rlij < cut_ar_h[ijpot - 1])) continue;
 
       double fj[3] = {0, 0, 0};
       int ktypj = ktyp[j];
@@ -421,8 +619,8 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
       double fcarij = cutfcnar[ij], dfcarijr = cutdrvar[ij];
       double ni[4], nj[4]; /* index by type 1..3 */
       for (int t = 1; t <= 3; t++) { ni[t] = NN(t, i); nj[t] = NN(t, j); }
-      ni[ktypj] = ni[ktypj] - cutfcnar[ij];
-      nj[ktypi] = nj[ktypi] - cutfcnar[ij];
+      ni[ktypj] = ni[ktypj] - cutfcnnc[ij];
+      nj[ktypi] = nj[ktypi] - cutfcnnc[ij];
       double nconjj = 0.0, nconji = 0.0;
       memset(dnjdl, 0, sizeof(double) * 3 * nebmax * typemax);
       if (ni[REBO2_C] > 4.0) ni[REBO2_C] = 4.0;
@@ -440,14 +638,14 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
       /* ik_loop2 :1407-1587 */
       ikc = 0;
       for (long ik = istart; ik <= ifinsh; ik++, ikc++) {
-        double fcik = cutfcnar[ik];
+        double fcik = cutfcnbo[ik];
         if (ik != ij) {
           int ikpot = bndtyp[ik];
           double rlik = bndlen[ik];
-          if (rlik < par->cut_in_h[ikpot - 1]) {
+          if (rlik < cut_bo_h[ikpot - 1]) {
             const double *rnik = &bndnm[3 * ik];
             double rik[3] = {rlik * rnik[0], rlik * rnik[1], rlik * rnik[2]};
-            double dfcikr = cutdrvar[ik];
+            double dfcikr = cutdrvbo[ik];
             double qfacan, qfadan, gfacan, gddan, dgdn;
             hfun(par, ijpot, ikpot, rlij - rlik, &qfacan, &qfadan);
             double costh = rnik[0] * rnij[0] + rnik[1] * rnij[1] + rnik[2] * rnij[2];
@@ -461,6 +659,7 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
             double dcsdjk = -disjk * rlijr / rlik;
             dzdni = dzdni + fcik * dgdn * qfacan;
             double dzfac = fcik * gddan * qfacan;
+            zfaci[ikc] = gfacan * qfacan; /* saved for the screening-function derivative */
             zij = zij + fcik * gfacan * qfacan;
             double dzdrij = gfacan * fcik * qfadan;
             double dzdrik = gfacan * (dfcikr * qfacan - fcik * qfadan);
@@ -477,9 +676,11 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
             outer_add(wijb, -1.0, rij, df);
             outer_add(wijb, -1.0, rik, &dbidk[3 * ikc]);
           } else {
+            zfaci[ikc] = 0.0;
             for (int c = 0; c < 3; c++) dbidk[3 * ikc + c] = 0.0;
           }
         } else {
+          fcik = cutfcnnc[ik];
           nconji = nconjit - fcik * fxik[ikc];
         }
       }
@@ -506,12 +707,14 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
         if (!(l != i || !szero(ldc))) continue;
         nebofj[jlc] = l;
         dcofj[jlc] = ldc;
+        seedj[jlc] = sneb_seed[jl];
+        lastj[jlc] = sneb_last[jl];
         int ktypl = ktyp[l];
         int jlpot = bndtyp[jl];
         double rljl = bndlen[jl];
         const double *rnjl = &bndnm[3 * jl];
         for (int c = 0; c < 3; c++) drj[3 * jlc + c] = rljl * rnjl[c];
-        double fcjl = cutfcnar[jl], dfcjlr = cutdrvar[jl];
+        double fcjl = cutfcnnc[jl], dfcjlr = cutdrvnc[jl];
         for (int c = 0; c < 3; c++) DN(dnjdl, c, jlc, ktypl) = rnjl[c] * dfcjlr;
         if (ktypl == REBO2_C) {
           int nl_ = (int)(neb_last[l] - neb_seed[l] + 1);
@@ -519,9 +722,11 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
             int o = (int)(ln - neb_seed[l]);
             nebofl[lnc + o] = neb[ln];
             dcofl[lnc + o] = sadd(ldc, &dcell[3 * ln]);
+            seedl[lnc + o] = sneb_seed[ln];
+            lastl[lnc + o] = sneb_last[ln];
             for (int c = 0; c < 3; c++) {
               drl[3 * (lnc + o) + c] = bndlen[ln] * bndnm[3 * ln + c];
-              xjldn[3 * o + c] = cutdrvar[ln] * bndnm[3 * ln + c];
+              xjldn[3 * o + c] = cutdrvnc[ln] * bndnm[3 * ln + c];
             }
           }
           double xjl = NN(REBO2_C, l) + NN(REBO2_H, l) - fcjl;
@@ -542,7 +747,9 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
           fxjl[jlc] = 0.0;
           for (int c = 0; c < 3; c++) dncnjdl[3 * jlc + c] = 0.0;
         }
-        if (rljl < par->cut_in_h[jlpot - 1]) {
+        if (rljl < cut_bo_h[jlpot - 1]) {
+          fcjl = cutfcnbo[jl];       /* the angular part uses the bond-order cutoff (:1755-1756) */
+          dfcjlr = cutdrvbo[jl];
           double rjl[3] = {rljl * rnjl[0], rljl * rnjl[1], rljl * rnjl[2]};
           double qfacan, qfadan, gfacan, gddan, dgdn;
           hfun(par, ijpot, jlpot, rlij - rljl, &qfacan, &qfadan);
@@ -557,6 +764,7 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
           double dcsdil = -disil * rlijr / rljl;
           dzdnj = dzdnj + fcjl * dgdn * qfacan;
           double dzfac = fcjl * gddan * qfacan;
+          zfacj[jlc] = gfacan * qfacan;
           zji = zji + fcjl * gfacan * qfacan;
           double dzdrji = gfacan * fcjl * qfadan;
           double dzdrjl = gfacan * (dfcjlr * qfacan - fcjl * qfadan);
@@ -573,6 +781,7 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
           outer_add(wjib, 1.0, rij, df);
           outer_add(wjib, -1.0, rjl, &dbjdl[3 * jlc]);
         } else {
+          zfacj[jlc] = 0.0;
           for (int c = 0; c < 3; c++) dbjdl[3 * jlc + c] = 0.0;
         }
         jlc++;
@@ -608,7 +817,7 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
             shift_t kdc = dcofi[ikc3];
             double rlik = bndlen[ik];
             const double *rnik = &bndnm[3 * ik];
-            double fcik = cutfcnar[ik], dfcikr = cutdrvar[ik];
+            double fcik = cutfcnbo[ik], dfcikr = cutdrvbo[ik];
             double dot_ij_ik = rnij[0] * rnik[0] + rnij[1] * rnik[1] + rnij[2] * rnik[2];
             double dcik = 1.0 - dot_ij_ik * dot_ij_ik;
             for (long jl = neb_seed[j]; jl <= neb_last[j]; jl++) {
@@ -617,7 +826,7 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
               if ((l != i || !szero(ldc)) && (l != k || !seq(ldc, kdc))) {
                 double rljl = bndlen[jl];
                 const double *rnjl = &bndnm[3 * jl];
-                double fcjl = cutfcnar[jl], dfcjlr = cutdrvar[jl];
+                double fcjl = cutfcnbo[jl], dfcjlr = cutdrvbo[jl];
                 double dot_ij_jl = rnij[0] * rnjl[0] + rnij[1] * rnjl[1] + rnij[2] * rnjl[2];
                 double dot_ik_jl = rnik[0] * rnjl[0] + rnik[1] * rnjl[1] + rnik[2] * rnjl[2];
                 double dcjl = 1.0 - dot_ij_jl * dot_ij_jl;
@@ -747,10 +956,68 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
         if (slotofi[ikc] == ij) continue;
         int k = nebofi[ikc];
         for (int c = 0; c < 3; c++) f[3 * k + c] += -dfbij * dbidk[3 * ikc + c];
+        if (scr) {
+          /* :2611-2648 forces due to screening of the bonds i-k */
+          if (seedi[ikc] <= lasti[ikc]) {
+            double dffac2;
+            if (ktyp[k] == REBO2_C) dffac2 = dpdnci * dfbij + dfdni + dfdncni * fxik[ikc];
+            else dffac2 = dpdnhi * dfbij + dfdni + dfdncni * fxik[ikc];
+            for (long q = seedi[ikc]; q <= lasti[ikc]; q++) {
+              sfacbo[q] = sfacbo[q] + zfaci[ikc] * dfbij;
+              sfacnc[q] = sfacnc[q] + dffac2;
+            }
+          }
+          double dffac3 = dfdncni * dnconjidxi[ikc];
+          for (int km = numnbk[ikc]; km < numnbk[ikc + 1]; km++)
+            if (nebofk[km] != i || !szero(dcofk[km]))
+              for (long q = seedk[km]; q <= lastk[km]; q++) sfacnc[q] = sfacnc[q] + dffac3;
+        }
       }
       for (jlc = 0; jlc < numnbj; jlc++) {
         int l = nebofj[jlc];
         for (int c = 0; c < 3; c++) f[3 * l + c] += -dfbji * dbjdl[3 * jlc + c];
+        if (scr) {
+          /* :2673-2712 */
+          if (seedj[jlc] <= lastj[jlc]) {
+            double dffac2;
+            if (ktyp[l] == REBO2_C) dffac2 = dpdncj * dfbji + dfdnj + dfdncnj * fxjl[jlc];
+            else dffac2 = dpdnhj * dfbji + dfdnj + dfdncnj * fxjl[jlc];
+            for (long q = seedj[jlc]; q <= lastj[jlc]; q++) {
+              sfacbo[q] = sfacbo[q] + zfacj[jlc] * dfbji;
+              sfacnc[q] = sfacnc[q] + dffac2;
+            }
+          }
+          double dffac3 = dfdncnj * dnconjjdxj[jlc];
+          for (int ln = numnbl[jlc]; ln < numnbl[jlc + 1]; ln++)
+            if (nebofl[ln] != j || !seq(dcofl[ln], jdc))
+              for (long q = seedl[ln]; q <= lastl[ln]; q++) sfacnc[q] = sfacnc[q] + dffac3;
+        }
+      }
+      if (scr) {
+        /* :2717-2757 forces on the screening neighbours of bond i-j, attractive/repulsive part */
+        double dffs = frij + baveij * faij;
+        for (long q = sneb_seed[ij]; q <= sneb_last[ij]; q++) {
+          int k = sneb[q];
+          double rik[3], rjk[3], d1[3];
+          for (int a = 0; a < 3; a++) {
+            double sh = 0.0;
+            for (int c = 0; c < 3; c++) sh += M3(Abox, a, c) * (double)dc[3 * sbnd[q] + c];
+            rik[a] = r[3 * k + a] - r[3 * i + a] - sh;
+            rjk[a] = -rij[a] + rik[a];
+          }
+          for (int c = 0; c < 3; c++) {
+            d1[c] = dffs * cutdrarik[q] * rik[c];
+            fi[c] += d1[c];
+            f[3 * k + c] += -d1[c];
+          }
+          outer_add(wij, 1.0, rik, d1);
+          for (int c = 0; c < 3; c++) {
+            d1[c] = dffs * cutdrarjk[q] * rjk[c];
+            fj[c] += d1[c];
+            f[3 * k + c] += -d1[c];
+          }
+          outer_add(wij, 1.0, rjk, d1);
+        }
       }
       for (int c = 0; c < 9; c++) wpot[c] += wij[c];
       if (wpot_per_bond)
@@ -763,6 +1030,56 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
       for (int c = 0; c < 3; c++) f[3 * j + c] += fj[c];
     }
     for (int c = 0; c < 3; c++) f[3 * i + c] += fi[c];
+  }
+
+  if (scr) {
+    /* loop 3 over ALL atoms: forces due to screening via the bond-order and neighbour-count
+     * cutoffs (bop_kernel_rebo2.f90:2783-2871) */
+    for (int i = 0; i < nat; i++) {
+      if (ktyp[i] <= 0) continue;
+      double fi[3] = {0, 0, 0};
+      for (long ij = neb_seed[i]; ij <= neb_last[i]; ij++) {
+        int j = neb[ij];
+        double fj[3] = {0, 0, 0}, wij[9] = {0};
+        double rij[3] = {bndlen[ij] * bndnm[3 * ij], bndlen[ij] * bndnm[3 * ij + 1], bndlen[ij] * bndnm[3 * ij + 2]};
+        for (long q = sneb_seed[ij]; q <= sneb_last[ij]; q++) {
+          cutdrboik[q] = sfacbo[q] * cutdrboik[q] + sfacnc[q] * cutdrncik[q];
+          cutdrbojk[q] = sfacbo[q] * cutdrbojk[q] + sfacnc[q] * cutdrncjk[q];
+        }
+        for (long q = sneb_seed[ij]; q <= sneb_last[ij]; q++) {
+          int k = sneb[q];
+          double rik[3], rjk[3], d1[3];
+          for (int a = 0; a < 3; a++) {
+            double sh = 0.0;
+            for (int c = 0; c < 3; c++) sh += M3(Abox, a, c) * (double)dc[3 * sbnd[q] + c];
+            rik[a] = r[3 * k + a] - r[3 * i + a] - sh;
+            rjk[a] = -rij[a] + rik[a];
+          }
+          for (int c = 0; c < 3; c++) {
+            d1[c] = cutdrboik[q] * rik[c];
+            fi[c] += d1[c];
+            f[3 * k + c] += -d1[c];
+          }
+          outer_add(wij, 1.0, rik, d1);
+          for (int c = 0; c < 3; c++) {
+            d1[c] = cutdrbojk[q] * rjk[c];
+            fj[c] += d1[c];
+            f[3 * k + c] += -d1[c];
+          }
+          outer_add(wij, 1.0, rjk, d1);
+        }
+        for (int c = 0; c < 9; c++) wpot[c] += wij[c];
+        if (wpot_per_bond)
+          for (int c = 0; c < 9; c++) wpot_per_bond[9 * nbb[ij] + c] += wij[c];
+        if (wpot_per_at)
+          for (int c = 0; c < 9; c++) {
+            wpot_per_at[9 * i + c] += wij[c] / 2;
+            wpot_per_at[9 * j + c] += wij[c] / 2;
+          }
+        for (int c = 0; c < 3; c++) f[3 * j + c] += fj[c];
+      }
+      for (int c = 0; c < 3; c++) f[3 * i + c] += fi[c];
+    }
   }
 
   double e = 0.0;
@@ -781,5 +1098,31 @@ int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natl
   free(fxik); free(fxjl); free(nebofi); free(nebofj); free(nebofk); free(nebofl); free(slotofi);
   free(dcofj); free(dcofk); free(dcofl); free(dcofi); free(numnbk); free(numnbl);
   free(dri); free(drj); free(drk); free(drl);
+  if (scr) { free(cutfcnbo); free(cutdrvbo); free(cutfcnnc); free(cutdrvnc); }
+  free(sneb_seed); free(sneb_last); free(sneb); free(sbnd); free(cutdrarik); free(cutdrarjk);
+  free(cutdrboik); free(cutdrbojk); free(cutdrncik); free(cutdrncjk); free(sfacbo); free(sfacnc);
+  free(seedi); free(lasti); free(seedj); free(lastj); free(seedk); free(lastk); free(seedl); free(lastl);
+  free(zfaci); free(zfacj);
   return err;
+}
+
+int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natloc,
+                                const double *r, const double *Abox, const int *ktyp,
+                                const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                const int *dc, double *epot, double *f_inout, double *wpot_inout,
+                                double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                double *wpot_per_at, double *wpot_per_bond) {
+  return rebo2_kernel(par, NULL, nat, natloc, r, Abox, ktyp, seed, last, neighbors, dc, epot, f_inout, wpot_inout,
+                      epot_per_at, epot_per_bond, f_per_bond, wpot_per_at, wpot_per_bond);
+}
+
+int orc_rebo2_scr_energy_and_forces(const orc_rebo2_params_t *par, const orc_rebo2_scr_t *scr, int nat,
+                                    int natloc, const double *r, const double *Abox, const int *ktyp,
+                                    const intptr_t *seed, const intptr_t *last, const int *neighbors,
+                                    const int *dc, double *epot, double *f_inout, double *wpot_inout,
+                                    double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                    double *wpot_per_at, double *wpot_per_bond) {
+  if (!scr) return -4;
+  return rebo2_kernel(par, scr, nat, natloc, r, Abox, ktyp, seed, last, neighbors, dc, epot, f_inout, wpot_inout,
+                      epot_per_at, epot_per_bond, f_per_bond, wpot_per_at, wpot_per_bond);
 }

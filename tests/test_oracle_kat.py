@@ -66,6 +66,15 @@ def rebo2_calc(**kw0):
     return calc
 
 
+def rebo2_scr_calc(**kw0):
+    rb = oracle.Rebo2Scr(**kw0)
+
+    def calc(a, **kw):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, rb.cutoff(a.symbols), 1000)
+        return rb.energy_and_forces(a.positions, a.cell, nl, rb.ktyp(a.symbols), **kw)
+    return calc
+
+
 def eam_calc(setfl):
     eam = oracle.EAM(setfl)
 
@@ -585,6 +594,57 @@ def test_surface_energy_100(pot, mat, sym, a0):
     # the reference allows 5 %; the restated kernels reproduce its 3-digit table values (also where the
     # screened and unscreened rows differ: C 5.59 vs 5.88, Si 1.95 vs 1.90, SiC 3.93 vs 3.87)
     assert abs(es - ref) < 0.006, (es, ref)
+
+
+# ---- Rebo2Scr (screened REBO2) ----------------------------------------------------------------------
+
+@pytest.mark.parametrize('name', MOLS)
+def test_rebo2scr_atomization_energy(name):
+    # tests/test_rebo2_molecules.py:117-118: Rebo2Scr(dihedral=False) against the same table
+    db = json.load(open(os.path.join(GOLDEN, 'molecules.json')))
+    builtin = _builtin_molecules()
+    sym, pos = builtin[name] if name in builtin else (db[name]['symbols'], db[name]['positions'])
+    e = _relaxed_energy(sym, pos, rebo2_scr_calc())
+    assert abs(e - KAT['rebo2_atomization_eV'][name]) < KAT['rebo2_atomization_tol_eV'], (name, e)
+
+
+def test_rebo2scr_bulk_diamond():
+    # tests/test_bulk_properties.py:130-133: same literature values as Rebo2, 5 %
+    ref = KAT['bulk']['Rebo2_dia_C']
+    Ec, a0, C11, C12 = bulk_props(rebo2_scr_calc(), lambda a0: S.diamond('C', a0, (2, 2, 2)), ref['a0'])
+    tol = KAT['bulk_tol_rel']
+    assert rel(Ec, ref['Ec']) < tol and rel(a0, ref['a0']) < tol
+    assert rel(C11, ref['C11']) < tol
+    assert rel(C12, ref['C12']) < 2 * tol or abs(C12 - ref['C12']) < 8.0
+
+
+def test_fd_rebo2scr(aC_small):
+    # tests/test_forces_and_virial.py:142-146 (Rebo2Scr row) + hydrocarbon solid
+    check_fd(rebo2_scr_calc(), aC_small)
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.7, (2, 2, 2))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=6)
+    check_fd(rebo2_scr_calc(), a)
+    a = S.diamond('C', 3.566, (2, 2, 2)); a.rattle(0.15, seed=9)
+    check_fd(rebo2_scr_calc(), a)
+
+
+def test_dimers_rebo2scr():
+    # tests/test_dimers.py:38-110: C2, H2 and CH dimers stretched in 1000 steps stay smooth
+    vac = 4.0
+    for syms, d0, d1, de, df in ((['C', 'C'], 1.2, 3.1, 0.05, 0.5), (['H', 'H'], 0.6, 1.8, 0.02, 0.2),
+                                 (['C', 'H'], 0.8, 1.9, 0.03, 0.3)):
+        for calc in (rebo2_calc(), rebo2_scr_calc()):
+            es, fs = [], []
+            for dist in np.linspace(d0, d1, 1000):
+                a = S.Atoms(syms, [[vac, vac, vac], [vac + dist, vac, vac]], [2 * vac + d1, 2 * vac, 2 * vac], True)
+                o = calc(a)
+                es.append(o['epot'])
+                fs.append(o['f'][0, 0])
+            assert np.abs(np.diff(es)).max() < de
+            assert np.abs(np.diff(fs)).max() < df
 
 
 # ---- neighbour list (tests/test_neighbor_list.py) -------------------------------------------------

@@ -915,3 +915,11 @@ class Rebo2Scr(Rebo2):
             out['f_per_bond'] = fpb
             out['wpot_per_bond'] = wpb.reshape(-1, 3, 3).transpose(0, 2, 1).copy()
         return out
+
+
+def cutoff_eval(kind, r1, r2, r):
+    """kind 'trig_off' or 'exp': (value, derivative) of the cutoff function between r1 and r2"""
+    v, d = C.c_double(0.0), C.c_double(0.0)
+    lib().orc_cutoff_eval(C.c_int(0 if kind == 'trig_off' else 1), C.c_double(r1), C.c_double(r2), C.c_double(r),
+                          C.byref(v), C.byref(d))
+    return v.value, d.value

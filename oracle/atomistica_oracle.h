@@ -135,6 +135,9 @@ int orc_pair_energy_and_forces(int kind, const double *par, int shift, int nat, 
                                const int *dc, const int *mask, double *epot, double *f, double *wpot,
                                double *epot_per_at, double *wpot_per_at);
 
+/* cutoff functions of src/support/cutoff.f90 (0 = trig_off :152-196, 1 = exp_cutoff :232-293) */
+void orc_cutoff_eval(int kind, double r1, double r2, double r, double *val, double *dval);
+
 /* ---- REBO2: src/potentials/bop/rebo2/ ---- */
 
 typedef struct {

@@ -968,3 +968,16 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
 #undef cut_ar_h
   return 0;
 }
+
+
+/* test hook for the cutoff functions (FRUIT tests src/unittests/test_cutoff.f90): kind 0 = trig_off,
+ * 1 = exp_cutoff */
+void orc_cutoff_eval(int kind, double r1, double r2, double r, double *val, double *dval) {
+  if (kind == 0) {
+    trig_off(r1, r2, r, val, dval);
+  } else {
+    exp_cutoff_t t;
+    exp_cutoff_init(&t, r1, r2);
+    exp_cutoff_f(&t, r, val, dval);
+  }
+}

@@ -755,3 +755,23 @@ def test_threaded_oracle_matches_serial(cu_setfl):
     assert np.array_equal(n1.neighbors[:n], n2.neighbors[:n]) and np.array_equal(n1.dc[:n], n2.dc[:n])
     assert abs(o1['epot'] - o2['epot']) < 1e-12 * abs(o1['epot'])
     assert np.abs(o1['f'] - o2['f']).max() < 1e-12
+
+
+@pytest.mark.parametrize('kind', ['trig_off', 'exp'])
+def test_cutoff_functions_fruit(kind):
+    """src/unittests/test_cutoff.f90 (MAKE_CUTOFF_TEST): 1 below the window, 0 above, values in
+    [0, 1], derivative of the right sign and consistent with finite differences (tol 1e-6)"""
+    r1, r2, tol, dr = 1.5, 2.75, 1e-6, 1e-6
+    lo, hi = 1.05 * r1, 0.95 * r2
+    v, d = oracle.cutoff_eval(kind, lo, hi, r1)
+    assert abs(v - 1.0) < tol and abs(d) < tol
+    v, d = oracle.cutoff_eval(kind, lo, hi, r2)
+    assert abs(v) < tol and abs(d) < tol
+    for i in range(101):
+        v, d = oracle.cutoff_eval(kind, lo, hi, r1 + i * (r2 - r1) / 100.0)
+        assert 0.0 <= v <= 1.0 and (0.0 - 1.0) * d >= 0.0
+    for i in range(100):
+        x = r1 + i * (r2 - r1) / 1000.0
+        v, d = oracle.cutoff_eval(kind, lo, hi, x)
+        v2, d2 = oracle.cutoff_eval(kind, lo, hi, x + dr)
+        assert abs((v2 - v) / dr - 0.5 * (d + d2)) < tol

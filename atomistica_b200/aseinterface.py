@@ -154,6 +154,14 @@ class Atomistica:
     def get_stresses(self, atoms):
         return self.calculate(atoms, ('stresses',))['stresses']
 
+    # aseinterface.py:459-470
+    def get_neighbors(self):
+        """(i, j, abs_dr) of the current neighbour list, like the reference's calculator"""
+        return self.nl.get_neighbors(self.particles)
+
+    def __str__(self):
+        return 'Atomistica([' + ','.join(type(pot).__name__ for pot in self.pots) + '])'
+
 
 def _calculator(cls):
     # aseinterface.py:491-504: classes ending in 'Scr' get avgn = 1000 (longer lists)

@@ -1265,11 +1265,11 @@ static int launch_center_v(atx_bop *pot, atx_particles *p, atx_neighbors *nl, co
                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
                          int nblocks, int pstride) {
   size_t smem = sizeof(BondSmem<NB>);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_dev = -1;   // the attribute belongs to the device: set it again when the device changes
+  if (attr_dev != pot->ctx->device) {
     ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB, VIRIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    attr_set = true;
+    attr_dev = pot->ctx->device;
   }
   k_bop_center<KIND, NB, MINB, VIRIAL><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
       nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
@@ -1312,11 +1312,11 @@ static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, c
     default: ATX_PASS((launch_center<KIND, BOP_NB_MAX>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
   }
   size_t smem = sizeof(BondSmem<BOP_NB_MAX>);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int attr_dev = -1;
+  if (attr_dev != pot->ctx->device) {
     ATX_CUDA(cudaFuncSetAttribute(k_bop_center_queued<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    attr_set = true;
+    attr_dev = pot->ctx->device;
   }
   k_bop_center_queued<KIND><<<nq, BOP_BLOCK, smem, st>>>(
       p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f, pe_own, o.wpa,

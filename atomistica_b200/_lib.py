@@ -59,6 +59,11 @@ class AtxRebo2Params(C.Structure):
         ('with_dihedral', C.c_int)] + [(k, c_double_p) for k in ('Fcc', 'Fch', 'Fhh', 'Tcc', 'Pcc', 'Pch')]
 
 
+class AtxRebo2Screening(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ('cc_ar_r1', 'cc_ar_r2', 'cc_bo_r1', 'cc_bo_r2', 'cc_nc_r1', 'cc_nc_r2',
+                                          'Cmin', 'Cmax')]
+
+
 # every symbol include/atomistica_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     'atx_ctx_create', 'atx_ctx_destroy', 'atx_ctx_synchronize', 'atx_last_error', 'atx_version',
@@ -73,7 +78,7 @@ SYMBOLS = [
     'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_create_juslin', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
     'atx_pair_create', 'atx_pair_destroy', 'atx_pair_bind_to', 'atx_pair_energy_and_forces',
     'atx_pair_set_store_outputs',
-    'atx_rebo2_create', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',
+    'atx_rebo2_create', 'atx_rebo2_create_screened', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',
     'atx_md_create', 'atx_md_destroy', 'atx_md_run', 'atx_md_get_state', 'atx_md_get_stats',
     'atx_dd_get_unique_id', 'atx_dd_create', 'atx_dd_destroy', 'atx_dd_md_create', 'atx_dd_md_destroy',
     'atx_dd_md_run', 'atx_dd_md_get_count', 'atx_dd_md_get_state', 'atx_dd_md_get_stats',

@@ -182,5 +182,6 @@ DoubleHarmonic = _calculator(native.DoubleHarmonic)
 BornMayer = _calculator(native.BornMayer)
 r6 = _calculator(native.r6)
 Rebo2 = _calculator(native.Rebo2)
+Rebo2Scr = _calculator(native.Rebo2Scr)
 TabulatedAlloyEAM = _calculator(native.TabulatedAlloyEAM)
 TabulatedEAM = _calculator(native.TabulatedEAM)

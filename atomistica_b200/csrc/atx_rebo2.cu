@@ -18,6 +18,10 @@
 
 #include "atx_rebo2_func.cuh"
 
+#define RBS_ADD(p, v) atomicAdd((p), (v))
+#define RBS_OR(p, v) atomicOr((p), (v))
+#include "atx_rebo2_scr.cuh"
+
 struct atx_rebo2 {
   atx_ctx *ctx = nullptr;
   Rebo2Dev dev{};
@@ -32,6 +36,14 @@ struct atx_rebo2 {
   DevBuf<double> epb, fpb, wpb, epa_out;
   DevBuf<int> flag;
   PotScratch sc;
+  // screened variant (Rebo2Scr): b_cut holds the attractive/repulsive cutoff, b_cbo / b_cnc the
+  // bond-order and neighbour-count cutoffs, s_* the screening neighbours (stride nss per atom)
+  bool screened = false;
+  RbsCut scr{};
+  int nss = 0;
+  DevBuf<int> b_sseed, b_scnt, s_ent;
+  DevBuf<double2> b_cbo, b_cnc;
+  DevBuf<double> s_arik, s_arjk, s_boik, s_bojk, s_ncik, s_ncjk, s_facbo, s_facnc;
 };
 
 // ---- kernel 1: bond table + nn -------------------------------------------------------------
@@ -531,6 +543,58 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
   }
 }
 
+// ---- screened variant: thin kernels around the per-atom functions of atx_rebo2_scr.cuh ---------
+
+__global__ void k_rbs_bonds(RbsTab T, Mat3 A, Rebo2Dev P, RbsCut S, const double4 *__restrict__ pos4,
+                            const long long *__restrict__ seed, const int2 *__restrict__ list,
+                            const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= T.nat) return;
+  rbs_bonds_atom(T, A, P, S, pos4, seed, list, s);
+}
+
+// partials layout [RBS_NSUM][nbtot]; this launch fills columns off .. off + gridDim.x
+__global__ void __launch_bounds__(RB_BLOCK)
+k_rbs_force(RbsTab T, Mat3 A, Rebo2Dev P, RbsCut S, const double4 *__restrict__ pos4,
+            const long long *__restrict__ seed, const int2 *__restrict__ list,
+            const int *__restrict__ order, double *__restrict__ f, double *__restrict__ epa,
+            double *__restrict__ wpa, double *__restrict__ epb, double *__restrict__ fpb,
+            double *__restrict__ wpb, double *__restrict__ partials, int nbtot, int off,
+            const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * (RB_BLOCK / 32)];
+  const int i = blockIdx.x * RB_BLOCK + threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+  if (i < T.nat) rbs_force_atom(T, A, P, S, pos4, seed, list, order, f, epa, wpa, epb, fpb, wpb, i, acc);
+  atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * nbtot + off + blockIdx.x] = acc[k];
+  }
+}
+
+__global__ void __launch_bounds__(RB_BLOCK)
+k_rbs_scr(RbsTab T, Mat3 A, Rebo2Dev P, const double4 *__restrict__ pos4,
+          const long long *__restrict__ seed, const int2 *__restrict__ list, double *__restrict__ f,
+          double *__restrict__ wpa, double *__restrict__ wpb, double *__restrict__ partials, int nbtot,
+          int off, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * (RB_BLOCK / 32)];
+  const int i = blockIdx.x * RB_BLOCK + threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+  if (i < T.nat) rbs_scr_atom(T, A, P, pos4, seed, list, f, wpa, wpb, i, acc);
+  atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * nbtot + off + blockIdx.x] = acc[k];
+  }
+}
+
 // ---------------------------------------------------------------------------
 
 extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_rebo2 **out) {
@@ -539,36 +603,7 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
   atx_rebo2 *pot = new atx_rebo2();
   pot->ctx = ctx;
   Rebo2Dev &D = pot->dev;
-  D.cc_B1 = par->cc_B1; D.cc_B2 = par->cc_B2; D.cc_B3 = par->cc_B3;
-  D.cc_beta1 = par->cc_beta1; D.cc_beta2 = par->cc_beta2; D.cc_beta3 = par->cc_beta3;
-  D.cc_Q = par->cc_Q; D.cc_A = par->cc_A; D.cc_alpha = par->cc_alpha;
-  D.ch_B1 = par->ch_B1; D.ch_beta1 = par->ch_beta1; D.ch_Q = par->ch_Q; D.ch_A = par->ch_A;
-  D.ch_alpha = par->ch_alpha;
-  D.hh_B1 = par->hh_B1; D.hh_beta1 = par->hh_beta1; D.hh_Q = par->hh_Q; D.hh_A = par->hh_A;
-  D.hh_alpha = par->hh_alpha;
-  for (int i = 0; i < 6; i++) D.cc_g_theta[i] = par->cc_g_theta[i];
-  for (int i = 0; i < 18; i++) {
-    D.g1c[i] = par->cc_g1_coeff[i];
-    D.g2c[i] = par->cc_g2_coeff[i];
-    D.spgh[i] = par->spgh[i];
-  }
-  for (int i = 0; i < 25; i++) D.igh[i] = par->igh[i];
-  D.conalp = par->conalp;
-  for (int i = 0; i < 36; i++) D.conear[i] = par->conear[i];
-  for (int i = 0; i < 3; i++) {
-    D.conpe[i] = par->conpe[i];
-    D.conan[i] = par->conan[i];
-    D.conpf[i] = par->conpf[i];
-  }
-  for (int i = 0; i < 7; i++) D.cut_l[i] = D.cut_h[i] = D.cut_h2[i] = D.cut_fac[i] = 0.0;
-  for (int t : {RB_CC, RB_CH, RB_HH}) {
-    D.cut_l[t] = par->cut_in_l[t - 1];
-    D.cut_h[t] = par->cut_in_h[t - 1];
-    D.cut_h2[t] = par->cut_in_h2[t - 1];
-    D.cut_fac[t] = RB_PI / (D.cut_h[t] - D.cut_l[t]);
-  }
-  D.with_dihedral = par->with_dihedral;
-  D.n37 = (double)3.7f;
+  rb_fill_dev(D, par);
   const size_t n3 = 144 * 64, n2 = 25 * 16;
   ATX_PASS(pot->tables.reserve(4 * n3 + 2 * n2));
   double *t = pot->tables.ptr;
@@ -581,6 +616,27 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
   D.Pcc = t + 4 * n3; D.Pch = t + 4 * n3 + n2;
   for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
   ATX_PASS(pot->flag.reserve(4));
+  *out = pot;
+  return 0;
+}
+
+// Rebo2Scr (rebo2_scr.f90, rebo2_db.f90:92-112, :170-253): the C-C cutoffs of the three families
+// come from `scr`, all other pairs keep the inner cutoff in all three.
+extern "C" int atx_rebo2_create_screened(atx_ctx *ctx, const atx_rebo2_params *par,
+                                         const atx_rebo2_screening *scr, atx_rebo2 **out) {
+  if (!ctx || !par || !scr || !out) return ATX_ERROR_UNSPECIFIED;
+  if (par->with_dihedral) {
+    atx_set_error("Rebo2Scr: the (alternative) dihedral term is not available.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  if (!(scr->Cmax > scr->Cmin) || !(scr->Cmax > 1.0)) {
+    atx_set_error("Rebo2Scr: need Cmax > Cmin and Cmax > 1.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  atx_rebo2 *pot = nullptr;
+  ATX_PASS(atx_rebo2_create(ctx, par, &pot));
+  pot->screened = true;
+  rbs_fill_cut(pot->scr, pot->dev, scr);
   *out = pot;
   return 0;
 }
@@ -607,6 +663,11 @@ extern "C" int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors
   }
   // rebo2_module.f90:96-125
   if (nl) {
+    // the screened variant needs every atom that can screen a bond of the longest cutoff
+    // (rebo2_module.f90:96-125 with SCREENING: sqrt(C_dr_cut) * max cutoff)
+    if (hasC && pot->screened)
+      ATX_PASS(atx_neighbors_request_interaction_range(
+          nl, sqrt(pot->scr.max_cut_sq[RB_CC]) * (pot->scr.C_dr_cut > 1.0 ? sqrt(pot->scr.C_dr_cut) : 1.0)));
     if (hasC) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_CC]));
     if (hasC && hasH) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_CH]));
     if (hasH) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_HH]));
@@ -615,9 +676,79 @@ extern "C" int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors
   return 0;
 }
 
+static int rebo2_scr_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o,
+                             double *epb, double *fpb, double *wpb) {
+  atx_ctx *ctx = pot->ctx;
+  cudaStream_t st = ctx->stream;
+  const int nat = nl->nat;
+  int nbs = nl->nebmax < 1 ? 1 : nl->nebmax;
+  if (nbs > RBS_NBL) nbs = RBS_NBL;
+  if (pot->nss < 1) pot->nss = 32;
+  pot->nbs = nbs;
+  const size_t nt = (size_t)nat * nbs + 1, ns = (size_t)nat * pot->nss + 1;
+  ATX_PASS(pot->b_cnt.reserve(nat + 1));
+  ATX_PASS(pot->b_nb.reserve(nt));
+  ATX_PASS(pot->b_typ.reserve(nt));
+  ATX_PASS(pot->b_shift.reserve(nt));
+  ATX_PASS(pot->b_slot.reserve(nt));
+  ATX_PASS(pot->b_sseed.reserve(nt));
+  ATX_PASS(pot->b_scnt.reserve(nt));
+  ATX_PASS(pot->b_vec.reserve(nt));
+  ATX_PASS(pot->b_cut.reserve(nt));
+  ATX_PASS(pot->b_cbo.reserve(nt));
+  ATX_PASS(pot->b_cnc.reserve(nt));
+  ATX_PASS(pot->nn.reserve(nat + 1));
+  ATX_PASS(pot->s_ent.reserve(ns));
+  ATX_PASS(pot->s_arik.reserve(ns));
+  ATX_PASS(pot->s_arjk.reserve(ns));
+  ATX_PASS(pot->s_boik.reserve(ns));
+  ATX_PASS(pot->s_bojk.reserve(ns));
+  ATX_PASS(pot->s_ncik.reserve(ns));
+  ATX_PASS(pot->s_ncjk.reserve(ns));
+  ATX_PASS(pot->s_facbo.reserve(ns));
+  ATX_PASS(pot->s_facnc.reserve(ns));
+  RbsTab T;
+  T.nat = nat; T.nbs = nbs; T.nss = pot->nss;
+  T.b_cnt = pot->b_cnt.ptr; T.b_nb = pot->b_nb.ptr; T.b_typ = pot->b_typ.ptr;
+  T.b_shift = pot->b_shift.ptr; T.b_slot = pot->b_slot.ptr; T.b_sseed = pot->b_sseed.ptr;
+  T.b_scnt = pot->b_scnt.ptr; T.b_vec = pot->b_vec.ptr; T.b_car = pot->b_cut.ptr;
+  T.b_cbo = pot->b_cbo.ptr; T.b_cnc = pot->b_cnc.ptr; T.nn = pot->nn.ptr;
+  T.s_ent = pot->s_ent.ptr; T.s_arik = pot->s_arik.ptr; T.s_arjk = pot->s_arjk.ptr;
+  T.s_boik = pot->s_boik.ptr; T.s_bojk = pot->s_bojk.ptr; T.s_ncik = pot->s_ncik.ptr;
+  T.s_ncjk = pot->s_ncjk.ptr; T.s_facbo = pot->s_facbo.ptr; T.s_facnc = pot->s_facnc.ptr;
+  T.flag = pot->flag.ptr;
+  int nblocks = (nat + RB_BLOCK - 1) / RB_BLOCK;
+  if (nblocks < 1) nblocks = 1;
+  const int nbtot = 2 * nblocks;  // loop 2 and loop 3 each contribute one column per block
+  ATX_PASS(pot->sc.partials.reserve((size_t)nbtot * ATX_NSUM));
+  ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  ATX_CUDA(cudaMemsetAsync(o.f, 0, sizeof(double) * 3 * (size_t)nat, st));
+  if (o.epa) ATX_CUDA(cudaMemsetAsync(o.epa, 0, sizeof(double) * (size_t)nat, st));
+  if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
+  if (nat > 0) {
+    k_rbs_bonds<<<(nat + 127) / 128, 128, 0, st>>>(T, p->Abox, pot->dev, pot->scr, nl->pos4.ptr,
+                                                   nl->seed.ptr, nl->list.ptr, o.stop);
+    ATX_LAUNCHED();
+  }
+  {
+    ProfScope ps_(ctx, "rebo2_scr_force");
+    k_rbs_force<<<nblocks, RB_BLOCK, 0, st>>>(T, p->Abox, pot->dev, pot->scr, nl->pos4.ptr, nl->seed.ptr,
+                                              nl->list.ptr, nl->order.ptr, o.f, o.epa, o.wpa, epb, fpb,
+                                              wpb, pot->sc.partials.ptr, nbtot, 0, o.stop);
+    ATX_LAUNCHED();
+    k_rbs_scr<<<nblocks, RB_BLOCK, 0, st>>>(T, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr,
+                                            nl->list.ptr, o.f, o.wpa, wpb, pot->sc.partials.ptr, nbtot,
+                                            nblocks, o.stop);
+    ATX_LAUNCHED();
+  }
+  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbtot, o.sums, o.stop));
+  return 0;
+}
+
 static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o,
                          double *epb, double *fpb, double *wpb) {
   atx_ctx *ctx = pot->ctx;
+  if (pot->screened) return rebo2_scr_compute(pot, p, nl, o, epb, fpb, wpb);
   cudaStream_t st = ctx->stream;
   int nat = nl->nat;
   int nbs = nl->nebmax < 1 ? 1 : nl->nebmax;
@@ -662,6 +793,11 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
 }
 
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o) {
+  if (pot->screened) {
+    // the screening table can overflow and is resized by the library-mode caller only
+    atx_set_error("Rebo2Scr is not available in the device-resident MD driver yet.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
   return rebo2_compute(pot, p, nl, o, nullptr, nullptr, nullptr);
 }
 
@@ -714,10 +850,22 @@ extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx
     ATX_CUDA(cudaMemsetAsync(pot->wpb.ptr, 0, sizeof(double) * 9 * nslots, ctx->stream));
     wpb = pot->wpb.ptr;
   }
-  ATX_PASS(rebo2_compute(pot, p, nl, o, epb, fpb, wpb));
   int h = 0;
-  ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int attempt = 0;; attempt++) {
+    ATX_PASS(rebo2_compute(pot, p, nl, o, epb, fpb, wpb));
+    ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ATX_CUDA(cudaStreamSynchronize(ctx->stream));
+    // screened variant: the per-atom table of screening neighbours was too small; the outputs of
+    // the failed pass are overwritten (per-bond arrays are zeroed again) by the repeat
+    if (pot->screened && (h & 2) && !(h & 1) && attempt < 4) {
+      pot->nss *= 2;
+      if (epb) ATX_CUDA(cudaMemsetAsync(epb, 0, sizeof(double) * nslots, ctx->stream));
+      if (fpb) ATX_CUDA(cudaMemsetAsync(fpb, 0, sizeof(double) * 3 * nslots, ctx->stream));
+      if (wpb) ATX_CUDA(cudaMemsetAsync(wpb, 0, sizeof(double) * 9 * nslots, ctx->stream));
+      continue;
+    }
+    break;
+  }
   if (h) {
     atx_set_error("Internal neighbor list exhausted, *nebmax* too small.");
     return ATX_ERROR_UNSPECIFIED;

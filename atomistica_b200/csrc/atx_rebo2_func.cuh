@@ -4,6 +4,8 @@
 // emulation harness of the test-suite (tests/emu/) compiles this header with a host compiler.
 #pragma once
 
+#include "atomistica_b200.h"
+
 #define RB_PI 3.14159265358979323846264338327950288
 #define RB_C 1
 #define RB_H 3
@@ -25,6 +27,40 @@ struct Rebo2Dev {
   const double *Fcc, *Fch, *Fhh, *Tcc, *Pcc, *Pch;
   double n37;  // (double)3.7f, single-precision literal of rebo2_func.f90:314
 };
+
+// host: parameters of the C ABI -> device view (tables and el2typ are set by the caller)
+inline void rb_fill_dev(Rebo2Dev &D, const atx_rebo2_params *par) {
+  D.cc_B1 = par->cc_B1; D.cc_B2 = par->cc_B2; D.cc_B3 = par->cc_B3;
+  D.cc_beta1 = par->cc_beta1; D.cc_beta2 = par->cc_beta2; D.cc_beta3 = par->cc_beta3;
+  D.cc_Q = par->cc_Q; D.cc_A = par->cc_A; D.cc_alpha = par->cc_alpha;
+  D.ch_B1 = par->ch_B1; D.ch_beta1 = par->ch_beta1; D.ch_Q = par->ch_Q; D.ch_A = par->ch_A;
+  D.ch_alpha = par->ch_alpha;
+  D.hh_B1 = par->hh_B1; D.hh_beta1 = par->hh_beta1; D.hh_Q = par->hh_Q; D.hh_A = par->hh_A;
+  D.hh_alpha = par->hh_alpha;
+  for (int i = 0; i < 6; i++) D.cc_g_theta[i] = par->cc_g_theta[i];
+  for (int i = 0; i < 18; i++) {
+    D.g1c[i] = par->cc_g1_coeff[i];
+    D.g2c[i] = par->cc_g2_coeff[i];
+    D.spgh[i] = par->spgh[i];
+  }
+  for (int i = 0; i < 25; i++) D.igh[i] = par->igh[i];
+  D.conalp = par->conalp;
+  for (int i = 0; i < 36; i++) D.conear[i] = par->conear[i];
+  for (int i = 0; i < 3; i++) {
+    D.conpe[i] = par->conpe[i];
+    D.conan[i] = par->conan[i];
+    D.conpf[i] = par->conpf[i];
+  }
+  for (int i = 0; i < 7; i++) D.cut_l[i] = D.cut_h[i] = D.cut_h2[i] = D.cut_fac[i] = 0.0;
+  for (int t : {RB_CC, RB_CH, RB_HH}) {
+    D.cut_l[t] = par->cut_in_l[t - 1];
+    D.cut_h[t] = par->cut_in_h[t - 1];
+    D.cut_h2[t] = par->cut_in_h2[t - 1];
+    D.cut_fac[t] = RB_PI / (D.cut_h[t] - D.cut_l[t]);
+  }
+  D.with_dihedral = par->with_dihedral;
+  D.n37 = (double)3.7f;
+}
 
 __device__ __forceinline__ void rb_table2d(const double *__restrict__ coeff, int nx, int ny,
                                            double nhi, double nci, double &v, double &dvdh, double &dvdc) {

@@ -122,6 +122,13 @@ module atx_c_api
        type(c_ptr), value :: ctx, par
        type(c_ptr)        :: pot
      endfunction
+     integer(c_int) function atx_rebo2_create_screened(ctx, par, scr, pot) &
+          bind(C, name="atx_rebo2_create_screened")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx, par
+       type(c_ptr), value :: scr      ! c_loc of a type(atx_rebo2_screening_t)
+       type(c_ptr)        :: pot
+     endfunction
      integer(c_int) function atx_rebo2_bind_to(pot, p, nl, nel, el2Z) bind(C, name="atx_rebo2_bind_to")
        import :: c_int, c_ptr
        type(c_ptr), value    :: pot, p, nl
@@ -203,6 +210,10 @@ module atx_c_api
   type, bind(C) :: atx_bop_screening_t
      real(c_double) :: or1(6), or2(6), bor1(6), bor2(6), Cmin(6), Cmax(6)
   endtype atx_bop_screening_t
+  !> rebo2_scr: cc_ar_r1 ... Cmax of rebo2_type.f90:204-213
+  type, bind(C) :: atx_rebo2_screening_t
+     real(c_double) :: cc_ar_r1, cc_ar_r2, cc_bo_r1, cc_bo_r2, cc_nc_r1, cc_nc_r2, Cmin, Cmax
+  endtype atx_rebo2_screening_t
   type, bind(C) :: atx_juslin_params_t
      integer(c_int) :: nel, Z(3)
      real(c_double) :: D0(9), r0(9), S(9), beta(9), gamma(9), c(9), d(9), h(9), n(9), r1(9), r2(9)

@@ -167,3 +167,29 @@ def build_params(kwargs):
     for k, v in keep.items():
         setattr(p, k, L.dptr(v))
     return d, tabs, p, keep
+
+
+# rebo2_type.f90:65-69, :204-213 (SCREENING branch): cutoffs of the C-C bonds of Rebo2Scr
+SCR_DEFAULTS = dict(cc_in_r1=1.95, cc_in_r2=2.25, cc_ar_r1=2.179347, cc_ar_r2=2.819732,
+                    cc_bo_r1=1.866344, cc_bo_r2=2.758372, cc_nc_r1=1.217335, cc_nc_r2=4.000000,
+                    Cmin=1.00, Cmax=2.00)
+SCR_KEYS = ('cc_ar_r1', 'cc_ar_r2', 'cc_bo_r1', 'cc_bo_r2', 'cc_nc_r1', 'cc_nc_r2', 'Cmin', 'Cmax')
+
+
+def build_params_scr(kwargs):
+    """parameter blocks of Rebo2Scr: (d, tabs, atx_rebo2_params, keep, atx_rebo2_screening, sd)"""
+    sd = dict(SCR_DEFAULTS)
+    base = {}
+    for k, v in kwargs.items():
+        if k in SCR_KEYS:
+            sd[k] = v
+        else:
+            base[k] = v
+    base.setdefault('cc_in_r1', sd['cc_in_r1'])
+    base.setdefault('cc_in_r2', sd['cc_in_r2'])
+    d, tabs, p, keep = build_params(base)
+    sd['cc_in_r1'], sd['cc_in_r2'] = d['cc_in_r1'], d['cc_in_r2']
+    q = L.AtxRebo2Screening()
+    for k in SCR_KEYS:
+        setattr(q, k, float(sd[k]))
+    return d, tabs, p, keep, q, sd

@@ -229,6 +229,16 @@ typedef struct {
 } atx_rebo2_params;
 
 int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_rebo2 **pot);
+/* Rebo2Scr (src/potentials/bop/rebo2/rebo2_scr.f90:60-64, parameters rebo2_type.f90 /
+ * rebo2_db.f90:92-112): screened C-C bonds with separate attractive-repulsive, bond-order and
+ * neighbour-count cutoffs; the inner C-C cutoff is par->cut_in_*[0].  The dihedral term of this
+ * variant is not available (par->with_dihedral must be 0).  The returned object is used with the
+ * atx_rebo2_* entry points below. */
+typedef struct {
+  double cc_ar_r1, cc_ar_r2, cc_bo_r1, cc_bo_r2, cc_nc_r1, cc_nc_r2, Cmin, Cmax;
+} atx_rebo2_screening;
+int atx_rebo2_create_screened(atx_ctx *ctx, const atx_rebo2_params *par,
+                              const atx_rebo2_screening *scr, atx_rebo2 **pot);
 int atx_rebo2_destroy(atx_rebo2 *pot);
 /* BIND_TO_FUNC (rebo2_module.f90:70-135) */
 int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, int nel,

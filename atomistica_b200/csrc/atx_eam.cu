@@ -58,6 +58,7 @@ struct atx_eam {
   bool force_generic = false;
   bool funcfl = false;
   int fast_lanes = 4, fast_unroll = 2;
+  int fast_map = 0;  // 1: consecutive lane -> entry mapping (experimental, ATX_EAM_MAP)
   ~atx_eam() {
     for (auto *t : tables) delete t;
   }
@@ -289,7 +290,12 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
 // the interval coordinate that a C2 spline turns into a relative change far below 1e-10.
 // ---------------------------------------------------------------------------
 
-template <int LANES, int U>
+// CONSEC = 0: lane l takes the U neighbouring entries (t*LANES + l)*U + u.  CONSEC = 1: entry
+// t*LANES*U + u*LANES + l, so that the lanes of ONE load instruction read neighbouring list entries
+// (which point at runs of neighbouring atoms inside a binning cell): fewer distinct 128-byte lines
+// per gather in the model of benchmarks/model_gather_wavefronts.py.  Selected by ATX_EAM_MAP=1;
+// not measured yet.
+template <int LANES, int U, int CONSEC = 0>
 __global__ void __launch_bounds__(128)
 k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
                    const long long *__restrict__ seed, const int2 *__restrict__ list,
@@ -306,11 +312,12 @@ k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 
   const int nr = T->r_n;
   double rho = 0.0;
   const long long b = dbi > 0 ? seed[s] : 0, e = dbi > 0 ? seed[s + 1] : 0;
-  for (long long a0 = b + lane * U; a0 < e; a0 += LANES * U) {
+  constexpr int ES = CONSEC ? LANES : 1;   // distance between the U entries of one lane
+  for (long long a0 = b + (CONSEC ? lane : lane * U); a0 < e; a0 += LANES * U) {
     int2 en[U];
     double4 pj[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) en[u] = (a0 + u < e) ? list[a0 + u] : make_int2(s, ATX_SHIFT_ZERO);
+    for (int u = 0; u < U; u++) en[u] = (a0 + u * ES < e) ? list[a0 + u * ES] : make_int2(s, ATX_SHIFT_ZERO);
 #pragma unroll
     for (int u = 0; u < U; u++) pj[u] = atx_ld4(&pos4[en[u].x]);
     double B[U], w[U];
@@ -327,7 +334,7 @@ k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 
       }
       const double r2 = dx * dx + dy * dy + dz * dz;
       const int dbj = T->el2db[ATX_ENTRY_EL(en[u].y)];
-      const bool in = (a0 + u < e) && dbj > 0 && r2 < cutoff_sq;
+      const bool in = (a0 + u * ES < e) && dbj > 0 && r2 < cutoff_sq;
       const double r = sqrt(in ? r2 : 1.0);
       const double xf = (r - x0) * inv_dx + 1.0;
       int i = (int)floor(xf);
@@ -357,7 +364,7 @@ k_eam_density_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 
 
 // Force pass.  Per pair it gathers ONE 32-byte record {x,y,z,F'_j} and ONE 64-byte table record
 // {phi: y c1 c2 c3 | rho_j: c1 c2 c3 | -}; derivative coefficients are formed as k*c_k/dx.
-template <int LANES, int U, bool VIRIAL>
+template <int LANES, int U, bool VIRIAL, int CONSEC = 0>
 __global__ void __launch_bounds__(128)
 k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pd4,
                  const double4 *__restrict__ pos4, const long long *__restrict__ seed,
@@ -380,11 +387,12 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
   const bool zsq = T->zsq != 0;
   const long long b = dbi > 0 ? seed[s] : 0, e = dbi > 0 ? seed[s + 1] : 0;
   const int di = dbi > 0 ? dbi - 1 : 0;
-  for (long long a0 = b + lane * U; a0 < e; a0 += LANES * U) {
+  constexpr int ES = CONSEC ? LANES : 1;
+  for (long long a0 = b + (CONSEC ? lane : lane * U); a0 < e; a0 += LANES * U) {
     int2 en[U];
     double4 pj[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) en[u] = (a0 + u < e) ? list[a0 + u] : make_int2(s, ATX_SHIFT_ZERO);
+    for (int u = 0; u < U; u++) en[u] = (a0 + u * ES < e) ? list[a0 + u * ES] : make_int2(s, ATX_SHIFT_ZERO);
 #pragma unroll
     for (int u = 0; u < U; u++) pj[u] = atx_ld4(&pd4[en[u].x]);
     double B[U], w[U], dx[U], dy[U], dz[U], rinv[U];
@@ -401,7 +409,7 @@ k_eam_force_fast(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *_
       }
       const double r2 = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
       const int dbj = T->el2db[ATX_ENTRY_EL(en[u].y)];
-      const bool in = (a0 + u < e) && dbj > 0 && r2 < cutoff_sq;
+      const bool in = (a0 + u * ES < e) && dbj > 0 && r2 < cutoff_sq;
       const double r = sqrt(in ? r2 : 1.0);
       rinv[u] = 1.0 / r;
       const double xf = (r - x0) * inv_dx + 1.0;
@@ -549,6 +557,7 @@ extern "C" int atx_eam_create(atx_ctx *ctx, int ndb, const atx_spline *fF, const
   if (const char *v = getenv("ATX_EAM_GENERIC")) pot->force_generic = atoi(v) != 0;
   if (const char *v = getenv("ATX_EAM_LANES")) pot->fast_lanes = atoi(v);
   if (const char *v = getenv("ATX_EAM_UNROLL")) pot->fast_unroll = atoi(v);
+  if (const char *v = getenv("ATX_EAM_MAP")) pot->fast_map = atoi(v) != 0;
   ATX_PASS(pot->dev.reserve(1));
   ATX_PASS(pot->flag.reserve(4));
   *out = pot;
@@ -617,28 +626,35 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
     const int nb = nat > 0 ? (nat + gp - 1) / gp : 1;
     ATX_PASS(pot->sc.partials.reserve((size_t)nb * ATX_NSUM));
     const bool vir = o.want_virial;
-#define EAM_FAST(LL, UU)                                                                          \
+#define EAM_FAST_M(LL, UU, MM)                                                                         \
   do {                                                                                            \
     {                                                                                             \
       ProfScope ps_(ctx, "eam_density");                                                          \
-      k_eam_density_fast<LL, UU><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,    \
+      k_eam_density_fast<LL, UU, MM><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,    \
                                                      nl->seed.ptr, nl->list.ptr, pot->pd4.ptr,    \
                                                      pot->Fe.ptr, o.role, o.stop);                \
     }                                                                                             \
     ATX_LAUNCHED();                                                                               \
     ProfScope ps2_(ctx, "eam_force");                                                             \
     if (vir)                                                                                      \
-      k_eam_force_fast<LL, UU, true><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
+      k_eam_force_fast<LL, UU, true, MM><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
           nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr, \
           o.role, o.stop);                                                                        \
     else                                                                                          \
-      k_eam_force_fast<LL, UU, false><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
+      k_eam_force_fast<LL, UU, false, MM><<<nb, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, pot->pd4.ptr, \
           nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, pot->Fe.ptr, o.f, o.epa, pot->sc.partials.ptr, \
           o.role, o.stop);                                                                        \
     ATX_LAUNCHED();                                                                               \
   } while (0)
+#define EAM_FAST(LL, UU) EAM_FAST_M(LL, UU, 0)
     const int U = pot->fast_unroll;
-    if (L == 4 && U == 4) EAM_FAST(4, 4);
+    if (pot->fast_map && L == 4 && U == 2) EAM_FAST_M(4, 2, 1);
+    else if (pot->fast_map && L == 4 && U == 4) EAM_FAST_M(4, 4, 1);
+    else if (pot->fast_map && L == 8 && U == 2) EAM_FAST_M(8, 2, 1);
+    else if (pot->fast_map && L == 8 && U == 4) EAM_FAST_M(8, 4, 1);
+    else if (pot->fast_map && L == 16 && U == 2) EAM_FAST_M(16, 2, 1);
+    else if (pot->fast_map) EAM_FAST_M(16, 1, 1);
+    else if (L == 4 && U == 4) EAM_FAST(4, 4);
     else if (L == 4 && U == 2) EAM_FAST(4, 2);
     else if (L == 8 && U == 4) EAM_FAST(8, 4);
     else if (L == 8 && U == 2) EAM_FAST(8, 2);
@@ -648,6 +664,7 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
     else if (L == 1 && U == 4) EAM_FAST(1, 4);
     else EAM_FAST(8, 2);
 #undef EAM_FAST
+#undef EAM_FAST_M
     ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nb, o.sums, o.stop));
     return 0;
   }

@@ -1,4 +1,6 @@
 """TabulatedAlloyEAM on the GPU vs the oracle (tolerance 1e-10 relative, BASELINE.json)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -217,3 +219,29 @@ def test_funcfl_tabulated_eam(au_funcfl):
     assert abs(e / len(a)) > 3.0
     with pytest.raises(RuntimeError):
         pot.energy_and_forces(p, nl, wpot_per_at=True)
+
+
+@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
+                    reason='experimental lane mapping (ATX_EAM_MAP=1) not yet run on hardware')
+@pytest.mark.parametrize('lanes,unroll', [(4, 2), (8, 2), (16, 1)])
+def test_consecutive_lane_mapping(cu_setfl, monkeypatch, lanes, unroll):
+    # the variant the wavefront model of benchmarks/model_gather_wavefronts.py suggests: same sums in
+    # another order.  per_at=False keeps the call on the fast kernels (the per-atom virial uses the
+    # generic ones)
+    monkeypatch.setenv('ATX_EAM_MAP', '1')
+    monkeypatch.setenv('ATX_EAM_LANES', str(lanes))
+    monkeypatch.setenv('ATX_EAM_UNROLL', str(unroll))
+    a = S.fcc('Cu', 3.615, (6, 5, 4))
+    a.rattle(0.1, seed=3)
+    p = native.from_atoms(a)
+    nl = native.Neighbors(200)
+    pot = native.TabulatedAlloyEAM(setfl=cu_setfl)
+    pot.bind_to(p, nl)
+    e, f, w, epa, _, _, _, _ = pot.energy_and_forces(p, nl, epot_per_at=True)
+    eam = oracle.EAM(cu_setfl)
+    onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, eam.cutoff, 200)
+    o = eam.energy_and_forces(a.positions, a.cell, onl, eam.eldb(a.symbols), per_at=True)
+    assert abs(e - o['epot']) <= RTOL * abs(o['epot'])
+    assert _close(f, o['f'], max(np.abs(o['f']).max(), 1.0))
+    assert _close(w, o['wpot'], max(np.abs(o['wpot']).max(), 1.0, abs(o['epot'])))
+    assert _close(epa, o['epot_per_at'])

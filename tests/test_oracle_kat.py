@@ -229,7 +229,10 @@ def _builtin_molecules():
     c6h6 = (['C'] * 6 + ['H'] * 6, [[1.395 * np.cos(x), 1.395 * np.sin(x), 0] for x in ang] +
             [[2.482 * np.cos(x), 2.482 * np.sin(x), 0] for x in ang])
     ch3 = (['C', 'H', 'H', 'H'], [[0, 0, 0], [1.08, 0, 0], [-0.54, 0.935, 0], [-0.54, -0.935, 0]])
-    return dict(CH4=ch4, C2H2=c2h2, C2H4=c2h4, C2H6=c2h6, C6H6=c6h6, CH3=ch3)
+    out = dict(CH4=ch4, C2H2=c2h2, C2H4=c2h4, C2H6=c2h6, C6H6=c6h6, CH3=ch3)
+    from molecule_builder import extra_molecules
+    out.update(extra_molecules())
+    return out
 
 
 def _relaxed_energy(symbols, positions, calc):
@@ -251,7 +254,10 @@ def _relaxed_energy(symbols, positions, calc):
 MOLS = ['CH4', 'C2H2', 'C2H4', 'C2H6', 'C6H6', 'CH3', 'C2H', 'H3C2H2', 'CH2=C=CH2', 'propyne', 'CH3CH=C=CH2',
         '1-butyne', '1-butene', 'cis-butene', 'i-C4H9', 't-C4H9', '1,3-pentadiene', '1,4-pentadiene',
         'cyclopentene', 'cyclopentane', '2-pentene', '1-butene,2-methyl', 'n-pentane', 'isopentane',
-        'neopentane', 'cyclohexane', 'naphthalene']
+        'neopentane', 'cyclohexane', 'naphthalene',
+        # the remaining rows of the reference's table (G2 geometries rebuilt by tests/molecule_builder.py)
+        'CH2_s1A1d', 'C3H8', 'trans-butane', 'isobutane', 'C3H6_Cs', 'C3H6_D3h', 'C3H4_C2v', 'butadiene',
+        '2-butyne']
 
 
 @pytest.mark.parametrize('name', MOLS)

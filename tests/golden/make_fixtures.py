@@ -178,6 +178,10 @@ def main():
             'Juslin_B1_WC': dict(Ec=(16.68 - 0.98) / 2, a0=4.380, B=433.0),
             'Juslin_B2_WC': dict(Ec=(16.68 - 2.32) / 2, a0=2.704, B=411.0),
             'Juslin_B3_WC': dict(Ec=(16.68 - 2.12) / 2, a0=4.679, B=511.0),
+            # tests/test_bulk_properties.py:72-76 (Brenner II) and :163-177 (Matsunaga B-C-N, also TersoffScr)
+            'Brenner_II_dia_C': dict(Ec=7.376 - 0.0524, a0=3.558, C11=621.0, C12=415.0, C44=383.0, B=484.0),
+            'Tersoff_BCN_dia_C': dict(Ec=7.396 - 0.0250, a0=3.566, C11=1067.0, C12=104.0, C44=636.0, C440=671.0),
+            'Tersoff_BCN_B3_BN': dict(Ec=6.63, a0=3.658, B=385.0),
         },
         'bulk_tol_rel': 0.05,
         # tests/test_surface_properties.py:228-262: relaxed (100) surface energies of the Erhart-Albe

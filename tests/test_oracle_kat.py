@@ -189,6 +189,12 @@ BULK = [
     ('Brenner_Erhart_dia_Si', lambda: bop_calc('Brenner', None), lambda a0: S.diamond('Si', a0, (2, 2, 2))),
     ('Brenner_Erhart_B3_SiC', lambda: bop_calc('Brenner', None), lambda a0: S.b3(['Si', 'C'], a0, (2, 2, 2))),
     ('Rebo2_dia_C', lambda: rebo2_calc(), lambda a0: S.diamond('C', a0, (2, 2, 2))),
+    ('Brenner_II_dia_C', lambda: bop_calc('Brenner', P.Brenner_PRB_42_9458_C_II),
+     lambda a0: S.diamond('C', a0, (2, 2, 2))),
+    ('Tersoff_BCN_dia_C', lambda: bop_calc('Tersoff', P.Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N),
+     lambda a0: S.diamond('C', a0, (2, 2, 2))),
+    ('Tersoff_BCN_B3_BN', lambda: bop_calc('Tersoff', P.Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N),
+     lambda a0: S.b3(['B', 'N'], a0, (2, 2, 2))),
 ]
 
 
@@ -204,6 +210,8 @@ def test_bulk_properties(name, mk, builder):
         assert rel(C11, ref['C11']) < tol
     if 'C12' in ref:
         assert rel(C12, ref['C12']) < 2 * tol or abs(C12 - ref['C12']) < 8.0
+    if 'B' in ref:
+        assert rel((C11 + 2 * C12) / 3, ref['B']) < tol
 
 
 def test_eam_au_bulk(au_setfl):
@@ -348,6 +356,12 @@ SCR_BULK = [
     ('Brenner_Erhart_dia_C', lambda: bop_scr_calc('Brenner', None), lambda a0: S.diamond('C', a0, (2, 2, 2))),
     ('Brenner_Erhart_dia_Si', lambda: bop_scr_calc('Brenner', None), lambda a0: S.diamond('Si', a0, (2, 2, 2))),
     ('Brenner_Erhart_B3_SiC', lambda: bop_scr_calc('Brenner', None), lambda a0: S.b3(['Si', 'C'], a0, (2, 2, 2))),
+    ('Tersoff_BCN_dia_C',
+     lambda: bop_scr_calc('Tersoff', P.Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N__Scr),
+     lambda a0: S.diamond('C', a0, (2, 2, 2))),
+    ('Tersoff_BCN_B3_BN',
+     lambda: bop_scr_calc('Tersoff', P.Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N__Scr),
+     lambda a0: S.b3(['B', 'N'], a0, (2, 2, 2))),
 ]
 
 
@@ -364,6 +378,8 @@ def test_bulk_properties_screened(name, mk, builder):
         assert rel(C11, ref['C11']) < tol
     if 'C12' in ref:
         assert rel(C12, ref['C12']) < 2 * tol or abs(C12 - ref['C12']) < 8.0
+    if 'B' in ref:
+        assert rel((C11 + 2 * C12) / 3, ref['B']) < tol
 
 
 def test_fd_screened(aC_small):

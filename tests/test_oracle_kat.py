@@ -296,6 +296,24 @@ def test_fd_brenner():
     check_fd(bop_calc('Brenner', P.Albe_PRB_65_195124_PtC), a)
 
 
+def test_fd_brenner_fec_with_masks(aC_small):
+    # tests/test_forces_and_virial.py:104-122: Henriksson Fe-C on seven structures, each also with masks
+    calc = bop_calc('Brenner', P.Henriksson_PRB_79_114107_FeC)
+    rng = np.random.RandomState(11)
+    structs = [S.diamond('C', 3.566, (2, 2, 2)), aC_small, S.bcc('Fe', 2.87, (2, 2, 2)), S.fcc('Fe', 3.6, (2, 2, 2)),
+               S.sc('Fe', 2.4, (3, 3, 3)), S.b1(['Fe', 'C'], 3.9, (2, 2, 2)), S.b3(['Fe', 'C'], 4.0, (2, 2, 2))]
+    for n, a in enumerate(structs):
+        a = a.copy()
+        if a is not aC_small:
+            a.rattle(0.08, seed=20 + n)
+        check_fd(calc, a, nat_check=3)
+        mask = (rng.rand(len(a)) > 0.5).astype(np.int32)
+        o0, o1, o2 = calc(a), calc(a, mask=mask), calc(a, mask=1 - mask)
+        assert abs(o1['epot'] + o2['epot'] - o0['epot']) < 1e-6
+        assert np.abs(o1['f'] + o2['f'] - o0['f']).max() < 1e-6
+        assert np.abs(o1['wpot'] + o2['wpot'] - o0['wpot']).max() < 1e-6
+
+
 def test_fd_rebo2(aC_small):
     check_fd(rebo2_calc(), aC_small)
     rng = np.random.RandomState(1)

@@ -332,6 +332,51 @@ def complete_juslin(db):
                     out[key][a] = out[key][b]
     return out
 
+# JuslinScr.  The Fortran default database (juslin_params.f90:95-103, SCREENING branch) has the outer
+# and bond-order cutoffs equal to the inner one and Cmin = 1, Cmax = 3; the Python module's
+# Juslin_JAP_98_123520_WCH__Scr (parameters.py:297-307) repeats the r1 / r2 rows in Cmin / Cmax.
+_J_R1 = [3.20, 2.60, 2.68, 0.0, 1.70, 1.30, 0.0, 1.30, 1.10]
+_J_R2 = [3.80, 3.00, 2.96, 0.0, 2.00, 1.80, 0.0, 1.80, 1.70]
+Juslin_WCH__Scr_fortran_default = copy.deepcopy(Juslin_JAP_98_123520_WCH)
+Juslin_WCH__Scr_fortran_default.update(
+    r1=list(_J_R1), r2=list(_J_R2), or1=list(_J_R1), or2=list(_J_R2), bor1=list(_J_R1), bor2=list(_J_R2),
+    Cmin=[1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0], Cmax=[3.0, 3.0, 3.0, 0.0, 3.0, 3.0, 0.0, 3.0, 3.0])
+Juslin_JAP_98_123520_WCH__Scr = copy.deepcopy(Juslin_JAP_98_123520_WCH)
+Juslin_JAP_98_123520_WCH__Scr.update(
+    r1=list(_J_R1), r2=list(_J_R2), or1=list(_J_R1), or2=list(_J_R2), bor1=list(_J_R1), bor2=list(_J_R2),
+    Cmin=list(_J_R1), Cmax=list(_J_R2))
+
+
+def complete_juslin_scr(db):
+    """JuslinScr: default database + mirroring, which in the SCREENING build also covers
+    or1 ... Cmax (juslin_module.f90:285-298)"""
+    base = copy.deepcopy(Juslin_WCH__Scr_fortran_default)
+    out = copy.deepcopy(db) if db is not None else base
+    for k, v in base.items():
+        if k not in out:
+            out[k] = list(v)
+    nel = len(out['el'])
+    for i in range(nel):
+        for j in range(nel):
+            a, b = j + i * nel, i + j * nel
+            if out['r0'][a] < 0.0:
+                for key in JUSLIN_PAIR_KEYS + SCR_KEYS:
+                    out[key][a] = out[key][b]
+    return out
+
+
+def juslin_scr_cutoff(db):
+    """list cutoff requested by JuslinScr: sqrt(C_dr_cut) of the pair times the largest cutoff of the
+    database (juslin_module.f90:379-395), maximum over the pairs in use"""
+    m = max(max(db['r2'][k], db['or2'][k], db['bor2'][k]) for k in range(len(db['r2'])))
+    x = 0.0
+    for k in range(len(db['r2'])):
+        cmax = db['Cmax'][k]
+        if cmax > 1.0:
+            x = max(x, (cmax * cmax / (4 * (cmax - 1))) ** 0.5)
+    return x * m
+
+
 # Fortran built-in defaults used when a key is not supplied
 # (type initialisers in tersoff_params.f90:62-77, brenner/kumagai: the default db itself)
 TERSOFF_FIELD_DEFAULTS = dict(A=1.0, B=1.0, xi=1.0, mu=1.0, omega=1.0, mubo=0.0, m=1, beta=1.0, n=1.0,

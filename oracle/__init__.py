@@ -422,13 +422,13 @@ def pair_energy_and_forces(kind, par, r, cell, nl, symbols, el1='*', el2='*', sh
 
 
 class BopScr(C.Structure):
-    _fields_ = [(k, C.c_double * 6) for k in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax')]
+    _fields_ = [(k, C.c_double * 9) for k in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax')]
 
 
 def bop_scr_params(db):
     """outer / bond-order cutoffs and screening bounds of a *__Scr parameter set"""
     s = BopScr()
-    npairs = len(db['el']) * (len(db['el']) + 1) // 2
+    npairs = len(db['or1'])      # el (el + 1) / 2, or el x el for the Juslin sets
     for key in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax'):
         for k in range(npairs):
             getattr(s, key)[k] = float(db[key][k])

@@ -108,11 +108,11 @@ int orc_bop_energy_and_forces(const orc_bop_params_t *par, int nat, int natloc, 
                               double *epot_per_at, double *epot_per_bond, double *f_per_bond,
                               double *wpot_per_at, double *wpot_per_bond);
 
-/* Screened variants (TersoffScr, KumagaiScr, BrennerScr): outer / bond-order cutoffs and the
+/* Screened variants (TersoffScr, KumagaiScr, BrennerScr; JuslinScr with trigonometric cutoffs): outer / bond-order cutoffs and the
  * Baskes screening bounds of the *_Scr parameter sets (parameters.py), pair-indexed.  In these
  * variants r1/r2 of orc_bop_params_t are the INNER cutoff and every cutoff is exp_cutoff_t. */
 typedef struct {
-  double or1[6], or2[6], bor1[6], bor2[6], Cmin[6], Cmax[6];
+  double or1[9], or2[9], bor1[9], bor2[9], Cmin[9], Cmax[9]; /* 9: Juslin's el x el pair index */
 } orc_bop_scr_t;
 
 int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr_t *scr, int nat,

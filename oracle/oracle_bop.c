@@ -473,6 +473,19 @@ static void exp_cutoff_init(exp_cutoff_t *t, double r1, double r2) {
   t->off = val1 + t->c + t->d;
 }
 
+/* JuslinScr keeps the trigonometric form for all three cutoffs (juslin_func.f90:27-122: fCin, fCar,
+ * fCbo; constants juslin_module.f90:345-372) */
+static void juslin_trig_f(const exp_cutoff_t *t, double r, double *val, double *dval) {
+  if (r > t->r2) { *val = 0.0; *dval = 0.0; }
+  else if (r < t->r1) { *val = 1.0; *dval = 0.0; }
+  else {
+    double fca = PI / (t->r2 - t->r1), fc = -0.5 * fca;
+    double arg = fca * (r - t->r1);
+    *val = 0.5 * (1.0 + cos(arg));
+    *dval = fc * sin(arg);
+  }
+}
+
 static void exp_cutoff_f(const exp_cutoff_t *t, double r, double *val, double *dval) {
   if (r <= t->r1) { *val = 1.0; *dval = 0.0; }
   else if (r >= t->r2) { *val = 0.0; *dval = 0.0; }
@@ -503,18 +516,20 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
   brenner_derived_t bd;
   memset(&bd, 0, sizeof(bd));
   if (par->kind == ORC_BRENNER || par->kind == ORC_JUSLIN) brenner_derive(par, &bd);
-  if (par->kind == ORC_JUSLIN) return -2; /* JuslinScr uses trigonometric cutoffs: not restated */
   const double screening_threshold = log(1e-6), dot_threshold = 1e-10;
 
-  int npairs = par->nel * (par->nel + 1) / 2;
-  exp_cutoff_t cut_in[6], cut_out[6], cut_bo[6];
-  double cut_in_l[6], cut_in_h[6], cut_in_h2[6], cut_out_l[6], cut_out_h[6], cut_bo_h[6],
-      max_cut_sq[6], Cmin[6], Cmax[6], dC[6], C_dr_cut[6];
+  const int juslin = par->kind == ORC_JUSLIN;
+  int npairs = juslin ? par->nel * par->nel : par->nel * (par->nel + 1) / 2;
+  void (*cutoff_f)(const exp_cutoff_t *, double, double *, double *) = juslin ? juslin_trig_f : exp_cutoff_f;
+  exp_cutoff_t cut_in[9], cut_out[9], cut_bo[9];
+  double cut_in_l[9], cut_in_h[9], cut_in_h2[9], cut_out_l[9], cut_out_h[9], cut_bo_h[9],
+      max_cut_sq[9], Cmin[9], Cmax[9], dC[9], C_dr_cut[9];
   for (int i = 0; i < npairs; i++) {
     Cmin[i] = scr->Cmin[i];
     Cmax[i] = scr->Cmax[i];
     dC[i] = Cmax[i] - Cmin[i];
-    C_dr_cut[i] = Cmax[i] > 2.0 ? Cmax[i] * Cmax[i] / (4 * (Cmax[i] - 1)) : 1.0;
+    /* brenner_module.f90:198-205 & co: 1 unless Cmax > 2; juslin_module.f90:307: unconditional */
+    C_dr_cut[i] = (juslin || Cmax[i] > 2.0) ? Cmax[i] * Cmax[i] / (4 * (Cmax[i] - 1)) : 1.0;
     exp_cutoff_init(&cut_in[i], par->r1[i], par->r2[i]);
     cut_in_l[i] = par->r1[i];
     cut_in_h[i] = par->r2[i];
@@ -684,16 +699,16 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
           bndtyp[nebtot] = el2ij;
           double fcinij, dfcinijr, fcarij, dfcarijr, fcboij, dfcboijr;
           if (screened) {
-            exp_cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
+            cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
             cutfcnar[nebtot] = fcinij; cutdrvar[nebtot] = dfcinijr;
             cutfcnbo[nebtot] = fcinij; cutdrvbo[nebtot] = dfcinijr;
             snebtot = ineb;
             sneb_last[nebtot] = ineb - 1;
           } else if (need_derivative) {
             sij = exp(sij);
-            exp_cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
-            exp_cutoff_f(&cut_out[el2ij], rlij, &fcarij, &dfcarijr);
-            exp_cutoff_f(&cut_bo[el2ij], rlij, &fcboij, &dfcboijr);
+            cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
+            cutoff_f(&cut_out[el2ij], rlij, &fcarij, &dfcarijr);
+            cutoff_f(&cut_bo[el2ij], rlij, &fcboij, &dfcboijr);
             cutfcnar[nebtot] = (1.0 - fcinij) * sij * fcarij + fcinij;
             cutdrvar[nebtot] = (1.0 - fcinij) * sij * (dfcarijr + fcarij * dsijdrij / rlij) -
                                dfcinijr * sij * fcarij + dfcinijr;
@@ -707,10 +722,10 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
               cutdrarjk[q] = cutdrarjk[q] * sij * fcarij * (1.0 - fcinij);
             }
           } else {
-            exp_cutoff_f(&cut_out[el2ij], rlij, &fcarij, &dfcarijr);
-            exp_cutoff_f(&cut_bo[el2ij], rlij, &fcboij, &dfcboijr);
+            cutoff_f(&cut_out[el2ij], rlij, &fcarij, &dfcarijr);
+            cutoff_f(&cut_bo[el2ij], rlij, &fcboij, &dfcboijr);
             if (rlij < cut_in_h[el2ij]) {
-              exp_cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
+              cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
               cutfcnar[nebtot] = (1.0 - fcinij) * fcarij + fcinij;
               cutdrvar[nebtot] = (1.0 - fcinij) * dfcarijr - dfcinijr * fcarij + dfcinijr;
               cutfcnbo[nebtot] = (1.0 - fcinij) * fcboij + fcinij;
@@ -730,7 +745,7 @@ int orc_bop_scr_energy_and_forces(const orc_bop_params_t *par, const orc_bop_scr
         for (int k = 0; k < 3; k++) bndnm[3 * nebtot + k] = rij[k] / rlij;
         bndtyp[nebtot] = el2ij;
         double fcinij, dfcinijr;
-        exp_cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
+        cutoff_f(&cut_in[el2ij], rlij, &fcinij, &dfcinijr);
         cutfcnar[nebtot] = fcinij; cutdrvar[nebtot] = dfcinijr;
         cutfcnbo[nebtot] = fcinij; cutdrvbo[nebtot] = dfcinijr;
         neb[nebtot] = j; nbb[nebtot] = jn - 1;

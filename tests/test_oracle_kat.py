@@ -57,6 +57,19 @@ def juslin_calc(db=None):
     return calc
 
 
+def juslin_scr_calc(db=None):
+    db = P.complete_juslin_scr(db)
+    par = oracle.bop_params(oracle.JUSLIN, db)
+    scr = oracle.bop_scr_params(db)
+    cutoff = P.juslin_scr_cutoff(db)
+
+    def calc(a, **kw):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 1000)
+        el = np.array([db['el'].index(s) + 1 if s in db['el'] else -1 for s in a.symbols], dtype=np.int32)
+        return oracle.bop_energy_and_forces(par, a.positions, a.cell, nl, el, scr=scr, **kw)
+    return calc
+
+
 def rebo2_calc(**kw0):
     rb = oracle.Rebo2(**kw0)
 
@@ -634,6 +647,47 @@ def test_surface_energy_100(pot, mat, sym, a0):
     # the reference allows 5 %; the restated kernels reproduce its 3-digit table values (also where the
     # screened and unscreened rows differ: C 5.59 vs 5.88, Si 1.95 vs 1.90, SiC 3.93 vs 3.87)
     assert abs(es - ref) < 0.006, (es, ref)
+
+
+# ---- JuslinScr (oracle only so far; no known answers in the reference's tests) ---------------------
+
+def _juslin_scr_wide():
+    """the default database with outer / bond-order cutoffs beyond the inner one, so that bonds are
+    really screened"""
+    db = P.complete_juslin_scr(None)
+    for k in range(9):
+        if db['r2'][k] > 0:
+            db['or1'][k], db['or2'][k] = db['r2'][k] * 1.05, db['r2'][k] * 1.45
+            db['bor1'][k], db['bor2'][k] = db['r2'][k] * 1.0, db['r2'][k] * 1.35
+    return db
+
+
+def test_juslin_scr_equals_juslin_without_switching_bonds():
+    # juslin_params.f90:95-103: the default JuslinScr database has or = bor = r; it differs from Juslin
+    # only for bonds inside a switching region (there the screened kernel uses fc (2 - fc))
+    db = P.complete_juslin_scr(None)
+    plain = {k: v for k, v in db.items() if k not in P.SCR_KEYS}
+    for a in (S.b1(['W', 'C'], 4.38, (2, 2, 2)), S.diamond('C', 3.558, (2, 2, 2))):
+        a.rattle(0.02, seed=1)
+        o1, o2 = juslin_scr_calc()(a), juslin_calc(plain)(a)
+        assert abs(o1['epot'] - o2['epot']) < 1e-10
+        assert np.abs(o1['f'] - o2['f']).max() < 1e-10
+        assert np.abs(o1['wpot'] - o2['wpot']).max() < 1e-9
+
+
+def test_juslin_scr_fd_and_mask():
+    calc = juslin_scr_calc(_juslin_scr_wide())
+    a = S.b1(['W', 'C'], 4.38, (2, 2, 2)); a.rattle(0.1, seed=1)
+    for i in (3, 9):
+        a.symbols[i] = 'H'
+    check_fd(calc, a, nat_check=4)
+    b = S.bcc('W', 3.165, (3, 3, 3)); b.rattle(0.15, seed=2)
+    check_fd(calc, b, nat_check=3)
+    assert abs(calc(b)['epot'] - juslin_scr_calc()(b)['epot']) > 1e-6   # the wider cutoffs matter
+    mask = (np.random.RandomState(4).rand(len(a)) > 0.5).astype(np.int32)
+    o0, o1, o2 = calc(a), calc(a, mask=mask), calc(a, mask=1 - mask)
+    assert abs(o1['epot'] + o2['epot'] - o0['epot']) < 1e-6
+    assert np.abs(o1['f'] + o2['f'] - o0['f']).max() < 1e-6
 
 
 # ---- Rebo2Scr (screened REBO2) ----------------------------------------------------------------------

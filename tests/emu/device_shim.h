@@ -35,5 +35,6 @@ static inline void atx_image_vector(const Mat3 &A, int sx, int sy, int sz, doubl
   az = (A.m[2] * s0 + A.m[5] * s1) + A.m[8] * s2;
 }
 // one host thread runs the atoms one after the other: plain read-modify-write
+#define ATX_NSUM 10
 #define RBS_ADD(p, v) (*(p) += (v))
 #define RBS_OR(p, v) (*(p) |= (v))

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "atx_rebo2_scr.cuh"
+#include "atx_rebo2_atom.cuh"
 
 extern "C" int emu_rebo2_scr(const atx_rebo2_params *par, const atx_rebo2_screening *scr, const int *el2typ,
                              int nat, int nbs, int nss, const double *Abox, const double *pos4_,
@@ -57,6 +58,41 @@ extern "C" int emu_rebo2_scr(const atx_rebo2_params *par, const atx_rebo2_screen
   for (int k = 0; k < RBS_NSUM; k++) acc[k] = 0.0;
   for (int i = 0; i < nat; i++) rbs_force_atom(T, A, P, S, pos4, seed, list, order, f, epa, wpa, epb, fpb, wpb, i, acc);
   for (int i = 0; i < nat; i++) rbs_scr_atom(T, A, P, pos4, seed, list, f, wpa, wpb, i, acc);
+  for (int k = 0; k < RBS_NSUM; k++) sums[k] = acc[k];
+  return 0;
+}
+
+
+// Unscreened REBO2: serial run of rb_bonds_atom / rb_force_atom (the bodies of k_rebo2_bonds /
+// k_rebo2_force), same inputs and outputs as above.
+extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat, int nbs, const double *Abox,
+                         const double *pos4_, const long long *seed, const int *list_, const int *order,
+                         double *sums, double *f, double *epa, double *wpa, double *epb, double *fpb,
+                         double *wpb) {
+  Rebo2Dev P;
+  std::memset(&P, 0, sizeof(P));
+  rb_fill_dev(P, par);
+  P.Fcc = par->Fcc; P.Fch = par->Fch; P.Fhh = par->Fhh; P.Tcc = par->Tcc; P.Pcc = par->Pcc; P.Pch = par->Pch;
+  for (int k = 0; k < 32; k++) P.el2typ[k] = el2typ[k];
+  Mat3 A;
+  for (int k = 0; k < 9; k++) A.m[k] = Abox[k];
+  const double4 *pos4 = reinterpret_cast<const double4 *>(pos4_);
+  const int2 *list = reinterpret_cast<const int2 *>(list_);
+  if (nbs > RB_NBL) nbs = RB_NBL;
+  const size_t nt = (size_t)nat * nbs + 1;
+  std::vector<int> b_cnt(nat + 1), b_nb(nt), b_typ(nt), b_shift(nt), b_slot(nt);
+  std::vector<double4> b_vec(nt);
+  std::vector<double2> b_cut(nt), nn(nat + 1);
+  int flag = 0;
+  for (int s = 0; s < nat; s++)
+    rb_bonds_atom(nbs, A, P, pos4, seed, list, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(),
+                  b_slot.data(), b_vec.data(), b_cut.data(), nn.data(), &flag, s);
+  if (flag) return flag;
+  double acc[RBS_NSUM];
+  for (int k = 0; k < RBS_NSUM; k++) acc[k] = 0.0;
+  for (int i = 0; i < nat; i++)
+    rb_force_atom(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_slot.data(),
+                  b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, epb, fpb, wpb, i, acc);
   for (int k = 0; k < RBS_NSUM; k++) sums[k] = acc[k];
   return 0;
 }

@@ -4,6 +4,7 @@ The screened-REBO2 kernels of atomistica_b200/csrc/atx_rebo2.cu are thin wrapper
 per-atom functions of csrc/atx_rebo2_scr.cuh.  That header is written without CUDA runtime types,
 so tests/emu/ compiles THE SAME SOURCE with g++ (device_shim.h stands in for double4, __ldg,
 atomicAdd, ...) and runs it one atom after the other on a neighbour list in the device format.
+The unscreened kernels are covered the same way (csrc/atx_rebo2_atom.cuh, emu_rebo2).
 This test checks that serial run against oracle.Rebo2Scr (which the reference's known answers pin,
 tests/test_oracle_kat.py): energy, forces, virial, per-atom and per-bond outputs at 1e-10.
 It covers the logic of the kernels, not their launch: the GPU parity test is
@@ -53,7 +54,9 @@ def device_list(nl, nat):
     return seed, ent, slots
 
 
-def run_emu(emu, a, nss=32, order=None, **kwargs):
+def run_emu(emu, a, nss=32, order=None, screened=True, **kwargs):
+    if not screened:
+        return run_emu_plain(emu, a, order=order, **kwargs)
     rb = oracle.Rebo2Scr(**kwargs)
     nat = len(a)
     nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, rb.cutoff(a.symbols), 1000)
@@ -81,6 +84,41 @@ def run_emu(emu, a, nss=32, order=None, **kwargs):
     out = dict(flag=flag, stats=stats, epot=sums[0], f=f, wpot=sums[1:].reshape(3, 3).T.copy(), epot_per_at=epa,
                wpot_per_at=wpa.reshape(nat, 3, 3).transpose(0, 2, 1).copy())
     # per-bond outputs: device slot n is reference slot slots[n]
+    for key, arr in (('epot_per_bond', epb), ('f_per_bond', fpb), ('wpot_per_bond', wpb)):
+        full = np.zeros((len(ref[key]),) + arr.shape[1:])
+        full[slots] = arr[:npairs]
+        out[key] = full.reshape(-1, 3, 3).transpose(0, 2, 1).copy() if key == 'wpot_per_bond' else full
+    return out, ref
+
+
+def run_emu_plain(emu, a, order=None, **kwargs):
+    """unscreened Rebo2: rb_bonds_atom / rb_force_atom (bodies of k_rebo2_bonds / k_rebo2_force)"""
+    okw = dict(kwargs)
+    if 'dihedral' in okw:
+        okw['with_dihedral'] = okw.pop('dihedral')
+    rb = oracle.Rebo2(**okw)
+    nat = len(a)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, rb.cutoff(a.symbols), 200)
+    ref = rb.energy_and_forces(a.positions, a.cell, nl, rb.ktyp(a.symbols), per_at=True, per_bond=True)
+    ref['nl'] = nl
+    d, tabs, par, keep = T.build_params(kwargs)
+    el2typ = np.zeros(32, dtype=np.int32)
+    el2typ[1], el2typ[2] = 1, 3
+    pos4 = np.zeros((nat, 4))
+    pos4[:, :3] = a.positions
+    pos4[:, 3] = [1 if s == 'C' else 2 if s == 'H' else 3 for s in a.symbols]
+    seed, ent, slots = device_list(nl, nat)
+    order = np.arange(nat, dtype=np.int32) if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    abox = oracle.abox_from_cell(a.cell)
+    nbs = int(max((seed[1:] - seed[:-1]).max(), 1))
+    npairs = len(ent)
+    sums = np.zeros(10); f = np.zeros((nat, 3)); epa = np.zeros(nat); wpa = np.zeros((nat, 9))
+    epb = np.zeros(npairs + 1); fpb = np.zeros((npairs + 1, 3)); wpb = np.zeros((npairs + 1, 9))
+    flag = emu.emu_rebo2(C.byref(par), L.iptr(el2typ), C.c_int(nat), C.c_int(nbs), L.dptr(abox), L.dptr(pos4),
+                         seed.ctypes.data_as(C.POINTER(C.c_longlong)), L.iptr(ent), L.iptr(order), L.dptr(sums),
+                         L.dptr(f), L.dptr(epa), L.dptr(wpa), L.dptr(epb), L.dptr(fpb), L.dptr(wpb))
+    out = dict(flag=flag, epot=sums[0], f=f, wpot=sums[1:].reshape(3, 3).T.copy(), epot_per_at=epa,
+               wpot_per_at=wpa.reshape(nat, 3, 3).transpose(0, 2, 1).copy())
     for key, arr in (('epot_per_bond', epb), ('f_per_bond', fpb), ('wpot_per_bond', wpb)):
         full = np.zeros((len(ref[key]),) + arr.shape[1:])
         full[slots] = arr[:npairs]
@@ -197,3 +235,24 @@ def test_other_screening_parameters(emu, aC_small):
 def test_screening_table_overflow_is_flagged(emu, aC_small):
     out, ref = run_emu(emu, aC_small, nss=1)
     assert out['flag'] & 2
+
+
+# ---- unscreened Rebo2: the same per-atom source that k_rebo2_bonds / k_rebo2_force wrap ------------
+
+def test_plain_rebo2_amorphous_carbon_and_dihedral(emu, aC_small):
+    check(emu, aC_small, screened=False)
+    check(emu, aC_small, screened=False, dihedral=True)
+
+
+def test_plain_rebo2_crystals_and_hydrocarbons(emu):
+    a = S.diamond('C', 3.566, (2, 2, 2)); a.rattle(0.1, seed=1)
+    check(emu, a, screened=False)
+    a = S.diamond('C', 3.566, (1, 1, 1)); a.rattle(0.05, seed=2)
+    check(emu, a, screened=False)
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.7, (2, 2, 2))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=6)
+    check(emu, a, screened=False)
+    check(emu, a, screened=False, dihedral=True)

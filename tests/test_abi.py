@@ -97,3 +97,26 @@ def test_parameter_completion():
     assert P.pair_index(0, 1, 2) == 1 and P.pair_index(1, 1, 2) == 2 and P.pair_index(2, 1, 3) == 4
     m = P.Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N
     assert abs(m['A'][1] - np.sqrt(1.3936e3 * 1.1e4)) < 1e-9
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """the drop-in boundary is a C header: it must compile as C99 (Fortran/C callers) and as C++, and
+    the ctypes mirrors in atomistica_b200/_lib.py must have the compiler's struct sizes"""
+    import subprocess
+    inc = os.path.join(ROOT, 'include')
+    structs = dict(atx_spline=L.AtxSpline, atx_bop_params=L.AtxBopParams, atx_bop_screening=L.AtxBopScreening,
+                   atx_juslin_params=L.AtxJuslinParams, atx_pair_params=L.AtxPairParams,
+                   atx_rebo2_params=L.AtxRebo2Params, atx_rebo2_screening=L.AtxRebo2Screening)
+    src = tmp_path / 'sizes.c'
+    src.write_text('#include <stdio.h>\n#include "atomistica_b200.h"\nint main(void) {\n' +
+                   ''.join('  printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in structs) +
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'sizes'
+    subprocess.run(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-I' + inc, str(src), '-o', str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    sizes = dict(zip(out[::2], map(int, out[1::2])))
+    for name, cls in structs.items():
+        assert sizes[name] == C.sizeof(cls), (name, sizes[name], C.sizeof(cls))
+    subprocess.run(['g++', '-std=c++17', '-pedantic', '-Wall', '-Werror', '-I' + inc, '-x', 'c++', '-c', str(src),
+                    '-o', str(tmp_path / 'sizes.o')], check=True)

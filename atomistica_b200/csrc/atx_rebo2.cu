@@ -92,6 +92,47 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
   }
 }
 
+// Caller-supplied (LAMMPS-style) lists: same loop 2 with the energy / virial of a bond counted for
+// its owned ends only, then the ghost rows are cleared (see rb_force_atom<ROLES>).
+__global__ void __launch_bounds__(RB_BLOCK)
+k_rebo2_force_roles(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
+                    const int *__restrict__ b_cnt, const int *__restrict__ b_nb,
+                    const int *__restrict__ b_typ, const int *__restrict__ b_shift,
+                    const int *__restrict__ b_slot, const double4 *__restrict__ b_vec,
+                    const double2 *__restrict__ b_cut, const double2 *__restrict__ nn,
+                    const double4 *__restrict__ pos4, const int *__restrict__ order,
+                    double *__restrict__ f, double *__restrict__ epa, double *__restrict__ wpa,
+                    double *__restrict__ partials, const unsigned char *__restrict__ role,
+                    const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * (RB_BLOCK / 32)];
+  const int i = blockIdx.x * RB_BLOCK + threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+  rb_force_atom<true>(nat, nbs, P, seed, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, pos4, order, f,
+                      epa, wpa, nullptr, nullptr, nullptr, i, acc, role);
+  atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
+  }
+}
+
+__global__ void k_rebo2_clear_ghosts(int nat, const unsigned char *__restrict__ role, double *__restrict__ f,
+                                     double *__restrict__ epa, double *__restrict__ wpa,
+                                     const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat || role[s] >= 2) return;
+  f[3 * (size_t)s] = 0.0; f[3 * (size_t)s + 1] = 0.0; f[3 * (size_t)s + 2] = 0.0;
+  if (epa) epa[s] = 0.0;
+  if (wpa) {
+#pragma unroll
+    for (int q = 0; q < 9; q++) wpa[9 * (size_t)s + q] = 0.0;
+  }
+}
+
 // ---- screened variant: thin kernels around the per-atom functions of atx_rebo2_scr.cuh ---------
 
 __global__ void k_rbs_bonds(RbsTab T, Mat3 A, Rebo2Dev P, RbsCut S, const double4 *__restrict__ pos4,
@@ -328,7 +369,16 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
                                                      pot->nn.ptr, pot->flag.ptr, o.stop);
     ATX_LAUNCHED();
   }
-  {
+  if (o.role) {
+    ProfScope ps_(ctx, "rebo2_force");
+    k_rebo2_force_roles<<<nblocks, RB_BLOCK, 0, st>>>(
+        nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
+        pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,
+        o.wpa, pot->sc.partials.ptr, o.role, o.stop);
+    ATX_LAUNCHED();
+    k_rebo2_clear_ghosts<<<(nat + 127) / 128, 128, 0, st>>>(nat, o.role, o.f, o.epa, o.wpa, o.stop);
+    ATX_LAUNCHED();
+  } else {
     ProfScope ps_(ctx, "rebo2_force");
     k_rebo2_force<<<nblocks, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr,
                                                 pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
@@ -342,6 +392,11 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
 }
 
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o) {
+  if (o.role) {
+    // the decomposed MD driver hands roles for its 2-cutoff ghost shell; REBO2 needs 5 bond cutoffs
+    atx_set_error("Rebo2 is not available under domain decomposition yet.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
   if (pot->screened) {
     // the screening table can overflow and is resized by the library-mode caller only
     atx_set_error("Rebo2Scr is not available in the device-resident MD driver yet.");
@@ -364,12 +419,16 @@ extern "C" int atx_rebo2_energy_and_forces(atx_rebo2 *pot, atx_particles *p, atx
     return ATX_ERROR_UNSPECIFIED;
   }
   atx_ctx *ctx = pot->ctx;
-  if (nl->external) {
-    atx_set_error("Rebo2 does not support an external neighbour list yet.");
+  if (nl->external && (pot->screened || epot_per_bond || f_per_bond || wpot_per_bond)) {
+    atx_set_error("Rebo2 with an external neighbour list: the screened variant and per-bond outputs are not "
+                  "available.");
     return ATX_ERROR_UNSPECIFIED;
   }
   ATX_PASS(atx_neighbors_update(nl, p));
   PotOut o;
+  // caller-supplied list with explicit ghosts: needs the ghosts within 5 bond cutoffs of the owned
+  // atoms and list rows for the ghosts
+  if (nl->external) o.role = nl->role_ext.ptr;
   ATX_PASS(pot->sc.f.reserve(3 * (size_t)nl->nat + 3));
   ATX_PASS(pot->sc.sums.reserve(ATX_NSUM));
   o.f = pot->sc.f.ptr;

@@ -85,7 +85,12 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
   nn[s] = make_double2(nC, nH);
 }
 
-// loop 2 of one atom (bop_kernel_rebo2.f90:1209-2781, SCREENING undefined, DIHEDRAL); i >= nat: nothing
+// loop 2 of one atom (bop_kernel_rebo2.f90:1209-2781, SCREENING undefined, DIHEDRAL); i >= nat: nothing.
+// ROLES (caller-supplied lists with explicit ghosts, role 2 = owned, 1 = ghost): every bond among the
+// local atoms is evaluated and scattered as usual, but the energy and the virial of a bond are
+// counted half for each OWNED end only, so that the sums over the ranks (or over the owned atoms of
+// an unfolded periodic system) are the reference's totals; the caller discards the ghost rows.
+template <bool ROLES = false>
 __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &P,
                                               const long long *__restrict__ seed,
                                               const int *__restrict__ b_cnt, const int *__restrict__ b_nb,
@@ -98,7 +103,8 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
                                               const int *__restrict__ order, double *__restrict__ f,
                                               double *__restrict__ epa, double *__restrict__ wpa,
                                               double *__restrict__ epb, double *__restrict__ fpb,
-                                              double *__restrict__ wpb, int i, double *acc) {
+                                              double *__restrict__ wpb, int i, double *acc,
+                                              const unsigned char *__restrict__ role = nullptr) {
   const int ktypi = i < nat ? P.el2typ[(int)pos4[i].w] : 0;
   const int nbi = (i < nat && ktypi > 0) ? b_cnt[i] : 0;
   if (nbi > 0) {
@@ -451,7 +457,12 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       // ---- pair terms (:2525-2716)
       const double baveij = 0.5 * (bij + bji + fij + tij * bdh);
       const double hlfvij = fcarij * (frij + baveij * faij) / 2;
-      acc[0] += 2 * hlfvij;
+      double wown = 1.0;  // share of this bond that belongs to owned atoms
+      if (ROLES) {
+        wown = 0.5 * ((role[i] >= 2 ? 1.0 : 0.0) + (role[j] >= 2 ? 1.0 : 0.0));
+        acc[0] += 2 * hlfvij * wown;
+      } else
+        acc[0] += 2 * hlfvij;
       if (epa) {
         RBS_ADD(&epa[i], hlfvij);
         RBS_ADD(&epa[j], hlfvij);
@@ -467,7 +478,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       fjx += -(dfbij * djx + dfbji * bjx); fjy += -(dfbij * djy + dfbji * bjy); fjz += -(dfbij * djz + dfbji * bjz);
       rb_add3(f, j, fjx, fjy, fjz);
 #pragma unroll
-      for (int q = 0; q < 9; q++) acc[1 + q] += wij[q];
+      for (int q = 0; q < 9; q++) acc[1 + q] += ROLES ? wown * wij[q] : wij[q];
       const long long a = seed[i] + b_slot[qi + ij];
       if (epb) epb[a] = 2 * hlfvij;
       if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }

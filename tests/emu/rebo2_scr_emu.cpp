@@ -68,7 +68,7 @@ extern "C" int emu_rebo2_scr(const atx_rebo2_params *par, const atx_rebo2_screen
 extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat, int nbs, const double *Abox,
                          const double *pos4_, const long long *seed, const int *list_, const int *order,
                          double *sums, double *f, double *epa, double *wpa, double *epb, double *fpb,
-                         double *wpb) {
+                         double *wpb, const unsigned char *role /* nullptr, or 2 owned / 1 ghost */) {
   Rebo2Dev P;
   std::memset(&P, 0, sizeof(P));
   rb_fill_dev(P, par);
@@ -90,9 +90,24 @@ extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat
   if (flag) return flag;
   double acc[RBS_NSUM];
   for (int k = 0; k < RBS_NSUM; k++) acc[k] = 0.0;
-  for (int i = 0; i < nat; i++)
-    rb_force_atom(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_slot.data(),
-                  b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, epb, fpb, wpb, i, acc);
+  if (role) {
+    // k_rebo2_force_roles + k_rebo2_clear_ghosts
+    for (int i = 0; i < nat; i++)
+      rb_force_atom<true>(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(),
+                          b_slot.data(), b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, nullptr,
+                          nullptr, nullptr, i, acc, role);
+    for (int s = 0; s < nat; s++) {
+      if (role[s] >= 2) continue;
+      f[3 * s] = f[3 * s + 1] = f[3 * s + 2] = 0.0;
+      if (epa) epa[s] = 0.0;
+      if (wpa)
+        for (int q = 0; q < 9; q++) wpa[9 * s + q] = 0.0;
+    }
+  } else {
+    for (int i = 0; i < nat; i++)
+      rb_force_atom(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_slot.data(),
+                    b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, epb, fpb, wpb, i, acc);
+  }
   for (int k = 0; k < RBS_NSUM; k++) sums[k] = acc[k];
   return 0;
 }

@@ -116,7 +116,7 @@ def run_emu_plain(emu, a, order=None, **kwargs):
     epb = np.zeros(npairs + 1); fpb = np.zeros((npairs + 1, 3)); wpb = np.zeros((npairs + 1, 9))
     flag = emu.emu_rebo2(C.byref(par), L.iptr(el2typ), C.c_int(nat), C.c_int(nbs), L.dptr(abox), L.dptr(pos4),
                          seed.ctypes.data_as(C.POINTER(C.c_longlong)), L.iptr(ent), L.iptr(order), L.dptr(sums),
-                         L.dptr(f), L.dptr(epa), L.dptr(wpa), L.dptr(epb), L.dptr(fpb), L.dptr(wpb))
+                         L.dptr(f), L.dptr(epa), L.dptr(wpa), L.dptr(epb), L.dptr(fpb), L.dptr(wpb), None)
     out = dict(flag=flag, epot=sums[0], f=f, wpot=sums[1:].reshape(3, 3).T.copy(), epot_per_at=epa,
                wpot_per_at=wpa.reshape(nat, 3, 3).transpose(0, 2, 1).copy())
     for key, arr in (('epot_per_bond', epb), ('f_per_bond', fpb), ('wpot_per_bond', wpb)):
@@ -256,3 +256,61 @@ def test_plain_rebo2_crystals_and_hydrocarbons(emu):
     a.rattle(0.1, seed=6)
     check(emu, a, screened=False)
     check(emu, a, screened=False, dihedral=True)
+
+
+def test_plain_rebo2_caller_supplied_list_with_ghosts(emu):
+    """LAMMPS-style operation of Rebo2 (k_rebo2_force_roles): owned atoms plus explicit ghost images,
+    full lists without periodic shifts for owned and ghost atoms.  Energy and virial count the owned
+    ends of every bond, forces are exact on owned atoms when the ghost shell is 5 bond cutoffs deep."""
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.6, (3, 3, 3))
+    for i in rng.choice(len(a), len(a) // 4, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=4)
+    rb = oracle.Rebo2()
+    cutoff = rb.cutoff(a.symbols)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
+    ref = rb.energy_and_forces(a.positions, a.cell, nl, rb.ktyp(a.symbols), per_at=True)
+
+    # unfold: ghosts within 5 cutoffs of the box, brute-force lists (with a skin, as a host code has)
+    Lbox = np.diag(a.cell)
+    w, skin = 5 * cutoff, 0.3
+    pos, sym = [a.positions], [list(a.symbols)]
+    for sx in (-1, 0, 1):
+        for sy in (-1, 0, 1):
+            for sz in (-1, 0, 1):
+                if (sx, sy, sz) == (0, 0, 0):
+                    continue
+                q = a.positions + np.array([sx, sy, sz]) * Lbox
+                m = np.all((q > -w) & (q < Lbox + w), axis=1)
+                pos.append(q[m]); sym.append([s for s, t in zip(a.symbols, m) if t])
+    pos = np.concatenate(pos); sym = sum(sym, [])
+    nall, nloc = len(pos), len(a)
+    assert w < Lbox.min()
+    d2 = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
+    np.fill_diagonal(d2, 1e9)
+    rows = [np.nonzero(d2[i] < (cutoff + skin) ** 2)[0] for i in range(nall)]
+    seed = np.zeros(nall + 1, dtype=np.int64)
+    seed[1:] = np.cumsum([len(r) for r in rows])
+    ent = np.zeros((seed[-1], 2), dtype=np.int32)
+    ent[:, 0] = np.concatenate(rows)
+    ent[:, 1] = 128 | (128 << 8) | (128 << 16)
+    role = np.ones(nall, dtype=np.uint8); role[:nloc] = 2
+    pos4 = np.zeros((nall, 4)); pos4[:, :3] = pos
+    pos4[:, 3] = [1 if s == 'C' else 2 for s in sym]
+    el2typ = np.zeros(32, dtype=np.int32); el2typ[1], el2typ[2] = 1, 3
+    d, tabs, par, keep = T.build_params({})
+    abox = np.eye(3).ravel() * 1000.0
+    sums = np.zeros(10); f = np.zeros((nall, 3)); epa = np.zeros(nall); wpa = np.zeros((nall, 9))
+    order = np.arange(nall, dtype=np.int32)
+    flag = emu.emu_rebo2(C.byref(par), L.iptr(el2typ), C.c_int(nall), C.c_int(12), L.dptr(abox), L.dptr(pos4),
+                         seed.ctypes.data_as(C.POINTER(C.c_longlong)), L.iptr(ent), L.iptr(order), L.dptr(sums),
+                         L.dptr(f), L.dptr(epa), L.dptr(wpa), None, None, None,
+                         role.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    assert flag == 0
+    close(sums[0], ref['epot'], 'epot')
+    close(sums[1:].reshape(3, 3).T, ref['wpot'], 'wpot')
+    close(f[:nloc], ref['f'], 'f')
+    close(epa[:nloc], ref['epot_per_at'], 'epot_per_at')
+    close(wpa[:nloc].reshape(nloc, 3, 3).transpose(0, 2, 1), ref['wpot_per_at'], 'wpot_per_at')
+    assert np.abs(f[nloc:]).max() == 0.0 and np.abs(epa[nloc:]).max() == 0.0

@@ -4,6 +4,8 @@ A periodic system is unfolded the way LAMMPS would hand it over -- owned atoms p
 within a 2 x cutoff shell, full lists for owned AND ghost atoms (REQ_FULL|REQ_GHOST), no periodic
 shifts -- and the result must equal the ordinary periodic calculation: energy, virial, forces on
 the owned atoms; ghost rows of the force array stay zero."""
+import os
+
 import numpy as np
 import pytest
 
@@ -13,11 +15,11 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
 
-def unfold(atoms, cutoff):
-    """owned atoms + ghost images within 2*cutoff of the (orthorhombic) box, brute-force full lists"""
+def unfold(atoms, cutoff, shell=2):
+    """owned atoms + ghost images within shell*cutoff of the (orthorhombic) box, brute-force full lists"""
     L = np.diag(atoms.cell)
     pos, sym = [atoms.positions], [list(atoms.symbols)]
-    w = 2 * cutoff
+    w = shell * cutoff
     rng = [range(-int(np.ceil(w / L[k])), int(np.ceil(w / L[k])) + 1) for k in range(3)]
     for i in rng[0]:
         for j in rng[1]:
@@ -43,7 +45,7 @@ def unfold(atoms, cutoff):
 SKIN = 0.3      # the host's list carries a skin; the kernels apply the potentials' own cutoffs
 
 
-def _compare(atoms, make_pot, cutoff, avgn=200):
+def _compare(atoms, make_pot, cutoff, avgn=200, shell=2):
     cutoff = cutoff + SKIN
     p0 = native.from_atoms(atoms)
     nl0 = native.Neighbors(avgn)
@@ -51,7 +53,7 @@ def _compare(atoms, make_pot, cutoff, avgn=200):
     pot0.bind_to(p0, nl0)
     e0, f0, w0 = pot0.energy_and_forces(p0, nl0)[:3]
 
-    big, lists = unfold(atoms, cutoff)
+    big, lists = unfold(atoms, cutoff, shell)
     nloc = len(atoms)
     p = native.from_atoms(big)
     nl = native.Neighbors(avgn)
@@ -68,7 +70,7 @@ def _compare(atoms, make_pot, cutoff, avgn=200):
     d = np.random.RandomState(1).normal(scale=0.01, size=(nloc, 3))
     atoms2 = atoms.copy()
     atoms2.positions = atoms.positions + d
-    big2, _ = unfold(atoms2, cutoff)
+    big2, _ = unfold(atoms2, cutoff, shell)
     if len(big2) == len(big) and np.abs(big2.positions - big.positions).max() < 0.1:
         p.coordinates[:, :] = big2.positions
         p.I_changed_positions()
@@ -103,7 +105,7 @@ def test_lj_external():
     _compare(a, lambda: native.LJCut(epsilon=0.0104, sigma=3.40, cutoff=6.0), 6.0)
 
 
-def test_rebo2_refuses_external():
+def test_rebo2_external_refuses_per_bond_outputs():
     a = S.diamond('C', 3.566, (2, 2, 2))
     big, lists = unfold(a, 2.0)
     p = native.from_atoms(big)
@@ -112,4 +114,17 @@ def test_rebo2_refuses_external():
     pot.bind_to(p, nl)
     nl.set_external(p, len(a), np.arange(len(big)), lists)
     with pytest.raises(RuntimeError):
-        pot.energy_and_forces(p, nl)
+        pot.energy_and_forces(p, nl, epot_per_bond=True)
+
+
+@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
+                    reason='k_rebo2_force_roles not yet run on hardware (its per-atom source is checked on the '
+                           'CPU by tests/test_emu_rebo2_scr.py)')
+def test_rebo2_external():
+    # REBO2 reaches five bonds: ghosts within 5 bond cutoffs
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.6, (3, 3, 3))
+    for i in rng.choice(len(a), len(a) // 4, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=4)
+    _compare(a, native.Rebo2, 2.0, avgn=50, shell=5)

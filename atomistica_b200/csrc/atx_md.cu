@@ -24,6 +24,7 @@ int atx_bop_compute_device(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
                            const int *mask_sorted, const PotOut &o);
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o);
 int atx_bop_check_overflow(atx_bop *pot);
+int atx_rebo2_check_overflow(atx_rebo2 *pot);
 
 struct MdCtrl {
   int stop;
@@ -370,6 +371,7 @@ extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
     ATX_CUDA(cudaStreamSynchronize(st));
     ATX_CUDA(cudaGetLastError());
     if (md->pot_kind == ATX_POT_BOP) ATX_PASS(atx_bop_check_overflow((atx_bop *)md->pot));
+    if (md->pot_kind == ATX_POT_REBO2) ATX_PASS(atx_rebo2_check_overflow((atx_rebo2 *)md->pot));
     MdCtrl hc = *md->hctrl.ptr;
     int done = hc.steps_done - done_total;
     done_total = hc.steps_done;

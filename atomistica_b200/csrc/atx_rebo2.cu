@@ -206,6 +206,8 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
   D.Pcc = t + 4 * n3; D.Pch = t + 4 * n3 + n2;
   for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
   ATX_PASS(pot->flag.reserve(4));
+  // guarded (batched MD) steps never clear the flag: it has to start from zero
+  ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 4 * sizeof(int)));
   *out = pot;
   return 0;
 }
@@ -388,6 +390,18 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
     ATX_LAUNCHED();
   }
   ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  return 0;
+}
+
+// overflow of the bond table during guarded (batched MD) steps; called by the MD driver after a sync
+int atx_rebo2_check_overflow(atx_rebo2 *pot) {
+  int h = 0;
+  ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, pot->ctx->stream));
+  ATX_CUDA(cudaStreamSynchronize(pot->ctx->stream));
+  if (h) {
+    atx_set_error("Internal neighbor list exhausted, *nebmax* too small (bond table overflow during MD).");
+    return ATX_ERROR_UNSPECIFIED;
+  }
   return 0;
 }
 

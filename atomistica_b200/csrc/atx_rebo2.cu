@@ -276,6 +276,9 @@ static int rebo2_scr_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl
   int nbs = nl->nebmax < 1 ? 1 : nl->nebmax;
   if (nbs > RBS_NBL) nbs = RBS_NBL;
   if (pot->nss < 1) pot->nss = 32;
+  // guarded (batched MD) steps cannot repeat a pass with a larger screening table: start wider; an
+  // overflow raises the sticky flag that atx_rebo2_check_overflow reports after the batch
+  if (o.stop && pot->nss < 64) pot->nss = 64;
   pot->nbs = nbs;
   const size_t nt = (size_t)nat * nbs + 1, ns = (size_t)nat * pot->nss + 1;
   ATX_PASS(pot->b_cnt.reserve(nat + 1));
@@ -313,7 +316,7 @@ static int rebo2_scr_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl
   if (nblocks < 1) nblocks = 1;
   const int nbtot = 2 * nblocks;  // loop 2 and loop 3 each contribute one column per block
   ATX_PASS(pot->sc.partials.reserve((size_t)nbtot * ATX_NSUM));
-  ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
+  if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
   ATX_CUDA(cudaMemsetAsync(o.f, 0, sizeof(double) * 3 * (size_t)nat, st));
   if (o.epa) ATX_CUDA(cudaMemsetAsync(o.epa, 0, sizeof(double) * (size_t)nat, st));
   if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
@@ -399,7 +402,8 @@ int atx_rebo2_check_overflow(atx_rebo2 *pot) {
   ATX_CUDA(cudaMemcpyAsync(&h, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, pot->ctx->stream));
   ATX_CUDA(cudaStreamSynchronize(pot->ctx->stream));
   if (h) {
-    atx_set_error("Internal neighbor list exhausted, *nebmax* too small (bond table overflow during MD).");
+    atx_set_error(h & 1 ? "Internal neighbor list exhausted, *nebmax* too small (bond table overflow during MD)."
+                        : "Rebo2Scr: table of screening neighbours exhausted during MD.");
     return ATX_ERROR_UNSPECIFIED;
   }
   return 0;
@@ -409,11 +413,6 @@ int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl
   if (o.role) {
     // the decomposed MD driver hands roles for its 2-cutoff ghost shell; REBO2 needs 5 bond cutoffs
     atx_set_error("Rebo2 is not available under domain decomposition yet.");
-    return ATX_ERROR_UNSPECIFIED;
-  }
-  if (pot->screened) {
-    // the screening table can overflow and is resized by the library-mode caller only
-    atx_set_error("Rebo2Scr is not available in the device-resident MD driver yet.");
     return ATX_ERROR_UNSPECIFIED;
   }
   return rebo2_compute(pot, p, nl, o, nullptr, nullptr, nullptr);

@@ -1,4 +1,6 @@
 """Device-resident velocity-Verlet vs a host velocity-Verlet driven by the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -90,3 +92,19 @@ def test_bop_md_energy_conservation(cls, avgn):
     assert drift < 5e-5, drift
     if cls is not native.Rebo2:
         assert drv.stats()['nrebuilds'] >= 1
+
+
+@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
+                    reason='Rebo2Scr kernels not yet run on hardware (set ATX_RUN_UNVERIFIED=1)')
+def test_rebo2scr_md_energy_conservation():
+    a = S.diamond('C', 3.566, (4, 4, 4))
+    a.rattle(0.02, seed=3)
+    m = np.full(len(a), 12.011)
+    v0 = md.maxwell_boltzmann(m, 600.0, seed=4)
+    p = native.from_atoms(a)
+    nl = native.Neighbors(1000)
+    drv = md.VelocityVerlet(native.Rebo2Scr(), p, nl, m, v0, dt=0.25, verlet_shell=0.3)
+    e0 = sum(drv.run(1))
+    es = [sum(drv.run(100)) for _ in range(4)]
+    drift = max(abs(e - e0) for e in es) / len(a)
+    assert drift < 5e-5, drift

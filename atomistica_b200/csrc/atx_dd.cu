@@ -791,10 +791,14 @@ extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const doubl
   const double shi_own = (!md->pbc[0] && me == P - 1) ? 1e300 : md->shi;
   // thickness of the whole cell between the faces spanned by a2, a3: 1/|Bbox(1,:)|
   double bn = std::sqrt(Bbox[0] * Bbox[0] + Bbox[3] * Bbox[3] + Bbox[6] * Bbox[6]);
-  double halo = P > 1 ? 2.0 * (rc + skin) : 0.0;
+  // EAM / BOP gather: 2 cutoffs.  REBO2 evaluates every bond among its local atoms and keeps the owned
+  // share (rb_force_atom<ROLES>): the forces on an owned atom depend on atoms up to five bonds away.
+  const double hmul = pot_kind == ATX_POT_REBO2 ? 5.0 : 2.0;
+  double halo = P > 1 ? hmul * (rc + skin) : 0.0;
   md->hfrac = halo * bn;
   if (P > 1 && md->hfrac > 1.0 / P) {
-    atx_set_error("Domain decomposition: slabs are thinner than the halo 2*(rc+skin); use fewer ranks.");
+    atx_set_error("Domain decomposition: slabs are thinner than the halo (2*(rc+skin), REBO2: 5*(rc+skin)); use "
+                  "fewer ranks.");
     delete md;
     return ATX_ERROR_UNSPECIFIED;
   }

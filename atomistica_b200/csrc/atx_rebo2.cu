@@ -410,9 +410,8 @@ int atx_rebo2_check_overflow(atx_rebo2 *pot) {
 }
 
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o) {
-  if (o.role) {
-    // the decomposed MD driver hands roles for its 2-cutoff ghost shell; REBO2 needs 5 bond cutoffs
-    atx_set_error("Rebo2 is not available under domain decomposition yet.");
+  if (o.role && pot->screened) {
+    atx_set_error("Rebo2Scr is not available under domain decomposition.");
     return ATX_ERROR_UNSPECIFIED;
   }
   return rebo2_compute(pot, p, nl, o, nullptr, nullptr, nullptr);

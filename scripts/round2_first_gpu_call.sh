@@ -6,6 +6,8 @@
 # 2. A/B of the EAM lane mapping and lanes per atom on the bench configuration (tells the two L1
 #    wavefront rules of DESIGN.md section 8.1 apart);
 # 3. first ncu captures of the kernels that were never profiled: REBO2, Rebo2Scr, screened BOP.
+# Second call, 2 GPUs (REBO2 under domain decomposition, also fenced):
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'ATX_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_dd.py -m gpu -q'
 # Everything lands in gpurun_out/r02_first/; nothing here is a bench value (ncu runs are profiles).
 set -u
 OUT=gpurun_out/r02_first

@@ -23,6 +23,11 @@ def main():
         a = S.fcc('Cu', 3.615, (24, 6, 6))
         mass, T, rc, skin, dt = 63.546, 1200.0, float(setfl['cutoff']), 0.4, 2.0
         mk = lambda dev: native.TabulatedAlloyEAM(setfl=setfl, device=dev)
+    elif case == 'rebo2':
+        # halo 5 x (rc + skin) = 11.5 A: slabs of 21 A at 4 ranks
+        a = S.diamond('C', 3.566, (24, 3, 3))
+        mass, T, rc, skin, dt = 12.011, 1500.0, 2.0, 0.3, 0.25
+        mk = lambda dev: native.Rebo2(device=dev)
     else:
         a = S.diamond('Si', 5.432, (16, 4, 4))
         mass, T, rc, skin, dt = 28.0855, 1500.0, 3.0, 0.3, 1.0

@@ -314,3 +314,15 @@ def test_plain_rebo2_caller_supplied_list_with_ghosts(emu):
     close(epa[:nloc], ref['epot_per_at'], 'epot_per_at')
     close(wpa[:nloc].reshape(nloc, 3, 3).transpose(0, 2, 1), ref['wpot_per_at'], 'wpot_per_at')
     assert np.abs(f[nloc:]).max() == 0.0 and np.abs(epa[nloc:]).max() == 0.0
+
+
+def test_reference_fd_configurations(emu):
+    """the structures of the reference's test_forces_and_virial.py rows for Rebo2 / Rebo2Scr (shifted,
+    then rattled by 0.5 A: up to 14 bonds and 19 screening neighbours per atom)"""
+    import test_gpu_forces_and_virial as G
+    for row, screened in ((10, False), (11, True)):
+        for name, a in G.table()[row][2]:
+            a.positions = a.positions + 0.1
+            for state in range(2):
+                out, ref = check(emu, a, screened=screened)
+                a.rattle(0.5, seed=row + 1)

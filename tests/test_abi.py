@@ -120,3 +120,40 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
         assert sizes[name] == C.sizeof(cls), (name, sizes[name], C.sizeof(cls))
     subprocess.run(['g++', '-std=c++17', '-pedantic', '-Wall', '-Werror', '-I' + inc, '-x', 'c++', '-c', str(src),
                     '-o', str(tmp_path / 'sizes.o')], check=True)
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    libdir = os.path.join(ROOT, 'atomistica_b200')
+    exe = str(tmp_path / 'tersoff_from_c')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-I' + os.path.join(ROOT, 'include'),
+                    os.path.join(ROOT, 'examples', 'tersoff_from_c.c'), '-o', exe, '-L' + libdir,
+                    '-latomistica_b200', '-Wl,-rpath,' + libdir, '-lm'], check=True)
+    return exe
+
+
+def test_c_example_links_and_fails_loudly_without_a_device(tmp_path):
+    """examples/tersoff_from_c.c is the C ABI used from plain C; without a GPU it must stop at
+    atx_ctx_create with the library's error text"""
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    if os.path.exists('/usr/bin/nvidia-smi') and subprocess.run(['nvidia-smi', '-L'],
+                                                                capture_output=True).returncode == 0:
+        pytest.skip('a GPU is present')
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2
+    assert 'no CPU fallback' in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1', reason='C example not yet run on hardware')
+def test_c_example_on_the_gpu(tmp_path):
+    import subprocess
+    r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    e0 = float(lines[1].split('=')[1].split()[0])
+    assert abs(e0 - (-4.6295950127)) < 1e-8          # closed form, tests/golden/kat.json
+    assert 'max |f|' in lines[2]
+    fsum = [abs(float(x)) for x in lines[2].split('sum f =')[1].split()]
+    assert max(fsum) < 1e-9

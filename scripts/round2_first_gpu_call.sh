@@ -7,7 +7,9 @@
 #    wavefront rules of DESIGN.md section 8.1 apart);
 # 3. first ncu captures of the kernels that were never profiled: REBO2, Rebo2Scr, screened BOP.
 # Second call, 2 GPUs (REBO2 under domain decomposition, also fenced):
-#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'ATX_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_dd.py -m gpu -q'
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'ATX_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_dd.py -m gpu -q;
+#     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 \
+#       benchmarks/run_dd.py --kind Rebo2 --cells 5 --steps 50 --skin 0.3'     # C3 under decomposition
 # Everything lands in gpurun_out/r02_first/; nothing here is a bench value (ncu runs are profiles).
 set -u
 OUT=gpurun_out/r02_first

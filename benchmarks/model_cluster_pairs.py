@@ -24,8 +24,26 @@ from atomistica_b200 import structures as S   # noqa: E402
 RC = 5.50679
 
 
+def _morton(ix, iy, iz, bits=10):
+    k = np.zeros(len(ix), dtype=np.int64)
+    for b in range(bits):
+        k |= ((ix >> b) & 1).astype(np.int64) << (3 * b + 2)
+        k |= ((iy >> b) & 1).astype(np.int64) << (3 * b + 1)
+        k |= ((iz >> b) & 1).astype(np.int64) << (3 * b)
+    return k
+
+
 def clusters(pos, L, m, cell):
-    """atoms binned into cubic cells of edge `cell`, cell-sorted, chunked into clusters of m"""
+    """atoms binned into cubic cells of edge `cell`, cell-sorted, chunked into clusters of m.
+    cell < 0: atoms sorted along a Morton curve over a grid of edge |cell| instead (spatially compact
+    clusters, what a tile list needs)"""
+    if cell < 0:
+        n = np.maximum(1, np.floor(L / -cell)).astype(int)
+        idx = np.floor(pos / (L / n)).astype(int) % n
+        order = np.argsort(_morton(idx[:, 0], idx[:, 1], idx[:, 2]), kind='stable')
+        ncl = (len(pos) + m - 1) // m
+        order = np.concatenate([order, np.full(ncl * m - len(pos), -1)])
+        return order.reshape(ncl, m)
     n = np.maximum(1, np.floor(L / cell)).astype(int)
     idx = np.floor(pos / (L / n)).astype(int) % n
     key = (idx[:, 0] * n[1] + idx[:, 1]) * n[2] + idx[:, 2]
@@ -92,7 +110,7 @@ def main():
     print('%8s %12s %12s %10s %8s   model wavefronts/atom (both passes, Newton-3 inside tiles)' %
           ('MI x MJ', 'tiles/atom', 'slots/atom', 'in range', 'fill'))
     for mi, mj in ((4, 4), (8, 4), (8, 8), (16, 4)):
-        for cell in (3.615, 2 * 3.615):
+        for cell in (3.615, 2 * 3.615, -1.2, -1.8):
             st = tile_stats(pos, L, mi, mj, rlist, RC, cell)
             # per tile and pass: 1 entry + 1 contiguous j-position load (+ MI rows of i in registers);
             # table records: half of the directed in-range pairs per pass (each undirected pair once),
@@ -100,9 +118,10 @@ def main():
             w = st['tiles_per_atom'] * mi * (1 + mj * 32 / 128.0) * 2 / mi * 1.0 \
                 + 0.5 * st['in_range_per_atom'] * (1 + 2) \
                 + st['tiles_per_atom'] * (1 + 3) * np.log2(mi) * 2 / mi
-            print('%8s %12.1f %12.0f %10.1f %7.0f%%   cell %.2f A: %.0f  (%.1fx fewer than today)' %
+            fp64 = st['slots_per_atom'] / 78.0      # pair slots a warp steps through per listed pair of today
+            print('%8s %12.1f %12.0f %10.1f %7.0f%%   %s %.2f A: %.0f  (%.1fx fewer than today); pair slots %.1fx today' %
                   ('%dx%d' % (mi, mj), st['tiles_per_atom'], st['slots_per_atom'], st['in_range_per_atom'],
-                   100 * st['fill'], cell, w, w_now / w))
+                   100 * st['fill'], 'cell' if cell > 0 else 'morton grid', abs(cell), w, w_now / w, fp64))
 
 
 if __name__ == '__main__':

@@ -66,4 +66,8 @@ for w in rebo2 rebo2scr tersoffscr; do
   echo "  ncu $w exit $?" | tee -a $OUT/summary.txt
   tail -2 $OUT/ncu_$w.log | tee -a $OUT/summary.txt
 done
+# neighbour build (never profiled with --set full): two builds of the bench system
+timeout 600 ncu --set full --clock-control none --import-source on -c 6 -k regex:'k_pairs|k_rows_to_csr' \
+  -o $OUT/r02_nl -f python bench.py --steps 70 --warmup 3 --no-cpu > $OUT/ncu_nl.log 2>&1
+echo "  ncu nl exit $?" | tee -a $OUT/summary.txt
 ls -la $OUT | tee -a $OUT/summary.txt

@@ -135,3 +135,31 @@ def maxwell_boltzmann(masses_amu, T, seed=12345):
     v = rng.normal(size=(len(m), 3)) * np.sqrt(kB * T / m)[:, None]
     v -= (v * m[:, None]).sum(axis=0) / m.sum()
     return v
+
+
+def oriented_diamond(symbols, a, directions, size=(1, 1, 1)):
+    """Diamond (one symbol) or zincblende ([A, B]: A on the fcc sites, B on the shifted ones) in the
+    smallest orthorhombic cell whose axes run along three mutually orthogonal integer directions, like
+    ase.lattice.cubic.Diamond(directions=...).  Along a direction [h, k, l] (coprime) the fcc repeat is
+    a/2 [h, k, l] when h + k + l is even and a [h, k, l] otherwise."""
+    if isinstance(symbols, str):
+        symbols = [symbols, symbols]
+    D = np.array(directions, dtype=np.int64)
+    assert D.shape == (3, 3) and not (D @ D.T - np.diag(np.diag(D @ D.T))).any(), 'directions must be orthogonal'
+    V = np.array([(0.5 if d.sum() % 2 == 0 else 1.0) * a * d for d in D])       # rows: cell vectors
+    L = np.sqrt((V * V).sum(axis=1))
+    n = int(np.ceil(np.abs(V).sum(axis=0).max() / a)) + 1
+    g = np.arange(-n, n + 1)
+    cells = np.stack(np.meshgrid(g, g, g, indexing='ij'), axis=-1).reshape(-1, 3)
+    pos, sym = [], []
+    for b in range(4):
+        for shift, s in ((0.0, symbols[0]), (0.25, symbols[1])):
+            p = (cells + _FCC[b] + shift) * a
+            frac = p @ V.T / (L * L)
+            keep = np.all((frac > -1e-9) & (frac < 1 - 1e-9), axis=1)
+            pos.append(frac[keep] * L)
+            sym += [s] * int(keep.sum())
+    pos = np.concatenate(pos)
+    order = np.lexsort((pos[:, 0], pos[:, 1], pos[:, 2]))
+    unit = Atoms([sym[i] for i in order], pos[order], L, True)
+    return unit.repeat(size)

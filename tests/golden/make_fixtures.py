@@ -184,11 +184,16 @@ def main():
             'Tersoff_BCN_B3_BN': dict(Ec=6.63, a0=3.658, B=385.0),
         },
         'bulk_tol_rel': 0.05,
-        # tests/test_surface_properties.py:228-262: relaxed (100) surface energies of the Erhart-Albe
-        # parameter set, unscreened and screened rows (5 % tolerance, atomistica/tests.py:597-700)
-        'surface_100_relaxed_J_m2': {'Brenner': {'C': 5.59, 'Si': 1.95, 'SiC': 3.93},
-                                     'BrennerScr': {'C': 5.88, 'Si': 1.90, 'SiC': 3.87}},
         'surface_tol_rel': 0.05,
+        # all rows of tests/test_surface_properties.py:213-246 that carry a value (r_Jm2): ideal (111),
+        # (110), (100) terminations and the dimerised (100)-2x1, relaxed to fmax = 0.005 eV/A
+        'surface_relaxed_J_m2': {
+            'Brenner': {'C': {'111': 2.06, '110': 2.96, '100': 5.59, '100-2x1': 5.65},
+                        'Si': {'111': 0.999, '110': 1.23, '100': 1.95, '100-2x1': 1.13},
+                        'SiC': {'111': 1.67, '110': 2.29, '100': 3.93, '100-2x1': 2.85}},
+            'BrennerScr': {'C': {'111': 2.06, '110': 2.96, '100': 5.88, '100-2x1': 5.89},
+                           'Si': {'111': 0.999, '110': 1.23, '100': 1.90, '100-2x1': 1.13},
+                           'SiC': {'111': 1.67, '110': 2.29, '100': 3.87, '100-2x1': 2.91}}},
         # closed form from the reference formulas
         'tersoff_si_diamond_a0_5.432_eV_per_atom': -4.6295950127,
         'kumagai_si_diamond_a0_5.429_eV_per_atom': -4.6299992839,

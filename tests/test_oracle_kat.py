@@ -159,6 +159,9 @@ def bulk_props(calc, builder, a0_guess):
     e12 = np.zeros((3, 3)); e12[0, 0] = d; e12[1, 1] = d
     Csum = (e_strain(e12) - 2 * e0 + e_strain(-e12)) / d ** 2 / V      # 2 C11 + 2 C12
     C12 = (Csum - 2 * C11) / 2
+    # C440: shear modulus without relaxing the internal coordinates (atomistica/tests.py:148-187)
+    e44 = np.zeros((3, 3)); e44[0, 1] = d / 2; e44[1, 0] = d / 2
+    bulk_props.C440 = (e_strain(e44) - 2 * e0 + e_strain(-e44)) / d ** 2 / V * GPa
     return -res.fun, a0, C11 * GPa, C12 * GPa
 
 
@@ -225,6 +228,8 @@ def test_bulk_properties(name, mk, builder):
         assert rel(C12, ref['C12']) < 2 * tol or abs(C12 - ref['C12']) < 8.0
     if 'B' in ref:
         assert rel((C11 + 2 * C12) / 3, ref['B']) < tol
+    if 'C440' in ref:
+        assert rel(bulk_props.C440, ref['C440']) < tol, (bulk_props.C440, ref['C440'])
 
 
 def test_eam_au_bulk(au_setfl):
@@ -232,6 +237,8 @@ def test_eam_au_bulk(au_setfl):
     Ec, a0, C11, C12 = bulk_props(eam_calc(au_setfl), lambda a0: S.fcc('Au', a0, (3, 3, 3)), ref['a0'])
     assert rel(Ec, ref['Ec']) < 0.05 and rel(a0, ref['a0']) < 0.05
     assert rel(C11, ref['C11']) < 0.05 and rel(C12, ref['C12']) < 0.05
+    # fcc is a Bravais lattice: C44 needs no internal relaxation
+    assert rel(bulk_props.C440, ref['C440']) < 0.05 and rel(bulk_props.C440, ref['C44']) < 0.05
 
 
 # ---- REBO2 atomisation energies (tests/test_rebo2_molecules.py) ---------------------------------
@@ -411,6 +418,8 @@ def test_bulk_properties_screened(name, mk, builder):
         assert rel(C12, ref['C12']) < 2 * tol or abs(C12 - ref['C12']) < 8.0
     if 'B' in ref:
         assert rel((C11 + 2 * C12) / 3, ref['B']) < tol
+    if 'C440' in ref:
+        assert rel(bulk_props.C440, ref['C440']) < tol, (bulk_props.C440, ref['C440'])
 
 
 def test_fd_screened(aC_small):
@@ -485,6 +494,10 @@ def test_bulk_properties_juslin(name, builder):
         assert rel(C12, ref['C12']) < 2 * tol
     if 'B' in ref:
         assert rel((C11 + 2 * C12) / 3, ref['B']) < tol
+    if 'C440' in ref:
+        assert rel(bulk_props.C440, ref['C440']) < tol, (bulk_props.C440, ref['C440'])
+    if name == 'Juslin_bcc_W':      # Bravais lattice: C44 without internal relaxation
+        assert rel(bulk_props.C440, ref['C44']) < tol, (bulk_props.C440, ref['C44'])
 
 
 def test_fd_juslin():
@@ -607,11 +620,12 @@ def test_funcfl_au_bulk_and_fd(au_funcfl):
     assert rel(Ec, ref['Ec']) < 0.05 and rel(a0, ref['a0']) < 0.05
     assert rel(C11, ref['C11']) < 0.05 and rel(C12, ref['C12']) < 0.05
     assert rel((C11 + 2 * C12) / 3, ref['B']) < 0.05
+    assert rel(bulk_props.C440, ref['C44']) < 0.05
     a = S.fcc('Au', 4.08, (3, 3, 3)); a.rattle(0.1, seed=8)
     check_fd(calc, a)
 
 
-# ---- relaxed (100) surface energies (tests/test_surface_properties.py:228-262) --------------------
+# ---- relaxed surface energies (tests/test_surface_properties.py:213-262) ---------------------------
 
 _SURFACES = {   # tests/test_surface_properties.py:55-207: directions, replication, shift of the cell origin
     '111': ([[1, -1, 0], [1, 1, -2], [1, 1, 1]], (1, 1), (1 / 12., 1 / 4., 1 / 12.)),

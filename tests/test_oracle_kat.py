@@ -625,6 +625,59 @@ def test_funcfl_au_bulk_and_fd(au_funcfl):
     check_fd(calc, a)
 
 
+# ---- C44 with relaxed internal coordinates (tests/test_bulk_properties.py, atomistica/tests.py:148-187)
+
+def c44_relaxed(calc, a, d=2e-3):
+    V = a.get_volume()
+
+    def e_relaxed(eps):
+        F = np.eye(3)
+        F[0, 1] += eps / 2
+        F[1, 0] += eps / 2
+        b = a.copy()
+        b.set_cell(b.cell @ F.T, scale_atoms=False)
+        b.positions = a.positions @ F.T
+        if eps == 0.0:
+            return calc(b)['epot']
+
+        def fun(x):
+            c = b.copy()
+            c.positions = x.reshape(-1, 3)
+            o = calc(c)
+            return o['epot'], -o['f'].ravel()
+        return minimize(fun, b.positions.ravel(), jac=True, method='L-BFGS-B',
+                        options=dict(gtol=1e-7, ftol=1e-15, maxiter=500)).fun
+    e0 = e_relaxed(0.0)
+    return (e_relaxed(d) - 2 * e0 + e_relaxed(-d)) / d ** 2 / V * GPa
+
+
+C44_ROWS = [
+    ('Tersoff_dia_C', lambda: bop_calc('Tersoff', None), 'C'),
+    ('Tersoff_dia_Si', lambda: bop_calc('Tersoff', None), 'Si'),
+    ('Brenner_Erhart_dia_C', lambda: bop_calc('Brenner', None), 'C'),
+    ('Brenner_II_dia_C', lambda: bop_calc('Brenner', P.Brenner_PRB_42_9458_C_II), 'C'),
+    ('Juslin_dia_C', lambda: juslin_calc(), 'C'),
+    ('Rebo2_dia_C', lambda: rebo2_calc(), 'C'),
+    # the screened classes are held to the same values (tests/test_bulk_properties.py:86-93, 130-133, 152-162)
+    ('Tersoff_dia_C', lambda: bop_scr_calc('Tersoff', None), 'C'),
+    ('Tersoff_dia_Si', lambda: bop_scr_calc('Tersoff', None), 'Si'),
+    ('Brenner_Erhart_dia_C', lambda: bop_scr_calc('Brenner', None), 'C'),
+    ('Rebo2_dia_C', lambda: rebo2_scr_calc(), 'C'),
+]
+
+
+@pytest.mark.parametrize('n', range(len(C44_ROWS)), ids=['%s%s' % (r[0], '_Scr' if k >= 6 else '')
+                                                        for k, r in enumerate(C44_ROWS)])
+def test_bulk_c44_relaxed(n):
+    name, mk, sym = C44_ROWS[n]
+    ref = KAT['bulk'][name]
+    calc = mk()
+    a0 = minimize_scalar(lambda x: calc(S.diamond(sym, x, (2, 2, 2)))['epot'],
+                         bracket=(ref['a0'] * 0.98, ref['a0'] * 1.02), tol=1e-10).x
+    c44 = c44_relaxed(calc, S.diamond(sym, a0, (2, 2, 2)))
+    assert rel(c44, ref['C44']) < KAT['bulk_tol_rel'], (c44, ref['C44'])
+
+
 # ---- relaxed surface energies (tests/test_surface_properties.py:213-262) ---------------------------
 
 _SURFACES = {   # tests/test_surface_properties.py:55-207: directions, replication, shift of the cell origin

@@ -14,6 +14,8 @@
 //                  recomputed from the bond table when their forces are applied.
 // Forces on i, j, k, l, m, n are accumulated with native FP64 atomicAdd (RED.ADD.F64); periodic
 // image identity along neighbour paths is tracked with 3-vector shift sums.
+#include <cstdlib>
+
 #include "atx_potential_common.cuh"
 
 #include "atx_rebo2_func.cuh"
@@ -37,6 +39,11 @@ struct atx_rebo2 {
   DevBuf<double> epb, fpb, wpb, epa_out;
   DevBuf<int> flag;
   PotScratch sc;
+  // one-thread-per-bond force kernel (ATX_REBO2_PERBOND=1, experimental): compact list of the bonds
+  // each atom is responsible for
+  bool per_bond = false;
+  DevBuf<int> own_cnt, own_off;
+  DevBuf<int2> own;
   // screened variant (Rebo2Scr): b_cut holds the attractive/repulsive cutoff, b_cbo / b_cnc the
   // bond-order and neighbour-count cutoffs, s_* the screening neighbours (stride nss per atom)
   bool screened = false;
@@ -85,6 +92,63 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
 
   rb_force_atom(nat, nbs, P, seed, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, pos4, order, f, epa,
                 wpa, epb, fpb, wpb, i, acc);
+  atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * gridDim.x + blockIdx.x] = acc[k];
+  }
+}
+
+// ---- one thread per bond (experimental, ATX_REBO2_PERBOND=1) ----------------------------------------
+// k_rebo2_force gives every thread the bonds its atom is responsible for: 0 .. 4 in amorphous carbon,
+// 1.9 on average, so a warp waits for its busiest lane (lane utilisation ~ 47 %).  Here the
+// responsible (atom, slot) pairs are compacted first (count, exclusive scan, fill) and every thread
+// evaluates exactly one bond with the same per-atom source (rb_force_atom<ROLES, ONE>).
+
+__global__ void k_rebo2_own_count(int nat, int nbs, Rebo2Dev P, const int *__restrict__ b_cnt,
+                                  const int *__restrict__ b_nb, const int *__restrict__ b_typ,
+                                  const int *__restrict__ b_shift, const double4 *__restrict__ b_vec,
+                                  const double4 *__restrict__ pos4, const int *__restrict__ order,
+                                  int *__restrict__ cnt, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > nat) return;
+  cnt[s] = s < nat ? rb_owned_bonds(nbs, P, b_cnt, b_nb, b_typ, b_shift, b_vec, pos4, order, s, nullptr) : 0;
+}
+
+__global__ void k_rebo2_own_fill(int nat, int nbs, Rebo2Dev P, const int *__restrict__ b_cnt,
+                                 const int *__restrict__ b_nb, const int *__restrict__ b_typ,
+                                 const int *__restrict__ b_shift, const double4 *__restrict__ b_vec,
+                                 const double4 *__restrict__ pos4, const int *__restrict__ order,
+                                 const int *__restrict__ off, int2 *__restrict__ own,
+                                 const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  rb_owned_bonds(nbs, P, b_cnt, b_nb, b_typ, b_shift, b_vec, pos4, order, s, own + off[s]);
+}
+
+__global__ void __launch_bounds__(RB_BLOCK)
+k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
+                   const int *__restrict__ b_cnt, const int *__restrict__ b_nb, const int *__restrict__ b_typ,
+                   const int *__restrict__ b_shift, const int *__restrict__ b_slot,
+                   const double4 *__restrict__ b_vec, const double2 *__restrict__ b_cut,
+                   const double2 *__restrict__ nn, const double4 *__restrict__ pos4,
+                   const int *__restrict__ order, double *__restrict__ f, double *__restrict__ epa,
+                   double *__restrict__ wpa, double *__restrict__ epb, double *__restrict__ fpb,
+                   double *__restrict__ wpb, double *__restrict__ partials, const int *__restrict__ off,
+                   const int2 *__restrict__ own, const int *__restrict__ stop) {
+  if (stop && *stop) return;
+  __shared__ double red[ATX_NSUM * (RB_BLOCK / 32)];
+  const int t = blockIdx.x * RB_BLOCK + threadIdx.x;
+  double acc[ATX_NSUM];
+#pragma unroll
+  for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
+  if (t < off[nat]) {
+    const int2 e = own[t];
+    rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, pos4, order,
+                               f, epa, wpa, epb, fpb, wpb, e.x, acc, nullptr, e.y);
+  }
   atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -206,6 +270,7 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
   D.Pcc = t + 4 * n3; D.Pch = t + 4 * n3 + n2;
   for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
   ATX_PASS(pot->flag.reserve(4));
+  if (const char *v = getenv("ATX_REBO2_PERBOND")) pot->per_bond = atoi(v) != 0;
   // guarded (batched MD) steps never clear the flag: it has to start from zero
   ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 4 * sizeof(int)));
   *out = pot;
@@ -383,6 +448,33 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
     ATX_LAUNCHED();
     k_rebo2_clear_ghosts<<<(nat + 127) / 128, 128, 0, st>>>(nat, o.role, o.f, o.epa, o.wpa, o.stop);
     ATX_LAUNCHED();
+  } else if (pot->per_bond && nat > 0) {
+    ProfScope ps_(ctx, "rebo2_force");
+    // every undirected bond has two directed table entries and one responsible end
+    const size_t bound = (size_t)nat * nbs / 2 + 1;
+    const int nbb = (int)((bound + RB_BLOCK - 1) / RB_BLOCK);
+    ATX_PASS(pot->own_cnt.reserve(nat + 2));
+    ATX_PASS(pot->own_off.reserve(nat + 2));
+    ATX_PASS(pot->own.reserve(bound + 1));
+    ATX_PASS(pot->sc.partials.reserve((size_t)nbb * ATX_NSUM));
+    k_rebo2_own_count<<<(nat + 1 + 127) / 128, 128, 0, st>>>(nat, nbs, pot->dev, pot->b_cnt.ptr, pot->b_nb.ptr,
+                                                             pot->b_typ.ptr, pot->b_shift.ptr, pot->b_vec.ptr,
+                                                             nl->pos4.ptr, nl->order.ptr, pot->own_cnt.ptr, o.stop);
+    ATX_LAUNCHED();
+    ATX_PASS(atx_scan_int(ctx, pot->own_cnt.ptr, pot->own_off.ptr, (size_t)nat + 1));
+    k_rebo2_own_fill<<<(nat + 127) / 128, 128, 0, st>>>(nat, nbs, pot->dev, pot->b_cnt.ptr, pot->b_nb.ptr,
+                                                        pot->b_typ.ptr, pot->b_shift.ptr, pot->b_vec.ptr,
+                                                        nl->pos4.ptr, nl->order.ptr, pot->own_off.ptr, pot->own.ptr,
+                                                        o.stop);
+    ATX_LAUNCHED();
+    k_rebo2_force_bond<<<nbb, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_nb.ptr,
+                                                 pot->b_typ.ptr, pot->b_shift.ptr, pot->b_slot.ptr, pot->b_vec.ptr,
+                                                 pot->b_cut.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,
+                                                 o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr,
+                                                 pot->own.ptr, o.stop);
+    ATX_LAUNCHED();
+    ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbb, o.sums, o.stop));
+    return 0;
   } else {
     ProfScope ps_(ctx, "rebo2_force");
     k_rebo2_force<<<nblocks, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr,

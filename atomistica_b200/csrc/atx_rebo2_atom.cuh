@@ -90,7 +90,9 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
 // local atoms is evaluated and scattered as usual, but the energy and the virial of a bond are
 // counted half for each OWNED end only, so that the sums over the ranks (or over the owned atoms of
 // an unfolded periodic system) are the reference's totals; the caller discards the ghost rows.
-template <bool ROLES = false>
+// ONE: evaluate only the bond in slot ij0 of atom i (one thread per bond, k_rebo2_force_bond) instead
+// of all bonds the atom is responsible for.
+template <bool ROLES = false, bool ONE = false>
 __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &P,
                                               const long long *__restrict__ seed,
                                               const int *__restrict__ b_cnt, const int *__restrict__ b_nb,
@@ -104,7 +106,8 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
                                               double *__restrict__ epa, double *__restrict__ wpa,
                                               double *__restrict__ epb, double *__restrict__ fpb,
                                               double *__restrict__ wpb, int i, double *acc,
-                                              const unsigned char *__restrict__ role = nullptr) {
+                                              const unsigned char *__restrict__ role = nullptr,
+                                              int ij0 = 0) {
   const int ktypi = i < nat ? P.el2typ[(int)pos4[i].w] : 0;
   const int nbi = (i < nat && ktypi > 0) ? b_cnt[i] : 0;
   if (nbi > 0) {
@@ -129,7 +132,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
     }
     const double2 nni = nn[i];
 
-    for (int ij = 0; ij < nbi; ij++) {
+    for (int ij = ONE ? ij0 : 0; ij < (ONE ? ij0 + 1 : nbi); ij++) {
       const int j = b_nb[qi + ij];
       int jsx, jsy, jsz;
       atx_unpack_shift(b_shift[qi + ij], jsx, jsy, jsz);
@@ -496,4 +499,31 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
     }
     rb_add3(f, i, fix, fiy, fiz);
   }
+}
+
+// The bonds atom i is responsible for: exactly the slots that the ij loop of rb_force_atom does not
+// skip (j_gt_i in original numbering, bop_kernel_rebo2.f90:1332, and rlij < cut_h).  Returns their
+// number and writes (i, slot) pairs to `out` when it is given.
+__device__ __forceinline__ int rb_owned_bonds(int nbs, const Rebo2Dev &P, const int *__restrict__ b_cnt,
+                                              const int *__restrict__ b_nb, const int *__restrict__ b_typ,
+                                              const int *__restrict__ b_shift,
+                                              const double4 *__restrict__ b_vec,
+                                              const double4 *__restrict__ pos4,
+                                              const int *__restrict__ order, int i, int2 *out) {
+  const int ktypi = P.el2typ[(int)pos4[i].w];
+  const int nbi = ktypi > 0 ? b_cnt[i] : 0;
+  const size_t qi = (size_t)i * nbs;
+  int n = 0;
+  for (int ij = 0; ij < nbi; ij++) {
+    const int j = b_nb[qi + ij];
+    int jsx, jsy, jsz;
+    atx_unpack_shift(b_shift[qi + ij], jsx, jsy, jsz);
+    const bool zero = (jsx == 0 && jsy == 0 && jsz == 0);
+    const bool pos = jsx != 0 ? jsx > 0 : (jsy != 0 ? jsy > 0 : jsz > 0);
+    if (!((zero && order[j] > order[i]) || pos)) continue;
+    if (!(b_vec[qi + ij].w < P.cut_h[b_typ[qi + ij]])) continue;
+    if (out) out[n] = make_int2(i, ij);
+    n++;
+  }
+  return n;
 }

@@ -38,6 +38,12 @@ except Exception as e:
 PY
 done
 
+echo "== 2b. REBO2 C3: thread per atom vs thread per bond" | tee -a $OUT/summary.txt
+for v in 0 1; do
+  ATX_REBO2_PERBOND=$v timeout 600 python benchmarks/run_configs.py C3 --out $OUT/c3_perbond$v.json > $OUT/c3_perbond$v.log 2>&1
+  grep -o '"device_ms": {[^}]*}' $OUT/c3_perbond$v.json | head -1 | sed "s/^/  per_bond=$v /" | tee -a $OUT/summary.txt
+done
+
 echo "== 3. ncu: REBO2 (C3, small replica), Rebo2Scr, screened BOP" | tee -a $OUT/summary.txt
 cat > /tmp/r02_prof.py <<'PY'
 import os, sys

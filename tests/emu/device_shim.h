@@ -13,6 +13,7 @@
 struct double2 { double x, y; };
 struct double4 { double x, y, z, w; };
 struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 using std::sqrt; using std::exp; using std::pow;

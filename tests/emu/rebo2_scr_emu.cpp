@@ -68,7 +68,8 @@ extern "C" int emu_rebo2_scr(const atx_rebo2_params *par, const atx_rebo2_screen
 extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat, int nbs, const double *Abox,
                          const double *pos4_, const long long *seed, const int *list_, const int *order,
                          double *sums, double *f, double *epa, double *wpa, double *epb, double *fpb,
-                         double *wpb, const unsigned char *role /* nullptr, or 2 owned / 1 ghost */) {
+                         double *wpb, const unsigned char *role /* nullptr, or 2 owned / 1 ghost */,
+                         int per_bond /* k_rebo2_own_count / scan / k_rebo2_own_fill / k_rebo2_force_bond */) {
   Rebo2Dev P;
   std::memset(&P, 0, sizeof(P));
   rb_fill_dev(P, par);
@@ -103,6 +104,21 @@ extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat
       if (wpa)
         for (int q = 0; q < 9; q++) wpa[9 * s + q] = 0.0;
     }
+  } else if (per_bond) {
+    std::vector<int> cnt(nat + 1, 0), off(nat + 2, 0);
+    for (int s = 0; s < nat; s++)
+      cnt[s] = rb_owned_bonds(nbs, P, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_vec.data(), pos4,
+                              order, s, nullptr);
+    for (int s = 0; s <= nat; s++) off[s + 1] = off[s] + cnt[s];     // exclusive scan over nat + 1 inputs
+    std::vector<int2> own(off[nat] + 1);
+    if ((size_t)off[nat] > (size_t)nat * nbs / 2 + 1) return -7;      // the bound the host code sizes with
+    for (int s = 0; s < nat; s++)
+      rb_owned_bonds(nbs, P, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_vec.data(), pos4, order, s,
+                     own.data() + off[s]);
+    for (int t = 0; t < off[nat]; t++)
+      rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(),
+                                 b_slot.data(), b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, epb,
+                                 fpb, wpb, own[t].x, acc, nullptr, own[t].y);
   } else {
     for (int i = 0; i < nat; i++)
       rb_force_atom(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_slot.data(),

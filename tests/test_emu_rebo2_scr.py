@@ -91,7 +91,7 @@ def run_emu(emu, a, nss=32, order=None, screened=True, **kwargs):
     return out, ref
 
 
-def run_emu_plain(emu, a, order=None, **kwargs):
+def run_emu_plain(emu, a, order=None, per_bond=False, **kwargs):
     """unscreened Rebo2: rb_bonds_atom / rb_force_atom (bodies of k_rebo2_bonds / k_rebo2_force)"""
     okw = dict(kwargs)
     if 'dihedral' in okw:
@@ -116,7 +116,8 @@ def run_emu_plain(emu, a, order=None, **kwargs):
     epb = np.zeros(npairs + 1); fpb = np.zeros((npairs + 1, 3)); wpb = np.zeros((npairs + 1, 9))
     flag = emu.emu_rebo2(C.byref(par), L.iptr(el2typ), C.c_int(nat), C.c_int(nbs), L.dptr(abox), L.dptr(pos4),
                          seed.ctypes.data_as(C.POINTER(C.c_longlong)), L.iptr(ent), L.iptr(order), L.dptr(sums),
-                         L.dptr(f), L.dptr(epa), L.dptr(wpa), L.dptr(epb), L.dptr(fpb), L.dptr(wpb), None)
+                         L.dptr(f), L.dptr(epa), L.dptr(wpa), L.dptr(epb), L.dptr(fpb), L.dptr(wpb), None,
+                         C.c_int(1 if per_bond else 0))
     out = dict(flag=flag, epot=sums[0], f=f, wpot=sums[1:].reshape(3, 3).T.copy(), epot_per_at=epa,
                wpot_per_at=wpa.reshape(nat, 3, 3).transpose(0, 2, 1).copy())
     for key, arr in (('epot_per_bond', epb), ('f_per_bond', fpb), ('wpot_per_bond', wpb)):
@@ -306,7 +307,7 @@ def test_plain_rebo2_caller_supplied_list_with_ghosts(emu):
     flag = emu.emu_rebo2(C.byref(par), L.iptr(el2typ), C.c_int(nall), C.c_int(12), L.dptr(abox), L.dptr(pos4),
                          seed.ctypes.data_as(C.POINTER(C.c_longlong)), L.iptr(ent), L.iptr(order), L.dptr(sums),
                          L.dptr(f), L.dptr(epa), L.dptr(wpa), None, None, None,
-                         role.ctypes.data_as(C.POINTER(C.c_ubyte)))
+                         role.ctypes.data_as(C.POINTER(C.c_ubyte)), C.c_int(0))
     assert flag == 0
     close(sums[0], ref['epot'], 'epot')
     close(sums[1:].reshape(3, 3).T, ref['wpot'], 'wpot')
@@ -326,3 +327,24 @@ def test_reference_fd_configurations(emu):
             for state in range(2):
                 out, ref = check(emu, a, screened=screened)
                 a.rattle(0.5, seed=row + 1)
+
+
+def test_plain_rebo2_one_thread_per_bond(emu, aC_small):
+    """k_rebo2_force_bond (ATX_REBO2_PERBOND=1): compacted list of responsible (atom, slot) pairs, one
+    bond per thread, same per-atom source"""
+    check(emu, aC_small, screened=False, per_bond=True)
+    check(emu, aC_small, screened=False, per_bond=True, dihedral=True)
+    a = S.diamond('C', 3.566, (1, 1, 1)); a.rattle(0.05, seed=2)       # self images
+    check(emu, a, screened=False, per_bond=True)
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.7, (2, 2, 2))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=6)
+    check(emu, a, screened=False, per_bond=True)
+    perm = np.random.RandomState(3).permutation(len(aC_small))          # sorted order != original order
+    b = S.Atoms([aC_small.symbols[i] for i in perm], aC_small.positions[perm], aC_small.cell, True)
+    out, _ = run_emu(emu, b, screened=False, per_bond=True, order=perm)
+    _, ref = run_emu(emu, aC_small, screened=False)
+    close(out['epot'], ref['epot'], 'epot')
+    close(out['f'], ref['f'][perm], 'f')

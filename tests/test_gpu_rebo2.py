@@ -135,3 +135,18 @@ def test_full_size_replication_invariance(aC):
     fscale = max(np.abs(o['f']).max(), 1.0)
     assert np.abs(f.reshape(125, -1, 3) - o['f'][None]).max() <= RTOL * fscale
     assert np.abs(f.sum(axis=0)).max() <= 1e-9 * fscale * np.sqrt(len(big))
+
+
+@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
+                    reason='one-thread-per-bond kernels (ATX_REBO2_PERBOND=1) not yet run on hardware; their '
+                           'per-atom source is checked on the CPU by tests/test_emu_rebo2_scr.py')
+def test_one_thread_per_bond_variant(aC_small, monkeypatch):
+    monkeypatch.setenv('ATX_REBO2_PERBOND', '1')
+    g, o = _both(aC_small, per_bond=True)
+    _check(g, o, per_bond=True)
+    g, o = _both(aC_small, dihedral=True)
+    _check(g, o)
+    a = S.diamond('C', 3.566, (1, 1, 1))
+    a.rattle(0.05, seed=2)
+    g, o = _both(a)
+    _check(g, o)

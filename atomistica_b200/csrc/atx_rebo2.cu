@@ -41,7 +41,7 @@ struct atx_rebo2 {
   PotScratch sc;
   // one-thread-per-bond force kernel (ATX_REBO2_PERBOND=1, experimental): compact list of the bonds
   // each atom is responsible for
-  bool per_bond = false;
+  int per_bond = 0;   // 0 off, 1 / 2 / 3: 4 / 6 / 8 resident blocks per SM
   DevBuf<int> own_cnt, own_off;
   DevBuf<int2> own;
   // screened variant (Rebo2Scr): b_cut holds the attractive/repulsive cutoff, b_cbo / b_cnc the
@@ -128,7 +128,10 @@ __global__ void k_rebo2_own_fill(int nat, int nbs, Rebo2Dev P, const int *__rest
   rb_owned_bonds(nbs, P, b_cnt, b_nb, b_typ, b_shift, b_vec, pos4, order, s, own + off[s]);
 }
 
-__global__ void __launch_bounds__(RB_BLOCK)
+// MINB: resident blocks per SM asked from the register allocator (4: 255 registers, 6: 170, 8: 128 with
+// spills) -- occupancy against spills is to be measured (ATX_REBO2_PERBOND = 1 / 2 / 3)
+template <int MINB>
+__global__ void __launch_bounds__(RB_BLOCK, MINB)
 k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
                    const int *__restrict__ b_cnt, const int *__restrict__ b_nb, const int *__restrict__ b_typ,
                    const int *__restrict__ b_shift, const int *__restrict__ b_slot,
@@ -270,7 +273,7 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
   D.Pcc = t + 4 * n3; D.Pch = t + 4 * n3 + n2;
   for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
   ATX_PASS(pot->flag.reserve(4));
-  if (const char *v = getenv("ATX_REBO2_PERBOND")) pot->per_bond = atoi(v) != 0;
+  if (const char *v = getenv("ATX_REBO2_PERBOND")) pot->per_bond = atoi(v);
   // guarded (batched MD) steps never clear the flag: it has to start from zero
   ATX_CUDA(cudaMemset(pot->flag.ptr, 0, 4 * sizeof(int)));
   *out = pot;
@@ -467,11 +470,15 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
                                                         nl->pos4.ptr, nl->order.ptr, pot->own_off.ptr, pot->own.ptr,
                                                         o.stop);
     ATX_LAUNCHED();
-    k_rebo2_force_bond<<<nbb, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_nb.ptr,
-                                                 pot->b_typ.ptr, pot->b_shift.ptr, pot->b_slot.ptr, pot->b_vec.ptr,
-                                                 pot->b_cut.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,
-                                                 o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr,
-                                                 pot->own.ptr, o.stop);
+#define RB_FORCE_BOND(MINB)                                                                                   \
+  k_rebo2_force_bond<MINB><<<nbb, RB_BLOCK, 0, st>>>(                                                         \
+      nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,      \
+      pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,  \
+      o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr, pot->own.ptr, o.stop)
+    if (pot->per_bond == 2) RB_FORCE_BOND(6);
+    else if (pot->per_bond == 3) RB_FORCE_BOND(8);
+    else RB_FORCE_BOND(4);
+#undef RB_FORCE_BOND
     ATX_LAUNCHED();
     ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbb, o.sums, o.stop));
     return 0;

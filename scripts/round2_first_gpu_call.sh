@@ -38,8 +38,8 @@ except Exception as e:
 PY
 done
 
-echo "== 2b. REBO2 C3: thread per atom vs thread per bond" | tee -a $OUT/summary.txt
-for v in 0 1; do
+echo "== 2b. REBO2 C3: thread per atom (0) vs thread per bond at 4 / 6 / 8 blocks per SM (1 / 2 / 3)" | tee -a $OUT/summary.txt
+for v in 0 1 2 3; do
   ATX_REBO2_PERBOND=$v timeout 600 python benchmarks/run_configs.py C3 --out $OUT/c3_perbond$v.json > $OUT/c3_perbond$v.log 2>&1
   grep -o '"device_ms": {[^}]*}' $OUT/c3_perbond$v.json | head -1 | sed "s/^/  per_bond=$v /" | tee -a $OUT/summary.txt
 done

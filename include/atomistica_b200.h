@@ -93,7 +93,10 @@ int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int *nebmax, in
  * atx_{eam,bop,pair}_energy_and_forces return epot / wpot summed over the OWNED atoms' bonds and
  * forces on owned atoms only (ghost rows of f receive zero: the gather formulation needs no
  * reverse communication; the ghost shell must be 2 x cutoff wide, which is what
- * particles_get_border already asks LAMMPS for).  Call again after every reneighbouring. */
+ * particles_get_border already asks LAMMPS for).  atx_rebo2_energy_and_forces works on such a list
+ * too (every bond among the local atoms is evaluated, energy / virial counted for owned ends, ghost
+ * rows cleared) and needs the ghosts within 5 bond cutoffs; per-bond outputs and the screened variant
+ * are refused there.  Call again after every reneighbouring. */
 int atx_neighbors_set_external(atx_neighbors *nl, atx_particles *p, int natloc, int inum,
                                const int *ilist, const int *numneigh, const int *const *firstneigh);
 /* number of list builds and of updates answered without a rebuild (Verlet shell, neighbors.f90:552-590) */

@@ -18,11 +18,16 @@ class Atomistica:
     potential_class = None
     avgn = 100
 
-    def __init__(self, potentials=None, avgn=None, device=0, verlet_shell=0.0, **kwargs):
+    def __init__(self, potentials=None, avgn=None, device=0, verlet_shell=0.0, zero_copy=False, **kwargs):
         """verlet_shell > 0 (Angstrom) keeps the neighbour list between calls until an atom has moved
         verlet_shell/2 from where it was at the last build (checked on the device); 0 rebuilds on every
-        change of the positions like the reference's Python host."""
+        change of the positions like the reference's Python host.
+
+        zero_copy=True makes get_forces() / results['forces'] a VIEW of one of two alternating
+        page-locked buffers (valid until the call after the next one) instead of a private copy; the
+        default returns copies, like ase.calculators.calculator.Calculator.get_property."""
         self.device = device
+        self.zero_copy = bool(zero_copy)
         self.verlet_shell = float(verlet_shell)
         self.pots = potentials if potentials is not None else [self.potential_class(device=device, **kwargs)]
         if avgn is not None:
@@ -122,12 +127,17 @@ class Atomistica:
             kwargs['mask'] = self.mask
         epa = wpa = None
         for pot in self.pots:
-            _e, _f, _w, epa, self.epot_per_bond, self.f_per_bond, wpa, self.wpot_per_bond = \
+            _e, _f, _w, _epa, self.epot_per_bond, self.f_per_bond, _wpa, self.wpot_per_bond = \
                 pot.energy_and_forces(self.particles, self.nl, forces=forces, **kwargs)
             epot += _e
             wpot += _w
+            if _epa is not None:
+                epa = _epa if epa is None else epa + _epa
+            if _wpa is not None:
+                wpa = _wpa if wpa is None else wpa + _wpa
         volume = atoms.get_volume()
-        self.results = dict(energy=epot, free_energy=epot, forces=forces, wpot=wpot)
+        self.results = dict(energy=epot, free_energy=epot, forces=forces if self.zero_copy else forces.copy(),
+                            wpot=wpot)
         self.results['stress'] = np.array([wpot[0, 0], wpot[1, 1], wpot[2, 2], (wpot[1, 2] + wpot[2, 1]) / 2,
                                            (wpot[0, 2] + wpot[2, 0]) / 2, (wpot[0, 1] + wpot[1, 0]) / 2]) / volume
         if per_at_e:
@@ -136,7 +146,8 @@ class Atomistica:
             self.results['stresses'] = np.transpose([wpa[:, 0, 0], wpa[:, 1, 1], wpa[:, 2, 2],
                                                      (wpa[:, 1, 2] + wpa[:, 2, 1]) / 2,
                                                      (wpa[:, 0, 2] + wpa[:, 2, 0]) / 2,
-                                                     (wpa[:, 0, 1] + wpa[:, 1, 0]) / 2]) / volume
+                                                     (wpa[:, 0, 1] + wpa[:, 1, 0]) / 2])
+            # aseinterface.py:438-446: Voigt-ordered wpot_per_at, NOT divided by the volume
         return self.results
 
     def get_potential_energy(self, atoms):

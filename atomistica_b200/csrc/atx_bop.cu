@@ -1547,7 +1547,14 @@ extern "C" int atx_bop_energy_and_forces(atx_bop *pot, atx_particles *p, atx_nei
   ATX_PASS(atx_prepare_mask(ctx, nl, pot->sc, mask, &mask_sorted));
   size_t nslots = (size_t)nl->npairs + 1;
   double *epb = nullptr, *fpb = nullptr, *wpb = nullptr;
-  if (nl->external) o.role = nl->role_ext.ptr;
+  if (nl->external) {
+    if (epot_per_bond || f_per_bond || wpot_per_bond) {
+      // the host-layout slot map needs nl->count, which a caller-supplied list never fills
+      atx_set_error("Per-bond outputs are not available with an external neighbour list.");
+      return ATX_ERROR_UNSPECIFIED;
+    }
+    o.role = nl->role_ext.ptr;
+  }
   // The screened tables are sized when the list is built; with a library-mode Verlet shell the
   // list can be reused while atoms gain bonds or screening neighbours.  If a table overflows, size
   // again from the current configuration and repeat once.

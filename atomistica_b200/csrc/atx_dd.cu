@@ -30,6 +30,7 @@ int atx_bop_compute_device(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
                            const int *mask_sorted, const PotOut &o);
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o);
 int atx_bop_check_overflow(atx_bop *pot);
+int atx_rebo2_check_overflow(atx_rebo2 *pot);
 
 // ---------------------------------------------------------------------------
 // NCCL through dlopen
@@ -724,6 +725,7 @@ static int dd_build_list(atx_ddmd *md) {
   std::swap(md->ploc.el.ptr, md->el.ptr);  // ploc.el aliases md->el while the list is built
   std::swap(md->ploc.el.cap, md->el.cap);
   md->ploc.pos_rev++;
+  md->nl->p_rev = -1;  // force a real rebuild (see md_rebuild in atx_md.cu)
   int err = atx_neighbors_update(md->nl, &md->ploc);
   std::swap(md->ploc.el.ptr, md->el.ptr);
   std::swap(md->ploc.el.cap, md->el.cap);
@@ -962,6 +964,7 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
     ATX_CUDA(cudaStreamSynchronize(st));
     ATX_CUDA(cudaGetLastError());
     if (md->pot_kind == ATX_POT_BOP) ATX_PASS(atx_bop_check_overflow((atx_bop *)md->pot));
+    if (md->pot_kind == ATX_POT_REBO2) ATX_PASS(atx_rebo2_check_overflow((atx_rebo2 *)md->pot));
     DdCtrl hc = *md->hctrl.ptr;
     int done = hc.steps_done - done_total;
     done_total = hc.steps_done;

@@ -668,6 +668,12 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
     ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nb, o.sums, o.stop));
     return 0;
   }
+  if (o.role) {
+    // the generic kernels know nothing of owned / ghost roles: refuse instead of counting ghosts as owned
+    atx_set_error("TabulatedAlloyEAM: ghost roles (external list / domain decomposition) need the packed-table "
+                  "kernels; the tables of this potential are on different grids or ATX_EAM_GENERIC is set.");
+    return ATX_ERROR_UNSPECIFIED;
+  }
 #define EAM_LAUNCH(L)                                                                             \
   do {                                                                                            \
     {                                                                                             \

@@ -220,6 +220,10 @@ static int md_rebuild(atx_md *md, bool first) {
     ATX_LAUNCHED();
   }
   md->pint.pos_rev++;
+  // the driver's rule (accumulated per-step maxima) has fired: a REAL rebuild, not the library-mode
+  // displacement check of atx_neighbors_update, which would keep the list (and its build positions)
+  // whenever the true displacement is still below shell/2
+  nl->p_rev = -1;
   ATX_PASS(atx_neighbors_update(nl, &md->pint));
   ATX_PASS(md->tmp3.reserve(3 * (size_t)nat + 3));
   ATX_PASS(md->tmp1.reserve(nat + 1));

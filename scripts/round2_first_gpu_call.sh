@@ -77,3 +77,13 @@ timeout 600 ncu --set full --clock-control none --import-source on -c 6 -k regex
   -o $OUT/r02_nl -f python bench.py --steps 70 --warmup 3 --no-cpu > $OUT/ncu_nl.log 2>&1
 echo "  ncu nl exit $?" | tee -a $OUT/summary.txt
 ls -la $OUT | tee -a $OUT/summary.txt
+# final k_bop_center instantiation (never captured): Tersoff and Kumagai Si, 2.1 M atoms
+for k in Tersoff Kumagai; do
+  timeout 600 ncu --set full --clock-control none --import-source on -c 4 -k regex:'k_bop_center|k_bop_gather' \
+    -o $OUT/r02_bop_$k -f python scripts/run_bop_md.py $k 64 4 > $OUT/ncu_bop_$k.log 2>&1
+  echo "  ncu bop $k exit $?" | tee -a $OUT/summary.txt
+done
+python scripts/run_bop_md.py Tersoff 64 50 | tee -a $OUT/summary.txt
+python scripts/run_bop_md.py Kumagai 64 50 | tee -a $OUT/summary.txt
+nvidia-smi -L | tee -a $OUT/summary.txt
+which gfortran | tee -a $OUT/summary.txt

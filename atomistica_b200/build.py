@@ -33,9 +33,18 @@ def _newest_dep():
     return max(os.path.getmtime(d) for d in deps)
 
 
+def _newest_header():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cuh') or f.endswith('.h')]
+    deps.append(os.path.join(HERE, '..', 'include', 'atomistica_b200.h'))
+    deps.append(os.path.abspath(__file__))
+    return max(os.path.getmtime(d) for d in deps)
+
+
 def _compile(src):
     obj = os.path.join(OBJ, os.path.splitext(src)[0] + '.o')
-    if os.path.exists(obj) and os.path.getmtime(obj) >= _newest_dep():
+    # a translation unit depends on itself and on every header, not on the other .cu files
+    if os.path.exists(obj) and os.path.getmtime(obj) >= max(_newest_header(),
+                                                            os.path.getmtime(os.path.join(CSRC, src))):
         return obj
     cmd = [NVCC] + NVCC_FLAGS + VISIBLE + ['-x', 'cu', '-c', os.path.join(CSRC, src), '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -18,6 +18,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "atx_potential_common.cuh"
@@ -45,6 +47,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -72,6 +75,7 @@ static int nccl_load() {
   LOAD(Send, "ncclSend")
   LOAD(Recv, "ncclRecv")
   LOAD(AllReduce, "ncclAllReduce")
+  LOAD(AllGather, "ncclAllGather")
   LOAD(GroupStart, "ncclGroupStart")
   LOAD(GroupEnd, "ncclGroupEnd")
   LOAD(GetErrorString, "ncclGetErrorString")
@@ -141,7 +145,23 @@ struct DdCtrl {
   double verlet_shell;
   double epot;       // local: sum of per-atom energies of owned atoms (last step)
   double ekin;
+  unsigned long long seq;     // executed guarded steps since create (stamps the peer-to-peer signals)
+  unsigned int counter_pack;
+  int err;                    // 1: a peer's signal did not arrive in time
 };
+
+// Peer-to-peer halo exchange (the step path when every rank could map its peers' mailboxes):
+// every rank owns one cudaMalloc'ed mailbox, exported with cudaIpcGetMemHandle and mapped by all
+// peers.  Layout: sig[2][DD_MAXP] signal words, then the ghost receive areas recvL[2][3*capG] and
+// recvR[2][3*capG] (positions arriving from the left / right slab; two parities, see below).
+// Per step the pack kernel STORES the ghost positions straight into the neighbours' receive areas
+// over NVLink, fences, and then stores (seq << 1 | rebuild wish) into the sig slot [seq & 1][me] of
+// EVERY rank: one message carries the halo-arrival flag and this rank's share of the global OR of
+// the rebuild rule (standalone/neighbors.f90:552-557), replacing ncclSend/ncclRecv + ncclAllReduce.
+// A rank can run at most one step ahead of a peer (it cannot pass wait(s) without the peer's
+// signal of step s), so two parities of every slot and receive area are enough.
+#define DD_MAXP 16
+#define DD_SIG_BYTES (2 * DD_MAXP * sizeof(unsigned long long))
 
 #define DD_ROW 9  // migration record: id, el, r(3), v(3), minv
 
@@ -176,6 +196,13 @@ struct atx_ddmd {
   double last_ms = 0.0;
   int batch = 16;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // peer-to-peer step path
+  bool p2p = false;
+  size_t capG = 0;                       // ghost capacity per side (atoms), identical on all ranks
+  char *mbox = nullptr;                  // own mailbox
+  char *peer_mbox[DD_MAXP] = {nullptr};  // mapped mailboxes ([rank] = own)
+  DevBuf<unsigned long long *> d_peer_sig;
+  double rebuild_host_ms[8] = {0};       // host wall time per rebuild phase (accumulated)
 };
 
 __global__ void k_dd_drift(int nown, double dt, double *__restrict__ r, double *__restrict__ v,
@@ -210,13 +237,103 @@ __global__ void k_dd_drift(int nown, double dt, double *__restrict__ r, double *
       ctrl->stepmax_bits = 0ull;
       ctrl->counter_drift = 0u;
       ctrl->want = (2.0 * acc >= ctrl->verlet_shell) ? 1 : 0;  // all-reduced into ctrl->stop
+      ctrl->seq += 1ull;
     }
   }
 }
 
 // ranks with no owned atoms still have to publish a wish
 __global__ void k_dd_nowish(DdCtrl *ctrl) {
-  if (!ctrl->stop) ctrl->want = 0;
+  if (!ctrl->stop) {
+    ctrl->want = 0;
+    ctrl->seq += 1ull;
+  }
+}
+
+// ---- peer-to-peer step path -------------------------------------------------------------------
+
+// Ghost positions of this step straight into the neighbours' receive areas (remote stores over
+// NVLink), then the step's signal word into every rank's mailbox.  dstL / dstR: parity-0 base of the
+// LEFT neighbour's recvR area / the RIGHT neighbour's recvL area as mapped into this process.
+__global__ void __launch_bounds__(256)
+k_dd_pack_p2p(int nL, int nR, const int *__restrict__ idxL, const int *__restrict__ idxR,
+              const double *__restrict__ r, double lx, double ly, double lz, double rx, double ry, double rz,
+              double *dstL, double *dstR, size_t par_stride, unsigned long long *const *peer_sig, int me,
+              int P, DdCtrl *ctrl) {
+  if (ctrl->stop) return;
+  __shared__ bool is_last;
+  const unsigned long long seq = ctrl->seq;
+  const size_t par = (size_t)(seq & 1ull) * par_stride;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nL) {
+    const int i = idxL[t];
+    double *o = dstL + par + 3 * (size_t)t;
+    o[0] = r[3 * i] + lx; o[1] = r[3 * i + 1] + ly; o[2] = r[3 * i + 2] + lz;
+  } else if (t < nL + nR) {
+    const int u = t - nL, i = idxR[u];
+    double *o = dstR + par + 3 * (size_t)u;
+    o[0] = r[3 * i] + rx; o[1] = r[3 * i + 1] + ry; o[2] = r[3 * i + 2] + rz;
+  }
+  __threadfence_system();   // this thread's remote stores before anything that follows
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int done = atomicAdd(&ctrl->counter_pack, 1u);
+    is_last = (done == gridDim.x - 1);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < P) {
+      const unsigned long long word = (seq << 1) | (ctrl->want ? 1ull : 0ull);
+      __threadfence_system();
+      *((volatile unsigned long long *)(peer_sig[threadIdx.x] + (seq & 1ull) * DD_MAXP + me)) = word;
+    }
+    if (threadIdx.x == 0) ctrl->counter_pack = 0u;
+  }
+}
+
+// One warp: lane p waits for rank p's signal of this step; the OR of the wishes becomes the stop flag
+// (identical on every rank).  A signal that does not arrive within ~4 s (a peer failed) raises
+// ctrl->err and stops the batch instead of hanging the device.
+__global__ void k_dd_wait(const unsigned long long *sig, int P, DdCtrl *ctrl) {
+  if (ctrl->stop) return;
+  const unsigned long long seq = ctrl->seq;
+  const int lane = threadIdx.x;
+  int want = 0, bad = 0;
+  if (lane < P) {
+    const volatile unsigned long long *s = sig + (seq & 1ull) * DD_MAXP + lane;
+    const long long t0 = clock64();
+    unsigned long long v = *s;
+    while ((v >> 1) != seq) {
+      if (clock64() - t0 > 8000000000ll) { bad = 1; break; }
+      __nanosleep(40);
+      v = *s;
+    }
+    want = (int)(v & 1ull);
+  }
+  __threadfence_system();
+  want = __any_sync(0xffffffffu, want);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    if (bad) { ctrl->err = 1; ctrl->stop = 1; }
+    else ctrl->stop = want;
+  }
+}
+
+// sorted position records from the owned positions and the receive areas of this step
+__global__ void k_dd_refresh_p2p(int nloc, int n, int ngl, const double *__restrict__ r, const double *recvL,
+                                 const double *recvR, size_t par_stride, const int *__restrict__ order,
+                                 double4 *__restrict__ pos4, const DdCtrl *ctrl) {
+  if (ctrl->stop) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  const size_t par = (size_t)(ctrl->seq & 1ull) * par_stride;
+  int i = order[s];
+  const double *src = i < n ? r + 3 * (size_t)i
+                            : (i < n + ngl ? recvL + par + 3 * (size_t)(i - n) : recvR + par + 3 * (size_t)(i - n - ngl));
+  double4 v = pos4[s];
+  v.x = src[0]; v.y = src[1]; v.z = src[2];
+  pos4[s] = v;
 }
 
 __global__ void k_dd_pack(int n, const int *__restrict__ idx, const double *__restrict__ r,
@@ -566,9 +683,28 @@ static int dd_compute(atx_ddmd *md, bool guarded) {
 }
 
 // migration + ghost construction + local neighbour list
+struct DdTimer {
+  atx_ddmd *md;
+  bool exact;
+  std::chrono::steady_clock::time_point t;
+  explicit DdTimer(atx_ddmd *m) : md(m) {
+    static const bool ex = getenv("ATX_DD_PROFILE") && atoi(getenv("ATX_DD_PROFILE")) != 0;
+    exact = ex;
+    if (exact) cudaStreamSynchronize(md->ctx->stream);
+    t = std::chrono::steady_clock::now();
+  }
+  void lap(int slot) {
+    if (exact) cudaStreamSynchronize(md->ctx->stream);
+    auto n = std::chrono::steady_clock::now();
+    md->rebuild_host_ms[slot] += std::chrono::duration<double, std::milli>(n - t).count();
+    t = n;
+  }
+};
+
 static int dd_rebuild(atx_ddmd *md) {
   atx_ctx *ctx = md->ctx;
   cudaStream_t st = ctx->stream;
+  DdTimer tm(md);
   const double b0 = md->B.m[0], b1 = md->B.m[3], b2 = md->B.m[6];  // Bbox(1,:)
   const double *t = md->torig;
   int n = md->nown;
@@ -590,12 +726,14 @@ static int dd_rebuild(atx_ddmd *md) {
     int c3[3];
     ATX_PASS(dd_read_counts(md, 3, c3));
     nL = c3[0]; nR = c3[1]; nstay = c3[2];
+    tm.lap(0);
     if ((md->left < 0 && nL > 0) || (md->right < 0 && nR > 0)) {
       atx_set_error("Particle outside simulation domain (left the non-periodic box along x).");
       return ATX_ERROR_UNSPECIFIED;
     }
     int inL = 0, inR = 0;
     ATX_PASS(dd_exchange_counts(md, nL, nR, &inL, &inR));
+    tm.lap(1);
     ATX_PASS(md->mig_send.reserve((size_t)DD_ROW * (nL + nR) + DD_ROW));
     ATX_PASS(md->mig_recv.reserve((size_t)DD_ROW * (inL + inR) + DD_ROW));
     // positions travel in the GLOBAL frame (+ periodic wrap), the receiver subtracts its origin
@@ -643,6 +781,7 @@ static int dd_rebuild(atx_ddmd *md) {
     swapbuf(md->idd, md->idd2); swapbuf(md->el, md->el2);
     md->nown = n = nnew;
     gb = (n + 255) / 256;
+    tm.lap(2);
   }
 
   // ---- ghosts: owned atoms within the halo of a face are sent to that neighbour
@@ -671,8 +810,16 @@ static int dd_rebuild(atx_ddmd *md) {
       md->nsendL = c2[0];
       md->nsendR = c2[1];
     }
+    tm.lap(3);
     ATX_PASS(dd_exchange_counts(md, md->nsendL, md->nsendR, &md->ngl, &md->ngr));
+    tm.lap(4);
     int nloc = n + md->ngl + md->ngr;
+    if (md->p2p && ((size_t)md->ngl > md->capG || (size_t)md->ngr > md->capG)) {
+      atx_set_error("Domain decomposition: more ghost atoms than the peer-to-peer receive areas hold (" +
+                    std::to_string(md->ngl) + " / " + std::to_string(md->ngr) + " of " + std::to_string(md->capG) +
+                    "); set ATX_DD_P2P=0 to use the NCCL halo path.");
+      return ATX_ERROR_MPI;
+    }
     ATX_PASS(dd_reserve_local(md, nloc));
     ATX_PASS(md->bufL.reserve(4 * (size_t)md->nsendL + 4));
     ATX_PASS(md->bufR.reserve(4 * (size_t)md->nsendR + 4));
@@ -699,6 +846,7 @@ static int dd_rebuild(atx_ddmd *md) {
       ATX_LAUNCHED();
       // receiver frame: subtract the local origin (ghost rows hold global positions)
     }
+    tm.lap(5);
   }
   return 0;
 }
@@ -713,6 +861,7 @@ __global__ void k_dd_shift(int n, int at, double *__restrict__ r, double sx, dou
 static int dd_build_list(atx_ddmd *md) {
   atx_ctx *ctx = md->ctx;
   cudaStream_t st = ctx->stream;
+  DdTimer tm(md);
   int n = md->nown, ng = md->ngl + md->ngr, nloc = n + ng;
   const double *t = md->torig;
   if (ng > 0) {
@@ -739,6 +888,7 @@ static int dd_build_list(atx_ddmd *md) {
     ATX_LAUNCHED();
   }
   md->nrebuilds++;
+  tm.lap(6);
   return 0;
 }
 
@@ -766,6 +916,88 @@ static int dd_kick(atx_ddmd *md) {
     k_dd_empty_step<<<1, 1, 0, st>>>(md->ctrl.ptr);
   }
   ATX_LAUNCHED();
+  return 0;
+}
+
+// Map every peer's mailbox (collective over the communicator).  Falls back to the NCCL step path
+// (md->p2p stays false) when any rank cannot export / map the handles; ATX_DD_P2P=0 forces that.
+static int dd_p2p_setup(atx_ddmd *md) {
+  atx_dd *dd = md->dd;
+  cudaStream_t st = md->ctx->stream;
+  const int P = dd->nranks, me = dd->rank;
+  if (P < 2 || P > DD_MAXP) return 0;
+  int enable = 1;
+  if (const char *v = getenv("ATX_DD_P2P")) enable = atoi(v) != 0;
+  // scratch: [0] capacity wish -> max, [1] ok flag -> min, then P ipc handles
+  DevBuf<int> d_i;
+  DevBuf<char> d_h;
+  ATX_PASS(d_i.reserve(4));
+  ATX_PASS(d_h.reserve((size_t)P * sizeof(cudaIpcMemHandle_t)));
+  int g = md->ngl > md->ngr ? md->ngl : md->ngr;
+  if (md->nsendL > g) g = md->nsendL;
+  if (md->nsendR > g) g = md->nsendR;
+  int h_i[2] = {g + g / 2 + 4096, 0};
+  ATX_CUDA(cudaMemcpyAsync(d_i.ptr, h_i, sizeof(int), cudaMemcpyHostToDevice, st));
+  ATX_NCCL(g_nccl.AllReduce(d_i.ptr, d_i.ptr, 1, ncclInt, ncclMax, dd->comm, st));
+  ATX_CUDA(cudaMemcpyAsync(h_i, d_i.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  md->capG = (size_t)h_i[0];
+  const size_t bytes = DD_SIG_BYTES + 4 * 3 * md->capG * sizeof(double);
+  int ok = enable;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc((void **)&md->mbox, bytes) != cudaSuccess) { ok = 0; md->mbox = nullptr; cudaGetLastError(); }
+  if (ok) {
+    ATX_CUDA(cudaMemsetAsync(md->mbox, 0, bytes, st));
+    if (cudaIpcGetMemHandle(&mine, md->mbox) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+  }
+  ATX_CUDA(cudaMemcpyAsync(d_h.ptr + (size_t)me * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+  ATX_NCCL(g_nccl.AllGather(d_h.ptr + (size_t)me * sizeof(mine), d_h.ptr, sizeof(mine), ncclChar, dd->comm, st));
+  std::vector<cudaIpcMemHandle_t> all(P);
+  ATX_CUDA(cudaMemcpyAsync(all.data(), d_h.ptr, (size_t)P * sizeof(mine), cudaMemcpyDeviceToHost, st));
+  h_i[1] = ok;
+  ATX_CUDA(cudaMemcpyAsync(d_i.ptr + 1, h_i + 1, sizeof(int), cudaMemcpyHostToDevice, st));
+  ATX_NCCL(g_nccl.AllReduce(d_i.ptr + 1, d_i.ptr + 1, 1, ncclInt, ncclMin, dd->comm, st));
+  ATX_CUDA(cudaMemcpyAsync(h_i + 1, d_i.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  ok = h_i[1];
+  if (ok) {
+    for (int p = 0; p < P; p++) {
+      if (p == me) { md->peer_mbox[p] = md->mbox; continue; }
+      void *q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+        break;
+      }
+      md->peer_mbox[p] = (char *)q;
+    }
+  }
+  // everybody must have mapped everybody before the first remote store / the fallback decision
+  h_i[1] = ok;
+  ATX_CUDA(cudaMemcpyAsync(d_i.ptr + 1, h_i + 1, sizeof(int), cudaMemcpyHostToDevice, st));
+  ATX_NCCL(g_nccl.AllReduce(d_i.ptr + 1, d_i.ptr + 1, 1, ncclInt, ncclMin, dd->comm, st));
+  ATX_CUDA(cudaMemcpyAsync(h_i + 1, d_i.ptr + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  ok = h_i[1];
+  if (!ok) {
+    for (int p = 0; p < P; p++) {
+      if (p != me && md->peer_mbox[p]) cudaIpcCloseMemHandle(md->peer_mbox[p]);
+      md->peer_mbox[p] = nullptr;
+    }
+    if (md->mbox) cudaFree(md->mbox);
+    md->mbox = nullptr;
+    cudaGetLastError();
+    md->p2p = false;
+    return 0;
+  }
+  std::vector<unsigned long long *> sigs(DD_MAXP, nullptr);
+  for (int p = 0; p < P; p++) sigs[p] = (unsigned long long *)md->peer_mbox[p];
+  ATX_PASS(md->d_peer_sig.reserve(DD_MAXP));
+  ATX_CUDA(cudaMemcpyAsync(md->d_peer_sig.ptr, sigs.data(), sizeof(unsigned long long *) * DD_MAXP,
+                           cudaMemcpyHostToDevice, st));
+  ATX_CUDA(cudaStreamSynchronize(st));
+  md->p2p = true;
   return 0;
 }
 
@@ -875,6 +1107,7 @@ extern "C" int atx_dd_md_create(atx_dd *dd, int pot_kind, void *pot, const doubl
     int n = md->nown;
     if (n > 0) err = atx_unsort(ctx, md->nown + md->ngl + md->ngr, 3, md->nl->order.ptr, md->tmpd.ptr, md->f.ptr);
   }
+  if (!err) err = dd_p2p_setup(md);
   if (err) {
     delete md;
     return err;
@@ -891,6 +1124,12 @@ extern "C" int atx_dd_md_destroy(atx_ddmd *md) {
   if (md->ev1) cudaEventDestroy(md->ev1);
   md->ploc.r_ext = nullptr;
   if (md->nl) atx_neighbors_destroy(md->nl);
+  if (md->p2p) {
+    cudaStreamSynchronize(md->ctx->stream);
+    for (int p = 0; p < md->dd->nranks && p < DD_MAXP; p++)
+      if (p != md->dd->rank && md->peer_mbox[p]) cudaIpcCloseMemHandle(md->peer_mbox[p]);
+    if (md->mbox) cudaFree(md->mbox);
+  }
   delete md;
   return 0;
 }
@@ -908,6 +1147,33 @@ static int dd_enqueue_step(atx_ddmd *md) {
     k_dd_nowish<<<1, 1, 0, st>>>(md->ctrl.ptr);
   }
   ATX_LAUNCHED();
+  if (dd->nranks > 1 && md->p2p) {
+    const double dL = 1.0 / dd->nranks, dR = -1.0 / dd->nranks;
+    const size_t par_stride = 3 * md->capG;
+    double *recvL = (double *)(md->mbox + DD_SIG_BYTES), *recvR = recvL + 2 * par_stride;
+    // my left neighbour receives in ITS recvR, my right neighbour in ITS recvL
+    double *dstL = md->left >= 0 ? (double *)(md->peer_mbox[md->left] + DD_SIG_BYTES) + 2 * par_stride : nullptr;
+    double *dstR = md->right >= 0 ? (double *)(md->peer_mbox[md->right] + DD_SIG_BYTES) : nullptr;
+    const int nsend = md->nsendL + md->nsendR;
+    {
+      ProfScope ps_(md->ctx, "dd_halo");
+      k_dd_pack_p2p<<<nsend > 0 ? (nsend + 255) / 256 : 1, 256, 0, st>>>(
+          md->nsendL, md->nsendR, md->sendL.ptr, md->sendR.ptr, md->r.ptr, dL * md->a1[0], dL * md->a1[1],
+          dL * md->a1[2], dR * md->a1[0], dR * md->a1[1], dR * md->a1[2], dstL, dstR, par_stride,
+          md->d_peer_sig.ptr, dd->rank, dd->nranks, md->ctrl.ptr);
+      ATX_LAUNCHED();
+      k_dd_wait<<<1, 32, 0, st>>>((const unsigned long long *)md->mbox, dd->nranks, md->ctrl.ptr);
+      ATX_LAUNCHED();
+    }
+    if (nloc > 0) {
+      k_dd_refresh_p2p<<<(nloc + 255) / 256, 256, 0, st>>>(nloc, n, md->ngl, md->r.ptr, recvL, recvR, par_stride,
+                                                           md->nl->order.ptr, md->nl->pos4.ptr, md->ctrl.ptr);
+      ATX_LAUNCHED();
+    }
+    ATX_PASS(dd_compute(md, true));
+    ATX_PASS(dd_kick(md));
+    return 0;
+  }
   if (dd->nranks > 1) {
     // global OR of the rebuild wish, written straight into the stop flag (no host involvement)
     {
@@ -966,6 +1232,10 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
     if (md->pot_kind == ATX_POT_BOP) ATX_PASS(atx_bop_check_overflow((atx_bop *)md->pot));
     if (md->pot_kind == ATX_POT_REBO2) ATX_PASS(atx_rebo2_check_overflow((atx_rebo2 *)md->pot));
     DdCtrl hc = *md->hctrl.ptr;
+    if (hc.err) {
+      atx_set_error("Domain decomposition: a peer's halo signal did not arrive (peer-to-peer step path timed out).");
+      return ATX_ERROR_MPI;
+    }
     int done = hc.steps_done - done_total;
     done_total = hc.steps_done;
     remaining -= done;
@@ -974,8 +1244,12 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
       ATX_PASS(dd_rebuild(md));
       ATX_PASS(dd_build_list(md));
       ATX_PASS(dd_reset_ctrl(md));
-      ATX_PASS(dd_compute(md, false));
-      ATX_PASS(dd_kick(md));
+      {
+        DdTimer tm(md);
+        ATX_PASS(dd_compute(md, false));
+        ATX_PASS(dd_kick(md));
+        tm.lap(7);
+      }
       done_total += 1;
       remaining -= 1;
     }
@@ -1035,5 +1309,17 @@ extern "C" int atx_dd_md_get_stats(atx_ddmd *md, long long *nrebuilds, double *l
   if (md && md->ctx) cudaSetDevice(md->ctx->device);
   if (nrebuilds) *nrebuilds = md->nrebuilds;
   if (last_run_ms) *last_run_ms = md->last_ms;
+  return 0;
+}
+
+// host wall time (ms, accumulated since create) of the rebuild phases: 0 migration select + counts,
+// 1 count exchange, 2 migration transfer + compaction, 3 ghost select + counts, 4 count exchange,
+// 5 ghost transfer, 6 local neighbour list + roles, 7 first force evaluation.  Exact per phase only
+// with ATX_DD_PROFILE=1 (a stream synchronisation at every phase boundary); p2p: 1 when the
+// peer-to-peer step path is active.
+extern "C" int atx_dd_md_get_profile(atx_ddmd *md, double *ms8, int *p2p) {
+  if (!md) return ATX_ERROR_UNSPECIFIED;
+  if (ms8) for (int k = 0; k < 8; k++) ms8[k] = md->rebuild_host_ms[k];
+  if (p2p) *p2p = md->p2p ? 1 : 0;
   return 0;
 }

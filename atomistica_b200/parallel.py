@@ -164,4 +164,7 @@ class DDVelocityVerlet:
     def stats(self):
         n, ms = C.c_longlong(0), C.c_double(0.0)
         L.check(L.lib().atx_dd_md_get_stats(self._h, C.byref(n), C.byref(ms)))
-        return dict(nrebuilds=n.value, last_run_ms=ms.value)
+        prof = (C.c_double * 8)()
+        p2p = C.c_int(0)
+        L.check(L.lib().atx_dd_md_get_profile(self._h, prof, C.byref(p2p)))
+        return dict(nrebuilds=n.value, last_run_ms=ms.value, rebuild_host_ms=list(prof), p2p=bool(p2p.value))

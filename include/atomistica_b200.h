@@ -333,6 +333,10 @@ int atx_dd_md_get_count(atx_ddmd *md, int *nown, int *nghost);
 /* owned atoms of this rank: global ids, positions (global frame), velocities, forces */
 int atx_dd_md_get_state(atx_ddmd *md, long long *id, double *r, double *v, double *f);
 int atx_dd_md_get_stats(atx_ddmd *md, long long *nrebuilds, double *last_run_ms);
+/* Host wall time (ms, accumulated) of the eight phases of the decomposition rebuild (migration,
+ * ghost construction, local list -- communicate_particles / communicate_ghosts,
+ * domain_decomposition.f90:494-826) and whether the peer-to-peer step path is active. */
+int atx_dd_md_get_profile(atx_ddmd *md, double *ms8, int *p2p);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------- */
 /* CUDA-event timing of the library's own kernels on the launching stream.  When enabled every

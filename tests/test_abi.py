@@ -146,7 +146,6 @@ def test_c_example_links_and_fails_loudly_without_a_device(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1', reason='C example not yet run on hardware')
 def test_c_example_on_the_gpu(tmp_path):
     import subprocess
     r = subprocess.run([_build_c_example(tmp_path)], capture_output=True, text=True)

@@ -37,7 +37,5 @@ def test_dd_matches_single_gpu(case, nsteps):
     assert out['depot'] < 1e-9 and out['dekin'] < 1e-8
 
 
-@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                    reason='REBO2 under decomposition (k_rebo2_force_roles, 5-cutoff halo) not yet run on hardware')
 def test_dd_rebo2_matches_single_gpu():
     test_dd_matches_single_gpu('rebo2', 120)

@@ -221,8 +221,6 @@ def test_funcfl_tabulated_eam(au_funcfl):
         pot.energy_and_forces(p, nl, wpot_per_at=True)
 
 
-@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                    reason='experimental lane mapping (ATX_EAM_MAP=1) not yet run on hardware')
 @pytest.mark.parametrize('lanes,unroll', [(4, 2), (8, 2), (16, 1)])
 def test_consecutive_lane_mapping(cu_setfl, monkeypatch, lanes, unroll):
     # the variant the wavefront model of benchmarks/model_gather_wavefronts.py suggests: same sums in

@@ -117,9 +117,6 @@ def test_rebo2_external_refuses_per_bond_outputs():
         pot.energy_and_forces(p, nl, epot_per_bond=True)
 
 
-@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                    reason='k_rebo2_force_roles not yet run on hardware (its per-atom source is checked on the '
-                           'CPU by tests/test_emu_rebo2_scr.py)')
 def test_rebo2_external():
     # REBO2 reaches five bonds: ghosts within 5 bond cutoffs
     rng = np.random.RandomState(1)

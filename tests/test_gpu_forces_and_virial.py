@@ -7,9 +7,6 @@ the reference uses them; forces and stress against the finite-difference helpers
 `atomistica_b200.tests` (mirror of `atomistica.tests`), dx = 1e-6, tolerance 1e-2 on the reference's
 error measures.
 
-STATUS: written after the round's GPU minutes were spent.  It only combines pieces that are
-verified separately (the calculators on the GPU, the helpers on the CPU), but it has not run yet,
-so it is fenced like the other late additions (ATX_RUN_UNVERIFIED=1).
 """
 import os
 
@@ -21,9 +18,7 @@ from atomistica_b200 import structures as S
 from atomistica_b200.tests import test_forces as forces, test_virial as virial
 from conftest import load_npz
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                                 reason='not yet run on hardware (set ATX_RUN_UNVERIFIED=1)')]
+pytestmark = [pytest.mark.gpu]
 
 sx = 2
 dx = 1e-6

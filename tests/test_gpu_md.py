@@ -94,8 +94,6 @@ def test_bop_md_energy_conservation(cls, avgn):
         assert drv.stats()['nrebuilds'] >= 1
 
 
-@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                    reason='Rebo2Scr kernels not yet run on hardware (set ATX_RUN_UNVERIFIED=1)')
 def test_rebo2scr_md_energy_conservation():
     a = S.diamond('C', 3.566, (4, 4, 4))
     a.rattle(0.02, seed=3)

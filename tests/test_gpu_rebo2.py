@@ -137,9 +137,6 @@ def test_full_size_replication_invariance(aC):
     assert np.abs(f.sum(axis=0)).max() <= 1e-9 * fscale * np.sqrt(len(big))
 
 
-@pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                    reason='one-thread-per-bond kernels (ATX_REBO2_PERBOND=1) not yet run on hardware; their '
-                           'per-atom source is checked on the CPU by tests/test_emu_rebo2_scr.py')
 @pytest.mark.parametrize('variant', ['1', '2', '3'])
 def test_one_thread_per_bond_variant(aC_small, monkeypatch, variant):
     monkeypatch.setenv('ATX_REBO2_PERBOND', variant)      # 4 / 6 / 8 resident blocks per SM

@@ -1,9 +1,7 @@
 """Rebo2Scr on the GPU vs the oracle (1e-10 relative), through the C ABI.
 
-STATUS: the kernels were written after this round's GPU budget was spent.  Their per-atom logic is
-the source that tests/test_emu_rebo2_scr.py runs on the CPU against the oracle (green); the launch
-glue (atx_rebo2.cu: rebo2_scr_compute) has NOT run on hardware yet, so these tests are fenced and
-only run with ATX_RUN_UNVERIFIED=1.  Remove the fence after the first green run on a B200.
+The per-atom logic is the source that tests/test_emu_rebo2_scr.py also runs on the CPU against the
+oracle; first green hardware run: round 2, first GPU call (124 passed with all fences lifted).
 """
 import os
 
@@ -13,9 +11,7 @@ import pytest
 import oracle
 from atomistica_b200 import native, structures as S
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('ATX_RUN_UNVERIFIED') != '1',
-                                 reason='Rebo2Scr kernels not yet run on hardware (set ATX_RUN_UNVERIFIED=1)')]
+pytestmark = [pytest.mark.gpu]
 RTOL = 1e-10
 
 

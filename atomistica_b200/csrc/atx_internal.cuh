@@ -175,6 +175,10 @@ struct atx_neighbors {
   DevBuf<double4> pos4;     // sorted: x,y,z, (w = element id as double bits)
   DevBuf<double4> pos_build;  // pos4 at the last build (library-mode Verlet shell only)
   DevBuf<int4> sshift;      // sorted: cell id + wrap shift
+  DevBuf<float4> posf;      // sorted: position relative to the atom's cell origin (float), w = bits of
+                            // (element << 24 | packed wrap shift): 16-byte candidate record of the
+                            // single-precision pre-filter of the pair search
+  double f32_delta = -1.0;  // > 0: half-width of the band around cutoff^2 inside which the exact test runs
   DevBuf<int> count;        // nat+1 neighbour counts (sorted order)
   DevBuf<long long> seed;   // nat+1 exclusive offsets (sorted order), 0-based
   DevBuf<int2> list;        // device list: {sorted j, packed shift}

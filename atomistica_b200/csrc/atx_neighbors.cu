@@ -147,16 +147,93 @@ __global__ void k_cell_sort(int ncell, const int *__restrict__ cell_start, int *
   }
 }
 
+// scal[5]: bit pattern of the largest |component| of a cell-relative position (non-negative doubles
+// order like unsigned integers); scal[6]: set when a wrap shift does not fit the 8-bit packing
+// the same for well-filled cells (metals: ~20 atoms per cell): one warp per cell ranks every atom by
+// counting the smaller indices of the cell (indices are distinct), no serial insertion
+__global__ void __launch_bounds__(256)
+k_cell_sort_warp(int ncell, const int *__restrict__ cell_start, int *__restrict__ order) {
+  const int c = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= ncell) return;
+  const int b = cell_start[c], n = cell_start[c + 1] - b;
+  if (n <= 1) return;
+  if (n <= 32) {
+    const int v = lane < n ? order[b + lane] : 0x7fffffff;
+    int rank = 0;
+    for (int k = 0; k < n; k++) rank += __shfl_sync(0xffffffffu, v, k) < v;
+    __syncwarp();
+    if (lane < n) order[b + rank] = v;
+  } else if (n <= 256) {
+    int v[8], rk[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int t = lane + 32 * q;
+      v[q] = t < n ? order[b + t] : 0x7fffffff;
+      rk[q] = 0;
+    }
+    for (int k = 0; k < n; k++) {
+      const int u = order[b + k];
+#pragma unroll
+      for (int q = 0; q < 8; q++) rk[q] += u < v[q];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (lane + 32 * q < n) order[b + rk[q]] = v[q];
+  } else if (lane == 0) {
+    for (int a = b + 1; a < b + n; a++) {
+      int v = order[a];
+      int q = a - 1;
+      while (q >= b && order[q] > v) {
+        order[q + 1] = order[q];
+        q--;
+      }
+      order[q + 1] = v;
+    }
+  }
+}
+
 __global__ void k_gather_sorted(int nat, const double *__restrict__ r, const int *__restrict__ el,
                                 const int4 *__restrict__ cellshift, const int *__restrict__ order,
                                 double4 *__restrict__ pos4, int4 *__restrict__ sshift,
-                                int *__restrict__ inv) {
+                                int *__restrict__ inv, Geo g, float4 *__restrict__ posf,
+                                long long *__restrict__ scal) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nat) return;
-  int i = order[s];
-  pos4[s] = make_double4(r[3 * i], r[3 * i + 1], r[3 * i + 2], el ? (double)el[i] : 1.0);
-  if (sshift) sshift[s] = cellshift[i];
-  if (inv) inv[i] = s;
+  double ext = 0.0;
+  int bad = 0;
+  if (s < nat) {
+    int i = order[s];
+    double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
+    int e = el ? el[i] : 1;
+    pos4[s] = make_double4(x, y, z, (double)e);
+    int4 cs = cellshift[i];
+    if (sshift) sshift[s] = cs;
+    if (inv) inv[i] = s;
+    if (posf) {
+      // wrapped position minus the origin of the atom's cell: r + A.(shift - c/n)
+      int c2 = cs.x % g.n[2], c1 = (cs.x / g.n[2]) % g.n[1], c0 = cs.x / (g.n[2] * g.n[1]);
+      double t0 = (double)cs.y - (double)c0 / g.n[0], t1 = (double)cs.z - (double)c1 / g.n[1],
+             t2 = (double)cs.w - (double)c2 / g.n[2];
+      double px = x + g.A.m[0] * t0 + g.A.m[3] * t1 + g.A.m[6] * t2;
+      double py = y + g.A.m[1] * t0 + g.A.m[4] * t1 + g.A.m[7] * t2;
+      double pz = z + g.A.m[2] * t0 + g.A.m[5] * t1 + g.A.m[8] * t2;
+      bad = (abs(cs.y) >= ATX_SHIFT_BIAS) | (abs(cs.z) >= ATX_SHIFT_BIAS) | (abs(cs.w) >= ATX_SHIFT_BIAS) |
+            !(px == px) | !(py == py) | !(pz == pz);
+      int w = bad ? 0 : (atx_pack_shift(cs.y, cs.z, cs.w) | (e << 24));
+      posf[s] = make_float4((float)px, (float)py, (float)pz, __int_as_float(w));
+      ext = fmax(fabs(px), fmax(fabs(py), fabs(pz)));
+    }
+  }
+  if (posf) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (ext > 0.0) atomicMax((unsigned long long *)&scal[5], (unsigned long long)__double_as_longlong(ext));
+      if (bad) atomicMax((unsigned long long *)&scal[6], 1ull);
+    }
+  }
 }
 
 // Pair search: one thread per atom (sorted order), reference stencil order.
@@ -227,6 +304,100 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
             }
             cnt++;
           }
+        }
+      }
+    }
+  }
+  if (!FILL) count[s] = cnt;
+}
+
+// Pair search with a single-precision pre-filter: the same walk as k_pairs, but a candidate costs one
+// 16-byte record (cell-relative float position + packed element / wrap shift) and a handful of FP32
+// operations.  d2 is first evaluated in float from cell-relative coordinates: |d2_f - d2| < delta
+// for every candidate whose classification matters (bound in atx_neighbors_update), so
+//   d2_f >= rc^2 + delta -> outside,   d2_f < rc^2 - delta -> inside,
+// and only inside the band of half-width delta (a fraction ~1e-5 of the candidates) the reference's
+// exact double-precision predicate of k_pairs decides.  The resulting list is bit-identical.
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+k_pairs_f32(int nat, Geo g, float lo2, float hi2, const float4 *__restrict__ posf,
+            const double4 *__restrict__ pos4, const int4 *__restrict__ sshift,
+            const int *__restrict__ cell_start, int *__restrict__ count,
+            const long long *__restrict__ seed, int2 *__restrict__ list, long long *__restrict__ scal,
+            int2 *__restrict__ rows, int rows_cap) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nat) return;
+  const float4 fi = posf[s];
+  const int4 cs = sshift[s];
+  int ci[3];
+  ci[2] = cs.x % g.n[2];
+  ci[1] = (cs.x / g.n[2]) % g.n[1];
+  ci[0] = cs.x / (g.n[2] * g.n[1]);
+  // cell vectors (columns of Abox / n_cells)
+  const double c0x = g.A.m[0] / g.n[0], c0y = g.A.m[1] / g.n[0], c0z = g.A.m[2] / g.n[0];
+  const double c1x = g.A.m[3] / g.n[1], c1y = g.A.m[4] / g.n[1], c1z = g.A.m[5] / g.n[1];
+  const double c2x = g.A.m[6] / g.n[2], c2y = g.A.m[7] / g.n[2], c2z = g.A.m[8] / g.n[2];
+  long long w = FILL ? seed[s] : 0;
+  int cnt = 0;
+  for (int x = -g.sten[0]; x <= g.sten[0]; x++) {
+    int cx = ci[0] + x, sx = cs.y;
+    if (g.pbc[0]) {
+      while (cx < 0) { cx += g.n[0]; sx += 1; }
+      while (cx >= g.n[0]) { cx -= g.n[0]; sx -= 1; }
+    } else if (cx < 0 || cx >= g.n[0]) continue;
+    for (int y = -g.sten[1]; y <= g.sten[1]; y++) {
+      int cy = ci[1] + y, sy = cs.z;
+      if (g.pbc[1]) {
+        while (cy < 0) { cy += g.n[1]; sy += 1; }
+        while (cy >= g.n[1]) { cy -= g.n[1]; sy -= 1; }
+      } else if (cy < 0 || cy >= g.n[1]) continue;
+      for (int z = -g.sten[2]; z <= g.sten[2]; z++) {
+        int cz = ci[2] + z, sz = cs.w;
+        if (g.pbc[2]) {
+          while (cz < 0) { cz += g.n[2]; sz += 1; }
+          while (cz >= g.n[2]) { cz -= g.n[2]; sz -= 1; }
+        } else if (cz < 0 || cz >= g.n[2]) continue;
+        // the image of the candidate's cell next to i: offset (x,y,z) cells from i's cell, whatever
+        // the wrapped index is; relative position of i as seen from that cell's origin
+        const float qx = fi.x - (float)(x * c0x + y * c1x + z * c2x);
+        const float qy = fi.y - (float)(x * c0y + y * c1y + z * c2y);
+        const float qz = fi.z - (float)(x * c0z + y * c1z + z * c2z);
+        const int cid = (cx * g.n[1] + cy) * g.n[2] + cz;
+        const int b = cell_start[cid], e = cell_start[cid + 1];
+        for (int t = b; t < e; t++) {
+          const float4 fj = posf[t];
+          const float dxf = qx - fj.x, dyf = qy - fj.y, dzf = qz - fj.z;
+          const float d2f = dxf * dxf + dyf * dyf + dzf * dzf;
+          if (d2f >= hi2) continue;
+          const int wj = __float_as_int(fj.w);
+          int jx, jy, jz;
+          atx_unpack_shift(wj, jx, jy, jz);
+          const int s2x = sx - jx, s2y = sy - jy, s2z = sz - jz;
+          const bool zero = (s2x | s2y | s2z) == 0;
+          if (t == s && zero) continue;
+          if (d2f >= lo2) {
+            // band around the cutoff: the reference's predicate in double precision (as in k_pairs)
+            const double4 pi = pos4[s], pj = pos4[t];
+            double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
+            if (!zero) {
+              double ax, ay, az;
+              atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
+              dx = __dadd_rn(dx, ax); dy = __dadd_rn(dy, ay); dz = __dadd_rn(dz, az);
+            }
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (!(d2 < g.cutoff_sq)) continue;
+          }
+          const int bad = (abs(s2x) >= ATX_SHIFT_BIAS) | (abs(s2y) >= ATX_SHIFT_BIAS) |
+                          (abs(s2z) >= ATX_SHIFT_BIAS);
+          const int2 ent = make_int2(t, atx_pack_shift(s2x, s2y, s2z) | (wj & 0x7f000000));
+          if (FILL) {
+            if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
+            list[w++] = ent;
+          } else if (rows && cnt < rows_cap) {
+            if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
+            rows[(size_t)s * rows_cap + cnt] = ent;
+          }
+          cnt++;
         }
       }
     }
@@ -478,6 +649,9 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   ATX_PASS(nl->count.reserve(nat + 1));
   ATX_PASS(nl->seed.reserve(nat + 2));
   ATX_PASS(nl->scal.reserve(8));
+  static const bool f32_env = !(getenv("ATX_NL_F32") && atoi(getenv("ATX_NL_F32")) == 0);
+  const bool use_f32 = f32_env;
+  if (use_f32) ATX_PASS(nl->posf.reserve(nat + 1));
 
   ATX_CUDA(cudaMemsetAsync(nl->cell_count.ptr, 0, sizeof(int) * (ncell + 1), st));
   ATX_CUDA(cudaMemsetAsync(nl->cell_fill.ptr, 0, sizeof(int) * (ncell + 1), st));
@@ -495,13 +669,47 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     k_cell_scatter<<<gb, TB, 0, st>>>(nat, nl->cellshift.ptr, nl->cell_start.ptr, nl->cell_fill.ptr,
                                       nl->order.ptr);
     ATX_LAUNCHED();
-    k_cell_sort<<<(ncell + TB - 1) / TB, TB, 0, st>>>(ncell, nl->cell_start.ptr, nl->order.ptr);
+    if ((long long)nat > 3ll * ncell) {
+      const long long nthr = (long long)ncell * 32;
+      k_cell_sort_warp<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(ncell, nl->cell_start.ptr, nl->order.ptr);
+    } else {
+      k_cell_sort<<<(ncell + TB - 1) / TB, TB, 0, st>>>(ncell, nl->cell_start.ptr, nl->order.ptr);
+    }
     ATX_LAUNCHED();
     k_gather_sorted<<<gb, TB, 0, st>>>(nat, p->rptr(), p->el.cap ? p->el.ptr : nullptr,
                                        nl->cellshift.ptr, nl->order.ptr, nl->pos4.ptr,
-                                       nl->sshift.ptr, nl->inv.ptr);
+                                       nl->sshift.ptr, nl->inv.ptr, g, use_f32 ? nl->posf.ptr : nullptr,
+                                       nl->scal.ptr);
     ATX_LAUNCHED();
   }
+  // single-precision pre-filter of the pair search: half-width of the band in which the exact
+  // predicate decides, from the largest cell-relative coordinate of this build (error analysis at
+  // k_pairs_f32).  u = 2^-24; every term carries a factor 2 of safety.
+  float lo2 = 0.f, hi2 = 0.f;
+  nl->f32_delta = -1.0;
+  if (use_f32 && nat > 0) {
+    long long hb[2] = {0, 0};
+    ATX_CUDA(cudaMemcpyAsync(hb, nl->scal.ptr + 5, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    ATX_CUDA(cudaStreamSynchronize(st));
+    double ext;
+    memcpy(&ext, &hb[0], sizeof(double));
+    const double *A = p->Abox.m;
+    double offmax = 0.0;
+    for (int k = 0; k < 3; k++) {
+      double len = std::sqrt(A[3 * k] * A[3 * k] + A[3 * k + 1] * A[3 * k + 1] + A[3 * k + 2] * A[3 * k + 2]);
+      offmax += nl->sten[k] * len / nl->n_cells[k];
+    }
+    const double eps = std::ldexp(1.0, -23), R2 = g.cutoff_sq, R = std::sqrt(R2);
+    const double e_d = eps * (5.0 * ext + 3.0 * offmax);
+    const double delta = 2.0 * (2.0 * std::sqrt(3.0) * R * e_d * 1.01 + 3.0 * e_d * e_d + 2.0 * eps * R2 * 1.01) +
+                         2.0 * eps * R2;
+    if (!hb[1] && delta <= 0.05 * R2 && ext == ext) {
+      nl->f32_delta = delta;
+      lo2 = std::nextafterf((float)(R2 - delta), -1.0f);
+      hi2 = std::nextafterf((float)(R2 + delta), 3.0e38f);
+    }
+  }
+  const bool f32 = nl->f32_delta > 0.0;
   long long h[4] = {0, 0, 0, 0};
   // Single-pass build from the second build on: the previous build's longest list (+ margin) sizes
   // fixed-width rows the counting pass fills; if an atom outgrows its row the classic second
@@ -515,6 +723,12 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nat > 0) {
     {
       ProfScope ps_(ctx, "nl_pairs_count");
+      if (f32)
+        k_pairs_f32<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, lo2, hi2, nl->posf.ptr, nl->pos4.ptr,
+                                                              nl->sshift.ptr, nl->cell_start.ptr, nl->count.ptr,
+                                                              nullptr, nullptr, nl->scal.ptr,
+                                                              rows_cap > 0 ? nl->rows.ptr : nullptr, rows_cap);
+      else
       k_pairs<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
                                                         nl->cell_start.ptr, nl->order.ptr,
                                                         nl->count.ptr, nullptr, nullptr, nl->scal.ptr,
@@ -549,6 +763,10 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
         const long long nthr = (long long)nat * 8;
         k_rows_to_csr<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(nat, nl->rows.ptr, rows_cap, nl->seed.ptr,
                                                                       nl->list.ptr);
+      } else if (f32) {
+        k_pairs_f32<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, lo2, hi2, nl->posf.ptr, nl->pos4.ptr,
+                                                             nl->sshift.ptr, nl->cell_start.ptr, nl->count.ptr,
+                                                             nl->seed.ptr, nl->list.ptr, nl->scal.ptr, nullptr, 0);
       } else {
         k_pairs<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, nl->pos4.ptr, nl->sshift.ptr,
                                                          nl->cell_start.ptr, nl->order.ptr,

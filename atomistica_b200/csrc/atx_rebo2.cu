@@ -435,6 +435,7 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
   if (o.epa) ATX_CUDA(cudaMemsetAsync(o.epa, 0, sizeof(double) * (size_t)nat, st));
   if (o.wpa) ATX_CUDA(cudaMemsetAsync(o.wpa, 0, sizeof(double) * 9 * (size_t)nat, st));
   if (nat > 0) {
+    ProfScope ps_(ctx, "rebo2_bonds");
     k_rebo2_bonds<<<(nat + 127) / 128, 128, 0, st>>>(nat, nbs, p->Abox, pot->dev, nl->pos4.ptr,
                                                      nl->seed.ptr, nl->list.ptr, pot->b_cnt.ptr,
                                                      pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,

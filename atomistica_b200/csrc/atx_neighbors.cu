@@ -74,6 +74,7 @@ static void neighbors_geometry(atx_neighbors *nl, const atx_particles *p) {
 struct Geo {
   Mat3 rec;
   Mat3 A;
+  Mat3 cvec;   // cell vectors of the binning grid: column k = Abox(:,k) / n_cells(k)
   int n[3];
   int pbc[3];
   int sten[3];
@@ -218,8 +219,8 @@ __global__ void k_gather_sorted(int nat, const double *__restrict__ r, const int
       double px = x + g.A.m[0] * t0 + g.A.m[3] * t1 + g.A.m[6] * t2;
       double py = y + g.A.m[1] * t0 + g.A.m[4] * t1 + g.A.m[7] * t2;
       double pz = z + g.A.m[2] * t0 + g.A.m[5] * t1 + g.A.m[8] * t2;
-      bad = (abs(cs.y) >= ATX_SHIFT_BIAS) | (abs(cs.z) >= ATX_SHIFT_BIAS) | (abs(cs.w) >= ATX_SHIFT_BIAS) |
-            !(px == px) | !(py == py) | !(pz == pz);
+      // wrap counts beyond +-59 cells (atoms far outside a periodic cell): the exact kernel takes over
+      bad = (abs(cs.y) >= 60) | (abs(cs.z) >= 60) | (abs(cs.w) >= 60) | !(px == px) | !(py == py) | !(pz == pz);
       int w = bad ? 0 : (atx_pack_shift(cs.y, cs.z, cs.w) | (e << 24));
       posf[s] = make_float4((float)px, (float)py, (float)pz, __int_as_float(w));
       ext = fmax(fabs(px), fmax(fabs(py), fabs(pz)));
@@ -318,9 +319,24 @@ k_pairs(int nat, Geo g, const double4 *__restrict__ pos4, const int4 *__restrict
 //   d2_f >= rc^2 + delta -> outside,   d2_f < rc^2 - delta -> inside,
 // and only inside the band of half-width delta (a fraction ~1e-5 of the candidates) the reference's
 // exact double-precision predicate of k_pairs decides.  The resulting list is bit-identical.
+// the reference's predicate in double precision (identical to k_pairs) for candidate t of atom s
+__device__ __noinline__ bool pairs_exact(const Geo &g, const double4 *__restrict__ pos4, int s, int t, int code) {
+  int s2x, s2y, s2z;
+  atx_unpack_shift(code, s2x, s2y, s2z);
+  const double4 pi = pos4[s], pj = pos4[t];
+  double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
+  if ((s2x | s2y | s2z) != 0) {
+    double ax, ay, az;
+    atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
+    dx = __dadd_rn(dx, ax); dy = __dadd_rn(dy, ay); dz = __dadd_rn(dz, az);
+  }
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  return d2 < g.cutoff_sq;
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
-k_pairs_f32(int nat, Geo g, float lo2, float hi2, const float4 *__restrict__ posf,
+k_pairs_f32(int nat, const __grid_constant__ Geo g, float lo2, float hi2, const float4 *__restrict__ posf,
             const double4 *__restrict__ pos4, const int4 *__restrict__ sshift,
             const int *__restrict__ cell_start, int *__restrict__ count,
             const long long *__restrict__ seed, int2 *__restrict__ list, long long *__restrict__ scal,
@@ -333,10 +349,6 @@ k_pairs_f32(int nat, Geo g, float lo2, float hi2, const float4 *__restrict__ pos
   ci[2] = cs.x % g.n[2];
   ci[1] = (cs.x / g.n[2]) % g.n[1];
   ci[0] = cs.x / (g.n[2] * g.n[1]);
-  // cell vectors (columns of Abox / n_cells)
-  const double c0x = g.A.m[0] / g.n[0], c0y = g.A.m[1] / g.n[0], c0z = g.A.m[2] / g.n[0];
-  const double c1x = g.A.m[3] / g.n[1], c1y = g.A.m[4] / g.n[1], c1z = g.A.m[5] / g.n[1];
-  const double c2x = g.A.m[6] / g.n[2], c2y = g.A.m[7] / g.n[2], c2z = g.A.m[8] / g.n[2];
   long long w = FILL ? seed[s] : 0;
   int cnt = 0;
   for (int x = -g.sten[0]; x <= g.sten[0]; x++) {
@@ -351,6 +363,8 @@ k_pairs_f32(int nat, Geo g, float lo2, float hi2, const float4 *__restrict__ pos
         while (cy < 0) { cy += g.n[1]; sy += 1; }
         while (cy >= g.n[1]) { cy -= g.n[1]; sy -= 1; }
       } else if (cy < 0 || cy >= g.n[1]) continue;
+      const double oxy0 = x * g.cvec.m[0] + y * g.cvec.m[3], oxy1 = x * g.cvec.m[1] + y * g.cvec.m[4],
+                   oxy2 = x * g.cvec.m[2] + y * g.cvec.m[5];
       for (int z = -g.sten[2]; z <= g.sten[2]; z++) {
         int cz = ci[2] + z, sz = cs.w;
         if (g.pbc[2]) {
@@ -359,45 +373,31 @@ k_pairs_f32(int nat, Geo g, float lo2, float hi2, const float4 *__restrict__ pos
         } else if (cz < 0 || cz >= g.n[2]) continue;
         // the image of the candidate's cell next to i: offset (x,y,z) cells from i's cell, whatever
         // the wrapped index is; relative position of i as seen from that cell's origin
-        const float qx = fi.x - (float)(x * c0x + y * c1x + z * c2x);
-        const float qy = fi.y - (float)(x * c0y + y * c1y + z * c2y);
-        const float qz = fi.z - (float)(x * c0z + y * c1z + z * c2z);
+        const float qx = fi.x - (float)(oxy0 + z * g.cvec.m[6]);
+        const float qy = fi.y - (float)(oxy1 + z * g.cvec.m[7]);
+        const float qz = fi.z - (float)(oxy2 + z * g.cvec.m[8]);
         const int cid = (cx * g.n[1] + cy) * g.n[2] + cz;
         const int b = cell_start[cid], e = cell_start[cid + 1];
+        // packed shift2 = (s + w) - cs_j as ONE integer subtraction: the biased bytes are base-256 digits and
+        // every digit of the result stays inside [0, 255] (|cs| < 60 is checked when the records are built)
+        const int psz = atx_pack_shift(sx, sy, sz) + ATX_SHIFT_ZERO;
+#pragma unroll 2
         for (int t = b; t < e; t++) {
           const float4 fj = posf[t];
           const float dxf = qx - fj.x, dyf = qy - fj.y, dzf = qz - fj.z;
           const float d2f = dxf * dxf + dyf * dyf + dzf * dzf;
-          if (d2f >= hi2) continue;
-          const int wj = __float_as_int(fj.w);
-          int jx, jy, jz;
-          atx_unpack_shift(wj, jx, jy, jz);
-          const int s2x = sx - jx, s2y = sy - jy, s2z = sz - jz;
-          const bool zero = (s2x | s2y | s2z) == 0;
-          if (t == s && zero) continue;
-          if (d2f >= lo2) {
-            // band around the cutoff: the reference's predicate in double precision (as in k_pairs)
-            const double4 pi = pos4[s], pj = pos4[t];
-            double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
-            if (!zero) {
-              double ax, ay, az;
-              atx_image_vector(g.A, s2x, s2y, s2z, ax, ay, az);
-              dx = __dadd_rn(dx, ax); dy = __dadd_rn(dy, ay); dz = __dadd_rn(dz, az);
+          if (d2f < hi2) {
+            const int wj = __float_as_int(fj.w);
+            const int code = psz - (wj & ATX_SHIFT_MASK);
+            bool hit = (t != s) | (code != ATX_SHIFT_ZERO);
+            if (d2f >= lo2 && hit) hit = pairs_exact(g, pos4, s, t, code);   // band around the cutoff (rare)
+            if (hit) {
+              const int2 ent = make_int2(t, code | (wj & 0x7f000000));
+              if (FILL) list[w++] = ent;
+              else if (rows && cnt < rows_cap) rows[(size_t)s * rows_cap + cnt] = ent;
+              cnt++;
             }
-            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if (!(d2 < g.cutoff_sq)) continue;
           }
-          const int bad = (abs(s2x) >= ATX_SHIFT_BIAS) | (abs(s2y) >= ATX_SHIFT_BIAS) |
-                          (abs(s2z) >= ATX_SHIFT_BIAS);
-          const int2 ent = make_int2(t, atx_pack_shift(s2x, s2y, s2z) | (wj & 0x7f000000));
-          if (FILL) {
-            if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
-            list[w++] = ent;
-          } else if (rows && cnt < rows_cap) {
-            if (bad) atomicMax((unsigned long long *)&scal[3], 1ull);
-            rows[(size_t)s * rows_cap + cnt] = ent;
-          }
-          cnt++;
         }
       }
     }
@@ -571,6 +571,8 @@ static Geo make_geo(const atx_neighbors *nl, const atx_particles *p) {
     g.pbc[k] = p->pbc[k];
     g.sten[k] = nl->sten[k];
   }
+  for (int k = 0; k < 3; k++)
+    for (int c = 0; c < 3; c++) g.cvec.m[3 * k + c] = p->Abox.m[3 * k + c] / nl->n_cells[k];
   g.cutoff_sq = nl->cutoff * nl->cutoff;
   return g;
 }

@@ -41,7 +41,8 @@ struct atx_rebo2 {
   PotScratch sc;
   // one-thread-per-bond force kernel (ATX_REBO2_PERBOND=1, experimental): compact list of the bonds
   // each atom is responsible for
-  int per_bond = 0;   // 0 off, 1 / 2 / 3: 4 / 6 / 8 resident blocks per SM
+  int per_bond = 3;   // 0: thread per atom; 1 / 2 / 3 / 4 / 5: thread per bond at 4 / 6 / 8 / 12 / 16 resident blocks
+                      // per SM.  C3 on a B200 (round 2): 1.58 ms per atom, 1.05 / 0.92 / 0.885 ms at 4 / 6 / 8 blocks
   DevBuf<int> own_cnt, own_off;
   DevBuf<int2> own;
   // screened variant (Rebo2Scr): b_cut holds the attractive/repulsive cutoff, b_cbo / b_cnc the
@@ -99,7 +100,7 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
   }
 }
 
-// ---- one thread per bond (experimental, ATX_REBO2_PERBOND=1) ----------------------------------------
+// ---- one thread per bond (default; ATX_REBO2_PERBOND=0 selects thread per atom) ----------------------------------------
 // k_rebo2_force gives every thread the bonds its atom is responsible for: 0 .. 4 in amorphous carbon,
 // 1.9 on average, so a warp waits for its busiest lane (lane utilisation ~ 47 %).  Here the
 // responsible (atom, slot) pairs are compacted first (count, exclusive scan, fill) and every thread
@@ -478,6 +479,8 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
       o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr, pot->own.ptr, o.stop)
     if (pot->per_bond == 2) RB_FORCE_BOND(6);
     else if (pot->per_bond == 3) RB_FORCE_BOND(8);
+    else if (pot->per_bond == 4) RB_FORCE_BOND(12);
+    else if (pot->per_bond == 5) RB_FORCE_BOND(16);
     else RB_FORCE_BOND(4);
 #undef RB_FORCE_BOND
     ATX_LAUNCHED();

@@ -25,6 +25,18 @@ METRICS = [
     'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
     'smsp__inst_executed.sum',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+    'smsp__thread_inst_executed_per_inst_executed.ratio',
+    'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum',
+    'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum',
+    'smsp__sass_thread_inst_executed_op_fadd_pred_on.sum', 'smsp__sass_thread_inst_executed_op_fmul_pred_on.sum',
+    'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum',
+    'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'launch__shared_mem_per_block_static',
+    'launch__occupancy_limit_warps', 'l1tex__data_pipe_lsu_wavefronts.sum', 'lts__t_bytes.sum',
+    'sm__inst_executed_pipe_fp64.sum', 'smsp__inst_executed_op_global_red.sum',
 ]
 
 

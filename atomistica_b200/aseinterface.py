@@ -23,9 +23,11 @@ class Atomistica:
         verlet_shell/2 from where it was at the last build (checked on the device); 0 rebuilds on every
         change of the positions like the reference's Python host.
 
-        zero_copy=True makes get_forces() / results['forces'] a VIEW of one of two alternating
-        page-locked buffers (valid until the call after the next one) instead of a private copy; the
-        default returns copies, like ase.calculators.calculator.Calculator.get_property."""
+        get_forces() / results['forces'] is an array nobody else writes to while the caller holds it
+        (like the copy ase.calculators.calculator.Calculator.get_property returns): the library writes
+        into a page-locked buffer that is only recycled once no outside reference to it (or to a view
+        of it) is left; when more than MAX_FORCE_BUFFERS arrays are held at once the result is copied.
+        zero_copy=True skips that copy as well (the caller then must not keep more arrays than that)."""
         self.device = device
         self.zero_copy = bool(zero_copy)
         self.verlet_shell = float(verlet_shell)
@@ -94,22 +96,36 @@ class Atomistica:
             positions[:, :] = new
             self.particles.I_changed_positions()
 
+    MAX_FORCE_BUFFERS = 8
+
     def _force_buffer(self, nat):
-        """page-locked force buffers reused between calls.  With a single potential the library
-        STORES the forces straight into the buffer (no zeroing, no host accumulation, no copy) and
-        two buffers alternate, so the array returned by one call stays valid during the next."""
+        """page-locked force buffer nobody else holds.  With a single potential the library STORES
+        the forces straight into it (no zeroing, no host accumulation, no copy).  A buffer is reused
+        only when neither it nor a view of it is referenced outside this object (reference counts of
+        the array and of the base that owns its views), so an array handed out by get_forces() is
+        never overwritten while the caller keeps it -- the guarantee a private copy gives, without
+        the copy.  Returns (array, private): private is False when the pool is exhausted and the
+        caller must copy."""
+        import sys
         if self._fbuf is None or self._fbuf[0].array.shape[0] != nat:
-            self._fbuf = [L.PinnedArray((nat, 3)), L.PinnedArray((nat, 3))]
-            self._fcur = 0
-        self._fcur ^= 1
-        return self._fbuf[self._fcur].array
+            self._fbuf = []
+        for pa in self._fbuf:
+            arr = pa.array
+            # attribute + local + argument = 3; the owner of the views: held by `arr` + argument = 2
+            if sys.getrefcount(arr) <= 3 and sys.getrefcount(arr.base) <= 2:
+                return arr, True
+        if len(self._fbuf) < self.MAX_FORCE_BUFFERS:
+            self._fbuf.append(L.PinnedArray((nat, 3)))
+            return self._fbuf[-1].array, True
+        return self._fbuf[0].array, False
 
     # aseinterface.py:355-440
     def calculate(self, atoms, properties=('energy',)):
         self.update(atoms)
         epot = 0.0
         nat = len(self.particles)
-        forces = self._force_buffer(nat)
+        self.results = {}          # drops this object's own reference to the previous force array
+        forces, private = self._force_buffer(nat)
         store = len(self.pots) == 1
         if store != self._store:
             for pot in self.pots:
@@ -136,7 +152,7 @@ class Atomistica:
             if _wpa is not None:
                 wpa = _wpa if wpa is None else wpa + _wpa
         volume = atoms.get_volume()
-        self.results = dict(energy=epot, free_energy=epot, forces=forces if self.zero_copy else forces.copy(),
+        self.results = dict(energy=epot, free_energy=epot, forces=forces if (private or self.zero_copy) else forces.copy(),
                             wpot=wpot)
         self.results['stress'] = np.array([wpot[0, 0], wpot[1, 1], wpot[2, 2], (wpot[1, 2] + wpot[2, 1]) / 2,
                                            (wpot[0, 2] + wpot[2, 0]) / 2, (wpot[0, 1] + wpot[1, 0]) / 2]) / volume

@@ -110,8 +110,10 @@ static bool fail(int rc, int *ierror, const char *where, int line) {
   else c_error_abort(rc);
   return true;
 }
-#define CHK(call, ierror) \
-  if (fail((call), (ierror), __FILE__, __LINE__)) return
+#define CHK(call, ierror)                                       \
+  do {                                                          \
+    if (fail((call), (ierror), __FILE__, __LINE__)) return;     \
+  } while (0)
 #define RAISE(ierror, msg)                                              \
   do {                                                                  \
     c_push_error_with_info((msg), __FILE__, __LINE__, ERROR_UNSPECIFIED); \

@@ -37,7 +37,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 A0, NCELL, TEMP, DT, SKIN = 3.615, 40, 300.0, 1.0, 0.5
 MASS_CU = 63.546
 MASS_SI = 28.0855
-C4_CELLS, C4_SKIN = 128, 0.4
+C4_CELLS, C4_LIST_CUTOFF = 128, 3.7   # list cutoff = r2 + Verlet shell, kept below the 2nd-neighbour shell (3.84 A)
 PRIME_MAX = 160          # upper bound of the untimed priming phase (steps)
 
 
@@ -500,6 +500,15 @@ def block_c2(args, dist, L, ctx):
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get('k_eam_force_dram_bytes_per_launch')
+    fl = flop_counts()
+    fp64_block = None
+    if fl.get('k_eam_force_flops_per_atom'):
+        tf = fl['k_eam_force_flops_per_atom'] * nat / (force_avg_ms * 1e-3) / 1e12
+        step_flops = (fl['k_eam_force_flops_per_atom'] + fl.get('k_eam_density_flops_per_atom', 0.0)) * nat
+        fp64_block = dict(achieved=tf, peak=fp64.value, unit='TFLOP/s', frac=tf / fp64.value,
+                          flops_per_atom=fl['k_eam_force_flops_per_atom'],
+                          whole_step_frac=step_flops / (dev_ms / steps * 1e-3) / 1e12 / fp64.value,
+                          source='ncu instruction counts (profiles/flops.json)')
     out = dict(
         metric='atom-steps/s', value=value, unit='atom-steps/s', n_gpus=world, steps=steps, warmup=warm,
         ms_per_step=dev_ms / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
@@ -514,7 +523,7 @@ def block_c2(args, dist, L, ctx):
                       unit='GB/s', frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                       algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=force_avg_ms, launches=force_n,
                       list_neighbors_per_atom=z_list, share_of_step=force_ms / dev_ms if dev_ms else None,
-                      whole_step_frac=alg_bytes / (dev_ms / steps * 1e-3) / 1e9 / peak),
+                      whole_step_frac=alg_bytes / (dev_ms / steps * 1e-3) / 1e9 / peak, fp64=fp64_block),
         kernels_ms=dict(eam_force=force_ms, eam_density=dens_ms, nl_pairs_count=cnt_ms, nl_pairs_fill=fill_ms,
                         total_device=dev_ms, dd=dd_prof),
         fp64_peak_tflops_measured=fp64.value,
@@ -540,6 +549,7 @@ def block_c4(args, dist, L, ctx):
     fl = flop_counts()
     res = {}
     for kind, a0, rc in (('Tersoff', 5.432, 3.0), ('Kumagai', 5.429, 3.3)):
+        C4_SKIN = C4_LIST_CUTOFF - rc
         pos, v0, ids = c4_slab(a0, n, rank, world)
         cell = np.diag([n * a0] * 3)
         nat, ntot = len(pos), 8 * n ** 3

@@ -1,0 +1,46 @@
+"""Calculator front end (atomistica_b200.aseinterface): result arrays are private to the caller."""
+import numpy as np
+import pytest
+
+import atomistica_b200 as ab
+from atomistica_b200 import structures as S
+
+pytestmark = pytest.mark.gpu
+
+
+def test_forces_are_not_overwritten_while_held():
+    """ase.calculators.calculator.Calculator.get_property returns copies; here the page-locked result
+    buffers are recycled only when the caller dropped them (f_old aliased f_new)"""
+    a = S.diamond('Si', 5.432, (3, 3, 3))
+    a.rattle(0.05, seed=1)
+    calc = ab.Tersoff()
+    held, copies = [], []
+    rng = np.random.RandomState(0)
+    for k in range(12):                       # more than the pool holds: the overflow path copies
+        a.positions += rng.normal(scale=0.01, size=a.positions.shape)
+        f = calc.get_forces(a)
+        calc.get_potential_energy(a)          # an intermediate call must not touch f either
+        held.append(f)
+        copies.append(f.copy())
+    for f, c in zip(held, copies):
+        assert np.array_equal(f, c)
+    view = held[-1][:5]
+    del held, f
+    keep = view.copy()
+    for k in range(20):                       # a VIEW keeps its buffer out of the pool as well
+        a.positions += rng.normal(scale=0.01, size=a.positions.shape)
+        calc.get_forces(a)
+    assert np.array_equal(view, keep)
+    assert len(calc._fbuf) <= calc.MAX_FORCE_BUFFERS
+
+
+def test_stresses_are_voigt_wpot_per_at():
+    """aseinterface.py:438-446: 'stresses' is the Voigt-ordered wpot_per_at, not divided by the volume;
+    its sum is stress * volume"""
+    a = S.diamond('Si', 5.432, (2, 2, 2))
+    a.rattle(0.05, seed=2)
+    calc = ab.Tersoff()
+    s = calc.get_stresses(a)
+    st = calc.get_stress(a)
+    assert s.shape == (len(a), 6)
+    assert np.abs(s.sum(axis=0) - st * a.get_volume()).max() < 1e-9 * max(1.0, np.abs(st * a.get_volume()).max())

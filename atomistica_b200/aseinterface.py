@@ -104,8 +104,8 @@ class Atomistica:
         only when neither it nor a view of it is referenced outside this object (reference counts of
         the array and of the base that owns its views), so an array handed out by get_forces() is
         never overwritten while the caller keeps it -- the guarantee a private copy gives, without
-        the copy.  Returns (array, private): private is False when the pool is exhausted and the
-        caller must copy."""
+        the copy.  When the caller holds every buffer of the pool the result goes into a fresh
+        ordinary array.  Returns (array, private)."""
         import sys
         if self._fbuf is None or self._fbuf[0].array.shape[0] != nat:
             self._fbuf = []
@@ -117,7 +117,8 @@ class Atomistica:
         if len(self._fbuf) < self.MAX_FORCE_BUFFERS:
             self._fbuf.append(L.PinnedArray((nat, 3)))
             return self._fbuf[-1].array, True
-        return self._fbuf[0].array, False
+        # every pooled buffer is held by the caller: a fresh pageable array (slower transfer, still private)
+        return np.zeros((nat, 3)), True
 
     # aseinterface.py:355-440
     def calculate(self, atoms, properties=('energy',)):

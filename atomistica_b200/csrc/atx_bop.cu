@@ -1465,6 +1465,7 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
       ATX_PASS(launch_center_nb<ATX_BOP_BRENNER>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
   }
   if (nat > 0) {
+    ProfScope ps_(ctx, "bop_gather");
     k_bop_gather<<<(nat + 127) / 128, 128, 0, st>>>(nat, nl->seed.ptr, nl->rev.ptr, pot->G.ptr, pe_own,
                                                     o.f, o.epa, o.role, o.stop);
     ATX_LAUNCHED();

@@ -205,9 +205,12 @@ struct atx_ddmd {
   double rebuild_host_ms[8] = {0};       // host wall time per rebuild phase (accumulated)
 };
 
+// inv / pos4 (peer-to-peer step path): the new position also goes straight into the atom's sorted
+// record, so that the refresh pass only has to place the ghosts
 __global__ void k_dd_drift(int nown, double dt, double *__restrict__ r, double *__restrict__ v,
                            const double *__restrict__ f, const double *__restrict__ minv,
-                           DdCtrl *__restrict__ ctrl) {
+                           DdCtrl *__restrict__ ctrl, const int *__restrict__ inv = nullptr,
+                           double4 *__restrict__ pos4 = nullptr) {
   if (ctrl->stop) return;
   __shared__ double red[8];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,7 +220,12 @@ __global__ void k_dd_drift(int nown, double dt, double *__restrict__ r, double *
     double vx = v[3 * i] + a * f[3 * i], vy = v[3 * i + 1] + a * f[3 * i + 1], vz = v[3 * i + 2] + a * f[3 * i + 2];
     v[3 * i] = vx; v[3 * i + 1] = vy; v[3 * i + 2] = vz;
     double dx = vx * dt, dy = vy * dt, dz = vz * dt;
-    r[3 * i] += dx; r[3 * i + 1] += dy; r[3 * i + 2] += dz;
+    const double x = r[3 * i] + dx, y = r[3 * i + 1] + dy, z = r[3 * i + 2] + dz;
+    r[3 * i] = x; r[3 * i + 1] = y; r[3 * i + 2] = z;
+    if (pos4) {
+      double *q = reinterpret_cast<double *>(pos4 + inv[i]);
+      q[0] = x; q[1] = y; q[2] = z;
+    }
     d2 = dx * dx + dy * dy + dz * dz;
   }
   for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
@@ -320,20 +328,18 @@ __global__ void k_dd_wait(const unsigned long long *sig, int P, DdCtrl *ctrl) {
   }
 }
 
-// sorted position records from the owned positions and the receive areas of this step
-__global__ void k_dd_refresh_p2p(int nloc, int n, int ngl, const double *__restrict__ r, const double *recvL,
-                                 const double *recvR, size_t par_stride, const int *__restrict__ order,
-                                 double4 *__restrict__ pos4, const DdCtrl *ctrl) {
+// sorted position records of the ghosts from the receive areas of this step (the owned atoms were
+// placed by the drift); one thread per ghost
+__global__ void k_dd_refresh_p2p(int ng, int n, int ngl, const double *recvL, const double *recvR,
+                                 size_t par_stride, const int *__restrict__ inv, double4 *__restrict__ pos4,
+                                 const DdCtrl *ctrl) {
   if (ctrl->stop) return;
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nloc) return;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
   const size_t par = (size_t)(ctrl->seq & 1ull) * par_stride;
-  int i = order[s];
-  const double *src = i < n ? r + 3 * (size_t)i
-                            : (i < n + ngl ? recvL + par + 3 * (size_t)(i - n) : recvR + par + 3 * (size_t)(i - n - ngl));
-  double4 v = pos4[s];
-  v.x = src[0]; v.y = src[1]; v.z = src[2];
-  pos4[s] = v;
+  const double *src = g < ngl ? recvL + par + 3 * (size_t)g : recvR + par + 3 * (size_t)(g - ngl);
+  double *q = reinterpret_cast<double *>(pos4 + inv[n + g]);
+  q[0] = src[0]; q[1] = src[1]; q[2] = src[2];
 }
 
 __global__ void k_dd_pack(int n, const int *__restrict__ idx, const double *__restrict__ r,
@@ -905,6 +911,7 @@ static int dd_reset_ctrl(atx_ddmd *md) {
 }
 
 static int dd_kick(atx_ddmd *md) {
+  ProfScope ps_(md->ctx, "dd_kick");
   cudaStream_t st = md->ctx->stream;
   int n = md->nown;
   if (n > 0) {
@@ -1140,13 +1147,18 @@ static int dd_enqueue_step(atx_ddmd *md) {
   cudaStream_t st = md->ctx->stream;
   const int n = md->nown, nloc = n + md->ngl + md->ngr;
   const int *stop = &md->ctrl.ptr->stop;
-  if (n > 0) {
-    k_dd_drift<<<(n + 255) / 256, 256, 0, st>>>(n, md->dt, md->r.ptr, md->v.ptr, md->f.ptr, md->minv.ptr,
-                                                md->ctrl.ptr);
-  } else {
-    k_dd_nowish<<<1, 1, 0, st>>>(md->ctrl.ptr);
+  {
+    ProfScope ps_(md->ctx, "dd_drift");
+    if (n > 0) {
+      const bool fuse = dd->nranks > 1 && md->p2p;
+      k_dd_drift<<<(n + 255) / 256, 256, 0, st>>>(n, md->dt, md->r.ptr, md->v.ptr, md->f.ptr, md->minv.ptr,
+                                                  md->ctrl.ptr, fuse ? md->nl->inv.ptr : nullptr,
+                                                  fuse ? md->nl->pos4.ptr : nullptr);
+    } else {
+      k_dd_nowish<<<1, 1, 0, st>>>(md->ctrl.ptr);
+    }
+    ATX_LAUNCHED();
   }
-  ATX_LAUNCHED();
   if (dd->nranks > 1 && md->p2p) {
     const double dL = 1.0 / dd->nranks, dR = -1.0 / dd->nranks;
     const size_t par_stride = 3 * md->capG;
@@ -1165,9 +1177,10 @@ static int dd_enqueue_step(atx_ddmd *md) {
       k_dd_wait<<<1, 32, 0, st>>>((const unsigned long long *)md->mbox, dd->nranks, md->ctrl.ptr);
       ATX_LAUNCHED();
     }
-    if (nloc > 0) {
-      k_dd_refresh_p2p<<<(nloc + 255) / 256, 256, 0, st>>>(nloc, n, md->ngl, md->r.ptr, recvL, recvR, par_stride,
-                                                           md->nl->order.ptr, md->nl->pos4.ptr, md->ctrl.ptr);
+    if (nloc > n) {
+      ProfScope ps_(md->ctx, "dd_refresh");
+      k_dd_refresh_p2p<<<(nloc - n + 255) / 256, 256, 0, st>>>(nloc - n, n, md->ngl, recvL, recvR, par_stride,
+                                                               md->nl->inv.ptr, md->nl->pos4.ptr, md->ctrl.ptr);
       ATX_LAUNCHED();
     }
     ATX_PASS(dd_compute(md, true));

@@ -595,6 +595,7 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nl->initialized && nl->p_rev == p->pos_rev && nl->cell_rev == p->cell_rev) return 0;
 
   const int nat = p->nat;
+  ProfScope ps_build_(ctx, "nl_update");
   if (nl->initialized && nl->verlet_shell > 0.0 && nl->cell_rev == p->cell_rev && nl->p_rev >= 0 &&
       nl->el_rev == p->el_rev && nl->pos_build.cap >= (size_t)nat && nat > 0) {
     // Verlet shell (neighbors.f90:520-560 / python_neighbors.f90:570-600: the list is kept while
@@ -912,6 +913,7 @@ int atx_neighbors_refresh_positions(atx_neighbors *nl, atx_particles *p) {
 
 int atx_neighbors_ensure_rev(atx_neighbors *nl) {
   if (nl->rev_valid) return 0;
+  ProfScope ps_(nl->ctx, "nl_reverse_index");
   ATX_PASS(nl->rev.reserve((size_t)nl->npairs + 1));
   if (nl->nat > 0 && nl->npairs > 0) {
     k_reverse_index<<<(nl->nat + 127) / 128, 128, 0, nl->ctx->stream>>>(nl->nat, nl->seed.ptr,

@@ -37,7 +37,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 A0, NCELL, TEMP, DT, SKIN = 3.615, 40, 300.0, 1.0, 0.5
 MASS_CU = 63.546
 MASS_SI = 28.0855
-C4_CELLS, C4_LIST_CUTOFF = 128, 3.7   # list cutoff = r2 + Verlet shell, kept below the 2nd-neighbour shell (3.84 A)
+C4_CELLS, C4_SKIN = 128, 0.4
 PRIME_MAX = 160          # upper bound of the untimed priming phase (steps)
 
 
@@ -463,7 +463,8 @@ def block_c2(args, dist, L, ctx):
             nl1 = native.Neighbors(200, device=local)
             pot1 = native.TabulatedAlloyEAM(setfl=setfl, device=local)
             return md.VelocityVerlet(pot1, p, nl1, np.full(len(gpos), MASS_CU), gvel, dt=DT, verlet_shell=SKIN)
-        parity = parity_block(dist, drv, e_ss, k_ss, ref_factory, total_steps)
+        if not args.no_parity:
+            parity = parity_block(dist, drv, e_ss, k_ss, ref_factory, total_steps)
     del drv
 
     # ---- e2e: reference-facing calculator API, host buffers, copies inside the timed region
@@ -549,7 +550,8 @@ def block_c4(args, dist, L, ctx):
     fl = flop_counts()
     res = {}
     for kind, a0, rc in (('Tersoff', 5.432, 3.0), ('Kumagai', 5.429, 3.3)):
-        C4_SKIN = C4_LIST_CUTOFF - rc
+        if kind not in args.c4_kinds.split(','):
+            continue
         pos, v0, ids = c4_slab(a0, n, rank, world)
         cell = np.diag([n * a0] * 3)
         nat, ntot = len(pos), 8 * n ** 3
@@ -583,6 +585,9 @@ def block_c4(args, dist, L, ctx):
                    ghost_atoms_rank0=counts[1], gpu_launches=launches,
                    bop_force_ms_per_step_rank0=bop_ms / steps, dd_halo_ms_per_step_rank0=halo_ms / steps,
                    epot_per_atom=epot / ntot)
+        blk['scopes_ms_per_step_rank0'] = {k: prof_read(L, ctx, k)[0] / steps for k in (
+            'bop_force', 'bop_gather', 'dd_drift', 'dd_halo', 'dd_refresh', 'dd_kick', 'nl_update', 'nl_pairs_count',
+            'nl_pairs_fill', 'nl_reverse_index')}
         if world > 1:
             blk['p2p'] = st['p2p']
             blk['rebuild_host_ms_since_create'] = st['rebuild_host_ms']
@@ -613,7 +618,8 @@ def block_c4(args, dist, L, ctx):
                 pot1 = getattr(native, kind)(device=local)
                 return md.VelocityVerlet(pot1, p1, nl1, np.full(len(gpos), MASS_SI), gvel, dt=1.0,
                                          verlet_shell=C4_SKIN)
-            blk['parity'] = parity_block(dist, drv, epot, ekin, ref_factory, primed + 3 + steps)
+            if not args.no_parity:
+                blk['parity'] = parity_block(dist, drv, epot, ekin, ref_factory, primed + 3 + steps)
         res[kind] = blk
         del drv, pot
         dist.barrier()
@@ -849,6 +855,8 @@ def main():
     ap.add_argument('--c4-cells', type=int, default=C4_CELLS)
     ap.add_argument('--c4-steps', type=int, default=60)
     ap.add_argument('--nl-sizes', default='1e4,1e5,1e6,4e6,1.6e7,6.4e7')
+    ap.add_argument('--c4-kinds', default='Tersoff,Kumagai')
+    ap.add_argument('--no-parity', action='store_true', help='skip the single-GPU parity runs at N > 1 (diagnostics)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -156,3 +156,22 @@ def test_c_example_on_the_gpu(tmp_path):
     assert 'max |f|' in lines[2]
     fsum = [abs(float(x)) for x in lines[2].split('sum f =')[1].split()]
     assert max(fsum) < 1e-9
+
+
+def test_fortran_interfaces_cover_the_whole_c_abi():
+    """atomistica_b200/fortran/atx_c_api.f90 is generated from the header (scripts/gen_fortran_api.py):
+    it is current, and every exported symbol has a bind(C) interface with as many dummy arguments as the C
+    prototype has parameters"""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location('gen_fortran_api', os.path.join(ROOT, 'scripts', 'gen_fortran_api.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, protos = gen.generate()
+    assert open(gen.OUT).read() == text, 'run scripts/gen_fortran_api.py'
+    assert {name for _, name, _ in protos} == set(L.SYMBOLS)
+    for ret, name, args in protos:
+        m = re.search(r'function %s\(([^)]*)\)' % name, text)
+        assert m, name
+        dummies = [a for a in m.group(1).split(',') if a.strip()]
+        assert len(dummies) == len(args), name

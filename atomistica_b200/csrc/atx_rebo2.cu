@@ -35,6 +35,7 @@ struct atx_rebo2 {
   DevBuf<int> b_cnt, b_nb, b_typ, b_shift, b_slot;
   DevBuf<double4> b_vec;   // rnx, rny, rnz, rl
   DevBuf<double2> b_cut;   // fc, dfc
+  DevBuf<RbBond> b_tab;    // unscreened path: the same fields as one 64-byte record per bond
   DevBuf<double2> nn;      // nn(C), nn(H)
   DevBuf<double> epb, fpb, wpb, epa_out;
   DevBuf<int> flag;
@@ -59,15 +60,13 @@ struct atx_rebo2 {
 
 __global__ void k_rebo2_bonds(int nat, int nbs, Mat3 A, Rebo2Dev P, const double4 *__restrict__ pos4,
                               const long long *__restrict__ seed, const int2 *__restrict__ list,
-                              int *__restrict__ b_cnt, int *__restrict__ b_nb, int *__restrict__ b_typ,
-                              int *__restrict__ b_shift, int *__restrict__ b_slot,
-                              double4 *__restrict__ b_vec, double2 *__restrict__ b_cut,
+                              int *__restrict__ b_cnt, RbBond *__restrict__ b_tab,
                               double2 *__restrict__ nn, int *__restrict__ flag,
                               const int *__restrict__ stop) {
   if (stop && *stop) return;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nat) return;
-  rb_bonds_atom(nbs, A, P, pos4, seed, list, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, flag, s);
+  rb_bonds_atom(nbs, A, P, pos4, seed, list, b_cnt, b_tab, nn, flag, s);
 }
 
 // ---- kernel 2: energies and forces ------------------------------------------------------------
@@ -76,9 +75,7 @@ __global__ void k_rebo2_bonds(int nat, int nbs, Mat3 A, Rebo2Dev P, const double
 
 __global__ void __launch_bounds__(RB_BLOCK)
 k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
-              const int *__restrict__ b_cnt, const int *__restrict__ b_nb, const int *__restrict__ b_typ,
-              const int *__restrict__ b_shift, const int *__restrict__ b_slot,
-              const double4 *__restrict__ b_vec, const double2 *__restrict__ b_cut,
+              const int *__restrict__ b_cnt, const RbBond *__restrict__ b_tab,
               const double2 *__restrict__ nn, const double4 *__restrict__ pos4,
               const int *__restrict__ order, double *__restrict__ f,
               double *__restrict__ epa, double *__restrict__ wpa, double *__restrict__ epb,
@@ -91,7 +88,7 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
 
-  rb_force_atom(nat, nbs, P, seed, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, pos4, order, f, epa,
+  rb_force_atom(nat, nbs, P, seed, b_cnt, b_tab, nn, pos4, order, f, epa,
                 wpa, epb, fpb, wpb, i, acc);
   atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
   if (threadIdx.x == 0) {
@@ -107,26 +104,24 @@ k_rebo2_force(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
 // evaluates exactly one bond with the same per-atom source (rb_force_atom<ROLES, ONE>).
 
 __global__ void k_rebo2_own_count(int nat, int nbs, Rebo2Dev P, const int *__restrict__ b_cnt,
-                                  const int *__restrict__ b_nb, const int *__restrict__ b_typ,
-                                  const int *__restrict__ b_shift, const double4 *__restrict__ b_vec,
+                                  const RbBond *__restrict__ b_tab,
                                   const double4 *__restrict__ pos4, const int *__restrict__ order,
                                   int *__restrict__ cnt, const int *__restrict__ stop) {
   if (stop && *stop) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nat) return;
-  cnt[s] = s < nat ? rb_owned_bonds(nbs, P, b_cnt, b_nb, b_typ, b_shift, b_vec, pos4, order, s, nullptr) : 0;
+  cnt[s] = s < nat ? rb_owned_bonds(nbs, P, b_cnt, b_tab, pos4, order, s, nullptr) : 0;
 }
 
 __global__ void k_rebo2_own_fill(int nat, int nbs, Rebo2Dev P, const int *__restrict__ b_cnt,
-                                 const int *__restrict__ b_nb, const int *__restrict__ b_typ,
-                                 const int *__restrict__ b_shift, const double4 *__restrict__ b_vec,
+                                 const RbBond *__restrict__ b_tab,
                                  const double4 *__restrict__ pos4, const int *__restrict__ order,
                                  const int *__restrict__ off, int2 *__restrict__ own,
                                  const int *__restrict__ stop) {
   if (stop && *stop) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nat) return;
-  rb_owned_bonds(nbs, P, b_cnt, b_nb, b_typ, b_shift, b_vec, pos4, order, s, own + off[s]);
+  rb_owned_bonds(nbs, P, b_cnt, b_tab, pos4, order, s, own + off[s]);
 }
 
 // MINB: resident blocks per SM asked from the register allocator (4: 255 registers, 6: 170, 8: 128 with
@@ -134,9 +129,7 @@ __global__ void k_rebo2_own_fill(int nat, int nbs, Rebo2Dev P, const int *__rest
 template <int MINB>
 __global__ void __launch_bounds__(RB_BLOCK, MINB)
 k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
-                   const int *__restrict__ b_cnt, const int *__restrict__ b_nb, const int *__restrict__ b_typ,
-                   const int *__restrict__ b_shift, const int *__restrict__ b_slot,
-                   const double4 *__restrict__ b_vec, const double2 *__restrict__ b_cut,
+                   const int *__restrict__ b_cnt, const RbBond *__restrict__ b_tab,
                    const double2 *__restrict__ nn, const double4 *__restrict__ pos4,
                    const int *__restrict__ order, double *__restrict__ f, double *__restrict__ epa,
                    double *__restrict__ wpa, double *__restrict__ epb, double *__restrict__ fpb,
@@ -150,7 +143,7 @@ k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ s
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   if (t < off[nat]) {
     const int2 e = own[t];
-    rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, pos4, order,
+    rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt, b_tab, nn, pos4, order,
                                f, epa, wpa, epb, fpb, wpb, e.x, acc, nullptr, e.y);
   }
   atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
@@ -164,10 +157,7 @@ k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ s
 // its owned ends only, then the ghost rows are cleared (see rb_force_atom<ROLES>).
 __global__ void __launch_bounds__(RB_BLOCK)
 k_rebo2_force_roles(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
-                    const int *__restrict__ b_cnt, const int *__restrict__ b_nb,
-                    const int *__restrict__ b_typ, const int *__restrict__ b_shift,
-                    const int *__restrict__ b_slot, const double4 *__restrict__ b_vec,
-                    const double2 *__restrict__ b_cut, const double2 *__restrict__ nn,
+                    const int *__restrict__ b_cnt, const RbBond *__restrict__ b_tab, const double2 *__restrict__ nn,
                     const double4 *__restrict__ pos4, const int *__restrict__ order,
                     double *__restrict__ f, double *__restrict__ epa, double *__restrict__ wpa,
                     double *__restrict__ partials, const unsigned char *__restrict__ role,
@@ -178,7 +168,7 @@ k_rebo2_force_roles(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ 
   double acc[ATX_NSUM];
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
-  rb_force_atom<true>(nat, nbs, P, seed, b_cnt, b_nb, b_typ, b_shift, b_slot, b_vec, b_cut, nn, pos4, order, f,
+  rb_force_atom<true>(nat, nbs, P, seed, b_cnt, b_tab, nn, pos4, order, f,
                       epa, wpa, nullptr, nullptr, nullptr, i, acc, role);
   atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
   if (threadIdx.x == 0) {
@@ -420,12 +410,7 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
   pot->nbs = nbs;
   size_t nt = (size_t)nat * nbs + 1;
   ATX_PASS(pot->b_cnt.reserve(nat + 1));
-  ATX_PASS(pot->b_nb.reserve(nt));
-  ATX_PASS(pot->b_typ.reserve(nt));
-  ATX_PASS(pot->b_shift.reserve(nt));
-  ATX_PASS(pot->b_slot.reserve(nt));
-  ATX_PASS(pot->b_vec.reserve(nt));
-  ATX_PASS(pot->b_cut.reserve(nt));
+  ATX_PASS(pot->b_tab.reserve(nt));
   ATX_PASS(pot->nn.reserve(nat + 1));
   int nblocks = (nat + RB_BLOCK - 1) / RB_BLOCK;
   if (nblocks < 1) nblocks = 1;
@@ -439,16 +424,14 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
     ProfScope ps_(ctx, "rebo2_bonds");
     k_rebo2_bonds<<<(nat + 127) / 128, 128, 0, st>>>(nat, nbs, p->Abox, pot->dev, nl->pos4.ptr,
                                                      nl->seed.ptr, nl->list.ptr, pot->b_cnt.ptr,
-                                                     pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
-                                                     pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr,
+                                                     pot->b_tab.ptr,
                                                      pot->nn.ptr, pot->flag.ptr, o.stop);
     ATX_LAUNCHED();
   }
   if (o.role) {
     ProfScope ps_(ctx, "rebo2_force");
     k_rebo2_force_roles<<<nblocks, RB_BLOCK, 0, st>>>(
-        nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
-        pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,
+        nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_tab.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,
         o.wpa, pot->sc.partials.ptr, o.role, o.stop);
     ATX_LAUNCHED();
     k_rebo2_clear_ghosts<<<(nat + 127) / 128, 128, 0, st>>>(nat, o.role, o.f, o.epa, o.wpa, o.stop);
@@ -462,20 +445,17 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
     ATX_PASS(pot->own_off.reserve(nat + 2));
     ATX_PASS(pot->own.reserve(bound + 1));
     ATX_PASS(pot->sc.partials.reserve((size_t)nbb * ATX_NSUM));
-    k_rebo2_own_count<<<(nat + 1 + 127) / 128, 128, 0, st>>>(nat, nbs, pot->dev, pot->b_cnt.ptr, pot->b_nb.ptr,
-                                                             pot->b_typ.ptr, pot->b_shift.ptr, pot->b_vec.ptr,
+    k_rebo2_own_count<<<(nat + 1 + 127) / 128, 128, 0, st>>>(nat, nbs, pot->dev, pot->b_cnt.ptr, pot->b_tab.ptr,
                                                              nl->pos4.ptr, nl->order.ptr, pot->own_cnt.ptr, o.stop);
     ATX_LAUNCHED();
     ATX_PASS(atx_scan_int(ctx, pot->own_cnt.ptr, pot->own_off.ptr, (size_t)nat + 1));
-    k_rebo2_own_fill<<<(nat + 127) / 128, 128, 0, st>>>(nat, nbs, pot->dev, pot->b_cnt.ptr, pot->b_nb.ptr,
-                                                        pot->b_typ.ptr, pot->b_shift.ptr, pot->b_vec.ptr,
+    k_rebo2_own_fill<<<(nat + 127) / 128, 128, 0, st>>>(nat, nbs, pot->dev, pot->b_cnt.ptr, pot->b_tab.ptr,
                                                         nl->pos4.ptr, nl->order.ptr, pot->own_off.ptr, pot->own.ptr,
                                                         o.stop);
     ATX_LAUNCHED();
 #define RB_FORCE_BOND(MINB)                                                                                   \
   k_rebo2_force_bond<MINB><<<nbb, RB_BLOCK, 0, st>>>(                                                         \
-      nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,      \
-      pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,  \
+      nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_tab.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,  \
       o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr, pot->own.ptr, o.stop)
     if (pot->per_bond == 2) RB_FORCE_BOND(6);
     else if (pot->per_bond == 3) RB_FORCE_BOND(8);
@@ -489,8 +469,7 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
   } else {
     ProfScope ps_(ctx, "rebo2_force");
     k_rebo2_force<<<nblocks, RB_BLOCK, 0, st>>>(nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr,
-                                                pot->b_nb.ptr, pot->b_typ.ptr, pot->b_shift.ptr,
-                                                pot->b_slot.ptr, pot->b_vec.ptr, pot->b_cut.ptr,
+                                                pot->b_tab.ptr,
                                                 pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa, o.wpa, epb, fpb,
                                                 wpb, pot->sc.partials.ptr, o.stop);
     ATX_LAUNCHED();

@@ -5,6 +5,18 @@
 
 #include "atx_rebo2_func.cuh"
 
+// One entry of the per-atom bond table (unscreened REBO2): 64 bytes, one cache line pair per bond
+// instead of six separate arrays (the force pass walks the tables of i, j and of their neighbours;
+// ncu, round 2: long-scoreboard stalls dominate k_rebo2_force_bond, L1 hit rate 37 %)
+struct __align__(16) RbBond {
+  double4 vec;   // unit vector i -> j and bond length
+  double2 cut;   // cutoff function and its derivative
+  int nb;        // neighbour (sorted numbering)
+  int typ;       // pair type
+  int shift;     // packed periodic shift
+  int slot;      // position in the atom's range of the pair list
+};
+
 __device__ __forceinline__ void rb_add3(double *f, int at, double x, double y, double z) {
   RBS_ADD(&f[3 * (size_t)at], x);
   RBS_ADD(&f[3 * (size_t)at + 1], y);
@@ -24,9 +36,7 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
                                               const double4 *__restrict__ pos4,
                                               const long long *__restrict__ seed,
                                               const int2 *__restrict__ list, int *__restrict__ b_cnt,
-                                              int *__restrict__ b_nb, int *__restrict__ b_typ,
-                                              int *__restrict__ b_shift, int *__restrict__ b_slot,
-                                              double4 *__restrict__ b_vec, double2 *__restrict__ b_cut,
+                                              RbBond *__restrict__ b_tab,
                                               double2 *__restrict__ nn, int *__restrict__ flag, int s) {
   double4 pi = pos4[s];
   int ti = P.el2typ[(int)pi.w];
@@ -71,12 +81,12 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
         continue;
       if (nb >= nbs || nb >= RB_NBL) { RBS_OR(flag, 1); break; }
       size_t q = (size_t)s * nbs + nb;
-      b_nb[q] = en.x;
-      b_typ[q] = ijpot;
-      b_shift[q] = en.y;
-      b_slot[q] = (int)(a - b0);
-      b_vec[q] = make_double4(dx / rl, dy / rl, dz / rl, rl);
-      b_cut[q] = make_double2(fc, dfc);
+      b_tab[q].nb = en.x;
+      b_tab[q].typ = ijpot;
+      b_tab[q].shift = en.y;
+      b_tab[q].slot = (int)(a - b0);
+      b_tab[q].vec = make_double4(dx / rl, dy / rl, dz / rl, rl);
+      b_tab[q].cut = make_double2(fc, dfc);
       if (tj == RB_C) nC += fc; else nH += fc;
       nb++;
     }
@@ -95,11 +105,7 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
 template <bool ROLES = false, bool ONE = false>
 __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &P,
                                               const long long *__restrict__ seed,
-                                              const int *__restrict__ b_cnt, const int *__restrict__ b_nb,
-                                              const int *__restrict__ b_typ, const int *__restrict__ b_shift,
-                                              const int *__restrict__ b_slot,
-                                              const double4 *__restrict__ b_vec,
-                                              const double2 *__restrict__ b_cut,
+                                              const int *__restrict__ b_cnt, const RbBond *__restrict__ b_tab,
                                               const double2 *__restrict__ nn,
                                               const double4 *__restrict__ pos4,
                                               const int *__restrict__ order, double *__restrict__ f,
@@ -117,12 +123,12 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
     double fxik[RB_NBL], dncx[RB_NBL];  // fconj(x_ik), fcik * dfconj/dx
     double nconjit = 0.0;
     for (int ik = 0; ik < nbi; ik++) {
-      int k = b_nb[qi + ik];
+      int k = b_tab[qi + ik].nb;
       int tk = P.el2typ[(int)pos4[k].w];
       fxik[ik] = 0.0;
       dncx[ik] = 0.0;
       if (tk == RB_C) {
-        double2 ck = b_cut[qi + ik];
+        double2 ck = b_tab[qi + ik].cut;
         double2 nk = nn[k];
         double xik = nk.x + nk.y - ck.x, dfx;
         rb_fconj(xik, fxik[ik], dfx);
@@ -133,24 +139,24 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
     const double2 nni = nn[i];
 
     for (int ij = ONE ? ij0 : 0; ij < (ONE ? ij0 + 1 : nbi); ij++) {
-      const int j = b_nb[qi + ij];
+      const int j = b_tab[qi + ij].nb;
       int jsx, jsy, jsz;
-      atx_unpack_shift(b_shift[qi + ij], jsx, jsy, jsz);
+      atx_unpack_shift(b_tab[qi + ij].shift, jsx, jsy, jsz);
       // j_gt_i (:1332): lexicographic sign of the shift, then index
       const bool zero = (jsx == 0 && jsy == 0 && jsz == 0);
       const bool pos = jsx != 0 ? jsx > 0 : (jsy != 0 ? jsy > 0 : jsz > 0);
       // the index comparison is made in ORIGINAL atom numbering so that per-bond outputs land in
       // the same list slot as in the reference
       if (!((zero && order[j] > order[i]) || pos)) continue;
-      const int ijpot = b_typ[qi + ij];
-      const double4 vij = b_vec[qi + ij];
+      const int ijpot = b_tab[qi + ij].typ;
+      const double4 vij = b_tab[qi + ij].vec;
       const double rlij = vij.w;
       if (!(rlij < P.cut_h[ijpot])) continue;
       const int ktypj = P.el2typ[(int)pos4[j].w];
       const double rlijr = 1.0 / rlij;
       const double nx = vij.x, ny = vij.y, nz = vij.z;
       const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
-      const double2 cij = b_cut[qi + ij];
+      const double2 cij = b_tab[qi + ij].cut;
       const double fcarij = cij.x, dfcarijr = cij.y;
       const double2 nnj = nn[j];
       double niC = nni.x, niH = nni.y, njC = nnj.x, njH = nnj.y;
@@ -175,13 +181,13 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
 
       // ---- ik_loop2 (:1407-1587)
       for (int ik = 0; ik < nbi; ik++) {
-        const double2 cik = b_cut[qi + ik];
+        const double2 cik = b_tab[qi + ik].cut;
         if (ik == ij) {
           nconji = nconjit - cik.x * fxik[ik];
           continue;
         }
-        const int ikpot = b_typ[qi + ik];
-        const double4 vik = b_vec[qi + ik];
+        const int ikpot = b_tab[qi + ik].typ;
+        const double4 vik = b_tab[qi + ik].vec;
         const double rlik = vik.w;
         if (!(rlik < P.cut_h[ikpot])) {
           dbk[ik][0] = dbk[ik][1] = dbk[ik][2] = 0.0;
@@ -239,17 +245,17 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       for (int jl = 0; jl < nbj; jl++) {
         fxjl[jl] = 0.0; dnlx[jl] = 0.0;
         dbl[jl][0] = dbl[jl][1] = dbl[jl][2] = 0.0;
-        const int l = b_nb[qj + jl];
+        const int l = b_tab[qj + jl].nb;
         int lsx, lsy, lsz;
-        atx_unpack_shift(b_shift[qj + jl], lsx, lsy, lsz);
+        atx_unpack_shift(b_tab[qj + jl].shift, lsx, lsy, lsz);
         lsx += jsx; lsy += jsy; lsz += jsz;
         if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;   // l_neq_i
         const int ktypl = P.el2typ[(int)pos4[l].w];
-        const int jlpot = b_typ[qj + jl];
-        const double4 vjl = b_vec[qj + jl];
+        const int jlpot = b_tab[qj + jl].typ;
+        const double4 vjl = b_tab[qj + jl].vec;
         const double rljl = vjl.w;
         const double lx = vjl.x, ly = vjl.y, lz = vjl.z;
-        const double2 cjl = b_cut[qj + jl];
+        const double2 cjl = b_tab[qj + jl].cut;
         const double fcjl = cjl.x, dfcjlr = cjl.y;
         if (ktypl == RB_C) {
           double2 nl_ = nn[l];
@@ -313,25 +319,25 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
         if (tij != 0) {
           for (int ik = 0; ik < nbi; ik++) {
             if (ik == ij) continue;
-            const int k = b_nb[qi + ik];
+            const int k = b_tab[qi + ik].nb;
             int ksx, ksy, ksz;
-            atx_unpack_shift(b_shift[qi + ik], ksx, ksy, ksz);
-            const double4 vik = b_vec[qi + ik];
+            atx_unpack_shift(b_tab[qi + ik].shift, ksx, ksy, ksz);
+            const double4 vik = b_tab[qi + ik].vec;
             const double rlik = vik.w, kx = vik.x, ky = vik.y, kz = vik.z;
-            const double2 cik = b_cut[qi + ik];
+            const double2 cik = b_tab[qi + ik].cut;
             const double fcik = cik.x, dfcikr = cik.y;
             const double dot_ij_ik = nx * kx + ny * ky + nz * kz;
             const double dcik = 1.0 - dot_ij_ik * dot_ij_ik;
             for (int jl = 0; jl < nbj; jl++) {
-              const int l = b_nb[qj + jl];
+              const int l = b_tab[qj + jl].nb;
               int lsx, lsy, lsz;
-              atx_unpack_shift(b_shift[qj + jl], lsx, lsy, lsz);
+              atx_unpack_shift(b_tab[qj + jl].shift, lsx, lsy, lsz);
               lsx += jsx; lsy += jsy; lsz += jsz;
               if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;
               if (l == k && lsx == ksx && lsy == ksy && lsz == ksz) continue;
-              const double4 vjl = b_vec[qj + jl];
+              const double4 vjl = b_tab[qj + jl].vec;
               const double rljl = vjl.w, lx = vjl.x, ly = vjl.y, lz = vjl.z;
-              const double2 cjl = b_cut[qj + jl];
+              const double2 cjl = b_tab[qj + jl].cut;
               const double fcjl = cjl.x, dfcjlr = cjl.y;
               const double dot_ij_jl = nx * lx + ny * ly + nz * lz;
               const double dot_ik_jl = kx * lx + ky * ly + kz * lz;
@@ -385,10 +391,10 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       // ---- forces through N_i, N^conj_i on the neighbours k of i and their neighbours m (:2433-2470)
       for (int ik = 0; ik < nbi; ik++) {
         if (ik == ij) continue;
-        const int k = b_nb[qi + ik];
+        const int k = b_tab[qi + ik].nb;
         const int tk = P.el2typ[(int)pos4[k].w];
-        const double4 vik = b_vec[qi + ik];
-        const double2 cik = b_cut[qi + ik];
+        const double4 vik = b_tab[qi + ik].vec;
+        const double2 cik = b_tab[qi + ik].cut;
         // dnidk(:, ikc, type) = rnik*dfcikr for the type of k, 0 for the other type
         const double sC = (tk == RB_C) ? cik.y : 0.0, sH = (tk == RB_H) ? cik.y : 0.0;
         const double dncdk = fxik[ik] * cik.y;  // dncnidk = nconjdr * rnik (0 unless k is C)
@@ -399,16 +405,16 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
         rb_outer(wij, -1.0, vik.w * vik.x, vik.w * vik.y, vik.w * vik.z, dx_, dy_, dz_);
         if (tk == RB_C && dfdncni * dncx[ik] != 0.0) {
           int ksx, ksy, ksz;
-          atx_unpack_shift(b_shift[qi + ik], ksx, ksy, ksz);
+          atx_unpack_shift(b_tab[qi + ik].shift, ksx, ksy, ksz);
           const size_t qk = (size_t)k * nbs;
           const int nbk = b_cnt[k];
           for (int km = 0; km < nbk; km++) {
-            const int m = b_nb[qk + km];
+            const int m = b_tab[qk + km].nb;
             int msx, msy, msz;
-            atx_unpack_shift(b_shift[qk + km], msx, msy, msz);
+            atx_unpack_shift(b_tab[qk + km].shift, msx, msy, msz);
             if (m == i && msx + ksx == 0 && msy + ksy == 0 && msz + ksz == 0) continue;
-            const double4 vkm = b_vec[qk + km];
-            const double c = -dfdncni * dncx[ik] * b_cut[qk + km].y;
+            const double4 vkm = b_tab[qk + km].vec;
+            const double c = -dfdncni * dncx[ik] * b_tab[qk + km].cut.y;
             const double mx = c * vkm.x, my = c * vkm.y, mz = c * vkm.z;
             rb_add3(f, m, mx, my, mz);
             fkx -= mx; fky -= my; fkz -= mz;
@@ -421,14 +427,14 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       }
       // ---- same on the j side (:2472-2517)
       for (int jl = 0; jl < nbj; jl++) {
-        const int l = b_nb[qj + jl];
+        const int l = b_tab[qj + jl].nb;
         int lsx, lsy, lsz;
-        atx_unpack_shift(b_shift[qj + jl], lsx, lsy, lsz);
+        atx_unpack_shift(b_tab[qj + jl].shift, lsx, lsy, lsz);
         lsx += jsx; lsy += jsy; lsz += jsz;
         if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;
         const int tl = P.el2typ[(int)pos4[l].w];
-        const double4 vjl = b_vec[qj + jl];
-        const double2 cjl = b_cut[qj + jl];
+        const double4 vjl = b_tab[qj + jl].vec;
+        const double2 cjl = b_tab[qj + jl].cut;
         const double sC = (tl == RB_C) ? cjl.y : 0.0, sH = (tl == RB_H) ? cjl.y : 0.0;
         const double dncdl = fxjl[jl] * cjl.y;
         const double pref = -(dfdnj * (sC + sH) + dfdncnj * dncdl) - dfbji * (dpdncj * sC + dpdnhj * sH);
@@ -440,13 +446,13 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
           const size_t ql = (size_t)l * nbs;
           const int nbl = b_cnt[l];
           for (int ln = 0; ln < nbl; ln++) {
-            const int n = b_nb[ql + ln];
+            const int n = b_tab[ql + ln].nb;
             int nsx, nsy, nsz;
-            atx_unpack_shift(b_shift[ql + ln], nsx, nsy, nsz);
+            atx_unpack_shift(b_tab[ql + ln].shift, nsx, nsy, nsz);
             // n /= j .or. ndc /= jdc with ndc = ldc + dcell(ln)
             if (n == j && nsx + lsx == jsx && nsy + lsy == jsy && nsz + lsz == jsz) continue;
-            const double4 vln = b_vec[ql + ln];
-            const double c = -dfdncnj * dnlx[jl] * b_cut[ql + ln].y;
+            const double4 vln = b_tab[ql + ln].vec;
+            const double c = -dfdncnj * dnlx[jl] * b_tab[ql + ln].cut.y;
             const double mx = c * vln.x, my = c * vln.y, mz = c * vln.z;
             rb_add3(f, n, mx, my, mz);
             flx -= mx; fly -= my; flz -= mz;
@@ -482,7 +488,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       rb_add3(f, j, fjx, fjy, fjz);
 #pragma unroll
       for (int q = 0; q < 9; q++) acc[1 + q] += ROLES ? wown * wij[q] : wij[q];
-      const long long a = seed[i] + b_slot[qi + ij];
+      const long long a = seed[i] + b_tab[qi + ij].slot;
       if (epb) epb[a] = 2 * hlfvij;
       if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
       if (wpb) {
@@ -505,9 +511,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
 // skip (j_gt_i in original numbering, bop_kernel_rebo2.f90:1332, and rlij < cut_h).  Returns their
 // number and writes (i, slot) pairs to `out` when it is given.
 __device__ __forceinline__ int rb_owned_bonds(int nbs, const Rebo2Dev &P, const int *__restrict__ b_cnt,
-                                              const int *__restrict__ b_nb, const int *__restrict__ b_typ,
-                                              const int *__restrict__ b_shift,
-                                              const double4 *__restrict__ b_vec,
+                                              const RbBond *__restrict__ b_tab,
                                               const double4 *__restrict__ pos4,
                                               const int *__restrict__ order, int i, int2 *out) {
   const int ktypi = P.el2typ[(int)pos4[i].w];
@@ -515,13 +519,13 @@ __device__ __forceinline__ int rb_owned_bonds(int nbs, const Rebo2Dev &P, const 
   const size_t qi = (size_t)i * nbs;
   int n = 0;
   for (int ij = 0; ij < nbi; ij++) {
-    const int j = b_nb[qi + ij];
+    const int j = b_tab[qi + ij].nb;
     int jsx, jsy, jsz;
-    atx_unpack_shift(b_shift[qi + ij], jsx, jsy, jsz);
+    atx_unpack_shift(b_tab[qi + ij].shift, jsx, jsy, jsz);
     const bool zero = (jsx == 0 && jsy == 0 && jsz == 0);
     const bool pos = jsx != 0 ? jsx > 0 : (jsy != 0 ? jsy > 0 : jsz > 0);
     if (!((zero && order[j] > order[i]) || pos)) continue;
-    if (!(b_vec[qi + ij].w < P.cut_h[b_typ[qi + ij]])) continue;
+    if (!(b_tab[qi + ij].vec.w < P.cut_h[b_tab[qi + ij].typ])) continue;
     if (out) out[n] = make_int2(i, ij);
     n++;
   }

@@ -9,6 +9,7 @@
 #define __device__
 #define __forceinline__ inline
 #define __ldg(p) (*(p))
+#define __align__(n) alignas(n)
 
 struct double2 { double x, y; };
 struct double4 { double x, y, z, w; };

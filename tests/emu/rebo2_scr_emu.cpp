@@ -81,21 +81,19 @@ extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat
   const int2 *list = reinterpret_cast<const int2 *>(list_);
   if (nbs > RB_NBL) nbs = RB_NBL;
   const size_t nt = (size_t)nat * nbs + 1;
-  std::vector<int> b_cnt(nat + 1), b_nb(nt), b_typ(nt), b_shift(nt), b_slot(nt);
-  std::vector<double4> b_vec(nt);
-  std::vector<double2> b_cut(nt), nn(nat + 1);
+  std::vector<int> b_cnt(nat + 1);
+  std::vector<RbBond> b_tab(nt);
+  std::vector<double2> nn(nat + 1);
   int flag = 0;
   for (int s = 0; s < nat; s++)
-    rb_bonds_atom(nbs, A, P, pos4, seed, list, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(),
-                  b_slot.data(), b_vec.data(), b_cut.data(), nn.data(), &flag, s);
+    rb_bonds_atom(nbs, A, P, pos4, seed, list, b_cnt.data(), b_tab.data(), nn.data(), &flag, s);
   if (flag) return flag;
   double acc[RBS_NSUM];
   for (int k = 0; k < RBS_NSUM; k++) acc[k] = 0.0;
   if (role) {
     // k_rebo2_force_roles + k_rebo2_clear_ghosts
     for (int i = 0; i < nat; i++)
-      rb_force_atom<true>(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(),
-                          b_slot.data(), b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, nullptr,
+      rb_force_atom<true>(nat, nbs, P, seed, b_cnt.data(), b_tab.data(), nn.data(), pos4, order, f, epa, wpa, nullptr,
                           nullptr, nullptr, i, acc, role);
     for (int s = 0; s < nat; s++) {
       if (role[s] >= 2) continue;
@@ -107,22 +105,20 @@ extern "C" int emu_rebo2(const atx_rebo2_params *par, const int *el2typ, int nat
   } else if (per_bond) {
     std::vector<int> cnt(nat + 1, 0), off(nat + 2, 0);
     for (int s = 0; s < nat; s++)
-      cnt[s] = rb_owned_bonds(nbs, P, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_vec.data(), pos4,
+      cnt[s] = rb_owned_bonds(nbs, P, b_cnt.data(), b_tab.data(), pos4,
                               order, s, nullptr);
     for (int s = 0; s <= nat; s++) off[s + 1] = off[s] + cnt[s];     // exclusive scan over nat + 1 inputs
     std::vector<int2> own(off[nat] + 1);
     if ((size_t)off[nat] > (size_t)nat * nbs / 2 + 1) return -7;      // the bound the host code sizes with
     for (int s = 0; s < nat; s++)
-      rb_owned_bonds(nbs, P, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_vec.data(), pos4, order, s,
+      rb_owned_bonds(nbs, P, b_cnt.data(), b_tab.data(), pos4, order, s,
                      own.data() + off[s]);
     for (int t = 0; t < off[nat]; t++)
-      rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(),
-                                 b_slot.data(), b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, epb,
+      rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt.data(), b_tab.data(), nn.data(), pos4, order, f, epa, wpa, epb,
                                  fpb, wpb, own[t].x, acc, nullptr, own[t].y);
   } else {
     for (int i = 0; i < nat; i++)
-      rb_force_atom(nat, nbs, P, seed, b_cnt.data(), b_nb.data(), b_typ.data(), b_shift.data(), b_slot.data(),
-                    b_vec.data(), b_cut.data(), nn.data(), pos4, order, f, epa, wpa, epb, fpb, wpb, i, acc);
+      rb_force_atom(nat, nbs, P, seed, b_cnt.data(), b_tab.data(), nn.data(), pos4, order, f, epa, wpa, epb, fpb, wpb, i, acc);
   }
   for (int k = 0; k < RBS_NSUM; k++) sums[k] = acc[k];
   return 0;

@@ -1418,7 +1418,9 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
   ATX_PASS(pot->sc.partials.reserve((size_t)ntot * ATX_NSUM));
   ATX_PASS(pot->queue.reserve((size_t)nat + 1));
   if (!o.stop) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr, 0, sizeof(int), st));
-  if (!o.stop && (pot->nb_cap == 0 || pot->sized_nl != nl || pot->sized_build != nl->nbuilds)) {
+  // (re-evaluated at the first call and then at every 16th list build: atoms that outgrow the chosen
+  // depth in between are handled by the queued pass, so a stale depth costs time, never correctness)
+  if (!o.stop && (pot->nb_cap == 0 || pot->sized_nl != nl || nl->nbuilds - pot->sized_build >= 16)) {
     // host-synchronous call (library mode, MD start, after every list rebuild): pick the bond-table
     // depth from the histogram of bonds per atom.  Atoms beyond it (or that gain bonds while the
     // list is reused) go through the queued pass, so the depth only has to fit the typical atom.

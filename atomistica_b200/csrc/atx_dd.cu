@@ -540,7 +540,7 @@ static void swapbuf(DevBuf<T> &a, DevBuf<T> &b) {
 }
 
 // stable selection of the indices i < n with flags[i] != 0 into out; the count lands in
-// md->cnt[8 + slot] on the device (read back later with dd_read_counts, one sync for several)
+// md->cnt[8 + slot] on the device (read back by dd_counts_roundtrip)
 static int dd_select(atx_ddmd *md, int n, const int *flags, int *out, int slot) {
   atx_ctx *ctx = md->ctx;
   ATX_PASS(md->tmpi.reserve(n + 1));
@@ -560,41 +560,31 @@ static int dd_select(atx_ddmd *md, int n, const int *flags, int *out, int slot) 
   return 0;
 }
 
-static int dd_read_counts(atx_ddmd *md, int nslots, int *out) {
-  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr + 8, md->cnt.ptr + 8, sizeof(int) * nslots, cudaMemcpyDeviceToHost,
-                           md->ctx->stream));
-  ATX_CUDA(cudaStreamSynchronize(md->ctx->stream));
-  for (int k = 0; k < nslots; k++) out[k] = md->hcnt.ptr[8 + k];
-  return 0;
-}
-
-// exchange two integers with the slab neighbours: what I send left/right -> what I receive
-static int dd_exchange_counts(atx_ddmd *md, int sendL, int sendR, int *recvL, int *recvR) {
+// counts of what I send left / right (device slots cnt[8], cnt[9], written by dd_select) go to the slab
+// neighbours straight from device memory; what they send me lands in cnt[12] (from the left) and cnt[13]
+// (from the right); ONE host round trip then returns cnt[8 .. 13] (own counts incl. slot 10, received counts)
+static int dd_counts_roundtrip(atx_ddmd *md, int *own3, int *recvL, int *recvR) {
   atx_dd *dd = md->dd;
   cudaStream_t st = md->ctx->stream;
-  ATX_PASS(md->cnt.reserve(16));
   int *d = md->cnt.ptr;
-  md->hcnt.ptr[0] = sendL;
-  md->hcnt.ptr[1] = sendR;
-  md->hcnt.ptr[2] = 0;
-  md->hcnt.ptr[3] = 0;
-  ATX_CUDA(cudaMemcpyAsync(d, md->hcnt.ptr, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+  ATX_CUDA(cudaMemsetAsync(d + 12, 0, 2 * sizeof(int), st));
   ATX_NCCL(g_nccl.GroupStart());
-  if (md->left >= 0) ATX_NCCL(g_nccl.Send(d + 0, 1, ncclInt, md->left, dd->comm, st));
-  if (md->right >= 0) ATX_NCCL(g_nccl.Send(d + 1, 1, ncclInt, md->right, dd->comm, st));
+  if (md->left >= 0) ATX_NCCL(g_nccl.Send(d + 8, 1, ncclInt, md->left, dd->comm, st));
+  if (md->right >= 0) ATX_NCCL(g_nccl.Send(d + 9, 1, ncclInt, md->right, dd->comm, st));
   if (md->left >= 0 && md->left == md->right) {
     // two ranks, periodic: the peer's first message is what it sent to ITS left, i.e. my right
-    ATX_NCCL(g_nccl.Recv(d + 3, 1, ncclInt, md->right, dd->comm, st));
-    ATX_NCCL(g_nccl.Recv(d + 2, 1, ncclInt, md->left, dd->comm, st));
+    ATX_NCCL(g_nccl.Recv(d + 13, 1, ncclInt, md->right, dd->comm, st));
+    ATX_NCCL(g_nccl.Recv(d + 12, 1, ncclInt, md->left, dd->comm, st));
   } else {
-    if (md->left >= 0) ATX_NCCL(g_nccl.Recv(d + 2, 1, ncclInt, md->left, dd->comm, st));
-    if (md->right >= 0) ATX_NCCL(g_nccl.Recv(d + 3, 1, ncclInt, md->right, dd->comm, st));
+    if (md->left >= 0) ATX_NCCL(g_nccl.Recv(d + 12, 1, ncclInt, md->left, dd->comm, st));
+    if (md->right >= 0) ATX_NCCL(g_nccl.Recv(d + 13, 1, ncclInt, md->right, dd->comm, st));
   }
   ATX_NCCL(g_nccl.GroupEnd());
-  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr + 4, d + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaMemcpyAsync(md->hcnt.ptr + 8, d + 8, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
   ATX_CUDA(cudaStreamSynchronize(st));
-  *recvL = md->hcnt.ptr[4];
-  *recvR = md->hcnt.ptr[5];
+  for (int k = 0; k < 3; k++) own3[k] = md->hcnt.ptr[8 + k];
+  *recvL = md->hcnt.ptr[12];
+  *recvR = md->hcnt.ptr[13];
   return 0;
 }
 
@@ -730,15 +720,14 @@ static int dd_rebuild(atx_ddmd *md) {
     ATX_PASS(dd_select(md, n, md->flags2.ptr, md->sendR.ptr, 1));
     ATX_PASS(dd_select(md, n, md->flags3.ptr, md->sel.ptr, 2));
     int c3[3];
-    ATX_PASS(dd_read_counts(md, 3, c3));
+    int inL = 0, inR = 0;
+    ATX_PASS(dd_counts_roundtrip(md, c3, &inL, &inR));
     nL = c3[0]; nR = c3[1]; nstay = c3[2];
     tm.lap(0);
     if ((md->left < 0 && nL > 0) || (md->right < 0 && nR > 0)) {
       atx_set_error("Particle outside simulation domain (left the non-periodic box along x).");
       return ATX_ERROR_UNSPECIFIED;
     }
-    int inL = 0, inR = 0;
-    ATX_PASS(dd_exchange_counts(md, nL, nR, &inL, &inR));
     tm.lap(1);
     ATX_PASS(md->mig_send.reserve((size_t)DD_ROW * (nL + nR) + DD_ROW));
     ATX_PASS(md->mig_recv.reserve((size_t)DD_ROW * (inL + inR) + DD_ROW));
@@ -811,13 +800,12 @@ static int dd_rebuild(atx_ddmd *md) {
       ATX_PASS(dd_select(md, n, md->flags2.ptr, md->sendR.ptr, 1));
     }
     {
-      int c2[2];
-      ATX_PASS(dd_read_counts(md, 2, c2));
-      md->nsendL = c2[0];
-      md->nsendR = c2[1];
+      int c3b[3];
+      ATX_PASS(dd_counts_roundtrip(md, c3b, &md->ngl, &md->ngr));
+      md->nsendL = c3b[0];
+      md->nsendR = c3b[1];
     }
     tm.lap(3);
-    ATX_PASS(dd_exchange_counts(md, md->nsendL, md->nsendR, &md->ngl, &md->ngr));
     tm.lap(4);
     int nloc = n + md->ngl + md->ngr;
     if (md->p2p && ((size_t)md->ngl > md->capG || (size_t)md->ngr > md->capG)) {
@@ -864,6 +852,48 @@ __global__ void k_dd_shift(int n, int at, double *__restrict__ r, double sx, dou
   r[3 * i] += sx; r[3 * i + 1] += sy; r[3 * i + 2] += sz;
 }
 
+// ---- local numbering follows the sorted order -------------------------------------------------
+// After a list build the owned atoms are renumbered so that their local index grows with their
+// sorted (cell-ordered) index: the per-step gathers / scatters between the local arrays (r, v, f)
+// and the sorted records (pos4, forces of the potentials) then touch memory almost sequentially.
+__global__ void k_dd_owned_flag(int nloc, int n, const int *__restrict__ order, int *__restrict__ flag) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s <= nloc) flag[s] = (s < nloc && order[s] < n) ? 1 : 0;
+}
+__global__ void k_dd_newidx(int n, const int *__restrict__ inv, const int *__restrict__ rank,
+                            int *__restrict__ newidx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) newidx[i] = rank[inv[i]];
+}
+__global__ void k_dd_permute_owned(int n, const int *__restrict__ newidx, const double *__restrict__ idd,
+                                   const int *__restrict__ el, const double *__restrict__ r,
+                                   const double *__restrict__ v, const double *__restrict__ minv,
+                                   double *__restrict__ idd2, int *__restrict__ el2, double *__restrict__ r2,
+                                   double *__restrict__ v2, double *__restrict__ minv2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = newidx[i];
+  idd2[k] = idd[i];
+  el2[k] = el[i];
+  minv2[k] = minv[i];
+  for (int c = 0; c < 3; c++) { r2[3 * k + c] = r[3 * i + c]; v2[3 * k + c] = v[3 * i + c]; }
+}
+__global__ void k_dd_renumber(int nloc, int n, const int *__restrict__ newidx, int *__restrict__ order,
+                              int *__restrict__ inv) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nloc) return;
+  int o = order[s];
+  if (o < n) {
+    o = newidx[o];
+    order[s] = o;
+  }
+  inv[o] = s;
+}
+__global__ void k_dd_remap(int m, const int *__restrict__ newidx, int *__restrict__ idx) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < m) idx[t] = newidx[idx[t]];
+}
+
 static int dd_build_list(atx_ddmd *md) {
   atx_ctx *ctx = md->ctx;
   cudaStream_t st = ctx->stream;
@@ -885,6 +915,31 @@ static int dd_build_list(atx_ddmd *md) {
   std::swap(md->ploc.el.ptr, md->el.ptr);
   std::swap(md->ploc.el.cap, md->el.cap);
   if (err) return err;
+  if (md->dd->nranks > 1 && n > 0) {
+    // renumber the owned atoms in sorted order (flags -> ranks -> permutation of the local arrays)
+    const int gl = (nloc + 1 + 255) / 256, go = (n + 255) / 256;
+    ATX_PASS(md->flags.reserve((size_t)nloc + 2));
+    ATX_PASS(md->flags2.reserve((size_t)nloc + 2));
+    ATX_PASS(md->flags3.reserve((size_t)nloc + 2));
+    k_dd_owned_flag<<<gl, 256, 0, st>>>(nloc, n, md->nl->order.ptr, md->flags.ptr);
+    ATX_PASS(atx_scan_int(ctx, md->flags.ptr, md->flags2.ptr, (size_t)nloc + 1));
+    k_dd_newidx<<<go, 256, 0, st>>>(n, md->nl->inv.ptr, md->flags2.ptr, md->flags3.ptr);
+    k_dd_permute_owned<<<go, 256, 0, st>>>(n, md->flags3.ptr, md->idd.ptr, md->el.ptr, md->r.ptr, md->v.ptr,
+                                           md->minv.ptr, md->idd2.ptr, md->el2.ptr, md->r2.ptr, md->v2.ptr,
+                                           md->minv2.ptr);
+    if (ng > 0) {
+      ATX_CUDA(cudaMemcpyAsync(md->r2.ptr + 3 * (size_t)n, md->r.ptr + 3 * (size_t)n, sizeof(double) * 3 * ng,
+                               cudaMemcpyDeviceToDevice, st));
+      ATX_CUDA(cudaMemcpyAsync(md->el2.ptr + n, md->el.ptr + n, sizeof(int) * ng, cudaMemcpyDeviceToDevice, st));
+    }
+    k_dd_renumber<<<(nloc + 255) / 256, 256, 0, st>>>(nloc, n, md->flags3.ptr, md->nl->order.ptr, md->nl->inv.ptr);
+    if (md->nsendL > 0) k_dd_remap<<<(md->nsendL + 255) / 256, 256, 0, st>>>(md->nsendL, md->flags3.ptr, md->sendL.ptr);
+    if (md->nsendR > 0) k_dd_remap<<<(md->nsendR + 255) / 256, 256, 0, st>>>(md->nsendR, md->flags3.ptr, md->sendR.ptr);
+    g_atx_launches += 6;
+    swapbuf(md->r, md->r2); swapbuf(md->v, md->v2); swapbuf(md->f, md->f2); swapbuf(md->minv, md->minv2);
+    swapbuf(md->idd, md->idd2); swapbuf(md->el, md->el2);
+    md->ploc.r_ext = md->r.ptr;
+  }
   if (md->dd->nranks > 1 && nloc > 0) {
     // inner ghosts: within rc + skin (= half the halo) of the slab; + a small margin
     const double band = 0.5 * md->hfrac * 1.02;

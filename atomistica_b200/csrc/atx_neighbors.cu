@@ -199,9 +199,11 @@ __global__ void k_gather_sorted(int nat, const double *__restrict__ r, const int
                                 const int4 *__restrict__ cellshift, const int *__restrict__ order,
                                 double4 *__restrict__ pos4, int4 *__restrict__ sshift,
                                 int *__restrict__ inv, Geo g, float4 *__restrict__ posf,
-                                long long *__restrict__ scal) {
+                                long long *__restrict__ scal, double ext_max) {
+  // scal[6] is raised when the single-precision records cannot be used: a cell-relative coordinate
+  // beyond ext_max (the bound the host derived the band width from; only atoms outside a non-periodic
+  // cell exceed it), a wrap count beyond +-59 cells, or a NaN position
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  double ext = 0.0;
   int bad = 0;
   if (s < nat) {
     int i = order[s];
@@ -219,21 +221,15 @@ __global__ void k_gather_sorted(int nat, const double *__restrict__ r, const int
       double px = x + g.A.m[0] * t0 + g.A.m[3] * t1 + g.A.m[6] * t2;
       double py = y + g.A.m[1] * t0 + g.A.m[4] * t1 + g.A.m[7] * t2;
       double pz = z + g.A.m[2] * t0 + g.A.m[5] * t1 + g.A.m[8] * t2;
-      // wrap counts beyond +-59 cells (atoms far outside a periodic cell): the exact kernel takes over
-      bad = (abs(cs.y) >= 60) | (abs(cs.z) >= 60) | (abs(cs.w) >= 60) | !(px == px) | !(py == py) | !(pz == pz);
+      const double ext = fmax(fabs(px), fmax(fabs(py), fabs(pz)));
+      bad = (abs(cs.y) >= 60) | (abs(cs.z) >= 60) | (abs(cs.w) >= 60) | !(ext <= ext_max);
       int w = bad ? 0 : (atx_pack_shift(cs.y, cs.z, cs.w) | (e << 24));
       posf[s] = make_float4((float)px, (float)py, (float)pz, __int_as_float(w));
-      ext = fmax(fabs(px), fmax(fabs(py), fabs(pz)));
     }
   }
   if (posf) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ext = fmax(ext, __shfl_xor_sync(0xffffffffu, ext, o));
     bad = __any_sync(0xffffffffu, bad);
-    if ((threadIdx.x & 31) == 0) {
-      if (ext > 0.0) atomicMax((unsigned long long *)&scal[5], (unsigned long long)__double_as_longlong(ext));
-      if (bad) atomicMax((unsigned long long *)&scal[6], 1ull);
-    }
+    if ((threadIdx.x & 31) == 0 && bad) atomicMax((unsigned long long *)&scal[6], 1ull);
   }
 }
 
@@ -661,6 +657,34 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   ATX_CUDA(cudaMemsetAsync(nl->scal.ptr, 0, sizeof(long long) * 8, st));
   ATX_CUDA(cudaMemsetAsync(nl->count.ptr, 0, sizeof(int) * (nat + 1), st));
 
+  // single-precision pre-filter of the pair search: half-width of the band in which the exact
+  // predicate decides (error analysis at k_pairs_f32; u = 2^-24, every term with a factor 2 of safety).
+  // The bound on the cell-relative coordinates is the cell diagonal sum -- every atom inside the
+  // (periodic or non-periodic) cell obeys it; the gather kernel checks it and the search is redone
+  // with the exact kernel in the rare case it does not hold (no host round trip on the normal path).
+  float lo2 = 0.f, hi2 = 0.f;
+  double ext_max = 0.0;
+  nl->f32_delta = -1.0;
+  if (use_f32 && nat > 0) {
+    const double *A = p->Abox.m;
+    double offmax = 0.0;
+    for (int k = 0; k < 3; k++) {
+      double len = std::sqrt(A[3 * k] * A[3 * k] + A[3 * k + 1] * A[3 * k + 1] + A[3 * k + 2] * A[3 * k + 2]);
+      offmax += nl->sten[k] * len / nl->n_cells[k];
+      ext_max += 1.02 * len / nl->n_cells[k];
+    }
+    const double eps = std::ldexp(1.0, -23), R2 = g.cutoff_sq, R = std::sqrt(R2);
+    const double e_d = eps * (5.0 * ext_max + 3.0 * offmax);
+    const double delta = 2.0 * (2.0 * std::sqrt(3.0) * R * e_d * 1.01 + 3.0 * e_d * e_d + 2.0 * eps * R2 * 1.01) +
+                         2.0 * eps * R2;
+    if (delta <= 0.05 * R2) {
+      nl->f32_delta = delta;
+      lo2 = std::nextafterf((float)(R2 - delta), -1.0f);
+      hi2 = std::nextafterf((float)(R2 + delta), 3.0e38f);
+    }
+  }
+  bool f32 = nl->f32_delta > 0.0;
+
   const int TB = 256;
   int gb = (nat + TB - 1) / TB;
   if (nat > 0) {
@@ -681,39 +705,11 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     ATX_LAUNCHED();
     k_gather_sorted<<<gb, TB, 0, st>>>(nat, p->rptr(), p->el.cap ? p->el.ptr : nullptr,
                                        nl->cellshift.ptr, nl->order.ptr, nl->pos4.ptr,
-                                       nl->sshift.ptr, nl->inv.ptr, g, use_f32 ? nl->posf.ptr : nullptr,
-                                       nl->scal.ptr);
+                                       nl->sshift.ptr, nl->inv.ptr, g, f32 ? nl->posf.ptr : nullptr,
+                                       nl->scal.ptr, ext_max);
     ATX_LAUNCHED();
   }
-  // single-precision pre-filter of the pair search: half-width of the band in which the exact
-  // predicate decides, from the largest cell-relative coordinate of this build (error analysis at
-  // k_pairs_f32).  u = 2^-24; every term carries a factor 2 of safety.
-  float lo2 = 0.f, hi2 = 0.f;
-  nl->f32_delta = -1.0;
-  if (use_f32 && nat > 0) {
-    long long hb[2] = {0, 0};
-    ATX_CUDA(cudaMemcpyAsync(hb, nl->scal.ptr + 5, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    ATX_CUDA(cudaStreamSynchronize(st));
-    double ext;
-    memcpy(&ext, &hb[0], sizeof(double));
-    const double *A = p->Abox.m;
-    double offmax = 0.0;
-    for (int k = 0; k < 3; k++) {
-      double len = std::sqrt(A[3 * k] * A[3 * k] + A[3 * k + 1] * A[3 * k + 1] + A[3 * k + 2] * A[3 * k + 2]);
-      offmax += nl->sten[k] * len / nl->n_cells[k];
-    }
-    const double eps = std::ldexp(1.0, -23), R2 = g.cutoff_sq, R = std::sqrt(R2);
-    const double e_d = eps * (5.0 * ext + 3.0 * offmax);
-    const double delta = 2.0 * (2.0 * std::sqrt(3.0) * R * e_d * 1.01 + 3.0 * e_d * e_d + 2.0 * eps * R2 * 1.01) +
-                         2.0 * eps * R2;
-    if (!hb[1] && delta <= 0.05 * R2 && ext == ext) {
-      nl->f32_delta = delta;
-      lo2 = std::nextafterf((float)(R2 - delta), -1.0f);
-      hi2 = std::nextafterf((float)(R2 + delta), 3.0e38f);
-    }
-  }
-  const bool f32 = nl->f32_delta > 0.0;
-  long long h[4] = {0, 0, 0, 0};
+  long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // Single-pass build from the second build on: the previous build's longest list (+ margin) sizes
   // fixed-width rows the counting pass fills; if an atom outgrows its row the classic second
   // search pass runs instead.  Scratch is bounded to 8 GiB.
@@ -723,6 +719,7 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
     if ((size_t)nat * cap * sizeof(int2) <= ((size_t)8 << 30) && nl->rows.reserve((size_t)nat * cap) == 0)
       rows_cap = cap;
   }
+  for (int attempt = 0; attempt < 2; attempt++) {
   if (nat > 0) {
     {
       ProfScope ps_(ctx, "nl_pairs_count");
@@ -743,8 +740,17 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   }
   ATX_PASS(atx_scan_int_to_ll(ctx, nl->count.ptr, nl->seed.ptr, nat + 1));
   ATX_CUDA(cudaMemcpyAsync(&h[0], nl->seed.ptr + nat, sizeof(long long), cudaMemcpyDeviceToHost, st));
-  ATX_CUDA(cudaMemcpyAsync(&h[1], nl->scal.ptr + 1, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  ATX_CUDA(cudaMemcpyAsync(&h[1], nl->scal.ptr + 1, 6 * sizeof(long long), cudaMemcpyDeviceToHost, st));
   ATX_CUDA(cudaStreamSynchronize(st));
+  if (f32 && h[6]) {
+    // the single-precision records were not usable (see k_gather_sorted): exact search instead
+    f32 = false;
+    nl->f32_delta = -1.0;
+    ATX_CUDA(cudaMemsetAsync(nl->scal.ptr, 0, sizeof(long long) * 8, st));
+    continue;
+  }
+  break;
+  }
   nl->npairs = h[0];
   nl->nebmax = (int)h[1];
   long long i_last = h[2];  // 1-based original index of the last atom that has a pair
@@ -778,8 +784,12 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
       }
     }
     ATX_LAUNCHED();
-    ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    ATX_CUDA(cudaStreamSynchronize(st));
+    if (!f32) {
+      // the exact kernels flag image shifts the 8-bit packing cannot hold (the single-precision path
+      // never produces them: wrap counts beyond +-59 cells send the build to the exact kernels)
+      ATX_CUDA(cudaMemcpyAsync(&h[3], nl->scal.ptr + 3, sizeof(long long), cudaMemcpyDeviceToHost, st));
+      ATX_CUDA(cudaStreamSynchronize(st));
+    }
     if (h[3]) {
       atx_set_error("Periodic image shift beyond +-127 cells; wrap the positions into the cell.");
       nl->initialized = false;

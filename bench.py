@@ -37,7 +37,10 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 A0, NCELL, TEMP, DT, SKIN = 3.615, 40, 300.0, 1.0, 0.5
 MASS_CU = 63.546
 MASS_SI = 28.0855
-C4_CELLS, C4_SKIN = 128, 0.4
+C4_CELLS = 128
+# Verlet shells of C4: the list cutoff r2 + shell stays below the rattled second-neighbour shell (3.84 A), so the
+# lists keep ~4 entries per atom while rebuilds are as rare as possible
+C4_SKINS = dict(Tersoff=0.6, Kumagai=0.4)
 PRIME_MAX = 160          # upper bound of the untimed priming phase (steps)
 
 
@@ -552,6 +555,7 @@ def block_c4(args, dist, L, ctx):
     for kind, a0, rc in (('Tersoff', 5.432, 3.0), ('Kumagai', 5.429, 3.3)):
         if kind not in args.c4_kinds.split(','):
             continue
+        C4_SKIN = C4_SKINS[kind]
         pos, v0, ids = c4_slab(a0, n, rank, world)
         cell = np.diag([n * a0] * 3)
         nat, ntot = len(pos), 8 * n ** 3

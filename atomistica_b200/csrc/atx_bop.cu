@@ -521,12 +521,13 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
              double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
              double *__restrict__ fpb, double *__restrict__ wpb, double *__restrict__ partials,
              int pstride, int *__restrict__ queue, int *__restrict__ qcount,
-             const unsigned char *__restrict__ role, const int *__restrict__ stop) {
+             const unsigned char *__restrict__ role, const int *__restrict__ stop, int boff) {
   if (stop && *stop) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BondSmem<NB> &S = *reinterpret_cast<BondSmem<NB> *>(smem_raw);
   const int t = threadIdx.x;
-  const int s = blockIdx.x * BOP_BLOCK + t;
+  const int blk = blockIdx.x + boff;     // the launch covers the blocks [boff, boff + gridDim.x)
+  const int s = blk * BOP_BLOCK + t;
   double acc[ATX_NSUM];
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
@@ -538,7 +539,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * pstride + blockIdx.x] = acc[k];
+    for (int k = 0; k < ATX_NSUM; k++) partials[(size_t)k * pstride + blk] = acc[k];
   }
 }
 
@@ -1263,7 +1264,8 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
 template <int KIND, int NB, int MINB, bool VIRIAL>
 static int launch_center_v(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
-                         int nblocks, int pstride) {
+                         int nblocks, int pstride, int b0 = 0) {
+  if (nblocks <= 0) return 0;
   size_t smem = sizeof(BondSmem<NB>);
   static int attr_dev = -1;   // the attribute belongs to the device: set it again when the device changes
   if (attr_dev != pot->ctx->device) {
@@ -1274,7 +1276,7 @@ static int launch_center_v(atx_bop *pot, atx_particles *p, atx_neighbors *nl, co
   k_bop_center<KIND, NB, MINB, VIRIAL><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
       nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
       pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pstride, pot->queue.ptr, pot->flag.ptr + 1,
-      o.role, o.stop);
+      o.role, o.stop, b0);
   ATX_LAUNCHED();
   return 0;
 }
@@ -1284,15 +1286,30 @@ static int launch_center_v(atx_bop *pot, atx_particles *p, atx_neighbors *nl, co
 template <int KIND, int NB, int MINB = 1>
 static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
-                         int nblocks, int pstride) {
+                         int nblocks, int pstride, int b0 = 0) {
   if (o.want_virial || o.wpa || wpb)
-    return launch_center_v<KIND, NB, MINB, true>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride);
-  return launch_center_v<KIND, NB, MINB, false>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride);
+    return launch_center_v<KIND, NB, MINB, true>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride, b0);
+  return launch_center_v<KIND, NB, MINB, false>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride, b0);
 }
 
 // bond-table depths that are compiled; the main pass uses the smallest one that holds (nearly)
 // every atom, the queued pass BOP_NB_MAX
 static const int kBopDepths[] = {4, 6, 8, 12, BOP_NB_MAX};
+
+template <int KIND>
+static int launch_center_range(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
+                               const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
+                               int b0, int b1, int pstride) {
+  const int nb = b1 - b0;
+  switch (pot->nb_cap) {
+    // depth 4: 30.9 KB of shared memory per block -> 7 blocks/SM if the kernel stays within 146 registers
+    case 4: return launch_center<KIND, 4, 7>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nb, pstride, b0);
+    case 6: return launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nb, pstride, b0);
+    case 8: return launch_center<KIND, 8>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nb, pstride, b0);
+    case 12: return launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nb, pstride, b0);
+    default: return launch_center<KIND, BOP_NB_MAX>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nb, pstride, b0);
+  }
+}
 
 template <int KIND>
 static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
@@ -1301,16 +1318,16 @@ static int launch_center_nb(atx_bop *pot, atx_particles *p, atx_neighbors *nl, c
   cudaStream_t st = pot->ctx->stream;
   const int nq = pot->ctx->sm_count;            // blocks of the queued pass
   const int pstride = nblocks + nq;
-  ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 1, 0, sizeof(int), st));   // queue length
+  // PotOut::phase: 1 = the centre blocks inside [split_lo, split_hi) only, 2 = everything else
+  int bl = (o.split_lo + BOP_BLOCK - 1) / BOP_BLOCK, bh = o.split_hi / BOP_BLOCK;
+  if (bh > nblocks) bh = nblocks;
+  if (bh < bl || o.phase == 0) bl = bh = 0;
+  if (o.phase != 2) ATX_CUDA(cudaMemsetAsync(pot->flag.ptr + 1, 0, sizeof(int), st));   // queue length
   ProfScope ps_(pot->ctx, "bop_force");
-  switch (pot->nb_cap) {
-    // depth 4: 30.9 KB of shared memory per block -> 7 blocks/SM if the kernel stays within 146 registers
-    case 4: ATX_PASS((launch_center<KIND, 4, 7>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
-    case 6: ATX_PASS((launch_center<KIND, 6>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
-    case 8: ATX_PASS((launch_center<KIND, 8>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
-    case 12: ATX_PASS((launch_center<KIND, 12>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride))); break;
-    default: ATX_PASS((launch_center<KIND, BOP_NB_MAX>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride)));
-  }
+  if (o.phase == 1)
+    return launch_center_range<KIND>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, bl, bh, pstride);
+  ATX_PASS(launch_center_range<KIND>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, 0, bl, pstride));
+  ATX_PASS(launch_center_range<KIND>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, bh, nblocks, pstride));
   size_t smem = sizeof(BondSmem<BOP_NB_MAX>);
   static int attr_dev = -1;
   if (attr_dev != pot->ctx->device) {
@@ -1466,6 +1483,7 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
     default:
       ATX_PASS(launch_center_nb<ATX_BOP_BRENNER>(pot, p, nl, mask_sorted, o, pe_own, epb, fpb, wpb, nblocks));
   }
+  if (o.phase == 1) return 0;   // interior centres only; phase 2 finishes the evaluation
   if (nat > 0) {
     ProfScope ps_(ctx, "bop_gather");
     k_bop_gather<<<(nat + 127) / 128, 128, 0, st>>>(nat, nl->seed.ptr, nl->rev.ptr, pot->G.ptr, pe_own,
@@ -1477,6 +1495,9 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
 }
 
 // overflow of the bond table during guarded (batched MD) steps; called by the MD drivers after a sync
+// the split evaluation of PotOut::phase exists for the unscreened kernels only
+bool atx_bop_supports_split(atx_bop *pot) { return pot && !pot->screened; }
+
 int atx_bop_check_overflow(atx_bop *pot) {
   ATX_PASS(pot->hflag.reserve(4));
   ATX_CUDA(cudaMemcpyAsync(pot->hflag.ptr, pot->flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, pot->ctx->stream));

@@ -19,6 +19,7 @@
 #include <nccl.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -32,6 +33,7 @@ int atx_bop_compute_device(atx_bop *pot, atx_particles *p, atx_neighbors *nl,
                            const int *mask_sorted, const PotOut &o);
 int atx_rebo2_compute_device(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, const PotOut &o);
 int atx_bop_check_overflow(atx_bop *pot);
+bool atx_bop_supports_split(atx_bop *pot);
 int atx_rebo2_check_overflow(atx_rebo2 *pot);
 
 // ---------------------------------------------------------------------------
@@ -203,6 +205,9 @@ struct atx_ddmd {
   char *peer_mbox[DD_MAXP] = {nullptr};  // mapped mailboxes ([rank] = own)
   DevBuf<unsigned long long *> d_peer_sig;
   double rebuild_host_ms[8] = {0};       // host wall time per rebuild phase (accumulated)
+  // sorted range of the interior atoms (owned, no ghost in their list): evaluated while the halo is in flight
+  int split_lo = 0, split_hi = 0;
+  bool split = false;
 };
 
 // inv / pos4 (peer-to-peer step path): the new position also goes straight into the atom's sorted
@@ -655,8 +660,11 @@ static int dd_reserve_local(atx_ddmd *md, size_t n) {
   return 0;
 }
 
-static int dd_compute(atx_ddmd *md, bool guarded) {
+static int dd_compute(atx_ddmd *md, bool guarded, int phase = 0) {
   PotOut o;
+  o.phase = phase;
+  o.split_lo = md->split_lo;
+  o.split_hi = md->split_hi;
   int nloc = md->nown + md->ngl + md->ngr;
   ATX_PASS(md->tmpd.reserve(3 * (size_t)nloc + 3));
   ATX_PASS(md->epa.reserve((size_t)nloc + 1));
@@ -948,6 +956,31 @@ static int dd_build_list(atx_ddmd *md) {
                                                    md->role.ptr);
     ATX_LAUNCHED();
   }
+  // interior atoms: owned atoms further than rc + skin (half the halo) from both slab faces at build
+  // time have only owned atoms in their lists.  Cells are ordered x-major, so the atoms of the cell
+  // planes that lie completely inside that region form ONE range of the sorted numbering.
+  md->split = false;
+  md->split_lo = md->split_hi = 0;
+  if (md->dd->nranks > 1 && md->p2p && md->pot_kind == ATX_POT_BOP && atx_bop_supports_split((atx_bop *)md->pot) &&
+      nloc > 0 && !(getenv("ATX_DD_SPLIT") && atoi(getenv("ATX_DD_SPLIT")) == 0)) {
+    const double alpha = 1.0 / md->dd->nranks + 2.0 * md->hfrac;
+    const double u_lo = (md->hfrac + 0.51 * md->hfrac) / alpha, u_hi = (md->hfrac + 1.0 / md->dd->nranks - 0.51 * md->hfrac) / alpha;
+    const int n0 = md->nl->n_cells[0], plane = md->nl->n_cells[1] * md->nl->n_cells[2];
+    int c_lo = (int)std::ceil(u_lo * n0), c_hi = (int)std::floor(u_hi * n0);
+    if (c_lo < 0) c_lo = 0;
+    if (c_hi > n0) c_hi = n0;
+    if (c_hi > c_lo) {
+      int h2[2] = {0, 0};
+      ATX_CUDA(cudaMemcpyAsync(&h2[0], md->nl->cell_start.ptr + (size_t)c_lo * plane, sizeof(int), cudaMemcpyDeviceToHost, st));
+      ATX_CUDA(cudaMemcpyAsync(&h2[1], md->nl->cell_start.ptr + (size_t)c_hi * plane, sizeof(int), cudaMemcpyDeviceToHost, st));
+      ATX_CUDA(cudaStreamSynchronize(st));
+      if (h2[1] > h2[0]) {
+        md->split_lo = h2[0];
+        md->split_hi = h2[1];
+        md->split = true;
+      }
+    }
+  }
   md->nrebuilds++;
   tm.lap(6);
   return 0;
@@ -1229,6 +1262,8 @@ static int dd_enqueue_step(atx_ddmd *md) {
           dL * md->a1[2], dR * md->a1[0], dR * md->a1[1], dR * md->a1[2], dstL, dstR, par_stride,
           md->d_peer_sig.ptr, dd->rank, dd->nranks, md->ctrl.ptr);
       ATX_LAUNCHED();
+      // interior centres do not depend on this step's ghost positions: they run while the halo travels
+      if (md->split) ATX_PASS(dd_compute(md, true, 1));
       k_dd_wait<<<1, 32, 0, st>>>((const unsigned long long *)md->mbox, dd->nranks, md->ctrl.ptr);
       ATX_LAUNCHED();
     }
@@ -1238,7 +1273,7 @@ static int dd_enqueue_step(atx_ddmd *md) {
                                                                md->nl->inv.ptr, md->nl->pos4.ptr, md->ctrl.ptr);
       ATX_LAUNCHED();
     }
-    ATX_PASS(dd_compute(md, true));
+    ATX_PASS(dd_compute(md, true, md->split ? 2 : 0));
     ATX_PASS(dd_kick(md));
     return 0;
   }

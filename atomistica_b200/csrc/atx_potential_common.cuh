@@ -16,6 +16,13 @@ struct PotOut {
   // domain decomposition: per sorted atom 2 = owned (everything), 1 = inner ghost (densities /
   // bond-order terms only, no forces), 0 = outer ghost (position only).  nullptr: all owned.
   const unsigned char *role = nullptr;
+  // split evaluation (domain decomposition, overlap of the halo exchange with interior work):
+  // phase 0 = everything; phase 1 = only the centre atoms of the sorted range [split_lo, split_hi)
+  // (rounded inwards to the kernel's block size; no gather, no sums); phase 2 = the remaining centres,
+  // the deferred atoms, the gather and the sums.  Phases 1 and 2 of one evaluation must see the same
+  // list; positions outside the range may change between them.
+  int phase = 0;
+  int split_lo = 0, split_hi = 0;
 };
 
 // Scratch owned by every potential object for library-mode calls.

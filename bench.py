@@ -496,6 +496,9 @@ def block_c2(args, dist, L, ctx):
     # ---- roofline of the dominant kernel
     peak, peak_src = measured_peaks()
     alg_bytes = nat * (68.0 + 16.0 * z_list)          # B_eam = 68 + 16 z per atom
+    # launches that really ran: one force evaluation per step + one per rebuild (the optimistic batches
+    # also enqueue steps that exit at once after a rebuild was requested; they carry no time)
+    force_n = steps + rebuilds
     force_avg_ms = force_ms / max(force_n, 1)
     achieved = alg_bytes / (force_avg_ms * 1e-3) / 1e9
     fp64 = C.c_double(0.0)
@@ -597,6 +600,7 @@ def block_c4(args, dist, L, ctx):
             blk['rebuild_host_ms_since_create'] = st['rebuild_host_ms']
         if world == 1:
             alg = nat * (68.0 + 16.0 * z)
+            bop_n = steps + (st['nrebuilds'] - st0['nrebuilds'])    # executed evaluations (see block_c2)
             avg = bop_ms / max(bop_n, 1)
             rf = dict(kernel='k_bop_center<%s>' % kind, avg_launch_ms=avg, launches=bop_n,
                       list_neighbors_per_atom=z,

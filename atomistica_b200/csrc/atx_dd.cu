@@ -956,13 +956,15 @@ static int dd_build_list(atx_ddmd *md) {
                                                    md->role.ptr);
     ATX_LAUNCHED();
   }
+  // Opt-in (ATX_DD_SPLIT=1): measured at N=8 on C4 the three centre launches per step lose in partial
+  // waves (0.82 vs 0.77 ms of centre kernels per step) what the hidden halo wait (0.07 ms) gains.
   // interior atoms: owned atoms further than rc + skin (half the halo) from both slab faces at build
   // time have only owned atoms in their lists.  Cells are ordered x-major, so the atoms of the cell
   // planes that lie completely inside that region form ONE range of the sorted numbering.
   md->split = false;
   md->split_lo = md->split_hi = 0;
   if (md->dd->nranks > 1 && md->p2p && md->pot_kind == ATX_POT_BOP && atx_bop_supports_split((atx_bop *)md->pot) &&
-      nloc > 0 && !(getenv("ATX_DD_SPLIT") && atoi(getenv("ATX_DD_SPLIT")) == 0)) {
+      nloc > 0 && getenv("ATX_DD_SPLIT") && atoi(getenv("ATX_DD_SPLIT")) != 0) {
     const double alpha = 1.0 / md->dd->nranks + 2.0 * md->hfrac;
     const double u_lo = (md->hfrac + 0.51 * md->hfrac) / alpha, u_hi = (md->hfrac + 1.0 / md->dd->nranks - 0.51 * md->hfrac) / alpha;
     const int n0 = md->nl->n_cells[0], plane = md->nl->n_cells[1] * md->nl->n_cells[2];

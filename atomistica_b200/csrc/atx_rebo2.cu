@@ -126,7 +126,7 @@ __global__ void k_rebo2_own_fill(int nat, int nbs, Rebo2Dev P, const int *__rest
 
 // MINB: resident blocks per SM asked from the register allocator (4: 255 registers, 6: 170, 8: 128 with
 // spills) -- occupancy against spills is to be measured (ATX_REBO2_PERBOND = 1 / 2 / 3)
-template <int MINB>
+template <int MINB, int NBL>
 __global__ void __launch_bounds__(RB_BLOCK, MINB)
 k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ seed,
                    const int *__restrict__ b_cnt, const RbBond *__restrict__ b_tab,
@@ -143,7 +143,7 @@ k_rebo2_force_bond(int nat, int nbs, Rebo2Dev P, const long long *__restrict__ s
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   if (t < off[nat]) {
     const int2 e = own[t];
-    rb_force_atom<false, true>(nat, nbs, P, seed, b_cnt, b_tab, nn, pos4, order,
+    rb_force_atom<false, true, NBL>(nat, nbs, P, seed, b_cnt, b_tab, nn, pos4, order,
                                f, epa, wpa, epb, fpb, wpb, e.x, acc, nullptr, e.y);
   }
   atx_block_sum<ATX_NSUM, RB_BLOCK>(acc, red);
@@ -454,9 +454,16 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
                                                         o.stop);
     ATX_LAUNCHED();
 #define RB_FORCE_BOND(MINB)                                                                                   \
-  k_rebo2_force_bond<MINB><<<nbb, RB_BLOCK, 0, st>>>(                                                         \
+  do {                                                                                                        \
+  if (nbs <= 6)                                                                                               \
+    k_rebo2_force_bond<MINB, 6><<<nbb, RB_BLOCK, 0, st>>>(                                                    \
       nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_tab.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,  \
-      o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr, pot->own.ptr, o.stop)
+      o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr, pot->own.ptr, o.stop);                    \
+  else                                                                                                        \
+  k_rebo2_force_bond<MINB, RB_NBL><<<nbb, RB_BLOCK, 0, st>>>(                                                         \
+      nat, nbs, pot->dev, nl->seed.ptr, pot->b_cnt.ptr, pot->b_tab.ptr, pot->nn.ptr, nl->pos4.ptr, nl->order.ptr, o.f, o.epa,  \
+      o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pot->own_off.ptr, pot->own.ptr, o.stop);                    \
+  } while (0)
     if (pot->per_bond == 2) RB_FORCE_BOND(6);
     else if (pot->per_bond == 3) RB_FORCE_BOND(8);
     else if (pot->per_bond == 4) RB_FORCE_BOND(12);

@@ -102,7 +102,9 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
 // an unfolded periodic system) are the reference's totals; the caller discards the ghost rows.
 // ONE: evaluate only the bond in slot ij0 of atom i (one thread per bond, k_rebo2_force_bond) instead
 // of all bonds the atom is responsible for.
-template <bool ROLES = false, bool ONE = false>
+// NBL: depth of the per-thread scratch arrays (>= nbs); the shallow instantiation keeps the local-memory
+// footprint of a resident block inside L1 for four-fold coordinated carbon
+template <bool ROLES = false, bool ONE = false, int NBL = RB_NBL>
 __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &P,
                                               const long long *__restrict__ seed,
                                               const int *__restrict__ b_cnt, const RbBond *__restrict__ b_tab,
@@ -120,7 +122,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
     const size_t qi = (size_t)i * nbs;
     double fix = 0.0, fiy = 0.0, fiz = 0.0;
     // ---- ik_loop1 (:1231-1317): conjugation inputs of the neighbours of i
-    double fxik[RB_NBL], dncx[RB_NBL];  // fconj(x_ik), fcik * dfconj/dx
+    double fxik[NBL], dncx[NBL];  // fconj(x_ik), fcik * dfconj/dx
     double nconjit = 0.0;
     for (int ik = 0; ik < nbi; ik++) {
       int k = b_tab[qi + ik].nb;
@@ -177,7 +179,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       double fjx = 0.0, fjy = 0.0, fjz = 0.0;
       double zij = 0.0, dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0, dzdni = 0.0;
       double nconji = 0.0;
-      double dbk[RB_NBL][3];
+      double dbk[NBL][3];
 
       // ---- ik_loop2 (:1407-1587)
       for (int ik = 0; ik < nbi; ik++) {
@@ -240,8 +242,8 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       const int nbj = b_cnt[j];
       double zji = 0.0, bix = 0, biy = 0, biz = 0, bjx = 0, bjy = 0, bjz = 0, dzdnj = 0.0;
       double nconjj = 0.0;
-      double dbl[RB_NBL][3];
-      double fxjl[RB_NBL], dnlx[RB_NBL];
+      double dbl[NBL][3];
+      double fxjl[NBL], dnlx[NBL];
       for (int jl = 0; jl < nbj; jl++) {
         fxjl[jl] = 0.0; dnlx[jl] = 0.0;
         dbl[jl][0] = dbl[jl][1] = dbl[jl][2] = 0.0;

@@ -816,6 +816,188 @@ static void eam_energy_and_forces(void *self, void *pp, void *nn, double *, doub
 }
 static void eam_register_data(void *, void *, int *ierror) { if (ierror) *ierror = ERROR_NONE; }
 
+// ---- Rebo2 / Rebo2Scr (rebo2_registry.f90:22-168, rebo2_module.f90:70-223) -------------------------------
+// The finished default parameter block (constants, g-splines, table coefficients) is generated at build
+// time; this shim exposes `elements` and `dihedral`.  Other parameter overrides of the reference's registry
+// (scalars, the nine tables) go through atomistica_b200.native.Rebo2, which rebuilds the tables.
+struct S2Rebo2 {
+  bool screened = false;
+  char elements[1024];
+  BOOL dihedral = 0;
+  atx_rebo2 *h = nullptr;
+  section_t *members = nullptr;
+};
+
+template <bool SCR>
+static void rebo2_new(void **self, section_t *cfg, section_t **members) {
+  S2Rebo2 *r = new S2Rebo2();
+  r->screened = SCR;
+  memset(r->elements, ' ', sizeof r->elements);
+  memcpy(r->elements, "C,H", 3);
+  section_t *m = ptrdict_register_section(cfg, (char *)(SCR ? "Rebo2Scr" : "Rebo2"),
+                                          (char *)"The 2nd generation REBO (Brenner 2002) potential.");
+  ptrdict_register_string_property(m, r->elements, (int)sizeof r->elements, (char *)"elements",
+                                   (char *)"Elements for which to use this potential (default: C,H).");
+  ptrdict_register_boolean_property(m, &r->dihedral, (char *)"dihedral", (char *)"Include the dihedral term?");
+  r->members = m;
+  *members = m;
+  *self = r;
+}
+static void rebo2_free(void *self) {
+  S2Rebo2 *r = (S2Rebo2 *)self;
+  if (r->h) atx_rebo2_destroy(r->h);
+  if (r->members) ptrdict_cleanup(r->members);
+  delete r;
+}
+static void rebo2_init(void *self, int *ierror) {
+  S2Rebo2 *r = (S2Rebo2 *)self;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!ctx()) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  if (fstr(r->elements, sizeof r->elements) != "C,H")
+    RAISE(ierror, "Rebo2: only elements='C,H' is available through this module.");
+  atx_rebo2_params par;
+  atx_rebo2_screening scr;
+  memset(&par, 0, sizeof par);
+  memset(&scr, 0, sizeof scr);
+  if (r->screened) s2_rebo2scr_defaults(&par, &scr);
+  else s2_rebo2_defaults(&par, &scr);
+  par.with_dihedral = r->dihedral ? 1 : 0;
+  if (r->h) { atx_rebo2_destroy(r->h); r->h = nullptr; }
+  if (r->screened) CHK(atx_rebo2_create_screened(ctx(), &par, &scr, &r->h), ierror);
+  else CHK(atx_rebo2_create(ctx(), &par, &r->h), ierror);
+}
+static void rebo2_bind_to(void *self, void *pp, void *nn, int *ierror) {
+  S2Rebo2 *r = (S2Rebo2 *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!r->h) RAISE(ierror, "The potential has not been initialised.");
+  neighbors_ensure(n);
+  if (!n->h || !p->h) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  n->p = p;
+  CHK(atx_rebo2_bind_to(r->h, p->h, n->h, (int)p->el2Z.size(), p->el2Z.data()), ierror);
+}
+static void rebo2_energy_and_forces(void *self, void *pp, void *nn, double *, double *epot, double *f, int *wpot_,
+                                    double *mask_, double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                    double *wpot_per_at, double *wpot_per_bond, int *ierror) {
+  S2Rebo2 *r = (S2Rebo2 *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (mask_) RAISE(ierror, "Rebo2 does not support masks.");      // features: per_at, per_bond (rebo2.f90:22-27)
+  if (!r->h || !n->h) RAISE(ierror, "bind_to has not been called on this potential.");
+  n->p = p;
+  CHK(particles_sync(p), ierror);
+  CHK(atx_rebo2_energy_and_forces(r->h, p->h, n->h, epot, f, (double *)wpot_, epot_per_at, epot_per_bond, f_per_bond,
+                                  wpot_per_at, wpot_per_bond), ierror);
+}
+
+// ---- pair potentials (src/potentials/pair_potentials/*.f90): el1, el2, parameters, cutoff, shift --------
+struct S2Pair {
+  int kind = 0;
+  char el1[8], el2[8];
+  double p[8];
+  BOOL shift = 0;
+  atx_pair *h = nullptr;
+  section_t *members = nullptr;
+};
+struct PairSpec { int kind; const char *name; int np; const char *pn[5]; double def[5]; bool has_shift; };
+static const PairSpec PAIR_SPECS[] = {
+    {ATX_PAIR_LJCUT, "LJCut", 3, {"epsilon", "sigma", "cutoff"}, {0.001, 3.0, 6.0}, true},
+    {ATX_PAIR_HARMONIC, "Harmonic", 3, {"k", "r0", "cutoff"}, {1.0, 1.0, 1.5}, true},
+    {ATX_PAIR_DOUBLE_HARMONIC, "DoubleHarmonic", 5, {"k1", "r1", "k2", "r2", "cutoff"}, {1.0, 1.0, 1.0, 1.41421356237, 1.6}, false},
+    {ATX_PAIR_BORN_MAYER, "BornMayer", 3, {"A", "rho", "cutoff"}, {1.0, 1.0, 1.0}, false},
+    {ATX_PAIR_R6, "r6", 3, {"A", "r0", "cutoff"}, {1.0, 0.0, 1.0}, false},
+};
+template <int WHICH>
+static void pair_new(void **self, section_t *cfg, section_t **members) {
+  const PairSpec &sp = PAIR_SPECS[WHICH];
+  S2Pair *q = new S2Pair();
+  q->kind = sp.kind;
+  memset(q->el1, ' ', sizeof q->el1); memset(q->el2, ' ', sizeof q->el2);
+  q->el1[0] = '*'; q->el2[0] = '*';
+  memset(q->p, 0, sizeof q->p);
+  section_t *m = ptrdict_register_section(cfg, (char *)sp.name, (char *)"Pair potential.");
+  ptrdict_register_string_property(m, q->el1, (int)sizeof q->el1, (char *)"el1", (char *)"First element.");
+  ptrdict_register_string_property(m, q->el2, (int)sizeof q->el2, (char *)"el2", (char *)"Second element.");
+  for (int k = 0; k < sp.np; k++) {
+    q->p[k] = sp.def[k];
+    ptrdict_register_real_property(m, &q->p[k], (char *)sp.pn[k], (char *)"See functional form.");
+  }
+  if (sp.has_shift)
+    ptrdict_register_boolean_property(m, &q->shift, (char *)"shift", (char *)"Shift potential to zero energy at cutoff.");
+  q->members = m;
+  *members = m;
+  *self = q;
+}
+static void pair_free(void *self) {
+  S2Pair *q = (S2Pair *)self;
+  if (q->h) atx_pair_destroy(q->h);
+  if (q->members) ptrdict_cleanup(q->members);
+  delete q;
+}
+static void pair_init(void *self, int *ierror) {
+  S2Pair *q = (S2Pair *)self;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!ctx()) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  atx_pair_params par;
+  memset(&par, 0, sizeof par);
+  par.kind = q->kind;
+  for (int k = 0; k < 8; k++) par.p[k] = q->p[k];
+  par.shift = q->shift ? 1 : 0;
+  if (q->h) { atx_pair_destroy(q->h); q->h = nullptr; }
+  CHK(atx_pair_create(ctx(), &par, &q->h), ierror);
+}
+// filter_from_string (src/core/filter.f90:55-120): bit k = particle element id k
+static int element_filter(const std::string &spec, const S2Particles *p, bool *ok) {
+  *ok = true;
+  int f = 0;
+  if (spec == "*") {
+    for (size_t k = 0; k < p->el2Z.size(); k++) f |= 1 << (k + 1);
+    return f;
+  }
+  std::stringstream ss(spec);
+  std::string sym;
+  while (std::getline(ss, sym, ',')) {
+    while (!sym.empty() && sym.back() == ' ') sym.pop_back();
+    while (!sym.empty() && sym.front() == ' ') sym.erase(sym.begin());
+    char s2[2] = {sym.size() > 0 ? sym[0] : ' ', sym.size() > 1 ? sym[1] : ' '};
+    const int z = symbol_to_Z(s2);
+    if (z <= 0) { *ok = false; return 0; }
+    for (size_t k = 0; k < p->el2Z.size(); k++)
+      if (p->el2Z[k] == z) f |= 1 << (k + 1);
+  }
+  return f;
+}
+static void pair_bind_to(void *self, void *pp, void *nn, int *ierror) {
+  S2Pair *q = (S2Pair *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!q->h) RAISE(ierror, "The potential has not been initialised.");
+  neighbors_ensure(n);
+  if (!n->h || !p->h) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  n->p = p;
+  bool ok1, ok2;
+  const int f1 = element_filter(fstr(q->el1, sizeof q->el1), p, &ok1), f2 = element_filter(fstr(q->el2, sizeof q->el2), p, &ok2);
+  if (!ok1 || !ok2) RAISE(ierror, "Unknown element in el1 / el2.");
+  CHK(atx_pair_bind_to(q->h, p->h, n->h, f1, f2), ierror);
+}
+static void pair_energy_and_forces(void *self, void *pp, void *nn, double *, double *epot, double *f, int *wpot_,
+                                   double *mask_, double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                   double *wpot_per_at, double *wpot_per_bond, int *ierror) {
+  S2Pair *q = (S2Pair *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (epot_per_bond || f_per_bond || wpot_per_bond) RAISE(ierror, "This potential does not support per-bond properties.");
+  if (mask_ && q->kind != ATX_PAIR_LJCUT) RAISE(ierror, "This potential does not support masks.");
+  if (!q->h || !n->h) RAISE(ierror, "bind_to has not been called on this potential.");
+  n->p = p;
+  CHK(particles_sync(p), ierror);
+  CHK(atx_pair_energy_and_forces(q->h, p->h, n->h, (int *)mask_, epot, f, (double *)wpot_, epot_per_at, wpot_per_at), ierror);
+}
+
 // the class table of src/python/c/factory.template.h; the header is generated by build.py from that
 // template with N_POTENTIAL_CLASSES = the number of entries below
 extern "C" {
@@ -829,7 +1011,20 @@ potential_class_t potential_classes[N_POTENTIAL_CLASSES] = {
     BOP_CLASS("Brenner", ATX_BOP_BRENNER, false),   BOP_CLASS("BrennerScr", ATX_BOP_BRENNER, true),
     {"TabulatedAlloyEAM", eam_new, eam_free, eam_register_data, eam_init, eam_bind_to, nullptr, nullptr, nullptr,
      eam_energy_and_forces},
+    {"Rebo2", rebo2_new<false>, rebo2_free, eam_register_data, rebo2_init, rebo2_bind_to, nullptr, nullptr, nullptr,
+     rebo2_energy_and_forces},
+    {"Rebo2Scr", rebo2_new<true>, rebo2_free, eam_register_data, rebo2_init, rebo2_bind_to, nullptr, nullptr, nullptr,
+     rebo2_energy_and_forces},
+#define PAIR_CLASS(W) \
+  {"", pair_new<W>, pair_free, eam_register_data, pair_init, pair_bind_to, nullptr, nullptr, nullptr, pair_energy_and_forces}
+    PAIR_CLASS(0), PAIR_CLASS(1), PAIR_CLASS(2), PAIR_CLASS(3), PAIR_CLASS(4),
 };
+// the pair classes take their names from PAIR_SPECS
+static struct PairNames {
+  PairNames() {
+    for (int w = 0; w < 5; w++) strncpy(potential_classes[9 + w].name, PAIR_SPECS[w].name, MAX_NAME);
+  }
+} g_pair_names;
 #include "coulomb_factory_c.h"
 coulomb_class_t coulomb_classes[N_COULOMB_CLASSES];
 }

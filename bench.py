@@ -597,7 +597,12 @@ def block_c4(args, dist, L, ctx):
             'nl_pairs_fill', 'nl_reverse_index')}
         if world > 1:
             blk['p2p'] = st['p2p']
-            blk['rebuild_host_ms_since_create'] = st['rebuild_host_ms']
+            nreb = max(st['nrebuilds'] - st0['nrebuilds'], 1)
+            blk['rebuild_host_ms_per_rebuild'] = [(a - b) / nreb for a, b in zip(st['rebuild_host_ms'],
+                                                                                 st0['rebuild_host_ms'])]
+            blk['rebuild_phases'] = ('migration select + counts, -, migration transfer, ghost select + counts, -, '
+                                     'ghost transfer, local list + renumbering, first force evaluation; host wall time, '
+                                     'exact per phase only with ATX_DD_PROFILE=1')
         if world == 1:
             alg = nat * (68.0 + 16.0 * z)
             bop_n = steps + (st['nrebuilds'] - st0['nrebuilds'])    # executed evaluations (see block_c2)

@@ -29,7 +29,8 @@ def mod():
 def test_module_exports(mod):
     """the reference's extension types, created by its own atomisticamodule.c from potential_classes[]"""
     for name in ('Particles', 'Neighbors', 'Tersoff', 'TersoffScr', 'Kumagai', 'KumagaiScr', 'Brenner', 'BrennerScr',
-                 'TabulatedAlloyEAM', 'startup', 'shutdown', 'set_logfile', 'pair_distribution'):
+                 'TabulatedAlloyEAM', 'Rebo2', 'Rebo2Scr', 'LJCut', 'Harmonic', 'DoubleHarmonic', 'BornMayer', 'r6',
+                 'startup', 'shutdown', 'set_logfile', 'pair_distribution'):
         assert hasattr(mod, name), name
     assert mod.Tersoff.__name__ == 'Tersoff'
 
@@ -200,3 +201,35 @@ def test_per_atom_and_per_bond_outputs(mod):
     el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
     o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.TERSOFF, db), a.positions, a.cell, onl, el, per_at=True)
     assert np.abs(epa - o['epot_per_at']).max() <= 1e-10 * np.abs(o['epot_per_at']).max()
+
+
+@pytest.mark.gpu
+def test_rebo2_and_pair_classes(mod):
+    """Rebo2 / Rebo2Scr (default parameter block generated at build time) and LJCut through the module == oracle"""
+    import oracle
+    d = load_npz('aC_small.npz')
+    a = S.Atoms([str(s) for s in d['symbols']], d['positions'], d['cell'], True)
+    for cls, ocls, avgn in ((mod.Rebo2, oracle.Rebo2, 100), (mod.Rebo2Scr, oracle.Rebo2Scr, 1000)):
+        p, nl, e, f, w = _calc(mod, cls(), a, avgn=avgn)
+        rb = ocls()
+        onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, rb.cutoff(a.symbols), avgn)
+        o = rb.energy_and_forces(a.positions, a.cell, onl, rb.ktyp(a.symbols))
+        assert abs(e - o['epot']) <= 1e-10 * abs(o['epot'])
+        assert np.abs(f - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
+    with pytest.raises(RuntimeError):
+        pot = mod.Rebo2()
+        p = _particles(mod, a)
+        nl = mod.Neighbors(100)
+        pot.bind_to(p, nl)
+        pot.energy_and_forces(p, nl, mask=np.ones(len(a), dtype=np.int32))
+    au = S.fcc('Au', 4.07, (3, 3, 3))
+    au.rattle(0.05, seed=4)
+    p, nl, e, f, w = _calc(mod, mod.LJCut(el1='Au', el2='Au', epsilon=1.0, sigma=2.6, cutoff=6.0), au, avgn=200)
+    assert np.isfinite(e) and e < 0.0 and np.abs(f.sum(axis=0)).max() < 1e-9
+    from atomistica_b200 import native
+    pn = native.from_atoms(au)
+    nn = native.Neighbors(200)
+    lj = native.LJCut(el1='Au', el2='Au', epsilon=1.0, sigma=2.6, cutoff=6.0)
+    lj.bind_to(pn, nn)
+    e2, f2 = lj.energy_and_forces(pn, nn)[:2]
+    assert abs(e - e2) <= 1e-12 * abs(e2) and np.abs(f - f2).max() <= 1e-12 * max(1.0, np.abs(f2).max())

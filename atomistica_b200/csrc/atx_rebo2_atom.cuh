@@ -12,7 +12,7 @@ struct __align__(16) RbBond {
   double4 vec;   // unit vector i -> j and bond length
   double2 cut;   // cutoff function and its derivative
   int nb;        // neighbour (sorted numbering)
-  int typ;       // pair type
+  int typ;       // pair type in bits 0..7, REBO2 element type of the neighbour (RB_C / RB_H) in bits 8..15
   int shift;     // packed periodic shift
   int slot;      // position in the atom's range of the pair list
 };
@@ -82,7 +82,7 @@ __device__ __forceinline__ void rb_bonds_atom(int nbs, const Mat3 &A, const Rebo
       if (nb >= nbs || nb >= RB_NBL) { RBS_OR(flag, 1); break; }
       size_t q = (size_t)s * nbs + nb;
       b_tab[q].nb = en.x;
-      b_tab[q].typ = ijpot;
+      b_tab[q].typ = ijpot | (tj << 8);
       b_tab[q].shift = en.y;
       b_tab[q].slot = (int)(a - b0);
       b_tab[q].vec = make_double4(dx / rl, dy / rl, dz / rl, rl);
@@ -126,7 +126,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
     double nconjit = 0.0;
     for (int ik = 0; ik < nbi; ik++) {
       int k = b_tab[qi + ik].nb;
-      int tk = P.el2typ[(int)pos4[k].w];
+      int tk = b_tab[qi + ik].typ >> 8;
       fxik[ik] = 0.0;
       dncx[ik] = 0.0;
       if (tk == RB_C) {
@@ -150,11 +150,11 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       // the index comparison is made in ORIGINAL atom numbering so that per-bond outputs land in
       // the same list slot as in the reference
       if (!((zero && order[j] > order[i]) || pos)) continue;
-      const int ijpot = b_tab[qi + ij].typ;
+      const int ijpot = b_tab[qi + ij].typ & 255;
       const double4 vij = b_tab[qi + ij].vec;
       const double rlij = vij.w;
       if (!(rlij < P.cut_h[ijpot])) continue;
-      const int ktypj = P.el2typ[(int)pos4[j].w];
+      const int ktypj = b_tab[qi + ij].typ >> 8;
       const double rlijr = 1.0 / rlij;
       const double nx = vij.x, ny = vij.y, nz = vij.z;
       const double rijx = rlij * nx, rijy = rlij * ny, rijz = rlij * nz;
@@ -188,7 +188,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
           nconji = nconjit - cik.x * fxik[ik];
           continue;
         }
-        const int ikpot = b_tab[qi + ik].typ;
+        const int ikpot = b_tab[qi + ik].typ & 255;
         const double4 vik = b_tab[qi + ik].vec;
         const double rlik = vik.w;
         if (!(rlik < P.cut_h[ikpot])) {
@@ -252,8 +252,8 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
         atx_unpack_shift(b_tab[qj + jl].shift, lsx, lsy, lsz);
         lsx += jsx; lsy += jsy; lsz += jsz;
         if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;   // l_neq_i
-        const int ktypl = P.el2typ[(int)pos4[l].w];
-        const int jlpot = b_tab[qj + jl].typ;
+        const int ktypl = b_tab[qj + jl].typ >> 8;
+        const int jlpot = b_tab[qj + jl].typ & 255;
         const double4 vjl = b_tab[qj + jl].vec;
         const double rljl = vjl.w;
         const double lx = vjl.x, ly = vjl.y, lz = vjl.z;
@@ -394,7 +394,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
       for (int ik = 0; ik < nbi; ik++) {
         if (ik == ij) continue;
         const int k = b_tab[qi + ik].nb;
-        const int tk = P.el2typ[(int)pos4[k].w];
+        const int tk = b_tab[qi + ik].typ >> 8;
         const double4 vik = b_tab[qi + ik].vec;
         const double2 cik = b_tab[qi + ik].cut;
         // dnidk(:, ikc, type) = rnik*dfcikr for the type of k, 0 for the other type
@@ -434,7 +434,7 @@ __device__ __forceinline__ void rb_force_atom(int nat, int nbs, const Rebo2Dev &
         atx_unpack_shift(b_tab[qj + jl].shift, lsx, lsy, lsz);
         lsx += jsx; lsy += jsy; lsz += jsz;
         if (l == i && lsx == 0 && lsy == 0 && lsz == 0) continue;
-        const int tl = P.el2typ[(int)pos4[l].w];
+        const int tl = b_tab[qj + jl].typ >> 8;
         const double4 vjl = b_tab[qj + jl].vec;
         const double2 cjl = b_tab[qj + jl].cut;
         const double sC = (tl == RB_C) ? cjl.y : 0.0, sH = (tl == RB_H) ? cjl.y : 0.0;
@@ -527,7 +527,7 @@ __device__ __forceinline__ int rb_owned_bonds(int nbs, const Rebo2Dev &P, const 
     const bool zero = (jsx == 0 && jsy == 0 && jsz == 0);
     const bool pos = jsx != 0 ? jsx > 0 : (jsy != 0 ? jsy > 0 : jsz > 0);
     if (!((zero && order[j] > order[i]) || pos)) continue;
-    if (!(b_tab[qi + ij].vec.w < P.cut_h[b_tab[qi + ij].typ])) continue;
+    if (!(b_tab[qi + ij].vec.w < P.cut_h[b_tab[qi + ij].typ & 255])) continue;
     if (out) out[n] = make_int2(i, ij);
     n++;
   }

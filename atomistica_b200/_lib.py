@@ -73,6 +73,8 @@ SYMBOLS = [
     'atx_neighbors_create', 'atx_neighbors_destroy', 'atx_neighbors_request_interaction_range',
     'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_rebuild', 'atx_neighbors_get_info', 'atx_neighbors_get_counters',
     'atx_neighbors_copy_to_host', 'atx_neighbors_set_external',
+    'atx_neighbors_coordination_numbers', 'atx_neighbors_pair_distribution', 'atx_neighbors_angle_distribution',
+    'atx_neighbors_bond_angles',
     'atx_eam_create', 'atx_eam_create_funcfl', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
     'atx_eam_set_store_outputs', 'atx_bop_set_store_outputs', 'atx_rebo2_set_store_outputs',
     'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_create_juslin', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',

@@ -101,6 +101,17 @@ int atx_neighbors_set_external(atx_neighbors *nl, atx_particles *p, int natloc, 
                                const int *ilist, const int *numneigh, const int *const *firstneigh);
 /* number of list builds and of updates answered without a rebuild (Verlet shell, neighbors.f90:552-590) */
 int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long *nreused);
+/* List post-processing on the device-resident list (no copy-back of the list):
+ * f_get_coordination_numbers (src/python/f90/neighbors_wrap.f90:271-302; c[nat], original atom order) and
+ * the helpers of src/python/c/analysis.c -- pair_distribution (:29-106), angle_distribution (:108-206),
+ * bond_angles (:208-318) -- over ALL entries of the list (the reference applies them to the (i, j, r)
+ * arrays of get_neighbors).  h / h2: mean and variance per bin (nbins doubles each), m[nat]. */
+int atx_neighbors_coordination_numbers(atx_neighbors *nl, atx_particles *p, double cutoff, int *c);
+int atx_neighbors_pair_distribution(atx_neighbors *nl, atx_particles *p, int nbins, double cutoff,
+                                    double *h, double *h2);
+int atx_neighbors_angle_distribution(atx_neighbors *nl, atx_particles *p, int nbins, double cutoff,
+                                     double *h, double *h2);
+int atx_neighbors_bond_angles(atx_neighbors *nl, atx_particles *p, int moment, double cutoff, double *m);
 /* host view of the list in the reference's layout and order (seed(nat+1), last(nat+1),
  * neighbors(capacity), dc(3,capacity)); used by f_get_all_neighbors & co
  * (src/python/f90/neighbors_wrap.f90:211-550) */

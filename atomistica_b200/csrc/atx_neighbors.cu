@@ -946,6 +946,13 @@ extern "C" int atx_neighbors_get_info(atx_neighbors *nl, long long *npairs, int 
   return 0;
 }
 
+extern "C" int atx_neighbors_get_interaction_range(atx_neighbors *nl, double *range, double *verlet_shell) {
+  if (!nl) return ATX_ERROR_UNSPECIFIED;
+  if (range) *range = nl->interaction_range;
+  if (verlet_shell) *verlet_shell = nl->verlet_shell;
+  return 0;
+}
+
 extern "C" int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long *nreused) {
   if (!nl) return ATX_ERROR_UNSPECIFIED;
   if (nbuilds) *nbuilds = nl->nbuilds;

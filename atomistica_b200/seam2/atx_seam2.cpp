@@ -998,6 +998,7 @@ static void pair_energy_and_forces(void *self, void *pp, void *nn, double *, dou
   CHK(atx_pair_energy_and_forces(q->h, p->h, n->h, (int *)mask_, epot, f, (double *)wpot_, epot_per_at, wpot_per_at), ierror);
 }
 
+#ifndef ATX_SEAM2_LAMMPS   // atx_lammps.cpp includes this file and supplies the LAMMPS-flavour table instead
 // the class table of src/python/c/factory.template.h; the header is generated by build.py from that
 // template with N_POTENTIAL_CLASSES = the number of entries below
 extern "C" {
@@ -1028,3 +1029,4 @@ static struct PairNames {
 #include "coulomb_factory_c.h"
 coulomb_class_t coulomb_classes[N_COULOMB_CLASSES];
 }
+#endif  // ATX_SEAM2_LAMMPS

@@ -388,11 +388,15 @@ def prime(drv, nreb=2):
     return done
 
 
-def timed_run(dist, L, ctx, drv, steps):
+def timed_run(dist, L, ctx, drv, steps, profile=False):
+    """K steps between barriers, device time of the whole run (CUDA events on the compute stream inside
+    the driver, max over ranks).  profile=True additionally brackets every kernel with an event pair
+    (atx_profile_*); those runs give the per-kernel times, never the headline numbers -- the event pairs
+    cost a few microseconds per launch."""
     dist.barrier()
     L.check(L.lib().atx_ctx_synchronize(ctx))
     L.kernel_launches(reset=True)
-    L.check(L.lib().atx_profile_enable(ctx, 1))
+    L.check(L.lib().atx_profile_enable(ctx, 1 if profile else 0))
     t0 = time.perf_counter()
     epot, ekin = drv.run(steps)
     wall = time.perf_counter() - t0
@@ -434,6 +438,10 @@ def block_c2(args, dist, L, ctx):
     epot, ekin, dev_ms, wall, launches = timed_run(dist, L, ctx, drv, steps)
     st = drv.stats()
     rebuilds = st['nrebuilds'] - st0['nrebuilds']
+    # the same K steps again with an event pair around every kernel: per-kernel times for the roofline
+    _, _, prof_ms, _, _ = timed_run(dist, L, ctx, drv, steps, profile=True)
+    prof_rebuilds = drv.stats()['nrebuilds'] - st['nrebuilds']
+    st = drv.stats()
     force_ms, force_n = prof_read(L, ctx, 'eam_force')
     dens_ms, dens_n = prof_read(L, ctx, 'eam_density')
     cnt_ms, _ = prof_read(L, ctx, 'nl_pairs_count')
@@ -452,7 +460,7 @@ def block_c2(args, dist, L, ctx):
     st1 = drv.stats()
     e_ss, k_ss, ss_ms, _, _ = timed_run(dist, L, ctx, drv, ss_steps)
     ss_reb = drv.stats()['nrebuilds'] - st1['nrebuilds']
-    total_steps = primed + warm + steps + ss_steps
+    total_steps = primed + warm + 2 * steps + ss_steps
 
     parity = None
     if world > 1:
@@ -498,7 +506,7 @@ def block_c2(args, dist, L, ctx):
     alg_bytes = nat * (68.0 + 16.0 * z_list)          # B_eam = 68 + 16 z per atom
     # launches that really ran: one force evaluation per step + one per rebuild (the optimistic batches
     # also enqueue steps that exit at once after a rebuild was requested; they carry no time)
-    force_n = steps + rebuilds
+    force_n = steps + prof_rebuilds
     force_avg_ms = force_ms / max(force_n, 1)
     achieved = alg_bytes / (force_avg_ms * 1e-3) / 1e9
     fp64 = C.c_double(0.0)
@@ -529,10 +537,13 @@ def block_c2(args, dist, L, ctx):
         roofline=dict(bound='hbm', kernel='k_eam_force_fast<4,2,VIRIAL=0,MAP=1>', achieved=achieved, peak=peak,
                       unit='GB/s', frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                       algorithmic_bytes_per_launch=alg_bytes, avg_launch_ms=force_avg_ms, launches=force_n,
-                      list_neighbors_per_atom=z_list, share_of_step=force_ms / dev_ms if dev_ms else None,
+                      list_neighbors_per_atom=z_list, share_of_step=force_ms / prof_ms if prof_ms else None,
+                      measured_in='an instrumented repeat of the K timed steps (event pair around every kernel; '
+                                  '%.4f ms/step against %.4f ms/step un-instrumented)' % (prof_ms / steps, dev_ms / steps),
                       whole_step_frac=alg_bytes / (dev_ms / steps * 1e-3) / 1e9 / peak, fp64=fp64_block),
         kernels_ms=dict(eam_force=force_ms, eam_density=dens_ms, nl_pairs_count=cnt_ms, nl_pairs_fill=fill_ms,
-                        total_device=dev_ms, dd=dd_prof),
+                        total_device=prof_ms, rebuilds=prof_rebuilds, dd=dd_prof,
+                        note='instrumented repeat of the K steps'),
         fp64_peak_tflops_measured=fp64.value,
         md=dict(epot=epot, ekin=ekin, rebuilds=rebuilds, wall_s=wall, owned_atoms_rank0=nown,
                 ghost_atoms_rank0=nghost, priming_steps_untimed=primed,
@@ -581,6 +592,8 @@ def block_c4(args, dist, L, ctx):
         st0 = drv.stats()
         epot, ekin, ms, wall, launches = timed_run(dist, L, ctx, drv, steps)
         st = drv.stats()
+        epot, ekin, pms, _, _ = timed_run(dist, L, ctx, drv, steps, profile=True)    # per-kernel times
+        stp = drv.stats()
         bop_ms, bop_n = prof_read(L, ctx, 'bop_force')
         halo_ms = prof_read(L, ctx, 'dd_halo')[0] if world > 1 else 0.0
         z = nl.info()['npairs'] / nat if world == 1 else None
@@ -591,21 +604,22 @@ def block_c4(args, dist, L, ctx):
                    rebuilds=st['nrebuilds'] - st0['nrebuilds'], owned_atoms_rank0=counts[0],
                    ghost_atoms_rank0=counts[1], gpu_launches=launches,
                    bop_force_ms_per_step_rank0=bop_ms / steps, dd_halo_ms_per_step_rank0=halo_ms / steps,
+                   instrumented_ms_per_step=pms / steps,
                    epot_per_atom=epot / ntot)
         blk['scopes_ms_per_step_rank0'] = {k: prof_read(L, ctx, k)[0] / steps for k in (
             'bop_force', 'bop_gather', 'dd_drift', 'dd_halo', 'dd_refresh', 'dd_kick', 'nl_update', 'nl_pairs_count',
             'nl_pairs_fill', 'nl_reverse_index')}
         if world > 1:
             blk['p2p'] = st['p2p']
-            nreb = max(st['nrebuilds'] - st0['nrebuilds'], 1)
-            blk['rebuild_host_ms_per_rebuild'] = [(a - b) / nreb for a, b in zip(st['rebuild_host_ms'],
+            nreb = max(stp['nrebuilds'] - st0['nrebuilds'], 1)
+            blk['rebuild_host_ms_per_rebuild'] = [(a - b) / nreb for a, b in zip(stp['rebuild_host_ms'],
                                                                                  st0['rebuild_host_ms'])]
             blk['rebuild_phases'] = ('migration select + counts, -, migration transfer, ghost select + counts, -, '
                                      'ghost transfer, local list + renumbering, first force evaluation; host wall time, '
                                      'exact per phase only with ATX_DD_PROFILE=1')
         if world == 1:
             alg = nat * (68.0 + 16.0 * z)
-            bop_n = steps + (st['nrebuilds'] - st0['nrebuilds'])    # executed evaluations (see block_c2)
+            bop_n = steps + (stp['nrebuilds'] - st['nrebuilds'])    # executed evaluations (see block_c2)
             avg = bop_ms / max(bop_n, 1)
             rf = dict(kernel='k_bop_center<%s>' % kind, avg_launch_ms=avg, launches=bop_n,
                       list_neighbors_per_atom=z,
@@ -632,7 +646,7 @@ def block_c4(args, dist, L, ctx):
                 return md.VelocityVerlet(pot1, p1, nl1, np.full(len(gpos), MASS_SI), gvel, dt=1.0,
                                          verlet_shell=C4_SKIN)
             if not args.no_parity:
-                blk['parity'] = parity_block(dist, drv, epot, ekin, ref_factory, primed + 3 + steps)
+                blk['parity'] = parity_block(dist, drv, epot, ekin, ref_factory, primed + 3 + 2 * steps)
         res[kind] = blk
         del drv, pot
         dist.barrier()

@@ -101,6 +101,9 @@ int atx_neighbors_set_external(atx_neighbors *nl, atx_particles *p, int natloc, 
                                const int *ilist, const int *numneigh, const int *const *firstneigh);
 /* number of list builds and of updates answered without a rebuild (Verlet shell, neighbors.f90:552-590) */
 int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long *nreused);
+/* largest interaction range requested so far (neighbors_request_interaction_range,
+ * python_neighbors.f90:381-423 / lammps_neighbors.f90:223-251) and the Verlet shell */
+int atx_neighbors_get_interaction_range(atx_neighbors *nl, double *range, double *verlet_shell);
 /* List post-processing on the device-resident list (no copy-back of the list):
  * f_get_coordination_numbers (src/python/f90/neighbors_wrap.f90:271-302; c[nat], original atom order) and
  * the helpers of src/python/c/analysis.c -- pair_distribution (:29-106), angle_distribution (:108-206),

@@ -85,7 +85,7 @@ SYMBOLS = [
     'atx_dd_get_unique_id', 'atx_dd_create', 'atx_dd_destroy', 'atx_dd_md_create', 'atx_dd_md_destroy',
     'atx_dd_md_run', 'atx_dd_md_get_count', 'atx_dd_md_get_state', 'atx_dd_md_get_stats', 'atx_dd_md_get_profile',
     'atx_profile_enable', 'atx_profile_read', 'atx_measure_fp64_peak', 'atx_measure_copy_bandwidth',
-    'atx_host_alloc_pinned', 'atx_host_free_pinned',
+    'atx_host_alloc_pinned', 'atx_host_free_pinned', 'atx_host_register', 'atx_host_unregister',
     'atx_host_spline_init', 'atx_host_gaussn', 'atx_host_table2d_init', 'atx_host_table3d_init',
     'atx_host_rebo2_g_spline',
 ]

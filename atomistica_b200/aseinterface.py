@@ -18,7 +18,8 @@ class Atomistica:
     potential_class = None
     avgn = 100
 
-    def __init__(self, potentials=None, avgn=None, device=0, verlet_shell=0.0, zero_copy=False, **kwargs):
+    def __init__(self, potentials=None, avgn=None, device=0, verlet_shell=0.0, zero_copy=False,
+                 alias_positions=True, **kwargs):
         """verlet_shell > 0 (Angstrom) keeps the neighbour list between calls until an atom has moved
         verlet_shell/2 from where it was at the last build (checked on the device); 0 rebuilds on every
         change of the positions like the reference's Python host.
@@ -27,8 +28,16 @@ class Atomistica:
         (like the copy ase.calculators.calculator.Calculator.get_property returns): the library writes
         into a page-locked buffer that is only recycled once no outside reference to it (or to a view
         of it) is left; when more than MAX_FORCE_BUFFERS arrays are held at once the result is copied.
-        zero_copy=True skips that copy as well (the caller then must not keep more arrays than that)."""
+        zero_copy=True skips that copy as well (the caller then must not keep more arrays than that).
+
+        alias_positions: when two consecutive calls present the SAME positions buffer (ase.Atoms updates
+        its array in place), that buffer is page-locked where it lies and uploaded from directly instead
+        of being copied into a staging mirror first; a caller that switches to another array falls back
+        to the mirror.  The contents are read during the call only."""
         self.device = device
+        import os
+        self.alias_positions = bool(alias_positions) and os.environ.get('ATX_ALIAS_POSITIONS', '1') != '0'
+        self._pos_seen = None
         self.zero_copy = bool(zero_copy)
         self.verlet_shell = float(verlet_shell)
         self.pots = potentials if potentials is not None else [self.potential_class(device=device, **kwargs)]
@@ -55,6 +64,9 @@ class Atomistica:
         if self.mask is not None and len(self.mask) != len(atoms):
             raise RuntimeError('Length of mask array (= {0}) does not equal number of atoms (= {1}).'
                                .format(len(self.mask), len(atoms)))
+        if self.particles is not None:
+            self.particles.unalias_coordinates()
+        self._pos_seen = None
         self.particles = native.Particles(self.device)
         self.particles.allocate(len(atoms))
         self.particles.set_cell(atoms.cell, atoms.pbc)
@@ -88,13 +100,29 @@ class Atomistica:
             self.initialize(atoms)
         if np.any(self.particles.cell != atoms.cell) or np.any(self.particles.pbc != atoms.pbc):
             self.particles.set_cell(atoms.cell, atoms.pbc)
-        positions = self.particles.coordinates
+        p = self.particles
         new = atoms.positions
+        key = None
+        if self.alias_positions and isinstance(new, np.ndarray) and new.dtype == np.float64 and \
+                new.flags.c_contiguous and new.flags.aligned and new.shape == (len(p), 3):
+            key = (new.ctypes.data, new.shape)
+        if p._alias is not None:
+            if key is not None and key == self._pos_seen:
+                p.I_changed_positions()        # the host's own page-locked array: upload, no mirror copy
+                return
+            p.unalias_coordinates()            # the host switched to another array: back to the mirror
+        elif key is not None and key == self._pos_seen:
+            # the same buffer twice in a row: from now on it is r_non_cyc itself
+            if p.alias_coordinates(new):
+                return
+            self.alias_positions = False       # cannot be page-locked here: keep the mirror for good
+        self._pos_seen = key
+        positions = p.coordinates
         # "did anything move?"  In MD every atom moves, so a strided sample answers it for 1/64 of
         # the cost; only when the sample is unchanged is the full comparison needed.
         if np.any(positions[::64] != new[::64]) or np.any(positions != new):
             positions[:, :] = new
-            self.particles.I_changed_positions()
+            p.I_changed_positions()
 
     MAX_FORCE_BUFFERS = 8
 

@@ -142,6 +142,40 @@ extern "C" int atx_host_free_pinned(void *ptr) {
   return 0;
 }
 
+extern "C" int atx_host_register(void *ptr, size_t bytes, int *already) {
+  if (already) *already = 0;
+  if (!ptr || !bytes) return ATX_ERROR_UNSPECIFIED;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    atx_set_error("No CUDA device available: host memory cannot be page-locked (no CPU fallback).");
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+    if (already) *already = 1;   // cudaMallocHost / cudaHostAlloc memory, or registered by somebody else
+    return 0;
+  }
+  cudaGetLastError();
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {
+    cudaGetLastError();
+    if (already) *already = 1;
+    return 0;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    atx_set_error(std::string("cudaHostRegister failed: ") + cudaGetErrorString(e));
+    return ATX_ERROR_UNSPECIFIED;
+  }
+  return 0;
+}
+
+extern "C" int atx_host_unregister(void *ptr) {
+  if (ptr && cudaHostUnregister(ptr) != cudaSuccess) cudaGetLastError();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------
 // scans
 // ---------------------------------------------------------------------------

@@ -255,6 +255,54 @@ __global__ void k_dd_drift(int nown, double dt, double *__restrict__ r, double *
   }
 }
 
+// Velocity-Verlet in leapfrog form for the steps inside a run: the second half kick of step n and the
+// first half kick of step n + 1 use the same force, so one kernel applies both (scale = 1; 0.5 for the
+// first step of a run, whose state has whole-step velocities) and drifts.  The force is read from the
+// potential's sorted output, the position goes to the local array (halo packing, rebuilds) and to
+// the sorted record.  The whole-step velocity, the local force array and the energy sums are
+// produced once, by k_dd_kick at the end of the run.
+__global__ void k_dd_kickdrift(int nown, double dt, double scale, double *__restrict__ r, double *__restrict__ v,
+                               const double *__restrict__ fs, const double *__restrict__ minv,
+                               DdCtrl *__restrict__ ctrl, const int *__restrict__ inv,
+                               double4 *__restrict__ pos4) {
+  if (ctrl->stop) return;
+  __shared__ double red[8];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (i < nown) {
+    const int s = inv[i];
+    double a = scale * minv[i] * ATX_ACCEL_CONV * dt;
+    double vx = v[3 * i] + a * fs[3 * s], vy = v[3 * i + 1] + a * fs[3 * s + 1], vz = v[3 * i + 2] + a * fs[3 * s + 2];
+    v[3 * i] = vx; v[3 * i + 1] = vy; v[3 * i + 2] = vz;
+    double dx = vx * dt, dy = vy * dt, dz = vz * dt;
+    const double x = r[3 * i] + dx, y = r[3 * i + 1] + dy, z = r[3 * i + 2] + dz;
+    r[3 * i] = x; r[3 * i + 1] = y; r[3 * i + 2] = z;
+    double *q = reinterpret_cast<double *>(pos4 + s);
+    q[0] = x; q[1] = y; q[2] = z;
+    d2 = dx * dx + dy * dy + dz * dz;
+  }
+  for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, red[w]);
+    atomicMax(&ctrl->stepmax_bits, (unsigned long long)__double_as_longlong(m));
+    __threadfence();
+    unsigned int done = atomicAdd(&ctrl->counter_drift, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      double mx = __longlong_as_double((long long)atomicAdd(&ctrl->stepmax_bits, 0ull));
+      double acc = ctrl->accum_max_dr + sqrt(mx);
+      ctrl->accum_max_dr = acc;
+      ctrl->stepmax_bits = 0ull;
+      ctrl->counter_drift = 0u;
+      ctrl->want = (2.0 * acc >= ctrl->verlet_shell) ? 1 : 0;
+      ctrl->seq += 1ull;
+    }
+  }
+}
+
 // ranks with no owned atoms still have to publish a wish
 __global__ void k_dd_nowish(DdCtrl *ctrl) {
   if (!ctrl->stop) {
@@ -308,7 +356,7 @@ k_dd_pack_p2p(int nL, int nR, const int *__restrict__ idxL, const int *__restric
 // One warp: lane p waits for rank p's signal of this step; the OR of the wishes becomes the stop flag
 // (identical on every rank).  A signal that does not arrive within ~4 s (a peer failed) raises
 // ctrl->err and stops the batch instead of hanging the device.
-__global__ void k_dd_wait(const unsigned long long *sig, int P, DdCtrl *ctrl) {
+__global__ void k_dd_wait(const unsigned long long *sig, int P, DdCtrl *ctrl, int count_step) {
   if (ctrl->stop) return;
   const unsigned long long seq = ctrl->seq;
   const int lane = threadIdx.x;
@@ -330,6 +378,8 @@ __global__ void k_dd_wait(const unsigned long long *sig, int P, DdCtrl *ctrl) {
   if (lane == 0) {
     if (bad) { ctrl->err = 1; ctrl->stop = 1; }
     else ctrl->stop = want;
+    // leapfrog form: nothing can stop this step any more, so it is counted here (no kick kernel follows)
+    if (count_step && !bad && !want) ctrl->steps_done += 1;
   }
 }
 
@@ -374,7 +424,7 @@ __global__ void k_dd_refresh(int n, const double *__restrict__ r, const int *__r
 __global__ void k_dd_kick(int nown, double dt, double *__restrict__ v, const double *__restrict__ fs,
                           const double *__restrict__ epa_s, const int *__restrict__ inv,
                           const double *__restrict__ minv, double *__restrict__ f_loc,
-                          double *__restrict__ partials, DdCtrl *__restrict__ ctrl) {
+                          double *__restrict__ partials, DdCtrl *__restrict__ ctrl, int count_step) {
   if (ctrl->stop) return;
   __shared__ double red[16];
   __shared__ bool is_last;
@@ -427,16 +477,16 @@ __global__ void k_dd_kick(int nown, double dt, double *__restrict__ v, const dou
       ctrl->ekin = tt;
       ctrl->epot = uu;
       ctrl->counter_kick = 0u;
-      ctrl->steps_done += 1;
+      ctrl->steps_done += count_step;
     }
   }
 }
 
-__global__ void k_dd_empty_step(DdCtrl *ctrl) {
+__global__ void k_dd_empty_step(DdCtrl *ctrl, int count_step) {
   if (ctrl->stop) return;
   ctrl->ekin = 0.0;
   ctrl->epot = 0.0;
-  ctrl->steps_done += 1;
+  ctrl->steps_done += count_step;
 }
 
 // flags for migration / ghost selection; s = Bbox(1,:) . (r + torig) is the fractional coordinate
@@ -1000,7 +1050,7 @@ static int dd_reset_ctrl(atx_ddmd *md) {
   return 0;
 }
 
-static int dd_kick(atx_ddmd *md) {
+static int dd_kick(atx_ddmd *md, int count_step = 1) {
   ProfScope ps_(md->ctx, "dd_kick");
   cudaStream_t st = md->ctx->stream;
   int n = md->nown;
@@ -1008,9 +1058,9 @@ static int dd_kick(atx_ddmd *md) {
     int gb = (n + 255) / 256;
     ATX_PASS(md->kin_partials.reserve(2 * (size_t)gb + 2));
     k_dd_kick<<<gb, 256, 0, st>>>(n, md->dt, md->v.ptr, md->tmpd.ptr, md->epa.ptr, md->nl->inv.ptr, md->minv.ptr,
-                                  md->f.ptr, md->kin_partials.ptr, md->ctrl.ptr);
+                                  md->f.ptr, md->kin_partials.ptr, md->ctrl.ptr, count_step);
   } else {
-    k_dd_empty_step<<<1, 1, 0, st>>>(md->ctrl.ptr);
+    k_dd_empty_step<<<1, 1, 0, st>>>(md->ctrl.ptr, count_step);
   }
   ATX_LAUNCHED();
   return 0;
@@ -1231,7 +1281,8 @@ extern "C" int atx_dd_md_destroy(atx_ddmd *md) {
   return 0;
 }
 
-static int dd_enqueue_step(atx_ddmd *md) {
+// scale: 0 = separate drift and kick kernels; 0.5 / 1 = leapfrog form (first / later step of a run)
+static int dd_enqueue_step(atx_ddmd *md, double scale) {
   ProfScope ps_step(md->ctx, "dd_step");
   atx_dd *dd = md->dd;
   cudaStream_t st = md->ctx->stream;
@@ -1239,7 +1290,10 @@ static int dd_enqueue_step(atx_ddmd *md) {
   const int *stop = &md->ctrl.ptr->stop;
   {
     ProfScope ps_(md->ctx, "dd_drift");
-    if (n > 0) {
+    if (n > 0 && scale > 0.0) {
+      k_dd_kickdrift<<<(n + 255) / 256, 256, 0, st>>>(n, md->dt, scale, md->r.ptr, md->v.ptr, md->tmpd.ptr,
+                                                      md->minv.ptr, md->ctrl.ptr, md->nl->inv.ptr, md->nl->pos4.ptr);
+    } else if (n > 0) {
       const bool fuse = dd->nranks > 1 && md->p2p;
       k_dd_drift<<<(n + 255) / 256, 256, 0, st>>>(n, md->dt, md->r.ptr, md->v.ptr, md->f.ptr, md->minv.ptr,
                                                   md->ctrl.ptr, fuse ? md->nl->inv.ptr : nullptr,
@@ -1266,7 +1320,7 @@ static int dd_enqueue_step(atx_ddmd *md) {
       ATX_LAUNCHED();
       // interior centres do not depend on this step's ghost positions: they run while the halo travels
       if (md->split) ATX_PASS(dd_compute(md, true, 1));
-      k_dd_wait<<<1, 32, 0, st>>>((const unsigned long long *)md->mbox, dd->nranks, md->ctrl.ptr);
+      k_dd_wait<<<1, 32, 0, st>>>((const unsigned long long *)md->mbox, dd->nranks, md->ctrl.ptr, scale > 0.0 ? 1 : 0);
       ATX_LAUNCHED();
     }
     if (nloc > n) {
@@ -1276,7 +1330,7 @@ static int dd_enqueue_step(atx_ddmd *md) {
       ATX_LAUNCHED();
     }
     ATX_PASS(dd_compute(md, true, md->split ? 2 : 0));
-    ATX_PASS(dd_kick(md));
+    if (scale == 0.0) ATX_PASS(dd_kick(md));
     return 0;
   }
   if (dd->nranks > 1) {
@@ -1328,9 +1382,17 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
   ATX_CUDA(cudaMemcpyAsync(&md->ctrl.ptr->steps_done, &md->hctrl.ptr->steps_done, sizeof(int),
                            cudaMemcpyHostToDevice, st));
   int remaining = nsteps, done_total = 0;
+  // leapfrog form of the step (one kick-and-drift kernel, no per-step kick / energy reduction) on the
+  // peer-to-peer path; ATX_DD_FUSED=0 keeps the separate kernels
+  static const bool fused_ok = !(getenv("ATX_DD_FUSED") && atoi(getenv("ATX_DD_FUSED")) == 0);
+  const bool fused = fused_ok && dd->nranks > 1 && md->p2p && nsteps > 0;
+  bool first = true;
   while (remaining > 0) {
     int batch = remaining < md->batch ? remaining : md->batch;
-    for (int b = 0; b < batch; b++) ATX_PASS(dd_enqueue_step(md));
+    for (int b = 0; b < batch; b++) {
+      ATX_PASS(dd_enqueue_step(md, fused ? (first ? 0.5 : 1.0) : 0.0));
+      first = false;
+    }
     ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(DdCtrl), cudaMemcpyDeviceToHost, st));
     ATX_CUDA(cudaStreamSynchronize(st));
     ATX_CUDA(cudaGetLastError());
@@ -1348,17 +1410,19 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
       // the stop flag is global: every rank arrives here after the same step
       ATX_PASS(dd_rebuild(md));
       ATX_PASS(dd_build_list(md));
+      if (fused) md->hctrl.ptr->steps_done += 1;   // no kick kernel counts the step the rebuild completes
       ATX_PASS(dd_reset_ctrl(md));
       {
         DdTimer tm(md);
         ATX_PASS(dd_compute(md, false));
-        ATX_PASS(dd_kick(md));
+        if (!fused) ATX_PASS(dd_kick(md));
         tm.lap(7);
       }
       done_total += 1;
       remaining -= 1;
     }
   }
+  if (fused) ATX_PASS(dd_kick(md, 0));   // whole-step velocities, local force array, energy sums
   ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(DdCtrl), cudaMemcpyDeviceToHost, st));
   // global energies
   ATX_PASS(md->sums.reserve(ATX_NSUM));

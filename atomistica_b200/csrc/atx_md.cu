@@ -100,9 +100,55 @@ __global__ void k_md_drift(int nat, double dt, double4 *__restrict__ pos4, doubl
   }
 }
 
+// Velocity-Verlet in leapfrog form for the steps inside a run (verlet.f90:100-235 applies two half
+// kicks with the same force around the force evaluation; inside a run they are one update): scale = 1,
+// or 0.5 for the first step of a run, whose state has whole-step velocities.  The last block applies the
+// rebuild rule; a step that is not stopped here will complete, so it is counted here.  The
+// whole-step velocities and the energies are produced once, by k_md_kick at the end of the run.
+__global__ void k_md_kickdrift(int nat, double dt, double scale, double4 *__restrict__ pos4, double *__restrict__ v,
+                               const double *__restrict__ f, const double *__restrict__ minv,
+                               MdCtrl *__restrict__ ctrl) {
+  if (ctrl->stop) return;
+  __shared__ double red[8];
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double d2 = 0.0;
+  if (s < nat) {
+    double a = scale * minv[s] * ATX_ACCEL_CONV * dt;
+    double vx = v[3 * s] + a * f[3 * s];
+    double vy = v[3 * s + 1] + a * f[3 * s + 1];
+    double vz = v[3 * s + 2] + a * f[3 * s + 2];
+    v[3 * s] = vx; v[3 * s + 1] = vy; v[3 * s + 2] = vz;
+    double dx = vx * dt, dy = vy * dt, dz = vz * dt;
+    double4 p = pos4[s];
+    p.x += dx; p.y += dy; p.z += dz;
+    pos4[s] = p;
+    d2 = dx * dx + dy * dy + dz * dz;
+  }
+  for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmax(m, red[w]);
+    atomicMax(&ctrl->stepmax_bits, (unsigned long long)__double_as_longlong(m));
+    __threadfence();
+    unsigned int done = atomicAdd(&ctrl->counter_drift, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      double mx = __longlong_as_double((long long)atomicAdd(&ctrl->stepmax_bits, 0ull));
+      double acc = ctrl->accum_max_dr + sqrt(mx);
+      ctrl->accum_max_dr = acc;
+      ctrl->stepmax_bits = 0ull;
+      ctrl->counter_drift = 0u;
+      if (2.0 * acc >= ctrl->verlet_shell) ctrl->stop = 1;
+      else ctrl->steps_done += 1;
+    }
+  }
+}
+
 __global__ void k_md_kick(int nat, double dt, double *__restrict__ v, const double *__restrict__ f,
                           const double *__restrict__ minv, const double *__restrict__ sums,
-                          double *__restrict__ kin_partials, MdCtrl *__restrict__ ctrl) {
+                          double *__restrict__ kin_partials, MdCtrl *__restrict__ ctrl, int count_step) {
   if (ctrl->stop) return;
   __shared__ double red[8];
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,7 +191,7 @@ __global__ void k_md_kick(int nat, double dt, double *__restrict__ v, const doub
       ctrl->ekin = t;
       ctrl->epot = sums[0];
       ctrl->counter_kick = 0u;
-      ctrl->steps_done += 1;
+      ctrl->steps_done += count_step;
     }
   }
 }
@@ -360,15 +406,28 @@ extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
                              cudaMemcpyHostToDevice, st));
   }
   int done_total = 0;
+  // leapfrog form of the step (one kick-and-drift kernel per step, final half kick and energy sums once
+  // per run); ATX_MD_FUSED=0 keeps the separate drift and kick kernels
+  static const bool fused_ok = !(getenv("ATX_MD_FUSED") && atoi(getenv("ATX_MD_FUSED")) == 0);
+  const bool fused = fused_ok && nsteps > 0 && nat > 0;
+  bool first = true;
   while (remaining > 0) {
     int batch = remaining < md->batch ? remaining : md->batch;
     for (int b = 0; b < batch; b++) {
+      if (fused) {
+        k_md_kickdrift<<<gb, 256, 0, st>>>(nat, md->dt, first ? 0.5 : 1.0, nl->pos4.ptr, md->v.ptr, md->f.ptr,
+                                           md->minv.ptr, md->ctrl.ptr);
+        ATX_LAUNCHED();
+        first = false;
+        ATX_PASS(md_compute(md, true));
+        continue;
+      }
       k_md_drift<<<gb, 256, 0, st>>>(nat, md->dt, nl->pos4.ptr, md->v.ptr, md->f.ptr, md->minv.ptr,
                                      md->ctrl.ptr);
       ATX_LAUNCHED();
       ATX_PASS(md_compute(md, true));
       k_md_kick<<<gb, 256, 0, st>>>(nat, md->dt, md->v.ptr, md->f.ptr, md->minv.ptr, md->sums.ptr,
-                                    md->kin_partials.ptr, md->ctrl.ptr);
+                                    md->kin_partials.ptr, md->ctrl.ptr, 1);
       ATX_LAUNCHED();
     }
     ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
@@ -383,14 +442,23 @@ extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
     if (hc.stop) {
       // a drift tripped the rebuild rule: rebuild, then finish that step
       ATX_PASS(md_rebuild(md, false));
+      if (fused) md->hctrl.ptr->steps_done += 1;   // no kick kernel counts the step the rebuild completes
       ATX_PASS(md_reset_ctrl_after_rebuild(md));
       ATX_PASS(md_compute(md, false));
-      k_md_kick<<<gb, 256, 0, st>>>(nat, md->dt, md->v.ptr, md->f.ptr, md->minv.ptr, md->sums.ptr,
-                                    md->kin_partials.ptr, md->ctrl.ptr);
-      ATX_LAUNCHED();
+      if (!fused) {
+        k_md_kick<<<gb, 256, 0, st>>>(nat, md->dt, md->v.ptr, md->f.ptr, md->minv.ptr, md->sums.ptr,
+                                      md->kin_partials.ptr, md->ctrl.ptr, 1);
+        ATX_LAUNCHED();
+      }
       done_total += 1;
       remaining -= 1;
     }
+  }
+  if (fused) {
+    // whole-step velocities and the energy sums of the last force evaluation
+    k_md_kick<<<gb, 256, 0, st>>>(nat, md->dt, md->v.ptr, md->f.ptr, md->minv.ptr, md->sums.ptr,
+                                  md->kin_partials.ptr, md->ctrl.ptr, 0);
+    ATX_LAUNCHED();
   }
   ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(MdCtrl), cudaMemcpyDeviceToHost, st));
   ATX_CUDA(cudaEventRecord(md->ev1, st));

@@ -368,6 +368,15 @@ int atx_measure_copy_bandwidth(atx_ctx *ctx, double *gbs);
  * copies from/to such buffers run at full PCIe speed and need no staging */
 int atx_host_alloc_pinned(size_t bytes, void **ptr);
 int atx_host_free_pinned(void *ptr);
+/* Page-lock an array the HOST owns (cudaHostRegister): the reference's hosts keep their positions
+ * in their own storage -- particles_t%r_non_cyc (src/python/f90/python_particles.f90:120-135),
+ * LAMMPS' atom->x aliased by lammps_particles.f90:176-200, the numpy array behind ase.Atoms -- and
+ * hand the same buffer to every call; registered once, atx_particles_set_positions DMAs straight out
+ * of it with no staging copy.  Returns an error (and leaves the array usable as ordinary pageable
+ * memory) when the range cannot be locked; a range that is already page-locked is not an error
+ * (*already = 1, do not unregister it).  `already` may be NULL. */
+int atx_host_register(void *ptr, size_t bytes, int *already);
+int atx_host_unregister(void *ptr);
 
 /* ---- host-side init helpers ------------------------------------------------ */
 /* The reference computes these on the host in Fortran; a Fortran host keeps doing so and passes

@@ -44,3 +44,51 @@ def test_stresses_are_voigt_wpot_per_at():
     st = calc.get_stress(a)
     assert s.shape == (len(a), 6)
     assert np.abs(s.sum(axis=0) - st * a.get_volume()).max() < 1e-9 * max(1.0, np.abs(st * a.get_volume()).max())
+
+
+def test_positions_buffer_is_used_in_place():
+    """two calls with the same positions buffer make that buffer r_non_cyc itself (page-locked where it
+    lies, no mirror copy); results equal those of a calculator that copies; switching to another array
+    falls back to the mirror; an array that is already page-locked is accepted and left locked"""
+    from atomistica_b200 import _lib as L
+    a = S.diamond('Si', 5.432, (3, 3, 3))
+    a.rattle(0.05, seed=3)
+    calc = ab.Tersoff(verlet_shell=0.4)
+    ref = ab.Tersoff(alias_positions=False)
+    rng = np.random.RandomState(1)
+    for k in range(5):
+        a.positions += rng.normal(scale=0.01, size=a.positions.shape)      # in place: same buffer
+        f = calc.get_forces(a)
+        e = calc.get_potential_energy(a)
+        b = a.copy()
+        assert np.abs(f - ref.get_forces(b)).max() < 1e-10
+        assert abs(e - ref.get_potential_energy(b)) < 1e-10 * abs(e)
+        assert ref.particles._alias is None
+    assert calc.particles._alias is a.positions and calc.particles._alias_registered
+    assert calc.particles.coordinates is a.positions
+    # another array: back to the mirror, and this one is adopted after it was seen twice
+    a.positions = a.positions + 0.01
+    f = calc.get_forces(a)
+    assert calc.particles._alias is None
+    assert np.abs(f - ref.get_forces(a.copy())).max() < 1e-10
+    calc.get_forces(a)
+    assert calc.particles._alias is a.positions
+    # a non-contiguous view is never adopted
+    big = np.zeros((len(a), 4))
+    big[:, :3] = a.positions
+    a.positions = big[:, :3]
+    for k in range(3):
+        f = calc.get_forces(a)
+    assert calc.particles._alias is None
+    assert np.abs(f - ref.get_forces(a.copy())).max() < 1e-10
+    # memory that is page-locked already
+    pinned = L.PinnedArray((len(a), 3))
+    pinned.array[...] = big[:, :3]
+    a.positions = pinned.array
+    for k in range(3):
+        a.positions += 0.001
+        f = calc.get_forces(a)
+    assert calc.particles._alias is pinned.array and not calc.particles._alias_registered
+    assert np.abs(f - ref.get_forces(a.copy())).max() < 1e-10
+    del calc                                    # unregisters nothing it did not register
+    pinned.array[...] = 0.0

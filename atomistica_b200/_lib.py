@@ -44,6 +44,10 @@ class AtxJuslinParams(C.Structure):
         [('alpha', C.c_double * 27), ('omega', C.c_double * 27), ('m', C.c_int * 27)]
 
 
+class AtxJuslinScreening(C.Structure):
+    _fields_ = [(k, C.c_double * 9) for k in ('or1', 'or2', 'bor1', 'bor2', 'Cmin', 'Cmax')]
+
+
 class AtxPairParams(C.Structure):
     _fields_ = [('kind', C.c_int), ('p', C.c_double * 8), ('shift', C.c_int)]
 
@@ -77,7 +81,7 @@ SYMBOLS = [
     'atx_neighbors_bond_angles',
     'atx_eam_create', 'atx_eam_create_funcfl', 'atx_eam_destroy', 'atx_eam_bind_to', 'atx_eam_energy_and_forces',
     'atx_eam_set_store_outputs', 'atx_bop_set_store_outputs', 'atx_rebo2_set_store_outputs',
-    'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_create_juslin', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
+    'atx_bop_create', 'atx_bop_create_screened', 'atx_bop_create_juslin', 'atx_bop_create_juslin_screened', 'atx_bop_destroy', 'atx_bop_bind_to', 'atx_bop_energy_and_forces',
     'atx_pair_create', 'atx_pair_destroy', 'atx_pair_bind_to', 'atx_pair_energy_and_forces',
     'atx_pair_set_store_outputs',
     'atx_rebo2_create', 'atx_rebo2_create_screened', 'atx_rebo2_destroy', 'atx_rebo2_bind_to', 'atx_rebo2_energy_and_forces',

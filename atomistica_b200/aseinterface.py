@@ -232,6 +232,7 @@ TersoffScr = _calculator(native.TersoffScr)
 KumagaiScr = _calculator(native.KumagaiScr)
 BrennerScr = _calculator(native.BrennerScr)
 Juslin = _calculator(native.Juslin)
+JuslinScr = _calculator(native.JuslinScr)
 LJCut = _calculator(native.LJCut)
 Harmonic = _calculator(native.Harmonic)
 DoubleHarmonic = _calculator(native.DoubleHarmonic)

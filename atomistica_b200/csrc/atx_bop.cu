@@ -47,11 +47,12 @@ struct ExpCut {
 
 // Screened variants (SCREENING defined): cutoffs and Baskes screening bounds per pair,
 // default_bind_to_func.f90:44-104
-struct BopScrDev {
-  ExpCut cin[6], cout[6], cbo[6];
-  double cut_in_l[6], cut_in_h[6], cut_in_h2[6], cut_out_l[6], cut_out_h[6], cut_bo_h[6], max_cut_sq[6];
-  double Cmin[6], Cmax[6], dC[6], C_dr_cut[6];
+struct BopScrDev {   // 9 = nel**2 pairs of JuslinScr (6 for the symmetric pair index of the others)
+  ExpCut cin[9], cout[9], cbo[9];
+  double cut_in_l[9], cut_in_h[9], cut_in_h2[9], cut_out_l[9], cut_out_h[9], cut_bo_h[9], max_cut_sq[9];
+  double Cmin[9], Cmax[9], dC[9], C_dr_cut[9];
   double screening_threshold, dot_threshold;
+  int trig;   // JuslinScr: trigonometric switching functions (juslin_func.f90:27-122) instead of exp_cutoff_t
 };
 
 // per-atom tables of the screened kernels, bond-major / entry-major: element (b, s) at b*nat + s
@@ -79,7 +80,7 @@ struct atx_bop {
   long long sized_build = -1;
   // screened variants
   bool screened = false;
-  atx_bop_screening scr_par{};
+  atx_juslin_screening scr_par{};   // 9 entries per row; the symmetric classes use the first 6
   DevBuf<BopScrDev> scr_dev;
   DevBuf<double> scr_d;   // backing store of the BopScrTab double fields
   DevBuf<int> scr_i;      // backing store of the BopScrTab int fields
@@ -605,6 +606,23 @@ __device__ __forceinline__ void bop_expcut(const ExpCut &t, double r, double &va
   }
 }
 
+// the three cutoffs of the screened kernels: exp_cutoff_t, or the cosine switch of JuslinScr
+// (fCin / fCar / fCbo, juslin_func.f90:27-122: 0.5 (1 + cos(pi (r - r1) / (r2 - r1))))
+__device__ __forceinline__ void bop_scrcut(int trig, const ExpCut &t, double r, double &val, double &dval) {
+  if (!trig) {
+    bop_expcut(t, r, val, dval);
+  } else if (r > t.r2) {
+    val = 0.0; dval = 0.0;
+  } else if (r < t.r1) {
+    val = 1.0; dval = 0.0;
+  } else {
+    const double fca = BOP_PI / (t.r2 - t.r1), fc = -0.5 * fca;
+    const double arg = fca * (r - t.r1);
+    val = 0.5 * (1.0 + cos(arg));
+    dval = fc * sin(arg);
+  }
+}
+
 __device__ __forceinline__ void bop_list_vec(const Mat3 &A, const double4 &pi, const double4 &pj, int packed,
                                              double &dx, double &dy, double &dz) {
   // r_j - r_i - Abox.dc
@@ -699,14 +717,14 @@ k_bopscr_bonds(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, BopS
             rlij = sqrt(rlij);
             double fcin, dfcin, fa, dfa, fb, dfb;
             if (screened) {
-              bop_expcut(S.cin[ij], rlij, fcin, dfcin);
+              bop_scrcut(S.trig, S.cin[ij], rlij, fcin, dfcin);
               fcar = fcin; dfcar = dfcin; fcbo = fcin; dfcbo = dfcin;
               ns = ineb;
             } else if (need_derivative) {
               sij = exp(sij);
-              bop_expcut(S.cin[ij], rlij, fcin, dfcin);
-              bop_expcut(S.cout[ij], rlij, fa, dfa);
-              bop_expcut(S.cbo[ij], rlij, fb, dfb);
+              bop_scrcut(S.trig, S.cin[ij], rlij, fcin, dfcin);
+              bop_scrcut(S.trig, S.cout[ij], rlij, fa, dfa);
+              bop_scrcut(S.trig, S.cbo[ij], rlij, fb, dfb);
               fcar = (1.0 - fcin) * sij * fa + fcin;
               dfcar = (1.0 - fcin) * sij * (dfa + fa * dsijdrij / rlij) - dfcin * sij * fa + dfcin;
               fcbo = (1.0 - fcin) * sij * fb + fcin;
@@ -723,10 +741,10 @@ k_bopscr_bonds(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, BopS
                 }
               }
             } else {
-              bop_expcut(S.cout[ij], rlij, fa, dfa);
-              bop_expcut(S.cbo[ij], rlij, fb, dfb);
+              bop_scrcut(S.trig, S.cout[ij], rlij, fa, dfa);
+              bop_scrcut(S.trig, S.cbo[ij], rlij, fb, dfb);
               if (rlij < S.cut_in_h[ij]) {
-                bop_expcut(S.cin[ij], rlij, fcin, dfcin);
+                bop_scrcut(S.trig, S.cin[ij], rlij, fcin, dfcin);
                 fcar = (1.0 - fcin) * fa + fcin;
                 dfcar = (1.0 - fcin) * dfa - dfcin * fa + dfcin;
                 fcbo = (1.0 - fcin) * fb + fcin;
@@ -741,7 +759,7 @@ k_bopscr_bonds(int nat, Mat3 A, BopDev P, const BopScrDev *__restrict__ Sp, BopS
           // pair without an outer cutoff: plain inner cutoff
           bond = true;
           rlij = sqrt(rlij);
-          bop_expcut(S.cin[ij], rlij, fcar, dfcar);
+          bop_scrcut(S.trig, S.cin[ij], rlij, fcar, dfcar);
           fcbo = fcar; dfcbo = dfcar;
         }
 
@@ -1183,7 +1201,12 @@ extern "C" int atx_bop_create_screened(atx_ctx *ctx, const atx_bop_params *par,
   ATX_PASS(atx_bop_create(ctx, par, out));
   atx_bop *pot = *out;
   pot->screened = true;
-  pot->scr_par = *scr;
+  pot->scr_par = atx_juslin_screening{};
+  for (int i = 0; i < ATX_BOP_MAX_PAIRS; i++) {
+    pot->scr_par.or1[i] = scr->or1[i]; pot->scr_par.or2[i] = scr->or2[i];
+    pot->scr_par.bor1[i] = scr->bor1[i]; pot->scr_par.bor2[i] = scr->bor2[i];
+    pot->scr_par.Cmin[i] = scr->Cmin[i]; pot->scr_par.Cmax[i] = scr->Cmax[i];
+  }
   // default_bind_to_func.f90:44-104
   BopScrDev S{};
   const int npairs = par->nel * (par->nel + 1) / 2;
@@ -1207,6 +1230,45 @@ extern "C" int atx_bop_create_screened(atx_ctx *ctx, const atx_bop_params *par,
     S.max_cut_sq[i] = m * m;
   }
   S.screening_threshold = log(1e-6);   // tersoff_type.f90:86
+  S.dot_threshold = 1e-10;
+  ATX_PASS(pot->scr_dev.reserve(1));
+  ATX_CUDA(cudaMemcpy(pot->scr_dev.ptr, &S, sizeof(S), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// JuslinScr: juslin_module.f90 compiled with SCREENING (juslin_scr.f90): nel**2 pair rows, cosine
+// switches for all three cutoffs, C_dr_cut = Cmax**2 / (4 (Cmax - 1)) for every pair (:301-307)
+extern "C" int atx_bop_create_juslin_screened(atx_ctx *ctx, const atx_juslin_params *par,
+                                              const atx_juslin_screening *scr, atx_bop **out) {
+  if (ctx) cudaSetDevice(ctx->device);
+  if (!scr) return ATX_ERROR_UNSPECIFIED;
+  ATX_PASS(atx_bop_create_juslin(ctx, par, out));
+  atx_bop *pot = *out;
+  pot->screened = true;
+  pot->scr_par = *scr;
+  BopScrDev S{};
+  S.trig = 1;
+  const int npairs = par->nel * par->nel;
+  for (int i = 0; i < npairs; i++) {
+    S.Cmin[i] = scr->Cmin[i];
+    S.Cmax[i] = scr->Cmax[i];
+    S.dC[i] = S.Cmax[i] - S.Cmin[i];
+    S.C_dr_cut[i] = S.Cmax[i] * S.Cmax[i] / (4 * (S.Cmax[i] - 1));
+    S.cin[i].r1 = par->r1[i]; S.cin[i].r2 = par->r2[i];       // only r1 / r2 enter the cosine switch
+    S.cout[i].r1 = scr->or1[i]; S.cout[i].r2 = scr->or2[i];
+    S.cbo[i].r1 = scr->bor1[i]; S.cbo[i].r2 = scr->bor2[i];
+    S.cut_in_l[i] = par->r1[i];
+    S.cut_in_h[i] = par->r2[i];
+    S.cut_in_h2[i] = par->r2[i] * par->r2[i];
+    S.cut_out_l[i] = scr->or1[i];
+    S.cut_out_h[i] = scr->or2[i];
+    S.cut_bo_h[i] = scr->bor2[i];
+    double m = S.cut_in_h[i];
+    if (S.cut_out_h[i] > m) m = S.cut_out_h[i];
+    if (S.cut_bo_h[i] > m) m = S.cut_bo_h[i];
+    S.max_cut_sq[i] = m * m;
+  }
+  S.screening_threshold = log(1e-6);
   S.dot_threshold = 1e-10;
   ATX_PASS(pot->scr_dev.reserve(1));
   ATX_CUDA(cudaMemcpy(pot->scr_dev.ptr, &S, sizeof(S), cudaMemcpyHostToDevice));
@@ -1244,16 +1306,19 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
           double cutoff = D.r2[ij];
           if (pot->screened) {
             // default_bind_to_func.f90:106-130: sqrt(C_dr_cut(pair)) * the largest cutoff of ANY pair
-            const atx_bop_screening &sp = pot->scr_par;
-            const int npairs = D.nel * (D.nel + 1) / 2;
+            const atx_juslin_screening &sp = pot->scr_par;
+            const bool jus = D.kind == ATX_BOP_JUSLIN;
+            const int npairs = jus ? D.nel * D.nel : D.nel * (D.nel + 1) / 2;
             double mx = 0.0;
             for (int q = 0; q < npairs; q++) {
-              mx = std::max(mx, pot->par.r2[q]);
+              mx = std::max(mx, D.r2[q]);
               mx = std::max(mx, sp.or2[q]);
               mx = std::max(mx, sp.bor2[q]);
             }
             const double cm = sp.Cmax[ij];
-            cutoff = std::sqrt(cm > 2.0 ? cm * cm / (4 * (cm - 1)) : 1.0) * mx;
+            // juslin_module.f90:301-307, 379-395: the unconditional form
+            if (jus) cutoff = cm > 1.0 ? std::sqrt(cm * cm / (4 * (cm - 1))) * mx : 0.0;
+            else cutoff = std::sqrt(cm > 2.0 ? cm * cm / (4 * (cm - 1)) : 1.0) * mx;
           }
           ATX_PASS(atx_neighbors_request_interaction_range(nl, cutoff));
         }
@@ -1407,6 +1472,7 @@ static int bopscr_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, con
     switch (pot->dev.kind) {
       case ATX_BOP_TERSOFF: BOPSCR_CENTER(ATX_BOP_TERSOFF); break;
       case ATX_BOP_KUMAGAI: BOPSCR_CENTER(ATX_BOP_KUMAGAI); break;
+      case ATX_BOP_JUSLIN: BOPSCR_CENTER(ATX_BOP_JUSLIN); break;
       default: BOPSCR_CENTER(ATX_BOP_BRENNER);
     }
 #undef BOPSCR_CENTER

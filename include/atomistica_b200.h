@@ -213,6 +213,16 @@ typedef struct {
   int m[27];
 } atx_juslin_params;
 int atx_bop_create_juslin(atx_ctx *ctx, const atx_juslin_params *par, atx_bop **pot);
+/* JuslinScr (src/potentials/bop/juslin_scr/juslin_scr.f90 = juslin_module.f90 with SCREENING): r1/r2
+ * of atx_juslin_params are the inner cutoff; or1/or2, bor1/bor2, Cmin/Cmax as in atx_bop_screening but
+ * with the nel**2 non-symmetric pair index and AFTER the mirroring of BIND_TO_FUNC
+ * (juslin_module.f90:285-298).  All three switching functions are the cosine form
+ * (juslin_func.f90:27-122); C_dr_cut = Cmax**2/(4 (Cmax-1)) for every pair (:301-307). */
+typedef struct {
+  double or1[9], or2[9], bor1[9], bor2[9], Cmin[9], Cmax[9];
+} atx_juslin_screening;
+int atx_bop_create_juslin_screened(atx_ctx *ctx, const atx_juslin_params *par,
+                                   const atx_juslin_screening *scr, atx_bop **pot);
 int atx_bop_destroy(atx_bop *pot);
 /* BIND_TO_FUNC (default_bind_to_func.f90:25-146): el2Z[nel] are the atomic numbers of the
  * particle element ids; builds Z2db and requests r2 of every present pair */

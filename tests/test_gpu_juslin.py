@@ -82,3 +82,89 @@ def test_fe_c_h():
     a.rattle(0.1, seed=7)
     g, o = _both(P.Kuopanportti_CMS_111_525_FeCH, a)
     _check(g, o)
+
+
+# ---- JuslinScr (juslin_scr.f90: the same module compiled with SCREENING) -----------------------------
+
+def _wide_scr_db():
+    """default JuslinScr database with outer / bond-order cutoffs beyond the inner one, so that bonds
+    are really screened (the Fortran default has or = bor = r)"""
+    db = P.complete_juslin_scr(None)
+    for k in range(9):
+        if db['r2'][k] > 0:
+            db['or1'][k], db['or2'][k] = db['r2'][k] * 1.05, db['r2'][k] * 1.45
+            db['bor1'][k], db['bor2'][k] = db['r2'][k] * 1.0, db['r2'][k] * 1.35
+    return db
+
+
+def _both_scr(db, atoms, mask=None, per_bond=False):
+    db = P.complete_juslin_scr(db)
+    p = native.from_atoms(atoms)
+    nl = native.Neighbors(1000)
+    pot = native.JuslinScr(db)
+    pot.bind_to(p, nl)
+    g = pot.energy_and_forces(p, nl, mask=mask, epot_per_at=True, wpot_per_at=True, epot_per_bond=per_bond,
+                              f_per_bond=per_bond, wpot_per_bond=per_bond)
+    # the list cutoff the device asked for: the largest of the pairs present (juslin_module.f90:379-395)
+    nel = len(db['el'])
+    idx = [db['el'].index(s) for s in set(atoms.symbols) if s in db['el']]
+    m = max(max(db['r2'][k], db['or2'][k], db['bor2'][k]) for k in range(nel * nel))
+    cutoff = max((db['Cmax'][j + i * nel] ** 2 / (4 * (db['Cmax'][j + i * nel] - 1))) ** 0.5 * m
+                 for i in idx for j in idx)
+    onl = oracle.neighbor_list(atoms.positions, atoms.cell, atoms.pbc, cutoff, 1000)
+    el = np.array([db['el'].index(s) + 1 if s in db['el'] else -1 for s in atoms.symbols], dtype=np.int32)
+    o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.JUSLIN, db), atoms.positions, atoms.cell, onl, el,
+                                     scr=oracle.bop_scr_params(db), mask=mask, per_at=True, per_bond=per_bond)
+    return g, o
+
+
+def test_juslin_scr_default_database():
+    a = S.b1(['W', 'C'], 4.38, (3, 3, 3))
+    a.rattle(0.05, seed=2)
+    g, o = _both_scr(None, a)
+    _check(g, o)
+    b = S.bcc('W', 3.165, (4, 4, 4))
+    b.rattle(0.1, seed=1)
+    g, o = _both_scr(None, b)
+    _check(g, o)
+
+
+def test_juslin_scr_screened_bonds_wch():
+    db = _wide_scr_db()
+    a = S.b1(['W', 'C'], 4.38, (3, 3, 3))
+    rng = np.random.RandomState(5)
+    for i in rng.choice(len(a), 30, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.15, seed=9)
+    g, o = _both_scr(db, a, per_bond=True)
+    _check(g, o, per_bond=True)
+    g1, _ = _both_scr(None, a)
+    assert abs(g[0] - g1[0]) > 1e-6              # the wider cutoffs matter
+    b = S.bcc('W', 3.165, (3, 3, 3))
+    b.rattle(0.15, seed=2)
+    g, o = _both_scr(db, b)
+    _check(g, o)
+
+
+def test_juslin_scr_mask_and_hydrocarbon():
+    db = _wide_scr_db()
+    a = S.diamond('C', 3.7, (3, 3, 3))
+    rng = np.random.RandomState(6)
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=6)
+    g, o = _both_scr(db, a)
+    _check(g, o)
+    mask = (np.random.RandomState(4).rand(len(a)) > 0.5).astype(np.int32)
+    g, o = _both_scr(db, a, mask=mask)
+    _check(g, o)
+
+
+def test_juslin_scr_calculator_and_md():
+    import atomistica_b200 as ab
+    a = S.bcc('W', 3.165, (4, 4, 4))
+    a.rattle(0.05, seed=3)
+    calc = ab.JuslinScr(db=_wide_scr_db())
+    e = calc.get_potential_energy(a)
+    g, o = _both_scr(_wide_scr_db(), a)
+    assert abs(e - o['epot']) <= RTOL * abs(o['epot'])

@@ -1481,7 +1481,7 @@ static int bopscr_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, con
                                                     o.f, o.epa, o.role, o.stop);
     ATX_LAUNCHED();
   }
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
   return 0;
 }
 
@@ -1556,7 +1556,7 @@ static int bop_compute(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const 
                                                     o.f, o.epa, o.role, o.stop);
     ATX_LAUNCHED();
   }
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, ntot, o.sums, o.stop));
+  if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, ntot, o.sums, o.stop));
   return 0;
 }
 

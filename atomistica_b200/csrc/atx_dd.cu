@@ -723,6 +723,7 @@ static int dd_compute(atx_ddmd *md, bool guarded, int phase = 0) {
   o.sums = md->sums.ptr;
   o.stop = guarded ? &md->ctrl.ptr->stop : nullptr;
   o.want_virial = false;
+  o.want_sums = false;   // the kick kernel sums the per-atom energies of the owned atoms itself
   o.role = md->dd->nranks > 1 ? md->role.ptr : nullptr;
   switch (md->pot_kind) {
     case ATX_POT_EAM:

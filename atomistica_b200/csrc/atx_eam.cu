@@ -665,7 +665,7 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
     else EAM_FAST(8, 2);
 #undef EAM_FAST
 #undef EAM_FAST_M
-    ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nb, o.sums, o.stop));
+    if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nb, o.sums, o.stop));
     return 0;
   }
   if (o.role) {
@@ -700,7 +700,7 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
   else if (lanes == 8) EAM_LAUNCH(8);
   else EAM_LAUNCH(4);
 #undef EAM_LAUNCH
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
   return 0;
 }
 

@@ -237,12 +237,13 @@ __global__ void k_md_gather_state(int nat, const int *__restrict__ id,
   }
 }
 
-static int md_compute(atx_md *md, bool guarded) {
+static int md_compute(atx_md *md, bool guarded, bool want_sums = true) {
   PotOut o;
   o.f = md->f.ptr;
   o.sums = md->sums.ptr;
   o.stop = guarded ? &md->ctrl.ptr->stop : nullptr;
   o.want_virial = false;
+  o.want_sums = want_sums;
   switch (md->pot_kind) {
     case ATX_POT_EAM:
       return atx_eam_compute_device((atx_eam *)md->pot, &md->pint, md->nl, nullptr, o);
@@ -419,7 +420,9 @@ extern "C" int atx_md_run(atx_md *md, int nsteps, double *epot, double *ekin) {
                                            md->minv.ptr, md->ctrl.ptr);
         ATX_LAUNCHED();
         first = false;
-        ATX_PASS(md_compute(md, true));
+        // the potential energy is read once, by the kick that ends the run: only the evaluation that can
+        // be the last one reduces its partial sums (a rebuild re-evaluates with sums)
+        ATX_PASS(md_compute(md, true, b == batch - 1 && remaining == batch));
         continue;
       }
       k_md_drift<<<gb, 256, 0, st>>>(nat, md->dt, nl->pos4.ptr, md->v.ptr, md->f.ptr, md->minv.ptr,

@@ -218,7 +218,7 @@ int atx_pair_compute_device(atx_pair *pot, atx_particles *p, atx_neighbors *nl, 
                                                   nl->seed.ptr, nl->list.ptr, mask_sorted, o.f, o.epa, o.wpa,
                                                   pot->sc.partials.ptr, o.role, o.stop);
   ATX_LAUNCHED();
-  return atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop);
+  return o.want_sums ? atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop) : 0;
 }
 
 extern "C" int atx_pair_energy_and_forces(atx_pair *pot, atx_particles *p, atx_neighbors *nl,

@@ -13,6 +13,7 @@ struct PotOut {
   double *sums = nullptr;   // ATX_NSUM doubles: epot, wpot(3,3)
   const int *stop = nullptr;  // MD driver: kernels return immediately when *stop != 0
   bool want_virial = true;    // NVE stepping does not need wpot
+  bool want_sums = true;      // false: the per-block partial sums are not reduced (MD steps whose energy nobody reads)
   // domain decomposition: per sorted atom 2 = owned (everything), 1 = inner ghost (densities /
   // bond-order terms only, no forces), 0 = outer ghost (position only).  nullptr: all owned.
   const unsigned char *role = nullptr;

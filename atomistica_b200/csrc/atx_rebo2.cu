@@ -395,7 +395,7 @@ static int rebo2_scr_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl
                                             nblocks, o.stop);
     ATX_LAUNCHED();
   }
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbtot, o.sums, o.stop));
+  if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbtot, o.sums, o.stop));
   return 0;
 }
 
@@ -471,7 +471,7 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
     else RB_FORCE_BOND(4);
 #undef RB_FORCE_BOND
     ATX_LAUNCHED();
-    ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbb, o.sums, o.stop));
+    if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nbb, o.sums, o.stop));
     return 0;
   } else {
     ProfScope ps_(ctx, "rebo2_force");
@@ -481,7 +481,7 @@ static int rebo2_compute(atx_rebo2 *pot, atx_particles *p, atx_neighbors *nl, co
                                                 wpb, pot->sc.partials.ptr, o.stop);
     ATX_LAUNCHED();
   }
-  ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
+  if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nblocks, o.sums, o.stop));
   return 0;
 }
 

@@ -537,6 +537,19 @@ struct S2Bop {
   section_t *members = nullptr;
 };
 
+// Juslin / JuslinScr instance (classes further down)
+struct S2Juslin {
+  bool screened = false;
+  char el[3][2];
+  int nel = 0;
+  char ref[128];
+  atx_juslin_params par;
+  atx_juslin_screening scr;
+  int len[24];
+  atx_bop *h = nullptr;
+  section_t *members = nullptr;
+};
+
 #include "seam2_defaults.inc"   // static void s2_bop_defaults(S2Bop *b): generated from parameters.py
 
 static void reg_list(section_t *m, S2Bop *b, int &k, double *ptr, int maxlen, int n, const char *name) {
@@ -816,6 +829,204 @@ static void eam_energy_and_forces(void *self, void *pp, void *nn, double *, doub
 }
 static void eam_register_data(void *, void *, int *ierror) { if (ierror) *ierror = ERROR_NONE; }
 
+
+// ---- Juslin / JuslinScr (juslin_registry.f90:22-125, juslin_module.f90:209-420) -----------------------
+// nel**2 pair rows (PAIR_INDEX_NS) and nel**3 triplet rows; the defaults are the W-C-H set of
+// juslin_params.f90 (generated from parameters.py); INIT mirrors the rows with r0 < 0 from the transposed
+// pair (BIND_TO_FUNC :283-312) before the device object is created.  `ref` is registered like the
+// reference does; the database it would select from has a single entry per class here.
+
+
+template <bool SCR>
+static void juslin_new(void **self, section_t *cfg, section_t **members) {
+  S2Juslin *b = new S2Juslin();
+  memset(&b->par, 0, sizeof b->par);
+  memset(&b->scr, 0, sizeof b->scr);
+  b->screened = SCR;
+  s2_juslin_defaults(b);
+  section_t *m = ptrdict_register_section(cfg, (char *)(SCR ? "JuslinScr" : "Juslin"),
+                                          (char *)(SCR ? "Juslin-Type bond-order potential (screened)."
+                                                       : "Juslin-Type bond-order potential."));
+  ptrdict_register_string_list_property(m, &b->el[0][0], 2, 3, &b->nel, (char *)"el", (char *)"List of element symbols.");
+  memset(b->ref, ' ', sizeof b->ref);
+  ptrdict_register_string_property(m, b->ref, (int)sizeof b->ref, (char *)"ref",
+                                   (char *)"Reference string to choose a parameters set from the database.");
+  const int np = b->nel * b->nel, nt = np * b->nel;
+  int k = 0;
+  auto reg = [&](double *ptr, int maxlen, int n, const char *name) {
+    b->len[k] = n;
+    ptrdict_register_list_property(m, ptr, maxlen, &b->len[k], (char *)name, (char *)"See functional form.");
+    k++;
+  };
+  atx_juslin_params &q = b->par;
+  reg(q.D0, 9, np, "D0"); reg(q.r0, 9, np, "r0"); reg(q.S, 9, np, "S"); reg(q.beta, 9, np, "beta");
+  reg(q.gamma, 9, np, "gamma"); reg(q.c, 9, np, "c"); reg(q.d, 9, np, "d"); reg(q.h, 9, np, "h");
+  reg(q.n, 9, np, "n"); reg(q.alpha, 27, nt, "alpha"); reg(q.omega, 27, nt, "omega");
+  b->len[k] = nt;
+  ptrdict_register_integer_list_property(m, (double *)q.m, 27, &b->len[k], (char *)"m", (char *)"See functional form.");
+  k++;
+  reg(q.r1, 9, np, "r1"); reg(q.r2, 9, np, "r2");
+  if (SCR) {
+    reg(b->scr.or1, 9, np, "or1"); reg(b->scr.or2, 9, np, "or2"); reg(b->scr.bor1, 9, np, "bor1");
+    reg(b->scr.bor2, 9, np, "bor2"); reg(b->scr.Cmin, 9, np, "Cmin"); reg(b->scr.Cmax, 9, np, "Cmax");
+  }
+  b->members = m;
+  *members = m;
+  *self = b;
+}
+static void juslin_free(void *self) {
+  S2Juslin *b = (S2Juslin *)self;
+  if (b->h) atx_bop_destroy(b->h);
+  if (b->members) ptrdict_cleanup(b->members);
+  delete b;
+}
+static void juslin_init(void *self, int *ierror) {
+  S2Juslin *b = (S2Juslin *)self;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!ctx()) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  if (b->nel < 1 || b->nel > 3) RAISE(ierror, "Number of elements out of range.");
+  atx_juslin_params q = b->par;          // the registered database stays as the host wrote it
+  atx_juslin_screening sc = b->scr;
+  q.nel = b->nel;
+  for (int i = 0; i < b->nel; i++) {
+    q.Z[i] = symbol_to_Z(b->el[i]);
+    if (q.Z[i] <= 0) RAISE(ierror, "Unknown element symbol in 'el'.");
+  }
+  const int ne = b->nel;
+  for (int i = 0; i < ne; i++)
+    for (int j = 0; j < ne; j++) {
+      const int a = j + i * ne, t = i + j * ne;   // PAIR_INDEX_NS(i,j), PAIR_INDEX_NS(j,i), 0-based
+      if (q.r0[a] < 0.0) {
+        double *rows[] = {q.D0, q.r0, q.S, q.beta, q.gamma, q.c, q.d, q.h, q.n, q.r1, q.r2,
+                          sc.or1, sc.or2, sc.bor1, sc.bor2, sc.Cmin, sc.Cmax};
+        for (double *row : rows) row[a] = row[t];
+      }
+    }
+  if (b->h) { atx_bop_destroy(b->h); b->h = nullptr; }
+  if (b->screened) CHK(atx_bop_create_juslin_screened(ctx(), &q, &sc, &b->h), ierror);
+  else CHK(atx_bop_create_juslin(ctx(), &q, &b->h), ierror);
+}
+static void juslin_bind_to(void *self, void *pp, void *nn, int *ierror) {
+  S2Juslin *b = (S2Juslin *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!b->h) RAISE(ierror, "The potential has not been initialised.");
+  neighbors_ensure(n);
+  if (!n->h || !p->h) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  n->p = p;
+  CHK(atx_bop_bind_to(b->h, p->h, n->h, (int)p->el2Z.size(), p->el2Z.data()), ierror);
+}
+static void juslin_energy_and_forces(void *self, void *pp, void *nn, double *, double *epot, double *f, int *wpot_,
+                                     double *mask_, double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                     double *wpot_per_at, double *wpot_per_bond, int *ierror) {
+  S2Juslin *b = (S2Juslin *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!b->h || !n->h) RAISE(ierror, "bind_to has not been called on this potential.");
+  n->p = p;
+  CHK(particles_sync(p), ierror);
+  CHK(atx_bop_energy_and_forces(b->h, p->h, n->h, (int *)mask_, epot, f, (double *)wpot_, epot_per_at, epot_per_bond,
+                                f_per_bond, wpot_per_at, wpot_per_bond), ierror);
+}
+
+// ---- TabulatedEAM (tabulated_eam.f90:141-214 init with the funcfl reader, :238-261 bind_to, :277-330) --
+struct S2Funcfl {
+  char elements[1024];
+  char fn[100];
+  std::vector<S2Spline *> keep;
+  double cutoff = 0.0;
+  atx_eam *h = nullptr;
+  section_t *members = nullptr;
+};
+static void funcfl_new(void **self, section_t *cfg, section_t **members) {
+  S2Funcfl *e = new S2Funcfl();
+  memset(e->elements, ' ', sizeof e->elements);
+  e->elements[0] = '*';
+  memset(e->fn, ' ', sizeof e->fn);
+  memcpy(e->fn, "default.in", 10);
+  section_t *m = ptrdict_register_section(
+      cfg, (char *)"TabulatedEAM",
+      (char *)"General tabulated EAM potential, see S.M. Foiles, M.I. Baskes, M.S. Daw, Phys. Rev. B 33, 7983 (1986).");
+  ptrdict_register_string_property(m, e->elements, (int)sizeof e->elements, (char *)"elements",
+                                   (char *)"Element for which to use this potential.");
+  ptrdict_register_string_property(m, e->fn, (int)sizeof e->fn, (char *)"fn", (char *)"Configuration file.");
+  e->members = m;
+  *members = m;
+  *self = e;
+}
+static void funcfl_free(void *self) {
+  S2Funcfl *e = (S2Funcfl *)self;
+  if (e->h) atx_eam_destroy(e->h);
+  for (auto *s : e->keep) delete s;
+  if (e->members) ptrdict_cleanup(e->members);
+  delete e;
+}
+// funcfl reader (:172-197): comment; Z mass a0 lattice; nF dF nr dr cutoff; nF F values, nr Z values,
+// nr rho values.  Z is scaled by sqrt(0.5 Hartree Bohr) (:199; Units.f90:74-76).
+static void funcfl_init(void *self, int *ierror) {
+  S2Funcfl *e = (S2Funcfl *)self;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!ctx()) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  const std::string fn = fstr(e->fn, sizeof e->fn);
+  std::ifstream in(fn);
+  if (!in) RAISE(ierror, ("Error opening file '" + fn + "'.").c_str());
+  std::string line;
+  std::getline(in, line);
+  std::getline(in, line);   // Z mass a0 lattice: not used by the kernel
+  std::string rest((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  for (char &c : rest)
+    if (c == 'D' || c == 'd') c = 'E';
+  std::istringstream ts(rest);
+  int nF = 0, nr = 0;
+  double dF = 0, dr = 0;
+  ts >> nF >> dF >> nr >> dr >> e->cutoff;
+  if (!ts || nF < 2 || nr < 2) RAISE(ierror, "Malformed funcfl header.");
+  std::vector<double> F(nF), Z(nr), rho(nr);
+  for (double &x : F) ts >> x;
+  for (double &x : Z) ts >> x;
+  for (double &x : rho) ts >> x;
+  if (!ts) RAISE(ierror, ("Unexpected end of file in '" + fn + "'.").c_str());
+  const double HARTREE = 27.2113961, BOHR = 0.529177249;
+  S2Spline *sF = make_spline(nF, dF, F, 1.0), *sZ = make_spline(nr, dr, Z, std::sqrt(0.5 * HARTREE * BOHR)),
+           *sr = make_spline(nr, dr, rho, 1.0);
+  e->keep.push_back(sF); e->keep.push_back(sZ); e->keep.push_back(sr);
+  if (e->h) { atx_eam_destroy(e->h); e->h = nullptr; }
+  CHK(atx_eam_create_funcfl(ctx(), &sF->s, &sr->s, &sZ->s, e->cutoff, &e->h), ierror);
+}
+static int element_filter(const std::string &spec, const S2Particles *p, bool *ok);
+static void funcfl_bind_to(void *self, void *pp, void *nn, int *ierror) {
+  S2Funcfl *e = (S2Funcfl *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (!e->h) RAISE(ierror, "The potential has not been initialised.");
+  neighbors_ensure(n);
+  if (!n->h || !p->h) RAISE(ierror, "No CUDA device available (no CPU fallback).");
+  n->p = p;
+  bool ok = true;
+  const int filt = element_filter(fstr(e->elements, sizeof e->elements), p, &ok);   // filter_from_string
+  if (!ok) RAISE(ierror, "Unknown element in 'elements'.");
+  std::vector<int> el2db;
+  for (size_t k = 0; k < p->el2Z.size(); k++) el2db.push_back((filt >> (k + 1)) & 1 ? 1 : -1);
+  CHK(atx_eam_bind_to(e->h, p->h, n->h, (int)el2db.size(), el2db.data()), ierror);
+}
+static void funcfl_energy_and_forces(void *self, void *pp, void *nn, double *, double *epot, double *f, int *wpot_,
+                                     double *mask_, double *epot_per_at, double *epot_per_bond, double *f_per_bond,
+                                     double *wpot_per_at, double *wpot_per_bond, int *ierror) {
+  S2Funcfl *e = (S2Funcfl *)self;
+  S2Particles *p = (S2Particles *)pp;
+  S2Neighbors *n = (S2Neighbors *)nn;
+  if (ierror) *ierror = ERROR_NONE;
+  if (epot_per_bond || f_per_bond || wpot_per_bond || mask_ || wpot_per_at)
+    RAISE(ierror, "TabulatedEAM supports per-atom energies only (no masks, per-bond or per-atom virial outputs).");
+  if (!e->h || !n->h) RAISE(ierror, "bind_to has not been called on this potential.");
+  n->p = p;
+  CHK(particles_sync(p), ierror);
+  CHK(atx_eam_energy_and_forces(e->h, p->h, n->h, nullptr, epot, f, (double *)wpot_, epot_per_at, nullptr), ierror);
+}
+
 // ---- Rebo2 / Rebo2Scr (rebo2_registry.f90:22-168, rebo2_module.f90:70-223) -------------------------------
 // The finished default parameter block (constants, g-splines, table coefficients) is generated at build
 // time; this shim exposes `elements` and `dihedral`.  Other parameter overrides of the reference's registry
@@ -1016,6 +1227,12 @@ potential_class_t potential_classes[N_POTENTIAL_CLASSES] = {
      rebo2_energy_and_forces},
     {"Rebo2Scr", rebo2_new<true>, rebo2_free, eam_register_data, rebo2_init, rebo2_bind_to, nullptr, nullptr, nullptr,
      rebo2_energy_and_forces},
+    {"Juslin", juslin_new<false>, juslin_free, eam_register_data, juslin_init, juslin_bind_to, nullptr, nullptr, nullptr,
+     juslin_energy_and_forces},
+    {"JuslinScr", juslin_new<true>, juslin_free, eam_register_data, juslin_init, juslin_bind_to, nullptr, nullptr,
+     nullptr, juslin_energy_and_forces},
+    {"TabulatedEAM", funcfl_new, funcfl_free, eam_register_data, funcfl_init, funcfl_bind_to, nullptr, nullptr, nullptr,
+     funcfl_energy_and_forces},
 #define PAIR_CLASS(W) \
   {"", pair_new<W>, pair_free, eam_register_data, pair_init, pair_bind_to, nullptr, nullptr, nullptr, pair_energy_and_forces}
     PAIR_CLASS(0), PAIR_CLASS(1), PAIR_CLASS(2), PAIR_CLASS(3), PAIR_CLASS(4),
@@ -1023,7 +1240,7 @@ potential_class_t potential_classes[N_POTENTIAL_CLASSES] = {
 // the pair classes take their names from PAIR_SPECS
 static struct PairNames {
   PairNames() {
-    for (int w = 0; w < 5; w++) strncpy(potential_classes[9 + w].name, PAIR_SPECS[w].name, MAX_NAME);
+    for (int w = 0; w < 5; w++) strncpy(potential_classes[12 + w].name, PAIR_SPECS[w].name, MAX_NAME);
   }
 } g_pair_names;
 #include "coulomb_factory_c.h"

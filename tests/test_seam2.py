@@ -29,7 +29,7 @@ def mod():
 def test_module_exports(mod):
     """the reference's extension types, created by its own atomisticamodule.c from potential_classes[]"""
     for name in ('Particles', 'Neighbors', 'Tersoff', 'TersoffScr', 'Kumagai', 'KumagaiScr', 'Brenner', 'BrennerScr',
-                 'TabulatedAlloyEAM', 'Rebo2', 'Rebo2Scr', 'LJCut', 'Harmonic', 'DoubleHarmonic', 'BornMayer', 'r6',
+                 'TabulatedAlloyEAM', 'TabulatedEAM', 'Juslin', 'JuslinScr', 'Rebo2', 'Rebo2Scr', 'LJCut', 'Harmonic', 'DoubleHarmonic', 'BornMayer', 'r6',
                  'startup', 'shutdown', 'set_logfile', 'pair_distribution'):
         assert hasattr(mod, name), name
     assert mod.Tersoff.__name__ == 'Tersoff'
@@ -233,3 +233,64 @@ def test_rebo2_and_pair_classes(mod):
     lj.bind_to(pn, nn)
     e2, f2 = lj.energy_and_forces(pn, nn)[:2]
     assert abs(e - e2) <= 1e-12 * abs(e2) and np.abs(f - f2).max() <= 1e-12 * max(1.0, np.abs(f2).max())
+
+
+@pytest.mark.gpu
+def test_juslin_classes_and_funcfl(mod, tmp_path):
+    """Juslin, JuslinScr (database through the ptrdict registry, mirrored by init like BIND_TO_FUNC) and
+    TabulatedEAM (funcfl file read by the shim) through the reference's module == the Python mirror on
+    the same device kernels == the oracle (tests/test_gpu_juslin.py, tests/test_gpu_eam.py)"""
+    from atomistica_b200 import native, parameters as P
+    a = S.b1(['W', 'C'], 4.38, (3, 3, 3))
+    rng = np.random.RandomState(5)
+    for i in rng.choice(len(a), 20, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=9)
+
+    def mirror(pot, avgn):
+        pn = native.from_atoms(a)
+        nn = native.Neighbors(avgn)
+        pot.bind_to(pn, nn)
+        return pot.energy_and_forces(pn, nn)[:3]
+
+    p, nl, e, f, w = _calc(mod, mod.Juslin(), a, avgn=200)
+    e0, f0, w0 = mirror(native.Juslin(), 200)
+    assert abs(e - e0) <= 1e-12 * abs(e0) and np.abs(f - f0).max() <= 1e-12 * max(1.0, np.abs(f0).max())
+    assert np.abs(np.asarray(w).reshape(3, 3) - w0).max() <= 1e-10 * max(1.0, np.abs(w0).max())
+    # screened class: default database, then wider outer / bond-order cutoffs by keyword
+    p, nl, e, f, w = _calc(mod, mod.JuslinScr(), a, avgn=1000)
+    e0, f0, w0 = mirror(native.JuslinScr(), 1000)
+    assert abs(e - e0) <= 1e-12 * abs(e0) and np.abs(f - f0).max() <= 1e-12 * max(1.0, np.abs(f0).max())
+    raw = {k: list(v) for k, v in P.Juslin_WCH__Scr_fortran_default.items() if not k.startswith('__')}
+    for k in range(9):
+        if raw['r2'][k] > 0:
+            raw['or1'][k], raw['or2'][k] = raw['r2'][k] * 1.05, raw['r2'][k] * 1.45
+            raw['bor1'][k], raw['bor2'][k] = raw['r2'][k] * 1.0, raw['r2'][k] * 1.35
+    kw = {k: raw[k] for k in ('or1', 'or2', 'bor1', 'bor2')}
+    p, nl, e1, f1, w1 = _calc(mod, mod.JuslinScr(**kw), a, avgn=1000)
+    e2, f2, w2 = mirror(native.JuslinScr(P.complete_juslin_scr(raw)), 1000)
+    assert abs(e1 - e) > 1e-6
+    assert abs(e1 - e2) <= 1e-12 * abs(e2) and np.abs(f1 - f2).max() <= 1e-12 * max(1.0, np.abs(f2).max())
+
+    # funcfl
+    tab = load_npz('au_u3_funcfl.npz')
+    fn = str(tmp_path / 'Au_u3.eam')
+    with open(fn, 'w') as fh:
+        fh.write('Au funcfl\n%d %.6f %.6f fcc\n' % (79, 196.97, 4.08))
+        fh.write('%d %.17g %d %.17g %.17g\n' % (int(tab['nF']), float(tab['dF']), int(tab['nr']), float(tab['dr']),
+                                                 float(tab['cutoff'])))
+        for key in ('F', 'Z', 'rho'):
+            v = np.asarray(tab[key], dtype=float)
+            for k in range(0, len(v), 5):
+                fh.write(' '.join('%.17g' % x for x in v[k:k + 5]) + '\n')
+    au = S.fcc('Au', 4.08, (3, 3, 3))
+    au.rattle(0.1, seed=41)
+    p, nl, e, f, w = _calc(mod, mod.TabulatedEAM(fn=fn), au, avgn=200)
+    pn = native.from_atoms(au)
+    nn = native.Neighbors(200)
+    pot = native.TabulatedEAM(funcfl=tab)
+    pot.bind_to(pn, nn)
+    e0, f0 = pot.energy_and_forces(pn, nn)[:2]
+    assert abs(e - e0) <= 1e-12 * abs(e0) and np.abs(f - f0).max() <= 1e-12 * max(1.0, np.abs(f0).max())
+    with pytest.raises(RuntimeError):
+        mod.TabulatedEAM(fn=str(tmp_path / 'missing.eam'))

@@ -170,3 +170,23 @@ def test_two_types_eam_and_rebo2(libs, tmp_path):
     assert abs(r['rcghost'] - 10.0) < 1e-12
     assert abs(r['eng'] - o['epot']) <= 1e-10 * abs(o['epot'])
     assert np.abs(r['f'][:r['nlocal']] - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
+
+
+@pytest.mark.gpu
+def test_juslin_through_the_pair_style_sequence(libs):
+    """Juslin W-C (non-symmetric pair index, rows mirrored by init) on an unfolded B1 crystal"""
+    import oracle
+    from atomistica_b200 import parameters as P
+    a = S.b1(['W', 'C'], 4.38, (3, 3, 3))
+    a.rattle(0.08, seed=6)
+    db = P.complete_juslin(None)
+    nel = len(db['el'])
+    idx = [db['el'].index(s) for s in ('W', 'C')]
+    cutoff = max(db['r2'][j + i * nel] for i in idx for j in idx)
+    onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
+    el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
+    o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.JUSLIN, db), a.positions, a.cell, onl, el)
+    r = _run(libs, 'Juslin', a, cutoff + 0.3, 2, ['W', 'C'], vatom=False)
+    assert abs(r['eng'] - o['epot']) <= 1e-10 * abs(o['epot'])
+    assert np.abs(r['f'][:r['nlocal']] - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
+    assert np.abs(r['virial'] - _voigt_minus(o['wpot'])).max() <= 1e-10 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))

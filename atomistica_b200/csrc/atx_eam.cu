@@ -121,14 +121,15 @@ __global__ void __launch_bounds__(128)
 k_eam_density(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__restrict__ pos4,
               const long long *__restrict__ seed, const int2 *__restrict__ list,
               const int *__restrict__ mask, double *__restrict__ dF, double *__restrict__ Fe,
-              int *__restrict__ flag, const int *__restrict__ stop) {
+              int *__restrict__ flag, const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   const int gpb = 128 / LANES;
   int s = blockIdx.x * gpb + threadIdx.x / LANES;
   int lane = threadIdx.x % LANES;
   const bool valid = s < nat;
   double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
-  int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  // outer ghosts (role 0) only lend their position: their list is incomplete, nobody reads their F'
+  int dbi = (valid && (!role || role[s] >= 1)) ? T->el2db[(int)pi.w] : -1;
   const bool active = dbi > 0 && (!mask || mask[s] != 0);
   double rho = 0.0;
   int err = 0;
@@ -174,7 +175,7 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
             const int *__restrict__ mask, const double *__restrict__ dF,
             const double *__restrict__ Fe, double *__restrict__ f, double *__restrict__ epa,
             double *__restrict__ wpa, double *__restrict__ partials, int *__restrict__ flag,
-            const int *__restrict__ stop) {
+            const unsigned char *__restrict__ role, const int *__restrict__ stop) {
   if (stop && *stop) return;
   __shared__ double red[ATX_NSUM * 4];
   const int gpb = 128 / LANES;
@@ -185,8 +186,11 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
 
   const bool valid = s < nat;
+  // only owned atoms (role 2) are centres of the force pass: ghost rows receive zero, and the energy /
+  // virial of a ghost is counted by the rank (or the periodic image) that owns it
+  const bool own = valid && (!role || role[s] >= 2);
   double4 pi = valid ? pos4[s] : make_double4(0, 0, 0, 0);
-  int dbi = valid ? T->el2db[(int)pi.w] : -1;
+  int dbi = own ? T->el2db[(int)pi.w] : -1;
   double fx = 0.0, fy = 0.0, fz = 0.0, e = 0.0;
   double wxx = 0, wyy = 0, wzz = 0, wxy = 0, wxz = 0, wyz = 0;    // total virial, i-visits
   double pxx = 0, pyy = 0, pzz = 0, pxy = 0, pxz = 0, pyz = 0;    // per-atom virial
@@ -258,7 +262,7 @@ k_eam_force(int nat, Mat3 A, const EamDev *__restrict__ T, const double4 *__rest
   }
   if (lane == 0 && valid) {
     f[3 * s] = fx; f[3 * s + 1] = fy; f[3 * s + 2] = fz;
-    double ei = e + Fe[s];
+    double ei = own ? e + Fe[s] : 0.0;
     if (epa) epa[s] = ei;
     if (PER_AT) {
       double *w = &wpa[9 * (size_t)s];
@@ -668,19 +672,14 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
     if (o.want_sums) ATX_PASS(atx_reduce_partials(ctx, pot->sc.partials.ptr, nb, o.sums, o.stop));
     return 0;
   }
-  if (o.role) {
-    // the generic kernels know nothing of owned / ghost roles: refuse instead of counting ghosts as owned
-    atx_set_error("TabulatedAlloyEAM: ghost roles (external list / domain decomposition) need the packed-table "
-                  "kernels; the tables of this potential are on different grids or ATX_EAM_GENERIC is set.");
-    return ATX_ERROR_UNSPECIFIED;
-  }
 #define EAM_LAUNCH(L)                                                                             \
   do {                                                                                            \
     {                                                                                             \
     ProfScope ps_(ctx, "eam_density");                                                            \
     k_eam_density<L><<<nblocks, 128, 0, st>>>(nat, p->Abox, pot->dev.ptr, nl->pos4.ptr,           \
                                               nl->seed.ptr, nl->list.ptr, mask_sorted,            \
-                                              pot->dF.ptr, pot->Fe.ptr, pot->flag.ptr, o.stop);   \
+                                              pot->dF.ptr, pot->Fe.ptr, pot->flag.ptr, o.role,    \
+                                              o.stop);                                            \
     }                                                                                             \
     ATX_LAUNCHED();                                                                               \
     ProfScope ps2_(ctx, "eam_force");                                                             \
@@ -688,12 +687,12 @@ int atx_eam_compute_device(atx_eam *pot, atx_particles *p, atx_neighbors *nl,
       k_eam_force<L, true><<<nblocks, 128, 0, st>>>(                                              \
           nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \
           pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr,      \
-          o.stop);                                                                                \
+          o.role, o.stop);                                                                        \
     else                                                                                          \
       k_eam_force<L, false><<<nblocks, 128, 0, st>>>(                                             \
           nat, p->Abox, pot->dev.ptr, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask_sorted,      \
           pot->dF.ptr, pot->Fe.ptr, o.f, o.epa, o.wpa, pot->sc.partials.ptr, pot->flag.ptr,      \
-          o.stop);                                                                                \
+          o.role, o.stop);                                                                        \
     ATX_LAUNCHED();                                                                               \
   } while (0)
   if (lanes == 16) EAM_LAUNCH(16);
@@ -731,13 +730,7 @@ extern "C" int atx_eam_energy_and_forces(atx_eam *pot, atx_particles *p, atx_nei
   ATX_PASS(atx_neighbors_update(nl, p));
   PotOut o;
   ATX_PASS(atx_prepare_out(pot->ctx, nl, pot->sc, epot_per_at != nullptr, wpot_per_at != nullptr, o));
-  if (nl->external) {
-    if (mask || wpot_per_at) {
-      atx_set_error("TabulatedAlloyEAM: masks and per-atom virials are not available with an external neighbour list.");
-      return ATX_ERROR_UNSPECIFIED;
-    }
-    o.role = nl->role_ext.ptr;
-  }
+  if (nl->external) o.role = nl->role_ext.ptr;   // masks / per-atom virials: the generic kernels honour roles too
   const int *mask_sorted = nullptr;
   ATX_PASS(atx_prepare_mask(pot->ctx, nl, pot->sc, mask, &mask_sorted));
   ATX_PASS(atx_eam_compute_device(pot, p, nl, mask_sorted, o));

@@ -87,6 +87,43 @@ def test_eam_external(cu_setfl):
     _compare(a, lambda: native.TabulatedAlloyEAM(setfl=cu_setfl), float(cu_setfl['cutoff']))
 
 
+def test_eam_external_mask_and_per_atom_virial(cu_setfl):
+    """masks and per-atom energies / virials of TabulatedAlloyEAM on a caller-supplied list (the generic
+    kernels honour the owned / ghost roles): owned rows equal the periodic calculation"""
+    a = S.fcc('Cu', 3.615, (4, 4, 4))
+    a.rattle(0.05, seed=3)
+    cutoff = float(cu_setfl['cutoff']) + SKIN
+    mask = (np.random.RandomState(7).rand(len(a)) > 0.4).astype(np.int32)
+    p0 = native.from_atoms(a)
+    nl0 = native.Neighbors(200)
+    pot0 = native.TabulatedAlloyEAM(setfl=cu_setfl)
+    pot0.bind_to(p0, nl0)
+    big, lists = unfold(a, cutoff, 2)
+    nloc = len(a)
+    # the mask of a ghost is the mask of the atom it is an image of
+    L = np.diag(a.cell)
+    frac = np.mod(big.positions / L, 1.0)
+    frac0 = np.mod(a.positions / L, 1.0)
+    owner = np.array([np.argmin(((np.abs(frac0 - fr) + 0.5) % 1.0 - 0.5).__abs__().sum(axis=1)) for fr in frac])
+    assert np.array_equal(owner[:nloc], np.arange(nloc))
+    p = native.from_atoms(big)
+    nl = native.Neighbors(200)
+    pot = native.TabulatedAlloyEAM(setfl=cu_setfl)
+    pot.bind_to(p, nl)
+    nl.set_external(p, nloc, np.arange(len(big)), lists)
+    for m0 in (None, mask):
+        m = None if m0 is None else m0[owner].astype(np.int32)
+        e0, f0, w0, epa0, _, _, wpa0, _ = pot0.energy_and_forces(p0, nl0, mask=m0, epot_per_at=True, wpot_per_at=True)
+        e, f, w, epa, _, _, wpa, _ = pot.energy_and_forces(p, nl, mask=m, epot_per_at=True, wpot_per_at=True)
+        assert abs(e - e0) <= RTOL * abs(e0)
+        assert np.abs(f[:nloc] - f0).max() <= RTOL * max(1.0, np.abs(f0).max())
+        assert np.all(f[nloc:] == 0.0)
+        assert np.abs(w - w0).max() <= RTOL * max(1.0, np.abs(w0).max(), abs(e0))
+        assert np.abs(epa[:nloc] - epa0).max() <= RTOL * max(1.0, np.abs(epa0).max())
+        assert np.abs(wpa[:nloc] - wpa0).max() <= RTOL * max(1.0, np.abs(wpa0).max())
+        assert np.all(epa[nloc:] == 0.0)
+
+
 def test_tersoff_external():
     a = S.diamond('Si', 5.432, (3, 3, 3))
     a.rattle(0.08, seed=4)

@@ -401,6 +401,198 @@ k_pairs_f32(int nat, const __grid_constant__ Geo g, float lo2, float hi2, const 
   if (!FILL) count[s] = cnt;
 }
 
+
+// Pair search for well-filled cells (metals: ~20 atoms per cell, ~500 candidates per atom): one WARP per
+// cell.  The (at most 27) stencil cells of the warp's cell, in the reference's order, form one
+// concatenated candidate sequence.
+//   phase 1: lanes = candidates (two per lane, coalesced 16-byte records, the cell offset folded in once),
+//            loop over the cell's atoms i (broadcast from shared memory): the single-precision test in its
+//            scalar-product form  fi.pj - (|pj|^2 - hi2)/2 > |fi|^2/2  costs three FMA and a compare per
+//            candidate; one ballot per 32 candidates is parked in shared memory.  Candidates in the band
+//            around the cutoff (about one per 50 atoms) go through the exact predicate before the ballot.
+//   phase 2: lanes = atoms i: every lane expands its own ballots in ascending candidate order -- stencil
+//            order, ascending sorted index inside a cell: the reference's order -- and writes its entries.
+// ~300 warp instructions per atom instead of ~590 in k_pairs_f32 (where a warp of 32 atoms straddles cells
+// with different trip counts and executes the hit path with a few active lanes in nearly every iteration).
+// Error bound of the scalar-product form: atx_neighbors_update.  Requires a stencil of +-1 cell.
+#define NLC_WPB 4      // warps (cells) per block
+#define NLC_CB 8       // 64-candidate groups per batch
+#ifndef NLC_MINB
+#define NLC_MINB 7
+#endif
+struct NlcWarp {
+  int prefix[28];           // exclusive prefix of the segment lengths, [27] = total
+  int tb[27];               // first sorted index of the segment minus its prefix
+  int P[27];                // wrap of the segment in the linear form of atx_pack_shift
+  float ox[27], oy[27], oz[27];
+  float4 fi[32];            // atoms of the cell: x, y, z, |f|^2 / 2
+  unsigned mw[NLC_CB * 2][32];   // ballots: word 2 cp + h holds candidates 64 cp + 32 h ... + 31 of atom [ii]
+  int2 cand[NLC_CB * 64];   // per candidate of the batch: sorted index, entry word minus the atom's own shift
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(32 * NLC_WPB, NLC_MINB)
+k_pairs_coop(int ncell, const __grid_constant__ Geo g, float hi2, float bw, const float4 *__restrict__ posf,
+             const double4 *__restrict__ pos4, const int4 *__restrict__ sshift,
+             const int *__restrict__ cell_start, int *__restrict__ count,
+             const long long *__restrict__ seed, int2 *__restrict__ list, int2 *__restrict__ rows, int rows_cap) {
+  __shared__ NlcWarp wsm[NLC_WPB];
+  const int lane = threadIdx.x & 31;
+  NlcWarp &W = wsm[threadIdx.x >> 5];
+  const int c = blockIdx.x * NLC_WPB + (threadIdx.x >> 5);
+  if (c >= ncell) return;
+  const int cb = cell_start[c], ce = cell_start[c + 1];
+  if (cb == ce) return;
+  // ---- the 27 segments (lane k: x = k / 9 - 1 outermost, z = k % 3 - 1 innermost, as the reference loops)
+  {
+    int len = 0, b = 0, P = 0;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (lane < 27) {
+      const int d[3] = {lane / 9 - 1, (lane / 3) % 3 - 1, lane % 3 - 1};
+      int cc[3] = {c / (g.n[2] * g.n[1]), (c / g.n[2]) % g.n[1], c % g.n[2]};
+      int w[3] = {0, 0, 0};
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        cc[k] += d[k];
+        if (g.pbc[k]) {
+          if (cc[k] < 0) { cc[k] += g.n[k]; w[k] = 1; }
+          else if (cc[k] >= g.n[k]) { cc[k] -= g.n[k]; w[k] = -1; }
+        } else if (cc[k] < 0 || cc[k] >= g.n[k]) ok = false;
+      }
+      if (ok) {
+        const int cid = (cc[0] * g.n[1] + cc[1]) * g.n[2] + cc[2];
+        b = cell_start[cid];
+        len = cell_start[cid + 1] - b;
+      }
+      P = w[0] + (w[1] << 8) + (w[2] << 16);
+      ox = (float)(d[0] * g.cvec.m[0] + d[1] * g.cvec.m[3] + d[2] * g.cvec.m[6]);
+      oy = (float)(d[0] * g.cvec.m[1] + d[1] * g.cvec.m[4] + d[2] * g.cvec.m[7]);
+      oz = (float)(d[0] * g.cvec.m[2] + d[1] * g.cvec.m[5] + d[2] * g.cvec.m[8]);
+    }
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane < 27) {
+      W.prefix[lane] = incl - len;
+      W.tb[lane] = b - (incl - len);
+      W.P[lane] = P;
+      W.ox[lane] = ox; W.oy[lane] = oy; W.oz[lane] = oz;
+    }
+    if (lane == 26) W.prefix[27] = incl;
+  }
+  __syncwarp();
+  const int total = W.prefix[27];
+  const int home0 = W.prefix[13];   // segment 13 = the cell itself with zero wrap: starts at cb
+
+  for (int i0 = cb; i0 < ce; i0 += 32) {
+    const int ni = min(32, ce - i0);
+    int psz_own = 0;
+    if (lane < ni) {
+      const float4 f = posf[i0 + lane];
+      W.fi[lane] = make_float4(f.x, f.y, f.z, 0.5f * (f.x * f.x + f.y * f.y + f.z * f.z));
+      const int4 cs = sshift[i0 + lane];
+      psz_own = atx_pack_shift(cs.y, cs.z, cs.w) + ATX_SHIFT_ZERO;
+    }
+    // phase 2 lays lpa lanes over every atom: lane -> (atom ii, part sub of the batch's ballot words)
+    const int lpa = min(NLC_CB, 32 / ni);
+    const int sub = lane / ni, ii2 = lane - sub * ni;
+    const bool act2 = sub < lpa;
+    const int s2 = i0 + ii2;
+    const int psz2 = __shfl_sync(0xffffffffu, psz_own, ii2);
+    int2 *dst = nullptr;
+    if (act2) dst = FILL ? list + seed[s2] : (rows ? rows + (size_t)s2 * rows_cap : nullptr);
+    const int cap2 = FILL ? 0x7fffffff : (rows ? rows_cap : 0);
+    __syncwarp();
+    const int gself = home0 + (i0 + lane - cb);   // atom i0 + lane itself in the candidate sequence
+    int cnt = 0, seg0 = 0, seg1 = 0;
+    for (int g0 = 0; g0 < total; g0 += NLC_CB * 64) {
+      const int nb = min(NLC_CB, (total - g0 + 63) >> 6);
+      // ---- phase 1
+      for (int cp = 0; cp < nb; cp++) {
+        const int gi0 = g0 + cp * 64 + lane, gi1 = gi0 + 32;
+        float p0x = 0.f, p0y = 0.f, p0z = 0.f, nh0 = -INFINITY, p1x = 0.f, p1y = 0.f, p1z = 0.f, nh1 = -INFINITY;
+        int t0 = 0, t1 = 0, a0 = 0, a1 = 0;
+        if (gi0 < total) {
+          while (gi0 >= W.prefix[seg0 + 1]) seg0++;
+          t0 = W.tb[seg0] + gi0;
+          const float4 fj = posf[t0];
+          p0x = fj.x + W.ox[seg0]; p0y = fj.y + W.oy[seg0]; p0z = fj.z + W.oz[seg0];
+          nh0 = -0.5f * ((p0x * p0x + p0y * p0y + p0z * p0z) - hi2);
+          const int wj = __float_as_int(fj.w);
+          a0 = W.P[seg0] - (wj & ATX_SHIFT_MASK);
+          W.cand[cp * 64 + lane] = make_int2(t0, a0 + (wj & 0x7f000000));
+        }
+        if (gi1 < total) {
+          while (gi1 >= W.prefix[seg1 + 1]) seg1++;
+          t1 = W.tb[seg1] + gi1;
+          const float4 fj = posf[t1];
+          p1x = fj.x + W.ox[seg1]; p1y = fj.y + W.oy[seg1]; p1z = fj.z + W.oz[seg1];
+          nh1 = -0.5f * ((p1x * p1x + p1y * p1y + p1z * p1z) - hi2);
+          const int wj = __float_as_int(fj.w);
+          a1 = W.P[seg1] - (wj & ATX_SHIFT_MASK);
+          W.cand[cp * 64 + 32 + lane] = make_int2(t1, a1 + (wj & 0x7f000000));
+        }
+#pragma unroll 2
+        for (int ii = 0; ii < ni; ii++) {
+          const float4 f = W.fi[ii];
+          const float x0 = fmaf(f.z, p0z, fmaf(f.y, p0y, fmaf(f.x, p0x, nh0)));
+          const float x1 = fmaf(f.z, p1z, fmaf(f.y, p1y, fmaf(f.x, p1x, nh1)));
+          bool in0 = x0 > f.w, in1 = x1 > f.w;
+          const float top = f.w + bw;
+          const bool band0 = in0 && x0 <= top, band1 = in1 && x1 <= top;
+          if (__any_sync(0xffffffffu, band0 || band1)) {
+            // the band around the cutoff: the reference's double-precision predicate decides
+            const int4 cs = sshift[i0 + ii];
+            const int psz = atx_pack_shift(cs.y, cs.z, cs.w) + ATX_SHIFT_ZERO;
+            if (band0) in0 = pairs_exact(g, pos4, i0 + ii, t0, psz + a0);
+            if (band1) in1 = pairs_exact(g, pos4, i0 + ii, t1, psz + a1);
+          }
+          const unsigned m0 = __ballot_sync(0xffffffffu, in0), m1 = __ballot_sync(0xffffffffu, in1);
+          if (lane < 2) W.mw[cp * 2 + lane][ii] = lane ? m1 : m0;
+        }
+      }
+      __syncwarp();
+      // the atom itself (same cell, zero wrap) is not its own neighbour
+      {
+        const unsigned rel = (unsigned)(gself - g0);
+        if (lane < ni && rel < (unsigned)(NLC_CB * 64)) W.mw[rel >> 5][lane] &= ~(1u << (rel & 31));
+      }
+      __syncwarp();
+      // ---- phase 2: every lane expands its share of the ballot words of its atom, in ascending order
+      if (act2) {
+        const int q_lo = 2 * ((sub * nb) / lpa), q_hi = 2 * (((sub + 1) * nb) / lpa);
+        int before = 0, tot = 0;
+        for (int q = 0; q < 2 * nb; q++) {
+          const int pc = __popc(W.mw[q][ii2]);
+          tot += pc;
+          if (q < q_lo) before += pc;
+        }
+        int pos = cnt + before;
+        cnt += tot;
+        int q = q_lo;
+        unsigned cur = 0;
+        for (;;) {
+          while (cur == 0 && q < q_hi) cur = W.mw[q++][ii2];
+          if (cur == 0) break;
+          const int k = __ffs(cur) - 1;
+          cur &= cur - 1;
+          int2 e = W.cand[(q - 1) * 32 + k];
+          e.y += psz2;
+          if (pos < cap2) dst[pos] = e;
+          pos++;
+        }
+      }
+      __syncwarp();
+    }
+    if (!FILL && lane < ni) count[i0 + lane] = cnt;   // lanes < ni are part 0 of atom i0 + lane
+    __syncwarp();
+  }
+}
+
 // nebmax = max count, i_last = largest original index (1-based) of an atom that has a pair.
 // (Per-atom atomicMax on two addresses used to cost more than the pair search itself: L2 atomics
 // serialise per address.)
@@ -662,7 +854,8 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   // The bound on the cell-relative coordinates is the cell diagonal sum -- every atom inside the
   // (periodic or non-periodic) cell obeys it; the gather kernel checks it and the search is redone
   // with the exact kernel in the rare case it does not hold (no host round trip on the normal path).
-  float lo2 = 0.f, hi2 = 0.f;
+  float lo2 = 0.f, hi2 = 0.f, hi2c = 0.f, bwc = 0.f;
+  bool coop = false;
   double ext_max = 0.0;
   nl->f32_delta = -1.0;
   if (use_f32 && nat > 0) {
@@ -681,6 +874,25 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
       nl->f32_delta = delta;
       lo2 = std::nextafterf((float)(R2 - delta), -1.0f);
       hi2 = std::nextafterf((float)(R2 + delta), 3.0e38f);
+    }
+    // warp-per-cell kernel (well-filled cells, stencil of +-1 cell): the test is evaluated in its
+    // scalar-product form  d2 = |fi|^2 + |pj|^2 - 2 fi.pj  with  |fi| <= E = sqrt(3) ext_max (the gather kernel
+    // checks the components against ext_max) and |pj| <= P = E + offmax.  With u = 2^-24:
+    //   |fi|^2: 3 roundings + the rounding of fi itself                  <=  5 u E^2
+    //   |pj|^2: 3 roundings + rounding of fj, of the offset, of the sum  <=  7 u P^2
+    //   2 fi.pj: 3 FMA roundings + the roundings of both vectors         <= 12 u E P
+    //   -(|pj|^2 - hi2)/2 and the three FMA partial sums (in d2 units)   <=  u (P^2 + R^2) + 3 u (P^2 + R^2 + 2 E P)
+    // sum <= 34 u P^2 + 4 u R^2; the band half-width is twice that (+5 %), the exact predicate decides inside.
+    const bool coop_env = !(getenv("ATX_NL_COOP") && atoi(getenv("ATX_NL_COOP")) == 0);
+    if (nl->f32_delta > 0.0 && coop_env && nl->sten[0] == 1 && nl->sten[1] == 1 && nl->sten[2] == 1 &&
+        (long long)nat >= 6ll * ncell) {
+      const double u = std::ldexp(1.0, -24), E = std::sqrt(3.0) * ext_max, Pm = E + offmax;
+      const double dc = 2.1 * (34.0 * u * Pm * Pm + 4.0 * u * R2);
+      if (dc <= 0.05 * R2) {
+        coop = true;
+        hi2c = std::nextafterf((float)(R2 + dc), 3.0e38f);
+        bwc = std::nextafterf((float)dc, 3.0e38f);
+      }
     }
   }
   bool f32 = nl->f32_delta > 0.0;
@@ -723,7 +935,11 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
   if (nat > 0) {
     {
       ProfScope ps_(ctx, "nl_pairs_count");
-      if (f32)
+      if (f32 && coop)
+        k_pairs_coop<false><<<(ncell + NLC_WPB - 1) / NLC_WPB, 32 * NLC_WPB, 0, st>>>(
+            ncell, g, hi2c, bwc, nl->posf.ptr, nl->pos4.ptr, nl->sshift.ptr, nl->cell_start.ptr, nl->count.ptr,
+            nullptr, nullptr, rows_cap > 0 ? nl->rows.ptr : nullptr, rows_cap);
+      else if (f32)
         k_pairs_f32<false><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, lo2, hi2, nl->posf.ptr, nl->pos4.ptr,
                                                               nl->sshift.ptr, nl->cell_start.ptr, nl->count.ptr,
                                                               nullptr, nullptr, nl->scal.ptr,
@@ -772,6 +988,10 @@ extern "C" int atx_neighbors_update(atx_neighbors *nl, atx_particles *p) {
         const long long nthr = (long long)nat * 8;
         k_rows_to_csr<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(nat, nl->rows.ptr, rows_cap, nl->seed.ptr,
                                                                       nl->list.ptr);
+      } else if (f32 && coop) {
+        k_pairs_coop<true><<<(ncell + NLC_WPB - 1) / NLC_WPB, 32 * NLC_WPB, 0, st>>>(
+            ncell, g, hi2c, bwc, nl->posf.ptr, nl->pos4.ptr, nl->sshift.ptr, nl->cell_start.ptr, nl->count.ptr,
+            nl->seed.ptr, nl->list.ptr, nullptr, 0);
       } else if (f32) {
         k_pairs_f32<true><<<(nat + 127) / 128, 128, 0, st>>>(nat, g, lo2, hi2, nl->posf.ptr, nl->pos4.ptr,
                                                              nl->sshift.ptr, nl->cell_start.ptr, nl->count.ptr,

@@ -178,3 +178,60 @@ def test_large_property(n):
     nl = native.neighbor_list(p, 3.0)
     assert nl.info()['npairs'] == 4 * len(a)
     assert nl.info()['nebmax'] == 4
+
+
+# ---- well-filled cells: the warp-per-cell kernel (>= 6 atoms per cell, stencil of +-1 cell) -------------
+
+def _gas(n, box, seed, pbc=True, cell=None):
+    rng = np.random.RandomState(seed)
+    pos = rng.rand(n, 3) * np.asarray(box)
+    return S.Atoms(['Cu'] * n, pos, np.diag(box) if cell is None else cell, pbc)
+
+
+@pytest.mark.parametrize('pbc', [True, False, [True, False, True], [False, True, False]])
+def test_dense_cells_pbc_variants(pbc):
+    a = _gas(400, [12.4, 9.3, 9.8], 11, pbc)           # 4 x 3 x 3 cells at cutoff 3.0: 11 atoms per cell
+    nl, p, ref = _compare(a, 3.0, avgn=200)
+    assert nl.info()['n_cells'] == [4, 3, 3] and nl.info()['stencil'] == [1, 1, 1]
+    # moved atoms, second build (fixed-width rows filled by the counting pass)
+    a.positions += np.random.RandomState(3).normal(scale=0.1, size=a.positions.shape)
+    p.coordinates[:, :] = a.positions
+    p.I_changed_positions()
+    seed, last, nb, dc = nl.to_host(p)
+    ref = oracle.neighbor_list(a.positions, a.cell, a.pbc, 3.0, 200)
+    n = ref.npairs + len(a)
+    assert np.array_equal(nb[:n], ref.neighbors[:n]) and np.array_equal(dc[:n], ref.dc[:n])
+
+
+def test_dense_cells_more_than_a_warp_per_cell():
+    a = _gas(1300, [9.1, 9.2, 9.3], 5)                  # 3 x 3 x 3 cells: 48 atoms per cell, 2 groups of lanes
+    nl, p, ref = _compare(a, 3.0, avgn=400)
+    assert nl.info()['n_cells'] == [3, 3, 3] and nl.info()['stencil'] == [1, 1, 1]
+
+
+def test_dense_cells_triclinic_and_band():
+    cell = np.array([[12.0, 0.0, 0.0], [2.5, 9.0, 0.0], [1.0, -1.5, 8.0]])
+    rng = np.random.RandomState(8)
+    pos = rng.rand(260, 3) @ cell
+    a = S.Atoms(['Cu'] * 260, pos, cell, True)
+    # pairs placed within 1e-9 of the cutoff sphere (inside and outside): the band of the single-precision
+    # test, decided by the exact predicate
+    rc = 2.9
+    for k in range(40):
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        a.positions[2 * k + 1] = a.positions[2 * k] + u * (rc + (1e-9 if k % 2 else -1e-9) * (1 + k))
+    _compare(a, rc, avgn=200)
+
+
+def test_dense_cells_match_the_thread_per_atom_kernel(monkeypatch):
+    a = _gas(4000, [30.0, 28.0, 31.0], 9)
+    p = native.from_atoms(a)
+    out = []
+    for coop in ('1', '0'):
+        monkeypatch.setenv('ATX_NL_COOP', coop)
+        nl = native.Neighbors(200)
+        nl.request_interaction_range(3.2)
+        out.append(nl.to_host(p))
+    for x, y in zip(out[0], out[1]):
+        assert np.array_equal(x, y)

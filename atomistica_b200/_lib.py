@@ -75,7 +75,7 @@ SYMBOLS = [
     'atx_particles_create', 'atx_particles_destroy', 'atx_particles_set_cell', 'atx_particles_set_positions',
     'atx_particles_set_elements', 'atx_particles_set_positions_device',
     'atx_neighbors_create', 'atx_neighbors_destroy', 'atx_neighbors_request_interaction_range',
-    'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_rebuild', 'atx_neighbors_get_info', 'atx_neighbors_get_counters', 'atx_neighbors_get_interaction_range',
+    'atx_neighbors_set_verlet_shell', 'atx_neighbors_update', 'atx_neighbors_rebuild', 'atx_neighbors_get_info', 'atx_neighbors_get_counters', 'atx_neighbors_get_interaction_range', 'atx_neighbors_request_interaction_range_pair', 'atx_neighbors_get_pair_range',
     'atx_neighbors_copy_to_host', 'atx_neighbors_set_external',
     'atx_neighbors_coordination_numbers', 'atx_neighbors_pair_distribution', 'atx_neighbors_angle_distribution',
     'atx_neighbors_bond_angles',

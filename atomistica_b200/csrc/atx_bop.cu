@@ -1320,7 +1320,7 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
             if (jus) cutoff = cm > 1.0 ? std::sqrt(cm * cm / (4 * (cm - 1))) * mx : 0.0;
             else cutoff = std::sqrt(cm > 2.0 ? cm * cm / (4 * (cm - 1)) : 1.0) * mx;
           }
-          ATX_PASS(atx_neighbors_request_interaction_range(nl, cutoff));
+          ATX_PASS(atx_neighbors_request_interaction_range_pair(nl, cutoff, i, j));
         }
   pot->bound = true;
   return 0;

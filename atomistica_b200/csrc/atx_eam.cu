@@ -603,7 +603,11 @@ extern "C" int atx_eam_bind_to(atx_eam *pot, atx_particles *p, atx_neighbors *nl
     any = any || el2db[k] > 0;
   }
   ATX_CUDA(cudaMemcpy(pot->dev.ptr, &pot->host, sizeof(EamDev), cudaMemcpyHostToDevice));
-  if (any && nl) ATX_PASS(atx_neighbors_request_interaction_range(nl, pot->cutoff));
+  if (any && nl)   // tabulated_alloy_eam.f90:297-350: every pair of elements the tables cover
+    for (int i = 1; i <= nel; i++)
+      for (int j = i; j <= nel; j++)
+        if (el2db[i - 1] > 0 && el2db[j - 1] > 0)
+          ATX_PASS(atx_neighbors_request_interaction_range_pair(nl, pot->cutoff, i, j));
   pot->bound = true;
   return 0;
 }

@@ -146,6 +146,7 @@ struct atx_neighbors {
   atx_ctx *ctx = nullptr;
   int avgn = 100;
   double interaction_range = 0.0;
+  double pair_range[32][32] = {{0.0}};   // largest request per pair of particle element ids (1-based), LAMMPS hosts ask for it
   double verlet_shell = 0.0;
   double cutoff = 0.0;
   bool initialized = false;

@@ -743,6 +743,24 @@ extern "C" int atx_neighbors_request_interaction_range(atx_neighbors *nl, double
   return 0;
 }
 
+// request_interaction_range(nl, cutoff, el1, el2) (lammps_neighbors.f90:223-251, python_neighbors.f90:381-423):
+// the list itself is built with the largest range; the per-pair values are what neighbors_get_cutoff hands
+// to a host that builds the list (LAMMPS sets cutsq(i,j) from them)
+extern "C" int atx_neighbors_request_interaction_range_pair(atx_neighbors *nl, double cutoff, int el1, int el2) {
+  if (!nl) return ATX_ERROR_UNSPECIFIED;
+  if (el1 >= 1 && el1 < 32 && el2 >= 1 && el2 < 32) {
+    if (cutoff > nl->pair_range[el1][el2]) nl->pair_range[el1][el2] = cutoff;
+    if (cutoff > nl->pair_range[el2][el1]) nl->pair_range[el2][el1] = cutoff;
+  }
+  return atx_neighbors_request_interaction_range(nl, cutoff);
+}
+
+extern "C" int atx_neighbors_get_pair_range(atx_neighbors *nl, int el1, int el2, double *range) {
+  if (!nl || !range) return ATX_ERROR_UNSPECIFIED;
+  *range = (el1 >= 1 && el1 < 32 && el2 >= 1 && el2 < 32) ? nl->pair_range[el1][el2] : 0.0;
+  return 0;
+}
+
 extern "C" int atx_neighbors_set_verlet_shell(atx_neighbors *nl, double verlet_shell) {
   if (nl && nl->ctx) cudaSetDevice(nl->ctx->device);
   nl->verlet_shell = verlet_shell;

@@ -202,7 +202,11 @@ extern "C" int atx_pair_bind_to(atx_pair *pot, atx_particles *p, atx_neighbors *
   pot->dev.el1 = el1;
   pot->dev.el2 = el2;
   // lj_cut.f90:168-174: request the cutoff for every element pair the filters select
-  if (nl && el1 != 0 && el2 != 0) ATX_PASS(atx_neighbors_request_interaction_range(nl, pot->cutoff));
+  if (nl && el1 != 0 && el2 != 0)
+    for (int i = 1; i < 32; i++)
+      for (int j = 1; j < 32; j++)
+        if (((el1 >> i) & 1) && ((el2 >> j) & 1))
+          ATX_PASS(atx_neighbors_request_interaction_range_pair(nl, pot->cutoff, i, j));
   pot->bound = true;
   return 0;
 }

@@ -306,22 +306,26 @@ extern "C" int atx_rebo2_bind_to(atx_rebo2 *pot, atx_particles *p, atx_neighbors
     return ATX_ERROR_UNSPECIFIED;
   }
   Rebo2Dev &D = pot->dev;
-  bool hasC = false, hasH = false;
   for (int k = 0; k < 32; k++) D.el2typ[k] = 0;
   for (int k = 0; k < nel; k++) {
-    if (el2Z[k] == 6) { D.el2typ[k + 1] = RB_C; hasC = true; }
-    else if (el2Z[k] == 1) { D.el2typ[k + 1] = RB_H; hasH = true; }
+    if (el2Z[k] == 6) D.el2typ[k + 1] = RB_C;
+    else if (el2Z[k] == 1) D.el2typ[k + 1] = RB_H;
   }
   // rebo2_module.f90:96-125
   if (nl) {
     // the screened variant needs every atom that can screen a bond of the longest cutoff
     // (rebo2_module.f90:96-125 with SCREENING: sqrt(C_dr_cut) * max cutoff)
-    if (hasC && pot->screened)
-      ATX_PASS(atx_neighbors_request_interaction_range(
-          nl, sqrt(pot->scr.max_cut_sq[RB_CC]) * (pot->scr.C_dr_cut > 1.0 ? sqrt(pot->scr.C_dr_cut) : 1.0)));
-    if (hasC) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_CC]));
-    if (hasC && hasH) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_CH]));
-    if (hasH) ATX_PASS(atx_neighbors_request_interaction_range(nl, D.cut_h[RB_HH]));
+    const double scr_range = pot->screened
+        ? sqrt(pot->scr.max_cut_sq[RB_CC]) * (pot->scr.C_dr_cut > 1.0 ? sqrt(pot->scr.C_dr_cut) : 1.0) : 0.0;
+    for (int i = 1; i <= nel; i++)
+      for (int j = i; j <= nel; j++) {
+        const int ti = D.el2typ[i], tj = D.el2typ[j];
+        if (!ti || !tj) continue;
+        const int pt = (ti == RB_C && tj == RB_C) ? RB_CC : ((ti == RB_H && tj == RB_H) ? RB_HH : RB_CH);
+        double c = D.cut_h[pt];
+        if (pt == RB_CC && scr_range > c) c = scr_range;
+        ATX_PASS(atx_neighbors_request_interaction_range_pair(nl, c, i, j));
+      }
   }
   pot->bound = true;
   return 0;

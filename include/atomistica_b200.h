@@ -104,6 +104,13 @@ int atx_neighbors_get_counters(atx_neighbors *nl, long long *nbuilds, long long 
 /* largest interaction range requested so far (neighbors_request_interaction_range,
  * python_neighbors.f90:381-423 / lammps_neighbors.f90:223-251) and the Verlet shell */
 int atx_neighbors_get_interaction_range(atx_neighbors *nl, double *range, double *verlet_shell);
+/* request_interaction_range(nl, cutoff, el1, el2) with the element pair (particle element ids, 1-based):
+ * same effect on the list as atx_neighbors_request_interaction_range, and the per-pair maximum is
+ * kept for hosts that build the list themselves -- neighbors_get_cutoff(nl, i, j)
+ * (lammps_neighbors.f90:223-251) feeds LAMMPS' cutsq(i,j) from it; 0 for pairs nobody asked for.
+ * The bind_to entry points of the potentials use it. */
+int atx_neighbors_request_interaction_range_pair(atx_neighbors *nl, double cutoff, int el1, int el2);
+int atx_neighbors_get_pair_range(atx_neighbors *nl, int el1, int el2, double *range);
 /* List post-processing on the device-resident list (no copy-back of the list):
  * f_get_coordination_numbers (src/python/f90/neighbors_wrap.f90:271-302; c[nat], original atom order) and
  * the helpers of src/python/c/analysis.c -- pair_distribution (:29-106), angle_distribution (:108-206),

@@ -70,6 +70,9 @@ int lmp_harness_run(const char *name, const char *param_file, int ntypes, const 
   particles_get_interaction_range(particles, 1, 1, &range);
   out[7] = rcghost;
   out[8] = rc;
+  // init_one(i, j) (pair_atomistica.cpp:366-384): the per-type-pair cutoffs LAMMPS builds its lists with
+  neighbors_get_cutoff(neighbors, ntypes, ntypes, &out[9]);
+  neighbors_get_cutoff(neighbors, 1, ntypes, &out[10]);
   // Atomistica_neigh: seed / last relative to a neighbour array that starts at address 0
   std::vector<intptr_t> seed(nall, -1), last(nall, -2);
   int *neighb = nullptr;

@@ -80,7 +80,7 @@ def _run(libs, name, atoms, cutoff, shell, types, param_file=None, eatom=True, v
                              dp(va), dp(out), err)
     if rc != 0:
         raise RuntimeError(err.value.decode(errors='replace'))
-    return dict(eng=out[0], virial=out[1:7].copy(), rcghost=out[7], rc=out[8], f=f, eatom=ea, vatom=va, nlocal=nlocal,
+    return dict(eng=out[0], virial=out[1:7].copy(), rcghost=out[7], rc=out[8], rc_last=out[9], rc_cross=out[10], f=f, eatom=ea, vatom=va, nlocal=nlocal,
                 img=img)
 
 
@@ -144,6 +144,9 @@ def test_two_types_eam_and_rebo2(libs, tmp_path):
     el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
     o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.BRENNER, db), a.positions, a.cell, onl, el)
     r = _run(libs, 'Brenner', a, max(db['r2']) + 0.3, 2, ['Si', 'C'], vatom=False)
+    # neighbors_get_cutoff(i, j): the cutoff of THAT pair of types (lammps_neighbors.f90:223-251), el = ['C', 'Si']
+    assert abs(r['rc'] - db['r2'][2]) < 1e-12 and abs(r['rc_last'] - db['r2'][0]) < 1e-12   # Si-Si, C-C
+    assert abs(r['rc_cross'] - db['r2'][1]) < 1e-12                                          # Si-C
     assert abs(r['eng'] - o['epot']) <= 1e-10 * abs(o['epot'])
     assert np.abs(r['f'][:r['nlocal']] - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
     # TabulatedAlloyEAM with its setfl file given in a ptrdict parameter file (pair_style atomistica <name> <file>)

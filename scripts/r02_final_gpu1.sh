@@ -48,6 +48,8 @@ for _ in range(3): e = pot.energy_and_forces(p, nl)[0]
 print(len(a), e / len(a))
 PY
 prof rebo2_final 'k_rebo2_' 4 python /tmp/prof_rebo2.py
+prof nl_cu_final 'k_pairs_coop|k_rows_to_csr|k_gather_sorted|k_cell_' 14 python scripts/r02_nl_probe.py
+prof bop_final 'k_bop_center|k_bop_gather' 6 python bench.py --steps 5 --warmup 3 --blocks c4 --c4-kinds Tersoff --c4-cells 64 --c4-steps 10 --no-cpu
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_raw.csv python bench.py --steps 20 --warmup 5 --blocks c2 --no-cpu > $OUT/ncu_launches.log 2>&1
 python scripts/summarize_ncu.py launches $OUT/launches_raw.csv $OUT/r02_launches_final.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 700 python bench.py --steps 20 --warmup 5 --blocks c2 --no-cpu" > /dev/null 2>> $OUT/summary.txt
 rm -f $OUT/launches_raw.csv

@@ -276,10 +276,6 @@ extern "C" int atx_rebo2_create(atx_ctx *ctx, const atx_rebo2_params *par, atx_r
 extern "C" int atx_rebo2_create_screened(atx_ctx *ctx, const atx_rebo2_params *par,
                                          const atx_rebo2_screening *scr, atx_rebo2 **out) {
   if (!ctx || !par || !scr || !out) return ATX_ERROR_UNSPECIFIED;
-  if (par->with_dihedral) {
-    atx_set_error("Rebo2Scr: the (alternative) dihedral term is not available.");
-    return ATX_ERROR_UNSPECIFIED;
-  }
   if (!(scr->Cmax > scr->Cmin) || !(scr->Cmax > 1.0)) {
     atx_set_error("Rebo2Scr: need Cmax > Cmin and Cmax > 1.");
     return ATX_ERROR_UNSPECIFIED;

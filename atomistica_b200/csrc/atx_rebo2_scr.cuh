@@ -1,8 +1,8 @@
 // Screened REBO2 (Rebo2Scr) per-atom device functions.
 //
 // Replaces rebo2_kernel of src/potentials/bop/rebo2/bop_kernel_rebo2.f90 compiled with SCREENING
-// and NUM_NEIGHBORS (rebo2_scr.f90:60-64; the ALT_DIHEDRAL term is not built and
-// atx_rebo2_create_screened refuses with_dihedral):
+// NUM_NEIGHBORS and ALT_DIHEDRAL (rebo2_scr.f90:60-64; with_dihedral switches the dihedral term of this
+// build, :2089-2371, on):
 //   rbs_bonds_atom  loop 1 (:700-1181): bond table with the three cutoff families ar / bo / nc
 //                   (attractive-repulsive, bond order, neighbour count), the Baskes screening
 //                   function of the C-C bonds beyond the inner cutoff and the per-bond lists of
@@ -474,11 +474,135 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
     if (nti > 3.0) nti = 3.0;
     if (ntj > 3.0) ntj = 3.0;
 
+    // ---- dihedral term of the screened build (ALT_DIHEDRAL, :2089-2371): the angle between the planes
+    //      (r_ij, r_k1k2) and (r_ij, r_l1l2) over the pairs k1 < k2 of bond partners of i and l1 < l2 of j
+    double bdh = 0.0, tij = 0.0, dtdni = 0.0, dtdnj = 0.0, dtdncn = 0.0;
+    if (P.with_dihedral && ijpot == RB_CC) {
+      rb_table3d(P.Tcc, 4, 4, 9, nti, ntj, nconj, tij, dtdni, dtdnj, dtdncn);
+      tij = 2 * tij; dtdni = 2 * dtdni; dtdnj = 2 * dtdnj; dtdncn = 2 * dtdncn;   // :2109-2112
+      const double tije = tij * faij * fcarij;
+      if (tij != 0) {
+        const double rlijsq = rlij * rlij;
+        for (int ik1 = 0; ik1 < nbi - 1; ik1++) {
+          if (ik1 == ij) continue;
+          const double4 v1 = T.b_vec[qi + ik1];
+          if (!(v1.w < S.bo_h[T.b_typ[qi + ik1]])) continue;
+          const int k1 = T.b_nb[qi + ik1], k1s = T.b_shift[qi + ik1];
+          const double2 c1 = T.b_cbo[qi + ik1];
+          for (int ik2 = ik1 + 1; ik2 < nbi; ik2++) {
+            if (ik2 == ij) continue;
+            const double4 v2 = T.b_vec[qi + ik2];
+            if (!(v2.w < S.bo_h[T.b_typ[qi + ik2]])) continue;
+            const int k2 = T.b_nb[qi + ik2], k2s = T.b_shift[qi + ik2];
+            const double2 c2 = T.b_cbo[qi + ik2];
+            const double kx = v2.w * v2.x - v1.w * v1.x, ky = v2.w * v2.y - v1.w * v1.y, kz = v2.w * v2.z - v1.w * v1.z;
+            const double dot_ij_k = rijx * kx + rijy * ky + rijz * kz;
+            const double ksq = kx * kx + ky * ky + kz * kz;
+            const double dck = rlijsq * ksq - dot_ij_k * dot_ij_k;
+            for (int jl1 = 0; jl1 < nbj - 1; jl1++) {
+              const int l1 = T.b_nb[qj + jl1];
+              int s1x, s1y, s1z;
+              atx_unpack_shift(T.b_shift[qj + jl1], s1x, s1y, s1z);
+              s1x += jsx; s1y += jsy; s1z += jsz;
+              const int l1s = atx_pack_shift(s1x, s1y, s1z);
+              // l1 is neither i nor k1 nor k2 (as atoms incl. their periodic image, :2163-2167)
+              if ((l1 == i && s1x == 0 && s1y == 0 && s1z == 0) ||
+                  (l1 == k1 && (l1s & ATX_SHIFT_MASK) == (k1s & ATX_SHIFT_MASK)) ||
+                  (l1 == k2 && (l1s & ATX_SHIFT_MASK) == (k2s & ATX_SHIFT_MASK))) continue;
+              const double4 w1 = T.b_vec[qj + jl1];
+              if (!(w1.w < S.bo_h[T.b_typ[qj + jl1]])) continue;
+              const double2 d1 = T.b_cbo[qj + jl1];
+              for (int jl2 = jl1 + 1; jl2 < nbj; jl2++) {
+                const int l2 = T.b_nb[qj + jl2];
+                int s2x, s2y, s2z;
+                atx_unpack_shift(T.b_shift[qj + jl2], s2x, s2y, s2z);
+                s2x += jsx; s2y += jsy; s2z += jsz;
+                const int l2s = atx_pack_shift(s2x, s2y, s2z);
+                if ((l2 == i && s2x == 0 && s2y == 0 && s2z == 0) ||
+                    (l2 == k1 && (l2s & ATX_SHIFT_MASK) == (k1s & ATX_SHIFT_MASK)) ||
+                    (l2 == k2 && (l2s & ATX_SHIFT_MASK) == (k2s & ATX_SHIFT_MASK))) continue;
+                const double4 w2 = T.b_vec[qj + jl2];
+                if (!(w2.w < S.bo_h[T.b_typ[qj + jl2]])) continue;
+                const double2 d2 = T.b_cbo[qj + jl2];
+                const double lx = w2.w * w2.x - w1.w * w1.x, ly = w2.w * w2.y - w1.w * w1.y,
+                             lz = w2.w * w2.z - w1.w * w1.z;
+                const double dot_ij_l = rijx * lx + rijy * ly + rijz * lz;
+                const double dot_k_l = kx * lx + ky * ly + kz * lz;
+                const double lsq = lx * lx + ly * ly + lz * lz;
+                const double dcl = rlijsq * lsq - dot_ij_l * dot_ij_l;
+                const double abs_dc = sqrt(dck * dcl);
+                const double cost = (dot_ij_k * dot_ij_l - rlijsq * dot_k_l) / abs_dc;
+                double bdhij = 1 - cost * cost;
+                const double fc4 = c1.x * c2.x * d1.x * d2.x;
+                bdh += bdhij * fc4;
+                bdhij = bdhij * tij * faij * fcarij / 2;
+                const double dbd = -2 * cost * tije * fc4 / 2;
+                const double ak = dot_ij_l / abs_dc + cost * dot_ij_k / dck;
+                const double al = dot_ij_k / abs_dc + cost * dot_ij_l / dcl;
+                const double ar = 2 * dot_k_l / abs_dc + cost * (ksq / dck + lsq / dcl);
+                double dx_ = dbd * (ak * kx + al * lx - ar * rijx), dy_ = dbd * (ak * ky + al * ly - ar * rijy),
+                       dz_ = dbd * (ak * kz + al * lz - ar * rijz);
+                fix += dx_; fiy += dy_; fiz += dz_;
+                fjx -= dx_; fjy -= dy_; fjz -= dz_;
+                rbs_outer(wij, 1.0, rijx, rijy, rijz, dx_, dy_, dz_);
+                dx_ = dbd * (-(cost / dck * kx + lx / abs_dc) * rlijsq + ak * rijx);
+                dy_ = dbd * (-(cost / dck * ky + ly / abs_dc) * rlijsq + ak * rijy);
+                dz_ = dbd * (-(cost / dck * kz + lz / abs_dc) * rlijsq + ak * rijz);
+                rbs_add3(f, k1, dx_, dy_, dz_);
+                rbs_add3(f, k2, -dx_, -dy_, -dz_);
+                rbs_outer(wij, 1.0, kx, ky, kz, dx_, dy_, dz_);
+                dx_ = dbd * (-(cost / dcl * lx + kx / abs_dc) * rlijsq + al * rijx);
+                dy_ = dbd * (-(cost / dcl * ly + ky / abs_dc) * rlijsq + al * rijy);
+                dz_ = dbd * (-(cost / dcl * lz + kz / abs_dc) * rlijsq + al * rijz);
+                rbs_add3(f, l1, dx_, dy_, dz_);
+                rbs_add3(f, l2, -dx_, -dy_, -dz_);
+                rbs_outer(wij, 1.0, lx, ly, lz, dx_, dy_, dz_);
+                // derivatives of the four bond-order cutoffs
+                double c = bdhij * c1.y * c2.x * d1.x * d2.x;
+                dx_ = c * v1.x; dy_ = c * v1.y; dz_ = c * v1.z;
+                fix += dx_; fiy += dy_; fiz += dz_;
+                rbs_add3(f, k1, -dx_, -dy_, -dz_);
+                rbs_outer(wij, 1.0, v1.w * v1.x, v1.w * v1.y, v1.w * v1.z, dx_, dy_, dz_);
+                c = bdhij * c2.y * c1.x * d1.x * d2.x;
+                dx_ = c * v2.x; dy_ = c * v2.y; dz_ = c * v2.z;
+                fix += dx_; fiy += dy_; fiz += dz_;
+                rbs_add3(f, k2, -dx_, -dy_, -dz_);
+                rbs_outer(wij, 1.0, v2.w * v2.x, v2.w * v2.y, v2.w * v2.z, dx_, dy_, dz_);
+                c = bdhij * d1.y * d2.x * c1.x * c2.x;
+                dx_ = c * w1.x; dy_ = c * w1.y; dz_ = c * w1.z;
+                fjx += dx_; fjy += dy_; fjz += dz_;
+                rbs_add3(f, l1, -dx_, -dy_, -dz_);
+                rbs_outer(wij, 1.0, w1.w * w1.x, w1.w * w1.y, w1.w * w1.z, dx_, dy_, dz_);
+                c = bdhij * d2.y * d1.x * c1.x * c2.x;
+                dx_ = c * w2.x; dy_ = c * w2.y; dz_ = c * w2.z;
+                fjx += dx_; fjy += dy_; fjz += dz_;
+                rbs_add3(f, l2, -dx_, -dy_, -dz_);
+                rbs_outer(wij, 1.0, w2.w * w2.x, w2.w * w2.y, w2.w * w2.z, dx_, dy_, dz_);
+                // screening neighbours of the four bonds (:2322-2354)
+                {
+                  const size_t q1 = (size_t)i * T.nss + T.b_sseed[qi + ik1], q2 = (size_t)i * T.nss + T.b_sseed[qi + ik2];
+                  const size_t q3 = (size_t)j * T.nss + T.b_sseed[qj + jl1], q4 = (size_t)j * T.nss + T.b_sseed[qj + jl2];
+                  const int n1 = T.b_scnt[qi + ik1], n2 = T.b_scnt[qi + ik2], n3 = T.b_scnt[qj + jl1], n4 = T.b_scnt[qj + jl2];
+                  for (int m = 0; m < n1; m++) RBS_ADD(&T.s_facbo[q1 + m], bdhij * c2.x * d1.x * d2.x);
+                  for (int m = 0; m < n2; m++) RBS_ADD(&T.s_facbo[q2 + m], bdhij * c1.x * d1.x * d2.x);
+                  for (int m = 0; m < n3; m++) RBS_ADD(&T.s_facbo[q3 + m], bdhij * d2.x * c1.x * c2.x);
+                  for (int m = 0; m < n4; m++) RBS_ADD(&T.s_facbo[q4 + m], bdhij * d1.x * c1.x * c2.x);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+
     double fij = 0.0, dfdni = 0.0, dfdnj = 0.0, dfdncn = 0.0;
     if (ijpot == RB_CC) rb_table3d(P.Fcc, 4, 4, 9, nti, ntj, nconj, fij, dfdni, dfdnj, dfdncn);
     else if (ijpot == RB_HH) rb_table3d(P.Fhh, 4, 4, 9, nti, ntj, nconj, fij, dfdni, dfdnj, dfdncn);
     else if (ktypi == RB_C) rb_table3d(P.Fch, 4, 4, 9, ntj, nti, nconj, fij, dfdnj, dfdni, dfdncn);
     else if (ktypj == RB_C) rb_table3d(P.Fch, 4, 4, 9, nti, ntj, nconj, fij, dfdni, dfdnj, dfdncn);
+    dfdni += dtdni * bdh;     // :2405-2411
+    dfdnj += dtdnj * bdh;
+    dfdncn += dtdncn * bdh;
     dfdni = 0.5 * fcarij * faij * dfdni;
     dfdnj = 0.5 * fcarij * faij * dfdnj;
     dfdncn = 0.5 * fcarij * faij * dfdncn;
@@ -583,7 +707,7 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
     }
 
     // ---- pair terms (:2525-2716)
-    const double baveij = 0.5 * (bij + bji + fij);
+    const double baveij = 0.5 * (bij + bji + fij + tij * bdh);   // :2524-2526
     const double hlfvij = fcarij * (frij + baveij * faij) / 2;
     acc[0] += 2 * hlfvij;
     if (epa) {

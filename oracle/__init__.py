@@ -856,7 +856,8 @@ REBO2_SCR_DEFAULTS = dict(cc_in_r1=1.95, cc_in_r2=2.25, cc_ar_r1=2.179347, cc_ar
 
 class Rebo2Scr(Rebo2):
     """rebo2_scr (src/potentials/bop/rebo2/rebo2_scr.f90): screened REBO2, C-C bonds screened only,
-    trigonometric cutoffs, without the (alternative) dihedral term"""
+    trigonometric cutoffs; with_dihedral=True adds the alternative dihedral term (ALT_DIHEDRAL,
+    bop_kernel_rebo2.f90:2089-2371)"""
 
     def __init__(self, **kwargs):
         sd = dict(REBO2_SCR_DEFAULTS)
@@ -869,8 +870,6 @@ class Rebo2Scr(Rebo2):
         base.setdefault('cc_in_r1', sd['cc_in_r1'])
         base.setdefault('cc_in_r2', sd['cc_in_r2'])
         super().__init__(**base)
-        if self.d['with_dihedral']:
-            raise NotImplementedError('ALT_DIHEDRAL of Rebo2Scr is not restated')
         self.sd = sd
         q = Rebo2ScrStruct()
         for k, _ in Rebo2ScrStruct._fields_:

@@ -273,7 +273,6 @@ static int rebo2_kernel(const orc_rebo2_params_t *par, const orc_rebo2_scr_t *sc
                         double *epot_per_at, double *epot_per_bond, double *f_per_bond,
                         double *wpot_per_at, double *wpot_per_bond) {
   const int typemax = 3;
-  if (scr && par->with_dihedral) return -3; /* ALT_DIHEDRAL (bop_kernel_rebo2.f90:2089-2371) not restated */
   /* cutoff families, index ijpot-1 (rebo2_db.f90:170-253) */
   double cut_ar_l[10], cut_ar_h[10], cut_bo_l[10], cut_bo_h[10], cut_nc_l[10], cut_nc_h[10], max_cut_sq[10];
   for (int q = 0; q < 10; q++) {
@@ -805,7 +804,111 @@ static int rebo2_kernel(const orc_rebo2_params_t *par, const orc_rebo2_scr_t *sc
       if (ntj > 3.0) ntj = 3.0;
 
       double bdh = 0.0, tij = 0.0, dtdni = 0.0, dtdnj = 0.0, dtdncn = 0.0;
-      if (par->with_dihedral && ijpot == C_C) {
+      if (scr && par->with_dihedral && ijpot == C_C) {
+        /* ALT_DIHEDRAL (the dihedral term of the screened build, rebo2_scr.f90:62), :2089-2371: the angle
+         * between the planes (r_ij, r_k1k2) and (r_ij, r_l1l2) over the PAIRS k1 < k2 of bond partners of i and
+         * l1 < l2 of j; T_ij enters doubled (:2109-2112) */
+        orc_table3d_eval(&par->Tcc, nti, ntj, nconj, &tij, &dtdni, &dtdnj, &dtdncn);
+        tij = 2 * tij; dtdni = 2 * dtdni; dtdnj = 2 * dtdnj; dtdncn = 2 * dtdncn;
+        double tije = tij * faij * fcarij;
+        if (tij != 0) {
+          const double rlijsq = rlij * rlij;
+          const double rij[3] = {rlij * rnij[0], rlij * rnij[1], rlij * rnij[2]};
+          for (long ik1 = istart; ik1 <= ifinsh - 1; ik1++) {
+            if (ik1 == ij) continue;
+            int k1 = neb[ik1];
+            shift_t kdc1 = dcofi[ik1 - istart];
+            double rlik1 = bndlen[ik1];
+            if (!(rlik1 < cut_bo_h[bndtyp[ik1] - 1])) continue;
+            const double *rnik1 = &bndnm[3 * ik1];
+            double fcik1 = cutfcnbo[ik1], dfcik1r = cutdrvbo[ik1];
+            for (long ik2 = ik1 + 1; ik2 <= ifinsh; ik2++) {
+              if (ik2 == ij) continue;
+              int k2 = neb[ik2];
+              shift_t kdc2 = dcofi[ik2 - istart];
+              double rlik2 = bndlen[ik2];
+              if (!(rlik2 < cut_bo_h[bndtyp[ik2] - 1])) continue;
+              const double *rnik2 = &bndnm[3 * ik2];
+              double rk1k2[3];
+              for (int c = 0; c < 3; c++) rk1k2[c] = rlik2 * rnik2[c] - rlik1 * rnik1[c];
+              double dot_ij_k1k2 = rij[0] * rk1k2[0] + rij[1] * rk1k2[1] + rij[2] * rk1k2[2];
+              double k1k2sq = rk1k2[0] * rk1k2[0] + rk1k2[1] * rk1k2[1] + rk1k2[2] * rk1k2[2];
+              double dck1k2 = rlijsq * k1k2sq - dot_ij_k1k2 * dot_ij_k1k2;
+              double fcik2 = cutfcnbo[ik2], dfcik2r = cutdrvbo[ik2];
+              for (long jl1 = neb_seed[j]; jl1 <= neb_last[j] - 1; jl1++) {
+                int l1 = neb[jl1];
+                shift_t ldc1 = sadd(jdc, &dcell[3 * jl1]);
+                if (!((l1 != i || !szero(ldc1)) && (l1 != k1 || !seq(ldc1, kdc1)) && (l1 != k2 || !seq(ldc1, kdc2))))
+                  continue;
+                double rljl1 = bndlen[jl1];
+                if (!(rljl1 < cut_bo_h[bndtyp[jl1] - 1])) continue;
+                const double *rnjl1 = &bndnm[3 * jl1];
+                double fcjl1 = cutfcnbo[jl1], dfcjl1r = cutdrvbo[jl1];
+                for (long jl2 = jl1 + 1; jl2 <= neb_last[j]; jl2++) {
+                  int l2 = neb[jl2];
+                  shift_t ldc2 = sadd(jdc, &dcell[3 * jl2]);
+                  if (!((l2 != i || !szero(ldc2)) && (l2 != k1 || !seq(ldc2, kdc1)) && (l2 != k2 || !seq(ldc2, kdc2))))
+                    continue;
+                  double rljl2 = bndlen[jl2];
+                  if (!(rljl2 < cut_bo_h[bndtyp[jl2] - 1])) continue;
+                  const double *rnjl2 = &bndnm[3 * jl2];
+                  double fcjl2 = cutfcnbo[jl2], dfcjl2r = cutdrvbo[jl2];
+                  double rl1l2[3];
+                  for (int c = 0; c < 3; c++) rl1l2[c] = rljl2 * rnjl2[c] - rljl1 * rnjl1[c];
+                  double dot_ij_l1l2 = rij[0] * rl1l2[0] + rij[1] * rl1l2[1] + rij[2] * rl1l2[2];
+                  double dot_k1k2_l1l2 = rk1k2[0] * rl1l2[0] + rk1k2[1] * rl1l2[1] + rk1k2[2] * rl1l2[2];
+                  double l1l2sq = rl1l2[0] * rl1l2[0] + rl1l2[1] * rl1l2[1] + rl1l2[2] * rl1l2[2];
+                  double dcl1l2 = rlijsq * l1l2sq - dot_ij_l1l2 * dot_ij_l1l2;
+                  double abs_dc = sqrt(dck1k2 * dcl1l2);
+                  double costijkl = (dot_ij_k1k2 * dot_ij_l1l2 - rlijsq * dot_k1k2_l1l2) / abs_dc;
+                  double bdhij = 1 - costijkl * costijkl;
+                  bdh = bdh + bdhij * fcik1 * fcik2 * fcjl1 * fcjl2;
+                  bdhij = bdhij * tij * faij * fcarij / 2;
+                  double dbdhij = -2 * costijkl * tije * fcik1 * fcik2 * fcjl1 * fcjl2 / 2;
+                  double df[3], v[3];
+                  for (int c = 0; c < 3; c++)
+                    df[c] = dbdhij * ((dot_ij_l1l2 / abs_dc + costijkl * dot_ij_k1k2 / dck1k2) * rk1k2[c] +
+                                      (dot_ij_k1k2 / abs_dc + costijkl * dot_ij_l1l2 / dcl1l2) * rl1l2[c] -
+                                      (2 * dot_k1k2_l1l2 / abs_dc + costijkl * (k1k2sq / dck1k2 + l1l2sq / dcl1l2)) * rij[c]);
+                  for (int c = 0; c < 3; c++) { fi[c] += df[c]; fj[c] -= df[c]; }
+                  outer_add(wij, 1.0, rij, df);
+                  for (int c = 0; c < 3; c++)
+                    df[c] = dbdhij * (-(1.0 / dck1k2 * costijkl * rk1k2[c] + 1.0 / abs_dc * rl1l2[c]) * rlijsq +
+                                      (dot_ij_l1l2 / abs_dc + costijkl * dot_ij_k1k2 / dck1k2) * rij[c]);
+                  for (int c = 0; c < 3; c++) { f[3 * k1 + c] += df[c]; f[3 * k2 + c] += -df[c]; }
+                  outer_add(wij, 1.0, rk1k2, df);
+                  for (int c = 0; c < 3; c++)
+                    df[c] = dbdhij * (-(1.0 / dcl1l2 * costijkl * rl1l2[c] + 1.0 / abs_dc * rk1k2[c]) * rlijsq +
+                                      (dot_ij_k1k2 / abs_dc + costijkl * dot_ij_l1l2 / dcl1l2) * rij[c]);
+                  for (int c = 0; c < 3; c++) { f[3 * l1 + c] += df[c]; f[3 * l2 + c] += -df[c]; }
+                  outer_add(wij, 1.0, rl1l2, df);
+                  for (int c = 0; c < 3; c++) df[c] = bdhij * dfcik1r * fcik2 * fcjl1 * fcjl2 * rnik1[c];
+                  for (int c = 0; c < 3; c++) { fi[c] += df[c]; f[3 * k1 + c] += -df[c]; v[c] = rlik1 * rnik1[c]; }
+                  outer_add(wij, 1.0, v, df);
+                  for (int c = 0; c < 3; c++) df[c] = bdhij * dfcik2r * fcik1 * fcjl1 * fcjl2 * rnik2[c];
+                  for (int c = 0; c < 3; c++) { fi[c] += df[c]; f[3 * k2 + c] += -df[c]; v[c] = rlik2 * rnik2[c]; }
+                  outer_add(wij, 1.0, v, df);
+                  for (int c = 0; c < 3; c++) df[c] = bdhij * dfcjl1r * fcjl2 * fcik1 * fcik2 * rnjl1[c];
+                  for (int c = 0; c < 3; c++) { fj[c] += df[c]; f[3 * l1 + c] += -df[c]; v[c] = rljl1 * rnjl1[c]; }
+                  outer_add(wij, 1.0, v, df);
+                  for (int c = 0; c < 3; c++) df[c] = bdhij * dfcjl2r * fcjl1 * fcik1 * fcik2 * rnjl2[c];
+                  for (int c = 0; c < 3; c++) { fj[c] += df[c]; f[3 * l2 + c] += -df[c]; v[c] = rljl2 * rnjl2[c]; }
+                  outer_add(wij, 1.0, v, df);
+                  /* screening neighbours of the four bonds (:2322-2354) */
+                  double dffac = bdhij * fcik2 * fcjl1 * fcjl2;
+                  for (long q = sneb_seed[ik1]; q <= sneb_last[ik1]; q++) sfacbo[q] += dffac;
+                  dffac = bdhij * fcik1 * fcjl1 * fcjl2;
+                  for (long q = sneb_seed[ik2]; q <= sneb_last[ik2]; q++) sfacbo[q] += dffac;
+                  dffac = bdhij * fcjl2 * fcik1 * fcik2;
+                  for (long q = sneb_seed[jl1]; q <= sneb_last[jl1]; q++) sfacbo[q] += dffac;
+                  dffac = bdhij * fcjl1 * fcik1 * fcik2;
+                  for (long q = sneb_seed[jl2]; q <= sneb_last[jl2]; q++) sfacbo[q] += dffac;
+                }
+              }
+            }
+          }
+        }
+      } else if (par->with_dihedral && ijpot == C_C) {
         /* :1950-2087 */
         orc_table3d_eval(&par->Tcc, nti, ntj, nconj, &tij, &dtdni, &dtdnj, &dtdncn);
         double tije = tij * faij * fcarij;

@@ -24,6 +24,9 @@ struct Mat3 { double m[9]; };
 #define ATX_SHIFT_ZERO (ATX_SHIFT_BIAS | (ATX_SHIFT_BIAS << 8) | (ATX_SHIFT_BIAS << 16))
 #define ATX_SHIFT_MASK 0xFFFFFF
 #define ATX_NONZERO_SHIFT(p) (((p) & ATX_SHIFT_MASK) != ATX_SHIFT_ZERO)
+static inline int atx_pack_shift(int sx, int sy, int sz) {
+  return (sx + ATX_SHIFT_BIAS) | ((sy + ATX_SHIFT_BIAS) << 8) | ((sz + ATX_SHIFT_BIAS) << 16);
+}
 static inline void atx_unpack_shift(int p, int &sx, int &sy, int &sz) {
   sx = (p & 255) - ATX_SHIFT_BIAS;
   sy = ((p >> 8) & 255) - ATX_SHIFT_BIAS;

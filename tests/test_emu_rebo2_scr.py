@@ -238,6 +238,35 @@ def test_screening_table_overflow_is_flagged(emu, aC_small):
     assert out['flag'] & 2
 
 
+def test_alt_dihedral(emu, aC_small):
+    """the dihedral term of the screened build (ALT_DIHEDRAL, bop_kernel_rebo2.f90:2089-2371): energy, forces,
+    virial, per-atom and per-bond outputs incl. the screening-force factors it feeds into loop 3"""
+    out, ref = check(emu, aC_small, with_dihedral=True)
+    _, ref0 = run_emu(emu, aC_small)
+    assert abs(ref['epot'] - ref0['epot']) > 0.1          # the term is active
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.7, (2, 2, 2))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=2)
+    check(emu, a, with_dihedral=True)
+    for a0, amp, seed in ((3.566, 0.15, 9), (3.3, 0.2, 3)):
+        a = S.diamond('C', a0, (2, 2, 2))
+        a.rattle(amp, seed=seed)
+        check(emu, a, with_dihedral=True)
+    a = S.diamond('C', 3.566, (1, 1, 1))                  # bond partners are periodic images of each other
+    a.rattle(0.1, seed=5)
+    check(emu, a, with_dihedral=True)
+    # cell-sorted (permuted) atom order
+    nat = len(aC_small)
+    perm = np.random.RandomState(3).permutation(nat)
+    b = S.Atoms([aC_small.symbols[i] for i in perm], aC_small.positions[perm], aC_small.cell, True)
+    out, _ = run_emu(emu, b, order=perm, with_dihedral=True)
+    close(out['epot'], ref['epot'], 'epot')
+    close(out['f'], ref['f'][perm], 'f')
+    close(out['wpot'], ref['wpot'], 'wpot')
+
+
 # ---- unscreened Rebo2: the same per-atom source that k_rebo2_bonds / k_rebo2_force wrap ------------
 
 def test_plain_rebo2_amorphous_carbon_and_dihedral(emu, aC_small):

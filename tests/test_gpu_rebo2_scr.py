@@ -97,6 +97,23 @@ def test_other_screening_parameters(aC_small):
     _check(g, o)
 
 
-def test_dihedral_is_refused():
-    with pytest.raises(RuntimeError):
-        native.Rebo2Scr(dihedral=True)
+def test_alt_dihedral(aC_small):
+    """with_dihedral switches on the dihedral term of the screened build (ALT_DIHEDRAL,
+    bop_kernel_rebo2.f90:2089-2371); the same per-atom source runs against the oracle on the CPU in
+    tests/test_emu_rebo2_scr.py::test_alt_dihedral, the oracle's term is checked by finite differences in
+    tests/test_oracle_kat.py"""
+    g, o = _both(aC_small, per_bond=True, with_dihedral=True)
+    _check(g, o, per_bond=True)
+    g0, _ = _both(aC_small)
+    assert abs(g[0] - g0[0]) > 0.1
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.7, (3, 3, 3))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=2)
+    g, o = _both(a, with_dihedral=True)
+    _check(g, o)
+    a = S.diamond('C', 3.566, (1, 1, 1))
+    a.rattle(0.1, seed=5)
+    g, o = _both(a, with_dihedral=True)
+    _check(g, o)

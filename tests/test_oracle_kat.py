@@ -964,3 +964,27 @@ def test_cutoff_functions_fruit(kind):
         v, d = oracle.cutoff_eval(kind, lo, hi, x)
         v2, d2 = oracle.cutoff_eval(kind, lo, hi, x + dr)
         assert abs((v2 - v) / dr - 0.5 * (d + d2)) < tol
+
+
+def test_rebo2_scr_alt_dihedral_fd(aC_small):
+    """the dihedral term of the screened build (ALT_DIHEDRAL, bop_kernel_rebo2.f90:2089-2371): the reference's
+    tests never switch it on, so the restatement is pinned by finite differences of its own energy (forces
+    and virial) and by momentum conservation"""
+    rb = oracle.Rebo2Scr(with_dihedral=True)
+    rb0 = oracle.Rebo2Scr()
+
+    def calc(a, **kw):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, rb.cutoff(a.symbols), 1000)
+        return rb.energy_and_forces(a.positions, a.cell, nl, rb.ktyp(a.symbols), **kw)
+    o = calc(aC_small)
+    nl = oracle.neighbor_list(aC_small.positions, aC_small.cell, aC_small.pbc, rb0.cutoff(aC_small.symbols), 1000)
+    o0 = rb0.energy_and_forces(aC_small.positions, aC_small.cell, nl, rb0.ktyp(aC_small.symbols))
+    assert abs(o['epot'] - o0['epot']) > 0.1
+    assert np.abs(o['f'].sum(axis=0)).max() < 1e-9
+    check_fd(calc, aC_small, nat_check=4)
+    rng = np.random.RandomState(1)
+    a = S.diamond('C', 3.7, (2, 2, 2))
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=2)
+    check_fd(calc, a, nat_check=3)

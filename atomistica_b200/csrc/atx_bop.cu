@@ -297,7 +297,7 @@ __global__ void k_bop_count_bonds(int nat, Mat3 A, BopDev P, const double4 *__re
 }
 
 // shared-memory bond table, field-major so that consecutive threads hit consecutive banks
-template <int NB>
+template <int NB, bool LEAN = false>
 struct BondSmem {
   double rnx[NB][BOP_BLOCK], rny[NB][BOP_BLOCK], rnz[NB][BOP_BLOCK];
   double rl[NB][BOP_BLOCK], ri[NB][BOP_BLOCK], fc[NB][BOP_BLOCK], dfc[NB][BOP_BLOCK];
@@ -307,12 +307,24 @@ struct BondSmem {
   int typ[NB][BOP_BLOCK];
   double red[ATX_NSUM * (BOP_BLOCK / 32)];
 };
+// MD steps whose energy nobody reads (no mask, no per-atom / per-bond outputs, no virial): no per-slot
+// energy, pair type and list slot in one word -- 108 instead of 120 bytes per bond and thread, which is
+// what lets an eighth block of the depth-4 kernel fit on an SM
+template <int NB>
+struct BondSmem<NB, true> {
+  double rnx[NB][BOP_BLOCK], rny[NB][BOP_BLOCK], rnz[NB][BOP_BLOCK];
+  double rl[NB][BOP_BLOCK], ri[NB][BOP_BLOCK], fc[NB][BOP_BLOCK], dfc[NB][BOP_BLOCK];
+  double kx[NB][BOP_BLOCK], ky[NB][BOP_BLOCK], kz[NB][BOP_BLOCK];
+  double gx[NB][BOP_BLOCK], gy[NB][BOP_BLOCK], gz[NB][BOP_BLOCK];
+  int st[NB][BOP_BLOCK];   // pair type | list slot << 4
+  double red[ATX_NSUM * (BOP_BLOCK / 32)];
+};
 
 // One centre atom: bond table in shared memory, then all bonds ij with their k-sums.  Returns false
 // (having written nothing but zeroed G slots) when the atom has more than NB bonds.
-template <int KIND, int NB, bool VIRIAL>
+template <int KIND, int NB, bool VIRIAL, bool LEAN = false>
 __device__ __forceinline__ bool bop_center_atom(
-    BondSmem<NB> &S, const int t, const int s, const Mat3 &A, const BopDev &P,
+    BondSmem<NB, LEAN> &S, const int t, const int s, const Mat3 &A, const BopDev &P,
     const double4 *__restrict__ pos4, const long long *__restrict__ seed, const int2 *__restrict__ list,
     const int *__restrict__ mask, double4 *__restrict__ G, double *__restrict__ f,
     double *__restrict__ pe_own, double *__restrict__ wpa, double *__restrict__ epb,
@@ -362,9 +374,14 @@ __device__ __forceinline__ bool bop_center_atom(
             const double ri = 1.0 / rl;
             S.rnx[nb][t] = dx * ri; S.rny[nb][t] = dy * ri; S.rnz[nb][t] = dz * ri;
             S.rl[nb][t] = rl; S.ri[nb][t] = ri; S.fc[nb][t] = fc; S.dfc[nb][t] = dfc;
-            S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0; S.ge[nb][t] = 0.0;
-            S.slot[nb][t] = (int)(a - b0);
-            S.typ[nb][t] = ij | (en.x << 4);
+            S.gx[nb][t] = 0.0; S.gy[nb][t] = 0.0; S.gz[nb][t] = 0.0;
+            if constexpr (LEAN) {
+              S.st[nb][t] = ij | ((int)(a - b0) << 4);
+            } else {
+              S.ge[nb][t] = 0.0;
+              S.slot[nb][t] = (int)(a - b0);
+              S.typ[nb][t] = ij | (en.x << 4);
+            }
             nb++;
             bond = true;
           }
@@ -380,13 +397,17 @@ __device__ __forceinline__ bool bop_center_atom(
   double fix = 0.0, fiy = 0.0, fiz = 0.0, pei = 0.0;
   const int mi = mask ? mask[s] : 1;
   for (int ij = 0; ij < nb; ij++) {
-    const int tij = S.typ[ij][t] & 15;
-    const int j = S.typ[ij][t] >> 4;
-    int maskfac = 2;
-    if (mask) {
-      int mj = mask[j];
-      if (mi == 0 && mj == 0) maskfac = 0;
-      else if (mi == 0 || mj == 0) maskfac = 1;
+    int tij, j = 0, maskfac = 2;
+    if constexpr (LEAN) {
+      tij = S.st[ij][t] & 15;
+    } else {
+      tij = S.typ[ij][t] & 15;
+      j = S.typ[ij][t] >> 4;
+      if (mask) {
+        int mj = mask[j];
+        if (mi == 0 && mj == 0) maskfac = 0;
+        else if (mi == 0 || mj == 0) maskfac = 1;
+      }
     }
     const double rlij = S.rl[ij][t];
     if (!(maskfac > 0 && rlij < P.r2[tij])) continue;
@@ -410,7 +431,8 @@ __device__ __forceinline__ bool bop_center_atom(
 
     for (int ik = 0; ik < nb; ik++) {
       if (ik == ij) continue;
-      const int tik = S.typ[ik][t] & 15;
+      int tik;
+      if constexpr (LEAN) tik = S.st[ik][t] & 15; else tik = S.typ[ik][t] & 15;
       const double rlik = S.rl[ik][t];
       if (!(rlik < P.r2[tik])) {
         S.kx[ik][t] = 0.0; S.ky[ik][t] = 0.0; S.kz[ik][t] = 0.0;
@@ -468,7 +490,7 @@ __device__ __forceinline__ bool bop_center_atom(
     bop_bo<KIND>(P, eli - 1, tij, zij, fcarij, VAij, bij, dfb);
     const double e_bond = 0.5 * fcarij * (VRij + bij * VAij);
     pei += e_bond;
-    S.ge[ij][t] += e_bond;
+    if constexpr (!LEAN) S.ge[ij][t] += e_bond;
     const double dffac = 0.5 * (dVRij * fcarij + bij * dVAij * fcarij + VRij * dfcarijr + bij * VAij * dfcarijr);
     const double dfx = dffac * nx, dfy = dffac * ny, dfz = dffac * nz;
     fix += dfx - dfb * dix; fiy += dfy - dfb * diy; fiz += dfz - dfb * diz;
@@ -478,7 +500,8 @@ __device__ __forceinline__ bool bop_center_atom(
       S.gx[ik][t] -= dfb * S.kx[ik][t]; S.gy[ik][t] -= dfb * S.ky[ik][t]; S.gz[ik][t] -= dfb * S.kz[ik][t];
     }
     if (own) acc[0] += e_bond;
-    const long long a = b0 + S.slot[ij][t];
+    long long a;
+    if constexpr (LEAN) a = b0 + (S.st[ij][t] >> 4); else a = b0 + S.slot[ij][t];
     if (epb) epb[a] = e_bond;
     if (fpb) { fpb[3 * a] = dfx; fpb[3 * a + 1] = dfy; fpb[3 * a + 2] = dfz; }
     if (VIRIAL) {
@@ -506,15 +529,17 @@ __device__ __forceinline__ bool bop_center_atom(
   }
   f[3 * s] = fix; f[3 * s + 1] = fiy; f[3 * s + 2] = fiz;
   pe_own[s] = pei;
-  for (int k = 0; k < nb; k++)
-    G[b0 + S.slot[k][t]] = make_double4(S.gx[k][t], S.gy[k][t], S.gz[k][t], S.ge[k][t]);
+  for (int k = 0; k < nb; k++) {
+    if constexpr (LEAN) G[b0 + (S.st[k][t] >> 4)] = make_double4(S.gx[k][t], S.gy[k][t], S.gz[k][t], 0.0);
+    else G[b0 + S.slot[k][t]] = make_double4(S.gx[k][t], S.gy[k][t], S.gz[k][t], S.ge[k][t]);
+  }
   return true;
 }
 
 // Main pass: one thread per atom with an NB-deep bond table; atoms with more bonds are appended to
 // `queue` and handled by k_bop_center_queued with the deepest table, so NB can be sized for the
 // typical atom instead of the worst one (shared memory per thread = 120 B x NB sets the occupancy).
-template <int KIND, int NB, int MINB, bool VIRIAL>
+template <int KIND, int NB, int MINB, bool VIRIAL, bool LEAN = false>
 __global__ void __launch_bounds__(BOP_BLOCK, MINB)
 k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
              const long long *__restrict__ seed, const int2 *__restrict__ list,
@@ -525,7 +550,7 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
              const unsigned char *__restrict__ role, const int *__restrict__ stop, int boff) {
   if (stop && *stop) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  BondSmem<NB> &S = *reinterpret_cast<BondSmem<NB> *>(smem_raw);
+  BondSmem<NB, LEAN> &S = *reinterpret_cast<BondSmem<NB, LEAN> *>(smem_raw);
   const int t = threadIdx.x;
   const int blk = blockIdx.x + boff;     // the launch covers the blocks [boff, boff + gridDim.x)
   const int s = blk * BOP_BLOCK + t;
@@ -533,8 +558,8 @@ k_bop_center(int nat, Mat3 A, BopDev P, const double4 *__restrict__ pos4,
 #pragma unroll
   for (int k = 0; k < ATX_NSUM; k++) acc[k] = 0.0;
   if (s < nat && (!role || role[s] >= 1)) {
-    if (!bop_center_atom<KIND, NB, VIRIAL>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb, wpb, acc,
-                                           !role || role[s] >= 2))
+    if (!bop_center_atom<KIND, NB, VIRIAL, LEAN>(S, t, s, A, P, pos4, seed, list, mask, G, f, pe_own, wpa, epb, fpb,
+                                                 wpb, acc, !role || role[s] >= 2))
       queue[atomicAdd(qcount, 1)] = s;
   }
   atx_block_sum<ATX_NSUM, BOP_BLOCK>(acc, S.red);
@@ -1326,19 +1351,22 @@ extern "C" int atx_bop_bind_to(atx_bop *pot, atx_particles *p, atx_neighbors *nl
   return 0;
 }
 
-template <int KIND, int NB, int MINB, bool VIRIAL>
+template <int KIND, int NB, int MINB, bool VIRIAL, bool LEAN = false>
 static int launch_center_v(atx_bop *pot, atx_particles *p, atx_neighbors *nl, const int *mask,
                          const PotOut &o, double *pe_own, double *epb, double *fpb, double *wpb,
                          int nblocks, int pstride, int b0 = 0) {
   if (nblocks <= 0) return 0;
-  size_t smem = sizeof(BondSmem<NB>);
+  size_t smem = sizeof(BondSmem<NB, LEAN>);
   static int attr_dev = -1;   // the attribute belongs to the device: set it again when the device changes
   if (attr_dev != pot->ctx->device) {
-    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB, VIRIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB, VIRIAL, LEAN>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (LEAN)   // eight blocks of 27.8 KB need (nearly) the whole shared-memory carve-out
+      ATX_CUDA(cudaFuncSetAttribute(k_bop_center<KIND, NB, MINB, VIRIAL, LEAN>,
+                                    cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_dev = pot->ctx->device;
   }
-  k_bop_center<KIND, NB, MINB, VIRIAL><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
+  k_bop_center<KIND, NB, MINB, VIRIAL, LEAN><<<nblocks, BOP_BLOCK, smem, pot->ctx->stream>>>(
       nl->nat, p->Abox, pot->dev, nl->pos4.ptr, nl->seed.ptr, nl->list.ptr, mask, pot->G.ptr, o.f,
       pe_own, o.wpa, epb, fpb, wpb, pot->sc.partials.ptr, pstride, pot->queue.ptr, pot->flag.ptr + 1,
       o.role, o.stop, b0);
@@ -1354,6 +1382,12 @@ static int launch_center(atx_bop *pot, atx_particles *p, atx_neighbors *nl, cons
                          int nblocks, int pstride, int b0 = 0) {
   if (o.want_virial || o.wpa || wpb)
     return launch_center_v<KIND, NB, MINB, true>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride, b0);
+  if constexpr (NB == 4) {
+    // an MD step whose energy nobody reads: the lean table, eight blocks per SM
+    static const bool lean_env = !(getenv("ATX_BOP_LEAN") && atoi(getenv("ATX_BOP_LEAN")) == 0);
+    if (lean_env && !mask && !epb && !fpb && !o.epa && !o.want_sums)
+      return launch_center_v<KIND, 4, 8, false, true>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride, b0);
+  }
   return launch_center_v<KIND, NB, MINB, false>(pot, p, nl, mask, o, pe_own, epb, fpb, wpb, nblocks, pstride, b0);
 }
 

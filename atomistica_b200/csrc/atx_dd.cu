@@ -710,7 +710,7 @@ static int dd_reserve_local(atx_ddmd *md, size_t n) {
   return 0;
 }
 
-static int dd_compute(atx_ddmd *md, bool guarded, int phase = 0) {
+static int dd_compute(atx_ddmd *md, bool guarded, int phase = 0, bool need_energy = true) {
   PotOut o;
   o.phase = phase;
   o.split_lo = md->split_lo;
@@ -719,7 +719,7 @@ static int dd_compute(atx_ddmd *md, bool guarded, int phase = 0) {
   ATX_PASS(md->tmpd.reserve(3 * (size_t)nloc + 3));
   ATX_PASS(md->epa.reserve((size_t)nloc + 1));
   o.f = md->tmpd.ptr;  // sorted order
-  o.epa = md->epa.ptr;
+  o.epa = need_energy ? md->epa.ptr : nullptr;   // per-atom energies: only the kick that ends a run sums them
   o.sums = md->sums.ptr;
   o.stop = guarded ? &md->ctrl.ptr->stop : nullptr;
   o.want_virial = false;
@@ -1283,7 +1283,7 @@ extern "C" int atx_dd_md_destroy(atx_ddmd *md) {
 }
 
 // scale: 0 = separate drift and kick kernels; 0.5 / 1 = leapfrog form (first / later step of a run)
-static int dd_enqueue_step(atx_ddmd *md, double scale) {
+static int dd_enqueue_step(atx_ddmd *md, double scale, bool need_energy = true) {
   ProfScope ps_step(md->ctx, "dd_step");
   atx_dd *dd = md->dd;
   cudaStream_t st = md->ctx->stream;
@@ -1320,7 +1320,7 @@ static int dd_enqueue_step(atx_ddmd *md, double scale) {
           md->d_peer_sig.ptr, dd->rank, dd->nranks, md->ctrl.ptr);
       ATX_LAUNCHED();
       // interior centres do not depend on this step's ghost positions: they run while the halo travels
-      if (md->split) ATX_PASS(dd_compute(md, true, 1));
+      if (md->split) ATX_PASS(dd_compute(md, true, 1, need_energy));
       k_dd_wait<<<1, 32, 0, st>>>((const unsigned long long *)md->mbox, dd->nranks, md->ctrl.ptr, scale > 0.0 ? 1 : 0);
       ATX_LAUNCHED();
     }
@@ -1330,7 +1330,7 @@ static int dd_enqueue_step(atx_ddmd *md, double scale) {
                                                                md->nl->inv.ptr, md->nl->pos4.ptr, md->ctrl.ptr);
       ATX_LAUNCHED();
     }
-    ATX_PASS(dd_compute(md, true, md->split ? 2 : 0));
+    ATX_PASS(dd_compute(md, true, md->split ? 2 : 0, need_energy));
     if (scale == 0.0) ATX_PASS(dd_kick(md));
     return 0;
   }
@@ -1391,7 +1391,8 @@ extern "C" int atx_dd_md_run(atx_ddmd *md, int nsteps, double *epot, double *eki
   while (remaining > 0) {
     int batch = remaining < md->batch ? remaining : md->batch;
     for (int b = 0; b < batch; b++) {
-      ATX_PASS(dd_enqueue_step(md, fused ? (first ? 0.5 : 1.0) : 0.0));
+      // leapfrog form: only the evaluation that can be the last one of the run needs per-atom energies
+      ATX_PASS(dd_enqueue_step(md, fused ? (first ? 0.5 : 1.0) : 0.0, !fused || (b == batch - 1 && remaining == batch)));
       first = false;
     }
     ATX_CUDA(cudaMemcpyAsync(md->hctrl.ptr, md->ctrl.ptr, sizeof(DdCtrl), cudaMemcpyDeviceToHost, st));

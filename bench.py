@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-A0, NCELL, TEMP, DT, SKIN = 3.615, 40, 300.0, 1.0, 0.5
+A0, NCELL, TEMP, DT, SKIN = 3.615, 40, 300.0, 1.0, float(os.environ.get('ATX_BENCH_SKIN', '0.5'))
 MASS_CU = 63.546
 MASS_SI = 28.0855
 C4_CELLS = 128
@@ -486,6 +486,16 @@ def block_c2(args, dist, L, ctx):
     r = a2.positions
     v = md.maxwell_boltzmann(m, TEMP, seed=12345)
     f = calc.get_forces(a2)          # initialises particles / neighbour list (untimed)
+    # priming, as for the device-resident run: untimed calls until the list has been rebuilt once inside the
+    # Verlet shell (the first rebuild allocates the fixed-width rows of the single-pass build); the timed
+    # calls then see rebuilds at their natural rate
+    e2e_primed = 0
+    while calc.nl.counters()[0] < 2 and e2e_primed < 120:
+        v += 0.5 * f / MASS_CU * md.ACCEL_CONV * DT
+        r += v * DT
+        f = calc.get_forces(a2)
+        v += 0.5 * f / MASS_CU * md.ACCEL_CONV * DT
+        e2e_primed += 1
     e2e_steps = max(3, min(steps, 20))
     t_api = 0.0
     for k in range(3 + e2e_steps):
@@ -548,7 +558,8 @@ def block_c2(args, dist, L, ctx):
         ms_per_step=dev_ms / steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
         data='synthetic', config=config_dict(world),
         e2e=dict(value=e2e_value, unit='atom-steps/s', h2d_bytes_per_step=nat * 24, d2h_bytes_per_step=nat * 24 + 80,
-                 steps=e2e_steps, ms_per_call=1e3 * t_api / e2e_steps, rebuild_every_call=e2e_rebuild,
+                 steps=e2e_steps, ms_per_call=1e3 * t_api / e2e_steps, priming_calls_untimed=e2e_primed,
+                 rebuild_every_call=e2e_rebuild,
                  note='calculator API (get_forces returns an array the caller owns, like ASE): host positions in, host '
                       'forces out every call; the positions buffer of the Atoms object is page-locked where it lies '
                       '(same buffer in consecutive calls) and uploaded from directly; neighbour list kept in a %.2f A '

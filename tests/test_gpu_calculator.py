@@ -92,3 +92,21 @@ def test_positions_buffer_is_used_in_place():
     assert np.abs(f - ref.get_forces(a.copy())).max() < 1e-10
     del calc                                    # unregisters nothing it did not register
     pinned.array[...] = 0.0
+
+
+def test_rebo2_dimer_results_are_reproducible():
+    """the reference's tests/test_io.py: energy, forces and stress of a C2 dimer in vacuum with Rebo2 and
+    Rebo2Scr survive a round trip of the structure (ASE's trajectory file there; a copy of the Atoms here) --
+    i.e. a fresh calculation on the same geometry gives the same numbers to 1e-10"""
+    vac, dist_min = 8.0, 1.2
+    pos = np.array([[0.0, 0.0, 0.0], [dist_min, 0.0, 0.0]]) + vac
+    a = S.Atoms(['C', 'C'], pos, [dist_min + 2 * vac, 2 * vac, 2 * vac], True)
+    for cls in (ab.Rebo2, ab.Rebo2Scr):
+        calc = cls()
+        e, f, st = calc.get_potential_energy(a), calc.get_forces(a).copy(), calc.get_stress(a).copy()
+        b = a.copy()
+        calc2 = cls()
+        assert abs(e - calc2.get_potential_energy(b)) < 1e-10
+        assert np.abs(f - calc2.get_forces(b)).max() < 1e-10
+        assert np.abs(st - calc2.get_stress(b)).max() < 1e-10
+        assert st.shape == (6,) and e < 0.0 and abs(f[0, 0] + f[1, 0]) < 1e-10

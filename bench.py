@@ -667,6 +667,22 @@ def block_c4(args, dist, L, ctx):
                                   flops_per_atom=fpa, source='ncu instruction counts (profiles/flops.json)')
             blk['roofline'] = rf
         else:
+            # per-GPU FP64 figure of rank 0: only its OWNED atoms are counted as work (the inner ghost centres it
+            # evaluates as well -- +8 % at N=8 -- are not), so the fraction is a lower bound
+            fpa = fl.get('k_bop_center_%s_flops_per_atom' % kind)
+            if fpa and bop_ms > 0:
+                import ctypes as C
+                fp64 = C.c_double(0.0)
+                L.check(L.lib().atx_measure_fp64_peak(ctx, C.byref(fp64)))
+                bop_n = steps + (stp['nrebuilds'] - st['nrebuilds'])
+                avg = bop_ms / max(bop_n, 1)
+                tf = fpa * counts[0] / (avg * 1e-3) / 1e12
+                blk['roofline'] = dict(kernel='k_bop_center<%s>' % kind, avg_launch_ms=avg, launches=bop_n, rank=0,
+                                       fp64=dict(achieved=tf, peak=fp64.value, unit='TFLOP/s', frac=tf / fp64.value,
+                                                 flops_per_atom=fpa, atoms_counted=int(counts[0]),
+                                                 source='ncu instruction counts (profiles/flops.json); owned atoms '
+                                                        'of rank 0 only'))
+
             def ref_factory():
                 allp = [c4_slab(a0, n, k, world) for k in range(world)]
                 gpos = np.concatenate([a[0] for a in allp])

@@ -333,8 +333,10 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
     double faij, dfaijr, frij, dfrijr;
     rb_VA(P, ijpot, rlij, faij, dfaijr);
     rb_VR(P, ijpot, rlij, frij, dfrijr);
-    double wij[9], wijb[9], wjib[9];
-    for (int q = 0; q < 9; q++) { wij[q] = 0.0; wijb[q] = 0.0; wjib[q] = 0.0; }
+    // virial of the bond: w = -sum_a (r_a - r_i) (x) F_a; the bond-order parts are added where the final force
+    // on each neighbour is known (as in atx_rebo2_atom.cuh)
+    double wij[9];
+    for (int q = 0; q < 9; q++) wij[q] = 0.0;
     double fjx = 0.0, fjy = 0.0, fjz = 0.0;
     double zij = 0.0, dix = 0, diy = 0, diz = 0, djx = 0, djy = 0, djz = 0, dzdni = 0.0;
     double nconji = 0.0;
@@ -382,8 +384,6 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
       const double ky_ = dzdrik * ky + dzfac * (dcsdik * ky + dcsdjk * ey);
       const double kz_ = dzdrik * kz + dzfac * (dcsdik * kz + dcsdjk * ez);
       dbk[ik][0] = kx_; dbk[ik][1] = ky_; dbk[ik][2] = kz_;
-      rbs_outer(wijb, -1.0, rijx, rijy, rijz, dfx, dfy, dfz);
-      rbs_outer(wijb, -1.0, rlik * kx, rlik * ky, rlik * kz, kx_, ky_, kz_);
     }
 
     double pij = 0.0, dpdnci = 0.0, dpdnhi = 0.0;
@@ -454,8 +454,6 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
         const double ly_ = dzdrjl * ly + dzfac * (dcsdjl * ly + dcsdil * ey);
         const double lz_ = dzdrjl * lz + dzfac * (dcsdjl * lz + dcsdil * ez);
         dbl[jl][0] = lx_; dbl[jl][1] = ly_; dbl[jl][2] = lz_;
-        rbs_outer(wjib, 1.0, rijx, rijy, rijz, dfx, dfy, dfz);
-        rbs_outer(wjib, -1.0, rljl * lx, rljl * ly, rljl * lz, lx_, ly_, lz_);
       }
     }
 
@@ -655,6 +653,7 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
         }
       }
       fkx += -dfbij * dbk[ik][0]; fky += -dfbij * dbk[ik][1]; fkz += -dfbij * dbk[ik][2];
+      rbs_outer(wij, dfbij, vik.w * vik.x, vik.w * vik.y, vik.w * vik.z, dbk[ik][0], dbk[ik][1], dbk[ik][2]);
       rbs_add3(f, k, fkx, fky, fkz);
     }
     // ---- same on the j side (:2472-2517, :2664-2712)
@@ -703,6 +702,7 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
         }
       }
       flx += -dfbji * dbl[jl][0]; fly += -dfbji * dbl[jl][1]; flz += -dfbji * dbl[jl][2];
+      rbs_outer(wij, dfbji, vjl.w * vjl.x, vjl.w * vjl.y, vjl.w * vjl.z, dbl[jl][0], dbl[jl][1], dbl[jl][2]);
       rbs_add3(f, l, flx, fly, flz);
     }
 
@@ -719,7 +719,8 @@ __device__ __forceinline__ void rbs_force_atom(const RbsTab &T, const Mat3 &A, c
     fix += dfx; fiy += dfy; fiz += dfz;
     fjx -= dfx; fjy -= dfy; fjz -= dfz;
     rbs_outer(wij, 1.0, rijx, rijy, rijz, dfx, dfy, dfz);
-    for (int q = 0; q < 9; q++) wij[q] = wij[q] - dfbij * wijb[q] - dfbji * wjib[q];
+    rbs_outer(wij, dfbij, rijx, rijy, rijz, djx, djy, djz);
+    rbs_outer(wij, -dfbji, rijx, rijy, rijz, bix, biy, biz);
     fix += -(dfbij * dix + dfbji * bix); fiy += -(dfbij * diy + dfbji * biy); fiz += -(dfbij * diz + dfbji * biz);
     fjx += -(dfbij * djx + dfbji * bjx); fjy += -(dfbij * djy + dfbji * bjy); fjz += -(dfbij * djz + dfbji * bjz);
 

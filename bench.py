@@ -289,7 +289,7 @@ def run_reference(args):
                cpu_baseline=dict(value=value, unit='atom-steps/s', cores=threads, kind='port', sample=sample),
                e2e=dict(value=value, unit='atom-steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0)
-    print(json.dumps(out))
+    emit(out)
 
 
 def config_dict(ngpu):
@@ -915,11 +915,35 @@ def run_ours(args):
                        'velocity-Verlet around the oracle port with %d OpenMP thread(s) of %d host threads (EAM '
                        'energy/forces + neighbour build, cutoff+%.1f A skin, same rebuild rule: %d rebuild(s) in the '
                        'sample); %s' % (res['nat'], threads, host_threads(), SKIN, res['rebuilds'], CPU_FLAGS))
-        print(json.dumps(out))
+        emit(out)
     dist.close()
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the
+    first communicator): from here on file descriptor 1 goes to stderr, and the JSON line is written to the
+    original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(out):
+    line = json.dumps(out)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + '\n')
+        _REAL_STDOUT.flush()
+    else:
+        print(line, flush=True)
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=1000)

@@ -519,6 +519,16 @@ static int symbol_to_Z(const char *s2) {   // two characters, blank padded (Fort
   return 0;
 }
 
+// Who frees the ptrdict section new_instance hands out?  In the Python flavour nobody but free_instance can
+// (potential_dealloc, src/python/c/potential.c:93-101, only calls free_instance); the LAMMPS pair style cleans
+// `members_` itself before free_instance (pair_atomistica.cpp:137-142, :296-306), so there the instance must
+// leave it alone -- ptrdict_cleanup frees the root (c_ptrdict.c:380-402) and a second call is a double free.
+#ifdef ATX_SEAM2_LAMMPS
+#define S2_CLEANUP_MEMBERS(m) ((void)(m))
+#else
+#define S2_CLEANUP_MEMBERS(m) do { if (m) ptrdict_cleanup(m); } while (0)
+#endif
+
 #define S2_EL ATX_BOP_MAX_EL
 #define S2_PAIRS ATX_BOP_MAX_PAIRS
 
@@ -613,7 +623,7 @@ static void bop_register(S2Bop *b, section_t *cfg, section_t **members, const ch
 static void bop_free(void *self) {
   S2Bop *b = (S2Bop *)self;
   if (b->h) atx_bop_destroy(b->h);
-  if (b->members) ptrdict_cleanup(b->members);
+  S2_CLEANUP_MEMBERS(b->members);
   delete b;
 }
 static void bop_register_data(void *, void *, int *ierror) { if (ierror) *ierror = ERROR_NONE; }
@@ -739,7 +749,7 @@ static void eam_free(void *self) {
   S2Eam *e = (S2Eam *)self;
   if (e->h) atx_eam_destroy(e->h);
   for (auto *s : e->keep) delete s;
-  if (e->members) ptrdict_cleanup(e->members);
+  S2_CLEANUP_MEMBERS(e->members);
   delete e;
 }
 // setfl reader: 3 comment lines; nel names; nF dF nr dr cutoff; per element header + F + rho; then
@@ -877,7 +887,7 @@ static void juslin_new(void **self, section_t *cfg, section_t **members) {
 static void juslin_free(void *self) {
   S2Juslin *b = (S2Juslin *)self;
   if (b->h) atx_bop_destroy(b->h);
-  if (b->members) ptrdict_cleanup(b->members);
+  S2_CLEANUP_MEMBERS(b->members);
   delete b;
 }
 static void juslin_init(void *self, int *ierror) {
@@ -960,7 +970,7 @@ static void funcfl_free(void *self) {
   S2Funcfl *e = (S2Funcfl *)self;
   if (e->h) atx_eam_destroy(e->h);
   for (auto *s : e->keep) delete s;
-  if (e->members) ptrdict_cleanup(e->members);
+  S2_CLEANUP_MEMBERS(e->members);
   delete e;
 }
 // funcfl reader (:172-197): comment; Z mass a0 lattice; nF dF nr dr cutoff; nF F values, nr Z values,
@@ -1057,7 +1067,7 @@ static void rebo2_new(void **self, section_t *cfg, section_t **members) {
 static void rebo2_free(void *self) {
   S2Rebo2 *r = (S2Rebo2 *)self;
   if (r->h) atx_rebo2_destroy(r->h);
-  if (r->members) ptrdict_cleanup(r->members);
+  S2_CLEANUP_MEMBERS(r->members);
   delete r;
 }
 static void rebo2_init(void *self, int *ierror) {
@@ -1144,7 +1154,7 @@ static void pair_new(void **self, section_t *cfg, section_t **members) {
 static void pair_free(void *self) {
   S2Pair *q = (S2Pair *)self;
   if (q->h) atx_pair_destroy(q->h);
-  if (q->members) ptrdict_cleanup(q->members);
+  S2_CLEANUP_MEMBERS(q->members);
   delete q;
 }
 static void pair_init(void *self, int *ierror) {

@@ -31,6 +31,7 @@ void neighbors_dump_cutoffs(void *, void *);
 void get_full_error_string(char *);
 void atomistica_startup(int);
 void ptrdict_read(section_t *, char *);
+void ptrdict_cleanup(section_t *);
 
 // returns 0 or -1 (message in errbuf); out[0] = eng_vdwl, out[1..6] = virial, out[7] = rcghost, out[8] = rc
 int lmp_harness_run(const char *name, const char *param_file, int ntypes, const char *const *type_symbols, int nall,
@@ -103,6 +104,7 @@ int lmp_harness_run(const char *name, const char *param_file, int ntypes, const 
   }
   out[0] = eng_vdwl;
   for (int k = 0; k < 6; k++) out[1 + k] = virial[k];
+  if (members) ptrdict_cleanup(members);   // ~PairAtomistica (:137): the pair style owns the section
   cls->del(potential);
   cls->free_instance(potential);
   neighbors_free(neighbors);

@@ -1,0 +1,1 @@
+#include "lmp_stub.h"

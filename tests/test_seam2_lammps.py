@@ -3,7 +3,12 @@ src/lammps/pair_style/pair_atomistica.cpp links against; tests/lammps/pair_harne
 pair style's call sequence without LAMMPS (class lookup, particles_set_element, set_pointers with
 the address-0 neighbour array and intptr_t seed/last, energy_and_forces into the live force array,
 virial[6] -= ..., Voigt-6 per-atom virial).  A periodic system is unfolded into owned + ghost atoms
-the way LAMMPS hands it over (REQ_FULL | REQ_GHOST) and must reproduce the periodic oracle."""
+the way LAMMPS hands it over (REQ_FULL | REQ_GHOST) and must reproduce the periodic oracle.
+
+Every case runs twice: through that restatement ('harness') and through the reference's UNMODIFIED
+pair_atomistica.cpp ('pairstyle'), compiled from the reference tree against the stand-in LAMMPS headers of
+tests/lammps/stub/ and driven like LAMMPS drives a pair style (settings, coeff, init_style, init_one,
+compute; tests/lammps/pair_driver.cpp)."""
 import ctypes as C
 import os
 import subprocess
@@ -37,6 +42,43 @@ def test_exports_the_symbols_of_the_pair_style(libs):
         assert sym in have, sym
 
 
+def test_reference_pair_style_links_against_the_shim(libs):
+    """the reference's unmodified pair_atomistica.cpp, compiled against stand-in LAMMPS headers, finds every
+    symbol it needs in libatomistica_lammps.so (linked with --no-undefined) and resolves at load time"""
+    ps = s2build.pairstyle_path()
+    if not os.path.exists(ps):
+        pytest.skip('the reference pair style was not built (needs /root/reference at build time)')
+    out = subprocess.run(['nm', '-D', ps], capture_output=True, text=True).stdout
+    need = {l.split()[-1] for l in out.splitlines() if ' U ' in l}
+    have = {l.split()[-1] for l in subprocess.run(['nm', '-D', '--defined-only', libs[0]], capture_output=True,
+                                                  text=True).stdout.splitlines() if l.strip()}
+    ours = {s for s in need if s.startswith(('particles_', 'neighbors_', 'potential_classes', 'ptrdict_',
+                                             'atomistica_', 'get_full_error_string'))}
+    assert {'particles_set_pointers', 'neighbors_set_pointers', 'potential_classes', 'ptrdict_read',
+            'atomistica_startup'} <= ours
+    assert ours <= have, ours - have
+    defined = subprocess.run(['nm', '-D', '--defined-only', ps], capture_output=True, text=True).stdout
+    assert 'PairAtomistica' in defined and 'get_atomistica_pair_style_git_ident' in defined
+    C.CDLL(ps)
+
+
+def test_pair_style_owns_the_ptrdict_section(libs):
+    """~PairAtomistica (pair_atomistica.cpp:137-142) cleans the ptrdict section itself and then calls del and
+    free_instance: the LAMMPS-flavour instances must not clean it again (found by running the reference's own
+    pair style: glibc aborted on the double free).  Runs in a child process, without a GPU."""
+    ps = s2build.pairstyle_path()
+    if not os.path.exists(ps):
+        pytest.skip('the reference pair style was not built (needs /root/reference at build time)')
+    code = ("import ctypes as C\n"
+            "lib = C.CDLL(%r)\n"
+            "for name in ('Tersoff', 'TersoffScr', 'Kumagai', 'KumagaiScr', 'Brenner', 'BrennerScr', 'TabulatedAlloyEAM',\n"
+            "             'Rebo2', 'Juslin', 'JuslinScr'):\n"
+            "    assert lib.lmp_pair_ownership(name.encode()) == 0, name\n"
+            "print('ok')\n" % ps)
+    r = subprocess.run([os.sys.executable, '-c', code], capture_output=True, text=True, env=dict(os.environ, MALLOC_CHECK_='3'))
+    assert r.returncode == 0 and 'ok' in r.stdout, (r.returncode, r.stderr[-500:])
+
+
 def _unfold(atoms, cutoff, shell):
     L = np.diag(atoms.cell)
     pos, sym, img = [atoms.positions], [list(atoms.symbols)], [np.arange(len(atoms))]
@@ -59,8 +101,19 @@ def _unfold(atoms, cutoff, shell):
     return pos, sym, img, lists
 
 
-def _run(libs, name, atoms, cutoff, shell, types, param_file=None, eatom=True, vatom=True, ncalls=1, f0=None):
-    har = C.CDLL(libs[1])
+DRIVERS = ('harness', 'pairstyle')
+
+
+def _run(libs, name, atoms, cutoff, shell, types, param_file=None, eatom=True, vatom=True, ncalls=1, f0=None,
+         driver='harness'):
+    if driver == 'pairstyle':
+        if not os.path.exists(s2build.pairstyle_path()):
+            pytest.skip('the reference pair style was not built (needs /root/reference at build time)')
+        har = C.CDLL(s2build.pairstyle_path())
+        entry = har.lmp_pair_run
+    else:
+        har = C.CDLL(libs[1])
+        entry = har.lmp_harness_run
     pos, sym, img, lists = _unfold(atoms, cutoff, shell)
     nall, nlocal = len(pos), len(atoms)
     x = np.ascontiguousarray(pos)
@@ -75,9 +128,9 @@ def _run(libs, name, atoms, cutoff, shell, types, param_file=None, eatom=True, v
     syms = (C.c_char_p * len(types))(*[t.encode() for t in types])
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
-    rc = har.lmp_harness_run(name.encode(), (param_file or '').encode(), len(types), syms, nall, nlocal, ip(tag), ip(typ),
-                             dp(x), nall, ip(ilist), ip(numneigh), first, int(eatom), int(vatom), ncalls, dp(f), dp(ea),
-                             dp(va), dp(out), err)
+    rc = entry(name.encode(), (param_file or '').encode(), len(types), syms, nall, nlocal, ip(tag), ip(typ),
+               dp(x), nall, ip(ilist), ip(numneigh), first, int(eatom), int(vatom), ncalls, dp(f), dp(ea),
+               dp(va), dp(out), err)
     if rc != 0:
         raise RuntimeError(err.value.decode(errors='replace'))
     return dict(eng=out[0], virial=out[1:7].copy(), rcghost=out[7], rc=out[8], rc_last=out[9], rc_cross=out[10], f=f, eatom=ea, vatom=va, nlocal=nlocal,
@@ -104,7 +157,8 @@ def _voigt_minus(w):
 
 
 @pytest.mark.gpu
-def test_tersoff_through_the_pair_style_sequence(libs):
+@pytest.mark.parametrize('driver', DRIVERS)
+def test_tersoff_through_the_pair_style_sequence(libs, driver):
     import oracle
     from atomistica_b200 import parameters as P
     a = S.diamond('Si', 5.432, (3, 3, 3))
@@ -114,7 +168,7 @@ def test_tersoff_through_the_pair_style_sequence(libs):
     el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
     o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.TERSOFF, db), a.positions, a.cell, onl, el, per_at=True)
     # the live force array of LAMMPS is not zero on entry: the potential ADDS (tls_reduce, bop_kernel.f90:1615-1620)
-    r = _run(libs, 'Tersoff', a, 3.0 + 0.3, 2, ['Si'], f0=lambda n: np.full((n, 3), 0.25), ncalls=2)
+    r = _run(libs, 'Tersoff', a, 3.0 + 0.3, 2, ['Si'], f0=lambda n: np.full((n, 3), 0.25), ncalls=2, driver=driver)
     n = r['nlocal']
     assert abs(r['rc'] - 3.0) < 1e-12 and abs(r['rcghost'] - 6.0) < 1e-12      # list cutoff, 2 x cutoff ghost shell
     assert abs(r['eng'] - 2 * o['epot']) <= 1e-10 * abs(2 * o['epot'])          # two calls accumulate eng_vdwl
@@ -133,7 +187,8 @@ def test_tersoff_through_the_pair_style_sequence(libs):
 
 
 @pytest.mark.gpu
-def test_two_types_eam_and_rebo2(libs, tmp_path):
+@pytest.mark.parametrize('driver', DRIVERS)
+def test_two_types_eam_and_rebo2(libs, tmp_path, driver):
     import oracle
     from atomistica_b200 import parameters as P
     # Brenner SiC: two LAMMPS types mapped to elements by particles_set_element
@@ -143,7 +198,7 @@ def test_two_types_eam_and_rebo2(libs, tmp_path):
     onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, max(db['r2']), 100)
     el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
     o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.BRENNER, db), a.positions, a.cell, onl, el)
-    r = _run(libs, 'Brenner', a, max(db['r2']) + 0.3, 2, ['Si', 'C'], vatom=False)
+    r = _run(libs, 'Brenner', a, max(db['r2']) + 0.3, 2, ['Si', 'C'], vatom=False, driver=driver)
     # neighbors_get_cutoff(i, j): the cutoff of THAT pair of types (lammps_neighbors.f90:223-251), el = ['C', 'Si']
     assert abs(r['rc'] - db['r2'][2]) < 1e-12 and abs(r['rc_last'] - db['r2'][0]) < 1e-12   # Si-Si, C-C
     assert abs(r['rc_cross'] - db['r2'][1]) < 1e-12                                          # Si-C
@@ -160,7 +215,7 @@ def test_two_types_eam_and_rebo2(libs, tmp_path):
     eam = oracle.EAM(setfl)
     onl = oracle.neighbor_list(cu.positions, cu.cell, cu.pbc, eam.cutoff, 200)
     o = eam.energy_and_forces(cu.positions, cu.cell, onl, eam.eldb(cu.symbols))
-    r = _run(libs, 'TabulatedAlloyEAM', cu, eam.cutoff + 0.3, 2, ['Cu'], param_file=str(par), vatom=False)
+    r = _run(libs, 'TabulatedAlloyEAM', cu, eam.cutoff + 0.3, 2, ['Cu'], param_file=str(par), vatom=False, driver=driver)
     assert abs(r['eng'] - o['epot']) <= 1e-10 * abs(o['epot'])
     assert np.abs(r['f'][:r['nlocal']] - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
     # REBO2: every bond once (the reference decides by atom tag, bop_kernel_rebo2.f90:1329), 5-bond ghost shell
@@ -169,14 +224,15 @@ def test_two_types_eam_and_rebo2(libs, tmp_path):
     rb = oracle.Rebo2()
     onl = oracle.neighbor_list(c.positions, c.cell, c.pbc, 2.0, 50)
     o = rb.energy_and_forces(c.positions, c.cell, onl, rb.ktyp(c.symbols))
-    r = _run(libs, 'Rebo2', c, 2.0, 5, ['C'], vatom=False)
+    r = _run(libs, 'Rebo2', c, 2.0, 5, ['C'], vatom=False, driver=driver)
     assert abs(r['rcghost'] - 10.0) < 1e-12
     assert abs(r['eng'] - o['epot']) <= 1e-10 * abs(o['epot'])
     assert np.abs(r['f'][:r['nlocal']] - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
 
 
 @pytest.mark.gpu
-def test_juslin_through_the_pair_style_sequence(libs):
+@pytest.mark.parametrize('driver', DRIVERS)
+def test_juslin_through_the_pair_style_sequence(libs, driver):
     """Juslin W-C (non-symmetric pair index, rows mirrored by init) on an unfolded B1 crystal"""
     import oracle
     from atomistica_b200 import parameters as P
@@ -189,7 +245,7 @@ def test_juslin_through_the_pair_style_sequence(libs):
     onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
     el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
     o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.JUSLIN, db), a.positions, a.cell, onl, el)
-    r = _run(libs, 'Juslin', a, cutoff + 0.3, 2, ['W', 'C'], vatom=False)
+    r = _run(libs, 'Juslin', a, cutoff + 0.3, 2, ['W', 'C'], vatom=False, driver=driver)
     assert abs(r['eng'] - o['epot']) <= 1e-10 * abs(o['epot'])
     assert np.abs(r['f'][:r['nlocal']] - o['f']).max() <= 1e-10 * max(1.0, np.abs(o['f']).max())
     assert np.abs(r['virial'] - _voigt_minus(o['wpot'])).max() <= 1e-10 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))

@@ -13,7 +13,10 @@
     type(neighbors_t),      intent(inout) :: nl
     integer,      optional, intent(inout) :: ierror
 
-    type(atx_rebo2_params_t), target :: par       ! bind(C) image of atx_rebo2_params (header)
+    type(atx_rebo2_params_t), target :: par       ! bind(C) image of atx_rebo2_params (atx_c_api.f90)
+#ifdef SCREENING
+    type(atx_rebo2_screening_t), target :: scr    ! rebo2_type.f90:59-71, 204-213
+#endif
     integer(c_int) :: ierr
 
     ! scalars of Brenner 2002 Tables 2, 6, 7 and the derived constants of rebo2_db.f90:147-168
@@ -39,7 +42,11 @@
 
     if (c_associated(this%atx_pot)) ierr = atx_rebo2_destroy(this%atx_pot)
 #ifdef SCREENING
-    ierr = atx_rebo2_create_screened(atx_ctx, c_loc(par), c_loc(scr_image(this)), this%atx_pot)
+    scr%cc_ar_r1 = this%cc_ar_r1 ; scr%cc_ar_r2 = this%cc_ar_r2
+    scr%cc_bo_r1 = this%cc_bo_r1 ; scr%cc_bo_r2 = this%cc_bo_r2
+    scr%cc_nc_r1 = this%cc_nc_r1 ; scr%cc_nc_r2 = this%cc_nc_r2
+    scr%Cmin = this%Cmin ; scr%Cmax = this%Cmax
+    ierr = atx_rebo2_create_screened(atx_ctx, c_loc(par), c_loc(scr), this%atx_pot)
 #else
     ierr = atx_rebo2_create(atx_ctx, c_loc(par), this%atx_pot)
 #endif

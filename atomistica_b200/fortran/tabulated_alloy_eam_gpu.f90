@@ -13,11 +13,7 @@
     type(neighbors_t),                   intent(inout) :: nl
     integer,                   optional, intent(inout) :: ierror
 
-    type, bind(C) :: atx_spline_t           ! atx_spline of the header
-       integer(c_int) :: n
-       real(c_double) :: x0, dx
-       type(c_ptr)    :: y, coeff1, coeff2, coeff3, dcoeff1, dcoeff2, dcoeff3
-    endtype
+    ! atx_spline_t: bind(C) image of atx_spline, defined in atx_c_api.f90
     type(atx_spline_t), target :: fF(this%db%nel), frho(this%db%nel), fphi(this%db%nel, this%db%nel)
     integer(c_int) :: ierr
     integer        :: i, j

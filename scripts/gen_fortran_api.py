@@ -5,9 +5,10 @@ include/atomistica_b200.h -- from the header itself, so the Fortran side cannot 
     python scripts/gen_fortran_api.py            # rewrites the .f90
     python scripts/gen_fortran_api.py --check    # exit 1 when the committed file is stale
 
-Opaque handles and parameter structs travel as type(c_ptr) (c_loc of a bind(C) derived type whose
-components follow the struct in the header).  tests/test_abi.py checks that every exported symbol has
-an interface with the right number of dummy arguments.
+Opaque handles and parameter structs travel as type(c_ptr) (c_loc of a bind(C) derived type; the types are
+generated from the typedefs of the header, the ATX_* constants from its #defines).  tests/test_abi.py checks
+that every exported symbol has an interface with the right number of dummy arguments, that the derived types
+equal the ctypes mirrors component by component, and that the hand-written shims use both consistently.
 """
 import os
 import re
@@ -76,15 +77,65 @@ def fortran_arg(decl):
     return name, 'type(c_ptr)', ', value', ''
 
 
+def structs(text):
+    """typedef struct { ... } name;  ->  [(name, [(field, fortran type, dimension or 0)])], and the integer
+    #defines of the header (array bounds, kind selectors)"""
+    text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+    text = re.sub(r'//[^\n]*', ' ', text)
+    defines = []
+    for m in re.finditer(r'#define\s+(ATX_\w+)\s+\(?(-?\d+)\)?\s*$', text, flags=re.M):
+        defines.append((m.group(1), int(m.group(2))))
+    values = dict(defines)
+    out = []
+    for m in re.finditer(r'typedef\s+struct\s*\{(.*?)\}\s*(atx_\w+)\s*;', text, flags=re.S):
+        fields = []
+        for stmt in m.group(1).split(';'):
+            stmt = ' '.join(stmt.replace('const ', '').split())
+            if not stmt:
+                continue
+            base, rest = stmt.split(' ', 1)
+            assert base in ('int', 'double'), stmt
+            for item in rest.split(','):
+                item = item.strip()
+                if item.startswith('*'):
+                    fields.append((item.lstrip('* '), 'type(c_ptr)', 0))
+                    continue
+                a = re.match(r'(\w+)\[(\w+)\]$', item)
+                if a:
+                    dim = a.group(2)
+                    fields.append((a.group(1), SCALAR[base], int(dim) if dim.isdigit() else values[dim]))
+                else:
+                    assert re.match(r'\w+$', item), stmt
+                    fields.append((item, SCALAR[base], 0))
+        out.append((m.group(2), fields))
+    return out, defines
+
+
 def generate():
-    protos = prototypes(open(HEADER).read())
+    header = open(HEADER).read()
+    protos = prototypes(header)
+    types, defines = structs(header)
     lines = ['!! ISO_C_BINDING interface blocks for libatomistica_b200.so -- GENERATED by scripts/gen_fortran_api.py',
              '!! from include/atomistica_b200.h (%d entry points); do not edit.' % len(protos),
              '!! Drop this file into src/support/ of the reference tree; it has no dependencies.  Opaque handles and',
-             '!! parameter structs (atx_bop_params, atx_spline, ...) are type(c_ptr): pass c_loc() of a bind(C) derived',
-             '!! type laid out like the struct in the header.  No Fortran compiler exists in the build image, so this',
-             '!! file is checked structurally (tests/test_abi.py), not compiled.',
-             'module atx_c_api', '  use, intrinsic :: iso_c_binding', '  implicit none', '', '  interface']
+             '!! parameter structs travel as type(c_ptr): pass c_loc() of one of the bind(C) derived types below',
+             '!! (atx_bop_params_t, atx_spline_t, ...: the structs of the header, component by component).  No Fortran',
+             '!! compiler exists in the build image, so this file and the shims that use it are checked structurally',
+             '!! (tests/test_abi.py: against the header, the ctypes mirrors and each other), not compiled.',
+             'module atx_c_api', '  use, intrinsic :: iso_c_binding', '  implicit none', '',
+             '  !! the device context the shims of one process share (created by the first neighbour-list build)',
+             '  type(c_ptr), save :: atx_ctx = C_NULL_PTR', '']
+    for name, value in defines:
+        lines.append('  integer(c_int), parameter :: %s = %d' % (name, value))
+    lines.append('')
+    lines.append('  !! bind(C) images of the parameter structs: same components, same order as in the header')
+    for name, fields in types:
+        lines.append('  type, bind(C) :: %s_t' % name)
+        for fname, ftype, dim in fields:
+            init = ' = C_NULL_PTR' if ftype == 'type(c_ptr)' else ''
+            lines.append('     %s :: %s%s%s' % (ftype, fname, '(%d)' % dim if dim else '', init))
+        lines.append('  endtype %s_t' % name)
+    lines += ['', '  interface']
     for ret, name, args in protos:
         fa = [fortran_arg(a) for a in args]
         names = [a[0] for a in fa]

@@ -175,3 +175,154 @@ def test_fortran_interfaces_cover_the_whole_c_abi():
         assert m, name
         dummies = [a for a in m.group(1).split(',') if a.strip()]
         assert len(dummies) == len(args), name
+
+
+def _fortran_calls(src):
+    """(name, [actual arguments]) of every atx_* function reference in a Fortran source: comments stripped,
+    continuation lines joined, arguments split at top-level commas"""
+    import re
+    lines, cur = [], ''
+    for raw in src.splitlines():
+        line = raw.split('!')[0].rstrip()
+        if not line.strip():
+            continue
+        body = line.strip()
+        if body.startswith('&'):
+            body = body[1:]
+        if body.endswith('&'):
+            cur += body[:-1]
+            continue
+        lines.append(cur + body)
+        cur = ''
+    calls = []
+    for line in lines:
+        for m in re.finditer(r'\b(atx_[a-z0-9_]+)\s*\(', line):
+            depth, args, start = 1, [], m.end()
+            for pos in range(m.end(), len(line)):
+                ch = line[pos]
+                if ch == '(':
+                    depth += 1
+                elif ch == ')':
+                    depth -= 1
+                    if depth == 0:
+                        args.append(line[start:pos].strip())
+                        break
+                elif ch == ',' and depth == 1:
+                    args.append(line[start:pos].strip())
+                    start = pos + 1
+            else:
+                raise AssertionError('unbalanced call: ' + line)
+            calls.append((m.group(1), [a for a in args if a]))
+    return calls
+
+
+def test_fortran_shims_call_the_generated_interfaces_consistently():
+    """No Fortran compiler exists in this image, so the hand-written shims are checked the way a compiler
+    would check them against atx_c_api.f90: every atx_* reference names an existing interface, passes as
+    many arguments as it has dummies, passes c_loc()/C_NULL_PTR/c_* handles only where the dummy is a
+    type(c_ptr) value, and passes nothing but those where it is"""
+    import glob
+    import re
+    api = open(os.path.join(ROOT, 'atomistica_b200', 'fortran', 'atx_c_api.f90')).read()
+    iface = {}
+    for m in re.finditer(r'function (atx_[a-z0-9_]+)\(([^)]*)\)(.*?)endfunction', api, re.S):
+        names = [a.strip() for a in m.group(2).split(',') if a.strip()]
+        kinds = {}
+        for decl in m.group(3).splitlines():
+            d = re.match(r'\s*(.+?)\s*::\s*(\w+)', decl)
+            if d and d.group(2) in names:
+                kinds[d.group(2)] = d.group(1)
+        iface[m.group(1)] = [(n, kinds[n]) for n in names]
+    assert len(iface) == len(L.SYMBOLS)
+    shims = sorted(glob.glob(os.path.join(ROOT, 'atomistica_b200', 'fortran', '*_gpu.f90')))
+    assert len(shims) == 5
+    local = {'atx_pass_error', 'atx_ctx', 'atx_nl', 'atx_p', 'atx_pot'}   # defined by the shims / the module
+    assert re.search(r'type\(c_ptr\), save :: atx_ctx = C_NULL_PTR', api)
+    ncalls = 0
+    for path in shims:
+        for name, args in _fortran_calls(open(path).read()):
+            if name in local:
+                continue
+            assert name in iface, '%s: %s has no interface' % (os.path.basename(path), name)
+            dummies = iface[name]
+            assert len(args) == len(dummies), '%s: %s passes %d arguments, interface has %d' % (
+                os.path.basename(path), name, len(args), len(dummies))
+            for actual, (dummy, kind) in zip(args, dummies):
+                is_ptr_actual = bool(re.match(r'(c_loc\(|C_NULL_PTR|c_[a-z]+\b|atx_ctx\b|[\w%]*atx_(nl|p|pot)\b)', actual))
+                if kind.replace(' ', '') == 'type(c_ptr),value':
+                    assert is_ptr_actual, '%s: %s(%s=%s): a c_ptr value is expected' % (
+                        os.path.basename(path), name, dummy, actual)
+                elif kind.strip() == 'type(c_ptr)':        # handle returned by reference
+                    assert re.search(r'atx_(ctx|nl|p|pot)\b', actual), (name, dummy, actual)
+                else:
+                    assert not actual.startswith(('c_loc(', 'C_NULL_PTR')), '%s: %s(%s=%s): interface takes %s' % (
+                        os.path.basename(path), name, dummy, actual, kind)
+            ncalls += 1
+    assert ncalls >= 20
+
+
+def _fortran_types(api):
+    """{type name: [(component, fortran type, dimension)]} of the bind(C) derived types of atx_c_api.f90"""
+    import re
+    out = {}
+    for m in re.finditer(r'type, bind\(C\) :: (\w+)\n(.*?)endtype', api, re.S):
+        comps = []
+        for line in m.group(2).strip().splitlines():
+            d = re.match(r'\s*(\S+) :: (\w+)(?:\((\d+)\))?', line)
+            comps.append((d.group(2), d.group(1), int(d.group(3) or 0)))
+        out[m.group(1)] = comps
+    return out
+
+
+def test_fortran_derived_types_mirror_the_structs():
+    """the bind(C) derived types generated from the header have the components of the ctypes mirrors (which
+    test_header_is_plain_c_and_struct_layouts_match_ctypes pins to the compiler's layout): same names, same
+    order, same basic type, same array bound"""
+    api = open(os.path.join(ROOT, 'atomistica_b200', 'fortran', 'atx_c_api.f90')).read()
+    types = _fortran_types(api)
+    mirrors = dict(atx_spline_t=L.AtxSpline, atx_bop_params_t=L.AtxBopParams, atx_bop_screening_t=L.AtxBopScreening,
+                   atx_juslin_params_t=L.AtxJuslinParams, atx_juslin_screening_t=L.AtxJuslinScreening,
+                   atx_pair_params_t=L.AtxPairParams, atx_rebo2_params_t=L.AtxRebo2Params,
+                   atx_rebo2_screening_t=L.AtxRebo2Screening)
+    assert set(types) == set(mirrors)
+    for name, cls in mirrors.items():
+        comps = types[name]
+        assert len(comps) == len(cls._fields_), name
+        for (fname, ftype, dim), (cname, ctype) in zip(comps, cls._fields_):
+            assert fname == cname.rstrip('_'), (name, fname, cname)      # ctypes: lambda_ (Python keyword)
+            length = getattr(ctype, '_length_', 0)
+            base = ctype._type_ if length else ctype
+            assert dim == length, (name, fname)
+            want = {C.c_int: 'integer(c_int)', C.c_double: 'real(c_double)'}.get(base, 'type(c_ptr)')
+            assert ftype == want, (name, fname, ftype, want)
+    # Fortran names are case-insensitive: no two components of a type may differ in case only
+    for name, comps in types.items():
+        lowered = [c[0].lower() for c in comps]
+        assert len(set(lowered)) == len(lowered), name
+    # the constants the shims select kinds with
+    for const, value in (('ATX_BOP_TERSOFF', 1), ('ATX_BOP_KUMAGAI', 2), ('ATX_BOP_BRENNER', 3), ('ATX_BOP_MAX_PAIRS', 6)):
+        assert 'parameter :: %s = %d\n' % (const, value) in api
+
+
+def test_fortran_shims_use_existing_types_and_components():
+    """every type(atx_*_t) a shim declares exists in atx_c_api.f90, and every component it assigns or reads
+    through such a variable is a component of that type"""
+    import glob
+    import re
+    api = open(os.path.join(ROOT, 'atomistica_b200', 'fortran', 'atx_c_api.f90')).read()
+    types = _fortran_types(api)
+    nrefs = 0
+    for path in sorted(glob.glob(os.path.join(ROOT, 'atomistica_b200', 'fortran', '*_gpu.f90'))):
+        src = '\n'.join(line.split('!')[0] for line in open(path).read().splitlines())
+        variables = {}
+        for m in re.finditer(r'type\((atx_\w+_t)\)[^:\n]*::\s*([^\n]+)', src):
+            assert m.group(1) in types, '%s: unknown type %s' % (os.path.basename(path), m.group(1))
+            for var in re.findall(r'(\w+)(?:\([^)]*\))?\s*(?:,|$)', m.group(2)):
+                variables[var] = m.group(1)
+        for var, tname in variables.items():
+            comps = {c[0].lower() for c in types[tname]}
+            for ref in re.findall(r'\b%s(?:\([^)%%]*\))?%%(\w+)' % var, src):
+                assert ref.lower() in comps, '%s: %s%%%s is not a component of %s' % (
+                    os.path.basename(path), var, ref, tname)
+                nrefs += 1
+    assert nrefs >= 80

@@ -2,7 +2,8 @@
 !! default_bind_to_func.f90 (BIND_TO_FUNC) when built with -DATX_GPU.
 !! BOP_TYPE gains:  type(c_ptr) :: atx_pot = C_NULL_PTR
 !! Each module (tersoff.f90, kumagai.f90, brenner.f90 and their *_scr.f90 twins) defines, next to BOP_NAME,
-!!     #define ATX_BOP_KIND  ATX_BOP_TERSOFF        (ATX_BOP_KUMAGAI, ATX_BOP_BRENNER)
+!!     #define ATX_BOP_KIND  1        (the preprocessor needs the number: 1 = ATX_BOP_TERSOFF, 2 = ATX_BOP_KUMAGAI,
+!!                                     3 = ATX_BOP_BRENNER of the header)
 !! and BIND_TO_FUNC calls  bop_bind_to_gpu(this, p, nl, ierror)  after its own bookkeeping (:25-146).
 !! Uses atx_c_api.f90 (interfaces, the bind(C) derived types and the ATX_* constants are generated from
 !! include/atomistica_b200.h).

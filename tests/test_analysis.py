@@ -115,3 +115,39 @@ def test_empty_and_isolated_atoms():
     dr = np.array([[1.0, 0, 0], [0, 1.0, 0], [1.0, 0, 0]])
     m = analysis.bond_angles(1, 4, i, j, dr, 2.0)
     assert abs(m[0] - np.pi / 2) < 1e-15 and m[3] == 0.0
+
+
+def _reference_module():
+    """the reference's own extension module (its unmodified src/python/c/analysis.c among the glue, built by
+    atomistica_b200/seam2/build.py where /root/reference exists; the built module travels)"""
+    import os
+    import pytest
+    from atomistica_b200.seam2 import build as s2build
+    if os.path.isdir('/root/reference/src/python/c'):
+        s2build.build()
+    m = s2build.load()
+    if m is None:
+        pytest.skip('the reference-built _atomistica module is not present')
+    return m
+
+
+def test_against_the_reference_c_code(aC_small):
+    """analysis.py (the checker of the device kernels in tests/test_gpu_analysis.py) against the REFERENCE's
+    compiled analysis.c -- these three helpers are plain C on numpy arrays, so the reference itself runs here"""
+    ref = _reference_module()
+    i, j, dr, absdr = _pairs(aC_small, 2.6)
+    dr = np.ascontiguousarray(dr)
+    for nbins, cutoff in ((50, 2.6), (13, 2.0), (200, 2.6)):
+        h, h2 = analysis.pair_distribution(i, absdr, nbins, cutoff)
+        rh, rh2 = ref.pair_distribution(i, np.ascontiguousarray(absdr), nbins, cutoff)
+        np.testing.assert_allclose(h, rh, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(h2, rh2, rtol=1e-10, atol=1e-13)
+    for nbins, cutoff in ((36, 1.85), (90, 2.2)):
+        h, h2 = analysis.angle_distribution(i, j, dr, nbins, cutoff)
+        rh, rh2 = ref.angle_distribution(i, j, dr, nbins, cutoff)
+        np.testing.assert_allclose(h, rh, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(h2, rh2, rtol=1e-10, atol=1e-13)
+    for moment in (1, 2, 3):
+        m = analysis.bond_angles(moment, len(aC_small), i, j, dr, 1.85)
+        rm = ref.bond_angles(moment, len(aC_small), i, j, dr, 1.85)
+        np.testing.assert_allclose(m, rm, rtol=1e-12, atol=1e-14)

@@ -346,6 +346,15 @@ Juslin_JAP_98_123520_WCH__Scr.update(
     r1=list(_J_R1), r2=list(_J_R2), or1=list(_J_R1), or2=list(_J_R2), bor1=list(_J_R1), bor2=list(_J_R2),
     Cmin=list(_J_R1), Cmax=list(_J_R2))
 
+# parameters.py:331-342 of the reference: Fe-C-H with the screening rows of JuslinScr
+_K_R1 = [2.95, 2.30, 2.2974, 0.0, 1.70, 1.30, 0.0, 1.30, 1.10]
+_K_R2 = [3.35, 2.70, 2.6966, 0.0, 2.00, 1.80, 0.0, 1.80, 1.70]
+Kuopanportti_CMS_111_525_FeCH__Scr = copy.deepcopy(Kuopanportti_CMS_111_525_FeCH)
+Kuopanportti_CMS_111_525_FeCH__Scr.update(
+    r1=list(_K_R1), r2=list(_K_R2), or1=list(_K_R1), or2=list(_K_R2), bor1=list(_K_R1), bor2=list(_K_R2),
+    Cmin=[1.0, 1.0, 1.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0], Cmax=[3.0, 3.0, 3.0, 0.0, 3.0, 3.0, 0.0, 3.0, 3.0],
+    m=[1] * 27)
+
 
 def complete_juslin_scr(db):
     """JuslinScr: default database + mirroring, which in the SCREENING build also covers

@@ -785,6 +785,23 @@ def test_juslin_scr_fd_and_mask():
     assert np.abs(o1['f'] + o2['f'] - o0['f']).max() < 1e-6
 
 
+def test_juslin_scr_fe_c_h_parameter_set():
+    # parameters.py:331-342 of the reference (Kuopanportti_CMS_111_525_FeCH__Scr: or = bor = r, Cmin 1, Cmax 3):
+    # equal to the unscreened Fe-C-H set while no bond is inside a switching region, consistent derivatives
+    db = P.Kuopanportti_CMS_111_525_FeCH__Scr
+    a = S.bcc('Fe', 2.87, (3, 3, 3))            # Fe-Fe: both shells (2.49, 2.87 A) below r1 = 2.95 A
+    a.rattle(0.01, seed=7)
+    o1, o2 = juslin_scr_calc(db)(a), juslin_calc(P.Kuopanportti_CMS_111_525_FeCH)(a)
+    assert abs(o1['epot'] - o2['epot']) < 1e-9 * abs(o2['epot'])
+    assert np.abs(o1['f'] - o2['f']).max() < 1e-9
+    for i in (0, 7, 20):                        # substitutional C sits inside the Fe-C switching region
+        a.symbols[i] = 'C'
+    a.symbols[11] = 'H'
+    a.rattle(0.12, seed=8)
+    assert abs(juslin_scr_calc(db)(a)['epot'] - juslin_calc(P.Kuopanportti_CMS_111_525_FeCH)(a)['epot']) > 1e-3
+    check_fd(juslin_scr_calc(db), a, nat_check=4)
+
+
 # ---- Rebo2Scr (screened REBO2) ----------------------------------------------------------------------
 
 @pytest.mark.parametrize('name', MOLS)

@@ -916,6 +916,30 @@ class Rebo2Scr(Rebo2):
         return out
 
 
+BOP_FUNCS = dict(VA=0, VR=1, g=2, bo=3, h=4)
+
+
+def bop_func(params, which, x, ktypj=1, ktypi=1, ktypk=1, ijpot=1, ikpot=1, fcij=1.0, faij=1.0):
+    """one evaluation of VA / VR / g / bo / h of the *_func.f90 files (1-based indices): (value, derivative);
+    for bo: (bij, dfbij)"""
+    v, d = C.c_double(0.0), C.c_double(0.0)
+    lib().orc_bop_func(C.byref(params), C.c_int(BOP_FUNCS[which]), C.c_int(ktypj), C.c_int(ktypi), C.c_int(ktypk),
+                       C.c_int(ijpot), C.c_int(ikpot), C.c_double(x), C.c_double(fcij), C.c_double(faij),
+                       C.byref(v), C.byref(d))
+    return v.value, d.value
+
+
+REBO2_FUNCS = dict(fconj=0, fCin=1, VA=2, VR=3, g=4, bo=5, h=6, Z2pair=7)
+
+
+def rebo2_func(params, which, x=0.0, y=0.0, z=0.0, i1=1, i2=1):
+    """one evaluation of a function of rebo2_func.f90: the three result slots of orc_rebo2_func"""
+    out = (C.c_double * 3)()
+    lib().orc_rebo2_func(C.byref(params), C.c_int(REBO2_FUNCS[which]), C.c_int(i1), C.c_int(i2), C.c_double(x),
+                         C.c_double(y), C.c_double(z), out)
+    return tuple(out)
+
+
 def cutoff_eval(kind, r1, r2, r):
     """kind 'trig_off' or 'exp': (value, derivative) of the cutoff function between r1 and r2"""
     v, d = C.c_double(0.0), C.c_double(0.0)

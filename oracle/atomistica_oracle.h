@@ -138,6 +138,11 @@ int orc_pair_energy_and_forces(int kind, const double *par, int shift, int nat, 
 /* cutoff functions of src/support/cutoff.f90 (0 = trig_off :152-196, 1 = exp_cutoff :232-293) */
 void orc_cutoff_eval(int kind, double r1, double r2, double r, double *val, double *dval);
 
+/* one evaluation of a function of {tersoff,kumagai,brenner,juslin}_func.f90 (test hook; 1-based indices).
+ * which: 0 VA(dr), 1 VR(dr), 2 g(costh), 3 bo(zij; fcij, faij), 4 h(dr) */
+void orc_bop_func(const orc_bop_params_t *p, int which, int ktypj, int ktypi, int ktypk, int ijpot,
+                  int ikpot, double x, double fcij, double faij, double *val, double *dval);
+
 /* ---- REBO2: src/potentials/bop/rebo2/ ---- */
 
 typedef struct {
@@ -187,6 +192,12 @@ int orc_rebo2_scr_energy_and_forces(const orc_rebo2_params_t *par, const orc_reb
                                     const int *dc, double *epot, double *f, double *wpot,
                                     double *epot_per_at, double *epot_per_bond, double *f_per_bond,
                                     double *wpot_per_at, double *wpot_per_bond);
+
+/* one evaluation of a function of rebo2_func.f90 (test hook).  which: 0 fconj(x), 1 fCin(ijpot = i1, x),
+ * 2 VA(i1, x), 3 VR(i1, x), 4 g(ktyp = i1, costh = x, n = y) -> val, d/dcosth, d/dN,
+ * 5 bo(ktypi = i1, zij = x, fcij = y, faij = z), 6 h(ijpot = i1, ikpot = i2, dr = x), 7 Z2pair(i1, i2) */
+void orc_rebo2_func(const orc_rebo2_params_t *p, int which, int i1, int i2, double x, double y, double z,
+                    double *out);
 
 int orc_rebo2_energy_and_forces(const orc_rebo2_params_t *par, int nat, int natloc,
                                 const double *r, const double *Abox, const int *ktyp,

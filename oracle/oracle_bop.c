@@ -996,3 +996,20 @@ void orc_cutoff_eval(int kind, double r1, double r2, double r, double *val, doub
     exp_cutoff_f(&t, r, val, dval);
   }
 }
+
+/* test hook for the per-pair / per-triplet functions of tersoff_func.f90, kumagai_func.f90,
+ * brenner_func.f90 and juslin_func.f90 (tests/test_func_vs_reference.py evaluates the reference's
+ * own source next to it).  which: 0 VA(dr), 1 VR(dr), 2 g(costh), 3 bo(zij; fcij, faij), 4 h(dr).
+ * All indices are 1-based as in the Fortran. */
+void orc_bop_func(const orc_bop_params_t *p, int which, int ktypj, int ktypi, int ktypk, int ijpot,
+                  int ikpot, double x, double fcij, double faij, double *val, double *dval) {
+  brenner_derived_t bd;
+  if (p->kind == ORC_BRENNER || p->kind == ORC_JUSLIN) brenner_derive(p, &bd);
+  switch (which) {
+    case 0: f_VA(p, &bd, ijpot - 1, x, val, dval); break;
+    case 1: f_VR(p, &bd, ijpot - 1, x, val, dval); break;
+    case 2: f_g(p, &bd, ktypi - 1, ikpot - 1, x, val, dval); break;
+    case 3: f_bo(p, &bd, ktypi - 1, ijpot - 1, x, fcij, faij, val, dval); break;
+    default: f_h(p, ktypj, ktypi, ktypk, ikpot - 1, x, val, dval);
+  }
+}

@@ -1229,3 +1229,22 @@ int orc_rebo2_scr_energy_and_forces(const orc_rebo2_params_t *par, const orc_reb
   return rebo2_kernel(par, scr, nat, natloc, r, Abox, ktyp, seed, last, neighbors, dc, epot, f_inout, wpot_inout,
                       epot_per_at, epot_per_bond, f_per_bond, wpot_per_at, wpot_per_bond);
 }
+
+/* test hook for the functions of rebo2_func.f90 (tests/test_func_vs_reference.py evaluates the reference's own
+ * source next to it).  which: 0 fconj(x), 1 fCin(ijpot = i1, x), 2 VA(i1, x), 3 VR(i1, x),
+ * 4 g(ktyp = i1, costh = x, n = y) -> val, d/dcosth, d/dN, 5 bo(ktypi = i1, zij = x, fcij = y, faij = z),
+ * 6 h(ijpot = i1, ikpot = i2, dr = x), 7 Z2pair(i1, i2) -> out[0] */
+void orc_rebo2_func(const orc_rebo2_params_t *p, int which, int i1, int i2, double x, double y, double z,
+                    double *out) {
+  out[0] = out[1] = out[2] = 0.0;
+  switch (which) {
+    case 0: fconj(x, &out[0], &out[1]); break;
+    case 1: fCin(p, i1, x, &out[0], &out[1]); break;
+    case 2: VA(p, i1, x, &out[0], &out[1]); break;
+    case 3: VR(p, i1, x, &out[0], &out[1]); break;
+    case 4: gfun(p, i1, x, y, &out[0], &out[1], &out[2]); break;
+    case 5: bo(p, i1, x, y, z, &out[0], &out[1]); break;
+    case 6: hfun(p, i1, i2, x, &out[0], &out[1]); break;
+    default: out[0] = (double)Z2pair(i1, i2);
+  }
+}

@@ -1,0 +1,470 @@
+"""A translator from the small Fortran subset the reference's *_func.f90 / *_db.f90 files are written in to
+Python, so that tests can EXECUTE the reference's own formulas (no Fortran compiler exists in this image) next to
+the oracle's restatement of them.  Test infrastructure only; reads the sources where they lie under
+/root/reference.
+
+Subset: [elemental|pure] subroutine / function units; scalar and explicit-shape array declarations; assignments
+to scalars, elements, sections and whole arrays; IF blocks and one-line IFs; DO loops (optional stride); CALL of
+other translated units or of Python callables supplied by the test; RAISE_ERROR / INIT_ERROR / PASS_ERROR;
+RETURN; component access through %; array constructors; kind suffixes (a real literal without one is single
+precision, as the compiler reads it); .and./.or./.not.; the intrinsics below.  Arrays are column-major objects
+with arbitrary lower bounds that are read with Fortran's parentheses (FA is callable), so an expression needs no
+distinction between a function reference and an array element.  Anything outside the subset raises
+NotImplementedError at translation time -- nothing is skipped silently."""
+import math
+import re
+import struct
+
+
+class S:
+    """subscript triplet lo:hi (inclusive, None = the bound)"""
+
+    def __init__(self, lo=None, hi=None):
+        self.lo, self.hi = lo, hi
+
+
+class FA:
+    """Fortran array: column-major, per-dimension lower bounds (default 1); a(i, j) reads, a[i, j] = x writes;
+    sections through S objects"""
+
+    def __init__(self, *shape, data=None, lower=None):
+        self.shape = tuple(int(n) for n in shape)
+        self.lower = tuple(lower) if lower is not None else (1,) * len(self.shape)
+        size = 1
+        for n in self.shape:
+            size *= n
+        self.data = list(data) if data is not None else [0.0] * size
+        assert len(self.data) == size, (len(self.data), self.shape)
+
+    def __len__(self):
+        return len(self.data)
+
+    def __iter__(self):
+        return iter(self.data)
+
+    def _select(self, idx):
+        """(flat offsets in column-major order, shape of the section or None for one element)"""
+        if not isinstance(idx, tuple):
+            idx = (idx,)
+        assert len(idx) == len(self.shape), (idx, self.shape)
+        offs, stride, shape = [0], 1, []
+        for i, n, lo in zip(idx, self.shape, self.lower):
+            if isinstance(i, S):
+                a = lo if i.lo is None else i.lo
+                b = lo + n - 1 if i.hi is None else i.hi
+                assert lo <= a and b <= lo + n - 1, (a, b, self.shape, self.lower)
+                r = range(a - lo, b - lo + 1)
+                shape.append(len(r))
+            else:
+                assert lo <= i <= lo + n - 1, (i, self.shape, self.lower)
+                r = range(i - lo, i - lo + 1)
+            offs = [o + k * stride for k in r for o in offs]
+            stride *= n
+        return offs, (shape if any(isinstance(i, S) for i in idx) else None)
+
+    def __call__(self, *idx):
+        offs, shape = self._select(idx)
+        if shape is None:
+            return self.data[offs[0]]
+        return FA(*shape, data=[self.data[o] for o in offs])
+
+    def __getitem__(self, idx):
+        return self(*idx) if isinstance(idx, tuple) else self(idx)
+
+    def __setitem__(self, idx, v):
+        offs, _ = self._select(idx)
+        if isinstance(v, FA):
+            assert len(v.data) == len(offs), (len(v.data), len(offs))
+            for o, x in zip(offs, list(v.data)):
+                self.data[o] = x
+        else:
+            for o in offs:
+                self.data[o] = v
+
+    def assign(self, v):
+        """whole-array assignment: scalar broadcast or element-wise copy"""
+        if isinstance(v, FA):
+            assert len(v.data) == len(self.data)
+            self.data[:] = list(v.data)
+        else:
+            self.data[:] = [v] * len(self.data)
+
+    # the element-wise arithmetic the sources use on sections
+    def _zip(self, o, f):
+        if isinstance(o, FA):
+            assert len(o.data) == len(self.data)
+            return FA(*self.shape, data=[f(a, b) for a, b in zip(self.data, o.data)])
+        return FA(*self.shape, data=[f(a, o) for a in self.data])
+
+    def __add__(self, o): return self._zip(o, lambda a, b: a + b)
+    def __sub__(self, o): return self._zip(o, lambda a, b: a - b)
+    def __mul__(self, o): return self._zip(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._zip(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._zip(o, lambda a, b: a / b)
+
+
+def F1(values):
+    return FA(len(values), data=values)
+
+
+class Obj:
+    """derived-type instance; components are set by the test or by translated code"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _set(obj, name, value):
+    cur = getattr(obj, name, None)
+    if isinstance(cur, FA):
+        cur.assign(value)
+    else:
+        setattr(obj, name, value)
+
+
+def _sp(x):
+    """a real literal without kind suffix is default real: single precision, promoted when used"""
+    return struct.unpack('f', struct.pack('f', x))[0]
+
+
+def _pair_index(i, j, maxval):
+    # macros.inc:123
+    return 1 + min((i - 1) + (j - 1) * maxval, (j - 1) + (i - 1) * maxval) - min((i - 1) * i // 2, (j - 1) * j // 2)
+
+
+_PI = 3.14159265358979323846264338327950288
+INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=math.log, acos=math.acos,
+                  abs=abs, max=max, min=min, real=lambda x, kind=None: float(x), int=int, DP=8,
+                  PAIR_INDEX=_pair_index,
+                  PAIR_INDEX_NS=lambda i, j, maxval: j + (i - 1) * maxval,                      # macros.inc:139
+                  TRIPLET_INDEX_NS=lambda i, j, k, maxval: k + maxval * (j - 1 + maxval * (i - 1)),  # macros.inc:146
+                  PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp,
+                  _ac=lambda v: FA(len(v), data=v))
+
+PY_KEYWORDS = {'lambda': 'lambda_'}
+ERROR_ARGS = ('error', 'ierror')
+
+
+def _strip_comment(line):
+    quote = None
+    for k, ch in enumerate(line):
+        if quote:
+            if ch == quote:
+                quote = None
+        elif ch in '"\'':
+            quote = ch
+        elif ch == '!':
+            return line[:k]
+    return line
+
+
+def preprocess(text, defined=()):
+    """cpp conditionals (only #ifdef / #ifndef / #if defined(A) || defined(B) / #else / #endif), comments,
+    continuation lines -> list of statements"""
+    out, active = [], []
+    for raw in text.splitlines():
+        if raw.startswith('#'):
+            d = raw.split()
+            if d[0] == '#ifdef':
+                active.append(d[1] in defined)
+            elif d[0] == '#ifndef':
+                active.append(d[1] not in defined)
+            elif d[0] == '#if':
+                active.append(any(n in defined for n in re.findall(r'defined\((\w+)\)', raw)))
+            elif d[0] == '#else':
+                active[-1] = not active[-1]
+            elif d[0] == '#endif':
+                active.pop()
+            elif d[0] in ('#include', '#define', '#undef'):
+                pass
+            else:
+                raise NotImplementedError(raw)
+            continue
+        if all(active):
+            out.append(_strip_comment(raw).rstrip())
+    joined, cur = [], ''
+    for line in out:
+        body = line.strip()
+        if not body:
+            continue
+        if body.startswith('&'):
+            body = body[1:].lstrip()
+        if body.endswith('&'):
+            cur += body[:-1] + ' '
+            continue
+        joined.append(cur + body)
+        cur = ''
+    return joined
+
+
+def _matching(s, start):
+    depth = 0
+    for k in range(start, len(s)):
+        if s[k] == '(':
+            depth += 1
+        elif s[k] == ')':
+            depth -= 1
+            if depth == 0:
+                return k
+    raise NotImplementedError('unbalanced: ' + s)
+
+
+def _split_top(s, sep):
+    out, depth, start = [], 0, 0
+    for k, ch in enumerate(s):
+        if ch in '([':
+            depth += 1
+        elif ch in ')]':
+            depth -= 1
+        elif ch == sep and depth == 0:
+            out.append(s[start:k])
+            start = k + 1
+    out.append(s[start:])
+    return out
+
+
+def _sections(e):
+    """subscript triplets inside any parenthesised list -> S(lo, hi)"""
+    out, k = '', 0
+    while k < len(e):
+        if e[k] == '(':
+            close = _matching(e, k)
+            pieces = []
+            for piece in _split_top(e[k + 1:close], ','):
+                tri = _split_top(piece, ':')
+                if len(tri) == 1:
+                    pieces.append(_sections(piece))
+                elif len(tri) == 2:
+                    lo, hi = (_sections(t).strip() or 'None' for t in tri)
+                    pieces.append('S(%s, %s)' % (lo, hi))
+                else:
+                    raise NotImplementedError('stride: ' + e)
+            out += '(' + ','.join(pieces) + ')'
+            k = close + 1
+        else:
+            out += e[k]
+            k += 1
+    return out
+
+
+def expr(e):
+    e = e.replace('(/', '_ac([').replace('/)', '])')
+    # default-real literals first (they carry neither a kind suffix nor a D exponent)
+    e = re.sub(r'(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])', r'_sp(\1)', e)
+    e = re.sub(r'(\d)_DP\b', r'\1', e)
+    e = re.sub(r'(\d+\.?\d*|\.\d+)[dD]([-+]?\d+)', r'\1e\2', e)
+    for a, b in (('.and.', ' and '), ('.or.', ' or '), ('.not.', ' not '), ('/=', '!='), ('.true.', 'True'),
+                 ('.false.', 'False'), ('.le.', '<='), ('.ge.', '>='), ('.lt.', '<'), ('.gt.', '>'), ('.eq.', '=='),
+                 ('.ne.', '!=')):
+        e = re.sub(re.escape(a), b, e, flags=re.I)
+    e = e.replace('%', '.')
+    for k, v in PY_KEYWORDS.items():
+        e = re.sub(r'\.%s\b' % k, '.' + v, e)
+        e = re.sub(r'(?<![\w.])%s\b' % k, v, e)
+    if re.search(r'(?<![\w.])\d+\s*/\s*\d+(?![\w.])', e):
+        raise NotImplementedError('integer division: ' + e)
+    return _sections(e).strip()
+
+
+def _lhs(target, arrays):
+    """python statement template (with %s for the value) for a scalar, component, element, section or whole array"""
+    target = target.strip()
+    m = re.fullmatch(r'([\w%]+)\((.*)\)', target)
+    if m:
+        idx = expr('(' + m.group(2) + ')')[1:-1]
+        return '%s[%s] = %%s' % (expr(m.group(1)), idx)
+    if '%' in target:
+        obj, comp = target.rsplit('%', 1)
+        return "_set(%s, '%s', %%s)" % (expr(obj), PY_KEYWORDS.get(comp, comp))
+    if target in arrays:
+        return '%s.assign(%%s)' % target
+    return '%s = %%s' % expr(target)
+
+
+def _results(outputs):
+    return 'return dict(%s)' % ', '.join('%s=%s' % (o, o) for o in outputs if o not in ERROR_ARGS)
+
+
+def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
+    """translate a list of executable statements; returns python source lines"""
+    py, depth = [], indent
+    sigs = sigs or {}
+
+    def emit(s):
+        py.append('    ' * depth + s)
+
+    for stmt in lines:
+        low = stmt.lower()
+        if low == 'implicit none' or low.startswith('use ') or ('::' in stmt and re.match(
+                r'(type\s*\(|integer|real|logical|character)', low)):
+            continue
+        if re.match(r'(init_error|pass_error|pass_error_with_info)\s*\(', low):
+            continue          # the error stack: an error is an exception here
+        if re.fullmatch(r'end\s*if', low) or re.fullmatch(r'end\s*do', low):
+            depth -= 1
+            continue
+        if low == 'else':
+            depth -= 1; emit('else:'); depth += 1
+            emit('pass')
+            continue
+        if low == 'return':
+            emit(_results(outputs))
+            continue
+        m = re.match(r'(else\s*if|if)\s*\(', low)
+        if m:
+            close = _matching(stmt, m.end() - 1)
+            cond, rest = expr(stmt[m.end():close]), stmt[close + 1:].strip()
+            kw = 'elif' if low.startswith('else') else 'if'
+            if rest.lower() == 'then':
+                if kw == 'elif':
+                    depth -= 1
+                emit('%s %s:' % (kw, cond)); depth += 1
+                emit('pass')
+            else:
+                assert kw == 'if', stmt
+                emit('if %s:' % cond)
+                depth += 1
+                py.extend(statements([rest], depth, outputs, sigs, arrays))
+                depth -= 1
+            continue
+        m = re.fullmatch(r'do\s+(\w+)\s*=\s*(.+)', stmt, re.I)
+        if m:
+            parts = [expr(p) for p in _split_top(m.group(2), ',')]
+            if len(parts) == 2:
+                emit('for %s in range(%s, (%s)+1):' % (m.group(1), parts[0], parts[1]))
+            else:
+                step = int(parts[2])
+                emit('for %s in range(%s, (%s)%s, %d):' % (m.group(1), parts[0], parts[1], '+1' if step > 0 else '-1', step))
+            depth += 1
+            emit('pass')
+            continue
+        m = re.match(r'RAISE_ERROR\s*\((.*)\)$', stmt)     # before assignments: the message may hold '='
+        if m:
+            emit('raise RuntimeError(%r)' % m.group(1))
+            continue
+        m = re.fullmatch(r'call\s+(\w+)\s*\((.*)\)', stmt, re.I)
+        if m:
+            name = m.group(1)
+            if name not in sigs:
+                raise NotImplementedError('call of an unknown unit: ' + stmt)
+            dummies, pure_out, outs = sigs[name]
+            actuals = [a.strip() for a in _split_top(m.group(2), ',')]
+            actuals = [a for a in actuals if not (re.fullmatch(r'\w+\s*=\s*\w+', a) and a.split('=')[0].strip() in ERROR_ARGS)]
+            assert len(actuals) <= len(dummies), stmt
+            ins = [expr(a) for a, d in zip(actuals, dummies) if d not in pure_out]
+            emit('_r = %s(%s)' % (name, ', '.join(ins)))
+            for a, d in zip(actuals, dummies):
+                if d in outs and d not in ERROR_ARGS:
+                    emit(_lhs(a, arrays) % ("_r['%s']" % d))
+            continue
+        if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall', 'allocate')):
+            # first '=' that is not part of ==, /=, <=, >=
+            k = re.search(r'(?<![=/<>])=(?!=)', stmt).start()
+            emit(_lhs(stmt[:k], arrays) % expr(stmt[k + 1:]))
+            continue
+        raise NotImplementedError(stmt)
+    return py
+
+
+def _signature(lines, k):
+    m = re.match(r'(?:(?:elemental|pure|recursive)\s+)*(subroutine|function)\s+(\w+)\s*\(([^)]*)\)', lines[k], re.I)
+    if not m:
+        return None
+    kind, name, args = m.group(1).lower(), m.group(2), [a.strip() for a in m.group(3).split(',') if a.strip()]
+    end = next(j for j in range(k + 1, len(lines)) if re.match(r'end\s*(subroutine|function)', lines[j], re.I))
+    body = lines[k + 1:end]
+    outs, pure_out, objects, local_arrays = [], set(), [], []
+    for decl in body:
+        if '::' not in decl or not re.match(r'(type\s*\(|integer|real|logical|character)', decl.lower()):
+            continue
+        names = [v.strip() for v in _split_top(decl.split('::', 1)[1], ',')]
+        bare = [re.match(r'\w+', n).group(0) for n in names]
+        m2 = re.search(r'intent\s*\(\s*(out|inout)\s*\)', decl, re.I)
+        if m2:
+            outs += bare
+            if m2.group(1).lower() == 'out':
+                pure_out.update(bare)
+                if decl.lower().startswith('type'):
+                    objects += bare                 # a derived-type result starts as an empty object
+        for n, b in zip(names, bare):
+            dims = re.fullmatch(r'\w+\((.*)\)', n.split('=')[0].strip())
+            if dims and (b not in args or b in pure_out):
+                local_arrays.append((b, dims.group(1)))      # locals and array results are created here
+    return dict(kind=kind, name=name, args=args, end=end, body=body, outs=outs, pure_out=pure_out, objects=objects,
+                local_arrays=local_arrays)
+
+
+def units(text, defined=(), env=None):
+    """{name: python callable} for every subroutine / function of a source text.  A subroutine returns the dict
+    of its intent(out) / intent(inout) arguments, a function its result.  env: extra names (constants, Python
+    callables; a callable that is CALLed needs .fortran_args = (dummy names, names of the intent(out) ones) and
+    returns the dict of those)"""
+    lines = preprocess(text, defined)
+    scope = dict(INTRINSICS)
+    scope.update(env or {})
+    found, k = [], 0
+    while k < len(lines):
+        sig = _signature(lines, k)
+        if sig is None:
+            k += 1
+            continue
+        found.append(sig)
+        k = sig['end'] + 1
+    sigs = {}
+    for name, fn in scope.items():
+        if hasattr(fn, 'fortran_args'):
+            d, po = fn.fortran_args
+            sigs[name] = (list(d), set(po), list(po))
+    for sig in found:
+        sigs[sig['name']] = (sig['args'], sig['pure_out'], sig['outs'])
+    sources = {}
+    for sig in found:
+        name = sig['name']
+        pyargs = [PY_KEYWORDS.get(a, a) for a in sig['args'] if a not in sig['pure_out']]   # intent(out): results only
+        src = ['def %s(%s):' % (name, ', '.join(pyargs))] + ['    %s = Obj()' % o for o in sig['objects']]
+        arrays = [b for b, _ in sig['local_arrays']]
+        # an intent(out) scalar a branch never assigns is undefined in Fortran: None here
+        src += ['    %s = None' % o for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]
+        try:
+            for b, dims in sig['local_arrays']:
+                shape, lower = [], []
+                for d in _split_top(dims, ','):
+                    if ':' in d:
+                        lo, hi = d.split(':')
+                        lower.append(expr(lo)); shape.append('(%s)-(%s)+1' % (expr(hi), expr(lo)))
+                    else:
+                        lower.append('1'); shape.append(expr(d))
+                src.append('    %s = FA(%s, lower=(%s,))' % (b, ', '.join(shape), ', '.join(lower)))
+            src += statements(sig['body'], 1, sig['outs'] if sig['kind'] == 'subroutine' else (), sigs, arrays)
+            src.append('    return %s' % name if sig['kind'] == 'function' else '    ' + _results(sig['outs']))
+            compile('\n'.join(src), name, 'exec')
+            sources[name] = '\n'.join(src)
+        except NotImplementedError as e:          # a unit outside the subset: recorded, never silently replaced
+            sources[name] = e
+        except Exception as e:                    # noqa: BLE001 -- statements the patterns above misread
+            sources[name] = NotImplementedError('%s: %r' % (name, e))
+    # one namespace for all units of the file, so that they can call each other
+    result = {}
+    for name, src in sources.items():
+        if isinstance(src, str):
+            exec(src, scope)
+            fn = scope[name]
+            fn.python_source = src
+            fn.fortran_args = (sigs[name][0], sigs[name][1])
+            result[name] = fn
+        else:
+            result[name] = src
+    return result
+
+
+def run_fragment(text, first, last, env, defined=(), arrays=()):
+    """execute the statements of `text` from the first one matching regex `first` to the first one after it
+    matching `last` (inclusive) in `env` (a dict: loop variables, `this`, ...)"""
+    lines = preprocess(text, defined)
+    a = next(k for k, s in enumerate(lines) if re.search(first, s))
+    b = next(k for k in range(a, len(lines)) if re.search(last, lines[k]))
+    src = statements(lines[a:b + 1], 0, (), None, arrays)
+    scope = dict(INTRINSICS)
+    scope.update(env)
+    exec('\n'.join(src), scope)
+    return '\n'.join(src)

@@ -1,0 +1,296 @@
+"""The oracle's per-pair / per-triplet functions (VA, VR, g, bo, h of oracle_bop.c) against the REFERENCE's own
+tersoff_func.f90 / kumagai_func.f90 / brenner_func.f90 / juslin_func.f90, executed here through the Fortran-subset
+translator of tests/fortran_subset.py (the derived constants of Brenner / Juslin through the reference's own
+brenner_module.f90 / juslin_module.f90 lines).  This pins the oracle's functional forms -- including quirks such as
+kumagai_func.f90's beta == 3 branch -- to the reference's source at rounding level, where the known-answer tests
+pin them to 1e-3.  Runs where /root/reference exists."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from atomistica_b200 import parameters as P
+from fortran_subset import F1, Obj, run_fragment, units
+
+BOP = '/root/reference/src/potentials/bop'
+pytestmark = pytest.mark.skipif(not os.path.isdir(BOP), reason='the reference tree is not present')
+
+RTOL = 4e-15     # a few ulp: libm exp/pow are the same on both sides, association order is the reference's
+
+
+def _db(d):
+    fields = {('lambda_' if k == 'lambda' else k): F1(v) for k, v in d.items() if k not in ('__ref__', 'el')}
+    return Obj(nel=len(d['el']), **fields)
+
+
+def _close(a, b, what, atol=1e-300):
+    for x, y in zip(a, b):
+        assert abs(x - y) <= RTOL * max(abs(x), abs(y)) + atol, (what, x, y)
+
+
+# the g(cos theta) polynomials of REBO2 are sums of terms of order 1-10 that cancel to 1e-2 near cos theta = -1;
+# x**k through pow() here and through the multiplications gfortran expands it into differ in the last bit of a term
+POLY_ATOL = 5e-15
+
+
+def _sweep(fn, ofn, xs, label):
+    n = 0
+    for x in xs:
+        _close(fn(x), ofn(x), (label, x))
+        n += 1
+    return n
+
+
+def _check(kind, db, this, funcs, juslin=False):
+    """all five functions, every pair / element / triplet index, a sweep of arguments each"""
+    par = oracle.bop_params(kind, db)
+    nel = len(db['el'])
+    npairs = nel * nel if juslin else nel * (nel + 1) // 2
+    rng = np.random.RandomState(11)
+    rs = np.concatenate([np.linspace(0.7, 4.0, 12), rng.uniform(0.8, 3.5, 8)])
+    n = 0
+    for ij in range(1, npairs + 1):
+        if juslin and db['r0'][ij - 1] <= 0.0 and db['D0'][ij - 1] == 0.0:
+            continue       # unset pairs of the W-C-H table (S = 0: VR_f is a division by -1 of zero; nothing to compare)
+        for name in ('VA', 'VR'):
+            n += _sweep(lambda x: tuple(funcs[name](this, ij, x).values()),
+                        lambda x: oracle.bop_func(par, name, x, ijpot=ij), rs, (name, ij))
+        for kt in range(1, nel + 1):
+            # bo: zij <= 0 branch, tiny, typical and large coordination sums
+            for z in (0.0, -0.1, 1e-9, 0.03, 0.7, 1.0, 2.9, 11.0):
+                for fc, fa in ((1.0, -3.1), (0.37, -0.9)):
+                    r = funcs['bo'](this, kt, ij, z, fc, fa)
+                    _close((r['bij'], r['dfbij']), oracle.bop_func(par, 'bo', z, ktypi=kt, ijpot=ij, fcij=fc, faij=fa),
+                           ('bo', ij, kt, z))
+                    n += 1
+    cs = np.concatenate([np.linspace(-1.0, 1.0, 9), rng.uniform(-1, 1, 6)])
+    for ki in range(1, nel + 1):
+        for kj in range(1, nel + 1):
+            for kk in range(1, nel + 1):
+                ij = funcs['Z2pair'](this, ki, kj)
+                ik = funcs['Z2pair'](this, ki, kk)
+                n += _sweep(lambda x: tuple(funcs['g'](this, kj, ki, kk, ij, ik, x).values()),
+                            lambda x: oracle.bop_func(par, 'g', x, ktypj=kj, ktypi=ki, ktypk=kk, ijpot=ij, ikpot=ik),
+                            cs, ('g', ki, kj, kk))
+                # h takes the difference of two bond lengths (bop_kernel.f90:1242)
+                n += _sweep(lambda x: tuple(funcs['h'](this, kj, ki, kk, ij, ik, x).values()),
+                            lambda x: oracle.bop_func(par, 'h', x, ktypj=kj, ktypi=ki, ktypk=kk, ijpot=ij, ikpot=ik),
+                            np.linspace(-0.9, 0.9, 7), ('h', ki, kj, kk))
+    return n
+
+
+def _with(db, **over):
+    out = {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in db.items()}
+    out.update(over)
+    return out
+
+
+TERSOFF_SETS = ['Tersoff_PRB_39_5566_Si_C', 'Goumri_Said_ChemPhys_302_135_Al_N',
+                'Matsunaga_Fisher_Matsubara_Jpn_J_Appl_Phys_39_48_B_C_N']
+
+
+@pytest.mark.parametrize('name', TERSOFF_SETS)
+def test_tersoff_functions(name):
+    funcs = units(open(BOP + '/tersoff/tersoff_func.f90').read())
+    assert set(funcs) >= {'VA', 'VR', 'g', 'bo', 'h', 'Z2pair'}
+    db = P.complete('Tersoff', getattr(P, name))
+    assert _check(oracle.TERSOFF, db, Obj(db=_db(db)), funcs) > 300
+    # the length-dependent factor of the bond order is off in the published sets: switch it on, all three branches
+    npairs = len(db['A'])
+    for m in (1, 3, 2, 5):
+        dbm = _with(db, mubo=[0.45 + 0.1 * k for k in range(npairs)], m=[m] * npairs)
+        assert _check(oracle.TERSOFF, dbm, Obj(db=_db(dbm)), funcs) > 300
+
+
+def test_kumagai_functions():
+    funcs = units(open(BOP + '/kumagai/kumagai_func.f90').read())
+    db = P.complete('Kumagai', P.Kumagai_CompMaterSci_39_457_Si)
+    assert _check(oracle.KUMAGAI, db, Obj(db=_db(db)), funcs) > 70
+    for beta in (1, 3, 2):      # beta == 3 is the branch whose exponent lacks alpha in the reference (:211-213)
+        dbm = _with(db, alpha=[1.3], beta=[beta])
+        assert _check(oracle.KUMAGAI, dbm, Obj(db=_db(dbm)), funcs) > 70
+    assert 'exp(dr*dr*dr)' in funcs['h'].python_source.replace(' ', '')
+
+
+def _brenner_this(db, module, npairs):
+    """derived constants by the reference's own lines (brenner_module.f90:269-288, juslin_module.f90:322-343)"""
+    this = Obj(db=_db(db), **{k: F1([0.0] * npairs) for k in (
+        'bo_exp', 'bo_fac', 'bo_exp1', 'expR', 'expA', 'c_sq', 'd_sq', 'c_d', 'VR_f', 'VA_f')})
+    text = open(module).read()
+    for i in range(1, npairs + 1):
+        if db['S'][i - 1] <= 1.0:
+            continue         # unset pair of a Juslin table; the reference raises for it only if the pair is used
+        src = run_fragment(text, r'this%bo_exp\(i\)\s*=', r'this%VA_f\(i\)\s*=', dict(this=this, i=i))
+    assert src.count('=') >= 10 and 'raise RuntimeError' in src
+    return this
+
+
+BRENNER_SETS = ['Erhart_PRB_71_035211_SiC', 'Albe_PRB_65_195124_PtC', 'Henriksson_PRB_79_114107_FeC',
+                'Kioseoglou_PSSb_245_1118_AlN', 'Brenner_PRB_42_9458_C_I', 'Brenner_PRB_42_9458_C_II']
+
+
+@pytest.mark.parametrize('name', BRENNER_SETS)
+def test_brenner_functions(name):
+    funcs = units(open(BOP + '/brenner/brenner_func.f90').read())
+    db = P.complete('Brenner', getattr(P, name))
+    npairs = len(db['D0'])
+    this = _brenner_this(db, BOP + '/brenner/brenner_module.f90', npairs)
+    assert _check(oracle.BRENNER, db, this, funcs) > 70
+    for m in (1, 3, 4):
+        dbm = _with(db, mu=[0.6 + 0.05 * k for k in range(npairs)], m=[m] * npairs, n=[0.8] * npairs)
+        assert _check(oracle.BRENNER, dbm, _brenner_this(dbm, BOP + '/brenner/brenner_module.f90', npairs), funcs) > 70
+
+
+@pytest.mark.parametrize('name', ['Juslin_JAP_98_123520_WCH', 'Kuopanportti_CMS_111_525_FeCH'])
+def test_juslin_functions(name):
+    funcs = units(open(BOP + '/juslin/juslin_func.f90').read())
+    db = P.complete_juslin(getattr(P, name))
+    this = _brenner_this(db, BOP + '/juslin/juslin_module.f90', 9)
+    assert _check(oracle.JUSLIN, db, this, funcs, juslin=True) > 500
+    for m in (3, 2):
+        dbm = _with(db, m=[m] * 27)
+        assert _check(oracle.JUSLIN, dbm, _brenner_this(dbm, BOP + '/juslin/juslin_module.f90', 9), funcs,
+                      juslin=True) > 500
+
+
+def test_cutoff_functions():
+    """src/support/cutoff.f90: trig_off (:152-196) and exp_cutoff (:232-293) -- the switching functions of the
+    plain and of the screened potentials"""
+    funcs = units(open('/root/reference/src/support/cutoff.f90').read())
+    for kind, init, f in (('trig_off', 'trig_off_init', 'trig_off_f'), ('exp', 'exp_cutoff_init', 'exp_cutoff_f')):
+        assert callable(funcs[init]) and callable(funcs[f]), (funcs[init], funcs[f])
+        for r1, r2 in ((1.7, 2.0), (2.7, 3.0), (2.179347, 2.819732), (0.5, 4.0)):
+            this = funcs[init](r1, r2)['this']
+            for r in np.concatenate([[r1 - 0.1, r1, r2, r2 + 0.1], np.linspace(r1, r2, 41)[1:-1]]):
+                got = funcs[f](this, float(r))
+                _close((got['val'], got['dval']), oracle.cutoff_eval(kind, r1, r2, float(r)), (kind, r1, r2, r))
+
+
+# ---- REBO2: rebo2_func.f90 and the constants of rebo2_db.f90:147-195 ------------------------------------------
+
+REBO2 = BOP + '/rebo2'
+REBO2_NAMES = dict(C_C=1, C_H=3, H_H=6, rebo2_C_=1, rebo2_H_=3)      # rebo2_type.f90:31-38
+
+
+def _rebo2_this(orc):
+    """a rebo2_t image: parameters (equal to the reference's defaults, tests/test_rebo2_tables_vs_reference.py),
+    the derived constants by the reference's own statements, the g-spline coefficients of the oracle (checked
+    against the reference's construction in test_rebo2_g_spline_construction)"""
+    from fortran_subset import FA
+    this = Obj(**{k: v for k, v in orc.d.items() if k != 'with_dihedral'})
+    this.cc_g_theta = F1(list(oracle.CC_G_THETA))
+    this.spgh = FA(6, 3, data=list(oracle.SPGH))
+    this.igh = F1(list(oracle.IGH))
+    this.cc_g1_coeff = Obj(c=FA(6, 3, data=list(orc.p.cc_g1_coeff)))
+    this.cc_g2_coeff = Obj(c=FA(6, 3, data=list(orc.p.cc_g2_coeff)))
+    this.conpe, this.conan, this.conpf = FA(3), FA(3), FA(3)
+    this.conear, this.conalp = FA(6, 6), None
+    for k in ('cut_in_l', 'cut_in_h', 'cut_in_h2', 'cut_in_m'):
+        setattr(this, k, FA(10))
+    src = run_fragment(open(REBO2 + '/rebo2_db.f90').read(), r'this%conpe\(1\)\s*=', r'this%cut_in_m\(H_H\)\s*=',
+                       dict(this=this, **REBO2_NAMES))
+    assert src.count('\n') >= 30
+    return this
+
+
+def test_rebo2_derived_constants():
+    orc = oracle.Rebo2()
+    this = _rebo2_this(orc)
+    p = orc.p
+    assert list(this.conpe) == list(p.conpe) and list(this.conan) == list(p.conan) and list(this.conpf) == list(p.conpf)
+    assert this.conalp == p.conalp
+    assert list(this.conear) == list(p.conear)                      # both column-major (6,6)
+    for k in ('cut_in_l', 'cut_in_h', 'cut_in_h2'):
+        assert list(getattr(this, k)) == list(getattr(p, k)), k
+    assert this.conear(3, 1) == 1.0 / this.conear(1, 3) and this.conear(1, 3) != 0.0
+
+
+def test_rebo2_functions():
+    from fortran_subset import FA
+    cut = units(open('/root/reference/src/support/cutoff.f90').read())
+    orc = oracle.Rebo2()
+    this = _rebo2_this(orc)
+    # rebo2_db.f90: the inner cutoff objects are CUTOFF_T = trig_off_t (rebo2.f90), f_and_df is their generic
+    this.spl_fCin = FA(10, data=[None] * 10)
+    for ij in (1, 3, 6):
+        this.spl_fCin[ij] = cut['trig_off_init'](this.cut_in_l(ij), this.cut_in_h(ij))['this']
+    funcs = units(open(REBO2 + '/rebo2_func.f90').read(), env=dict(f_and_df=cut['trig_off_f'], **REBO2_NAMES))
+    for name in ('fconj', 'fCin', 'VA', 'VR', 'g', 'cc_g_from_spline', 'bo', 'h', 'Z2pair'):
+        assert callable(funcs[name]), (name, funcs[name])
+    p, n = orc.p, 0
+    rng = np.random.RandomState(3)
+    for x in np.concatenate([np.linspace(1.5, 3.5, 21), [2.0, 3.0]]):
+        r = funcs['fconj'](this, float(x))
+        _close((r['fx'], r['dfx']), oracle.rebo2_func(p, 'fconj', x=float(x))[:2], ('fconj', x)); n += 1
+    for ij in (1, 3, 6):
+        lo, hi = this.cut_in_l(ij), this.cut_in_h(ij)
+        for x in np.concatenate([np.linspace(lo - 0.2, hi + 0.2, 33), [lo, hi]]):
+            for name in ('fCin', 'VA', 'VR'):
+                r = funcs[name](this, ij, float(x))
+                _close((r['val'], r['dval']), oracle.rebo2_func(p, name, x=float(x), i1=ij)[:2], (name, ij, x)); n += 1
+    # g: carbon (both splines and the blend between N = 3.2 and 3.7, whose upper bound is a single-precision
+    # literal in the reference), hydrogen (sixth-order polynomials selected through IGH)
+    for c in np.concatenate([np.linspace(-1.0, 1.0, 41), rng.uniform(-1, 1, 20), [-0.5, -1.0 / 3]]):
+        for nn in (0.0, 2.0, 3.2, 3.3, 3.45, 3.6999, 3.7, 3.70000005, 3.8, 4.0):
+            r = funcs['g'](this, 1, float(c), nn)
+            _close((r['val'], r['dval_dcosth'], r['dval_dN']), oracle.rebo2_func(p, 'g', x=float(c), y=nn, i1=1), ('gC', c, nn), POLY_ATOL)
+            n += 1
+        if c < 1.0:       # int(-costh*12)+13 indexes IGH(1:25); costh = 1 is the last interval
+            r = funcs['g'](this, 3, float(c), 1.0)
+            _close((r['val'], r['dval_dcosth']), oracle.rebo2_func(p, 'g', x=float(c), y=1.0, i1=3)[:2], ('gH', c), 1e-11); n += 1
+    for kt in (1, 3):
+        for z in (0.0, 1e-6, 0.3, 1.0, 2.7, 9.0):
+            r = funcs['bo'](this, kt, 1, z, 0.8, -2.5)
+            _close((r['bij'], r['dfbij']), oracle.rebo2_func(p, 'bo', x=z, y=0.8, z=-2.5, i1=kt)[:2], ('bo', kt, z)); n += 1
+    for ij in (1, 3, 6):
+        for ik in (1, 3, 6):
+            for x in np.linspace(-0.8, 0.8, 9):
+                r = funcs['h'](this, 1, 1, 1, ij, ik, float(x))
+                _close((r['val'], r['dval']), oracle.rebo2_func(p, 'h', x=float(x), i1=ij, i2=ik)[:2], ('h', ij, ik, x)); n += 1
+    for a in (1, 3):
+        for b in (1, 3):
+            assert funcs['Z2pair'](this, a, b) == int(oracle.rebo2_func(p, 'Z2pair', i1=a, i2=b)[0])
+    assert n > 1000
+
+
+def test_rebo2_g_spline_construction():
+    """rebo2_db_make_cc_g_spline (rebo2_db.f90:405-524) executed: the matrices and right-hand sides are the
+    reference's, the 6x6 systems are solved exactly (rational arithmetic) where the reference calls gauss1 / dgesv;
+    the oracle's coefficients (its own elimination) must agree to the conditioning of the systems"""
+    from fractions import Fraction
+    from fortran_subset import FA
+
+    def gauss1(n, A, x):
+        M = [[Fraction(A(i, j)) for j in range(1, n + 1)] + [Fraction(x(i))] for i in range(1, n + 1)]
+        for c in range(n):
+            piv = next(r for r in range(c, n) if M[r][c] != 0)
+            M[c], M[piv] = M[piv], M[c]
+            for r in range(n):
+                if r != c and M[r][c] != 0:
+                    f = M[r][c] / M[c][c]
+                    M[r] = [a - f * b for a, b in zip(M[r], M[c])]
+        for i in range(n):
+            x[i + 1] = float(M[i][n] / M[i][i])
+        return {}
+    gauss1.fortran_args = (('n', 'A', 'x', 'error'), ('error',))
+
+    funcs = units(open(REBO2 + '/rebo2_db.f90').read(), env=dict(gauss1=gauss1, **REBO2_NAMES))
+    make = funcs['rebo2_db_make_cc_g_spline']
+    assert callable(make), make
+    this = Obj(cc_g_theta=F1(list(oracle.CC_G_THETA)), cc_g_g1=F1(list(oracle.CC_G_G1)),
+               cc_g_dg1=F1(list(oracle.CC_G_DG1)), cc_g_d2g1=F1(list(oracle.CC_G_D2G1)),
+               cc_g_g2=F1(list(oracle.CC_G_G2)), cc_g1_coeff=Obj(c=FA(6, 3)), cc_g2_coeff=Obj(c=FA(6, 3)))
+    make(this)
+    g1, g2 = oracle.make_cc_g_spline()
+    for mine, ref in ((g1, this.cc_g1_coeff.c), (g2, this.cc_g2_coeff.c)):
+        mine, ref = np.asarray(mine), np.asarray(list(ref))
+        assert np.abs(ref).max() > 1.0
+        assert np.abs(mine - ref).max() <= 1e-11 * np.abs(ref).max(), np.abs(mine - ref).max()
+    # the splines interpolate the published nodes (Brenner 2002, Table 3) -- through the reference's evaluator
+    ev = units(open(REBO2 + '/rebo2_func.f90').read(), env=dict(f_and_df=None, **REBO2_NAMES))['cc_g_from_spline']
+    for k, th in enumerate(oracle.CC_G_THETA):
+        r = ev(this, this.cc_g1_coeff, th)
+        assert abs(r['val'] - oracle.CC_G_G1[k]) < 1e-12, (k, r)
+        if k >= 2:
+            assert abs(ev(this, this.cc_g2_coeff, th)['val'] - oracle.CC_G_G2[k]) < 1e-12

@@ -138,6 +138,8 @@ INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=
                   PAIR_INDEX=_pair_index,
                   PAIR_INDEX_NS=lambda i, j, maxval: j + (i - 1) * maxval,                      # macros.inc:139
                   TRIPLET_INDEX_NS=lambda i, j, k, maxval: k + maxval * (j - 1 + maxval * (i - 1)),  # macros.inc:146
+                  floor=math.floor, present=lambda x: x is not None, allocated=lambda x: x is not None,
+                  lbound=lambda a, d: a.lower[d - 1], ubound=lambda a, d: a.lower[d - 1] + a.shape[d - 1] - 1, size=lambda a, d=None: len(a) if d is None else a.shape[d - 1],
                   PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp,
                   _ac=lambda v: FA(len(v), data=v))
 
@@ -261,7 +263,8 @@ def expr(e):
     for k, v in PY_KEYWORDS.items():
         e = re.sub(r'\.%s\b' % k, '.' + v, e)
         e = re.sub(r'(?<![\w.])%s\b' % k, v, e)
-    if re.search(r'(?<![\w.])\d+\s*/\s*\d+(?![\w.])', e):
+    # int/int would be an integer division in Fortran: flag it where both operands open a term (after ( + - = ,)
+    if re.search(r'(?:^|[(+\-=,])\s*\d+\s*/\s*\d+(?![\w.])', e):
         raise NotImplementedError('integer division: ' + e)
     return _sections(e).strip()
 
@@ -295,8 +298,35 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
 
     for stmt in lines:
         low = stmt.lower()
-        if low == 'implicit none' or low.startswith('use ') or ('::' in stmt and re.match(
-                r'(type\s*\(|integer|real|logical|character)', low)):
+        if low == 'implicit none' or low.startswith('use '):
+            continue
+        if '::' in stmt and re.match(r'(type\s*\(|integer|real|logical|character)', low):
+            # named constants and initialised scalars: "real(DP), parameter :: sig = 0.5"
+            for ent in _split_top(stmt.split('::', 1)[1], ','):
+                if '=' in ent:
+                    name = re.match(r'\s*(\w+)', ent).group(1)
+                    emit('%s = %s' % (name, expr(ent.split('=', 1)[1])))
+            continue
+        m = re.fullmatch(r'deallocate\s*\(([\w%]+)\)', stmt, re.I)
+        if m:
+            if '%' in m.group(1):
+                obj, comp = m.group(1).rsplit('%', 1)
+                emit("setattr(%s, '%s', None)" % (expr(obj), comp))
+            else:
+                emit('%s = None' % m.group(1))
+            continue
+        m = re.fullmatch(r'allocate\s*\((.*)\)', stmt, re.I)
+        if m:
+            for ent in _split_top(m.group(1), ','):
+                a = re.fullmatch(r'\s*([\w%]+)\((.*)\)\s*', ent)
+                if not a:
+                    raise NotImplementedError(stmt)
+                target, dims = a.group(1), expr(a.group(2))
+                if '%' in target:
+                    obj, comp = target.rsplit('%', 1)
+                    emit("setattr(%s, '%s', FA(%s))" % (expr(obj), comp, dims))
+                else:
+                    emit('%s = FA(%s)' % (target, dims))
             continue
         if re.match(r'(init_error|pass_error|pass_error_with_info)\s*\(', low):
             continue          # the error stack: an error is an exception here
@@ -357,7 +387,7 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
                 if d in outs and d not in ERROR_ARGS:
                     emit(_lhs(a, arrays) % ("_r['%s']" % d))
             continue
-        if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall', 'allocate')):
+        if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall')):
             # first '=' that is not part of ==, /=, <=, >=
             k = re.search(r'(?<![=/<>])=(?!=)', stmt).start()
             emit(_lhs(stmt[:k], arrays) % expr(stmt[k + 1:]))
@@ -373,12 +403,14 @@ def _signature(lines, k):
     kind, name, args = m.group(1).lower(), m.group(2), [a.strip() for a in m.group(3).split(',') if a.strip()]
     end = next(j for j in range(k + 1, len(lines)) if re.match(r'end\s*(subroutine|function)', lines[j], re.I))
     body = lines[k + 1:end]
-    outs, pure_out, objects, local_arrays = [], set(), [], []
+    outs, pure_out, objects, local_arrays, optional = [], set(), [], [], set()
     for decl in body:
         if '::' not in decl or not re.match(r'(type\s*\(|integer|real|logical|character)', decl.lower()):
             continue
         names = [v.strip() for v in _split_top(decl.split('::', 1)[1], ',')]
         bare = [re.match(r'\w+', n).group(0) for n in names]
+        if re.search(r'\boptional\b', decl.split('::')[0], re.I):
+            optional.update(bare)
         m2 = re.search(r'intent\s*\(\s*(out|inout)\s*\)', decl, re.I)
         if m2:
             outs += bare
@@ -389,9 +421,10 @@ def _signature(lines, k):
         for n, b in zip(names, bare):
             dims = re.fullmatch(r'\w+\((.*)\)', n.split('=')[0].strip())
             if dims and (b not in args or b in pure_out):
-                local_arrays.append((b, dims.group(1)))      # locals and array results are created here
+                deferred = all(d.strip() == ':' for d in _split_top(dims.group(1), ','))
+                local_arrays.append((b, None if deferred else dims.group(1)))   # locals / array results are created here
     return dict(kind=kind, name=name, args=args, end=end, body=body, outs=outs, pure_out=pure_out, objects=objects,
-                local_arrays=local_arrays)
+                local_arrays=local_arrays, optional=optional)
 
 
 def units(text, defined=(), env=None):
@@ -420,13 +453,17 @@ def units(text, defined=(), env=None):
     sources = {}
     for sig in found:
         name = sig['name']
-        pyargs = [PY_KEYWORDS.get(a, a) for a in sig['args'] if a not in sig['pure_out']]   # intent(out): results only
+        pyargs = [PY_KEYWORDS.get(a, a) + ('=None' if a in sig['optional'] else '')
+                  for a in sig['args'] if a not in sig['pure_out']]                       # intent(out): results only
         src = ['def %s(%s):' % (name, ', '.join(pyargs))] + ['    %s = Obj()' % o for o in sig['objects']]
         arrays = [b for b, _ in sig['local_arrays']]
         # an intent(out) scalar a branch never assigns is undefined in Fortran: None here
         src += ['    %s = None' % o for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]
         try:
             for b, dims in sig['local_arrays']:
+                if dims is None:
+                    src.append('    %s = None' % b)          # allocatable: created by ALLOCATE
+                    continue
                 shape, lower = [], []
                 for d in _split_top(dims, ','):
                     if ':' in d:

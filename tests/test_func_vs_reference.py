@@ -294,3 +294,116 @@ def test_rebo2_g_spline_construction():
         assert abs(r['val'] - oracle.CC_G_G1[k]) < 1e-12, (k, r)
         if k >= 2:
             assert abs(ev(this, this.cc_g2_coeff, th)['val'] - oracle.CC_G_G2[k]) < 1e-12
+
+
+# ---- EAM: src/support/simple_spline.f90 ----------------------------------------------------------------------
+
+def test_simple_spline_init_and_evaluation(cu_setfl):
+    """simple_spline_init (:127-195) and simple_spline_f_and_df (:536-614), executed on the tables of the
+    reference's own Cu_mishin1.eam.alloy: every coefficient array bit-identical with the oracle's spline_init,
+    evaluation (inside the table, at the cutoff, extrapolated on both sides) at rounding level"""
+    from fortran_subset import FA
+    funcs = units(open('/root/reference/src/support/simple_spline.f90').read())
+    init, fdf = funcs['simple_spline_init'], funcs['simple_spline_f_and_df']
+    assert callable(init) and callable(fdf), (init, fdf)
+    t = cu_setfl
+    rng = np.random.RandomState(2)
+    pad = np.zeros(2)          # tabulated_alloy_eam.f90 pads the r tables with two zeros (simple_spline_read)
+    for name, y, x0, dx in (('F', t['F'][0], 0.0, t['dF']), ('rho', np.concatenate([t['rho'][0], pad]), 0.0, t['dr']),
+                            ('r*phi', np.concatenate([t['rphi'][0], pad]), 0.0, t['dr'])):
+        y = np.asarray(y, dtype=np.float64)
+        n = len(y)
+        this = init(n, float(x0), float(dx), FA(n, data=y.tolist()))['this']
+        mine = oracle.spline_init(n, float(x0), float(dx), y)
+        assert this.n == mine['n'] and this.cut == mine['cut']
+        for fk, ok in (('y', 'y'), ('d2y', 'd2y'), ('coeff1', 'c1'), ('coeff2', 'c2'), ('coeff3', 'c3'),
+                       ('dcoeff1', 'd1'), ('dcoeff2', 'd2'), ('dcoeff3', 'd3')):
+            assert np.array_equal(np.asarray(list(getattr(this, fk))), np.asarray(mine[ok])), (name, fk)
+        cut = mine['cut']
+        xs = np.concatenate([rng.uniform(x0, cut, 40), [x0, cut, x0 + 3 * dx, cut - dx / 3]])
+        for x in xs:
+            r = fdf(this, float(x))
+            _close((r['f'], r['df']), oracle.spline_eval(mine, float(x)), (name, x))
+        for x in (x0 - 0.7 * dx, cut + 2.5 * dx, cut, 0.5 * cut):
+            r = fdf(this, float(x), True)
+            _close((r['f'], r['df']), oracle.spline_eval(mine, float(x), extrapolate=True), (name, 'extrapolate', x))
+        with pytest.raises(RuntimeError):
+            fdf(this, float(cut + dx))
+
+
+# ---- REBO2 tables: src/special/table2d.f90, table3d.f90 -----------------------------------------------------
+
+def _gaussn(n, A, m, x):
+    """the reference's gaussn is LAPACK dgesv when HAVE_LAPACK is defined (f_linearalgebra.f90:599-637) -- numpy's
+    solve is the same routine"""
+    a = np.array(list(A)).reshape(n, n, order='F')
+    b = np.array(list(x)).reshape(n, m, order='F')
+    x.assign(type(x)(n, m, data=np.linalg.solve(a, b).ravel(order='F').tolist()))
+    return {}
+
+
+_gaussn.fortran_args = (('n', 'A', 'm', 'x', 'error'), ('error',))
+
+
+def _fa0(a):
+    from fortran_subset import FA
+    a = np.asarray(a, dtype=np.float64)
+    return FA(*a.shape, data=a.ravel(order='F').tolist(), lower=(0,) * a.ndim)
+
+
+def test_table3d_init_and_eval():
+    """table3d_init (:85-284) and table3d_eval (:313-389) executed on the reference's default F_CC (with its
+    derivative tables), F_CH and T_CC: coefficients against the oracle's table3d_init, evaluation against
+    orc_table3d_eval incl. arguments outside the table (clamped boxes)"""
+    funcs = units(open('/root/reference/src/special/table3d.f90').read(), env=dict(gaussn=_gaussn, npara=64, ncorn=8))
+    init, ev = funcs['table3d_init'], funcs['table3d_eval']
+    assert callable(init) and callable(ev), (init, ev)
+    tabs = oracle.rebo2_default_tables()
+    rng = np.random.RandomState(5)
+    for name, extra in (('Fcc', ('dFdi', 'dFdj', 'dFdk')), ('Fch', ()), ('Tcc', ())):
+        t = Obj(coeff=None)
+        init(t, 4, 4, 9, _fa0(tabs[name]), *[_fa0(tabs[k]) for k in extra])
+        ref = np.asarray(list(t.coeff))
+        mine = oracle.table3d_init(4, 4, 9, tabs[name], *[tabs[k] for k in extra])
+        assert ref.shape == np.asarray(mine).shape == (144 * 64,)
+        assert np.abs(ref).max() > 1e-3
+        assert np.abs(np.asarray(mine) - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), name
+        # evaluation with the REFERENCE's coefficients on both sides: the Horner loops alone
+        st = oracle.Table3d(); st.nx, st.ny, st.nz = 4, 4, 9
+        keep = np.ascontiguousarray(ref)
+        st.coeff = keep.ctypes.data_as(type(st.coeff))
+        pts = np.concatenate([rng.uniform(0, 4, (40, 3)) * [1, 1, 2.25], [[0, 0, 0], [4, 4, 9], [1, 2, 3], [-0.3, 4.7, 9.9],
+                                                                         [3.999, 0.001, 8.5]]])
+        for a, b, c in pts:
+            r = ev(t, float(a), float(b), float(c))
+            out = [oracle.C.c_double() for _ in range(4)]
+            oracle.lib().orc_table3d_eval(oracle.C.byref(st), oracle.C.c_double(a), oracle.C.c_double(b),
+                                          oracle.C.c_double(c), *[oracle.C.byref(o) for o in out])
+            _close((r['fcc'], r['dfccdi'], r['dfccdj'], r['dfccdc']), [o.value for o in out], (name, a, b, c), 1e-16)
+    # the table reproduces its nodes and node derivatives (the FRUIT test of the reference, test_table3d.f90)
+    r = ev(t, 2.0, 2.0, 0.0)
+    assert abs(r['fcc'] - tabs['Tcc'][2, 2, 0]) < 1e-12
+
+
+def test_table2d_init_and_eval():
+    funcs = units(open('/root/reference/src/special/table2d.f90').read(), env=dict(gaussn=_gaussn, npara=16, ncorn=4))
+    init, ev = funcs['table2d_init'], funcs['table2d_eval']
+    assert callable(init) and callable(ev), (init, ev)
+    tabs = oracle.rebo2_default_tables()
+    rng = np.random.RandomState(6)
+    for name in ('Pcc', 'Pch'):
+        t = Obj(coeff=None)
+        init(t, 5, 5, _fa0(tabs[name]))
+        ref = np.asarray(list(t.coeff))
+        mine = np.asarray(oracle.table2d_init(5, 5, tabs[name]))
+        assert ref.shape == mine.shape == (25 * 16,)
+        assert np.abs(mine - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), name
+        st = oracle.Table2d(); st.nx, st.ny = 5, 5
+        keep = np.ascontiguousarray(ref)
+        st.coeff = keep.ctypes.data_as(type(st.coeff))
+        for a, b in np.concatenate([rng.uniform(0, 5, (40, 2)), [[0, 0], [5, 5], [1, 2], [-0.2, 5.5]]]):
+            r = ev(t, float(a), float(b))
+            out = [oracle.C.c_double() for _ in range(3)]
+            oracle.lib().orc_table2d_eval(oracle.C.byref(st), oracle.C.c_double(a), oracle.C.c_double(b),
+                                          *[oracle.C.byref(o) for o in out])
+            _close(tuple(r.values()), [o.value for o in out], (name, a, b), 1e-16)

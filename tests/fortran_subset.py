@@ -101,6 +101,8 @@ class FA:
     def __mul__(self, o): return self._zip(o, lambda a, b: a * b)
     def __rmul__(self, o): return self._zip(o, lambda a, b: b * a)
     def __truediv__(self, o): return self._zip(o, lambda a, b: a / b)
+    def __neg__(self): return FA(*self.shape, data=[-a for a in self.data])
+    def __radd__(self, o): return self._zip(o, lambda a, b: b + a)
 
 
 def F1(values):
@@ -132,6 +134,38 @@ def _pair_index(i, j, maxval):
     return 1 + min((i - 1) + (j - 1) * maxval, (j - 1) + (i - 1) * maxval) - min((i - 1) * i // 2, (j - 1) * j // 2)
 
 
+def _dot_product(a, b):
+    acc = 0.0
+    for x, y in zip(a.data, b.data):
+        acc = acc + x * y
+    return acc
+
+
+def _matmul(a, b):
+    """matrix (n, m) times vector (m): each component accumulated over the second index in order"""
+    n, m = a.shape
+    assert len(b.data) == m
+    out = []
+    for i in range(n):
+        acc = 0.0
+        for j in range(m):
+            acc = acc + a.data[i + n * j] * b.data[j]
+        out.append(acc)
+    return FA(n, data=out)
+
+
+def _outer_product(x, y):
+    # macros.inc:82: spread(x, dim=2, ncopies=size(y)) * spread(y, dim=1, ncopies=size(x))
+    return FA(len(x.data), len(y.data), data=[a * b for b in y.data for a in x.data])
+
+
+def _sum(a):
+    acc = 0.0
+    for x in a.data:
+        acc = acc + x
+    return acc
+
+
 _PI = 3.14159265358979323846264338327950288
 INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=math.log, acos=math.acos,
                   abs=abs, max=max, min=min, real=lambda x, kind=None: float(x), int=int, DP=8,
@@ -140,6 +174,8 @@ INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=
                   TRIPLET_INDEX_NS=lambda i, j, k, maxval: k + maxval * (j - 1 + maxval * (i - 1)),  # macros.inc:146
                   floor=math.floor, present=lambda x: x is not None, allocated=lambda x: x is not None,
                   lbound=lambda a, d: a.lower[d - 1], ubound=lambda a, d: a.lower[d - 1] + a.shape[d - 1] - 1, size=lambda a, d=None: len(a) if d is None else a.shape[d - 1],
+                  dot_product=_dot_product, matmul=_matmul, outer_product=_outer_product, sum=_sum,
+                  iand=lambda a, b: a & b, ishft=lambda a, n: a << n if n >= 0 else a >> -n,
                   PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp,
                   _ac=lambda v: FA(len(v), data=v))
 
@@ -160,19 +196,83 @@ def _strip_comment(line):
     return line
 
 
-def preprocess(text, defined=()):
-    """cpp conditionals (only #ifdef / #ifndef / #if defined(A) || defined(B) / #else / #endif), comments,
-    continuation lines -> list of statements"""
+def _cpp_condition(raw, defined):
+    d = raw.split()
+    if d[0] == '#ifdef':
+        return d[1] in defined
+    if d[0] == '#ifndef':
+        return d[1] not in defined
+    cond = raw[len('#if'):].split('/*')[0]
+    cond = re.sub(r'defined\s*\(\s*(\w+)\s*\)', lambda m: str(m.group(1) in defined), cond)
+    cond = cond.replace('||', ' or ').replace('&&', ' and ').replace('!', ' not ')
+    if not re.fullmatch(r'[\s()\w]*', cond):
+        raise NotImplementedError(raw)
+    return bool(eval(cond, {'__builtins__': {}}, {}))      # True / False / 0 / 1 and boolean operators only
+
+
+MACRO_SKIP = {'outer_product', 'PAIR_INDEX', 'PAIR_INDEX_NS', 'TRIPLET_INDEX_NS'}    # provided as Python intrinsics
+
+
+def load_macros(text, defined=()):
+    """{name: (parameter list or None, body)} of the #define lines of a header that are active for `defined`"""
+    macros, active = {}, []
+    for raw in text.splitlines():
+        if not raw.startswith('#'):
+            continue
+        d = raw.split()
+        if d[0] in ('#ifdef', '#ifndef', '#if'):
+            active.append(_cpp_condition(raw, defined))
+        elif d[0] == '#else':
+            active[-1] = not active[-1]
+        elif d[0] == '#endif':
+            active.pop()
+        elif d[0] == '#define' and all(active):
+            m = re.match(r'#define\s+(\w+)(\(([^)]*)\))?\s*(.*)$', raw)
+            if m.group(1) not in MACRO_SKIP:
+                params = None if m.group(2) is None else [a.strip() for a in m.group(3).split(',') if a.strip()]
+                macros[m.group(1)] = (params, m.group(4).strip())
+    return macros
+
+
+def expand_macros(line, macros):
+    for _ in range(30):
+        changed = False
+        for name, (params, body) in macros.items():
+            for m in re.finditer(r'(?<![\w%%])%s\b' % name, line):
+                if params is None:
+                    line = line[:m.start()] + body + line[m.end():]
+                else:
+                    k = m.end()
+                    while k < len(line) and line[k] == ' ':
+                        k += 1
+                    if k >= len(line) or line[k] != '(':
+                        continue
+                    close = _matching(line, k)
+                    actuals = [a.strip() for a in _split_top(line[k + 1:close], ',')]
+                    assert len(actuals) == len(params), (name, line)
+                    sub = body
+                    # simultaneous substitution of the parameters (whole words)
+                    sub = re.sub(r'\b(%s)\b' % '|'.join(map(re.escape, params)),
+                                 lambda r: actuals[params.index(r.group(1))], sub)
+                    line = line[:m.start()] + sub + line[close + 1:]
+                changed = True
+                break
+            if changed:
+                break
+        if not changed:
+            return line
+    raise NotImplementedError('macro recursion: ' + line)
+
+
+def preprocess(text, defined=(), macros=None):
+    """cpp conditionals, comments, continuation lines, macro expansion (when `macros` is given), ';' -> list of
+    statements"""
     out, active = [], []
     for raw in text.splitlines():
         if raw.startswith('#'):
             d = raw.split()
-            if d[0] == '#ifdef':
-                active.append(d[1] in defined)
-            elif d[0] == '#ifndef':
-                active.append(d[1] not in defined)
-            elif d[0] == '#if':
-                active.append(any(n in defined for n in re.findall(r'defined\((\w+)\)', raw)))
+            if d[0] in ('#ifdef', '#ifndef', '#if'):
+                active.append(_cpp_condition(raw, defined))
             elif d[0] == '#else':
                 active[-1] = not active[-1]
             elif d[0] == '#endif':
@@ -196,15 +296,43 @@ def preprocess(text, defined=()):
             continue
         joined.append(cur + body)
         cur = ''
+    if macros:
+        expanded = []
+        for line in joined:
+            line = expand_macros(line, macros)
+            expanded += [part.strip() for part in _split_statements(line) if part.strip()]
+        joined = expanded
     return joined
 
 
+def _split_statements(line):
+    """';' separates statements (outside strings)"""
+    out, quote, start = [], None, 0
+    for k, ch in enumerate(line):
+        if quote:
+            if ch == quote:
+                quote = None
+        elif ch in '"\'':
+            quote = ch
+        elif ch == ';':
+            out.append(line[start:k])
+            start = k + 1
+    out.append(line[start:])
+    return out
+
+
 def _matching(s, start):
-    depth = 0
+    depth, quote = 0, None
     for k in range(start, len(s)):
-        if s[k] == '(':
+        ch = s[k]
+        if quote:
+            if ch == quote:
+                quote = None
+        elif ch in '"\'':
+            quote = ch
+        elif ch == '(':
             depth += 1
-        elif s[k] == ')':
+        elif ch == ')':
             depth -= 1
             if depth == 0:
                 return k
@@ -212,9 +340,14 @@ def _matching(s, start):
 
 
 def _split_top(s, sep):
-    out, depth, start = [], 0, 0
+    out, depth, start, quote = [], 0, 0, None
     for k, ch in enumerate(s):
-        if ch in '([':
+        if quote:
+            if ch == quote:
+                quote = None
+        elif ch in '"\'':
+            quote = ch
+        elif ch in '([':
             depth += 1
         elif ch in ')]':
             depth -= 1
@@ -378,13 +511,19 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
             if name not in sigs:
                 raise NotImplementedError('call of an unknown unit: ' + stmt)
             dummies, pure_out, outs = sigs[name]
-            actuals = [a.strip() for a in _split_top(m.group(2), ',')]
-            actuals = [a for a in actuals if not (re.fullmatch(r'\w+\s*=\s*\w+', a) and a.split('=')[0].strip() in ERROR_ARGS)]
-            assert len(actuals) <= len(dummies), stmt
-            ins = [expr(a) for a, d in zip(actuals, dummies) if d not in pure_out]
+            pairs = []                                     # (dummy, actual), keyword arguments matched by name
+            for pos, a in enumerate(a.strip() for a in _split_top(m.group(2), ',')):
+                kw = re.fullmatch(r'(\w+)\s*=(?!=)\s*(.+)', a)
+                if kw and kw.group(1) in dummies:
+                    pairs.append((kw.group(1), kw.group(2)))
+                else:
+                    assert pos < len(dummies) and not kw, stmt
+                    pairs.append((dummies[pos], a))
+            pairs = [(d, a) for d, a in pairs if d not in ERROR_ARGS]
+            ins = ['%s=%s' % (PY_KEYWORDS.get(d, d), expr(a)) for d, a in pairs if d not in pure_out]
             emit('_r = %s(%s)' % (name, ', '.join(ins)))
-            for a, d in zip(actuals, dummies):
-                if d in outs and d not in ERROR_ARGS:
+            for d, a in pairs:
+                if d in outs:
                     emit(_lhs(a, arrays) % ("_r['%s']" % d))
             continue
         if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall')):
@@ -427,12 +566,12 @@ def _signature(lines, k):
                 local_arrays=local_arrays, optional=optional)
 
 
-def units(text, defined=(), env=None):
+def units(text, defined=(), env=None, macros=None):
     """{name: python callable} for every subroutine / function of a source text.  A subroutine returns the dict
     of its intent(out) / intent(inout) arguments, a function its result.  env: extra names (constants, Python
     callables; a callable that is CALLed needs .fortran_args = (dummy names, names of the intent(out) ones) and
     returns the dict of those)"""
-    lines = preprocess(text, defined)
+    lines = preprocess(text, defined, macros)
     scope = dict(INTRINSICS)
     scope.update(env or {})
     found, k = [], 0
@@ -494,10 +633,10 @@ def units(text, defined=(), env=None):
     return result
 
 
-def run_fragment(text, first, last, env, defined=(), arrays=()):
+def run_fragment(text, first, last, env, defined=(), arrays=(), macros=None):
     """execute the statements of `text` from the first one matching regex `first` to the first one after it
     matching `last` (inclusive) in `env` (a dict: loop variables, `this`, ...)"""
-    lines = preprocess(text, defined)
+    lines = preprocess(text, defined, macros)
     a = next(k for k, s in enumerate(lines) if re.search(first, s))
     b = next(k for k in range(a, len(lines)) if re.search(last, lines[k]))
     src = statements(lines[a:b + 1], 0, (), None, arrays)

@@ -407,3 +407,91 @@ def test_table2d_init_and_eval():
             oracle.lib().orc_table2d_eval(oracle.C.byref(st), oracle.C.c_double(a), oracle.C.c_double(b),
                                           *[oracle.C.byref(o) for o in out])
             _close(tuple(r.values()), [o.value for o in out], (name, a, b), 1e-16)
+
+
+# ---- the EAM kernel itself: tabulated_alloy_eam.f90:423-627 --------------------------------------------------
+
+def _reference_macros(defined):
+    from fortran_subset import load_macros
+    m = load_macros(open('/root/reference/src/macros.inc').read(), defined)
+    m.update(load_macros(open('/root/reference/src/filter.inc').read(), defined))
+    return m
+
+
+def _particles_and_list(a, cutoff):
+    """particles_t / neighbors_t images (python_particles.f90, python_neighbors.f90) from the oracle's list"""
+    from fortran_subset import FA
+    nat = len(a)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
+    p = Obj(nat=nat, natloc=nat, r_non_cyc=FA(3, nat, data=np.asarray(a.positions, float).ravel().tolist()),
+            Abox=FA(3, 3, data=oracle.abox_from_cell(a.cell).ravel().tolist()),      # column-major 3x3, as passed to C
+            el=F1([1] * nat))
+    n = FA(len(nl.neighbors), data=[int(x) for x in nl.neighbors])
+    fnl = Obj(seed=F1([int(x) for x in nl.seed]), last=F1([int(x) for x in nl.last]), neighbors=n,
+              dc=FA(3, len(nl.neighbors), data=[int(x) for x in np.asarray(nl.dc).ravel()]))
+    return p, fnl, nl
+
+
+def test_eam_kernel_executed(cu_setfl):
+    """The reference's EAM kernel, statement by statement (macros of macros.inc / filter.inc expanded, simple_spline
+    routines from simple_spline.f90), on rattled fcc Cu with the reference's Cu_mishin1 tables: energy, forces,
+    virial, per-atom energies and virials, and a mask, against the oracle's orc_eam_energy_and_forces"""
+    from fortran_subset import FA
+    from atomistica_b200 import structures as S_
+    macros = _reference_macros({'PYTHON'})
+    spl = units(open('/root/reference/src/support/simple_spline.f90').read())
+    for k in ('simple_spline_init', 'simple_spline_f', 'simple_spline_df', 'simple_spline_f_and_df',
+              'simple_spline_scale_y_axis'):
+        assert callable(spl[k]), (k, spl[k])
+    t = cu_setfl
+    pad = [0.0, 0.0]
+    nr, dr, nF, dF = int(t['nr']), float(t['dr']), int(t['nF']), float(t['dF'])
+    fF = spl['simple_spline_init'](nF, 0.0, dF, FA(nF, data=t['F'][0].tolist()))['this']
+    frho = spl['simple_spline_init'](nr + 2, 0.0, dr, FA(nr + 2, data=t['rho'][0].tolist() + pad))['this']
+    fphi = spl['simple_spline_init'](nr + 2, 0.0, dr, FA(nr + 2, data=t['rphi'][0].tolist() + pad))['this']
+    spl['simple_spline_scale_y_axis'](fphi, 0.5)                   # tabulated_alloy_eam.f90:245
+    cutoff = float(t['cutoff'])
+    this = Obj(els=2, cutoff=cutoff, el2db=F1([1]), fF=F1([fF]), frho=F1([frho]), fphi=FA(1, 1, data=[fphi]))
+
+    a = S_.fcc('Cu', 3.615, (2, 2, 2))
+    a.rattle(0.08, seed=3)
+    nat = len(a)
+    p, fnl, nl = _particles_and_list(a, cutoff)
+    tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):      # tls.f90:185-269, one thread
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+
+    env = dict(func=spl['simple_spline_f'], dfunc=spl['simple_spline_df'], f_and_df=spl['simple_spline_f_and_df'],
+               tls_init=tls_init, tls_reduce=tls_reduce, **tls)
+    kern = units(open('/root/reference/src/potentials/eam/tabulated_alloy_eam.f90').read(), defined={'PYTHON'},
+                 env=env, macros=macros)['tabulated_alloy_eam_energy_and_forces_kernel']
+    assert callable(kern), kern
+    assert 'matmul(p.Abox' in kern.python_source and 'iand(els' in kern.python_source       # the macros expanded
+
+    orc = oracle.EAM(t)
+    eldb = orc.eldb(a.symbols)
+    rng = np.random.RandomState(8)
+    for mask in (None, (rng.rand(nat) > 0.4).astype(np.int32)):
+        f, epa, wpa = FA(3, nat), FA(nat), FA(3, 3, nat)
+        r = kern(this, p, fnl, 0.0, f, FA(3, 3), 200, None if mask is None else F1([int(m) for m in mask]), epa, wpa)
+        o = orc.energy_and_forces(a.positions, a.cell, nl, eldb, mask=mask, per_at=True)
+        scale = max(1.0, np.abs(o['f']).max())
+        assert abs(r['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
+        assert np.abs(np.asarray(list(f)).reshape(nat, 3) - o['f']).max() <= 1e-13 * scale
+        wref = np.asarray(list(r['wpot'])).reshape(3, 3).T                 # column-major (3,3) -> [a][b]
+        assert np.abs(wref - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max())
+        assert np.abs(np.asarray(list(epa)) - o['epot_per_at']).max() <= 1e-13 * np.abs(o['epot_per_at']).max()
+        wpa_ref = np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1)
+        assert np.abs(wpa_ref - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())
+        assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1

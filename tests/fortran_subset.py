@@ -102,6 +102,19 @@ class FA:
     def __rmul__(self, o): return self._zip(o, lambda a, b: b * a)
     def __truediv__(self, o): return self._zip(o, lambda a, b: a / b)
     def __neg__(self): return FA(*self.shape, data=[-a for a in self.data])
+    def __lt__(self, o): return self._zip(o, lambda a, b: a < b)
+    def __gt__(self, o): return self._zip(o, lambda a, b: a > b)
+    def __le__(self, o): return self._zip(o, lambda a, b: a <= b)
+    def __ge__(self, o): return self._zip(o, lambda a, b: a >= b)
+    def __eq__(self, o): return self._zip(o, lambda a, b: a == b)
+    def __ne__(self, o): return self._zip(o, lambda a, b: a != b)
+    __hash__ = None
+
+    def assign_where(self, mask, v):
+        """WHERE (mask) self = v"""
+        for k, m in enumerate(mask.data):
+            if m:
+                self.data[k] = v.data[k] if isinstance(v, FA) else v
     def __radd__(self, o): return self._zip(o, lambda a, b: b + a)
 
 
@@ -132,6 +145,17 @@ def _sp(x):
 def _pair_index(i, j, maxval):
     # macros.inc:123
     return 1 + min((i - 1) + (j - 1) * maxval, (j - 1) + (i - 1) * maxval) - min((i - 1) * i // 2, (j - 1) * j // 2)
+
+
+def _elementwise(f):
+    return lambda x, *a: FA(*x.shape, data=[f(v) for v in x.data]) if isinstance(x, FA) else f(x)
+
+
+def _cross_product(a, b):
+    # f_linearalgebra.f90 cross_product: (a2 b3 - a3 b2, a3 b1 - a1 b3, a1 b2 - a2 b1)
+    a1, a2, a3 = a.data
+    b1, b2, b3 = b.data
+    return FA(3, data=[a2 * b3 - a3 * b2, a3 * b1 - a1 * b3, a1 * b2 - a2 * b1])
 
 
 def _dot_product(a, b):
@@ -168,11 +192,13 @@ def _sum(a):
 
 _PI = 3.14159265358979323846264338327950288
 INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=math.log, acos=math.acos,
-                  abs=abs, max=max, min=min, real=lambda x, kind=None: float(x), int=int, DP=8,
+                  abs=abs, max=max, min=min, real=lambda x, kind=None: float(x), int=_elementwise(int), DP=8,
+                  any=lambda a: any(a.data), all=lambda a: all(a.data), shape=lambda a: FA(len(a.shape), data=list(a.shape)),
+                  cross_product=_cross_product,
                   PAIR_INDEX=_pair_index,
                   PAIR_INDEX_NS=lambda i, j, maxval: j + (i - 1) * maxval,                      # macros.inc:139
                   TRIPLET_INDEX_NS=lambda i, j, k, maxval: k + maxval * (j - 1 + maxval * (i - 1)),  # macros.inc:146
-                  floor=math.floor, present=lambda x: x is not None, allocated=lambda x: x is not None,
+                  floor=_elementwise(math.floor), present=lambda x: x is not None, allocated=lambda x: x is not None,
                   lbound=lambda a, d: a.lower[d - 1], ubound=lambda a, d: a.lower[d - 1] + a.shape[d - 1] - 1, size=lambda a, d=None: len(a) if d is None else a.shape[d - 1],
                   dot_product=_dot_product, matmul=_matmul, outer_product=_outer_product, sum=_sum,
                   iand=lambda a, b: a & b, ishft=lambda a, n: a << n if n >= 0 else a >> -n,
@@ -429,9 +455,41 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
     def emit(s):
         py.append('    ' * depth + s)
 
+    in_where = None
     for stmt in lines:
+        stmt = re.sub(r'^\w+\s*:\s*(?=(do|if)\b)', '', stmt, flags=re.I)          # construct names
+        stmt = re.sub(r'^(end\s*(?:do|if))\s+\w+$', r'\1', stmt, flags=re.I)
         low = stmt.lower()
-        if low == 'implicit none' or low.startswith('use '):
+        if low == 'implicit none' or low.startswith('use ') or re.match(r'(write|print)\b', low):
+            continue
+        if re.match(r'(invoke_delayed_error)\s*\(', low):
+            continue
+        m = re.fullmatch(r'do\s+while\s*\((.*)\)', stmt, re.I)
+        if m:
+            emit('while %s:' % expr(m.group(1))); depth += 1
+            emit('pass')
+            continue
+        m = re.fullmatch(r'forall\s*\(\s*(\w+)\s*=\s*(.+?)\s*:\s*(.+?)\s*\)', stmt, re.I)
+        if m:       # the bodies in the sources have no cross-iteration dependence: a DO loop
+            emit('for %s in range(%s, (%s)+1):' % (m.group(1), expr(m.group(2)), expr(m.group(3)))); depth += 1
+            emit('pass')
+            continue
+        if re.fullmatch(r'end\s*forall', low):
+            depth -= 1
+            continue
+        m = re.fullmatch(r'where\s*\((.*)\)', stmt, re.I)
+        if m:
+            emit('_mask = %s' % expr(m.group(1)))
+            in_where = True
+            continue
+        if re.fullmatch(r'end\s*where', low):
+            in_where = None
+            continue
+        if in_where:
+            k = re.search(r'(?<![=/<>])=(?!=)', stmt).start()
+            target = stmt[:k].strip()
+            assert re.fullmatch(r'[\w%]+', target), stmt
+            emit('%s.assign_where(_mask, %s)' % (expr(target), expr(stmt[k + 1:])))
             continue
         if '::' in stmt and re.match(r'(type\s*\(|integer|real|logical|character)', low):
             # named constants and initialised scalars: "real(DP), parameter :: sig = 0.5"

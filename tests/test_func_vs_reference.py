@@ -495,3 +495,78 @@ def test_eam_kernel_executed(cu_setfl):
         wpa_ref = np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1)
         assert np.abs(wpa_ref - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())
         assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+
+
+# ---- the neighbour list: python_neighbors.f90:570-959 (binning_init, binning_update, fill_neighbor_list) ---------
+
+def _reference_neighbor_list(a, cutoff, avgn=200):
+    """the reference's three routines executed on particles_t / neighbors_t images; returns (seed, last, neighbors,
+    dc) as numpy arrays in the reference's layout"""
+    from fortran_subset import FA
+    nat = len(a)
+    abox = oracle.abox_from_cell(a.cell)
+    bbox = oracle.bbox_from_abox(abox)
+    pbc = np.broadcast_to(np.asarray(a.pbc, dtype=bool), (3,))
+    p = Obj(nat=nat, natloc=nat, maxnatloc=nat, r_non_cyc=FA(3, nat, data=np.asarray(a.positions, float).ravel().tolist()),
+            Abox=FA(3, 3, data=abox.ravel().tolist()), Bbox=FA(3, 3, data=bbox.ravel().tolist()),
+            pbc=F1([int(x) for x in pbc]), lower_with_border=F1([0.0, 0.0, 0.0]))
+    cap = max(nat * avgn, 1)
+    this = Obj(cutoff=float(cutoff), bin_size=float(cutoff), Abox=FA(3, 3), box_size=FA(3), n_cells=FA(3), n_cells_tot=0,
+               cell_size=FA(3, 3), rec_cell_size=FA(3, 3), binning_seed=None, binning_last=None, next_particle=None,
+               d=None, n_d=0, seed=FA(nat + 1), last=FA(nat + 1), neighbors=FA(cap), dc=FA(3, cap), nupdate=0, avgnn=0.0)
+
+    def timer(name):
+        return {}
+    timer.fortran_args = (('name',), ())
+
+    def particles_dump_info(p, i, cell):
+        return {}
+    particles_dump_info.fortran_args = (('p', 'i', 'cell'), ())
+    funcs = units(open('/root/reference/src/python/f90/python_neighbors.f90').read(), defined={'PYTHON'},
+                  env=dict(timer_start=timer, timer_stop=timer, particles_dump_info=particles_dump_info, ERROR_NONE=0,
+                           ilog=0),
+                  macros=_reference_macros({'PYTHON'}))
+    for k in ('neighbors_binning_init', 'neighbors_binning_update', 'fill_neighbor_list'):
+        assert callable(funcs[k]), (k, funcs[k])
+    funcs['neighbors_binning_init'](this, p)
+    funcs['neighbors_binning_update'](this, p)
+    funcs['fill_neighbor_list'](this, p)
+    npairs = int(this.seed(nat + 1)) - 1
+    return (np.asarray(list(this.seed), dtype=np.int64), np.asarray(list(this.last), dtype=np.int64),
+            np.asarray(list(this.neighbors), dtype=np.int64)[:npairs],
+            np.asarray(list(this.dc), dtype=np.int64).reshape(-1, 3)[:npairs], this)
+
+
+def _list_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('Si', 5.43, (2, 2, 2)); a.rattle(0.1, seed=1)
+    yield 'Si diamond', a, 3.0
+    a = S_.fcc('Cu', 3.615, (2, 2, 2)); a.rattle(0.05, seed=2)
+    yield 'fcc Cu, cutoff beyond half the box', a, 5.5
+    a = S_.diamond('C', 3.57, (2, 2, 2)); a.rattle(0.05, seed=3)
+    a.cell = np.array([[7.14, 0.0, 0.0], [1.3, 7.0, 0.0], [-0.8, 0.9, 7.3]])       # triclinic, atoms partly outside
+    yield 'triclinic', a, 2.2
+    a = S_.diamond('Si', 5.43, (2, 2, 2)); a.rattle(0.1, seed=4)
+    a.pbc = np.array([True, False, True]); a.positions[5] += [0.0, -9.0, 0.0]; a.positions[11] += [17.0, 0.0, 0.0]
+    yield 'partial pbc, atoms far outside', a, 3.0
+    a = S_.fcc('Cu', 3.615, (1, 1, 1))
+    yield 'one unit cell, self images', a, 4.0
+
+
+@pytest.mark.parametrize('case', range(5))
+def test_neighbor_list_executed(case):
+    """The reference's cell binning and pair search executed statement by statement: seed, last, neighbors and dc
+    equal the oracle's arrays ENTRY BY ENTRY (same order, same terminator slots) -- the arrays the GPU lists are
+    compared with in tests/test_gpu_neighbors.py"""
+    name, a, cutoff = list(_list_cases())[case]
+    nat = len(a)
+    seed, last, neighbors, dc, this = _reference_neighbor_list(a, cutoff)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
+    assert np.array_equal(seed, np.asarray(nl.seed)), name
+    assert np.array_equal(last[:nat], np.asarray(nl.last)[:nat]), name
+    n = len(neighbors)
+    assert n == int(nl.seed[nat]) - 1 and nl.npairs > 2 * nat
+    assert np.array_equal(neighbors, np.asarray(nl.neighbors)[:n]), name
+    real = neighbors != 0                                          # terminator slots carry no shift
+    assert np.array_equal(dc[real], np.asarray(nl.dc)[:n][real]), name
+    assert int(np.count_nonzero(real)) == nl.npairs

@@ -52,7 +52,7 @@ class FA:
             if isinstance(i, S):
                 a = lo if i.lo is None else i.lo
                 b = lo + n - 1 if i.hi is None else i.hi
-                assert lo <= a and b <= lo + n - 1, (a, b, self.shape, self.lower)
+                assert b < a or (lo <= a and b <= lo + n - 1), (a, b, self.shape, self.lower)
                 r = range(a - lo, b - lo + 1)
                 shape.append(len(r))
             else:
@@ -194,7 +194,7 @@ _PI = 3.14159265358979323846264338327950288
 INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=math.log, acos=math.acos,
                   abs=abs, max=max, min=min, real=lambda x, kind=None: float(x), int=_elementwise(int), DP=8,
                   any=lambda a: any(a.data), all=lambda a: all(a.data), shape=lambda a: FA(len(a.shape), data=list(a.shape)),
-                  cross_product=_cross_product,
+                  cross_product=_cross_product, maxval=lambda a: max(a.data) if len(a.data) else -2147483648,
                   PAIR_INDEX=_pair_index,
                   PAIR_INDEX_NS=lambda i, j, maxval: j + (i - 1) * maxval,                      # macros.inc:139
                   TRIPLET_INDEX_NS=lambda i, j, k, maxval: k + maxval * (j - 1 + maxval * (i - 1)),  # macros.inc:146
@@ -264,7 +264,7 @@ def expand_macros(line, macros):
     for _ in range(30):
         changed = False
         for name, (params, body) in macros.items():
-            for m in re.finditer(r'(?<![\w%%])%s\b' % name, line):
+            for m in re.finditer(r'(?<!\w)%s\b' % name, line):        # token replacement, also after %% (as cpp does)
                 if params is None:
                     line = line[:m.start()] + body + line[m.end():]
                 else:
@@ -563,14 +563,16 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
         if m:
             emit('raise RuntimeError(%r)' % m.group(1))
             continue
-        m = re.fullmatch(r'call\s+(\w+)\s*\((.*)\)', stmt, re.I)
+        m = re.fullmatch(r'call\s+(\w+)\s*(?:\((.*)\))?', stmt, re.I)
+        if m and sigs.get(m.group(1), 0) is None:
+            continue                                  # logging / timers: declared as no-ops by the test
         if m:
             name = m.group(1)
             if name not in sigs:
                 raise NotImplementedError('call of an unknown unit: ' + stmt)
             dummies, pure_out, outs = sigs[name]
             pairs = []                                     # (dummy, actual), keyword arguments matched by name
-            for pos, a in enumerate(a.strip() for a in _split_top(m.group(2), ',')):
+            for pos, a in enumerate(a.strip() for a in _split_top(m.group(2) or '', ',') if a.strip()):
                 kw = re.fullmatch(r'(\w+)\s*=(?!=)\s*(.+)', a)
                 if kw and kw.group(1) in dummies:
                     pairs.append((kw.group(1), kw.group(2)))
@@ -624,7 +626,7 @@ def _signature(lines, k):
                 local_arrays=local_arrays, optional=optional)
 
 
-def units(text, defined=(), env=None, macros=None):
+def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
     """{name: python callable} for every subroutine / function of a source text.  A subroutine returns the dict
     of its intent(out) / intent(inout) arguments, a function its result.  env: extra names (constants, Python
     callables; a callable that is CALLed needs .fortran_args = (dummy names, names of the intent(out) ones) and
@@ -647,15 +649,18 @@ def units(text, defined=(), env=None, macros=None):
             sigs[name] = (list(d), set(po), list(po))
     for sig in found:
         sigs[sig['name']] = (sig['args'], sig['pure_out'], sig['outs'])
+    for name in noops:
+        sigs[name] = None
     sources = {}
     for sig in found:
         name = sig['name']
         pyargs = [PY_KEYWORDS.get(a, a) + ('=None' if a in sig['optional'] else '')
                   for a in sig['args'] if a not in sig['pure_out']]                       # intent(out): results only
         src = ['def %s(%s):' % (name, ', '.join(pyargs))] + ['    %s = Obj()' % o for o in sig['objects']]
-        arrays = [b for b, _ in sig['local_arrays']]
+        arrays = [b for b, _ in sig['local_arrays']] + list(global_arrays)
         # an intent(out) scalar a branch never assigns is undefined in Fortran: None here
         src += ['    %s = None' % o for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]
+        locals_only = [b for b, _ in sig['local_arrays']]
         try:
             for b, dims in sig['local_arrays']:
                 if dims is None:
@@ -697,7 +702,12 @@ def run_fragment(text, first, last, env, defined=(), arrays=(), macros=None):
     lines = preprocess(text, defined, macros)
     a = next(k for k, s in enumerate(lines) if re.search(first, s))
     b = next(k for k in range(a, len(lines)) if re.search(last, lines[k]))
-    src = statements(lines[a:b + 1], 0, (), None, arrays)
+    sigs = {}
+    for name, fn in env.items():
+        if hasattr(fn, 'fortran_args'):
+            d, po = fn.fortran_args
+            sigs[name] = (list(d), set(po), list(po))
+    src = statements(lines[a:b + 1], 0, (), sigs, arrays)
     scope = dict(INTRINSICS)
     scope.update(env)
     exec('\n'.join(src), scope)

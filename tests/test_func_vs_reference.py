@@ -570,3 +570,124 @@ def test_neighbor_list_executed(case):
     real = neighbors != 0                                          # terminator slots carry no shift
     assert np.array_equal(dc[real], np.asarray(nl.dc)[:n][real]), name
     assert int(np.count_nonzero(real)) == nl.npairs
+
+
+# ---- the bond-order kernel itself: bop_kernel.f90 (unscreened build) -----------------------------------------
+
+def _bop_kernel(kind):
+    """bop_kernel.f90 as tersoff.f90 / kumagai.f90 / brenner.f90 compile it for the Python host: cpp conditionals for
+    PYTHON without SCREENING / LAMMPS / _OPENMP, the macros of macros.inc, filter.inc and of the file itself
+    expanded, the functions of <kind>_func.f90 and default_cutoff.f90 called"""
+    from fortran_subset import load_macros
+    name = kind.lower()
+    src = open(BOP + '/bop_kernel.f90').read()
+    macros = _reference_macros({'PYTHON'})
+    macros.update(load_macros(src, {'PYTHON'}))
+    macros.update({'BOP_KERNEL': (None, name + '_kernel'), 'BOP_TYPE': (None, name + '_t'),
+                   'BOP_NAME_STR': (None, '"%s"' % name)})
+    cut = units(open('/root/reference/src/support/cutoff.f90').read())
+    funcs = units(open('%s/%s/%s_func.f90' % (BOP, name, name)).read())
+    fcin = units(open(BOP + '/default_cutoff.f90').read(), env=dict(fc=cut['trig_off_f']))['fCin']
+    assert callable(fcin), fcin
+    return macros, cut, funcs, fcin, src
+
+
+def _run_bop_kernel(kind, db, a, mask=None):
+    from fortran_subset import FA
+    macros, cut, funcs, fcin, src = _bop_kernel(kind)
+    nat = len(a)
+    dbc = P.complete(kind, db)
+    nel = len(dbc['el'])
+    npairs = nel * (nel + 1) // 2
+    this = Obj(db=_db(dbc), it=0, neighbor_list_allocated=False, neb=None, nbb=None, dcell=None, bndtyp=None,
+               bndlen=None, bndnm=None, cutfcnar=None, cutdrvar=None, cut_in=FA(npairs, data=[None] * npairs),
+               cut_in_l=FA(npairs), cut_in_h=FA(npairs), cut_in_h2=FA(npairs))
+    if kind == 'Brenner':
+        this = _brenner_this(dbc, BOP + '/brenner/brenner_module.f90', npairs)
+        this.__dict__.update(it=0, neighbor_list_allocated=False, neb=None, nbb=None, dcell=None, bndtyp=None,
+                             bndlen=None, bndnm=None, cutfcnar=None, cutdrvar=None,
+                             cut_in=FA(npairs, data=[None] * npairs), cut_in_l=FA(npairs), cut_in_h=FA(npairs),
+                             cut_in_h2=FA(npairs))
+    bind = open(BOP + '/default_bind_to_func.f90').read()
+    for i in range(1, npairs + 1):                    # default_bind_to_func.f90:87-92
+        run_fragment(bind, r'call init\(this%cut_in\(i\)', r'this%cut_in_h2\(i\)\s*=',
+                     dict(this=this, i=i, init=cut['trig_off_init']))
+    present = [dbc['el'].index(s) for s in set(a.symbols) if s in dbc['el']]
+    cutoff = max(dbc['r2'][P.pair_index(i, j, nel)] for i in present for j in present)
+    p, fnl, nl = _particles_and_list(a, cutoff)
+    el = [dbc['el'].index(s) + 1 if s in dbc['el'] else -1 for s in a.symbols]
+    d = [int(nl.last[i] - nl.seed[i] + 1) for i in range(nat)]               # default_compute_func.f90:62-72
+    nebmax, nebavg = max(d), (sum(d) + 1) // max(nat, 1) + 1
+    tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+    env = dict(VA=funcs['VA'], VR=funcs['VR'], g=funcs['g'], bo=funcs['bo'], h=funcs['h'], Z2pair=funcs['Z2pair'],
+               fCin=fcin, tls_init=tls_init, tls_reduce=tls_reduce, **tls)
+    kern = units(src, defined={'PYTHON'}, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
+                 noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))[kind.lower() + '_kernel']
+    assert callable(kern), kern
+    ptrmax = len(nl.neighbors)
+    f, epa, epb = FA(3, nat), FA(nat), FA(ptrmax)
+    fpb, wpa, wpb = FA(3, ptrmax), FA(3, 3, nat), FA(3, 3, ptrmax)
+    r = kern(this, p.Abox, nat, nat, nat, p.r_non_cyc, F1(el), nebmax, nebavg, fnl.seed, fnl.last, fnl.neighbors, ptrmax,
+             fnl.dc, 0.0, f, FA(3, 3), None if mask is None else F1([int(m) for m in mask]), epa, epb, fpb, wpa, wpb)
+    out = dict(epot=r['epot'], f=np.asarray(list(f)).reshape(nat, 3), wpot=np.asarray(list(r['wpot_inout'])).reshape(3, 3).T,
+               epot_per_at=np.asarray(list(epa)), epot_per_bond=np.asarray(list(epb)),
+               f_per_bond=np.asarray(list(fpb)).reshape(ptrmax, 3),
+               wpot_per_at=np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1),
+               wpot_per_bond=np.asarray(list(wpb)).reshape(ptrmax, 3, 3).transpose(0, 2, 1))
+    okind = dict(Tersoff=oracle.TERSOFF, Kumagai=oracle.KUMAGAI, Brenner=oracle.BRENNER)[kind]
+    o = oracle.bop_energy_and_forces(oracle.bop_params(okind, dbc), a.positions, a.cell, nl, np.asarray(el, np.int32),
+                                     mask=mask, per_at=True, per_bond=True)
+    return out, o, kern
+
+
+def _bop_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('Si', 5.43, (2, 2, 2)); a.rattle(0.12, seed=1)
+    yield 'Tersoff', P.Tersoff_PRB_39_5566_Si_C, a
+    a = S_.b3(['Si', 'C'], 4.36, (2, 2, 2)); a.rattle(0.1, seed=2)
+    yield 'Tersoff', P.Tersoff_PRB_39_5566_Si_C, a
+    a = S_.diamond('Si', 5.43, (2, 2, 2)); a.rattle(0.12, seed=3)
+    yield 'Kumagai', P.Kumagai_CompMaterSci_39_457_Si, a
+    a = S_.b3(['Si', 'C'], 4.36, (2, 2, 2)); a.rattle(0.1, seed=4)
+    yield 'Brenner', P.Erhart_PRB_71_035211_SiC, a
+    a = S_.diamond('C', 3.57, (2, 2, 2)); a.rattle(0.08, seed=5)
+    yield 'Brenner', P.Brenner_PRB_42_9458_C_II, a
+
+
+@pytest.mark.parametrize('case', range(5))
+def test_bop_kernel_executed(case):
+    """bop_kernel.f90 executed statement by statement (both loops: the internal bond list with its cutoff
+    functions, then energies, forces, virials with the three-body derivatives) for Tersoff, Kumagai and Brenner:
+    every output of the oracle's orc_bop_energy_and_forces -- energy, forces, virial, per-atom and per-bond
+    energies / forces / virials, with and without a mask -- at rounding level"""
+    kind, db, a = list(_bop_cases())[case]
+    nat = len(a)
+    rng = np.random.RandomState(case)
+    for mask in (None, (rng.rand(nat) > 0.4).astype(np.int32)):
+        out, o, kern = _run_bop_kernel(kind, db, a, mask)
+        assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+        assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot']), (kind, out['epot'], o['epot'])
+        fs = max(1.0, np.abs(o['f']).max())
+        ws = max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+        assert np.abs(out['f'] - o['f']).max() <= 1e-12 * fs
+        assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-12 * ws
+        for key, scale in (('epot_per_at', 1.0), ('epot_per_bond', 1.0), ('f_per_bond', fs), ('wpot_per_at', ws),
+                           ('wpot_per_bond', ws)):
+            got, want = np.asarray(out[key]), np.asarray(o[key])
+            assert got.shape == want.shape, key
+            assert np.abs(want).max() > 0, key
+            assert np.abs(got - want).max() <= 1e-12 * max(scale, np.abs(want).max()), (kind, key, np.abs(got - want).max())
+    assert 'matmul(cell' in kern.python_source and 'outer_product(rij, df)' in kern.python_source

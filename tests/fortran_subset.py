@@ -102,6 +102,9 @@ class FA:
     def __rmul__(self, o): return self._zip(o, lambda a, b: b * a)
     def __truediv__(self, o): return self._zip(o, lambda a, b: a / b)
     def __neg__(self): return FA(*self.shape, data=[-a for a in self.data])
+    def __pow__(self, o): return self._zip(o, lambda a, b: a ** b)
+    def __rsub__(self, o): return self._zip(o, lambda a, b: b - a)
+    def __rtruediv__(self, o): return self._zip(o, lambda a, b: b / a)
     def __lt__(self, o): return self._zip(o, lambda a, b: a < b)
     def __gt__(self, o): return self._zip(o, lambda a, b: a > b)
     def __le__(self, o): return self._zip(o, lambda a, b: a <= b)

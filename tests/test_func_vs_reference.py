@@ -574,46 +574,60 @@ def test_neighbor_list_executed(case):
 
 # ---- the bond-order kernel itself: bop_kernel.f90 (unscreened build) -----------------------------------------
 
-def _bop_kernel(kind):
-    """bop_kernel.f90 as tersoff.f90 / kumagai.f90 / brenner.f90 compile it for the Python host: cpp conditionals for
-    PYTHON without SCREENING / LAMMPS / _OPENMP, the macros of macros.inc, filter.inc and of the file itself
-    expanded, the functions of <kind>_func.f90 and default_cutoff.f90 called"""
+def _bop_kernel(kind, screened=False):
+    """bop_kernel.f90 as tersoff.f90 / kumagai.f90 / brenner.f90 (or their *_scr.f90 twins) compile it for the Python
+    host: cpp conditionals for PYTHON [+ SCREENING] without LAMMPS / _OPENMP, the macros of macros.inc, filter.inc
+    and of the file itself expanded, the functions of <kind>_func.f90 and default_cutoff.f90 called"""
     from fortran_subset import load_macros
     name = kind.lower()
+    defined = {'PYTHON', 'SCREENING'} if screened else {'PYTHON'}
     src = open(BOP + '/bop_kernel.f90').read()
-    macros = _reference_macros({'PYTHON'})
-    macros.update(load_macros(src, {'PYTHON'}))
+    macros = _reference_macros(defined)
+    macros.update(load_macros(src, defined))
+    macros.update(load_macros(open('%s/%s/%s_type.f90' % (BOP, name, name)).read(), defined))    # cut_ar_h -> cut_out_h
     macros.update({'BOP_KERNEL': (None, name + '_kernel'), 'BOP_TYPE': (None, name + '_t'),
                    'BOP_NAME_STR': (None, '"%s"' % name)})
     cut = units(open('/root/reference/src/support/cutoff.f90').read())
-    funcs = units(open('%s/%s/%s_func.f90' % (BOP, name, name)).read())
-    fcin = units(open(BOP + '/default_cutoff.f90').read(), env=dict(fc=cut['trig_off_f']))['fCin']
-    assert callable(fcin), fcin
-    return macros, cut, funcs, fcin, src
+    # CUTOFF_T: trig_off_t in tersoff.f90, exp_cutoff_t in tersoff_scr.f90 (:46-47) and its siblings
+    cinit, cfunc = (cut['exp_cutoff_init'], cut['exp_cutoff_f']) if screened else (cut['trig_off_init'], cut['trig_off_f'])
+    funcs = units(open('%s/%s/%s_func.f90' % (BOP, name, name)).read(), defined=defined)
+    cutf = units(open(BOP + '/default_cutoff.f90').read(), defined=defined, env=dict(fc=cfunc))
+    for k in (('fCin', 'fCar', 'fCbo') if screened else ('fCin',)):
+        assert callable(cutf[k]), (k, cutf[k])
+    return defined, macros, cinit, funcs, cutf, src
 
 
-def _run_bop_kernel(kind, db, a, mask=None):
+BOP_BUFFERS = ('neb', 'nbb', 'dcell', 'bndtyp', 'bndlen', 'bndnm', 'cutfcnar', 'cutdrvar', 'cutfcnbo', 'cutdrvbo',
+               'sneb_seed', 'sneb_last', 'sneb', 'sbnd', 'sfacbo', 'cutdrarik', 'cutdrarjk', 'cutdrboik', 'cutdrbojk')
+
+
+def _run_bop_kernel(kind, db, a, mask=None, screened=False):
     from fortran_subset import FA
-    macros, cut, funcs, fcin, src = _bop_kernel(kind)
+    defined, macros, cinit, funcs, cutf, src = _bop_kernel(kind, screened)
     nat = len(a)
-    dbc = P.complete(kind, db)
+    dbc = P.complete_scr(kind, db) if screened else P.complete(kind, db)
     nel = len(dbc['el'])
     npairs = nel * (nel + 1) // 2
-    this = Obj(db=_db(dbc), it=0, neighbor_list_allocated=False, neb=None, nbb=None, dcell=None, bndtyp=None,
-               bndlen=None, bndnm=None, cutfcnar=None, cutdrvar=None, cut_in=FA(npairs, data=[None] * npairs),
-               cut_in_l=FA(npairs), cut_in_h=FA(npairs), cut_in_h2=FA(npairs))
-    if kind == 'Brenner':
-        this = _brenner_this(dbc, BOP + '/brenner/brenner_module.f90', npairs)
-        this.__dict__.update(it=0, neighbor_list_allocated=False, neb=None, nbb=None, dcell=None, bndtyp=None,
-                             bndlen=None, bndnm=None, cutfcnar=None, cutdrvar=None,
-                             cut_in=FA(npairs, data=[None] * npairs), cut_in_l=FA(npairs), cut_in_h=FA(npairs),
-                             cut_in_h2=FA(npairs))
+    this = _brenner_this(dbc, BOP + '/brenner/brenner_module.f90', npairs) if kind == 'Brenner' else Obj(db=_db(dbc))
+    this.__dict__.update(it=0, neighbor_list_allocated=False, **{k: None for k in BOP_BUFFERS})
+    for k in ('cut_in', 'cut_out', 'cut_bo'):
+        setattr(this, k, FA(npairs, data=[None] * npairs))
+    for k in ('cut_in_l', 'cut_in_h', 'cut_in_h2', 'cut_out_l', 'cut_out_h', 'cut_bo_l', 'cut_bo_h', 'max_cut_sq',
+              'Cmin', 'Cmax', 'dC', 'C_dr_cut'):
+        setattr(this, k, FA(npairs))
+    this.screening_threshold = float(np.log(1e-6))          # tersoff_type.f90:85-86: log(1d-6), 1e-10 (default real)
+    this.dot_threshold = float(np.float32(1e-10))
     bind = open(BOP + '/default_bind_to_func.f90').read()
-    for i in range(1, npairs + 1):                    # default_bind_to_func.f90:87-92
-        run_fragment(bind, r'call init\(this%cut_in\(i\)', r'this%cut_in_h2\(i\)\s*=',
-                     dict(this=this, i=i, init=cut['trig_off_init']))
-    present = [dbc['el'].index(s) for s in set(a.symbols) if s in dbc['el']]
-    cutoff = max(dbc['r2'][P.pair_index(i, j, nel)] for i in present for j in present)
+    if screened:                                             # default_bind_to_func.f90:44-69
+        run_fragment(bind, r'this%Cmin\s*=', r'endwhere', dict(this=this), defined=defined)
+    for i in range(1, npairs + 1):                           # :87-110
+        run_fragment(bind, r'call init\(this%cut_in\(i\)', r'this%max_cut_sq\(i\)\s*=' if screened else r'this%cut_in_h2\(i\)\s*=',
+                     dict(this=this, i=i, init=cinit), defined=defined)
+    if screened:
+        cutoff = P.scr_cutoff(dbc)
+    else:
+        present = [dbc['el'].index(s) for s in set(a.symbols) if s in dbc['el']]
+        cutoff = max(dbc['r2'][P.pair_index(i, j, nel)] for i in present for j in present)
     p, fnl, nl = _particles_and_list(a, cutoff)
     el = [dbc['el'].index(s) + 1 if s in dbc['el'] else -1 for s in a.symbols]
     d = [int(nl.last[i] - nl.seed[i] + 1) for i in range(nat)]               # default_compute_func.f90:62-72
@@ -633,8 +647,9 @@ def _run_bop_kernel(kind, db, a, mask=None):
         return {}
     tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
     env = dict(VA=funcs['VA'], VR=funcs['VR'], g=funcs['g'], bo=funcs['bo'], h=funcs['h'], Z2pair=funcs['Z2pair'],
-               fCin=fcin, tls_init=tls_init, tls_reduce=tls_reduce, **tls)
-    kern = units(src, defined={'PYTHON'}, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
+               tls_init=tls_init, tls_reduce=tls_reduce, **tls)
+    env.update({k: v for k, v in cutf.items() if callable(v)})
+    kern = units(src, defined=defined, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
                  noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))[kind.lower() + '_kernel']
     assert callable(kern), kern
     ptrmax = len(nl.neighbors)
@@ -649,7 +664,8 @@ def _run_bop_kernel(kind, db, a, mask=None):
                wpot_per_bond=np.asarray(list(wpb)).reshape(ptrmax, 3, 3).transpose(0, 2, 1))
     okind = dict(Tersoff=oracle.TERSOFF, Kumagai=oracle.KUMAGAI, Brenner=oracle.BRENNER)[kind]
     o = oracle.bop_energy_and_forces(oracle.bop_params(okind, dbc), a.positions, a.cell, nl, np.asarray(el, np.int32),
-                                     mask=mask, per_at=True, per_bond=True)
+                                     mask=mask, per_at=True, per_bond=True,
+                                     scr=oracle.bop_scr_params(dbc) if screened else None)
     return out, o, kern
 
 
@@ -691,3 +707,40 @@ def test_bop_kernel_executed(case):
             assert np.abs(want).max() > 0, key
             assert np.abs(got - want).max() <= 1e-12 * max(scale, np.abs(want).max()), (kind, key, np.abs(got - want).max())
     assert 'matmul(cell' in kern.python_source and 'outer_product(rij, df)' in kern.python_source
+
+
+def _bop_scr_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('Si', 5.43, (2, 2, 2)); a.rattle(0.15, seed=11)
+    yield 'Tersoff', P.Tersoff_PRB_39_5566_Si_C__Scr, a
+    a = S_.b3(['Si', 'C'], 4.36, (2, 2, 2)); a.rattle(0.12, seed=12)
+    a.cell = np.asarray(a.cell) * 1.04; a.positions *= 1.04           # stretched: bonds inside the screened region
+    yield 'Tersoff', P.Tersoff_PRB_39_5566_Si_C__Scr, a
+    a = S_.diamond('Si', 5.43, (2, 2, 2)); a.rattle(0.15, seed=13)
+    yield 'Kumagai', P.Kumagai_CompMaterSci_39_457_Si__Scr, a
+    a = S_.diamond('C', 3.57, (2, 2, 2)); a.rattle(0.12, seed=14)
+    a.cell = np.asarray(a.cell) * 1.06; a.positions *= 1.06
+    yield 'Brenner', P.Erhart_PRB_71_035211_SiC__Scr, a
+
+
+@pytest.mark.parametrize('case', range(4))
+def test_screened_bop_kernel_executed(case):
+    """the same source compiled with SCREENING (TersoffScr / KumagaiScr / BrennerScr: exp_cutoff_t switching
+    functions, Baskes screening sums with their derivative tables): every output of orc_bop_scr_energy_and_forces"""
+    kind, db, a = list(_bop_scr_cases())[case]
+    nat = len(a)
+    rng = np.random.RandomState(20 + case)
+    for mask in (None, (rng.rand(nat) > 0.4).astype(np.int32)):
+        out, o, kern = _run_bop_kernel(kind, db, a, mask, screened=True)
+        assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+        assert abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot']), (kind, out['epot'], o['epot'])
+        fs = max(1.0, np.abs(o['f']).max())
+        ws = max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+        assert np.abs(out['f'] - o['f']).max() <= 1e-11 * fs
+        assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-11 * ws
+        for key, scale in (('epot_per_at', 1.0), ('epot_per_bond', 1.0), ('f_per_bond', fs), ('wpot_per_at', ws),
+                           ('wpot_per_bond', ws)):
+            got, want = np.asarray(out[key]), np.asarray(o[key])
+            assert got.shape == want.shape, key
+            assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (kind, key, np.abs(got - want).max())
+    assert 'this.sneb' in kern.python_source and 'this.Cmax' in kern.python_source

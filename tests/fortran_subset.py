@@ -186,11 +186,21 @@ def _outer_product(x, y):
     return FA(len(x.data), len(y.data), data=[a * b for b in y.data for a in x.data])
 
 
-def _sum(a):
-    acc = 0.0
-    for x in a.data:
-        acc = acc + x
-    return acc
+def _sum(a, dim=None):
+    if dim is None:
+        acc = 0.0
+        for x in a.data:
+            acc = acc + x
+        return acc
+    assert len(a.shape) == 2 and dim == 2, (a.shape, dim)       # SUM(array, 2): over the second index, in order
+    n, m = a.shape
+    out = []
+    for i in range(n):
+        acc = 0.0
+        for j in range(m):
+            acc = acc + a.data[i + n * j]
+        out.append(acc)
+    return FA(n, data=out)
 
 
 _PI = 3.14159265358979323846264338327950288
@@ -205,7 +215,7 @@ INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=
                   lbound=lambda a, d: a.lower[d - 1], ubound=lambda a, d: a.lower[d - 1] + a.shape[d - 1] - 1, size=lambda a, d=None: len(a) if d is None else a.shape[d - 1],
                   dot_product=_dot_product, matmul=_matmul, outer_product=_outer_product, sum=_sum,
                   iand=lambda a, b: a & b, ishft=lambda a, n: a << n if n >= 0 else a >> -n,
-                  PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp,
+                  PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp, UNDEF=float('nan'),
                   _ac=lambda v: FA(len(v), data=v))
 
 PY_KEYWORDS = {'lambda': 'lambda_'}
@@ -446,11 +456,24 @@ def _lhs(target, arrays):
     return '%s = %%s' % expr(target)
 
 
+def _create(name, dims):
+    if dims is None:
+        return '%s = None' % name          # allocatable: created by ALLOCATE
+    shape, lower = [], []
+    for d in _split_top(dims, ','):
+        if ':' in d:
+            lo, hi = d.split(':')
+            lower.append(expr(lo)); shape.append('(%s)-(%s)+1' % (expr(hi), expr(lo)))
+        else:
+            lower.append('1'); shape.append(expr(d))
+    return '%s = FA(%s, lower=(%s,))' % (name, ', '.join(shape), ', '.join(lower))
+
+
 def _results(outputs):
     return 'return dict(%s)' % ', '.join('%s=%s' % (o, o) for o in outputs if o not in ERROR_ARGS)
 
 
-def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
+def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=None):
     """translate a list of executable statements; returns python source lines"""
     py, depth = [], indent
     sigs = sigs or {}
@@ -496,9 +519,15 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
             continue
         if '::' in stmt and re.match(r'(type\s*\(|integer|real|logical|character)', low):
             # named constants and initialised scalars: "real(DP), parameter :: sig = 0.5"
+            is_arg = re.search(r'\bintent\b', stmt.split('::')[0], re.I)
             for ent in _split_top(stmt.split('::', 1)[1], ','):
+                name = re.match(r'\s*(\w+)', ent).group(1)
+                if local_dims and name in local_dims:       # local arrays come to life where they are declared
+                    emit(_create(name, local_dims[name]))
+                elif local_dims is not None and not is_arg and '=' not in ent and '(' not in ent \
+                        and re.match(r'real', low):
+                    emit('%s = UNDEF' % name)               # an undefined real local: visible if it is ever used
                 if '=' in ent:
-                    name = re.match(r'\s*(\w+)', ent).group(1)
                     emit('%s = %s' % (name, expr(ent.split('=', 1)[1])))
             continue
         m = re.fullmatch(r'deallocate\s*\(([\w%]+)\)', stmt, re.I)
@@ -587,7 +616,9 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=()):
             emit('_r = %s(%s)' % (name, ', '.join(ins)))
             for d, a in pairs:
                 if d in outs:
-                    emit(_lhs(a, arrays) % ("_r['%s']" % d))
+                    # a dummy the callee never assigned leaves the actual argument as it was
+                    emit("if _r['%s'] is not None:" % d)
+                    emit('    ' + _lhs(a, arrays) % ("_r['%s']" % d))
             continue
         if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall')):
             # first '=' that is not part of ==, /=, <=, >=
@@ -665,19 +696,8 @@ def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
         src += ['    %s = None' % o for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]
         locals_only = [b for b, _ in sig['local_arrays']]
         try:
-            for b, dims in sig['local_arrays']:
-                if dims is None:
-                    src.append('    %s = None' % b)          # allocatable: created by ALLOCATE
-                    continue
-                shape, lower = [], []
-                for d in _split_top(dims, ','):
-                    if ':' in d:
-                        lo, hi = d.split(':')
-                        lower.append(expr(lo)); shape.append('(%s)-(%s)+1' % (expr(hi), expr(lo)))
-                    else:
-                        lower.append('1'); shape.append(expr(d))
-                src.append('    %s = FA(%s, lower=(%s,))' % (b, ', '.join(shape), ', '.join(lower)))
-            src += statements(sig['body'], 1, sig['outs'] if sig['kind'] == 'subroutine' else (), sigs, arrays)
+            src += statements(sig['body'], 1, sig['outs'] if sig['kind'] == 'subroutine' else (), sigs, arrays,
+                              dict(sig['local_arrays']))
             src.append('    return %s' % name if sig['kind'] == 'function' else '    ' + _results(sig['outs']))
             compile('\n'.join(src), name, 'exec')
             sources[name] = '\n'.join(src)

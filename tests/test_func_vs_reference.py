@@ -5,6 +5,7 @@ brenner_module.f90 / juslin_module.f90 lines).  This pins the oracle's functiona
 kumagai_func.f90's beta == 3 branch -- to the reference's source at rounding level, where the known-answer tests
 pin them to 1e-3.  Runs where /root/reference exists."""
 import os
+import re
 
 import numpy as np
 import pytest
@@ -744,3 +745,110 @@ def test_screened_bop_kernel_executed(case):
             assert got.shape == want.shape, key
             assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (kind, key, np.abs(got - want).max())
     assert 'this.sneb' in kern.python_source and 'this.Cmax' in kern.python_source
+
+
+# ---- the REBO2 kernel: bop_kernel_rebo2.f90 as rebo2.f90 compiles it (DIHEDRAL, NUM_NEIGHBORS) ----------------
+
+def _run_rebo2_kernel(a, with_dihedral):
+    from fortran_subset import FA, load_macros
+    defined = {'PYTHON', 'DIHEDRAL', 'NUM_NEIGHBORS'}                       # rebo2.f90:57-59
+    src = open(REBO2 + '/bop_kernel_rebo2.f90').read()
+    # "call eval(...)" is the generic of table2d_eval / table3d_eval; the compiler resolves it by the table's type
+    src = re.sub(r'call eval\(this%(P\w+)', r'call table2d_eval(this%\1', src)
+    src = re.sub(r'call eval\(this%([FT]\w+)', r'call table3d_eval(this%\1', src)
+    macros = _reference_macros(defined)
+    macros.update(load_macros(src, defined))
+    macros.update(load_macros(open(REBO2 + '/rebo2.f90').read(), defined))
+    cut = units(open('/root/reference/src/support/cutoff.f90').read())
+    t2 = units(open('/root/reference/src/special/table2d.f90').read(), env=dict(gaussn=_gaussn, npara=16, ncorn=4))
+    t3 = units(open('/root/reference/src/special/table3d.f90').read(), env=dict(gaussn=_gaussn, npara=64, ncorn=8))
+    orc = oracle.Rebo2(with_dihedral=with_dihedral)
+    this = _rebo2_this(orc)
+    this.with_dihedral = bool(with_dihedral)
+    this.spl_fCin = FA(10, data=[None] * 10)
+    for ij in (1, 3, 6):
+        this.spl_fCin[ij] = cut['trig_off_init'](this.cut_in_l(ij), this.cut_in_h(ij))['this']
+    tabs = oracle.rebo2_default_tables()
+    for name, extra in (('Fcc', ('dFdi', 'dFdj', 'dFdk')), ('Fch', ()), ('Fhh', ()), ('Tcc', ())):
+        t = Obj(coeff=None)
+        t3['table3d_init'](t, 4, 4, 9, _fa0(tabs[name]), *[_fa0(tabs[k]) for k in extra])
+        setattr(this, name, t)
+    for name in ('Pcc', 'Pch'):
+        t = Obj(coeff=None)
+        t2['table2d_init'](t, 5, 5, _fa0(tabs[name]))
+        setattr(this, name, t)
+    this.__dict__.update(it=0, neighbor_list_allocated=False, **{k: None for k in BOP_BUFFERS + ('neb_seed', 'neb_last', 'nn')})
+    funcs = units(open(REBO2 + '/rebo2_func.f90').read(), env=dict(f_and_df=cut['trig_off_f'], **REBO2_NAMES))
+    nat = len(a)
+    p, fnl, nl = _particles_and_list(a, orc.cutoff(a.symbols))
+    ktyp = orc.ktyp(a.symbols)
+    d = [int(nl.last[i] - nl.seed[i] + 1) for i in range(nat)]
+    nebmax, nebavg = max(d), (sum(d) + 1) // max(nat, 1) + 1
+    tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+    env = dict(tls_init=tls_init, tls_reduce=tls_reduce, table2d_eval=t2['table2d_eval'], table3d_eval=t3['table3d_eval'],
+               **tls, **REBO2_NAMES)
+    env.update({k: funcs[k] for k in ('fconj', 'fCin', 'VA', 'VR', 'g', 'bo', 'h', 'Z2pair')})
+    kern = units(src, defined=defined, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
+                 noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))['rebo2_kernel']
+    assert callable(kern), kern
+    ptrmax = len(nl.neighbors)
+    f, epa, epb = FA(3, nat), FA(nat), FA(ptrmax)
+    fpb, wpa, wpb = FA(3, ptrmax), FA(3, 3, nat), FA(3, 3, ptrmax)
+    r = kern(this, p.Abox, nat, nat, nat, p.r_non_cyc, F1([int(k) for k in ktyp]), nebmax, nebavg, fnl.seed, fnl.last,
+             fnl.neighbors, ptrmax, fnl.dc, 0.0, f, FA(3, 3), epa, epb, fpb, wpa, wpb)
+    out = dict(epot=r['epot'], f=np.asarray(list(f)).reshape(nat, 3), wpot=np.asarray(list(r['wpot_inout'])).reshape(3, 3).T,
+               epot_per_at=np.asarray(list(epa)), epot_per_bond=np.asarray(list(epb)),
+               f_per_bond=np.asarray(list(fpb)).reshape(ptrmax, 3),
+               wpot_per_at=np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1),
+               wpot_per_bond=np.asarray(list(wpb)).reshape(ptrmax, 3, 3).transpose(0, 2, 1))
+    o = orc.energy_and_forces(a.positions, a.cell, nl, ktyp, per_at=True, per_bond=True)
+    return out, o, kern
+
+
+def _rebo2_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('C', 3.57, (2, 2, 1)); a.rattle(0.1, seed=31)
+    yield 'diamond', a, False
+    a = S_.diamond('C', 3.7, (2, 2, 1))
+    rng = np.random.RandomState(32)
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.12, seed=33)
+    yield 'hydrocarbon solid', a, False
+    yield 'hydrocarbon solid, dihedral term', a, True
+    a = S_.diamond('C', 3.57, (2, 2, 1)); a.rattle(0.25, seed=34)            # under-coordinated sites: conjugation
+    a.cell = np.asarray(a.cell) * 1.08; a.positions *= 1.08
+    yield 'strained carbon, dihedral term', a, True
+
+
+@pytest.mark.parametrize('case', range(4))
+def test_rebo2_kernel_executed(case):
+    """bop_kernel_rebo2.f90 executed statement by statement (bond list, neighbour counts, both bond orders with the
+    P / F / T table look-ups, conjugation, the dihedral term, forces on all partners): every output of
+    orc_rebo2_energy_and_forces at rounding level"""
+    name, a, dih = list(_rebo2_cases())[case]
+    out, o, kern = _run_rebo2_kernel(a, dih)
+    assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+    assert abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot']), (name, out['epot'], o['epot'])
+    fs = max(1.0, np.abs(o['f']).max())
+    ws = max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    assert np.abs(out['f'] - o['f']).max() <= 1e-11 * fs
+    assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-11 * ws
+    for key, scale in (('epot_per_at', 1.0), ('epot_per_bond', 1.0), ('f_per_bond', fs), ('wpot_per_at', ws),
+                       ('wpot_per_bond', ws)):
+        got, want = np.asarray(out[key]), np.asarray(o[key])
+        assert got.shape == want.shape, key
+        assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (name, key, np.abs(got - want).max())

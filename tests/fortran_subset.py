@@ -482,6 +482,7 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
         py.append('    ' * depth + s)
 
     in_where = None
+    forall_masks = []
     for stmt in lines:
         stmt = re.sub(r'^\w+\s*:\s*(?=(do|if)\b)', '', stmt, flags=re.I)          # construct names
         stmt = re.sub(r'^(end\s*(?:do|if))\s+\w+$', r'\1', stmt, flags=re.I)
@@ -495,12 +496,31 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
             emit('while %s:' % expr(m.group(1))); depth += 1
             emit('pass')
             continue
-        m = re.fullmatch(r'forall\s*\(\s*(\w+)\s*=\s*(.+?)\s*:\s*(.+?)\s*\)', stmt, re.I)
-        if m:       # the bodies in the sources have no cross-iteration dependence: a DO loop
-            emit('for %s in range(%s, (%s)+1):' % (m.group(1), expr(m.group(2)), expr(m.group(3)))); depth += 1
+        m = re.match(r'forall\s*\(', stmt, re.I)
+        if m:       # the bodies in the sources have no cross-iteration dependence: a DO loop (+ IF for the mask)
+            close = _matching(stmt, m.end() - 1)
+            parts = _split_top(stmt[m.end():close], ',')
+            var, rng = parts[0].split('=', 1)
+            lo, hi = _split_top(rng, ':')
+            emit('for %s in range(%s, (%s)+1):' % (var.strip(), expr(lo), expr(hi))); depth += 1
             emit('pass')
+            rest = stmt[close + 1:].strip()
+            if len(parts) > 1:
+                assert len(parts) == 2, stmt
+                emit('if %s:' % expr(parts[1]))
+                depth += 1
+                emit('pass')
+                forall_masks.append(depth)
+            if rest:
+                py.extend(statements([rest], depth, outputs, sigs, arrays))
+                depth -= 2 if len(parts) > 1 else 1
+                if len(parts) > 1:
+                    forall_masks.pop()
             continue
         if re.fullmatch(r'end\s*forall', low):
+            if forall_masks and forall_masks[-1] == depth:
+                forall_masks.pop()
+                depth -= 1
             depth -= 1
             continue
         m = re.fullmatch(r'where\s*\((.*)\)', stmt, re.I)

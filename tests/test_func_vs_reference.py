@@ -749,25 +749,42 @@ def test_screened_bop_kernel_executed(case):
 
 # ---- the REBO2 kernel: bop_kernel_rebo2.f90 as rebo2.f90 compiles it (DIHEDRAL, NUM_NEIGHBORS) ----------------
 
-def _run_rebo2_kernel(a, with_dihedral):
-    from fortran_subset import FA, load_macros
-    defined = {'PYTHON', 'DIHEDRAL', 'NUM_NEIGHBORS'}                       # rebo2.f90:57-59
+def _run_rebo2_kernel(a, with_dihedral, screened=False):
+    from fortran_subset import FA, load_macros, preprocess
+    # rebo2.f90:57-59 / rebo2_scr.f90:60-64
+    defined = {'PYTHON', 'SCREENING', 'ALT_DIHEDRAL', 'NUM_NEIGHBORS'} if screened else {'PYTHON', 'DIHEDRAL', 'NUM_NEIGHBORS'}
+    module = REBO2 + ('/rebo2_scr.f90' if screened else '/rebo2.f90')
     src = open(REBO2 + '/bop_kernel_rebo2.f90').read()
     # "call eval(...)" is the generic of table2d_eval / table3d_eval; the compiler resolves it by the table's type
     src = re.sub(r'call eval\(this%(P\w+)', r'call table2d_eval(this%\1', src)
     src = re.sub(r'call eval\(this%([FT]\w+)', r'call table3d_eval(this%\1', src)
     macros = _reference_macros(defined)
     macros.update(load_macros(src, defined))
-    macros.update(load_macros(open(REBO2 + '/rebo2.f90').read(), defined))
+    macros.update(load_macros(open(module).read(), defined))
     cut = units(open('/root/reference/src/support/cutoff.f90').read())
     t2 = units(open('/root/reference/src/special/table2d.f90').read(), env=dict(gaussn=_gaussn, npara=16, ncorn=4))
     t3 = units(open('/root/reference/src/special/table3d.f90').read(), env=dict(gaussn=_gaussn, npara=64, ncorn=8))
-    orc = oracle.Rebo2(with_dihedral=with_dihedral)
+    orc = oracle.Rebo2Scr(with_dihedral=with_dihedral) if screened else oracle.Rebo2(with_dihedral=with_dihedral)
     this = _rebo2_this(orc)
     this.with_dihedral = bool(with_dihedral)
-    this.spl_fCin = FA(10, data=[None] * 10)
-    for ij in (1, 3, 6):
-        this.spl_fCin[ij] = cut['trig_off_init'](this.cut_in_l(ij), this.cut_in_h(ij))['this']
+    families = ('in',)
+    if screened:
+        families = ('in', 'ar', 'bo', 'nc')
+        this.__dict__.update(orc.sd)
+        this.screening_threshold, this.dot_threshold = float(np.log(1e-6)), float(np.float32(1e-10))   # rebo2_type.f90:68-69
+        for fam in ('ar', 'bo', 'nc'):
+            for k in ('l', 'h', 'h2', 'm'):
+                setattr(this, 'cut_%s_%s' % (fam, k), FA(10))
+        this.max_cut_sq = FA(10)
+        db = open(REBO2 + '/rebo2_db.f90').read()
+        run_fragment(db, r'this%dC\s*=', r'this%C_dr_cut\s*=', dict(this=this), defined=defined)          # :106-107
+        run_fragment(db, r'this%conpe\(1\)\s*=', r'this%max_cut_sq\(i\)\s*=', dict(this=this, **REBO2_NAMES),
+                     defined=defined)                                                                   # :147-250
+    for fam in families:
+        objs = FA(10, data=[None] * 10)
+        for ij in (1, 3, 6):
+            objs[ij] = cut['trig_off_init'](getattr(this, 'cut_%s_l' % fam)(ij), getattr(this, 'cut_%s_h' % fam)(ij))['this']
+        setattr(this, 'spl_fC' + fam, objs)
     tabs = oracle.rebo2_default_tables()
     for name, extra in (('Fcc', ('dFdi', 'dFdj', 'dFdk')), ('Fch', ()), ('Fhh', ()), ('Tcc', ())):
         t = Obj(coeff=None)
@@ -777,8 +794,12 @@ def _run_rebo2_kernel(a, with_dihedral):
         t = Obj(coeff=None)
         t2['table2d_init'](t, 5, 5, _fa0(tabs[name]))
         setattr(this, name, t)
-    this.__dict__.update(it=0, neighbor_list_allocated=False, **{k: None for k in BOP_BUFFERS + ('neb_seed', 'neb_last', 'nn')})
-    funcs = units(open(REBO2 + '/rebo2_func.f90').read(), env=dict(f_and_df=cut['trig_off_f'], **REBO2_NAMES))
+    # every buffer the kernel allocates starts unallocated
+    for line in preprocess(src, defined, macros):
+        for comp in re.findall(r'allocate\(this%(\w+)\(', line):
+            setattr(this, comp, None)
+    this.__dict__.update(it=0, neighbor_list_allocated=False)
+    funcs = units(open(REBO2 + '/rebo2_func.f90').read(), defined=defined, env=dict(f_and_df=cut['trig_off_f'], **REBO2_NAMES))
     nat = len(a)
     p, fnl, nl = _particles_and_list(a, orc.cutoff(a.symbols))
     ktyp = orc.ktyp(a.symbols)
@@ -800,9 +821,13 @@ def _run_rebo2_kernel(a, with_dihedral):
     tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
     env = dict(tls_init=tls_init, tls_reduce=tls_reduce, table2d_eval=t2['table2d_eval'], table3d_eval=t3['table3d_eval'],
                **tls, **REBO2_NAMES)
-    env.update({k: funcs[k] for k in ('fconj', 'fCin', 'VA', 'VR', 'g', 'bo', 'h', 'Z2pair')})
+    names = ('fconj', 'fCin', 'VA', 'VR', 'g', 'bo', 'h', 'Z2pair') + (('fCar', 'fCbo', 'fCnc') if screened else ())
+    for k in names:
+        assert callable(funcs[k]), (k, funcs[k])
+        env[k] = funcs[k]
+    kname = 'rebo2_scr_kernel' if screened else 'rebo2_kernel'
     kern = units(src, defined=defined, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
-                 noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))['rebo2_kernel']
+                 noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))[kname]
     assert callable(kern), kern
     ptrmax = len(nl.neighbors)
     f, epa, epb = FA(3, nat), FA(nat), FA(ptrmax)
@@ -852,3 +877,165 @@ def test_rebo2_kernel_executed(case):
         got, want = np.asarray(out[key]), np.asarray(o[key])
         assert got.shape == want.shape, key
         assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (name, key, np.abs(got - want).max())
+
+
+def _rebo2_scr_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('C', 3.57, (2, 2, 1)); a.rattle(0.12, seed=41)
+    yield 'diamond', a, False
+    a = S_.diamond('C', 3.57, (2, 2, 1)); a.rattle(0.2, seed=42)
+    a.cell = np.asarray(a.cell) * 1.12; a.positions *= 1.12                  # bonds between the inner and outer cutoffs
+    yield 'stretched carbon', a, False
+    yield 'stretched carbon, ALT_DIHEDRAL', a, True
+    a = S_.diamond('C', 3.7, (2, 2, 1))
+    rng = np.random.RandomState(43)
+    for i in rng.choice(len(a), len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.12, seed=44)
+    yield 'hydrocarbon solid, ALT_DIHEDRAL', a, True
+
+
+@pytest.mark.parametrize('case', range(4))
+def test_rebo2_scr_kernel_executed(case):
+    """bop_kernel_rebo2.f90 as rebo2_scr.f90 compiles it (SCREENING, ALT_DIHEDRAL, NUM_NEIGHBORS): every output of
+    orc_rebo2_scr_energy_and_forces"""
+    name, a, dih = list(_rebo2_scr_cases())[case]
+    out, o, kern = _run_rebo2_kernel(a, dih, screened=True)
+    assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+    assert abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot']), (name, out['epot'], o['epot'])
+    fs = max(1.0, np.abs(o['f']).max())
+    ws = max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    assert np.abs(out['f'] - o['f']).max() <= 1e-11 * fs
+    assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-11 * ws
+    for key, scale in (('epot_per_at', 1.0), ('epot_per_bond', 1.0), ('f_per_bond', fs), ('wpot_per_at', ws),
+                       ('wpot_per_bond', ws)):
+        got, want = np.asarray(out[key]), np.asarray(o[key])
+        assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (name, key, np.abs(got - want).max())
+
+
+# ---- Juslin / JuslinScr: juslin_module.f90 (mirroring, constants) + ../bop_kernel.f90 + juslin_func.f90 -------------
+
+JUSLIN = BOP + '/juslin'
+
+
+def _run_juslin_kernel(raw, a, mask=None, screened=False):
+    from fortran_subset import FA, load_macros, preprocess
+    import copy
+    defined = {'PYTHON', 'SCREENING', 'EXP_BOP'} if screened else {'PYTHON'}
+    module = JUSLIN + ('/juslin_scr.f90' if screened else '/juslin.f90')
+    src = open(BOP + '/bop_kernel.f90').read()
+    macros = _reference_macros(defined)
+    macros.update(load_macros(src, defined))
+    macros.update(load_macros(open(JUSLIN + '/juslin_type.f90').read(), defined))
+    macros.update(load_macros(open(module).read(), defined))
+    kname = macros['BOP_KERNEL'][1]
+    # the database as the Python host hands it over (no mirroring yet), completed from the Fortran default
+    base = P.Juslin_WCH__Scr_fortran_default if screened else P.Juslin_JAP_98_123520_WCH
+    db = copy.deepcopy(raw)
+    for k, v in base.items():
+        db.setdefault(k, list(v))
+    this = Obj(db=_db(db), Z2db=None, it=0, neighbor_list_allocated=False)
+    names = ['bo_exp', 'bo_fac', 'bo_exp1', 'expR', 'expA', 'c_sq', 'd_sq', 'c_d', 'VR_f', 'VA_f', 'cut_in_l', 'cut_in_h',
+             'cut_in_h2', 'cut_in_fca', 'cut_in_fc', 'cut_out_l', 'cut_out_h', 'cut_out_fca', 'cut_out_fc', 'cut_bo_l',
+             'cut_bo_h', 'cut_bo_fca', 'cut_bo_fc', 'max_cut_sq', 'Cmin', 'Cmax', 'dC', 'C_dr_cut']
+    for k in names:
+        setattr(this, k, FA(9))
+    this.screening_threshold, this.dot_threshold = float(np.log(1e-6)), float(np.float32(1e-10))   # juslin_type.f90:86-87
+    mod = open(JUSLIN + '/juslin_module.f90').read()
+    # BIND_TO_FUNC :272-312: the mirroring of pairs given with r0 < 0, then (SCREENING) Cmin ... C_dr_cut
+    run_fragment(mod, r'^do i = 1, this%db%nel$', r'^this%Z2db\s*=\s*0$', dict(this=this, JUSLIN_MAX_EL=3), defined=defined)
+    want = P.complete_juslin_scr(raw) if screened else P.complete_juslin(raw)
+    for key in P.JUSLIN_PAIR_KEYS + (P.SCR_KEYS if screened else ()):
+        assert list(getattr(this.db, key)) == [float(x) for x in want[key]], key
+    for i in range(1, 10):                                   # :322-343 constants, :345-373 cutoffs
+        run_fragment(mod, r'this%bo_exp\(i\)\s*=', r'this%VA_f\(i\)\s*=', dict(this=this, i=i), defined=defined)
+        run_fragment(mod, r'this%cut_in_l\(i\)\s*=', r'this%max_cut_sq\(i\)\s*=' if screened else r'this%cut_in_fc\(i\)\s*=',
+                     dict(this=this, i=i), defined=defined)
+    for line in preprocess(src, defined, macros):
+        for comp in re.findall(r'allocate\(this%(\w+)\(', line):
+            setattr(this, comp, None)
+    funcs = units(open(JUSLIN + '/juslin_func.f90').read(), defined=defined)
+    cutoff = P.juslin_scr_cutoff(want) if screened else max(want['r2'])
+    nat = len(a)
+    p, fnl, nl = _particles_and_list(a, cutoff)
+    el = [want['el'].index(s) + 1 if s in want['el'] else -1 for s in a.symbols]
+    d = [int(nl.last[i] - nl.seed[i] + 1) for i in range(nat)]
+    nebmax, nebavg = max(d), (sum(d) + 1) // max(nat, 1) + 1
+    tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+    env = dict(tls_init=tls_init, tls_reduce=tls_reduce, **tls)
+    for k in ('VA', 'VR', 'g', 'bo', 'h', 'Z2pair', 'fCin') + (('fCar', 'fCbo') if screened else ()):
+        assert callable(funcs[k]), (k, funcs[k])
+        env[k] = funcs[k]
+    kern = units(src, defined=defined, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
+                 noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))[kname]
+    assert callable(kern), kern
+    ptrmax = len(nl.neighbors)
+    f, epa, epb = FA(3, nat), FA(nat), FA(ptrmax)
+    fpb, wpa, wpb = FA(3, ptrmax), FA(3, 3, nat), FA(3, 3, ptrmax)
+    r = kern(this, p.Abox, nat, nat, nat, p.r_non_cyc, F1(el), nebmax, nebavg, fnl.seed, fnl.last, fnl.neighbors, ptrmax,
+             fnl.dc, 0.0, f, FA(3, 3), None if mask is None else F1([int(m) for m in mask]), epa, epb, fpb, wpa, wpb)
+    out = dict(epot=r['epot'], f=np.asarray(list(f)).reshape(nat, 3), wpot=np.asarray(list(r['wpot_inout'])).reshape(3, 3).T,
+               epot_per_at=np.asarray(list(epa)), epot_per_bond=np.asarray(list(epb)),
+               f_per_bond=np.asarray(list(fpb)).reshape(ptrmax, 3),
+               wpot_per_at=np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1),
+               wpot_per_bond=np.asarray(list(wpb)).reshape(ptrmax, 3, 3).transpose(0, 2, 1))
+    o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.JUSLIN, want), a.positions, a.cell, nl, np.asarray(el, np.int32),
+                                     mask=mask, per_at=True, per_bond=True,
+                                     scr=oracle.bop_scr_params(want) if screened else None)
+    return out, o
+
+
+def _juslin_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.b1(['W', 'C'], 4.38, (2, 2, 1))
+    for i in (3, 9):
+        a.symbols[i] = 'H'
+    a.rattle(0.1, seed=51)
+    yield 'W-C-H', P.Juslin_JAP_98_123520_WCH, a, False
+    a = S_.bcc('Fe', 2.87, (2, 2, 2))
+    a.symbols[0] = 'C'; a.symbols[5] = 'H'
+    a.rattle(0.1, seed=52)
+    yield 'Fe-C-H', P.Kuopanportti_CMS_111_525_FeCH, a, False
+    a = S_.b1(['W', 'C'], 4.38, (2, 2, 1))
+    for i in (3, 9):
+        a.symbols[i] = 'H'
+    a.rattle(0.12, seed=53)
+    yield 'W-C-H screened (the Python module set: Cmin / Cmax repeat r1 / r2)', P.Juslin_JAP_98_123520_WCH__Scr, a, True
+    a = S_.bcc('Fe', 2.87, (2, 2, 2))
+    a.symbols[0] = 'C'; a.symbols[5] = 'H'
+    a.rattle(0.12, seed=54)
+    yield 'Fe-C-H screened', P.Kuopanportti_CMS_111_525_FeCH__Scr, a, True
+
+
+@pytest.mark.parametrize('case', range(4))
+def test_juslin_kernel_executed(case):
+    """Juslin (W-C-H, Fe-C-H) and JuslinScr: the mirroring and constants of juslin_module.f90's BIND_TO_FUNC, then
+    bop_kernel.f90 with juslin_func.f90 (non-symmetric pair index, triplet-indexed h), all executed"""
+    name, raw, a, screened = list(_juslin_cases())[case]
+    nat = len(a)
+    rng = np.random.RandomState(50 + case)
+    for mask in (None, (rng.rand(nat) > 0.4).astype(np.int32)):
+        out, o = _run_juslin_kernel(raw, a, mask, screened)
+        assert abs(o['epot']) > 5.0 and np.abs(o['f']).max() > 0.1
+        assert abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot']), (name, out['epot'], o['epot'])
+        fs = max(1.0, np.abs(o['f']).max())
+        ws = max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+        assert np.abs(out['f'] - o['f']).max() <= 1e-11 * fs
+        assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-11 * ws
+        for key, scale in (('epot_per_at', 1.0), ('epot_per_bond', 1.0), ('f_per_bond', fs), ('wpot_per_at', ws),
+                           ('wpot_per_bond', ws)):
+            got, want = np.asarray(out[key]), np.asarray(o[key])
+            assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (name, key, np.abs(got - want).max())

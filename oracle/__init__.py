@@ -6,9 +6,13 @@ __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package; the product package `atomistica_b200` never does.
 
 Parity status: the Fortran reference cannot be built in the build container
-(no Fortran compiler), so there is no oracle/_ref.  The oracle is pinned by the
-reference's own known-answer tests instead (tests/test_oracle_kat.py against
-tests/golden/kat.json).
+(no Fortran compiler), so there is no oracle/_ref.  The oracle is pinned (1) by the
+reference's own known-answer tests (tests/test_oracle_kat.py against
+tests/golden/kat.json) and (2) by the reference's own Fortran kernels EXECUTED next to
+it through a Fortran-subset translator (tests/test_func_vs_reference.py: neighbour lists
+equal entry by entry; energies, forces, virials, per-atom and per-bond outputs of the
+EAM, Tersoff / Kumagai / Brenner (plain and screened), Juslin and REBO2 / Rebo2Scr
+kernels at <= 1e-12) -- not by output of a compiled reference binary.
 """
 import ctypes as C
 import os

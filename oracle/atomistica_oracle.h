@@ -10,7 +10,10 @@
  * Parity status: the Fortran reference cannot be compiled in the build
  * container (no Fortran compiler), so this oracle is pinned against the
  * reference's own known-answer tests (tests/golden/kat.json, generated from
- * /root/reference/tests/*.py) rather than against raw reference output.
+ * /root/reference/tests/*.py) and against the reference's Fortran kernels
+ * executed statement by statement through tests/fortran_subset.py
+ * (tests/test_func_vs_reference.py) rather than against output of a compiled
+ * reference binary.
  *
  * Array conventions are the Fortran host's: r(3,nat) contiguous per atom,
  * Abox(3,3) column-major (columns are the cell vectors), 1-based atom indices

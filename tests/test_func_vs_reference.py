@@ -307,7 +307,7 @@ def test_simple_spline_init_and_evaluation(cu_setfl):
     funcs = units(open('/root/reference/src/support/simple_spline.f90').read())
     init, fdf = funcs['simple_spline_init'], funcs['simple_spline_f_and_df']
     assert callable(init) and callable(fdf), (init, fdf)
-    t = cu_setfl
+
     rng = np.random.RandomState(2)
     pad = np.zeros(2)          # tabulated_alloy_eam.f90 pads the r tables with two zeros (simple_spline_read)
     for name, y, x0, dx in (('F', t['F'][0], 0.0, t['dF']), ('rho', np.concatenate([t['rho'][0], pad]), 0.0, t['dr']),
@@ -433,10 +433,8 @@ def _particles_and_list(a, cutoff):
     return p, fnl, nl
 
 
-def test_eam_kernel_executed(cu_setfl):
-    """The reference's EAM kernel, statement by statement (macros of macros.inc / filter.inc expanded, simple_spline
-    routines from simple_spline.f90), on rattled fcc Cu with the reference's Cu_mishin1 tables: energy, forces,
-    virial, per-atom energies and virials, and a mask, against the oracle's orc_eam_energy_and_forces"""
+def run_eam_kernel_cases(t):
+    """the reference's EAM kernel on rattled fcc Cu, without and with a mask: yields (outputs, atoms, mask)"""
     from fortran_subset import FA
     from atomistica_b200 import structures as S_
     macros = _reference_macros({'PYTHON'})
@@ -444,7 +442,7 @@ def test_eam_kernel_executed(cu_setfl):
     for k in ('simple_spline_init', 'simple_spline_f', 'simple_spline_df', 'simple_spline_f_and_df',
               'simple_spline_scale_y_axis'):
         assert callable(spl[k]), (k, spl[k])
-    t = cu_setfl
+
     pad = [0.0, 0.0]
     nr, dr, nF, dF = int(t['nr']), float(t['dr']), int(t['nF']), float(t['dF'])
     fF = spl['simple_spline_init'](nF, 0.0, dF, FA(nF, data=t['F'][0].tolist()))['this']
@@ -480,22 +478,34 @@ def test_eam_kernel_executed(cu_setfl):
     assert callable(kern), kern
     assert 'matmul(p.Abox' in kern.python_source and 'iand(els' in kern.python_source       # the macros expanded
 
-    orc = oracle.EAM(t)
-    eldb = orc.eldb(a.symbols)
     rng = np.random.RandomState(8)
     for mask in (None, (rng.rand(nat) > 0.4).astype(np.int32)):
         f, epa, wpa = FA(3, nat), FA(nat), FA(3, 3, nat)
         r = kern(this, p, fnl, 0.0, f, FA(3, 3), 200, None if mask is None else F1([int(m) for m in mask]), epa, wpa)
-        o = orc.energy_and_forces(a.positions, a.cell, nl, eldb, mask=mask, per_at=True)
+        yield dict(epot=r['epot'], f=np.asarray(list(f)).reshape(nat, 3),
+                   wpot=np.asarray(list(r['wpot'])).reshape(3, 3).T,                   # column-major (3,3) -> [a][b]
+                   epot_per_at=np.asarray(list(epa)),
+                   wpot_per_at=np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1)), a, mask
+
+
+def test_eam_kernel_executed(cu_setfl):
+    """The reference's EAM kernel, statement by statement (macros of macros.inc / filter.inc expanded, simple_spline
+    routines from simple_spline.f90), on rattled fcc Cu with the reference's Cu_mishin1 tables: energy, forces,
+    virial, per-atom energies and virials, and a mask, against the oracle's orc_eam_energy_and_forces"""
+    orc = oracle.EAM(cu_setfl)
+    n = 0
+    for out, a, mask in run_eam_kernel_cases(cu_setfl):
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, orc.cutoff, 200)
+        o = orc.energy_and_forces(a.positions, a.cell, nl, orc.eldb(a.symbols), mask=mask, per_at=True)
         scale = max(1.0, np.abs(o['f']).max())
-        assert abs(r['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
-        assert np.abs(np.asarray(list(f)).reshape(nat, 3) - o['f']).max() <= 1e-13 * scale
-        wref = np.asarray(list(r['wpot'])).reshape(3, 3).T                 # column-major (3,3) -> [a][b]
-        assert np.abs(wref - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max())
-        assert np.abs(np.asarray(list(epa)) - o['epot_per_at']).max() <= 1e-13 * np.abs(o['epot_per_at']).max()
-        wpa_ref = np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1)
-        assert np.abs(wpa_ref - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())
+        assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
+        assert np.abs(out['f'] - o['f']).max() <= 1e-13 * scale
+        assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max())
+        assert np.abs(out['epot_per_at'] - o['epot_per_at']).max() <= 1e-13 * np.abs(o['epot_per_at']).max()
+        assert np.abs(out['wpot_per_at'] - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())
         assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+        n += 1
+    assert n == 2
 
 
 # ---- the neighbour list: python_neighbors.f90:570-959 (binning_init, binning_update, fill_neighbor_list) ---------

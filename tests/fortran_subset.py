@@ -218,7 +218,11 @@ INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=
                   PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp, UNDEF=float('nan'),
                   _ac=lambda v: FA(len(v), data=v))
 
-PY_KEYWORDS = {'lambda': 'lambda_'}
+PY_KEYWORDS = {'lambda': 'lambda_', 'for': 'for_', 'in': 'in_', 'is': 'is_', 'del': 'del_', 'pass': 'pass_'}
+
+
+def _py(name):
+    return PY_KEYWORDS.get(name, name)
 ERROR_ARGS = ('error', 'ierror')
 
 
@@ -470,7 +474,7 @@ def _create(name, dims):
 
 
 def _results(outputs):
-    return 'return dict(%s)' % ', '.join('%s=%s' % (o, o) for o in outputs if o not in ERROR_ARGS)
+    return 'return dict(%s)' % ', '.join('%s=%s' % (_py(o), _py(o)) for o in outputs if o not in ERROR_ARGS)
 
 
 def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=None):
@@ -546,9 +550,9 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
                     emit(_create(name, local_dims[name]))
                 elif local_dims is not None and not is_arg and '=' not in ent and '(' not in ent \
                         and re.match(r'real', low):
-                    emit('%s = UNDEF' % name)               # an undefined real local: visible if it is ever used
+                    emit('%s = UNDEF' % _py(name))          # an undefined real local: visible if it is ever used
                 if '=' in ent:
-                    emit('%s = %s' % (name, expr(ent.split('=', 1)[1])))
+                    emit('%s = %s' % (_py(name), expr(ent.split('=', 1)[1])))
             continue
         m = re.fullmatch(r'deallocate\s*\(([\w%]+)\)', stmt, re.I)
         if m:
@@ -637,8 +641,8 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
             for d, a in pairs:
                 if d in outs:
                     # a dummy the callee never assigned leaves the actual argument as it was
-                    emit("if _r['%s'] is not None:" % d)
-                    emit('    ' + _lhs(a, arrays) % ("_r['%s']" % d))
+                    emit("if _r['%s'] is not None:" % _py(d))
+                    emit('    ' + _lhs(a, arrays) % ("_r['%s']" % _py(d)))
             continue
         if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall')):
             # first '=' that is not part of ==, /=, <=, >=
@@ -713,7 +717,7 @@ def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
         src = ['def %s(%s):' % (name, ', '.join(pyargs))] + ['    %s = Obj()' % o for o in sig['objects']]
         arrays = [b for b, _ in sig['local_arrays']] + list(global_arrays)
         # an intent(out) scalar a branch never assigns is undefined in Fortran: None here
-        src += ['    %s = None' % o for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]
+        src += ['    %s = None' % _py(o) for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]
         locals_only = [b for b, _ in sig['local_arrays']]
         try:
             src += statements(sig['body'], 1, sig['outs'] if sig['kind'] == 'subroutine' else (), sigs, arrays,

@@ -1049,3 +1049,89 @@ def test_juslin_kernel_executed(case):
                            ('wpot_per_bond', ws)):
             got, want = np.asarray(out[key]), np.asarray(o[key])
             assert np.abs(got - want).max() <= 1e-11 * max(scale, np.abs(want).max()), (name, key, np.abs(got - want).max())
+
+
+# ---- pair styles: src/potentials/pair_potentials/*.f90 (each with its own traversal and weighting conventions) ----
+
+PAIRS = '/root/reference/src/potentials/pair_potentials'
+
+
+def _pair_cases():
+    from atomistica_b200 import structures as S_
+    a = S_.b1(['Na', 'Cl'], 5.6, (2, 2, 1)); a.rattle(0.15, seed=61)
+    two = a
+    one = S_.fcc('Cu', 3.615, (2, 2, 1)); one.rattle(0.1, seed=62)
+    #      file,             oracle kind,                  this fields,                               par,        cutoff, shift, el1, el2, mask?
+    yield 'lj_cut', oracle.PAIR_LJCUT, dict(epsilon=0.05, sigma=2.3), [0.05, 2.3], 4.0, True, '*', '*', one, True
+    yield 'lj_cut', oracle.PAIR_LJCUT, dict(epsilon=0.02, sigma=2.6), [0.02, 2.6], 4.5, False, 'Na', 'Cl', two, True
+    yield 'harmonic', oracle.PAIR_HARMONIC, dict(k=1.3, r0=2.5), [1.3, 2.5], 3.1, True, '*', '*', one, False
+    yield 'harmonic', oracle.PAIR_HARMONIC, dict(k=0.7, r0=2.8), [0.7, 2.8], 3.4, False, 'Na', 'Cl', two, False
+    yield ('double_harmonic', oracle.PAIR_DOUBLE_HARMONIC, dict(k1=1.0, r1=2.55, k2=0.4, r2=3.6), [1.0, 2.55, 0.4, 3.6],
+           4.0, False, '*', '*', one, False)
+    yield 'r6', oracle.PAIR_R6, dict(A=35.0, r0=0.8), [35.0, 0.8], 4.2, False, 'Na', 'Na', two, False
+    yield 'born_mayer', oracle.PAIR_BORN_MAYER, dict(A=900.0, rho=0.32), [900.0, 0.32], 4.0, False, 'Na', 'Cl', two, False
+
+
+@pytest.mark.parametrize('case', range(7))
+def test_pair_styles_executed(case):
+    """lj_cut.f90, harmonic.f90, double_harmonic.f90, r6.f90, born_mayer.f90: <name>_energy_and_forces executed (the
+    shift offsets by the statements of <name>_bind_to) against orc_pair_energy_and_forces -- element filters, masks
+    (LJCut), the i <= j / i > j / every-entry traversals and the per-atom conventions each file has"""
+    from fortran_subset import FA
+    name, kind, fields, par, cutoff, shift, e1, e2, a, with_mask = list(_pair_cases())[case]
+    text = open('%s/%s.f90' % (PAIRS, name)).read()
+    macros = _reference_macros({'PYTHON'})
+    nat = len(a)
+    p, fnl, nl = _particles_and_list(a, cutoff)
+    el, order = oracle.element_ids(a.symbols)
+    p.el = F1([int(x) for x in el]); p.maxnatloc = nat; p.nel = len(order)
+    fnl.neighbors_size = len(nl.neighbors)
+    this = Obj(cutoff=float(cutoff), shift=bool(shift), offset=0.0, el1=oracle.element_filter(e1, order),
+               el2=oracle.element_filter(e2, order), **fields)
+    if name in ('lj_cut', 'harmonic'):
+        run_fragment(text, r'this%offset\s*=\s*0', r'^endif$', dict(this=this), defined={'PYTHON'}, macros=macros)
+        assert (this.offset != 0.0) == bool(shift)
+    if name == 'born_mayer':                      # born_mayer.f90:176: always shifted to zero at the cutoff
+        run_fragment(text, r'this%shift\s*=', r'this%shift\s*=', dict(this=this), defined={'PYTHON'}, macros=macros)
+        assert this.shift > 0.0
+    if name == 'double_harmonic' and 'rm' in re.findall(r'this%(\w+)', text):
+        run_fragment(text, r'this%rm\s*=', r'this%rm\s*=', dict(this=this), defined={'PYTHON'}, macros=macros)
+    tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+    fn = units(text, defined={'PYTHON'}, env=dict(tls_init=tls_init, tls_reduce=tls_reduce, **tls), macros=macros,
+               global_arrays=('tls_sca1', 'tls_vec1'),
+               noops=('timer_start', 'timer_stop', 'update', 'prlog', 'filter_prlog'))[name + '_energy_and_forces']
+    assert callable(fn), fn
+    rng = np.random.RandomState(60 + case)
+    for mask in ((None, (rng.rand(nat) > 0.4).astype(np.int32)) if with_mask else (None,)):
+        f, epa, wpa = FA(3, nat), FA(nat), FA(3, 3, nat)
+        if name == 'lj_cut':
+            r = fn(this, p, fnl, 0.0, f, FA(3, 3), None if mask is None else F1([int(m) for m in mask]), epa, wpa)
+        elif name == 'born_mayer':
+            r = fn(this, p, fnl, 0.0, f, FA(3, 3))
+        else:
+            r = fn(this, p, fnl, 0.0, f, FA(3, 3), epa, wpa)
+        o = oracle.pair_energy_and_forces(kind, par + [cutoff], a.positions, a.cell, nl, a.symbols, el1=e1, el2=e2,
+                                          shift=shift, mask=mask, per_at=(name != 'born_mayer'))
+        assert abs(o['epot']) > 1e-3
+        assert abs(r['epot'] - o['epot']) <= 1e-12 * abs(o['epot']), (name, r['epot'], o['epot'])
+        got_f = np.asarray(list(f)).reshape(nat, 3)
+        assert np.abs(got_f - o['f']).max() <= 1e-12 * max(1.0, np.abs(o['f']).max())
+        if name != 'born_mayer':                       # born_mayer.f90 never touches wpot or the per-atom outputs
+            w = np.asarray(list(r['wpot'])).reshape(3, 3).T
+            assert np.abs(w - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max())
+            assert np.abs(np.asarray(list(epa)) - o['epot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['epot_per_at']).max())
+            got = np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1)
+            assert np.abs(got - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())

@@ -49,7 +49,11 @@ class FA:
         assert len(idx) == len(self.shape), (idx, self.shape)
         offs, stride, shape = [0], 1, []
         for i, n, lo in zip(idx, self.shape, self.lower):
-            if isinstance(i, S):
+            if isinstance(i, FA):                      # vector subscript
+                assert all(lo <= int(v) <= lo + n - 1 for v in i.data), (i.data, self.shape)
+                r = [int(v) - lo for v in i.data]
+                shape.append(len(r))
+            elif isinstance(i, S):
                 a = lo if i.lo is None else i.lo
                 b = lo + n - 1 if i.hi is None else i.hi
                 assert b < a or (lo <= a and b <= lo + n - 1), (a, b, self.shape, self.lower)
@@ -60,7 +64,7 @@ class FA:
                 r = range(i - lo, i - lo + 1)
             offs = [o + k * stride for k in r for o in offs]
             stride *= n
-        return offs, (shape if any(isinstance(i, S) for i in idx) else None)
+        return offs, (shape if any(isinstance(i, (S, FA)) for i in idx) else None)
 
     def __call__(self, *idx):
         offs, shape = self._select(idx)
@@ -186,6 +190,15 @@ def _outer_product(x, y):
     return FA(len(x.data), len(y.data), data=[a * b for b in y.data for a in x.data])
 
 
+def _spread(v, dim, ncopies):
+    """SPREAD of a vector: dim=1 -> (ncopies, n) with v along the second index; dim=2 -> (n, ncopies)"""
+    n = len(v.data)
+    if dim == 1:
+        return FA(ncopies, n, data=[x for x in v.data for _ in range(ncopies)])
+    assert dim == 2
+    return FA(n, ncopies, data=list(v.data) * ncopies)
+
+
 def _sum(a, dim=None):
     if dim is None:
         acc = 0.0
@@ -213,7 +226,7 @@ INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=
                   TRIPLET_INDEX_NS=lambda i, j, k, maxval: k + maxval * (j - 1 + maxval * (i - 1)),  # macros.inc:146
                   floor=_elementwise(math.floor), present=lambda x: x is not None, allocated=lambda x: x is not None,
                   lbound=lambda a, d: a.lower[d - 1], ubound=lambda a, d: a.lower[d - 1] + a.shape[d - 1] - 1, size=lambda a, d=None: len(a) if d is None else a.shape[d - 1],
-                  dot_product=_dot_product, matmul=_matmul, outer_product=_outer_product, sum=_sum,
+                  dot_product=_dot_product, matmul=_matmul, spread=_spread, outer_product=_outer_product, sum=_sum,
                   iand=lambda a, b: a & b, ishft=lambda a, n: a << n if n >= 0 else a >> -n,
                   PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp, UNDEF=float('nan'),
                   _ac=lambda v: FA(len(v), data=v))
@@ -297,6 +310,7 @@ def expand_macros(line, macros):
                     # simultaneous substitution of the parameters (whole words)
                     sub = re.sub(r'\b(%s)\b' % '|'.join(map(re.escape, params)),
                                  lambda r: actuals[params.index(r.group(1))], sub)
+                    sub = re.sub(r'\s*##\s*', '', sub.replace('/**/', ''))        # token pasting (both cpp dialects)
                     line = line[:m.start()] + sub + line[close + 1:]
                 changed = True
                 break
@@ -477,7 +491,7 @@ def _results(outputs):
     return 'return dict(%s)' % ', '.join('%s=%s' % (_py(o), _py(o)) for o in outputs if o not in ERROR_ARGS)
 
 
-def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=None):
+def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=None, integers=None):
     """translate a list of executable statements; returns python source lines"""
     py, depth = [], indent
     sigs = sigs or {}
@@ -601,7 +615,7 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
                 assert kw == 'if', stmt
                 emit('if %s:' % cond)
                 depth += 1
-                py.extend(statements([rest], depth, outputs, sigs, arrays))
+                py.extend(statements([rest], depth, outputs, sigs, arrays, None, integers))
                 depth -= 1
             continue
         m = re.fullmatch(r'do\s+(\w+)\s*=\s*(.+)', stmt, re.I)
@@ -647,7 +661,10 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
         if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall')):
             # first '=' that is not part of ==, /=, <=, >=
             k = re.search(r'(?<![=/<>])=(?!=)', stmt).start()
-            emit(_lhs(stmt[:k], arrays) % expr(stmt[k + 1:]))
+            value = expr(stmt[k + 1:])
+            if integers is not None and re.match(r'\s*(\w+)', stmt[:k]).group(1) in integers:
+                value = 'int(%s)' % value                 # assignment to an integer variable converts (truncates)
+            emit(_lhs(stmt[:k], arrays) % value)
             continue
         raise NotImplementedError(stmt)
     return py
@@ -660,12 +677,14 @@ def _signature(lines, k):
     kind, name, args = m.group(1).lower(), m.group(2), [a.strip() for a in m.group(3).split(',') if a.strip()]
     end = next(j for j in range(k + 1, len(lines)) if re.match(r'end\s*(subroutine|function)', lines[j], re.I))
     body = lines[k + 1:end]
-    outs, pure_out, objects, local_arrays, optional = [], set(), [], [], set()
+    outs, pure_out, objects, local_arrays, optional, integers = [], set(), [], [], set(), set()
     for decl in body:
         if '::' not in decl or not re.match(r'(type\s*\(|integer|real|logical|character)', decl.lower()):
             continue
         names = [v.strip() for v in _split_top(decl.split('::', 1)[1], ',')]
         bare = [re.match(r'\w+', n).group(0) for n in names]
+        if decl.lower().startswith('integer'):
+            integers.update(bare)
         if re.search(r'\boptional\b', decl.split('::')[0], re.I):
             optional.update(bare)
         m2 = re.search(r'intent\s*\(\s*(out|inout)\s*\)', decl, re.I)
@@ -681,7 +700,7 @@ def _signature(lines, k):
                 deferred = all(d.strip() == ':' for d in _split_top(dims.group(1), ','))
                 local_arrays.append((b, None if deferred else dims.group(1)))   # locals / array results are created here
     return dict(kind=kind, name=name, args=args, end=end, body=body, outs=outs, pure_out=pure_out, objects=objects,
-                local_arrays=local_arrays, optional=optional)
+                local_arrays=local_arrays, optional=optional, integers=integers)
 
 
 def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
@@ -721,7 +740,7 @@ def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
         locals_only = [b for b, _ in sig['local_arrays']]
         try:
             src += statements(sig['body'], 1, sig['outs'] if sig['kind'] == 'subroutine' else (), sigs, arrays,
-                              dict(sig['local_arrays']))
+                              dict(sig['local_arrays']), sig['integers'])
             src.append('    return %s' % name if sig['kind'] == 'function' else '    ' + _results(sig['outs']))
             compile('\n'.join(src), name, 'exec')
             sources[name] = '\n'.join(src)

@@ -307,7 +307,7 @@ def test_simple_spline_init_and_evaluation(cu_setfl):
     funcs = units(open('/root/reference/src/support/simple_spline.f90').read())
     init, fdf = funcs['simple_spline_init'], funcs['simple_spline_f_and_df']
     assert callable(init) and callable(fdf), (init, fdf)
-
+    t = cu_setfl
     rng = np.random.RandomState(2)
     pad = np.zeros(2)          # tabulated_alloy_eam.f90 pads the r tables with two zeros (simple_spline_read)
     for name, y, x0, dx in (('F', t['F'][0], 0.0, t['dF']), ('rho', np.concatenate([t['rho'][0], pad]), 0.0, t['dr']),
@@ -1135,3 +1135,56 @@ def test_pair_styles_executed(case):
             assert np.abs(np.asarray(list(epa)) - o['epot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['epot_per_at']).max())
             got = np.asarray(list(wpa)).reshape(nat, 3, 3).transpose(0, 2, 1)
             assert np.abs(got - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())
+
+
+# ---- TabulatedEAM (funcfl): tabulated_eam.f90:334-511 with the inlined spline macros of src/spline.inc ----------
+
+def test_funcfl_eam_kernel_executed():
+    """the single-element funcfl kernel (effective-charge pair term Z(r)**2 / r, array-valued spline evaluation
+    through the SPLINE_* macros of spline.inc) on rattled fcc Au with the reference's Au_u3.eam tables"""
+    from fortran_subset import FA, load_macros
+    from atomistica_b200 import structures as S_
+    from conftest import load_npz
+    t = load_npz('au_u3_funcfl.npz')
+    macros = _reference_macros({'PYTHON'})
+    macros.update(load_macros(open('/root/reference/src/spline.inc').read(), {'PYTHON'}))
+    spl = units(open('/root/reference/src/support/simple_spline.f90').read())
+    nr, dr, nF, dF = int(t['nr']), float(t['dr']), int(t['nF']), float(t['dF'])
+    fF = spl['simple_spline_init'](nF, 0.0, dF, FA(nF, data=t['F'].tolist()))['this']
+    fZ = spl['simple_spline_init'](nr, 0.0, dr, FA(nr, data=t['Z'].tolist()))['this']
+    frho = spl['simple_spline_init'](nr, 0.0, dr, FA(nr, data=t['rho'].tolist()))['this']
+    spl['simple_spline_scale_y_axis'](fZ, float(np.sqrt(0.5 * oracle.HARTREE * oracle.BOHR)))   # tabulated_eam.f90:199
+    cutoff = float(t['cutoff'])
+    this = Obj(els=2, cutoff=cutoff, fF=fF, fZ=fZ, frho=frho)
+    a = S_.fcc('Au', 4.08, (2, 2, 2)); a.rattle(0.1, seed=71)
+    nat = len(a)
+    p, fnl, nl = _particles_and_list(a, cutoff)
+    tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+    kern = units(open('/root/reference/src/potentials/eam/tabulated_eam.f90').read(), defined={'PYTHON'},
+                 env=dict(tls_init=tls_init, tls_reduce=tls_reduce, **tls), macros=macros,
+                 global_arrays=('tls_sca1', 'tls_vec1'))['tabulated_eam_energy_and_forces_kernel']
+    assert callable(kern), kern
+    assert 'Z_spl_y(spl_arr_i(' in kern.python_source.replace(' ', '')            # the inlined array splines
+    maxneb = int(max(nl.last[i] - nl.seed[i] + 1 for i in range(nat)))
+    f, epa = FA(3, nat), FA(nat)
+    r = kern(this, p, fnl, 0.0, f, FA(3, 3), maxneb, epa)
+    o = oracle.EAMFuncfl(t).energy_and_forces(a.positions, a.cell, nl, a.symbols, per_at=True)
+    assert abs(o['epot']) > 10.0 and np.abs(o['f']).max() > 0.1
+    assert abs(r['epot'] - o['epot']) <= 1e-12 * abs(o['epot'])
+    assert np.abs(np.asarray(list(f)).reshape(nat, 3) - o['f']).max() <= 1e-12 * max(1.0, np.abs(o['f']).max())
+    w = np.asarray(list(r['wpot'])).reshape(3, 3).T
+    assert np.abs(w - o['wpot']).max() <= 1e-11 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    assert np.abs(np.asarray(list(epa)) - o['epot_per_at']).max() <= 1e-12 * np.abs(o['epot_per_at']).max()

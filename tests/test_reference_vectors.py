@@ -122,3 +122,96 @@ def test_the_checkers_the_gpu_test_uses():
     nb = np.array(nl.neighbors).copy(); nb[3], nb[4] = nb[4], nb[3]
     with pytest.raises(AssertionError):
         RV.check_list(nl.seed, nl.last, nb, nl.dc, gl, len(a))
+
+
+def test_gpu_file_dry_run_with_the_oracle_as_the_device(monkeypatch):
+    """tests/test_zz_gpu_reference_vectors.py end to end without a GPU: the device-side helpers (_both of the per-family
+    GPU test modules, native.from_atoms / Neighbors) are replaced by the oracle, so every case's routing, argument
+    passing and unpacking is exercised here; on the GPU box the same functions run against the CUDA kernels"""
+    import test_gpu_bop, test_gpu_bop_scr, test_gpu_eam, test_gpu_juslin, test_gpu_rebo2, test_gpu_rebo2_scr
+    import test_zz_gpu_reference_vectors as Z
+    from atomistica_b200 import native
+
+    def as_g(o):
+        return (o['epot'], o['f'], o['wpot'], o['epot_per_at'], None, None, o['wpot_per_at'], None)
+
+    def bop(kind, db, a, mask=None, per_bond=False, avgn=100):
+        db = P.complete(kind, db)
+        okind = dict(Tersoff=oracle.TERSOFF, Kumagai=oracle.KUMAGAI, Brenner=oracle.BRENNER)[kind]
+        idx = [db['el'].index(s) for s in set(a.symbols) if s in db['el']]
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, max(db['r2'][P.pair_index(i, j, len(db['el']))] for i in idx for j in idx), avgn)
+        el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
+        o = oracle.bop_energy_and_forces(oracle.bop_params(okind, db), a.positions, a.cell, nl, el, mask=mask, per_at=True)
+        return as_g(o), o, nl
+
+    def bop_scr(kind, db, a, mask=None, per_bond=False, avgn=1000):
+        db = P.complete_scr(kind, db)
+        okind = dict(Tersoff=oracle.TERSOFF, Kumagai=oracle.KUMAGAI, Brenner=oracle.BRENNER)[kind]
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, P.scr_cutoff(db), avgn)
+        el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
+        o = oracle.bop_energy_and_forces(oracle.bop_params(okind, db), a.positions, a.cell, nl, el, mask=mask, per_at=True,
+                                         scr=oracle.bop_scr_params(db))
+        return as_g(o), o
+
+    def eam(a, setfl, mask=None, per_at=True):
+        e = oracle.EAM(setfl)
+        nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, e.cutoff, 200)
+        o = e.energy_and_forces(a.positions, a.cell, nl, e.eldb(a.symbols), mask=mask, per_at=True)
+        return (o['epot'], o['f'], o['wpot'], o['epot_per_at'], o['wpot_per_at']), o
+
+    def rebo2(cls):
+        def both(a, per_bond=False, **kw):
+            if 'dihedral' in kw:
+                kw['with_dihedral'] = kw.pop('dihedral')
+            rb = cls(**kw)
+            nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, rb.cutoff(a.symbols), 1000)
+            o = rb.energy_and_forces(a.positions, a.cell, nl, rb.ktyp(a.symbols), per_at=True)
+            return as_g(o), o
+        return both
+
+    def juslin(screened):
+        def both(db, a, mask=None, per_bond=False):
+            db = (P.complete_juslin_scr if screened else P.complete_juslin)(db)
+            cutoff = P.juslin_scr_cutoff(db) if screened else max(db['r2'])
+            nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 1000)
+            el = np.array([db['el'].index(s) + 1 for s in a.symbols], dtype=np.int32)
+            o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.JUSLIN, db), a.positions, a.cell, nl, el, mask=mask,
+                                             per_at=True, scr=oracle.bop_scr_params(db) if screened else None)
+            return as_g(o), o
+        return both
+
+    class FakeNeighbors:
+        def __init__(self, avgn):
+            self.avgn = avgn
+
+        def request_interaction_range(self, cutoff):
+            self.cutoff = cutoff
+
+        def to_host(self, a):
+            nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, self.cutoff, self.avgn)
+            return nl.seed, nl.last, nl.neighbors, nl.dc
+
+    monkeypatch.setattr(test_gpu_bop, '_both', bop)
+    monkeypatch.setattr(test_gpu_bop_scr, '_both', bop_scr)
+    monkeypatch.setattr(test_gpu_eam, '_both', eam)
+    monkeypatch.setattr(test_gpu_rebo2, '_both', rebo2(oracle.Rebo2))
+    monkeypatch.setattr(test_gpu_rebo2_scr, '_both', rebo2(oracle.Rebo2Scr))
+    monkeypatch.setattr(test_gpu_juslin, '_both', juslin(False))
+    monkeypatch.setattr(test_gpu_juslin, '_both_scr', juslin(True))
+    monkeypatch.setattr(native, 'from_atoms', lambda a: a)
+    monkeypatch.setattr(native, 'Neighbors', FakeNeighbors)
+    n = 0
+    for c in RV.cases():
+        fam = c[1]
+        if fam == 'nl':
+            Z.test_neighbor_lists(c[0])
+        elif fam == 'eam':
+            Z.test_eam(c[0])
+        elif fam == 'bop':
+            Z.test_bond_order_potentials(c)
+        elif fam == 'rebo2':
+            Z.test_rebo2(c)
+        else:
+            Z.test_juslin(c)
+        n += 1
+    assert n == 33

@@ -662,6 +662,11 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
             # first '=' that is not part of ==, /=, <=, >=
             k = re.search(r'(?<![=/<>])=(?!=)', stmt).start()
             value = expr(stmt[k + 1:])
+            if integers is not None:
+                # integer / integer is an integer division in Fortran and a true division in Python: none may occur
+                for a, b in re.findall(r'(?<![\w.%)*])(?<!\*\s)(\w+)\s*/\s*(\w+)(?![\w.(%])', stmt[k + 1:]):
+                    if (a in integers or a.isdigit()) and (b in integers or b.isdigit()):
+                        raise NotImplementedError('integer division: ' + stmt)
             if integers is not None and re.match(r'\s*(\w+)', stmt[:k]).group(1) in integers:
                 value = 'int(%s)' % value                 # assignment to an integer variable converts (truncates)
             emit(_lhs(stmt[:k], arrays) % value)

@@ -1,16 +1,29 @@
-"""A translator from the small Fortran subset the reference's *_func.f90 / *_db.f90 files are written in to
-Python, so that tests can EXECUTE the reference's own formulas (no Fortran compiler exists in this image) next to
-the oracle's restatement of them.  Test infrastructure only; reads the sources where they lie under
-/root/reference.
+"""A translator from the Fortran subset the reference's kernels are written in to Python, so that tests can EXECUTE
+the reference's own source (no Fortran compiler exists in this image) next to the oracle's restatement of it.  Test
+infrastructure only; it reads the sources where they lie under /root/reference and copies nothing.
 
-Subset: [elemental|pure] subroutine / function units; scalar and explicit-shape array declarations; assignments
-to scalars, elements, sections and whole arrays; IF blocks and one-line IFs; DO loops (optional stride); CALL of
-other translated units or of Python callables supplied by the test; RAISE_ERROR / INIT_ERROR / PASS_ERROR;
-RETURN; component access through %; array constructors; kind suffixes (a real literal without one is single
-precision, as the compiler reads it); .and./.or./.not.; the intrinsics below.  Arrays are column-major objects
-with arbitrary lower bounds that are read with Fortran's parentheses (FA is callable), so an expression needs no
-distinction between a function reference and an array element.  Anything outside the subset raises
-NotImplementedError at translation time -- nothing is skipped silently."""
+Subset
+  units        [elemental|pure|recursive] subroutine / function; intent(out) dummies become results (a subroutine
+               returns the dict of its out / inout arguments), optional dummies default to None, present()
+  data         scalars; explicit-shape arrays with arbitrary lower bounds, sections, vector subscripts, whole-array
+               and masked (WHERE) assignment, element-wise arithmetic and comparisons (class FA, column-major);
+               allocatable components / locals through ALLOCATE / DEALLOCATE / allocated(); derived types as plain
+               objects with % components; array constructors; named constants and initialised declarations
+  statements   assignment (to an integer variable: truncating conversion), IF blocks and one-line IFs, DO (stride),
+               DO WHILE, FORALL (with mask), construct names, CALL with positional / keyword / optional arguments
+               of other translated units or of Python callables supplied by the test, RETURN, RAISE_ERROR (an
+               exception); INIT_ERROR / PASS_ERROR / write / print are dropped; calls named as no-ops by the test
+  cpp          #ifdef / #ifndef / #if defined() with || && ! / #else / #endif; object- and function-like macros
+               (macros.inc, filter.inc, spline.inc and the #defines of the kernel files) with token pasting,
+               multi-statement bodies (;)
+  semantics    IEEE doubles, no contraction; a real literal without kind suffix is default real (single precision,
+               promoted); an intent(out) dummy the callee never assigns leaves the actual argument as it was; a
+               declared real local starts as NaN so that a use before definition shows up in the results;
+               integer / integer in an assignment is refused (it would be an integer division)
+  intrinsics   exp sqrt cos sin log acos abs max min int floor real mod-free; dot_product matmul sum (also along a
+               dimension) maxval any all shape size lbound ubound spread cross_product iand ishft; PAIR_INDEX macros
+Anything outside the subset raises NotImplementedError when the unit is translated (the unit is then recorded as that
+exception, and the test that needs it fails) -- nothing is skipped silently."""
 import math
 import re
 import struct

@@ -1188,3 +1188,104 @@ def test_funcfl_eam_kernel_executed():
     w = np.asarray(list(r['wpot'])).reshape(3, 3).T
     assert np.abs(w - o['wpot']).max() <= 1e-11 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
     assert np.abs(np.asarray(list(epa)) - o['epot_per_at']).max() <= 1e-12 * np.abs(o['epot_per_at']).max()
+
+
+# ---- the LAMMPS build of the same kernels: ghosts instead of dc, Voigt-6 per-atom virial with the minus sign ------
+
+def _unfold(a, width):
+    """owned atoms followed by their periodic images within `width` of the cell (orthorhombic), LAMMPS style"""
+    L = np.diag(np.asarray(a.cell, float))
+    pos, img = [np.asarray(a.positions, float)], [np.arange(len(a))]
+    reach = [range(-int(np.ceil(width / L[k])), int(np.ceil(width / L[k])) + 1) for k in range(3)]
+    for i in reach[0]:
+        for j in reach[1]:
+            for k in reach[2]:
+                if (i, j, k) != (0, 0, 0):
+                    p = a.positions + np.array([i, j, k]) * L
+                    m = np.all((p > -width) & (p < L + width), axis=1)
+                    pos.append(p[m]); img.append(np.nonzero(m)[0])
+    return np.concatenate(pos), np.concatenate(img)
+
+
+def test_lammps_build_of_the_tersoff_kernel():
+    """bop_kernel.f90 compiled as LAMMPS compiles it (-DLAMMPS: no dc array, 0-based neighbour indices, forces and
+    per-atom quantities ACCUMULATED INTO GHOSTS, per-atom virial as Voigt-6 with the minus sign of macros.inc:202),
+    executed on an unfolded system: folding the ghost rows onto their owners -- what LAMMPS' reverse communication
+    does, and what the LAMMPS flavour of this library returns directly -- gives the periodic
+    result of the oracle"""
+    from fortran_subset import FA, load_macros
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('Si', 5.432, (2, 2, 2)); a.rattle(0.1, seed=81)
+    db = P.complete('Tersoff', None)
+    cutoff = max(db['r2'])
+    pos, img = _unfold(a, 2 * cutoff)
+    nloc, nall = len(a), len(pos)
+    assert nall > 3 * nloc
+    neigh, seed, last = [], [], []
+    for i in range(nloc):                                  # full list of the owned atoms, 0-based indices (LAMMPS)
+        d2 = ((pos - pos[i]) ** 2).sum(axis=1)
+        nb = [int(j) for j in np.nonzero(d2 < cutoff * cutoff)[0] if j != i]
+        seed.append(len(neigh) + 1); neigh += nb; last.append(len(neigh))
+    seed += [len(neigh) + 1] * (nall - nloc + 1); last += [len(neigh)] * (nall - nloc + 1)
+    defined = {'LAMMPS'}
+    src = open(BOP + '/bop_kernel.f90').read()
+    macros = _reference_macros(defined)
+    macros.update(load_macros(src, defined))
+    macros.update({'BOP_KERNEL': (None, 'tersoff_kernel'), 'BOP_TYPE': (None, 'tersoff_t'), 'BOP_NAME_STR': (None, '"tersoff"')})
+    assert macros['SUM_VIRIAL'][1].startswith('a(1, i) = a(1, i) - b(1, 1)')
+    cut = units(open('/root/reference/src/support/cutoff.f90').read())
+    funcs = units(open(BOP + '/tersoff/tersoff_func.f90').read(), defined=defined)
+    fcin = units(open(BOP + '/default_cutoff.f90').read(), defined=defined, env=dict(fc=cut['trig_off_f']))['fCin']
+    npairs = 3
+    this = Obj(db=_db(db), it=0, neighbor_list_allocated=False, **{k: None for k in BOP_BUFFERS})
+    this.cut_in = FA(npairs, data=[None] * npairs)
+    for k in ('cut_in_l', 'cut_in_h', 'cut_in_h2'):
+        setattr(this, k, FA(npairs))
+    bind = open(BOP + '/default_bind_to_func.f90').read()
+    for i in range(1, npairs + 1):
+        run_fragment(bind, r'call init\(this%cut_in\(i\)', r'this%cut_in_h2\(i\)\s*=', dict(this=this, i=i, init=cut['trig_off_init']),
+                     defined=defined)
+    tls = dict(tls_sca1=FA(nall), tls_vec1=FA(3, nall))
+
+    def tls_init(n, sca=None, vec=None, mat=None):
+        tls['tls_sca1'].assign(0.0); tls['tls_vec1'].assign(0.0)
+        return {}
+    tls_init.fortran_args = (('n', 'sca', 'vec', 'mat', 'ierror'), ())
+
+    def tls_reduce(n, sca1=None, vec1=None, mat1=None, mat2=None):
+        if sca1 is not None:
+            sca1.assign(sca1 + tls['tls_sca1'])
+        if vec1 is not None:
+            vec1.assign(vec1 + tls['tls_vec1'])
+        return {}
+    tls_reduce.fortran_args = (('n', 'sca1', 'vec1', 'mat1', 'mat2'), ())
+    env = dict(VA=funcs['VA'], VR=funcs['VR'], g=funcs['g'], bo=funcs['bo'], h=funcs['h'], Z2pair=funcs['Z2pair'], fCin=fcin,
+               tls_init=tls_init, tls_reduce=tls_reduce, **tls)
+    kern = units(src, defined=defined, env=env, macros=macros, global_arrays=('tls_sca1', 'tls_vec1'),
+                 noops=('prlog', 'log_memory_start', 'log_memory_stop', 'log_memory_estimate'))['tersoff_kernel']
+    assert callable(kern), kern
+    assert 'bptr(jn)+1' in kern.python_source.replace(' ', '') and 'matmul(cell' not in kern.python_source
+    d = [last[i] - seed[i] + 1 for i in range(nloc)]
+    nebmax, nebavg = max(d), (sum(d) + 1) // max(nall, 1) + 1 + 4
+    ptrmax = len(neigh)
+    f, epa, wpa = FA(3, nall, data=[0.25] * (3 * nall)), FA(nall), FA(6, nall)       # LAMMPS' force array is live: += semantics
+    r = kern(this, nall, nloc, nall, FA(3, nall, data=pos.ravel().tolist()), F1([1] * nall), nebmax, nebavg, F1(seed), F1(last),
+             F1(neigh), ptrmax, 0.0, f, FA(3, 3), None, epa, None, None, wpa, None)
+    # the periodic answer
+    onl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 100)
+    o = oracle.bop_energy_and_forces(oracle.bop_params(oracle.TERSOFF, db), a.positions, a.cell, onl,
+                                     np.ones(nloc, np.int32), per_at=True)
+    assert abs(r['epot'] - o['epot']) <= 1e-12 * abs(o['epot'])
+    fall = np.asarray(list(f)).reshape(nall, 3) - 0.25
+    assert np.abs(fall[nloc:]).max() > 0.1                      # the reference really leaves force on the ghosts
+    folded = np.zeros((nloc, 3)); np.add.at(folded, img, fall)
+    assert np.abs(folded - o['f']).max() <= 1e-12 * max(1.0, np.abs(o['f']).max())
+    e_fold = np.zeros(nloc); np.add.at(e_fold, img, np.asarray(list(epa)))
+    assert np.abs(e_fold - o['epot_per_at']).max() <= 1e-12 * np.abs(o['epot_per_at']).max()
+    v = np.asarray(list(wpa)).reshape(nall, 6)
+    v_fold = np.zeros((nloc, 6)); np.add.at(v_fold, img, v)
+    w = o['wpot_per_at']
+    want = -np.stack([w[:, 0, 0], w[:, 1, 1], w[:, 2, 2], w[:, 1, 0], w[:, 2, 0], w[:, 2, 1]], axis=1)
+    assert np.abs(v_fold - want).max() <= 1e-11 * max(1.0, np.abs(want).max(), abs(o['epot']))
+    wtot = np.asarray(list(r['wpot_inout'])).reshape(3, 3).T
+    assert np.abs(wtot - o['wpot']).max() <= 1e-11 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))

@@ -419,11 +419,11 @@ def _reference_macros(defined):
     return m
 
 
-def _particles_and_list(a, cutoff):
+def _particles_and_list(a, cutoff, avgn=200):
     """particles_t / neighbors_t images (python_particles.f90, python_neighbors.f90) from the oracle's list"""
     from fortran_subset import FA
     nat = len(a)
-    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, 200)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, avgn)
     p = Obj(nat=nat, natloc=nat, r_non_cyc=FA(3, nat, data=np.asarray(a.positions, float).ravel().tolist()),
             Abox=FA(3, 3, data=oracle.abox_from_cell(a.cell).ravel().tolist()),      # column-major 3x3, as passed to C
             el=F1([1] * nat))
@@ -433,8 +433,9 @@ def _particles_and_list(a, cutoff):
     return p, fnl, nl
 
 
-def run_eam_kernel_cases(t):
-    """the reference's EAM kernel on rattled fcc Cu, without and with a mask: yields (outputs, atoms, mask)"""
+def run_eam_kernel_cases(t, scale=1.0):
+    """the reference's EAM kernel on rattled fcc Cu (lattice constant scaled by `scale`), without and with a mask:
+    yields (outputs, atoms, mask)"""
     from fortran_subset import FA
     from atomistica_b200 import structures as S_
     macros = _reference_macros({'PYTHON'})
@@ -452,10 +453,10 @@ def run_eam_kernel_cases(t):
     cutoff = float(t['cutoff'])
     this = Obj(els=2, cutoff=cutoff, el2db=F1([1]), fF=F1([fF]), frho=F1([frho]), fphi=FA(1, 1, data=[fphi]))
 
-    a = S_.fcc('Cu', 3.615, (2, 2, 2))
-    a.rattle(0.08, seed=3)
+    a = S_.fcc('Cu', 3.615 * scale, (2, 2, 2))
+    a.rattle(0.08 * scale, seed=3)
     nat = len(a)
-    p, fnl, nl = _particles_and_list(a, cutoff)
+    p, fnl, nl = _particles_and_list(a, cutoff, avgn=400 if scale < 1.0 else 200)
     tls = dict(tls_sca1=FA(nat), tls_vec1=FA(3, nat))
 
     def tls_init(n, sca=None, vec=None, mat=None):
@@ -481,7 +482,7 @@ def run_eam_kernel_cases(t):
     rng = np.random.RandomState(8)
     for mask in (None, (rng.rand(nat) > 0.4).astype(np.int32)):
         f, epa, wpa = FA(3, nat), FA(nat), FA(3, 3, nat)
-        r = kern(this, p, fnl, 0.0, f, FA(3, 3), 200, None if mask is None else F1([int(m) for m in mask]), epa, wpa)
+        r = kern(this, p, fnl, 0.0, f, FA(3, 3), 400, None if mask is None else F1([int(m) for m in mask]), epa, wpa)
         yield dict(epot=r['epot'], f=np.asarray(list(f)).reshape(nat, 3),
                    wpot=np.asarray(list(r['wpot'])).reshape(3, 3).T,                   # column-major (3,3) -> [a][b]
                    epot_per_at=np.asarray(list(epa)),
@@ -1289,3 +1290,57 @@ def test_lammps_build_of_the_tersoff_kernel():
     assert np.abs(v_fold - want).max() <= 1e-11 * max(1.0, np.abs(want).max(), abs(o['epot']))
     wtot = np.asarray(list(r['wpot_inout'])).reshape(3, 3).T
     assert np.abs(wtot - o['wpot']).max() <= 1e-11 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+
+
+# ---- edge cases, each through the executed reference ---------------------------------------------------------------
+
+def test_bop_kernel_with_an_element_the_database_lacks():
+    """atoms whose element is not in the parameter set (el = -1: default_compute_func.f90:62-66) take no part --
+    bop_kernel.f90's eli > 0 / elj > 0 tests"""
+    from atomistica_b200 import structures as S_
+    a = S_.b3(['Si', 'C'], 4.36, (2, 2, 2)); a.rattle(0.1, seed=91)
+    for i in (1, 8, 30):
+        a.symbols[i] = 'H'
+    out, o, _ = _run_bop_kernel('Tersoff', P.Tersoff_PRB_39_5566_Si_C, a)
+    assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-12 * max(1.0, np.abs(o['f']).max())
+    assert np.all(out['f'][[1, 8, 30]] == 0.0) and np.all(o['f'][[1, 8, 30]] == 0.0)
+    assert np.abs(out['epot_per_at'] - o['epot_per_at']).max() <= 1e-13 * np.abs(o['epot_per_at']).max()
+
+
+def test_rebo2_kernel_overcoordinated_and_hydrogen_rich():
+    """compressed carbon (neighbour counts above 4 are clamped before the table look-ups, bop_kernel_rebo2.f90:1367-1373)
+    and a hydrogen-rich solid (H-H and C-H bonds, the hydrogen g polynomials, P_CH)"""
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('C', 3.57, (2, 2, 1)); a.rattle(0.15, seed=92)
+    a.cell = np.asarray(a.cell) * 0.86; a.positions *= 0.86
+    out, o, _ = _run_rebo2_kernel(a, True)
+    nn = [int(np.sum(np.linalg.norm(a.positions - a.positions[i], axis=1) < 1.7)) - 1 for i in range(len(a))]
+    assert max(nn) >= 4 and abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-11 * max(1.0, np.abs(o['f']).max())
+    assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-11 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    a = S_.diamond('C', 3.3, (2, 2, 1))
+    rng = np.random.RandomState(93)
+    for i in rng.choice(len(a), 2 * len(a) // 3, replace=False):
+        a.symbols[i] = 'H'
+    a.rattle(0.15, seed=94)
+    out, o, _ = _run_rebo2_kernel(a, True)
+    assert abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-11 * max(1.0, np.abs(o['f']).max())
+    assert np.abs(out['epot_per_bond'] - o['epot_per_bond']).max() <= 1e-11 * max(1.0, np.abs(o['epot_per_bond']).max())
+
+
+def test_eam_kernel_compressed_beyond_the_density_table():
+    """tests/test_eam_special_cases.py of the reference: a strongly compressed cell drives the density beyond the last
+    knot of F(rho); the kernel evaluates F with extrapolate=.true. (tabulated_alloy_eam.f90:549-556)"""
+    from fortran_subset import FA
+    from conftest import load_npz
+    t = load_npz('cu_mishin1_setfl.npz')
+    gen = run_eam_kernel_cases(t, scale=0.74)
+    out, a, mask = next(gen)
+    orc = oracle.EAM(t)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, orc.cutoff, 400)
+    o = orc.energy_and_forces(a.positions, a.cell, nl, orc.eldb(a.symbols), per_at=True)
+    assert abs(o['epot']) > 1e3                            # the cubic continuation of F beyond its last knot dominates
+    assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-13 * max(1.0, np.abs(o['f']).max())

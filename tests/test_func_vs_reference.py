@@ -1344,3 +1344,20 @@ def test_eam_kernel_compressed_beyond_the_density_table():
     assert abs(o['epot']) > 1e3                            # the cubic continuation of F beyond its last knot dominates
     assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
     assert np.abs(out['f'] - o['f']).max() <= 1e-13 * max(1.0, np.abs(o['f']).max())
+
+
+def test_neighbor_list_overflow_threshold():
+    """"Neighbor list overflow" (python_neighbors.f90:716-718) is raised at the same list capacity as in the oracle
+    (capacity nat * avgn; 1762 slots are needed here)"""
+    name, a, cutoff = list(_list_cases())[1]
+    for avgn, want in ((55, 'overflow'), (56, 'ok')):
+        got = []
+        for build in (lambda: _reference_neighbor_list(a, cutoff, avgn),
+                      lambda: oracle.neighbor_list(a.positions, a.cell, a.pbc, cutoff, avgn)):
+            try:
+                build()
+                got.append('ok')
+            except RuntimeError as e:
+                assert 'overflow' in str(e).lower()
+                got.append('overflow')
+        assert got == [want, want], (avgn, got)

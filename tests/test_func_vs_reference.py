@@ -433,7 +433,7 @@ def _particles_and_list(a, cutoff, avgn=200):
     return p, fnl, nl
 
 
-def run_eam_kernel_cases(t, scale=1.0):
+def run_eam_kernel_cases(t, scale=1.0, size=(2, 2, 2)):
     """the reference's EAM kernel on rattled fcc Cu (lattice constant scaled by `scale`), without and with a mask:
     yields (outputs, atoms, mask)"""
     from fortran_subset import FA
@@ -453,7 +453,7 @@ def run_eam_kernel_cases(t, scale=1.0):
     cutoff = float(t['cutoff'])
     this = Obj(els=2, cutoff=cutoff, el2db=F1([1]), fF=F1([fF]), frho=F1([frho]), fphi=FA(1, 1, data=[fphi]))
 
-    a = S_.fcc('Cu', 3.615 * scale, (2, 2, 2))
+    a = S_.fcc('Cu', 3.615 * scale, size)
     a.rattle(0.08 * scale, seed=3)
     nat = len(a)
     p, fnl, nl = _particles_and_list(a, cutoff, avgn=400 if scale < 1.0 else 200)
@@ -1361,3 +1361,40 @@ def test_neighbor_list_overflow_threshold():
                 assert 'overflow' in str(e).lower()
                 got.append('overflow')
         assert got == [want, want], (avgn, got)
+
+
+def test_eam_kernel_one_unit_cell():
+    """4 atoms in one fcc cell, cutoff 5.5 A > the cell edge: every atom sees its own images and every neighbour through
+    several shifts (the i == j entries of the list carry a non-zero dc)"""
+    from conftest import load_npz
+    t = load_npz('cu_mishin1_setfl.npz')
+    out, a, mask = next(run_eam_kernel_cases(t, size=(1, 1, 1)))
+    orc = oracle.EAM(t)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, orc.cutoff, 400)
+    i, j, dc, _ = oracle.pairs(nl, len(a))
+    assert np.any(i == j) and nl.npairs > 50 * len(a)
+    o = orc.energy_and_forces(a.positions, a.cell, nl, orc.eldb(a.symbols), per_at=True)
+    assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-12 * max(1.0, np.abs(o['f']).max())
+    assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    assert np.abs(out['wpot_per_at'] - o['wpot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_at']).max())
+
+
+def test_bop_kernel_same_neighbour_through_two_images():
+    """8 carbon atoms in one diamond cell with the C-C cutoff widened beyond half the cell edge: second neighbours enter
+    the bond list, the same atom k appears as neighbour of i through different cell shifts -- the (k, kdc) bookkeeping
+    of bop_kernel.f90 (DCELL_INDEX, "k /= j .or. kdc /= jdc")"""
+    from atomistica_b200 import structures as S_
+    a = S_.diamond('C', 3.57, (1, 1, 1)); a.rattle(0.06, seed=95)
+    db = {k: (list(v) if isinstance(v, (list, tuple)) else v) for k, v in P.Brenner_PRB_42_9458_C_II.items()}
+    db['r1'], db['r2'] = [2.35], [2.75]
+    out, o, _ = _run_bop_kernel('Brenner', db, a)
+    nl = oracle.neighbor_list(a.positions, a.cell, a.pbc, 2.75, 200)
+    i, j, dc, _ = oracle.pairs(nl, len(a))
+    keys = set(zip(i.tolist(), j.tolist()))
+    assert len(keys) < len(i)                              # some (i, j) occur with more than one shift
+    assert abs(out['epot'] - o['epot']) <= 1e-13 * abs(o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-12 * max(1.0, np.abs(o['f']).max())
+    assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    assert np.abs(out['epot_per_bond'] - o['epot_per_bond']).max() <= 1e-12 * max(1.0, np.abs(o['epot_per_bond']).max())
+    assert np.abs(out['wpot_per_bond'] - o['wpot_per_bond']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_bond']).max())

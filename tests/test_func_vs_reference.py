@@ -1398,3 +1398,23 @@ def test_bop_kernel_same_neighbour_through_two_images():
     assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-12 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
     assert np.abs(out['epot_per_bond'] - o['epot_per_bond']).max() <= 1e-12 * max(1.0, np.abs(o['epot_per_bond']).max())
     assert np.abs(out['wpot_per_bond'] - o['wpot_per_bond']).max() <= 1e-12 * max(1.0, np.abs(o['wpot_per_bond']).max())
+
+
+@pytest.mark.parametrize('name', ['C2H', 'propyne', 'CH2=C=CH2', 'cyclopentene', 'naphthalene', 't-C4H9'])
+@pytest.mark.parametrize('screened', [False, True])
+def test_rebo2_kernel_on_molecules(name, screened):
+    """hydrocarbons of Brenner 2002's Table 12 (radicals, triple and cumulated double bonds, an aromatic system: fractional
+    conjugation numbers in the F and T tables, the dihedral term around double bonds), in a box with vacuum"""
+    import json
+    from atomistica_b200 import structures as S_
+    m = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'molecules.json')))[name]
+    pos = np.array(m['positions'], dtype=float)
+    pos += np.random.RandomState(len(name)).normal(0.0, 0.03, pos.shape)      # off the symmetric geometry
+    pos -= pos.min(axis=0) - 3.0
+    a = S_.Atoms(m['symbols'], pos, pos.max(axis=0) + 3.0, True)
+    out, o, _ = _run_rebo2_kernel(a, True, screened=screened)
+    assert abs(o['epot']) > 3.0
+    assert abs(out['epot'] - o['epot']) <= 1e-12 * abs(o['epot']), (name, out['epot'], o['epot'])
+    assert np.abs(out['f'] - o['f']).max() <= 1e-11 * max(1.0, np.abs(o['f']).max())
+    assert np.abs(out['wpot'] - o['wpot']).max() <= 1e-11 * max(1.0, np.abs(o['wpot']).max(), abs(o['epot']))
+    assert np.abs(out['epot_per_at'] - o['epot_per_at']).max() <= 1e-12 * max(1.0, np.abs(o['epot_per_at']).max())

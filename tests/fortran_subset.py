@@ -242,6 +242,9 @@ INTRINSICS = dict(exp=math.exp, sqrt=math.sqrt, cos=math.cos, sin=math.sin, log=
                   dot_product=_dot_product, matmul=_matmul, spread=_spread, outer_product=_outer_product, sum=_sum,
                   iand=lambda a, b: a & b, ishft=lambda a, n: a << n if n >= 0 else a >> -n,
                   PI=_PI, pi=_PI, Obj=Obj, FA=FA, S=S, _set=_set, _sp=_sp, UNDEF=float('nan'),
+                  _new_type=lambda name: Obj(), c_loc=lambda x: x, c_associated=lambda x: x is not None, C_NULL_PTR=None,
+                  c_int=4, c_double=8, c_long_long=8, merge=lambda a, b, mask: a if mask else b,
+                  reshape=lambda a, shape: FA(*[int(n) for n in shape.data], data=list(a.data)),
                   _ac=lambda v: FA(len(v), data=v))
 
 PY_KEYWORDS = {'lambda': 'lambda_', 'for': 'for_', 'in': 'in_', 'is': 'is_', 'del': 'del_', 'pass': 'pass_'}
@@ -265,18 +268,22 @@ def _strip_comment(line):
     return line
 
 
-def _cpp_condition(raw, defined):
+def _cpp_condition(raw, defined, values=None):
     d = raw.split()
     if d[0] == '#ifdef':
         return d[1] in defined
     if d[0] == '#ifndef':
         return d[1] not in defined
-    cond = raw[len('#if'):].split('/*')[0]
+    cond = raw[len(d[0]):].split('/*')[0]
     cond = re.sub(r'defined\s*\(\s*(\w+)\s*\)', lambda m: str(m.group(1) in defined), cond)
-    cond = cond.replace('||', ' or ').replace('&&', ' and ').replace('!', ' not ')
-    if not re.fullmatch(r'[\s()\w]*', cond):
+    for name, value in (values or {}).items():            # object-like macros with a numeric value
+        cond = re.sub(r'\b%s\b' % name, str(value), cond)
+    cond = cond.replace('||', ' or ').replace('&&', ' and ')
+    cond = re.sub(r'!(?!=)', ' not ', cond)
+    cond = re.sub(r'\b(?!True\b|False\b|and\b|or\b|not\b)[A-Za-z_]\w*', '0', cond)     # an undefined identifier is 0
+    if not re.fullmatch(r'[\s()\w=!<>]*', cond):
         raise NotImplementedError(raw)
-    return bool(eval(cond, {'__builtins__': {}}, {}))      # True / False / 0 / 1 and boolean operators only
+    return bool(eval(cond, {'__builtins__': {}}, {}))      # constants, comparisons and boolean operators only
 
 
 MACRO_SKIP = {'outer_product', 'PAIR_INDEX', 'PAIR_INDEX_NS', 'TRIPLET_INDEX_NS'}    # provided as Python intrinsics
@@ -337,16 +344,22 @@ def expand_macros(line, macros):
 def preprocess(text, defined=(), macros=None):
     """cpp conditionals, comments, continuation lines, macro expansion (when `macros` is given), ';' -> list of
     statements"""
-    out, active = [], []
+    out, active, taken = [], [], []
+    values = {k: v[1] for k, v in (macros or {}).items() if v[0] is None and re.fullmatch(r'-?\d+', v[1])}
     for raw in text.splitlines():
         if raw.startswith('#'):
             d = raw.split()
             if d[0] in ('#ifdef', '#ifndef', '#if'):
-                active.append(_cpp_condition(raw, defined))
+                active.append(_cpp_condition(raw, defined, values))
+                taken.append(active[-1])
+            elif d[0] == '#elif':
+                active[-1] = (not taken[-1]) and _cpp_condition(raw, defined, values)
+                taken[-1] = taken[-1] or active[-1]
             elif d[0] == '#else':
-                active[-1] = not active[-1]
+                active[-1] = not taken[-1]
+                taken[-1] = True
             elif d[0] == '#endif':
-                active.pop()
+                active.pop(); taken.pop()
             elif d[0] in ('#include', '#define', '#undef'):
                 pass
             else:
@@ -366,13 +379,12 @@ def preprocess(text, defined=(), macros=None):
             continue
         joined.append(cur + body)
         cur = ''
-    if macros:
-        expanded = []
-        for line in joined:
+    expanded = []
+    for line in joined:
+        if macros:
             line = expand_macros(line, macros)
-            expanded += [part.strip() for part in _split_statements(line) if part.strip()]
-        joined = expanded
-    return joined
+        expanded += [part.strip() for part in _split_statements(line) if part.strip()]
+    return expanded
 
 
 def _split_statements(line):
@@ -457,6 +469,7 @@ def expr(e):
     # default-real literals first (they carry neither a kind suffix nor a D exponent)
     e = re.sub(r'(?<![\w.])((?:\d+\.\d*|\.\d+)(?:[eE][-+]?\d+)?|\d+[eE][-+]?\d+)(?![\w.])', r'_sp(\1)', e)
     e = re.sub(r'(\d)_DP\b', r'\1', e)
+    e = re.sub(r'(?<![\w.])(\d+)_[A-Za-z]\w*', r'\1', e)               # 0_c_int, 2048_c_int
     e = re.sub(r'(\d+\.?\d*|\.\d+)[dD]([-+]?\d+)', r'\1e\2', e)
     for a, b in (('.and.', ' and '), ('.or.', ' or '), ('.not.', ' not '), ('/=', '!='), ('.true.', 'True'),
                  ('.false.', 'False'), ('.le.', '<='), ('.ge.', '>='), ('.lt.', '<'), ('.gt.', '>'), ('.eq.', '=='),
@@ -571,6 +584,16 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
         if '::' in stmt and re.match(r'(type\s*\(|integer|real|logical|character)', low):
             # named constants and initialised scalars: "real(DP), parameter :: sig = 0.5"
             is_arg = re.search(r'\bintent\b', stmt.split('::')[0], re.I)
+            tm = re.match(r'type\s*\(\s*(\w+)\s*\)', stmt, re.I)
+            if tm and not is_arg and local_dims is not None:
+                for ent in _split_top(stmt.split('::', 1)[1], ','):      # a derived-type local: an instance of its own
+                    name = re.match(r'\s*(\w+)', ent).group(1)
+                    if name in local_dims and local_dims[name] is not None:      # an array of them
+                        emit(_create(name, local_dims[name]))
+                        emit("%s.data[:] = [_new_type('%s') for _ in %s.data]" % (name, tm.group(1), name))
+                    else:
+                        emit("%s = _new_type('%s')" % (name, tm.group(1)))
+                continue
             for ent in _split_top(stmt.split('::', 1)[1], ','):
                 name = re.match(r'\s*(\w+)', ent).group(1)
                 if local_dims and name in local_dims:       # local arrays come to life where they are declared
@@ -674,6 +697,19 @@ def statements(lines, indent=1, outputs=(), sigs=None, arrays=(), local_dims=Non
         if '=' in stmt and not low.startswith(('write', 'print', 'select', 'where', 'forall')):
             # first '=' that is not part of ==, /=, <=, >=
             k = re.search(r'(?<![=/<>])=(?!=)', stmt).start()
+            fm = re.fullmatch(r'\s*(\w+)\s*\((.*)\)\s*', stmt[k + 1:])
+            if fm and sigs.get(fm.group(1)) and sigs[fm.group(1)][2]:
+                # a function with intent(out) arguments (the C ABI seen from Fortran): results come back in a dict
+                name = fm.group(1)
+                dummies, pure_out, outs = sigs[name]
+                actuals = [a.strip() for a in _split_top(fm.group(2), ',')]
+                assert len(actuals) == len(dummies), stmt
+                emit('_r = %s(%s)' % (name, ', '.join(expr(a) for a, d in zip(actuals, dummies) if d not in pure_out)))
+                for a, d in zip(actuals, dummies):
+                    if d in outs:
+                        emit(_lhs(a, arrays) % ("_r['%s']" % _py(d)))
+                emit(_lhs(stmt[:k], arrays) % "_r['result']")
+                continue
             value = expr(stmt[k + 1:])
             if integers is not None:
                 # integer / integer is an integer division in Fortran and a true division in Python: none may occur
@@ -693,8 +729,19 @@ def _signature(lines, k):
     if not m:
         return None
     kind, name, args = m.group(1).lower(), m.group(2), [a.strip() for a in m.group(3).split(',') if a.strip()]
-    end = next(j for j in range(k + 1, len(lines)) if re.match(r'end\s*(subroutine|function)', lines[j], re.I))
-    body = lines[k + 1:end]
+    # the unit ends at its own END; internal procedures (after CONTAINS) nest
+    depth, end, contains = 0, None, None
+    for j in range(k + 1, len(lines)):
+        if re.match(r'(?:(?:elemental|pure|recursive)\s+)*(subroutine|function)\s+\w+\s*\(', lines[j], re.I):
+            depth += 1
+        elif re.match(r'end\s*(subroutine|function)', lines[j], re.I):
+            if depth == 0:
+                end = j
+                break
+            depth -= 1
+        elif lines[j].strip().lower() == 'contains' and depth == 0:
+            contains = j
+    body = lines[k + 1:contains if contains is not None else end]
     outs, pure_out, objects, local_arrays, optional, integers = [], set(), [], [], set(), set()
     for decl in body:
         if '::' not in decl or not re.match(r'(type\s*\(|integer|real|logical|character)', decl.lower()):
@@ -718,10 +765,10 @@ def _signature(lines, k):
                 deferred = all(d.strip() == ':' for d in _split_top(dims.group(1), ','))
                 local_arrays.append((b, None if deferred else dims.group(1)))   # locals / array results are created here
     return dict(kind=kind, name=name, args=args, end=end, body=body, outs=outs, pure_out=pure_out, objects=objects,
-                local_arrays=local_arrays, optional=optional, integers=integers)
+                local_arrays=local_arrays, optional=optional, integers=integers, contains=contains)
 
 
-def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
+def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=(), global_scalars=()):
     """{name: python callable} for every subroutine / function of a source text.  A subroutine returns the dict
     of its intent(out) / intent(inout) arguments, a function its result.  env: extra names (constants, Python
     callables; a callable that is CALLed needs .fortran_args = (dummy names, names of the intent(out) ones) and
@@ -736,6 +783,15 @@ def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
             k += 1
             continue
         found.append(sig)
+        if sig['contains'] is not None:          # internal procedures become units of their own (they use their arguments only)
+            j = sig['contains'] + 1
+            while j < sig['end']:
+                inner = _signature(lines, j)
+                if inner is None:
+                    j += 1
+                    continue
+                found.append(inner)
+                j = inner['end'] + 1
         k = sig['end'] + 1
     sigs = {}
     for name, fn in scope.items():
@@ -751,7 +807,8 @@ def units(text, defined=(), env=None, macros=None, global_arrays=(), noops=()):
         name = sig['name']
         pyargs = [PY_KEYWORDS.get(a, a) + ('=None' if a in sig['optional'] else '')
                   for a in sig['args'] if a not in sig['pure_out']]                       # intent(out): results only
-        src = ['def %s(%s):' % (name, ', '.join(pyargs))] + ['    %s = Obj()' % o for o in sig['objects']]
+        src = ['def %s(%s):' % (name, ', '.join(pyargs))] + ['    global %s' % g for g in global_scalars] + \
+            ['    %s = Obj()' % o for o in sig['objects']]
         arrays = [b for b, _ in sig['local_arrays']] + list(global_arrays)
         # an intent(out) scalar a branch never assigns is undefined in Fortran: None here
         src += ['    %s = None' % _py(o) for o in sig['pure_out'] if o not in sig['objects'] and o not in arrays]

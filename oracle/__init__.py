@@ -384,8 +384,9 @@ PAIR_LJCUT, PAIR_HARMONIC, PAIR_DOUBLE_HARMONIC, PAIR_BORN_MAYER, PAIR_R6 = 1, 2
 
 
 def element_ids(symbols):
-    """particle element ids like python_particles.f90: 1-based, in order of first appearance;
-    returns (ids per atom, list of symbols by id-1)"""
+    """compact 1-based particle element ids, here in order of first appearance (the reference numbers them by
+    ascending atomic number, python_particles.f90:617-658; the ids are internal -- filters and el2db maps are built
+    from the same numbering, so any consistent one gives the same energies); returns (ids per atom, symbols by id-1)"""
     order = []
     for s in symbols:
         if s not in order:
